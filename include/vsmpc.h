@@ -1,0 +1,174 @@
+/*
+ * vsmpc.h — C-ABI of the B200-native batched variable-sampling ("multi-rate") MPC.
+ *
+ * Drop-in boundary for ONE path of ami-iit/paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub:
+ *   VariableSamplingMPC::{configure, update, solveMPC, get*}
+ *   (src/flight-controller/momentum-based-linear-mpc-lib/include/variableSamplingMPC/variableSamplingMPC.h:15-41,
+ *    .../include/IMPCProblem/IMPCProblem.h:35-118), as bound to Python in
+ *   .../bindings/python/MPCPyBindings.cpp:22-90.
+ *
+ * A handle owns B independent MPC instances on one GPU.  All arrays crossing this boundary are
+ * plain FP64 / int32 buffers owned by the caller; nothing is retained past a call except the
+ * handle.  Every function returns 0 on success or a VSMPC_ERR_* code; vsmpc_last_error() gives
+ * the message (the reference returns `bool` and logs through yError()).
+ *
+ * Layout conventions
+ *   pack      : structure-of-arrays, double[VSMPC_PACK_DOUBLES][B]  (row = scalar, column = instance)
+ *   outputs   : one row per instance, double[B][VSMPC_OUT_DOUBLES]
+ *   solution  : one row per instance, double[B][n_var]   (reference variable order)
+ */
+#ifndef VSMPC_H
+#define VSMPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSMPC_NX 26        /* states:   VSconstant.h:9-16 */
+#define VSMPC_NJ 8         /* N_JOINTS: VSconstant.h:6    */
+#define VSMPC_NT 4         /* N_THRUSTS: VSconstant.h:7   */
+
+/* ---- per-tick input pack: what update(QPInput&) reads (row offsets) -------- */
+#define VSMPC_PK_WRB            0   /* 9  Robot::getBasePose().getRotation(), row-major          */
+#define VSMPC_PK_OMEGA_WORLD    9   /* 3  getBaseVel().getAngularVec3()                           */
+#define VSMPC_PK_RPY           12   /* 3  getRotation().asRPY()                                   */
+#define VSMPC_PK_MASS          15   /* 1  getTotalMass() (already float-rounded, Robot.h:338)     */
+#define VSMPC_PK_GRAVITY       16   /* 3  getGravity()                                            */
+#define VSMPC_PK_MB            19   /* 36 getMassMatrix().block(0,0,6,6), row-major               */
+#define VSMPC_PK_BASE_POS      55   /* 3  getBasePose().getPosition()                             */
+#define VSMPC_PK_P_COM         58   /* 3  getPositionCoM()                                        */
+#define VSMPC_PK_MOMENTUM_BODY 61   /* 6  getMomentum(true)                                       */
+#define VSMPC_PK_AMOM_BODY     67   /* 24 getMatrixAmomJets(true), 6x4 row-major                  */
+#define VSMPC_PK_JET_AXES      91   /* 12 getMatrixOfJetAxes()[i], world, 4x3                     */
+#define VSMPC_PK_JET_ARMS     103   /* 12 getMatrixOfJetArms()[i], world, 4x3                     */
+#define VSMPC_PK_J_REL_ANG    115   /* 96 getRelativeJacobianJetsBodyFrame()[i].bottomRows(3), controlled joints, 4x3x8 */
+#define VSMPC_PK_J_JET_LIN    211   /* 96 getJacobian(jet).topRightCorner(3,nJ), controlled joints, 4x3x8 */
+#define VSMPC_PK_J_COM        307   /* 24 getJacobianCoM().topRightCorner(3,nJ), controlled joints, 3x8   */
+#define VSMPC_PK_THRUST       331   /* 4  getJetThrusts()                                         */
+#define VSMPC_PK_THRUST_DOT_EST 335 /* 4  QPInput::getEstimatedThrustDot()                        */
+#define VSMPC_PK_THRUST_DES   339   /* 4  QPInput::getThrustDesMPC()                              */
+#define VSMPC_PK_THRUST_DOT_DES 343 /* 4  QPInput::getThrustDotDesMPC()                           */
+#define VSMPC_PK_THROTTLE_PREV 347  /* 4  QPInput::getThrottleMPC()  [percent]                    */
+#define VSMPC_PK_Q_CMD        351   /* 8  QPInput::getOutputQPJointsPosition()[controlled]        */
+#define VSMPC_PACK_DOUBLES    359
+
+/* ---- per-instance output row: the getters of variableSamplingMPC.cpp:88-227 ------------------ */
+#define VSMPC_OUT_DELTA_Q       0   /* 8  m_deltaJointsPositionReference                          */
+#define VSMPC_OUT_THROTTLE      8   /* 4  getThrottleReference()  [percent, clipped 0..100]       */
+#define VSMPC_OUT_THRUST       12   /* 4  getThrustReference()                                    */
+#define VSMPC_OUT_THRUST_DOT   16   /* 4  getThrustDotReference()                                 */
+#define VSMPC_OUT_FINAL_STATE  20   /* 26 m_finalState -> getFinalCoMPosition/LinMom/RPY/AngMom   */
+#define VSMPC_OUT_JOINTS_REF   46   /* 8  getJointsReferencePosition()[controlled] (accumulated)  */
+#define VSMPC_OUT_DOUBLES      54
+
+/* per-instance solver status; outputs of a non-solved instance are held (variableSamplingMPC.cpp:91) */
+#define VSMPC_STATUS_SOLVED     0
+#define VSMPC_STATUS_MAX_ITER   1   /* active-set iteration / working-set cap reached             */
+#define VSMPC_STATUS_NUMERICAL  2   /* non-finite data or non-positive pivot                      */
+
+#define VSMPC_OK                0
+#define VSMPC_ERR_ARG           1
+#define VSMPC_ERR_CUDA          2
+#define VSMPC_ERR_UNSUPPORTED   3
+#define VSMPC_ERR_STATE         4   /* call order violated (e.g. solve before configure)          */
+
+#define VSMPC_MAX_ITER        128   /* max nIter supported by one handle                          */
+
+typedef struct vsmpc_handle vsmpc_handle;
+
+/* Problem configuration = group VS_MPC_CONFIG of src/config/vs_mcp_config.xml:5-44 plus the two
+ * trajectory files it names (:34-40) as plain arrays (TrajectoryManager.cpp:67-140) and the jet
+ * model constants (UT/src/JetModel.cpp:13-26). */
+typedef struct vsmpc_config
+{
+    int n_iter;               /* nIter            */
+    int n_iter_small;         /* nIterSmall       */
+    int control_horizon;      /* controlHorizon   */
+    double period_mpc;        /* periodMPC        */
+    double period_large;      /* periodMPCLargeSteps */
+    double period_small;      /* periodMPCSmallSteps */
+    int use_jet_dynamic;      /* useJetDynamic    */
+    int use_estimated_thrust; /* useEstimatedThrust */
+    int joints_lambda_option; /* 0 = "unfiltered" (only option implemented), 1 = "constant" */
+    double weight_com_pos[3];
+    double weight_com_pos_error[3];
+    double weight_lin_mom[3];
+    double weight_rpy[3];
+    double weight_rpy_error[3];
+    double weight_ang_mom[3];
+    double weight_delta_joint[VSMPC_NJ];
+    double weight_throttle;
+    double weight_initial_throttle;
+    double weight_regularization_joint_pos;
+    double throttle_min;
+    double throttle_max;
+    double jet_coeff[13];     /* m_u2TCoeff          */
+    double jet_norm[4];       /* m_u2Tnormalization  */
+    /* TRAJECTORY_MANAGER: alphaGravity[alpha_len] at alpha_fps */
+    const double* alpha_gravity;
+    int alpha_len;
+    int alpha_fps;
+    /* POSITION_TRAJECTORY: 3 x traj_len each, sample-major (element [3*s + axis]), at traj_fps */
+    const double* position_com;
+    const double* velocity_com;
+    const double* rpy;
+    const double* rpy_dot;
+    int traj_len;
+    int traj_fps;
+    int solver;               /* 0 = default (structured Riccati kernel) ; 1 = generic dense variant */
+} vsmpc_config;
+
+/* lifecycle ------------------------------------------------------------------------------------ */
+int vsmpc_create(const vsmpc_config* cfg, int n_instances, int device, vsmpc_handle** out);
+int vsmpc_destroy(vsmpc_handle* h);
+const char* vsmpc_last_error(const vsmpc_handle* h);
+/* launch everything on this CUDA stream (a cudaStream_t; NULL = the handle's own stream) */
+int vsmpc_set_stream(vsmpc_handle* h, void* cuda_stream);
+
+int vsmpc_n_var(const vsmpc_handle* h);          /* IMPCProblem::getNOptimizationVariables */
+int vsmpc_n_constraints(const vsmpc_handle* h);  /* IMPCProblem::getNConstraints           */
+int vsmpc_n_instances(const vsmpc_handle* h);
+
+/* IMPCProblem::configure (IMPCProblem.cpp:3-148): initialise every instance's persistent state
+ * from the robot state at configure time and run "tick 0" of all counters / trajectory cursors.
+ * joint_pos_sel: double[8][B], Robot::getJointPos() of the controlled joints (costsVSMPC.cpp:540-550,
+ * variableSamplingMPC.cpp:60).  phase0: optional int[B] number of extra ticks (0..ratio-1) by which
+ * the 20-tick phase counters start ahead (NULL = reference behaviour). */
+int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* joint_pos_sel_host,
+                    const int* phase0_host);
+
+/* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel. */
+int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);
+/* same, pack already resident on the handle's GPU */
+int vsmpc_set_state_device(vsmpc_handle* h, const double* pack_dev);
+
+/* VariableSamplingMPC::solveMPC (variableSamplingMPC.cpp:88-112): structured QP solve + output
+ * extraction + joint accumulator.  vsmpc_solve blocks; _async + vsmpc_wait split it. */
+int vsmpc_solve(vsmpc_handle* h);
+int vsmpc_solve_async(vsmpc_handle* h);
+int vsmpc_wait(vsmpc_handle* h);
+
+/* getters: out_rows double[B][VSMPC_OUT_DOUBLES], status int[B] (either may be NULL) */
+int vsmpc_get_output(vsmpc_handle* h, double* out_rows_host, int* status_host);
+/* device pointers of the same buffers (valid for the handle's lifetime) */
+int vsmpc_get_output_device(vsmpc_handle* h, double** out_rows_dev, int** status_dev);
+/* IMPCProblem::getSolution: double[B][n_var] */
+int vsmpc_get_full_solution(vsmpc_handle* h, double* z_host);
+
+/* ---- inner seams, separately callable for parity tests -------------------------- */
+/* dense expansions of what the linearise kernel produced for the current tick:
+ *   A double[B][26*26], BJ double[B][26*8], BT double[B][26*4], c double[B][26] (row-major),
+ *   dt double[n_iter]  — SystemDynamicVS::get{A,BJoints,BThrottle}Matrix/getCVector + dt grid      */
+int vsmpc_get_dynamics(vsmpc_handle* h, double* A, double* BJ, double* BT, double* c, double* dt);
+/* IMPCProblem::getGradient / getLowerBound / getUpperBound: q double[B][n_var], l,u double[B][n_con] */
+int vsmpc_get_qp_vectors(vsmpc_handle* h, double* q, double* l, double* u);
+/* executed Riccati factorisations / back-solves per instance in the last solve (int[B] each) */
+int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve);
+/* test hook: overwrite the two 20-tick phase counters (ReferenceTrackingCost::m_counter,
+ * ThrottleConstraint::m_counter) of every instance; -1 leaves a counter unchanged */
+int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSMPC_H */

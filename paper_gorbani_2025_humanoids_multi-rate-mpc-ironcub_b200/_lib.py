@@ -1,0 +1,89 @@
+"""ctypes binding of libvsmpc.so (the C-ABI declared in include/vsmpc.h).
+
+There is NO fallback: if the CUDA library is missing or cannot be loaded the import of any compute
+entry point raises — the product path never routes through the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvsmpc.so")
+
+NX, NJ, NT = 26, 8, 4
+PACK_DOUBLES = 359
+OUT_DOUBLES = 54
+OUT_DELTA_Q, OUT_THROTTLE, OUT_THRUST, OUT_THRUST_DOT, OUT_FINAL_STATE, OUT_JOINTS_REF = 0, 8, 12, 16, 20, 46
+STATUS_SOLVED, STATUS_MAX_ITER, STATUS_NUMERICAL = 0, 1, 2
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, 1, 2, 3, 4
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+
+
+class VsmpcConfig(C.Structure):
+    _fields_ = [
+        ("n_iter", C.c_int), ("n_iter_small", C.c_int), ("control_horizon", C.c_int),
+        ("period_mpc", C.c_double), ("period_large", C.c_double), ("period_small", C.c_double),
+        ("use_jet_dynamic", C.c_int), ("use_estimated_thrust", C.c_int), ("joints_lambda_option", C.c_int),
+        ("weight_com_pos", C.c_double * 3), ("weight_com_pos_error", C.c_double * 3),
+        ("weight_lin_mom", C.c_double * 3), ("weight_rpy", C.c_double * 3),
+        ("weight_rpy_error", C.c_double * 3), ("weight_ang_mom", C.c_double * 3),
+        ("weight_delta_joint", C.c_double * 8),
+        ("weight_throttle", C.c_double), ("weight_initial_throttle", C.c_double),
+        ("weight_regularization_joint_pos", C.c_double),
+        ("throttle_min", C.c_double), ("throttle_max", C.c_double),
+        ("jet_coeff", C.c_double * 13), ("jet_norm", C.c_double * 4),
+        ("alpha_gravity", c_double_p), ("alpha_len", C.c_int), ("alpha_fps", C.c_int),
+        ("position_com", c_double_p), ("velocity_com", c_double_p), ("rpy", c_double_p),
+        ("rpy_dot", c_double_p), ("traj_len", C.c_int), ("traj_fps", C.c_int),
+        ("solver", C.c_int),
+    ]
+
+
+EXPORTS = [
+    "vsmpc_create", "vsmpc_destroy", "vsmpc_last_error", "vsmpc_set_stream", "vsmpc_n_var",
+    "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
+    "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
+    "vsmpc_get_output_device", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
+    "vsmpc_get_counts", "vsmpc_debug_set_counters",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.vsmpc_create.argtypes = [C.POINTER(VsmpcConfig), C.c_int, C.c_int, C.POINTER(H)]
+    lib.vsmpc_destroy.argtypes = [H]
+    lib.vsmpc_last_error.argtypes = [H]
+    lib.vsmpc_last_error.restype = C.c_char_p
+    lib.vsmpc_set_stream.argtypes = [H, C.c_void_p]
+    for f in ("vsmpc_n_var", "vsmpc_n_constraints", "vsmpc_n_instances"):
+        getattr(lib, f).argtypes = [H]
+    lib.vsmpc_configure.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vsmpc_set_state.argtypes = [H, C.c_void_p]
+    lib.vsmpc_set_state_device.argtypes = [H, C.c_void_p]
+    for f in ("vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait"):
+        getattr(lib, f).argtypes = [H]
+    lib.vsmpc_get_output.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.vsmpc_get_output_device.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.vsmpc_get_full_solution.argtypes = [H, C.c_void_p]
+    lib.vsmpc_get_dynamics.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vsmpc_get_qp_vectors.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vsmpc_get_counts.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
+    for f in EXPORTS:
+        if f != "vsmpc_last_error":
+            getattr(lib, f).restype = C.c_int
+    _lib = lib
+    return lib

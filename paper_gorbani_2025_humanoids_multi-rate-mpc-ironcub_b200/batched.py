@@ -1,0 +1,222 @@
+"""Batched host-side mirror of the reference's ``VariableSamplingMPC`` over the C-ABI.
+
+``BatchedVSMPC`` keeps the reference's configure / update / solveMPC / get* surface
+(variableSamplingMPC.h:15-41; MPCPyBindings.cpp:22-90) with every array carrying a leading
+instance dimension B.  All compute happens in libvsmpc.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .config import JET_COEFF, JET_NORM, default_params
+from .pack import PACK_DOUBLES, build_pack, DEFAULT_JOINT_SELECTOR
+
+
+class VsmpcError(RuntimeError):
+    pass
+
+
+def _cfg_struct(params: dict, traj: dict, solver: int, keep: list) -> L.VsmpcConfig:
+    p = dict(default_params())
+    p.update(params or {})
+    c = L.VsmpcConfig()
+    c.n_iter, c.n_iter_small, c.control_horizon = int(p["nIter"]), int(p["nIterSmall"]), int(p["controlHorizon"])
+    c.period_mpc, c.period_large, c.period_small = p["periodMPC"], p["periodMPCLargeSteps"], p["periodMPCSmallSteps"]
+    c.use_jet_dynamic = int(bool(p["useJetDynamic"]))
+    c.use_estimated_thrust = int(bool(p["useEstimatedThrust"]))
+    opt = p["jointsLambdaOption"]
+    if opt not in ("unfiltered", "constant"):
+        raise VsmpcError("Parameter 'jointsLambdaOption' should be 'unfiltered' or 'constant'.")
+    c.joints_lambda_option = 0 if opt == "unfiltered" else 1
+    for name, key in (("weight_com_pos", "weightCoMPos"), ("weight_com_pos_error", "weightCoMPosError"),
+                      ("weight_lin_mom", "weightLinMom"), ("weight_rpy", "weightRPY"),
+                      ("weight_rpy_error", "weightRPYError"), ("weight_ang_mom", "weightAngMom")):
+        v = list(p[key])
+        if len(v) != 3:
+            raise VsmpcError(f"Parameter '{key}' must have 3 elements")
+        setattr(c, name, (C.c_double * 3)(*v))
+    wdj = list(p["weightDeltaJoint"])
+    if len(wdj) != 8:
+        raise VsmpcError("The size of the vector containing the weights for the joint deltas is not correct.")
+    c.weight_delta_joint = (C.c_double * 8)(*wdj)
+    c.weight_throttle = p["weightThrottle"]
+    c.weight_initial_throttle = p["weightInitialThrottle"]
+    c.weight_regularization_joint_pos = p["weightRegularizationJointPos"]
+    c.throttle_min, c.throttle_max = p["throttleMin"], p["throttleMax"]
+    c.jet_coeff = (C.c_double * 13)(*p.get("jetCoeff", JET_COEFF))
+    c.jet_norm = (C.c_double * 4)(*p.get("jetNorm", JET_NORM))
+
+    def arr(a, shape_rows):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        if a.ndim != 2 or a.shape[0] != shape_rows:
+            raise VsmpcError(f"trajectory array must be ({shape_rows}, n)")
+        t = np.ascontiguousarray(a.T)  # sample-major
+        keep.append(t)
+        return t.ctypes.data_as(L.c_double_p), a.shape[1]
+
+    c.alpha_gravity, c.alpha_len = arr(traj["alphaGravity"], 1)
+    c.alpha_fps = int(traj["alpha_fps"])
+    c.position_com, n = arr(traj["positionCoM"], 3)
+    c.velocity_com, n2 = arr(traj["velocityCoM"], 3)
+    c.rpy, n3 = arr(traj["RPY"], 3)
+    c.rpy_dot, n4 = arr(traj["RPYDot"], 3)
+    if not (n == n2 == n3 == n4):
+        raise VsmpcError("trajectory arrays differ in length")
+    c.traj_len, c.traj_fps = n, int(traj["traj_fps"])
+    c.solver = int(solver)
+    return c
+
+
+class BatchedVSMPC:
+    """B independent MPC instances on one GPU."""
+
+    def __init__(self, n_instances: int, params: dict | None, trajectories: dict, device: int = 0,
+                 solver: int = 0):
+        self._lib = L.load()
+        self.B = int(n_instances)
+        self.params = dict(default_params())
+        self.params.update(params or {})
+        keep: list = []
+        cfg = _cfg_struct(self.params, trajectories, solver, keep)
+        h = C.c_void_p()
+        rc = self._lib.vsmpc_create(C.byref(cfg), self.B, int(device), C.byref(h))
+        self._h = h
+        if rc != L.OK:
+            msg = self._lib.vsmpc_last_error(h).decode() if h else "vsmpc_create failed"
+            if h:
+                self._lib.vsmpc_destroy(h)
+            self._h = None
+            raise VsmpcError(f"vsmpc_create: {msg} (code {rc})")
+        self.n_var = self._lib.vsmpc_n_var(h)
+        self.n_con = self._lib.vsmpc_n_constraints(h)
+        self.sel = list(DEFAULT_JOINT_SELECTOR)
+        self.device = int(device)
+
+    # ---- lifecycle -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vsmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != L.OK:
+            raise VsmpcError(f"{what}: {self._lib.vsmpc_last_error(self._h).decode()} (code {rc})")
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self._lib.vsmpc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "vsmpc_set_stream")
+
+    @staticmethod
+    def _f64(a, shape):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if a.shape != shape:
+            raise VsmpcError(f"expected array of shape {shape}, got {a.shape}")
+        return a
+
+    # ---- reference surface -------------------------------------------------------------------------
+    def configure_pack(self, pack: np.ndarray, joint_pos_sel: np.ndarray, phase0=None) -> bool:
+        """IMPCProblem::configure with the SoA pack (PACK_DOUBLES, B) and joint_pos_sel (8, B)."""
+        pack = self._f64(pack, (PACK_DOUBLES, self.B))
+        jp = self._f64(joint_pos_sel, (L.NJ, self.B))
+        ph = None
+        if phase0 is not None:
+            ph = np.ascontiguousarray(phase0, dtype=np.int32)
+            if ph.shape != (self.B,):
+                raise VsmpcError("phase0 must have shape (B,)")
+        self._ck(self._lib.vsmpc_configure(self._h, pack.ctypes.data, jp.ctypes.data,
+                                           ph.ctypes.data if ph is not None else None), "vsmpc_configure")
+        return True
+
+    def configure(self, state: dict, phase0=None) -> bool:
+        """``state``: getter-level batch dict (see synthetic.make_states)."""
+        pack = build_pack(state, self.sel)
+        jp = np.ascontiguousarray(state["joint_pos"][:, self.sel].T)
+        return self.configure_pack(pack, jp, phase0)
+
+    def update_pack(self, pack: np.ndarray) -> bool:
+        pack = self._f64(pack, (PACK_DOUBLES, self.B))
+        self._ck(self._lib.vsmpc_set_state(self._h, pack.ctypes.data), "vsmpc_set_state")
+        return True
+
+    def update_ptr(self, host_ptr: int) -> bool:
+        """update from a caller-owned (e.g. pinned) host buffer of PACK_DOUBLES*B doubles."""
+        self._ck(self._lib.vsmpc_set_state(self._h, C.c_void_p(host_ptr)), "vsmpc_set_state")
+        return True
+
+    def update_device_ptr(self, dev_ptr: int) -> bool:
+        self._ck(self._lib.vsmpc_set_state_device(self._h, C.c_void_p(dev_ptr)), "vsmpc_set_state_device")
+        return True
+
+    def update(self, state: dict) -> bool:
+        return self.update_pack(build_pack(state, self.sel))
+
+    def solveMPC(self) -> bool:
+        self._ck(self._lib.vsmpc_solve(self._h), "vsmpc_solve")
+        return True
+
+    def solve_async(self):
+        self._ck(self._lib.vsmpc_solve_async(self._h), "vsmpc_solve_async")
+
+    def wait(self):
+        self._ck(self._lib.vsmpc_wait(self._h), "vsmpc_wait")
+
+    # ---- getters ---------------------------------------------------------------------------------------
+    def get_output(self):
+        out = np.empty((self.B, L.OUT_DOUBLES))
+        status = np.empty(self.B, dtype=np.int32)
+        self._ck(self._lib.vsmpc_get_output(self._h, out.ctypes.data, status.ctypes.data), "vsmpc_get_output")
+        return out, status
+
+    def get_output_into(self, out_ptr: int, status_ptr: int):
+        self._ck(self._lib.vsmpc_get_output(self._h, C.c_void_p(out_ptr), C.c_void_p(status_ptr)), "vsmpc_get_output")
+
+    def output_device_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self._lib.vsmpc_get_output_device(self._h, C.byref(a), C.byref(b)), "vsmpc_get_output_device")
+        return a.value, b.value
+
+    def getSolution(self) -> np.ndarray:
+        z = np.empty((self.B, self.n_var))
+        self._ck(self._lib.vsmpc_get_full_solution(self._h, z.ctypes.data), "vsmpc_get_full_solution")
+        return z
+
+    def getThrottleReference(self): return self.get_output()[0][:, L.OUT_THROTTLE:L.OUT_THROTTLE + 4]
+    def getThrustReference(self): return self.get_output()[0][:, L.OUT_THRUST:L.OUT_THRUST + 4]
+    def getThrustDotReference(self): return self.get_output()[0][:, L.OUT_THRUST_DOT:L.OUT_THRUST_DOT + 4]
+    def getDeltaJoints(self): return self.get_output()[0][:, L.OUT_DELTA_Q:L.OUT_DELTA_Q + 8]
+    def getJointsReferencePositionControlled(self): return self.get_output()[0][:, L.OUT_JOINTS_REF:L.OUT_JOINTS_REF + 8]
+    def getFinalState(self): return self.get_output()[0][:, L.OUT_FINAL_STATE:L.OUT_FINAL_STATE + 26]
+    def getQPProblemStatus(self): return self.get_output()[1]
+    def getNOptimizationVariables(self): return self.n_var
+    def getNConstraints(self): return self.n_con
+
+    # ---- inner seams (parity tests) -----------------------------------------------------------------------
+    def get_dynamics(self):
+        B = self.B
+        A = np.empty((B, 26, 26)); BJ = np.empty((B, 26, 8)); BT = np.empty((B, 26, 4)); c = np.empty((B, 26))
+        dt = np.empty(int(self.params["nIter"]))
+        self._ck(self._lib.vsmpc_get_dynamics(self._h, A.ctypes.data, BJ.ctypes.data, BT.ctypes.data, c.ctypes.data,
+                                              dt.ctypes.data), "vsmpc_get_dynamics")
+        return A, BJ, BT, c, dt
+
+    def get_qp_vectors(self):
+        q = np.empty((self.B, self.n_var)); l = np.empty((self.B, self.n_con)); u = np.empty((self.B, self.n_con))
+        self._ck(self._lib.vsmpc_get_qp_vectors(self._h, q.ctypes.data, l.ctypes.data, u.ctypes.data),
+                 "vsmpc_get_qp_vectors")
+        return q, l, u
+
+    def get_counts(self):
+        nf = np.empty(self.B, dtype=np.int32); ns = np.empty(self.B, dtype=np.int32)
+        self._ck(self._lib.vsmpc_get_counts(self._h, nf.ctypes.data, ns.ctypes.data), "vsmpc_get_counts")
+        return nf, ns
+
+    def debug_set_counters(self, ref_counter: int = -1, throttle_counter: int = -1):
+        self._ck(self._lib.vsmpc_debug_set_counters(self._h, ref_counter, throttle_counter), "vsmpc_debug_set_counters")

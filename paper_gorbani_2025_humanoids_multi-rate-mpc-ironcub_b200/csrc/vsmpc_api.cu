@@ -1,0 +1,502 @@
+// C-ABI host layer (include/vsmpc.h): owns the device buffers of one batch of MPC instances on one
+// GPU and launches the kernels.  Mirrors the call sequence of the reference's
+// VariableSamplingMPC (configure -> update -> solveMPC -> getters).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "vsmpc_common.cuh"
+
+namespace vsmpc
+{
+cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
+                             const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
+                             int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
+                             const double* traj_rpy, const double* traj_rpyd, double* qd, cudaStream_t s);
+cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const double* qd, double* A, double* BJ,
+                                   double* BT, double* c, cudaStream_t s);
+cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
+                                     double* u, cudaStream_t s);
+size_t generic_scratch_doubles(const DeviceConfig& cfg);
+cudaError_t launch_qp_generic(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
+                              double* ws, double* scratch, double* z, double* st, double* out_rows, int* status,
+                              int* n_factor, int* n_solve, cudaStream_t s);
+size_t structured_scratch_doubles(const DeviceConfig& cfg);
+cudaError_t launch_qp_structured(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
+                                 double* ws, double* scratch, double* z, double* st, double* out_rows, int* status,
+                                 int* n_factor, int* n_solve, cudaStream_t s);
+} // namespace vsmpc
+
+using namespace vsmpc;
+
+struct vsmpc_handle
+{
+    DeviceConfig cfg{};
+    DeviceConfig* d_cfg = nullptr;
+    int B = 0;
+    int device = 0;
+    int solver = 0;
+    bool configured = false;
+    bool has_state = false;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    // device buffers
+    double* d_pack = nullptr;
+    double* d_jpos = nullptr;
+    int* d_phase = nullptr;
+    double* d_st = nullptr;
+    int* d_si = nullptr;
+    double* d_alpha = nullptr;
+    double *d_tpos = nullptr, *d_tvel = nullptr, *d_trpy = nullptr, *d_trpyd = nullptr;
+    double* d_qd = nullptr;
+    double* d_ws = nullptr;
+    double* d_scratch = nullptr;
+    double* d_z = nullptr;
+    double* d_out = nullptr;
+    int* d_status = nullptr;
+    int *d_nf = nullptr, *d_ns = nullptr;
+    std::string err;
+};
+
+namespace
+{
+int fail(vsmpc_handle* h, int code, const std::string& msg)
+{
+    if (h)
+        h->err = msg;
+    return code;
+}
+
+int cuda_fail(vsmpc_handle* h, cudaError_t e, const char* what)
+{
+    return fail(h, VSMPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call)                                      \
+    do                                                \
+    {                                                 \
+        cudaError_t e__ = (call);                     \
+        if (e__ != cudaSuccess)                       \
+            return cuda_fail(h, e__, #call);          \
+    } while (0)
+
+// Trajectory::upsample, UT/src/TrajectoryManager.cpp:23-39 (drops the last sample)
+std::vector<double> upsample(const double* v, int dim, int len, int fps, int des_fps)
+{
+    std::vector<double> out;
+    const double ratio = static_cast<double>(des_fps) / fps;
+    for (int i = 0; i + 1 < len; ++i)
+        for (size_t k = 0; k < ratio; ++k)
+            for (int a = 0; a < dim; ++a)
+                out.push_back(v[(size_t)i * dim + a] + (v[(size_t)(i + 1) * dim + a] - v[(size_t)i * dim + a]) * (k / ratio));
+    return out;
+}
+
+template <typename T> cudaError_t dalloc(T** p, size_t n)
+{
+    return cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+}
+} // namespace
+
+extern "C" {
+
+const char* vsmpc_last_error(const vsmpc_handle* h)
+{
+    return h ? h->err.c_str() : "null handle";
+}
+
+int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handle** out)
+{
+    if (!c || !out || n_instances <= 0)
+        return VSMPC_ERR_ARG;
+    *out = nullptr;
+    vsmpc_handle* h = new (std::nothrow) vsmpc_handle();
+    if (!h)
+        return VSMPC_ERR_ARG;
+    auto bail = [&](int code, const std::string& msg) {
+        // keep the handle alive so that the message can be read, but mark it unusable
+        h->err = msg;
+        h->B = 0;
+        *out = h;
+        return code;
+    };
+    if (c->n_iter < 2 || c->n_iter > MAX_ITER || c->n_iter_small < 2 || c->control_horizon < c->n_iter_small
+        || c->control_horizon > c->n_iter)
+        return bail(VSMPC_ERR_ARG, "need 2 <= nIterSmall <= controlHorizon <= nIter <= VSMPC_MAX_ITER");
+    if (c->joints_lambda_option != 0)
+        return bail(VSMPC_ERR_UNSUPPORTED, "jointsLambdaOption 'constant' is not implemented (only 'unfiltered')");
+    if (!c->alpha_gravity || c->alpha_len < 1 || !c->position_com || !c->velocity_com || !c->rpy || !c->rpy_dot
+        || c->traj_len < 1)
+        return bail(VSMPC_ERR_ARG, "trajectory arrays missing");
+    if (!(c->period_mpc > 0) || !(c->period_large > 0) || !(c->period_small > 0))
+        return bail(VSMPC_ERR_ARG, "periods must be positive");
+
+    DeviceConfig& g = h->cfg;
+    g.N = c->n_iter;
+    g.Ns = c->n_iter_small;
+    g.Nc = c->control_horizon;
+    g.NC = g.N - g.Ns + 1;
+    g.nblk = g.Nc - g.Ns + 1;
+    g.n_var = NX * (g.N + 1) + NJ * g.Nc + NT * g.nblk;               // variableSamplingMPC.cpp:44-45
+    g.n_con = NX * g.N + NX + NT * (g.N - g.Ns + 1);                  // constraintsVSMPC.cpp:7,283; IQPUtilsMPC.cpp:59
+    g.ratio = (int)std::lround(c->period_large / c->period_small);    // costsVSMPC.cpp:69
+    g.use_jet_dynamic = c->use_jet_dynamic;
+    g.use_estimated_thrust = c->use_estimated_thrust;
+    g.qd_stride = (QD_XREF + 12 * g.NC + 3) & ~3;
+    g.st_rows = ST_WIN + 12 * g.NC;
+    for (int i = 0; i < NX; ++i)
+        g.Qd[i] = 0.0;
+    for (int a = 0; a < 3; ++a)
+    { // costsVSMPC.cpp:78-93
+        g.Qd[IX_COM + a] = c->weight_com_pos[a];
+        g.Qd[IX_LIN + a] = c->weight_lin_mom[a];
+        g.Qd[IX_RPY + a] = c->weight_rpy[a];
+        g.Qd[IX_ANG + a] = c->weight_ang_mom[a];
+        g.Qd[IX_EP + a] = c->weight_com_pos_error[a];
+        g.Qd[IX_ER + a] = c->weight_rpy_error[a];
+    }
+    for (int a = 0; a < NJ; ++a) // costsVSMPC.cpp:375-382 + :564-571
+        g.Rqd[a] = c->weight_delta_joint[a] + c->weight_regularization_joint_pos;
+    g.w_reg_q = c->weight_regularization_joint_pos;
+    g.w_t = c->weight_throttle;
+    g.w_i = c->weight_initial_throttle;
+    g.throttle_min = c->throttle_min;
+    g.throttle_max = c->throttle_max;
+    std::memcpy(g.jc, c->jet_coeff, sizeof(g.jc));
+    std::memcpy(g.jn, c->jet_norm, sizeof(g.jn));
+    { // warp function, constraintsVSMPC.cpp:45-51,76-84,156-159
+        const double beta2 = (c->period_large - g.Ns * c->period_small) / (g.Ns * (g.Ns - 1));
+        const double beta1 = c->period_small - beta2;
+        auto warp = [&](double t) { return beta1 * t + beta2 * t * t; };
+        for (int k = 0; k < g.N; ++k)
+            g.dt[k] = k < g.Ns ? warp(k + 1) - warp(k) : c->period_large;
+    }
+    // trajectories with the TrajectoryManager's resampling (TrajectoryManager.cpp:121-126)
+    std::vector<double> alpha(c->alpha_gravity, c->alpha_gravity + c->alpha_len);
+    const int des_alpha = (int)(1 / c->period_mpc); // double -> int at systemDynamicsVSMPC.cpp:272
+    if (c->alpha_fps != des_alpha && c->alpha_len > 1)
+        alpha = upsample(c->alpha_gravity, 1, c->alpha_len, c->alpha_fps, des_alpha);
+    const int des_traj = (int)(1 / c->period_large); // costsVSMPC.cpp:68
+    std::vector<double> tp(c->position_com, c->position_com + 3 * (size_t)c->traj_len);
+    std::vector<double> tv(c->velocity_com, c->velocity_com + 3 * (size_t)c->traj_len);
+    std::vector<double> tr(c->rpy, c->rpy + 3 * (size_t)c->traj_len);
+    std::vector<double> td(c->rpy_dot, c->rpy_dot + 3 * (size_t)c->traj_len);
+    if (c->traj_fps != des_traj && c->traj_len > 1)
+    {
+        tp = upsample(c->position_com, 3, c->traj_len, c->traj_fps, des_traj);
+        tv = upsample(c->velocity_com, 3, c->traj_len, c->traj_fps, des_traj);
+        tr = upsample(c->rpy, 3, c->traj_len, c->traj_fps, des_traj);
+        td = upsample(c->rpy_dot, 3, c->traj_len, c->traj_fps, des_traj);
+    }
+    g.alpha_len = (int)alpha.size();
+    g.traj_len = (int)(tp.size() / 3);
+    if (g.alpha_len < 1 || g.traj_len < 1)
+        return bail(VSMPC_ERR_ARG, "empty trajectory after resampling");
+
+    h->B = n_instances;
+    h->device = device;
+    h->solver = c->solver;
+    const int B = n_instances;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return bail(VSMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    const size_t scratch = h->solver == 1 ? generic_scratch_doubles(g) : structured_scratch_doubles(g);
+    bool ok = true;
+    auto A = [&](cudaError_t r) { ok = ok && (r == cudaSuccess); if (r != cudaSuccess) e = r; };
+    A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    A(dalloc(&h->d_cfg, 1));
+    A(dalloc(&h->d_pack, (size_t)VSMPC_PACK_DOUBLES * B));
+    A(dalloc(&h->d_jpos, (size_t)NJ * B));
+    A(dalloc(&h->d_phase, (size_t)B));
+    A(dalloc(&h->d_st, (size_t)g.st_rows * B));
+    A(dalloc(&h->d_si, (size_t)SI_COUNT * B));
+    A(dalloc(&h->d_alpha, alpha.size()));
+    A(dalloc(&h->d_tpos, tp.size()));
+    A(dalloc(&h->d_tvel, tv.size()));
+    A(dalloc(&h->d_trpy, tr.size()));
+    A(dalloc(&h->d_trpyd, td.size()));
+    A(dalloc(&h->d_qd, (size_t)g.qd_stride * B));
+    A(dalloc(&h->d_ws, (size_t)g.N * WS_STAGE * B));
+    A(dalloc(&h->d_scratch, scratch * B));
+    A(dalloc(&h->d_z, (size_t)g.n_var * B));
+    A(dalloc(&h->d_out, (size_t)VSMPC_OUT_DOUBLES * B));
+    A(dalloc(&h->d_status, (size_t)B));
+    A(dalloc(&h->d_nf, (size_t)B));
+    A(dalloc(&h->d_ns, (size_t)B));
+    if (ok)
+    {
+        A(cudaMemcpy(h->d_cfg, &g, sizeof(g), cudaMemcpyHostToDevice));
+        A(cudaMemcpy(h->d_alpha, alpha.data(), alpha.size() * 8, cudaMemcpyHostToDevice));
+        A(cudaMemcpy(h->d_tpos, tp.data(), tp.size() * 8, cudaMemcpyHostToDevice));
+        A(cudaMemcpy(h->d_tvel, tv.data(), tv.size() * 8, cudaMemcpyHostToDevice));
+        A(cudaMemcpy(h->d_trpy, tr.data(), tr.size() * 8, cudaMemcpyHostToDevice));
+        A(cudaMemcpy(h->d_trpyd, td.data(), td.size() * 8, cudaMemcpyHostToDevice));
+        A(cudaMemset(h->d_out, 0, (size_t)VSMPC_OUT_DOUBLES * B * 8));
+        A(cudaMemset(h->d_status, 0, (size_t)B * 4));
+        A(cudaMemset(h->d_z, 0, (size_t)g.n_var * B * 8));
+        A(cudaMemset(h->d_nf, 0, (size_t)B * 4));
+        A(cudaMemset(h->d_ns, 0, (size_t)B * 4));
+    }
+    if (!ok)
+    {
+        std::string msg = std::string("device allocation/initialisation failed: ") + cudaGetErrorString(e);
+        vsmpc_destroy(h);
+        h = new (std::nothrow) vsmpc_handle();
+        if (!h)
+            return VSMPC_ERR_CUDA;
+        return bail(VSMPC_ERR_CUDA, msg);
+    }
+    *out = h;
+    return VSMPC_OK;
+}
+
+int vsmpc_destroy(vsmpc_handle* h)
+{
+    if (!h)
+        return VSMPC_OK;
+    if (h->B > 0)
+        cudaSetDevice(h->device);
+    void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
+                    h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
+                    h->d_status, h->d_nf, h->d_ns};
+    for (void* p : ptrs)
+        if (p)
+            cudaFree(p);
+    if (h->own_stream)
+        cudaStreamDestroy(h->own_stream);
+    delete h;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_stream(vsmpc_handle* h, void* s)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+    return VSMPC_OK;
+}
+
+int vsmpc_n_var(const vsmpc_handle* h) { return h ? h->cfg.n_var : -1; }
+int vsmpc_n_constraints(const vsmpc_handle* h) { return h ? h->cfg.n_con : -1; }
+int vsmpc_n_instances(const vsmpc_handle* h) { return h ? h->B : -1; }
+
+static int run_linearise(vsmpc_handle* h, int mode)
+{
+    CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
+                        h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* joint_pos_sel_host, const int* phase0_host)
+{
+    if (!h || h->B <= 0 || !pack_host || !joint_pos_sel_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_configure: null argument");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->B;
+    CK(cudaMemcpyAsync(h->d_pack, pack_host, VSMPC_PACK_DOUBLES * B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_jpos, joint_pos_sel_host, NJ * B * 8, cudaMemcpyHostToDevice, h->stream));
+    if (phase0_host)
+    {
+        for (size_t i = 0; i < B; ++i)
+            if (phase0_host[i] < 0 || phase0_host[i] >= h->cfg.ratio)
+                return fail(h, VSMPC_ERR_ARG, "vsmpc_configure: phase0 out of [0, ratio)");
+        CK(cudaMemcpyAsync(h->d_phase, phase0_host, B * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    else
+        CK(cudaMemsetAsync(h->d_phase, 0, B * 4, h->stream));
+    int rc = run_linearise(h, 1);
+    if (rc)
+        return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->configured = true;
+    h->has_state = false;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_state(vsmpc_handle* h, const double* pack_host)
+{
+    if (!h || h->B <= 0 || !pack_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_set_state: null argument");
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_set_state: configure first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_pack, pack_host, (size_t)VSMPC_PACK_DOUBLES * h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_linearise(h, 0);
+    if (rc)
+        return rc;
+    h->has_state = true;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_state_device(vsmpc_handle* h, const double* pack_dev)
+{
+    if (!h || h->B <= 0 || !pack_dev)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_set_state_device: null argument");
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_set_state_device: configure first");
+    CK(cudaSetDevice(h->device));
+    double* saved = h->d_pack;
+    h->d_pack = const_cast<double*>(pack_dev);
+    int rc = run_linearise(h, 0);
+    h->d_pack = saved;
+    if (rc)
+        return rc;
+    h->has_state = true;
+    return VSMPC_OK;
+}
+
+int vsmpc_solve_async(vsmpc_handle* h)
+{
+    if (!h || h->B <= 0)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_solve: bad handle");
+    if (!h->has_state)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_solve: no state set since configure (call vsmpc_set_state)");
+    CK(cudaSetDevice(h->device));
+    if (h->solver == 1)
+        CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
+                             h->d_status, h->d_nf, h->d_ns, h->stream));
+    else
+        CK(launch_qp_structured(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
+                                h->d_status, h->d_nf, h->d_ns, h->stream));
+    h->has_state = false; // one solve per update, like the reference's tick
+    return VSMPC_OK;
+}
+
+int vsmpc_wait(vsmpc_handle* h)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_solve(vsmpc_handle* h)
+{
+    int rc = vsmpc_solve_async(h);
+    return rc ? rc : vsmpc_wait(h);
+}
+
+int vsmpc_get_output(vsmpc_handle* h, double* out_rows_host, int* status_host)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (out_rows_host)
+        CK(cudaMemcpyAsync(out_rows_host, h->d_out, (size_t)VSMPC_OUT_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (status_host)
+        CK(cudaMemcpyAsync(status_host, h->d_status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_get_output_device(vsmpc_handle* h, double** out_rows_dev, int** status_dev)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    if (out_rows_dev)
+        *out_rows_dev = h->d_out;
+    if (status_dev)
+        *status_dev = h->d_status;
+    return VSMPC_OK;
+}
+
+int vsmpc_get_full_solution(vsmpc_handle* h, double* z_host)
+{
+    if (!h || h->B <= 0 || !z_host)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(z_host, h->d_z, (size_t)h->cfg.n_var * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_get_dynamics(vsmpc_handle* h, double* A, double* BJ, double* BT, double* c, double* dt)
+{
+    if (!h || h->B <= 0 || !A || !BJ || !BT || !c)
+        return VSMPC_ERR_ARG;
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_get_dynamics: configure first");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->B;
+    double *dA, *dBJ, *dBT, *dc;
+    CK(dalloc(&dA, B * NX * NX));
+    CK(dalloc(&dBJ, B * NX * NJ));
+    CK(dalloc(&dBT, B * NX * NT));
+    CK(dalloc(&dc, B * NX));
+    cudaError_t e = launch_expand_dynamics(h->d_cfg, h->B, h->d_qd, dA, dBJ, dBT, dc, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(A, dA, B * NX * NX * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(BJ, dBJ, B * NX * NJ * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(BT, dBT, B * NX * NT * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c, dc, B * NX * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dA); cudaFree(dBJ); cudaFree(dBT); cudaFree(dc);
+    if (e != cudaSuccess)
+        return cuda_fail(h, e, "vsmpc_get_dynamics");
+    if (dt)
+        std::memcpy(dt, h->cfg.dt, sizeof(double) * h->cfg.N);
+    return VSMPC_OK;
+}
+
+int vsmpc_get_qp_vectors(vsmpc_handle* h, double* q, double* l, double* u)
+{
+    if (!h || h->B <= 0 || !q || !l || !u)
+        return VSMPC_ERR_ARG;
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_get_qp_vectors: configure first");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->B;
+    double *dq, *dl, *du;
+    CK(dalloc(&dq, B * h->cfg.n_var));
+    CK(dalloc(&dl, B * h->cfg.n_con));
+    CK(dalloc(&du, B * h->cfg.n_con));
+    cudaError_t e = launch_expand_qp_vectors(h->d_cfg, h->B, h->d_qd, dq, dl, du, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q, dq, B * h->cfg.n_var * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(l, dl, B * h->cfg.n_con * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u, du, B * h->cfg.n_con * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dq); cudaFree(dl); cudaFree(du);
+    if (e != cudaSuccess)
+        return cuda_fail(h, e, "vsmpc_get_qp_vectors");
+    return VSMPC_OK;
+}
+
+int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (n_factor)
+        CK(cudaMemcpyAsync(n_factor, h->d_nf, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (n_solve)
+        CK(cudaMemcpyAsync(n_solve, h->d_ns, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_debug_set_counters: configure first");
+    CK(cudaSetDevice(h->device));
+    std::vector<int> v(h->B);
+    if (ref_counter >= 0)
+    {
+        std::fill(v.begin(), v.end(), ref_counter);
+        CK(cudaMemcpy(h->d_si + (size_t)SI_REF_COUNTER * h->B, v.data(), (size_t)h->B * 4, cudaMemcpyHostToDevice));
+    }
+    if (throttle_counter >= 0)
+    {
+        std::fill(v.begin(), v.end(), throttle_counter);
+        CK(cudaMemcpy(h->d_si + (size_t)SI_THR_COUNTER * h->B, v.data(), (size_t)h->B * 4, cudaMemcpyHostToDevice));
+    }
+    return VSMPC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,634 @@
+// K1 — linearise + discretise-prep kernel (sm_100a, FP64 CUDA cores).
+//
+// One thread per MPC instance.  Reads the structure-of-arrays pack (fully coalesced: consecutive
+// threads read consecutive doubles of each pack row) and the per-instance persistent state, and
+// replaces, for one controller tick, the host work of
+//   IMPCProblem::update                       MPC/src/IMPCProblem/IMPCProblem.cpp:150-194
+//     ReferenceTrackingCost::compute...       MPC/src/variableSamplingMPC/costsVSMPC.cpp:121-181
+//     ThrottleInitialValueCost::compute...    costsVSMPC.cpp:468-487
+//     JointPositionRegularizationCost::...    costsVSMPC.cpp:558-592
+//     SystemDynamicVS::updateDynamicMatrices  systemDynamicsVSMPC.cpp:495-507 (Angular :72-226,
+//                                             Linear :282-350, Jet :384-461)
+//     ConstraintInitialState::updateInitial.. constraintsVSMPC.cpp:206-247
+//     ThrottleConstraint::compute...          constraintsVSMPC.cpp:338-374
+// It emits the ~120 structural nonzeros of (A, B_J, B_T, c) instead of the reference's dense
+// 512x588 constraint matrix; the per-knot dt scaling (constraintsVSMPC.cpp:76-131) is applied by
+// the QP kernel on the fly.  The instance-major QP data block is staged through shared memory so
+// that the global stores are coalesced.
+#include "vsmpc_common.cuh"
+
+namespace vsmpc
+{
+
+__device__ __forceinline__ void mat3T_vec(const double* R, const double* v, double* o)
+{ // o = R^T v, R row-major
+    o[0] = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+    o[1] = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+    o[2] = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+}
+
+__device__ __forceinline__ void skew3(const double* v, double* S)
+{ // UT/src/FlightControlUtils.cpp:77-85
+    S[0] = 0.0; S[1] = -v[2]; S[2] = v[1];
+    S[3] = v[2]; S[4] = 0.0; S[5] = -v[0];
+    S[6] = -v[1]; S[7] = v[0]; S[8] = 0.0;
+}
+
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3 + 0] * B[0 + j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+
+__device__ __forceinline__ void mat3_inv(const double* A, double* I)
+{
+    const double c00 = A[4] * A[8] - A[5] * A[7];
+    const double c01 = A[5] * A[6] - A[3] * A[8];
+    const double c02 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
+    const double id = 1.0 / det;
+    I[0] = c00 * id;
+    I[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+    I[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    I[3] = c01 * id;
+    I[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+    I[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    I[6] = c02 * id;
+    I[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+    I[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+}
+
+// (X^T M_b X).block(3,3,3,3) with X = Ad(G_H_B) = [[R, S(r)R],[0, R]]
+// (systemDynamicsVSMPC.cpp:110-130, costsVSMPC.cpp:268-285)
+__device__ void locked_inertia(const double* __restrict__ pack, int B, int i, const double* R, double* I3)
+{
+    double r[3], Sr[9], SR[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        r[a] = pack[(VSMPC_PK_P_COM + a) * (size_t)B + i] - pack[(VSMPC_PK_BASE_POS + a) * (size_t)B + i];
+    skew3(r, Sr);
+    mat3_mul(Sr, R, SR);
+    // Xc = [SR; R] (6x3): I3 = Xc^T M_b Xc
+    double MX[18]; // M_b * Xc  (6x3)
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+    {
+        double m[6];
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+            m[b] = pack[(VSMPC_PK_MB + a * 6 + b) * (size_t)B + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += m[b] * SR[b * 3 + c];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += m[3 + b] * R[b * 3 + c];
+            MX[a * 3 + c] = s;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += SR[b * 3 + a] * MX[b * 3 + c];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += R[b * 3 + a] * MX[(3 + b) * 3 + c];
+            I3[a * 3 + c] = s;
+        }
+}
+
+// W(rpy): costsVSMPC.cpp:276-282
+__device__ __forceinline__ void W_of_rpy(const double* rpy, double* W)
+{
+    const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), s1 = sin(rpy[1]), c1 = cos(rpy[1]);
+    W[0] = 1.0; W[1] = 0.0; W[2] = -s1;
+    W[3] = 0.0; W[4] = c0; W[5] = c1 * s0;
+    W[6] = 0.0; W[7] = -s0; W[8] = c0 * c1;
+}
+
+constexpr int K1_THREADS = 64;
+
+// mode 0: update tick.  mode 1: configure (initialise persistent state, then run tick 0).
+__global__ void __launch_bounds__(K1_THREADS)
+linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
+                 const double* __restrict__ pack, const double* __restrict__ joint_pos_sel,
+                 const int* __restrict__ phase0, double* __restrict__ st, int* __restrict__ si,
+                 const double* __restrict__ alpha_traj, const double* __restrict__ traj_pos,
+                 const double* __restrict__ traj_vel, const double* __restrict__ traj_rpy,
+                 const double* __restrict__ traj_rpyd, double* __restrict__ qd)
+{
+    extern __shared__ double stage[]; // [K1_THREADS][qd_stride + 1]
+    const DeviceConfig& cfg = *cfgp;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * K1_THREADS + tid;
+    const int NC = cfg.NC;
+    const int ld = cfg.qd_stride + 1;
+    double* out = stage + (size_t)tid * ld;
+    const size_t Bs = (size_t)B;
+#define PK(f) pack[(size_t)(f) * Bs + i]
+#define ST(f) st[(size_t)(f) * Bs + i]
+#define SI(f) si[(size_t)(f) * Bs + i]
+    if (i < B)
+    {
+        const Jet jet{cfg.jc, cfg.jn};
+        double R[9], rpy[3], pcom[3];
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+            R[a] = PK(VSMPC_PK_WRB + a);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            rpy[a] = PK(VSMPC_PK_RPY + a);
+            pcom[a] = PK(VSMPC_PK_P_COM + a);
+        }
+        const double mass = PK(VSMPC_PK_MASS);
+        double I3[9], W[9];
+        locked_inertia(pack, B, i, R, I3);
+        W_of_rpy(rpy, W);
+
+        // new reference-window column at trajectory index idx (costsVSMPC.cpp:105-112,132-149)
+        auto ref_column = [&](int idx, const double* pinit, const double* rinit, double* col) {
+            double vel[3], rd[3], mv[3], Wr[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                col[a] = pinit[a] + traj_pos[3 * idx + a];
+                vel[a] = traj_vel[3 * idx + a];
+                col[6 + a] = rinit[a] + traj_rpy[3 * idx + a];
+                rd[a] = traj_rpyd[3 * idx + a];
+                mv[a] = mass * vel[a];
+            }
+            mat3T_vec(R, mv, col + 3);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                Wr[a] = W[a * 3] * rd[0] + W[a * 3 + 1] * rd[1] + W[a * 3 + 2] * rd[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                col[9 + a] = I3[a * 3] * Wr[0] + I3[a * 3 + 1] * Wr[1] + I3[a * 3 + 2] * Wr[2];
+        };
+
+        if (mode == 1)
+        {
+            // configureDynVectorsSize of the costs/constraints (costsVSMPC.cpp:74-119,
+            // constraintsVSMPC.cpp:184-204,326-336; systemDynamicsVSMPC.cpp:67; variableSamplingMPC.cpp:60)
+            double col[12];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                ST(ST_P_INIT + a) = pcom[a];
+                ST(ST_RPY_INIT + a) = rpy[a];
+                ST(ST_RPY_OLD + a) = rpy[a];
+                ST(ST_NTURNS + a) = 0.0;
+                ST(ST_P_REF + a) = 0.0;
+                ST(ST_RPY_REF + a) = 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+                ST(ST_MOM_REF + a) = 0.0;
+            ST(ST_ALPHA) = 0.0;
+#pragma unroll
+            for (int a = 0; a < NJ; ++a)
+            {
+                const double q0 = joint_pos_sel[(size_t)a * Bs + i];
+                ST(ST_QREF0 + a) = q0;
+                ST(ST_QACC + a) = q0;
+            }
+            ref_column(0, pcom, rpy, col);
+            for (int r = 0; r < 12; ++r)
+                for (int c = 0; c < NC; ++c)
+                    ST(ST_WIN + r * NC + c) = col[r];
+            const int ph = phase0 ? phase0[i] : 0;
+            // both 20-tick counters start at ratio-1 (costsVSMPC.cpp:118, constraintsVSMPC.cpp:335)
+            SI(SI_REF_COUNTER) = (cfg.ratio - 1 + ph) % cfg.ratio;
+            SI(SI_THR_COUNTER) = (cfg.ratio - 1 + ph) % cfg.ratio;
+            SI(SI_ALPHA_IDX) = 0;
+            SI(SI_REF_IDX) = 0;
+        }
+
+        // ---------------- costs (evaluated before the constraints, IMPCProblem.cpp:157-192) ---------
+        {
+            int rc = SI(SI_REF_COUNTER);
+            if (rc == cfg.ratio - 1)
+            {
+                int idx = SI(SI_REF_IDX);
+                if (idx < cfg.traj_len - 1) // TrajectoryManager::advanceTrajectory, TrajectoryManager.cpp:142-153
+                    idx++;
+                SI(SI_REF_IDX) = idx;
+                double pinit[3], rinit[3], col[12];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    pinit[a] = ST(ST_P_INIT + a);
+                    rinit[a] = ST(ST_RPY_INIT + a);
+                }
+                ref_column(idx, pinit, rinit, col);
+                for (int r = 0; r < 12; ++r)
+                {
+                    for (int c = 0; c + 1 < NC; ++c)
+                        ST(ST_WIN + r * NC + c) = ST(ST_WIN + r * NC + c + 1);
+                    ST(ST_WIN + r * NC + NC - 1) = col[r];
+                }
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    ST(ST_P_REF + a) = ST(ST_WIN + (0 + a) * NC);
+                    ST(ST_RPY_REF + a) = ST(ST_WIN + (6 + a) * NC);
+                    ST(ST_MOM_REF + a) = ST(ST_WIN + (3 + a) * NC);
+                    ST(ST_MOM_REF + 3 + a) = ST(ST_WIN + (9 + a) * NC);
+                }
+                rc = 0;
+            }
+            else
+                rc++;
+            SI(SI_REF_COUNTER) = rc;
+        }
+        for (int r = 0; r < 12; ++r)
+            for (int c = 0; c < NC; ++c)
+                out[QD_XREF + r * NC + c] = ST(ST_WIN + r * NC + c);
+
+        double uprev[NT], vbar[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+        {
+            uprev[j] = PK(VSMPC_PK_THROTTLE_PREV + j);
+            vbar[j] = jet.v(jet.stdU(uprev[j]));
+            out[QD_VBAR + j] = vbar[j];
+        }
+#pragma unroll
+        for (int a = 0; a < NJ; ++a)
+            out[QD_GQ + a] = cfg.w_reg_q * (PK(VSMPC_PK_Q_CMD + a) - ST(ST_QREF0 + a));
+
+        // ---------------- dynamics ---------------------------------------------------------------------
+        double omw[3], omB[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            omw[a] = PK(VSMPC_PK_OMEGA_WORLD + a);
+        mat3T_vec(R, omw, omB);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            out[QD_OMEGA + a] = omB[a];
+        { // A[rpy, angMom] = W^-1 * I^-1     (systemDynamicsVSMPC.cpp:86-87,140-147)
+            const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), t1 = tan(rpy[1]), c1 = cos(rpy[1]);
+            double Wi[9] = {1.0, s0 * t1, c0 * t1, 0.0, c0, -s0, 0.0, s0 / c1, c0 / c1};
+            double Ii[9], WI[9];
+            mat3_inv(I3, Ii);
+            mat3_mul(Wi, Ii, WI);
+#pragma unroll
+            for (int a = 0; a < 9; ++a)
+                out[QD_WI + a] = WI[a];
+        }
+        const double inv_m = 1.0 / mass;
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+            out[QD_RM + a] = inv_m * R[a];
+#pragma unroll
+        for (int a = 0; a < 12; ++a)
+        {
+            out[QD_ALIN + a] = PK(VSMPC_PK_AMOM_BODY + a);
+            out[QD_AANG + a] = PK(VSMPC_PK_AMOM_BODY + 12 + a);
+        }
+        // Lambda_lin / Lambda_ang ("unfiltered", systemDynamicsVSMPC.cpp:166-186,338-346)
+        double Llin[24], Lang[24];
+#pragma unroll
+        for (int a = 0; a < 24; ++a)
+            Llin[a] = Lang[a] = 0.0;
+        double thrust[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            thrust[j] = PK(VSMPC_PK_THRUST + j);
+        for (int j = 0; j < NT; ++j)
+        {
+            double ax[3], ar[3], ab[3], rb[3], Sa[9], Srb[9], SrSa[9];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                ax[a] = PK(VSMPC_PK_JET_AXES + j * 3 + a);
+                ar[a] = PK(VSMPC_PK_JET_ARMS + j * 3 + a);
+            }
+            mat3T_vec(R, ax, ab);
+            mat3T_vec(R, ar, rb);
+            skew3(ab, Sa);
+            skew3(rb, Srb);
+            mat3_mul(Srb, Sa, SrSa);
+            const double T = thrust[j];
+            for (int b = 0; b < NJ; ++b)
+            {
+                double Jw[3], dl[3], Jc[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    Jw[a] = PK(VSMPC_PK_J_REL_ANG + (j * 3 + a) * NJ + b);
+                    dl[a] = PK(VSMPC_PK_J_JET_LIN + (j * 3 + a) * NJ + b) - PK(VSMPC_PK_J_COM + a * NJ + b);
+                }
+                mat3T_vec(R, dl, Jc); // getRelativeJacobianCoM, :208-226
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    const double saJc = Sa[a * 3] * Jc[0] + Sa[a * 3 + 1] * Jc[1] + Sa[a * 3 + 2] * Jc[2];
+                    const double ssJw = SrSa[a * 3] * Jw[0] + SrSa[a * 3 + 1] * Jw[1] + SrSa[a * 3 + 2] * Jw[2];
+                    const double saJw = Sa[a * 3] * Jw[0] + Sa[a * 3 + 1] * Jw[1] + Sa[a * 3 + 2] * Jw[2];
+                    Lang[a * NJ + b] -= T * saJc;
+                    Lang[a * NJ + b] -= T * ssJw;
+                    Llin[a * NJ + b] -= T * saJw;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 24; ++a)
+        {
+            out[QD_LLIN + a] = Llin[a];
+            out[QD_LANG + a] = Lang[a];
+        }
+        { // c[linMom] = alpha_g * m * wRb^T g ; advance the alpha cursor (:307-311)
+            int aidx = SI(SI_ALPHA_IDX);
+            const double alpha = alpha_traj[aidx];
+            ST(ST_ALPHA) = alpha;
+            if (aidx < cfg.alpha_len - 1)
+                aidx++;
+            SI(SI_ALPHA_IDX) = aidx;
+            const double s = alpha * mass;
+            double g[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                g[a] = PK(VSMPC_PK_GRAVITY + a);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                out[QD_CL + a] = (s * R[a]) * g[0] + (s * R[3 + a]) * g[1] + (s * R[6 + a]) * g[2];
+        }
+        double pref[3], rref[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            pref[a] = ST(ST_P_REF + a);
+            rref[a] = ST(ST_RPY_REF + a);
+            out[QD_CEP + a] = -pref[a];               // :316
+            out[QD_CER + a] = -ST(ST_RPY_INIT + a);   // :100 (configure-time RPY)
+        }
+        // jets (:384-429)
+        double Tdest[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            Tdest[j] = PK(VSMPC_PK_THRUST_DOT_EST + j);
+        if (cfg.use_jet_dynamic)
+        {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+            {
+                const double Tdes = PK(VSMPC_PK_THRUST_DES + j), Tddes = PK(VSMPC_PK_THRUST_DOT_DES + j);
+                const double T = cfg.use_estimated_thrust ? thrust[j] : Tdes;
+                const double Td = cfg.use_estimated_thrust ? Tdest[j] : Tddes;
+                const double Tb = jet.stdT(T), Tdb = jet.stdTd(Td);
+                const double vu = jet.v(jet.stdU(uprev[j]));
+                const double dh_dT = jet.df_dT(Tb, Tdb) + jet.dg_dT(Tb, Tdb) * vu;
+                const double dh_dTd = jet.df_dTd(Tb, Tdb) + jet.dg_dTd(Tb, Tdb) * vu;
+                out[QD_JA + j] = dh_dT;
+                out[QD_JB + j] = dh_dTd;
+                out[QD_JG + j] = jet.g(jet.stdT(Tdes), jet.stdTd(Tddes)) * cfg.jn[1];
+                out[QD_CTD + j] = jet.f(Tb, Tdb) * cfg.jn[1] - dh_dT * T - dh_dTd * Td;
+            }
+            out[QD_JTT] = 1.0;
+            out[QD_JGT] = 0.0;
+        }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                out[QD_JA + j] = out[QD_JB + j] = out[QD_JG + j] = out[QD_CTD + j] = 0.0;
+            out[QD_JTT] = 0.0;
+            out[QD_JGT] = 1.0;
+        }
+        // ---------------- initial state (constraintsVSMPC.cpp:206-247) ---------------------------------
+        {
+            const double PI = 3.14159265358979323846;
+            double unw[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                double nt = ST(ST_NTURNS + a);
+                const double old = ST(ST_RPY_OLD + a);
+                if (rpy[a] - old > PI)
+                    nt -= 1.0;
+                else if (rpy[a] - old < -PI)
+                    nt += 1.0;
+                ST(ST_NTURNS + a) = nt;
+                ST(ST_RPY_OLD + a) = rpy[a];
+                unw[a] = rpy[a] + 2 * PI * nt;
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                out[QD_X0 + IX_COM + a] = pcom[a];
+                out[QD_X0 + IX_LIN + a] = PK(VSMPC_PK_MOMENTUM_BODY + a);
+                out[QD_X0 + IX_RPY + a] = unw[a];
+                out[QD_X0 + IX_ANG + a] = PK(VSMPC_PK_MOMENTUM_BODY + 3 + a);
+                out[QD_X0 + IX_EP + a] = pcom[a] - pref[a];
+                out[QD_X0 + IX_ER + a] = unw[a] - rref[a];
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+            {
+                out[QD_X0 + IX_T + j] = cfg.use_estimated_thrust ? thrust[j] : PK(VSMPC_PK_THRUST_DES + j);
+                out[QD_X0 + IX_TD + j] = cfg.use_estimated_thrust ? Tdest[j] : PK(VSMPC_PK_THRUST_DOT_DES + j);
+            }
+        }
+        // ---------------- throttle box / pin (constraintsVSMPC.cpp:338-374) ----------------------------
+        {
+            int tc = SI(SI_THR_COUNTER);
+            out[QD_PINNED] = (tc != cfg.ratio - 1) ? 1.0 : 0.0;
+            tc = (tc == cfg.ratio - 1) ? 0 : tc + 1;
+            SI(SI_THR_COUNTER) = tc;
+            out[QD_VMIN] = jet.v(jet.stdU(cfg.throttle_min));
+            out[QD_VMAX] = jet.v(jet.stdU(cfg.throttle_max));
+        }
+        out[QD_JGT + 1] = out[QD_JGT + 2] = out[QD_JGT + 3] = 0.0; // padding 161..163
+    }
+#undef PK
+#undef ST
+#undef SI
+    __syncthreads();
+    // coalesced write-out of the instance-major blocks staged in shared memory
+    const int first = blockIdx.x * K1_THREADS;
+    const int nvalid = min(K1_THREADS, B - first);
+    const int stride = cfg.qd_stride;
+    for (int e = tid; e < nvalid * stride; e += K1_THREADS)
+    {
+        const int t = e / stride, r = e - t * stride;
+        qd[(size_t)first * stride + e] = stage[(size_t)t * ld + r];
+    }
+}
+
+// ---- dense expansion for parity tests (vsmpc_get_dynamics / vsmpc_get_qp_vectors) ----------------
+__device__ void expand_dense(const double* __restrict__ q, double* A, double* BJ, double* BT, double* c)
+{
+    for (int e = 0; e < NX * NX; ++e)
+        A[e] = 0.0;
+    for (int e = 0; e < NX * NJ; ++e)
+        BJ[e] = 0.0;
+    for (int e = 0; e < NX * NT; ++e)
+        BT[e] = 0.0;
+    for (int e = 0; e < NX; ++e)
+        c[e] = 0.0;
+    double S[9];
+    skew3(q + QD_OMEGA, S);
+    for (int a = 0; a < 3; ++a)
+    {
+        for (int b = 0; b < 3; ++b)
+        {
+            A[(IX_COM + a) * NX + IX_LIN + b] = q[QD_RM + a * 3 + b];
+            A[(IX_LIN + a) * NX + IX_LIN + b] = (S[a * 3 + b] == 0.0) ? 0.0 : -S[a * 3 + b];
+            A[(IX_RPY + a) * NX + IX_ANG + b] = q[QD_WI + a * 3 + b];
+            A[(IX_ANG + a) * NX + IX_ANG + b] = (S[a * 3 + b] == 0.0) ? 0.0 : -S[a * 3 + b];
+        }
+        for (int j = 0; j < NT; ++j)
+        {
+            A[(IX_LIN + a) * NX + IX_T + j] = q[QD_ALIN + a * NT + j];
+            A[(IX_ANG + a) * NX + IX_T + j] = q[QD_AANG + a * NT + j];
+        }
+        for (int b = 0; b < NJ; ++b)
+        {
+            BJ[(IX_LIN + a) * NJ + b] = q[QD_LLIN + a * NJ + b];
+            BJ[(IX_ANG + a) * NJ + b] = q[QD_LANG + a * NJ + b];
+        }
+        A[(IX_EP + a) * NX + IX_COM + a] = 1.0;
+        A[(IX_ER + a) * NX + IX_RPY + a] = 1.0;
+        c[IX_LIN + a] = q[QD_CL + a];
+        c[IX_EP + a] = q[QD_CEP + a];
+        c[IX_ER + a] = q[QD_CER + a];
+    }
+    for (int j = 0; j < NT; ++j)
+    {
+        A[(IX_T + j) * NX + IX_TD + j] = q[QD_JTT];
+        A[(IX_TD + j) * NX + IX_T + j] = q[QD_JA + j];
+        A[(IX_TD + j) * NX + IX_TD + j] = q[QD_JB + j];
+        BT[(IX_TD + j) * NT + j] = q[QD_JG + j];
+        BT[(IX_T + j) * NT + j] = q[QD_JGT];
+        c[IX_TD + j] = q[QD_CTD + j];
+    }
+}
+
+__global__ void expand_dynamics_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __restrict__ qd,
+                                       double* A, double* BJ, double* BT, double* c)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B)
+        return;
+    expand_dense(qd + (size_t)i * cfgp->qd_stride, A + (size_t)i * NX * NX, BJ + (size_t)i * NX * NJ,
+                 BT + (size_t)i * NX * NT, c + (size_t)i * NX);
+}
+
+// gradient and bounds in the reference's dense ordering (IMPCProblem.cpp:156-192)
+__global__ void expand_qp_vectors_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __restrict__ qd,
+                                         double* q, double* l, double* u)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B)
+        return;
+    const DeviceConfig& cfg = *cfgp;
+    const double* d = qd + (size_t)i * cfg.qd_stride;
+    double* qi = q + (size_t)i * cfg.n_var;
+    double* li = l + (size_t)i * cfg.n_con;
+    double* ui = u + (size_t)i * cfg.n_con;
+    const int N = cfg.N, NC = cfg.NC;
+    for (int e = 0; e < cfg.n_var; ++e)
+        qi[e] = 0.0;
+    for (int e = 0; e < cfg.n_con; ++e)
+        li[e] = ui[e] = 0.0;
+    // q[x_k] = -Q xref_{k-1}   (costsVSMPC.cpp:175-178)
+    for (int k = 1; k <= N; ++k)
+    {
+        const int col = ref_col(k - 1, cfg.Ns);
+        for (int r = 0; r < 12; ++r)
+        {
+            const double v = -cfg.Qd[r] * d[QD_XREF + r * NC + col];
+            qi[k * NX + r] = (v == 0.0) ? 0.0 : v;
+        }
+    }
+    const int base = NX * (N + 1);
+    for (int j = 0; j < cfg.Nc; ++j)
+        for (int a = 0; a < NJ; ++a)
+            qi[base + j * NJ + a] = d[QD_GQ + a];
+    const int tb = base + cfg.Nc * NJ;
+    for (int a = 0; a < NT; ++a)
+        qi[tb + a] = -cfg.w_i * d[QD_VBAR + a];
+    // bounds: dynamics rows -dt_k c ; x0 rows ; throttle rows
+    double c[NX];
+    for (int e = 0; e < NX; ++e)
+        c[e] = 0.0;
+    for (int a = 0; a < 3; ++a)
+    {
+        c[IX_LIN + a] = d[QD_CL + a];
+        c[IX_EP + a] = d[QD_CEP + a];
+        c[IX_ER + a] = d[QD_CER + a];
+    }
+    for (int j = 0; j < NT; ++j)
+        c[IX_TD + j] = d[QD_CTD + j];
+    for (int k = 0; k < N; ++k)
+        for (int r = 0; r < NX; ++r)
+        {
+            const double v = -cfg.dt[k] * c[r];
+            li[k * NX + r] = ui[k * NX + r] = v;
+        }
+    for (int r = 0; r < NX; ++r)
+        li[N * NX + r] = ui[N * NX + r] = d[QD_X0 + r];
+    const int t0 = N * NX + NX;
+    for (int b = 0; b < cfg.nblk; ++b)
+        for (int a = 0; a < NT; ++a)
+        {
+            if (b == 0 && d[QD_PINNED] != 0.0)
+                li[t0 + a] = ui[t0 + a] = d[QD_VBAR + a];
+            else
+            {
+                li[t0 + b * NT + a] = d[QD_VMIN];
+                ui[t0 + b * NT + a] = d[QD_VMAX];
+            }
+        }
+}
+
+// ---- host-side launchers ---------------------------------------------------------------------------
+cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
+                             const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
+                             int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
+                             const double* traj_rpy, const double* traj_rpyd, double* qd, cudaStream_t s)
+{
+    const size_t smem = (size_t)K1_THREADS * (h_cfg.qd_stride + 1) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        cudaFuncSetAttribute(linearise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    if (smem > 200 * 1024)
+        return cudaErrorInvalidValue;
+    const int grid = (B + K1_THREADS - 1) / K1_THREADS;
+    linearise_kernel<<<grid, K1_THREADS, smem, s>>>(d_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
+                                                    alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const double* qd, double* A, double* BJ,
+                                   double* BT, double* c, cudaStream_t s)
+{
+    expand_dynamics_kernel<<<(B + 63) / 64, 64, 0, s>>>(d_cfg, B, qd, A, BJ, BT, c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
+                                     double* u, cudaStream_t s)
+{
+    expand_qp_vectors_kernel<<<(B + 63) / 64, 64, 0, s>>>(d_cfg, B, qd, q, l, u);
+    return cudaGetLastError();
+}
+
+} // namespace vsmpc

@@ -1,0 +1,84 @@
+"""GPU parity: CUDA path (through the C-ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): optimal thrusts / joint commands within 1e-6 relative (FP64).
+The assembly quantities (A, B, c, q, l, u) are required to agree to 1e-12 relative.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_trajectories, pkg
+from oracle_driver import OracleInstance, oracle_trajectories_to_product
+
+pytestmark = pytest.mark.gpu
+
+REL_SOL = 1e-6      # north_star tolerance on the solution
+REL_ASM = 1e-12     # assembly (linearisation, gradient, bounds)
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+def make(B, solver, seed=20251002, near=0.10, params=None):
+    syn = pkg("synthetic")
+    bat = pkg("batched")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=seed, perturbed=True, near_bound_fraction=near)
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=solver)
+    return mpc, nom, per, traj
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_linearise_matches_oracle(solver):
+    B = 24
+    mpc, nom, per, traj = make(B, solver)
+    mpc.configure(nom)
+    mpc.update(per)
+    A, BJ, BT, c, dt = mpc.get_dynamics()
+    q, l, u = mpc.get_qp_vectors()
+    for i in range(B):
+        o = OracleInstance(nom, i, trajectories=traj)
+        o.update(per)
+        oA, oBJ, oBT, oc, odt = o.dynamics()
+        assert rel_err(A[i], oA) < REL_ASM
+        assert rel_err(BJ[i], oBJ) < REL_ASM
+        assert rel_err(BT[i], oBT) < REL_ASM
+        assert rel_err(c[i], oc) < REL_ASM
+        assert rel_err(dt, odt) < 1e-15
+        assert rel_err(q[i], o.mpc.gradient) < REL_ASM
+        assert rel_err(l[i], o.mpc.lowerBound) < REL_ASM
+        assert rel_err(u[i], o.mpc.upperBound) < REL_ASM
+    mpc.close()
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("free_tick", [False, True])
+def test_solve_matches_exact_oracle(solver, free_tick):
+    B = 32
+    mpc, nom, per, traj = make(B, solver, near=0.3)
+    mpc.configure(nom)
+    if free_tick:
+        mpc.debug_set_counters(-1, 19)   # next tick releases throttle block 0
+    mpc.update(per)
+    mpc.solveMPC()
+    z = mpc.getSolution()
+    out, status = mpc.get_output()
+    nf, ns = mpc.get_counts()
+    assert (status == 0).all()
+    n_active = 0
+    for i in range(B):
+        o = OracleInstance(nom, i, trajectories=traj)
+        if free_tick:
+            o.mpc.vectorConstraints[2].counter = 19
+        o.update(per)
+        zo = o.solve()
+        n_active += o.mpc.solveInfo["n_active"]
+        assert rel_err(z[i], zo) < REL_SOL, (i, rel_err(z[i], zo))
+        row = o.output_row()
+        assert rel_err(out[i], row) < REL_SOL
+        # inputs alone (thrusts / joint commands), scaled by their own magnitude
+        assert rel_err(z[i, 468:], zo[468:]) < REL_SOL
+    assert n_active > 0, "test workload should exercise the active-set path"
+    assert (nf == 1).all() and (ns >= 1).all()
+    mpc.close()
