@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the batched multi-rate MPC hot path (BASELINE.json: "MPC solves/sec").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
+
+One *step* = one controller tick of a batch of B = 1024 independent MPC instances per GPU
+(BASELINE.json configs[1]: perturbed initial states, reference horizon 17 knots and the
+variable-sampling grid): linearise kernel + structured QP kernel + output extraction.
+
+* ``value``  : solves/s with the input packs already resident in HBM (CUDA-event timed on the
+               launching stream, L2 flushed between steps, max over ranks).
+* ``e2e``    : the same metric through the public C-ABI call sequence with HOST buffers:
+               vsmpc_set_state (H2D from pinned memory + K1) -> vsmpc_solve (K2) -> vsmpc_get_output (D2H).
+* ``roofline``: FP64 (CUDA-core DFMA) roofline of the QP kernel: algorithmic flops per SURVEY §8(d)
+               (F = F_l + n_f F_f + n_s F_s at (nx,nu,N) = (30,12,17)) over the kernel's own CUDA-event
+               time, against the DFMA peak measured on this device in the same run.
+* ``cpu_baseline``: the oracle port timed on this box's host cores on a bounded sample.
+
+Multi-GPU: instances are independent — each rank owns its own batch (weak scaling), no collective in
+the data path; results are only gathered (timing max over ranks).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub_b200"
+METRIC = "MPC solves/sec (batched)"
+B_PER_GPU = 1024
+
+
+def pkg(sub=""):
+    return importlib.import_module(PKG + (("." + sub) if sub else ""))
+
+
+# ---- algorithmic flop model, SURVEY.md §8(d) / BASELINE.md §5 --------------------------------------
+def flops_per_solve(nx, nu, N, n_f, n_s):
+    F_f = N * (7.0 / 3.0 * nx ** 3 + 4 * nx ** 2 * nu + 2 * nx * nu ** 2 + nu ** 3 / 3.0)
+    F_s = N * (8 * nx ** 2 + 8 * nx * nu + 2 * nu ** 2)
+    F_l = 4000 + 2 * N * (nx ** 2 + nx * nu + nx)
+    return F_l + n_f * F_f + n_s * F_s, dict(F_f=F_f, F_s=F_s, F_l=F_l)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self._stop.is_set():
+                    break
+                self.samples.append([s.strip() for s in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for n, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_traj():
+    return pkg("config").load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+
+
+def make_workload(B, seed, n_sets):
+    """n_sets distinct perturbed packs (SURVEY §8(d) Config 2) + the nominal configure pack."""
+    syn, pack = pkg("synthetic"), pkg("pack")
+    nom = syn.make_states(B, perturbed=False)
+    packs = [pack.build_pack(syn.make_states(B, seed=seed + 7919 * j, perturbed=True)) for j in range(n_sets)]
+    jp = np.ascontiguousarray(nom["joint_pos"][:, pack.DEFAULT_JOINT_SELECTOR].T)
+    return pack.build_pack(nom), jp, packs
+
+
+# =====================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    bat, L = pkg("batched"), pkg("_lib")
+    lib = L.load()
+    B = args.batch
+    K, Wm = args.steps, args.warmup
+    n_sets = 4
+    nom_pack, jp, packs = make_workload(B, 20251002 + rank, n_sets)
+    mpc = bat.BatchedVSMPC(B, None, load_traj(), device=local_rank, solver=args.solver)
+    stream = torch.cuda.Stream(device=dev)   # an explicit stream: events and kernels share it
+    torch.cuda.set_stream(stream)
+    mpc.set_stream(stream.cuda_stream)
+    # stagger the 20-tick phase so that every step has the steady-state mix of pinned / released ticks
+    phase0 = (np.arange(B) % 20).astype(np.int32)
+    mpc.configure_pack(nom_pack, jp, phase0)
+    d_packs = [torch.from_numpy(p).to(dev) for p in packs]
+    h_packs = [torch.from_numpy(p).pin_memory() for p in packs]
+    h_out = torch.empty((B, L.OUT_DOUBLES), dtype=torch.float64).pin_memory()
+    h_status = torch.empty((B,), dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def step_dev(j):
+        mpc.update_device_ptr(d_packs[j % n_sets].data_ptr())
+        mpc.solve_async()
+
+    def step_e2e(j):
+        mpc.update_ptr(h_packs[j % n_sets].data_ptr())
+        mpc.solve_async()
+        mpc.get_output_into(h_out.data_ptr(), h_status.data_ptr())  # blocks until the D2H copy landed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident leg -------------------------------------------------------------
+    for j in range(Wm):
+        step_dev(j)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    nf_sum = ns_sum = 0.0
+    t_wall0 = time.perf_counter()
+    for j in range(K):
+        flush.zero_()                      # L2 flush between timed iterations (outside the events)
+        e0, e1, e2 = ev[j]
+        e0.record(stream)
+        mpc.update_device_ptr(d_packs[j % n_sets].data_ptr())
+        e1.record(stream)
+        mpc.solve_async()
+        e2.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    k1_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in ev)
+    k2_ms = sum(e1.elapsed_time(e2) for _, e1, e2 in ev)
+    total_ms = sum(e0.elapsed_time(e2) for e0, _, e2 in ev)
+    nf, ns = mpc.get_counts()
+    _, status = mpc.get_output()
+    solved_frac = float((status == 0).mean())
+    # ---------------- end-to-end leg (host buffers through the C-ABI) -----------------------------------
+    for j in range(Wm):
+        step_e2e(j)
+    barrier()
+    e2e_s = 0.0
+    for j in range(K):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e(j)
+        e2e_s += time.perf_counter() - t0
+    barrier()
+    sampler.stop()
+    # ---------------- reduce over ranks: max time --------------------------------------------------------
+    t = torch.tensor([total_ms, e2e_s * 1e3, k1_ms, k2_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, k1_ms, k2_ms = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * B * K / (total_ms * 1e-3)
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    # ---------------- roofline of the QP kernel -----------------------------------------------------------
+    import ctypes
+    tf = ctypes.c_double(0.0)
+    lib.vsmpc_microbench_fp64(local_rank, 0, ctypes.byref(tf))
+    tf_dmma = ctypes.c_double(0.0)
+    lib.vsmpc_microbench_fp64(local_rank, 1, ctypes.byref(tf_dmma))
+    nf_mean, ns_mean = float(nf.mean()), float(ns.mean())
+    F, parts = flops_per_solve(30, 12, 17, nf_mean, ns_mean)
+    k2_s_per_launch = k2_ms * 1e-3 / K
+    achieved = F * B / k2_s_per_launch / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("qp_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+                "frac": achieved / tf.value if tf.value > 0 else None, "traffic": traffic,
+                "kernel": "qp_structured_kernel" if args.solver == 0 else "qp_generic_kernel",
+                "peak_source": "DFMA microbenchmark on this device in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                "dmma_peak_tflops": tf_dmma.value,
+                "flops_per_solve": F, "n_factor_mean": nf_mean, "n_solve_mean": ns_mean,
+                "kernel_ms_per_launch": k2_s_per_launch * 1e3, "linearise_ms_per_launch": k1_ms / K,
+                "hbm_algorithmic_bytes_per_solve": 359 * 8 + 54 * 8,
+                "hbm_gbs_at_value": value * (359 * 8 + 54 * 8) / 1e9}
+    cpu = cpu_baseline(sample_solves=args.cpu_sample)
+    line = {
+        "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch of 1024 independent MPC solves per GPU, reference horizon "
+                               "(17 knots, 7 fine + 10 coarse), perturbed states (SURVEY §8d Config 2)",
+                   "instances_per_gpu": B, "n_var": mpc.n_var, "n_con": mpc.n_con,
+                   "l2": "flushed (256 MiB memset) between timed steps", "pack_sets": n_sets,
+                   "solver": "structured" if args.solver == 0 else "generic-dense",
+                   "phase": "20-tick phase staggered across instances"},
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(packs[0].nbytes),
+                "d2h_bytes_per_step": int(h_out.numel() * 8 + h_status.numel() * 4),
+                "ms_per_step": e2e_ms / K, "timing": "host perf_counter around set_state+solve+get_output, synchronized"},
+        "gpu_launches": 2 * K,
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        "solved_fraction": solved_frac, "wall_ms_timed_loop": t_wall * 1e3,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =====================================================================================================
+def cpu_baseline(sample_solves=24, threads=None):
+    """Oracle ("port") timed on the host: per-instance update + solve, bounded sample."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_driver import OracleInstance  # noqa
+        from helpers import load_trajectories  # noqa
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+    try:
+        from oracle import cbaseline  # C restatement (OSQP-style ADMM) if built
+        return cbaseline.time_baseline(sample_solves=max(sample_solves, 256), threads=threads)
+    except Exception:
+        pass
+    syn = pkg("synthetic")
+    n = sample_solves
+    nom = syn.make_states(n, perturbed=False)
+    per = syn.make_states(n, perturbed=True)
+    traj = load_trajectories()
+    inst = [OracleInstance(nom, i, trajectories=traj) for i in range(n)]
+    t0 = time.perf_counter()
+    for o in inst:
+        o.update(per)
+        o.solve()
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "solves/s", "cores": 1, "kind": "port",
+            "sample": f"{n} instances of the same workload, NumPy/SciPy oracle (dense assembly + exact sparse-KKT active set), 1 thread"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, Wm = args.steps, args.warmup
+    cores = os.cpu_count() or 1
+    per_step = max(8, args.cpu_sample)
+    vals = []
+    res = None
+    for j in range(Wm + K):
+        res = cpu_baseline(sample_solves=per_step, threads=cores)
+        if j >= Wm:
+            vals.append(res["value"])
+    value = float(np.mean(vals))
+    res = dict(res)
+    res["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": Wm,
+            "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1] sample: same synthetic instances, CPU restatement of the reference path",
+                       "instances_per_step": per_step},
+            "cpu_baseline": res,
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--solver", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=24)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

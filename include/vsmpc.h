@@ -168,6 +168,10 @@ int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve);
  * ThrottleConstraint::m_counter) of every instance; -1 leaves a counter unchanged */
 int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter);
 
+/* measured FP64 throughput of `device` in TFLOP/s: kind 0 = DFMA on the CUDA cores, kind 1 = DMMA
+ * (mma.sync.m8n8k4.f64).  Used as the roofline denominator of the QP kernel (bench.py). */
+int vsmpc_microbench_fp64(int device, int kind, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

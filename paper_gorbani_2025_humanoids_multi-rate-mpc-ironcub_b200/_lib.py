@@ -47,7 +47,7 @@ EXPORTS = [
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
     "vsmpc_get_output_device", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
-    "vsmpc_get_counts", "vsmpc_debug_set_counters",
+    "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_microbench_fp64",
 ]
 
 _lib = None
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.vsmpc_get_qp_vectors.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_get_counts.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
+    lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]
     for f in EXPORTS:
         if f != "vsmpc_last_error":
             getattr(lib, f).restype = C.c_int
