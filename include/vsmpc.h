@@ -152,7 +152,10 @@ int vsmpc_wait(vsmpc_handle* h);
 int vsmpc_get_output(vsmpc_handle* h, double* out_rows_host, int* status_host);
 /* device pointers of the same buffers (valid for the handle's lifetime) */
 int vsmpc_get_output_device(vsmpc_handle* h, double** out_rows_dev, int** status_dev);
-/* IMPCProblem::getSolution: double[B][n_var] */
+/* IMPCProblem::getSolution: double[B][n_var].  The full 588-vector is optional output: the controller
+ * only consumes the getters above, so the structured kernel skips it unless enabled here (when
+ * disabled vsmpc_get_full_solution returns VSMPC_ERR_STATE). */
+int vsmpc_set_full_solution(vsmpc_handle* h, int enable);
 int vsmpc_get_full_solution(vsmpc_handle* h, double* z_host);
 
 /* ---- inner seams, separately callable for parity tests -------------------------- */

@@ -46,7 +46,7 @@ EXPORTS = [
     "vsmpc_create", "vsmpc_destroy", "vsmpc_last_error", "vsmpc_set_stream", "vsmpc_n_var",
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
-    "vsmpc_get_output_device", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
+    "vsmpc_get_output_device", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
     "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_microbench_fp64",
 ]
 
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
         getattr(lib, f).argtypes = [H]
     lib.vsmpc_get_output.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.vsmpc_get_output_device.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.vsmpc_set_full_solution.argtypes = [H, C.c_int]
     lib.vsmpc_get_full_solution.argtypes = [H, C.c_void_p]
     lib.vsmpc_get_dynamics.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_get_qp_vectors.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]

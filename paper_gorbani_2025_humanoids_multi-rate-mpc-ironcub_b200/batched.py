@@ -74,7 +74,7 @@ class BatchedVSMPC:
     """B independent MPC instances on one GPU."""
 
     def __init__(self, n_instances: int, params: dict | None, trajectories: dict, device: int = 0,
-                 solver: int = 0):
+                 solver: int = 0, full_solution: bool = False):
         self._lib = L.load()
         self.B = int(n_instances)
         self.params = dict(default_params())
@@ -94,6 +94,7 @@ class BatchedVSMPC:
         self.n_con = self._lib.vsmpc_n_constraints(h)
         self.sel = list(DEFAULT_JOINT_SELECTOR)
         self.device = int(device)
+        self._ck(self._lib.vsmpc_set_full_solution(h, 1 if full_solution else 0), "vsmpc_set_full_solution")
 
     # ---- lifecycle -------------------------------------------------------------------------------
     def close(self):

@@ -27,7 +27,7 @@ cudaError_t launch_qp_generic(const DeviceConfig* d_cfg, const DeviceConfig& h_c
 size_t structured_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_structured(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                  double* ws, double* scratch, double* z, double* st, double* out_rows, int* status,
-                                 int* n_factor, int* n_solve, cudaStream_t s);
+                                 int* n_factor, int* n_solve, int want_z, cudaStream_t s);
 } // namespace vsmpc
 
 using namespace vsmpc;
@@ -41,6 +41,7 @@ struct vsmpc_handle
     int solver = 0;
     bool configured = false;
     bool has_state = false;
+    bool want_full = false;   // write the full primal (IMPCProblem::getSolution) every solve
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     // device buffers
@@ -361,7 +362,7 @@ int vsmpc_solve_async(vsmpc_handle* h)
                              h->d_status, h->d_nf, h->d_ns, h->stream));
     else
         CK(launch_qp_structured(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
-                                h->d_status, h->d_nf, h->d_ns, h->stream));
+                                h->d_status, h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
     h->has_state = false; // one solve per update, like the reference's tick
     return VSMPC_OK;
 }
@@ -405,10 +406,20 @@ int vsmpc_get_output_device(vsmpc_handle* h, double** out_rows_dev, int** status
     return VSMPC_OK;
 }
 
+int vsmpc_set_full_solution(vsmpc_handle* h, int enable)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    h->want_full = enable != 0;
+    return VSMPC_OK;
+}
+
 int vsmpc_get_full_solution(vsmpc_handle* h, double* z_host)
 {
     if (!h || h->B <= 0 || !z_host)
         return VSMPC_ERR_ARG;
+    if (h->solver != 1 && !h->want_full)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_get_full_solution: enable it first with vsmpc_set_full_solution(h, 1)");
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(z_host, h->d_z, (size_t)h->cfg.n_var * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

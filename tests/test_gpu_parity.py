@@ -19,13 +19,13 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
-def make(B, solver, seed=20251002, near=0.10, params=None):
+def make(B, solver, seed=20251002, near=0.10, params=None, full=True):
     syn = pkg("synthetic")
     bat = pkg("batched")
     traj = load_trajectories()
     nom = syn.make_states(B, perturbed=False)
     per = syn.make_states(B, seed=seed, perturbed=True, near_bound_fraction=near)
-    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=solver)
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=solver, full_solution=full)
     return mpc, nom, per, traj
 
 
@@ -81,4 +81,28 @@ def test_solve_matches_exact_oracle(solver, free_tick):
         assert rel_err(z[i, 468:], zo[468:]) < REL_SOL
     assert n_active > 0, "test workload should exercise the active-set path"
     assert (nf == 1).all() and (ns >= 1).all()
+    mpc.close()
+
+
+@pytest.mark.parametrize("free_tick", [False, True])
+def test_outputs_without_full_solution(free_tick):
+    """Default mode of the structured kernel: outputs by superposition, no 588-vector written."""
+    B = 48
+    mpc, nom, per, traj = make(B, 0, near=0.3, full=False)
+    mpc.configure(nom)
+    if free_tick:
+        mpc.debug_set_counters(-1, 19)
+    mpc.update(per)
+    mpc.solveMPC()
+    out, status = mpc.get_output()
+    assert (status == 0).all()
+    with pytest.raises(Exception):
+        mpc.getSolution()
+    for i in range(B):
+        o = OracleInstance(nom, i, trajectories=traj)
+        if free_tick:
+            o.mpc.vectorConstraints[2].counter = 19
+        o.update(per)
+        o.solve()
+        assert rel_err(out[i], o.output_row()) < REL_SOL, (i, rel_err(out[i], o.output_row()))
     mpc.close()

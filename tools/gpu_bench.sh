@@ -1,3 +1,4 @@
 set -x
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 --solver 1 2>&1 | tail -2
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -15
+python bench.py --steps 30 --warmup 3 --solver 0 --cpu-sample 8 2>&1 | tail -1
+python bench.py --steps 30 --warmup 3 --solver 0 --batch 16384 --cpu-sample 8 2>&1 | tail -1
