@@ -1,8 +1,7 @@
 // K1 — linearise + discretise-prep kernel (sm_100a, FP64 CUDA cores).
 //
-// One thread per MPC instance.  Reads the structure-of-arrays pack (fully coalesced: consecutive
-// threads read consecutive doubles of each pack row) and the per-instance persistent state, and
-// replaces, for one controller tick, the host work of
+// One warp per MPC instance.  Reads the instance's column of the structure-of-arrays pack into shared
+// memory, splits the work across the lanes and replaces, for one controller tick, the host work of
 //   IMPCProblem::update                       MPC/src/IMPCProblem/IMPCProblem.cpp:150-194
 //     ReferenceTrackingCost::compute...       MPC/src/variableSamplingMPC/costsVSMPC.cpp:121-181
 //     ThrottleInitialValueCost::compute...    costsVSMPC.cpp:468-487
@@ -13,8 +12,8 @@
 //     ThrottleConstraint::compute...          constraintsVSMPC.cpp:338-374
 // It emits the ~120 structural nonzeros of (A, B_J, B_T, c) instead of the reference's dense
 // 512x588 constraint matrix; the per-knot dt scaling (constraintsVSMPC.cpp:76-131) is applied by
-// the QP kernel on the fly.  The instance-major QP data block is staged through shared memory so
-// that the global stores are coalesced.
+// the QP kernel on the fly.  The instance-major QP data block is staged in shared memory and written
+// with coalesced stores.
 #include "vsmpc_common.cuh"
 
 namespace vsmpc
@@ -118,10 +117,54 @@ __device__ __forceinline__ void W_of_rpy(const double* rpy, double* W)
     W[6] = 0.0; W[7] = -s0; W[8] = c0 * c1;
 }
 
-constexpr int K1_THREADS = 64;
+constexpr int K1_WARPS = 4; // instances per CTA (one warp each)
 
+// (X^T M_b X).block(3,3,3,3) from the pack row staged in shared memory
+__device__ __forceinline__ void locked_inertia_sm(const double* __restrict__ pk, const double* R, double* I3)
+{
+    double r[3], Sr[9], SR[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        r[a] = pk[VSMPC_PK_P_COM + a] - pk[VSMPC_PK_BASE_POS + a];
+    skew3(r, Sr);
+    mat3_mul(Sr, R, SR);
+    double MX[18];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += pk[VSMPC_PK_MB + a * 6 + b] * SR[b * 3 + c];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += pk[VSMPC_PK_MB + a * 6 + 3 + b] * R[b * 3 + c];
+            MX[a * 3 + c] = s;
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += SR[b * 3 + a] * MX[b * 3 + c];
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                s += R[b * 3 + a] * MX[(3 + b) * 3 + c];
+            I3[a * 3 + c] = s;
+        }
+}
+
+// One warp per MPC instance.  The instance's pack column (359 doubles, strided by B in the SoA buffer)
+// is staged in shared memory, the lanes split the work (lane = 8*jet + joint for the Lambda matrices,
+// one lane per jet / per state entry elsewhere), and the instance-major QP data block is written back
+// with fully coalesced stores.
 // mode 0: update tick.  mode 1: configure (initialise persistent state, then run tick 0).
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(32 * K1_WARPS)
 linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
                  const double* __restrict__ pack, const double* __restrict__ joint_pos_sel,
                  const int* __restrict__ phase0, double* __restrict__ st, int* __restrict__ si,
@@ -129,345 +172,345 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
                  const double* __restrict__ traj_vel, const double* __restrict__ traj_rpy,
                  const double* __restrict__ traj_rpyd, double* __restrict__ qd)
 {
-    extern __shared__ double stage[]; // [K1_THREADS][qd_stride + 1]
+    extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12]
     const DeviceConfig& cfg = *cfgp;
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x * K1_THREADS + tid;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * K1_WARPS + warp;
+    if (i >= B)
+        return;
     const int NC = cfg.NC;
-    const int ld = cfg.qd_stride + 1;
-    double* out = stage + (size_t)tid * ld;
+    const int per_warp = 360 + cfg.qd_stride + 12;
+    double* pk = k1_smem + (size_t)warp * per_warp;
+    double* out = pk + 360;
+    double* colbuf = out + cfg.qd_stride;
     const size_t Bs = (size_t)B;
-#define PK(f) pack[(size_t)(f) * Bs + i]
 #define ST(f) st[(size_t)(f) * Bs + i]
 #define SI(f) si[(size_t)(f) * Bs + i]
-    if (i < B)
-    {
-        const Jet jet{cfg.jc, cfg.jn};
-        double R[9], rpy[3], pcom[3];
+    for (int f = lane; f < VSMPC_PACK_DOUBLES; f += 32)
+        pk[f] = pack[(size_t)f * Bs + i];
+    __syncwarp();
+    const Jet jet{cfg.jc, cfg.jn};
+    double R[9], rpy[3], pcom[3];
 #pragma unroll
-        for (int a = 0; a < 9; ++a)
-            R[a] = PK(VSMPC_PK_WRB + a);
+    for (int a = 0; a < 9; ++a)
+        R[a] = pk[VSMPC_PK_WRB + a];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        rpy[a] = pk[VSMPC_PK_RPY + a];
+        pcom[a] = pk[VSMPC_PK_P_COM + a];
+    }
+    const double mass = pk[VSMPC_PK_MASS];
+    double I3[9], W[9];
+    locked_inertia_sm(pk, R, I3);
+    W_of_rpy(rpy, W);
+
+    // new reference-window column at trajectory index idx (costsVSMPC.cpp:105-112,132-149) -> colbuf
+    auto ref_column = [&](int idx, const double* pinit, const double* rinit) {
+        double vel[3], rd[3], mv[3], Wr[3], col[12];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
         {
-            rpy[a] = PK(VSMPC_PK_RPY + a);
-            pcom[a] = PK(VSMPC_PK_P_COM + a);
+            col[a] = pinit[a] + traj_pos[3 * idx + a];
+            vel[a] = traj_vel[3 * idx + a];
+            col[6 + a] = rinit[a] + traj_rpy[3 * idx + a];
+            rd[a] = traj_rpyd[3 * idx + a];
+            mv[a] = mass * vel[a];
         }
-        const double mass = PK(VSMPC_PK_MASS);
-        double I3[9], W[9];
-        locked_inertia(pack, B, i, R, I3);
-        W_of_rpy(rpy, W);
-
-        // new reference-window column at trajectory index idx (costsVSMPC.cpp:105-112,132-149)
-        auto ref_column = [&](int idx, const double* pinit, const double* rinit, double* col) {
-            double vel[3], rd[3], mv[3], Wr[3];
+        mat3T_vec(R, mv, col + 3);
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-            {
-                col[a] = pinit[a] + traj_pos[3 * idx + a];
-                vel[a] = traj_vel[3 * idx + a];
-                col[6 + a] = rinit[a] + traj_rpy[3 * idx + a];
-                rd[a] = traj_rpyd[3 * idx + a];
-                mv[a] = mass * vel[a];
-            }
-            mat3T_vec(R, mv, col + 3);
+        for (int a = 0; a < 3; ++a)
+            Wr[a] = W[a * 3] * rd[0] + W[a * 3 + 1] * rd[1] + W[a * 3 + 2] * rd[2];
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-                Wr[a] = W[a * 3] * rd[0] + W[a * 3 + 1] * rd[1] + W[a * 3 + 2] * rd[2];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-                col[9 + a] = I3[a * 3] * Wr[0] + I3[a * 3 + 1] * Wr[1] + I3[a * 3 + 2] * Wr[2];
-        };
-
-        if (mode == 1)
+        for (int a = 0; a < 3; ++a)
+            col[9 + a] = I3[a * 3] * Wr[0] + I3[a * 3 + 1] * Wr[1] + I3[a * 3 + 2] * Wr[2];
+        if (lane == 0)
         {
-            // configureDynVectorsSize of the costs/constraints (costsVSMPC.cpp:74-119,
-            // constraintsVSMPC.cpp:184-204,326-336; systemDynamicsVSMPC.cpp:67; variableSamplingMPC.cpp:60)
-            double col[12];
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
-            {
-                ST(ST_P_INIT + a) = pcom[a];
-                ST(ST_RPY_INIT + a) = rpy[a];
-                ST(ST_RPY_OLD + a) = rpy[a];
-                ST(ST_NTURNS + a) = 0.0;
-                ST(ST_P_REF + a) = 0.0;
-                ST(ST_RPY_REF + a) = 0.0;
-            }
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-                ST(ST_MOM_REF + a) = 0.0;
+            for (int a = 0; a < 12; ++a)
+                colbuf[a] = col[a];
+        }
+        __syncwarp();
+    };
+
+    int rc, tc, aidx, ridx;
+    if (mode == 1)
+    {
+        // configureDynVectorsSize of the costs/constraints (costsVSMPC.cpp:74-119,
+        // constraintsVSMPC.cpp:184-204,326-336; systemDynamicsVSMPC.cpp:67; variableSamplingMPC.cpp:60)
+        if (lane < 3)
+        {
+            ST(ST_P_INIT + lane) = pcom[lane];
+            ST(ST_RPY_INIT + lane) = rpy[lane];
+            ST(ST_RPY_OLD + lane) = rpy[lane];
+            ST(ST_NTURNS + lane) = 0.0;
+            ST(ST_P_REF + lane) = 0.0;
+            ST(ST_RPY_REF + lane) = 0.0;
+        }
+        if (lane < 6)
+            ST(ST_MOM_REF + lane) = 0.0;
+        if (lane == 0)
             ST(ST_ALPHA) = 0.0;
-#pragma unroll
-            for (int a = 0; a < NJ; ++a)
-            {
-                const double q0 = joint_pos_sel[(size_t)a * Bs + i];
-                ST(ST_QREF0 + a) = q0;
-                ST(ST_QACC + a) = q0;
-            }
-            ref_column(0, pcom, rpy, col);
-            for (int r = 0; r < 12; ++r)
-                for (int c = 0; c < NC; ++c)
-                    ST(ST_WIN + r * NC + c) = col[r];
-            const int ph = phase0 ? phase0[i] : 0;
-            // both 20-tick counters start at ratio-1 (costsVSMPC.cpp:118, constraintsVSMPC.cpp:335)
-            SI(SI_REF_COUNTER) = (cfg.ratio - 1 + ph) % cfg.ratio;
-            SI(SI_THR_COUNTER) = (cfg.ratio - 1 + ph) % cfg.ratio;
-            SI(SI_ALPHA_IDX) = 0;
-            SI(SI_REF_IDX) = 0;
-        }
-
-        // ---------------- costs (evaluated before the constraints, IMPCProblem.cpp:157-192) ---------
+        if (lane < NJ)
         {
-            int rc = SI(SI_REF_COUNTER);
-            if (rc == cfg.ratio - 1)
-            {
-                int idx = SI(SI_REF_IDX);
-                if (idx < cfg.traj_len - 1) // TrajectoryManager::advanceTrajectory, TrajectoryManager.cpp:142-153
-                    idx++;
-                SI(SI_REF_IDX) = idx;
-                double pinit[3], rinit[3], col[12];
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-                {
-                    pinit[a] = ST(ST_P_INIT + a);
-                    rinit[a] = ST(ST_RPY_INIT + a);
-                }
-                ref_column(idx, pinit, rinit, col);
-                for (int r = 0; r < 12; ++r)
-                {
-                    for (int c = 0; c + 1 < NC; ++c)
-                        ST(ST_WIN + r * NC + c) = ST(ST_WIN + r * NC + c + 1);
-                    ST(ST_WIN + r * NC + NC - 1) = col[r];
-                }
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-                {
-                    ST(ST_P_REF + a) = ST(ST_WIN + (0 + a) * NC);
-                    ST(ST_RPY_REF + a) = ST(ST_WIN + (6 + a) * NC);
-                    ST(ST_MOM_REF + a) = ST(ST_WIN + (3 + a) * NC);
-                    ST(ST_MOM_REF + 3 + a) = ST(ST_WIN + (9 + a) * NC);
-                }
-                rc = 0;
-            }
-            else
-                rc++;
-            SI(SI_REF_COUNTER) = rc;
+            const double q0 = joint_pos_sel[(size_t)lane * Bs + i];
+            ST(ST_QREF0 + lane) = q0;
+            ST(ST_QACC + lane) = q0;
         }
-        for (int r = 0; r < 12; ++r)
-            for (int c = 0; c < NC; ++c)
-                out[QD_XREF + r * NC + c] = ST(ST_WIN + r * NC + c);
-
-        double uprev[NT], vbar[NT];
+        ref_column(0, pcom, rpy);
+        for (int e = lane; e < 12 * NC; e += 32)
+            ST(ST_WIN + e) = colbuf[e / NC];
+        const int ph = phase0 ? phase0[i] : 0;
+        // both 20-tick counters start at ratio-1 (costsVSMPC.cpp:118, constraintsVSMPC.cpp:335)
+        rc = tc = (cfg.ratio - 1 + ph) % cfg.ratio;
+        aidx = ridx = 0;
+        __syncwarp();
+    }
+    else
+    {
+        rc = SI(SI_REF_COUNTER);
+        tc = SI(SI_THR_COUNTER);
+        aidx = SI(SI_ALPHA_IDX);
+        ridx = SI(SI_REF_IDX);
+    }
+    double pinit[3], rinit[3];
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
+    for (int a = 0; a < 3; ++a)
+    {
+        pinit[a] = (mode == 1) ? pcom[a] : ST(ST_P_INIT + a);
+        rinit[a] = (mode == 1) ? rpy[a] : ST(ST_RPY_INIT + a);
+    }
+    // ---------------- costs (evaluated before the constraints, IMPCProblem.cpp:157-192) -------------
+    const bool shift = rc == cfg.ratio - 1; // ReferenceTrackingCost, costsVSMPC.cpp:124-165
+    if (shift)
+    {
+        if (ridx < cfg.traj_len - 1) // TrajectoryManager::advanceTrajectory, TrajectoryManager.cpp:142-153
+            ridx++;
+        ref_column(ridx, pinit, rinit);
+        rc = 0;
+    }
+    else
+        rc++;
+    {
+        // window entries of this lane: read (shifted) sources first, then write
+        double wv[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
         {
-            uprev[j] = PK(VSMPC_PK_THROTTLE_PREV + j);
-            vbar[j] = jet.v(jet.stdU(uprev[j]));
-            out[QD_VBAR + j] = vbar[j];
+            const int e = lane + 32 * t;
+            wv[t] = 0.0;
+            if (e < 12 * NC)
+            {
+                const int r = e / NC, cidx = e - r * NC;
+                if (shift)
+                    wv[t] = (cidx + 1 < NC) ? ST(ST_WIN + e + 1) : colbuf[r];
+                else
+                    wv[t] = ST(ST_WIN + e);
+            }
         }
+        for (int e = lane + 160; e < 12 * NC; e += 32) // horizons with more than 13 reference columns
+        {
+            const int r = e / NC, cidx = e - r * NC;
+            const double v = shift ? ((cidx + 1 < NC) ? ST(ST_WIN + e + 1) : colbuf[r]) : ST(ST_WIN + e);
+            out[QD_XREF + e] = v;
+        }
+        __syncwarp();
 #pragma unroll
-        for (int a = 0; a < NJ; ++a)
-            out[QD_GQ + a] = cfg.w_reg_q * (PK(VSMPC_PK_Q_CMD + a) - ST(ST_QREF0 + a));
-
-        // ---------------- dynamics ---------------------------------------------------------------------
+        for (int t = 0; t < 5; ++t)
+        {
+            const int e = lane + 32 * t;
+            if (e < 12 * NC)
+            {
+                out[QD_XREF + e] = wv[t];
+                if (shift)
+                    ST(ST_WIN + e) = wv[t];
+            }
+        }
+        if (shift)
+            for (int e = lane + 160; e < 12 * NC; e += 32)
+                ST(ST_WIN + e) = out[QD_XREF + e];
+        __syncwarp();
+    }
+    if (shift && lane < 3)
+    { // publish the references into "QPInput" (costsVSMPC.cpp:155-160)
+        ST(ST_P_REF + lane) = out[QD_XREF + (0 + lane) * NC];
+        ST(ST_RPY_REF + lane) = out[QD_XREF + (6 + lane) * NC];
+        ST(ST_MOM_REF + lane) = out[QD_XREF + (3 + lane) * NC];
+        ST(ST_MOM_REF + 3 + lane) = out[QD_XREF + (9 + lane) * NC];
+    }
+    __syncwarp();
+    double pref[3], rref[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        pref[a] = ST(ST_P_REF + a);
+        rref[a] = ST(ST_RPY_REF + a);
+    }
+    if (lane < NT) // ThrottleInitialValueCost gradient, costsVSMPC.cpp:479-485
+        out[QD_VBAR + lane] = jet.v(jet.stdU(pk[VSMPC_PK_THROTTLE_PREV + lane]));
+    if (lane < NJ) // JointPositionRegularizationCost gradient, costsVSMPC.cpp:574-590
+        out[QD_GQ + lane] = cfg.w_reg_q * (pk[VSMPC_PK_Q_CMD + lane] - ST(ST_QREF0 + lane));
+    // ---------------- dynamics ---------------------------------------------------------------------------
+    if (lane == 0)
+    {
         double omw[3], omB[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
-            omw[a] = PK(VSMPC_PK_OMEGA_WORLD + a);
+            omw[a] = pk[VSMPC_PK_OMEGA_WORLD + a];
         mat3T_vec(R, omw, omB);
 #pragma unroll
         for (int a = 0; a < 3; ++a)
             out[QD_OMEGA + a] = omB[a];
-        { // A[rpy, angMom] = W^-1 * I^-1     (systemDynamicsVSMPC.cpp:86-87,140-147)
-            const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), t1 = tan(rpy[1]), c1 = cos(rpy[1]);
-            double Wi[9] = {1.0, s0 * t1, c0 * t1, 0.0, c0, -s0, 0.0, s0 / c1, c0 / c1};
-            double Ii[9], WI[9];
-            mat3_inv(I3, Ii);
-            mat3_mul(Wi, Ii, WI);
-#pragma unroll
-            for (int a = 0; a < 9; ++a)
-                out[QD_WI + a] = WI[a];
-        }
-        const double inv_m = 1.0 / mass;
+        // A[rpy, angMom] = W^-1 * I^-1     (systemDynamicsVSMPC.cpp:86-87,140-147)
+        const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), t1 = tan(rpy[1]), c1 = cos(rpy[1]);
+        double Wi[9] = {1.0, s0 * t1, c0 * t1, 0.0, c0, -s0, 0.0, s0 / c1, c0 / c1};
+        double Ii[9], WI[9];
+        mat3_inv(I3, Ii);
+        mat3_mul(Wi, Ii, WI);
 #pragma unroll
         for (int a = 0; a < 9; ++a)
-            out[QD_RM + a] = inv_m * R[a];
-#pragma unroll
-        for (int a = 0; a < 12; ++a)
-        {
-            out[QD_ALIN + a] = PK(VSMPC_PK_AMOM_BODY + a);
-            out[QD_AANG + a] = PK(VSMPC_PK_AMOM_BODY + 12 + a);
-        }
-        // Lambda_lin / Lambda_ang ("unfiltered", systemDynamicsVSMPC.cpp:166-186,338-346)
-        double Llin[24], Lang[24];
-#pragma unroll
-        for (int a = 0; a < 24; ++a)
-            Llin[a] = Lang[a] = 0.0;
-        double thrust[NT];
-#pragma unroll
-        for (int j = 0; j < NT; ++j)
-            thrust[j] = PK(VSMPC_PK_THRUST + j);
-        for (int j = 0; j < NT; ++j)
-        {
-            double ax[3], ar[3], ab[3], rb[3], Sa[9], Srb[9], SrSa[9];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-            {
-                ax[a] = PK(VSMPC_PK_JET_AXES + j * 3 + a);
-                ar[a] = PK(VSMPC_PK_JET_ARMS + j * 3 + a);
-            }
-            mat3T_vec(R, ax, ab);
-            mat3T_vec(R, ar, rb);
-            skew3(ab, Sa);
-            skew3(rb, Srb);
-            mat3_mul(Srb, Sa, SrSa);
-            const double T = thrust[j];
-            for (int b = 0; b < NJ; ++b)
-            {
-                double Jw[3], dl[3], Jc[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-                {
-                    Jw[a] = PK(VSMPC_PK_J_REL_ANG + (j * 3 + a) * NJ + b);
-                    dl[a] = PK(VSMPC_PK_J_JET_LIN + (j * 3 + a) * NJ + b) - PK(VSMPC_PK_J_COM + a * NJ + b);
-                }
-                mat3T_vec(R, dl, Jc); // getRelativeJacobianCoM, :208-226
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-                {
-                    const double saJc = Sa[a * 3] * Jc[0] + Sa[a * 3 + 1] * Jc[1] + Sa[a * 3 + 2] * Jc[2];
-                    const double ssJw = SrSa[a * 3] * Jw[0] + SrSa[a * 3 + 1] * Jw[1] + SrSa[a * 3 + 2] * Jw[2];
-                    const double saJw = Sa[a * 3] * Jw[0] + Sa[a * 3 + 1] * Jw[1] + Sa[a * 3 + 2] * Jw[2];
-                    Lang[a * NJ + b] -= T * saJc;
-                    Lang[a * NJ + b] -= T * ssJw;
-                    Llin[a * NJ + b] -= T * saJw;
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 24; ++a)
-        {
-            out[QD_LLIN + a] = Llin[a];
-            out[QD_LANG + a] = Lang[a];
-        }
-        { // c[linMom] = alpha_g * m * wRb^T g ; advance the alpha cursor (:307-311)
-            int aidx = SI(SI_ALPHA_IDX);
-            const double alpha = alpha_traj[aidx];
-            ST(ST_ALPHA) = alpha;
-            if (aidx < cfg.alpha_len - 1)
-                aidx++;
-            SI(SI_ALPHA_IDX) = aidx;
-            const double s = alpha * mass;
-            double g[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-                g[a] = PK(VSMPC_PK_GRAVITY + a);
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-                out[QD_CL + a] = (s * R[a]) * g[0] + (s * R[3 + a]) * g[1] + (s * R[6 + a]) * g[2];
-        }
-        double pref[3], rref[3];
+            out[QD_WI + a] = WI[a];
+        // throttle box / pin (constraintsVSMPC.cpp:338-374)
+        out[QD_PINNED] = (tc != cfg.ratio - 1) ? 1.0 : 0.0;
+        out[QD_VMIN] = jet.v(jet.stdU(cfg.throttle_min));
+        out[QD_VMAX] = jet.v(jet.stdU(cfg.throttle_max));
+        out[QD_JTT] = cfg.use_jet_dynamic ? 1.0 : 0.0;
+        out[QD_JGT] = cfg.use_jet_dynamic ? 0.0 : 1.0;
+        out[QD_JGT + 1] = out[QD_JGT + 2] = out[QD_JGT + 3] = 0.0;
+    }
+    if (lane < 9)
+        out[QD_RM + lane] = (1.0 / mass) * pk[VSMPC_PK_WRB + lane]; // 1/m * wRb (:296-297)
+    if (lane < 12)
+    {
+        out[QD_ALIN + lane] = pk[VSMPC_PK_AMOM_BODY + lane];
+        out[QD_AANG + lane] = pk[VSMPC_PK_AMOM_BODY + 12 + lane];
+    }
+    { // Lambda_lin / Lambda_ang ("unfiltered", systemDynamicsVSMPC.cpp:166-186,338-346): lane = 8*jet + joint
+        const int j = lane >> 3, b = lane & 7;
+        double ax[3], ar[3], ab[3], rb[3], Sa[9], Srb[9], SrSa[9];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
         {
-            pref[a] = ST(ST_P_REF + a);
-            rref[a] = ST(ST_RPY_REF + a);
-            out[QD_CEP + a] = -pref[a];               // :316
-            out[QD_CER + a] = -ST(ST_RPY_INIT + a);   // :100 (configure-time RPY)
+            ax[a] = pk[VSMPC_PK_JET_AXES + j * 3 + a];
+            ar[a] = pk[VSMPC_PK_JET_ARMS + j * 3 + a];
         }
-        // jets (:384-429)
-        double Tdest[NT];
+        mat3T_vec(R, ax, ab);
+        mat3T_vec(R, ar, rb);
+        skew3(ab, Sa);
+        skew3(rb, Srb);
+        mat3_mul(Srb, Sa, SrSa);
+        const double T = pk[VSMPC_PK_THRUST + j];
+        double Jw[3], dl[3], Jc[3];
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
-            Tdest[j] = PK(VSMPC_PK_THRUST_DOT_EST + j);
+        for (int a = 0; a < 3; ++a)
+        {
+            Jw[a] = pk[VSMPC_PK_J_REL_ANG + (j * 3 + a) * NJ + b];
+            dl[a] = pk[VSMPC_PK_J_JET_LIN + (j * 3 + a) * NJ + b] - pk[VSMPC_PK_J_COM + a * NJ + b];
+        }
+        mat3T_vec(R, dl, Jc); // getRelativeJacobianCoM, :208-226
+        double lin[3], ang[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            const double saJc = Sa[a * 3] * Jc[0] + Sa[a * 3 + 1] * Jc[1] + Sa[a * 3 + 2] * Jc[2];
+            const double ssJw = SrSa[a * 3] * Jw[0] + SrSa[a * 3 + 1] * Jw[1] + SrSa[a * 3 + 2] * Jw[2];
+            const double saJw = Sa[a * 3] * Jw[0] + Sa[a * 3 + 1] * Jw[1] + Sa[a * 3 + 2] * Jw[2];
+            ang[a] = -(T * saJc) - T * ssJw;
+            lin[a] = -(T * saJw);
+        }
+        // sum over the jets in the reference's order ((j0 + j1) + j2) + j3
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            double l1 = __shfl_sync(0xffffffffu, lin[a], b + 8), l2 = __shfl_sync(0xffffffffu, lin[a], b + 16),
+                   l3 = __shfl_sync(0xffffffffu, lin[a], b + 24);
+            double a1 = __shfl_sync(0xffffffffu, ang[a], b + 8), a2 = __shfl_sync(0xffffffffu, ang[a], b + 16),
+                   a3 = __shfl_sync(0xffffffffu, ang[a], b + 24);
+            if (lane < NJ)
+            {
+                out[QD_LLIN + a * NJ + b] = ((lin[a] + l1) + l2) + l3;
+                out[QD_LANG + a * NJ + b] = ((ang[a] + a1) + a2) + a3;
+            }
+        }
+    }
+    if (lane < 3)
+    { // c[linMom] = alpha_g * m * wRb^T g (:307-311) ; c[posErr], c[rpyErr]
+        const double alpha = alpha_traj[aidx];
+        const double s = alpha * mass;
+        const double g0 = pk[VSMPC_PK_GRAVITY], g1 = pk[VSMPC_PK_GRAVITY + 1], g2 = pk[VSMPC_PK_GRAVITY + 2];
+        out[QD_CL + lane] = (s * pk[VSMPC_PK_WRB + lane]) * g0 + (s * pk[VSMPC_PK_WRB + 3 + lane]) * g1
+                            + (s * pk[VSMPC_PK_WRB + 6 + lane]) * g2;
+        out[QD_CEP + lane] = -pref[lane];              // :316
+        out[QD_CER + lane] = -rinit[lane];             // :100 (configure-time RPY)
+        if (lane == 0)
+            ST(ST_ALPHA) = alpha;
+    }
+    if (aidx < cfg.alpha_len - 1)
+        aidx++;
+    if (lane < NT)
+    { // jets (:384-429)
+        const int j = lane;
+        const double thrust = pk[VSMPC_PK_THRUST + j], Tdest = pk[VSMPC_PK_THRUST_DOT_EST + j];
+        const double Tdes = pk[VSMPC_PK_THRUST_DES + j], Tddes = pk[VSMPC_PK_THRUST_DOT_DES + j];
         if (cfg.use_jet_dynamic)
         {
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-            {
-                const double Tdes = PK(VSMPC_PK_THRUST_DES + j), Tddes = PK(VSMPC_PK_THRUST_DOT_DES + j);
-                const double T = cfg.use_estimated_thrust ? thrust[j] : Tdes;
-                const double Td = cfg.use_estimated_thrust ? Tdest[j] : Tddes;
-                const double Tb = jet.stdT(T), Tdb = jet.stdTd(Td);
-                const double vu = jet.v(jet.stdU(uprev[j]));
-                const double dh_dT = jet.df_dT(Tb, Tdb) + jet.dg_dT(Tb, Tdb) * vu;
-                const double dh_dTd = jet.df_dTd(Tb, Tdb) + jet.dg_dTd(Tb, Tdb) * vu;
-                out[QD_JA + j] = dh_dT;
-                out[QD_JB + j] = dh_dTd;
-                out[QD_JG + j] = jet.g(jet.stdT(Tdes), jet.stdTd(Tddes)) * cfg.jn[1];
-                out[QD_CTD + j] = jet.f(Tb, Tdb) * cfg.jn[1] - dh_dT * T - dh_dTd * Td;
-            }
-            out[QD_JTT] = 1.0;
-            out[QD_JGT] = 0.0;
+            const double T = cfg.use_estimated_thrust ? thrust : Tdes;
+            const double Td = cfg.use_estimated_thrust ? Tdest : Tddes;
+            const double Tb = jet.stdT(T), Tdb = jet.stdTd(Td);
+            const double vu = jet.v(jet.stdU(pk[VSMPC_PK_THROTTLE_PREV + j]));
+            const double dh_dT = jet.df_dT(Tb, Tdb) + jet.dg_dT(Tb, Tdb) * vu;
+            const double dh_dTd = jet.df_dTd(Tb, Tdb) + jet.dg_dTd(Tb, Tdb) * vu;
+            out[QD_JA + j] = dh_dT;
+            out[QD_JB + j] = dh_dTd;
+            out[QD_JG + j] = jet.g(jet.stdT(Tdes), jet.stdTd(Tddes)) * cfg.jn[1];
+            out[QD_CTD + j] = jet.f(Tb, Tdb) * cfg.jn[1] - dh_dT * T - dh_dTd * Td;
         }
         else
-        {
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-                out[QD_JA + j] = out[QD_JB + j] = out[QD_JG + j] = out[QD_CTD + j] = 0.0;
-            out[QD_JTT] = 0.0;
-            out[QD_JGT] = 1.0;
-        }
-        // ---------------- initial state (constraintsVSMPC.cpp:206-247) ---------------------------------
-        {
-            const double PI = 3.14159265358979323846;
-            double unw[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-            {
-                double nt = ST(ST_NTURNS + a);
-                const double old = ST(ST_RPY_OLD + a);
-                if (rpy[a] - old > PI)
-                    nt -= 1.0;
-                else if (rpy[a] - old < -PI)
-                    nt += 1.0;
-                ST(ST_NTURNS + a) = nt;
-                ST(ST_RPY_OLD + a) = rpy[a];
-                unw[a] = rpy[a] + 2 * PI * nt;
-            }
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-            {
-                out[QD_X0 + IX_COM + a] = pcom[a];
-                out[QD_X0 + IX_LIN + a] = PK(VSMPC_PK_MOMENTUM_BODY + a);
-                out[QD_X0 + IX_RPY + a] = unw[a];
-                out[QD_X0 + IX_ANG + a] = PK(VSMPC_PK_MOMENTUM_BODY + 3 + a);
-                out[QD_X0 + IX_EP + a] = pcom[a] - pref[a];
-                out[QD_X0 + IX_ER + a] = unw[a] - rref[a];
-            }
-#pragma unroll
-            for (int j = 0; j < NT; ++j)
-            {
-                out[QD_X0 + IX_T + j] = cfg.use_estimated_thrust ? thrust[j] : PK(VSMPC_PK_THRUST_DES + j);
-                out[QD_X0 + IX_TD + j] = cfg.use_estimated_thrust ? Tdest[j] : PK(VSMPC_PK_THRUST_DOT_DES + j);
-            }
-        }
-        // ---------------- throttle box / pin (constraintsVSMPC.cpp:338-374) ----------------------------
-        {
-            int tc = SI(SI_THR_COUNTER);
-            out[QD_PINNED] = (tc != cfg.ratio - 1) ? 1.0 : 0.0;
-            tc = (tc == cfg.ratio - 1) ? 0 : tc + 1;
-            SI(SI_THR_COUNTER) = tc;
-            out[QD_VMIN] = jet.v(jet.stdU(cfg.throttle_min));
-            out[QD_VMAX] = jet.v(jet.stdU(cfg.throttle_max));
-        }
-        out[QD_JGT + 1] = out[QD_JGT + 2] = out[QD_JGT + 3] = 0.0; // padding 161..163
+            out[QD_JA + j] = out[QD_JB + j] = out[QD_JG + j] = out[QD_CTD + j] = 0.0;
+        out[QD_X0 + IX_T + j] = cfg.use_estimated_thrust ? thrust : Tdes;
+        out[QD_X0 + IX_TD + j] = cfg.use_estimated_thrust ? Tdest : Tddes;
     }
-#undef PK
+    if (lane < 3)
+    { // initial state (constraintsVSMPC.cpp:206-247) incl. RPY unwrapping
+        const double PI = 3.14159265358979323846;
+        const int a = lane;
+        double nt = (mode == 1) ? 0.0 : ST(ST_NTURNS + a);
+        const double old = (mode == 1) ? rpy[a] : ST(ST_RPY_OLD + a);
+        const double cur = pk[VSMPC_PK_RPY + a];
+        if (cur - old > PI)
+            nt -= 1.0;
+        else if (cur - old < -PI)
+            nt += 1.0;
+        ST(ST_NTURNS + a) = nt;
+        ST(ST_RPY_OLD + a) = cur;
+        const double unw = cur + 2 * PI * nt;
+        const double pc = pk[VSMPC_PK_P_COM + a];
+        out[QD_X0 + IX_COM + a] = pc;
+        out[QD_X0 + IX_LIN + a] = pk[VSMPC_PK_MOMENTUM_BODY + a];
+        out[QD_X0 + IX_RPY + a] = unw;
+        out[QD_X0 + IX_ANG + a] = pk[VSMPC_PK_MOMENTUM_BODY + 3 + a];
+        out[QD_X0 + IX_EP + a] = pc - pref[a];
+        out[QD_X0 + IX_ER + a] = unw - rref[a];
+    }
+    tc = (tc == cfg.ratio - 1) ? 0 : tc + 1;
+    if (lane == 0)
+    {
+        SI(SI_REF_COUNTER) = rc;
+        SI(SI_THR_COUNTER) = tc;
+        SI(SI_ALPHA_IDX) = aidx;
+        SI(SI_REF_IDX) = ridx;
+    }
 #undef ST
 #undef SI
-    __syncthreads();
-    // coalesced write-out of the instance-major blocks staged in shared memory
-    const int first = blockIdx.x * K1_THREADS;
-    const int nvalid = min(K1_THREADS, B - first);
-    const int stride = cfg.qd_stride;
-    for (int e = tid; e < nvalid * stride; e += K1_THREADS)
-    {
-        const int t = e / stride, r = e - t * stride;
-        qd[(size_t)first * stride + e] = stage[(size_t)t * ld + r];
-    }
+    for (int e = QD_XREF + 12 * NC + lane; e < cfg.qd_stride; e += 32)
+        out[e] = 0.0; // padding
+    __syncwarp();
+    // coalesced write-out of the instance-major block
+    double* dst = qd + (size_t)i * cfg.qd_stride;
+    for (int e = lane; e < cfg.qd_stride; e += 32)
+        dst[e] = out[e];
 }
+
 
 // ---- dense expansion for parity tests (vsmpc_get_dynamics / vsmpc_get_qp_vectors) ----------------
 __device__ void expand_dense(const double* __restrict__ q, double* A, double* BJ, double* BT, double* c)
@@ -602,7 +645,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
                              const double* traj_rpy, const double* traj_rpyd, double* qd, cudaStream_t s)
 {
-    const size_t smem = (size_t)K1_THREADS * (h_cfg.qd_stride + 1) * sizeof(double);
+    const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set)
     {
@@ -611,9 +654,9 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
     }
     if (smem > 200 * 1024)
         return cudaErrorInvalidValue;
-    const int grid = (B + K1_THREADS - 1) / K1_THREADS;
-    linearise_kernel<<<grid, K1_THREADS, smem, s>>>(d_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
-                                                    alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd);
+    const int grid = (B + K1_WARPS - 1) / K1_WARPS;
+    linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(d_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
+                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd);
     return cudaGetLastError();
 }
 

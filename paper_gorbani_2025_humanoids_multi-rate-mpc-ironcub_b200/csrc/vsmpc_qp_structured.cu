@@ -44,8 +44,9 @@ struct SolveVec
 struct StSmem
 {
     double W[NZ * LDW];          // value-function matrix (in place); later SolveVec / active-set matrix
-    double Hs[NU * NU];          // inverse of H_uu (broadcast buffer)
-    double Ks[NU * 32];          // gain columns (broadcast buffer)
+    double Hs[NU * NU];          // inverse of H_uu (broadcast buffer)        } after the factorisation these
+    double Ks[NU * 32];          // gain columns (broadcast buffer)            } 576 contiguous doubles hold the
+    double hk_pad[MAXW * MAXW - NU * NU - NU * 32]; //                           } active-set inverse (MAXW x MAXW)
     double cf[CF];
     double P0vx[NT * NX];
     double M0inv[NT * NT];
@@ -914,26 +915,21 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
             st_solve<1>(c, tab, false, nullptr, nullptr, 0, nullptr, nullptr, vo, ro, z);
             ns++;
         }
+        // ---- Goldfarb-Idnani dual active set on the throttle boxes, one variable per lane ----
+        // per-lane registers: value of variable `lane`, slot of its G column, position in the working set
         const double tol = 1e-10;
+        const bool isvar = lane >= first && lane < nvtot;
+        double v_e = lane < nvtot ? vv[lane] : 0.0;
+        int slot_e = -1, wpos_e = -1;
+        double lamW = 0.0;              // lane a < nW: multiplier of working-set position a
+        double* Minv = sm.Hs;           // inverse of the signed G_WW (ld = MAXW); Hs/Ks are dead after the factorisation
         int iters = 0;
-        double* GW = sm.W; // the active-set matrix reuses the (dead) matrix buffer between passes
-        while (true)
+        bool fail = false;
+        while (!fail)
         {
-            // most violated bound among the variables not in the working set
-            double best = -1.0;
-            int p_idx = 0x7fffffff;
-            for (int e = first + lane; e < nvtot; e += 32)
-            {
-                bool inW = false;
-                for (int a = 0; a < nW; ++a)
-                    inW = inW || (sm.W_idx[a] == e);
-                const double v = fmax(vv[e] - up, lo - vv[e]);
-                if (!inW && v > best)
-                {
-                    best = v;
-                    p_idx = e;
-                }
-            }
+            double viol = (isvar && wpos_e < 0) ? fmax(v_e - up, lo - v_e) : -1.0;
+            double best = viol;
+            int p_idx = lane;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
             {
@@ -947,9 +943,10 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
             }
             if (!(best > tol))
                 break;
-            const double s = (vv[p_idx] - up > lo - vv[p_idx]) ? 1.0 : -1.0;
+            const double v_p0 = __shfl_sync(0xffffffffu, v_e, p_idx);
+            const double s = (v_p0 - up > lo - v_p0) ? 1.0 : -1.0;
+            const double bound = s > 0 ? up : lo;
             double lam_p = 0.0;
-            bool fail = false;
             while (true)
             {
                 if (++iters > 6 * MAXW)
@@ -958,124 +955,106 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
                     fail = true;
                     break;
                 }
-                int qp = -1;
-                for (int q = 0; q < ncols; ++q)
-                    if (sm.col_of[q] == p_idx)
-                        qp = q;
+                int qp = __shfl_sync(0xffffffffu, slot_e, p_idx);
                 if (qp < 0)
                 {
-                    // lazily compute up to RMAX columns in one multi-RHS homogeneous back-solve:
-                    // the needed one plus the currently most violated variables without a column
+                    // lazily compute up to RMAX columns in one multi-RHS homogeneous back-solve: the needed
+                    // one plus the currently most violated variables that have no column yet
                     if (ncols >= MAXW)
                     {
                         stat = VSMPC_STATUS_MAX_ITER;
                         fail = true;
                         break;
                     }
-                    __syncwarp();
-                    if (lane == 0)
-                    {
-                        int cnt = 0;
-                        sm.gidx[cnt++] = p_idx;
-                        while (cnt < RMAX && ncols + cnt < MAXW)
-                        {
-                            double bv = tol;
-                            int bi = -1;
-                            for (int e = first; e < nvtot; ++e)
-                            {
-                                bool skip = false;
-                                for (int q = 0; q < ncols; ++q)
-                                    skip = skip || (sm.col_of[q] == e);
-                                for (int q = 0; q < cnt; ++q)
-                                    skip = skip || (sm.gidx[q] == e);
-                                const double v = fmax(vv[e] - up, lo - vv[e]);
-                                if (!skip && v > bv)
-                                {
-                                    bv = v;
-                                    bi = e;
-                                }
-                            }
-                            if (bi < 0)
-                                break;
-                            sm.gidx[cnt++] = bi;
-                        }
-                        for (int q = cnt; q < RMAX; ++q)
-                            sm.gidx[q] = -1;
-                        for (int q = 0; q < RMAX; ++q)
-                            sm.gval[q] = 1.0;
-                    }
-                    __syncwarp();
-                    int cnt = 0;
                     int gi[RMAX];
+                    gi[0] = p_idx;
+                    int cnt = 1;
+                    double cand = (isvar && slot_e < 0 && lane != p_idx && viol > tol) ? viol : -1.0;
+#pragma unroll
+                    for (int q = 1; q < RMAX; ++q)
+                    {
+                        double bv = cand;
+                        int bi = lane;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                        {
+                            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                            if (ov > bv || (ov == bv && oi < bi))
+                            {
+                                bv = ov;
+                                bi = oi;
+                            }
+                        }
+                        const bool take = bv > tol && ncols + cnt < MAXW;
+                        gi[q] = take ? bi : -1;
+                        cnt += take;
+                        if (take && lane == bi)
+                            cand = -1.0;
+                    }
                     double* vo[RMAX];
                     double* ro[RMAX];
 #pragma unroll
                     for (int q = 0; q < RMAX; ++q)
                     {
-                        gi[q] = sm.gidx[q];
-                        cnt += gi[q] >= 0;
                         vo[q] = vtmp + (size_t)q * nvtot;
                         ro[q] = recb + (size_t)(1 + min(ncols + q, MAXW - 1)) * NREC;
                     }
+                    if (lane < RMAX)
+                        sm.gval[lane] = 1.0;
+                    __syncwarp();
                     if (cnt == 1)
                         st_solve<1>(c, tab, true, gi, sm.gval, 0, nullptr, nullptr, vo, ro, nullptr);
                     else
                         st_solve<RMAX>(c, tab, true, gi, sm.gval, 0, nullptr, nullptr, vo, ro, nullptr);
                     ns += cnt;
-                    for (int q = 0; q < cnt; ++q)
+#pragma unroll
+                    for (int q = 0; q < RMAX; ++q)
                     {
-                        for (int e = lane; e < nvtot; e += 32)
-                            gcols[(size_t)(ncols + q) * nvtot + e] = -vo[q][e];
-                        if (lane == 0)
-                            sm.col_of[ncols + q] = gi[q];
+                        if (q < cnt)
+                        {
+                            if (lane < nvtot)
+                                gcols[(size_t)(ncols + q) * nvtot + lane] = -vo[q][lane];
+                            if (lane == gi[q])
+                                slot_e = ncols + q;
+                        }
                     }
                     qp = ncols;
                     ncols += cnt;
                     __syncwarp();
                 }
-                const double* gp = gcols + (size_t)qp * nvtot;
-                if (nW > 0)
+                const double gp_e = lane < nvtot ? gcols[(size_t)qp * nvtot + lane] : 0.0; // G[:, p]
+                // r = Minv * gwp,  gwp_a = sgn_a s G[W_a][p]  (lane a < nW owns position a)
+                const int widx_a = lane < nW ? sm.W_idx[lane] : 0;
+                const double sgn_a = lane < nW ? sm.sgn[lane] : 0.0;
+                const double gwp_a = sgn_a * s * __shfl_sync(0xffffffffu, gp_e, widx_a);
+                double r_a = 0.0;
+                for (int b = 0; b < nW; ++b)
                 {
-                    const int ldg = nW + 1;
-                    for (int e = lane; e < nW * ldg; e += 32)
-                    {
-                        const int a = e / ldg, b = e - a * ldg;
-                        double v;
-                        if (b < nW)
-                            v = gcols[(size_t)sm.slot_of[b] * nvtot + sm.W_idx[a]] * sm.sgn[a] * sm.sgn[b];
-                        else
-                            v = gp[sm.W_idx[a]] * sm.sgn[a] * s;
-                        GW[e] = v;
-                    }
-                    __syncwarp();
-                    for (int pv = 0; pv < nW; ++pv)
-                    {
-                        const double dinv = 1.0 / GW[pv * ldg + pv];
-                        __syncwarp();
-                        for (int e = lane; e < nW * ldg; e += 32)
-                        {
-                            const int a = e / ldg, b = e - a * ldg;
-                            if (a != pv && b > pv)
-                                GW[e] -= GW[a * ldg + pv] * dinv * GW[pv * ldg + b];
-                        }
-                        __syncwarp();
-                    }
-                    for (int a = lane; a < nW; a += 32)
-                        sm.r[a] = GW[a * ldg + nW] / GW[a * ldg + a];
-                    __syncwarp();
+                    const double gb = __shfl_sync(0xffffffffu, gwp_a, b);
+                    if (lane < nW)
+                        r_a = fma(Minv[lane * MAXW + b], gb, r_a);
                 }
-                double zp = gp[p_idx];
-                for (int a = 0; a < nW; ++a)
-                    zp -= s * sm.r[a] * sm.sgn[a] * gcols[(size_t)sm.slot_of[a] * nvtot + p_idx];
-                const double t2 = (zp > 1e-300) ? (s * vv[p_idx] - s * (s > 0 ? up : lo)) / zp : INFINITY;
-                double t1 = INFINITY;
-                int drop = -1;
-                for (int a = 0; a < nW; ++a)
-                    if (sm.r[a] > 0.0 && sm.lam[a] / sm.r[a] < t1)
+                // zp = G_pp - sum_a r_a gwp_a ; t1 = min_{r_a > 0} lam_a / r_a
+                double zsum = (lane < nW) ? r_a * gwp_a : 0.0;
+                double t1 = (lane < nW && r_a > 0.0) ? lamW / r_a : INFINITY;
+                int drop = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+                    const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
+                    const int od = __shfl_xor_sync(0xffffffffu, drop, o);
+                    if (ot < t1 || (ot == t1 && od < drop))
                     {
-                        t1 = sm.lam[a] / sm.r[a];
-                        drop = a;
+                        t1 = ot;
+                        drop = od;
                     }
+                }
+                const double gpp = __shfl_sync(0xffffffffu, gp_e, p_idx);
+                const double v_p = __shfl_sync(0xffffffffu, v_e, p_idx);
+                const double zp = gpp - zsum;
+                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) / zp : INFINITY;
                 const double t = fmin(t1, t2);
                 if (!isfinite(t))
                 {
@@ -1083,59 +1062,110 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
                     fail = true;
                     break;
                 }
+                // primal step: v_e -= t * (s G[e][p] - sum_a r_a sgn_a G[e][W_a])
+                if (lane < nW)
+                    sm.r[lane] = r_a * sgn_a;
                 __syncwarp();
-                for (int e = lane; e < nvtot; e += 32)
                 {
-                    double zd = s * gp[e];
+                    double zd = s * gp_e;
                     for (int a = 0; a < nW; ++a)
-                        zd -= sm.r[a] * sm.sgn[a] * gcols[(size_t)sm.slot_of[a] * nvtot + e];
-                    vv[e] -= t * zd;
+                        if (lane < nvtot)
+                            zd = fma(-sm.r[a], gcols[(size_t)sm.slot_of[a] * nvtot + lane], zd);
+                    v_e = fma(-t, zd, v_e);
                 }
-                __syncwarp();
-                if (lane == 0)
-                    for (int a = 0; a < nW; ++a)
-                        sm.lam[a] -= t * sm.r[a];
+                if (lane < nW)
+                    lamW -= t * r_a;
                 lam_p += t;
-                __syncwarp();
                 if (t2 <= t1)
                 {
+                    // full step: p joins the working set; bordered update of Minv (Schur complement = zp)
                     if (nW >= MAXW)
                     {
                         stat = VSMPC_STATUS_MAX_ITER;
                         fail = true;
                         break;
                     }
-                    if (lane == 0)
+                    const double izp = 1.0 / zp;
+                    if (lane < nW)
+                        sm.lam[lane] = r_a; // plain r for the rank-1 term
+                    __syncwarp();
+                    if (lane < nW)
                     {
+                        for (int b = 0; b < nW; ++b)
+                            Minv[lane * MAXW + b] = fma(r_a * izp, sm.lam[b], Minv[lane * MAXW + b]);
+                        Minv[lane * MAXW + nW] = -r_a * izp;
+                        Minv[nW * MAXW + lane] = -r_a * izp;
+                    }
+                    if (lane == nW)
+                    {
+                        Minv[nW * MAXW + nW] = izp;
                         sm.W_idx[nW] = p_idx;
                         sm.slot_of[nW] = qp;
                         sm.sgn[nW] = s;
-                        sm.lam[nW] = lam_p;
+                        lamW = lam_p;
                     }
+                    if (lane == p_idx)
+                        wpos_e = nW;
                     nW++;
                     __syncwarp();
                     break;
                 }
-                if (lane == 0)
-                    for (int a = drop; a + 1 < nW; ++a)
+                // partial step: position `drop` leaves the working set; downdate Minv, move the last
+                // position into the hole
+                {
+                    const int last = nW - 1;
+                    const int var_d = sm.W_idx[drop], var_l = sm.W_idx[last];
+                    const double mdd = Minv[drop * MAXW + drop];
+                    __syncwarp();
+                    const double f = lane < nW ? Minv[lane * MAXW + drop] / mdd : 0.0;
+                    // row `drop` is needed by every lane: stage it
+                    if (lane < nW)
+                        sm.lam[lane] = Minv[drop * MAXW + lane];
+                    __syncwarp();
+                    if (lane < nW)
+                        for (int b = 0; b < nW; ++b)
+                            Minv[lane * MAXW + b] = fma(-f, sm.lam[b], Minv[lane * MAXW + b]);
+                    __syncwarp();
+                    // move position `last` into `drop`
+                    if (drop != last)
                     {
-                        sm.W_idx[a] = sm.W_idx[a + 1];
-                        sm.slot_of[a] = sm.slot_of[a + 1];
-                        sm.sgn[a] = sm.sgn[a + 1];
-                        sm.lam[a] = sm.lam[a + 1];
+                        if (lane < nW)
+                            sm.lam[lane] = Minv[last * MAXW + lane]; // row last
+                        __syncwarp();
+                        if (lane < nW)
+                        {
+                            Minv[drop * MAXW + lane] = sm.lam[lane];
+                            Minv[lane * MAXW + drop] = sm.lam[lane]; // symmetric
+                        }
+                        __syncwarp();
+                        if (lane == 0)
+                        {
+                            Minv[drop * MAXW + drop] = sm.lam[last];
+                            sm.W_idx[drop] = var_l;
+                            sm.slot_of[drop] = sm.slot_of[last];
+                            sm.sgn[drop] = sm.sgn[last];
+                        }
+                        const double lam_last = __shfl_sync(0xffffffffu, lamW, last);
+                        if (lane == drop)
+                            lamW = lam_last;
+                        if (lane == var_l)
+                            wpos_e = drop;
                     }
-                nW--;
-                __syncwarp();
+                    if (lane == var_d)
+                        wpos_e = -1;
+                    nW--;
+                    __syncwarp();
+                }
             }
-            if (fail)
-                break;
         }
+        // publish the final throttle iterate and the multipliers
+        if (lane < nvtot)
+            vv[lane] = v_e;
+        if (lane < nW)
+            sm.r[lane] = sm.sgn[lane] * lamW;
+        __syncwarp();
         if (stat == VSMPC_STATUS_SOLVED && nW > 0)
         {
-            if (lane == 0)
-                for (int a = 0; a < nW; ++a)
-                    sm.r[a] = sm.sgn[a] * sm.lam[a];
-            __syncwarp();
             if (want_z)
             {
                 // full primal requested: one more inhomogeneous pass with the multipliers as linear cost
@@ -1144,9 +1174,8 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
                 st_solve<1>(c, tab, false, nullptr, nullptr, nW, sm.W_idx, sm.r, vo, ro, z);
                 ns++;
                 const int base = NX * (N + 1) + cfg.Nc * NJ;
-                if (lane == 0)
-                    for (int a = 0; a < nW; ++a)
-                        z[base + sm.W_idx[a]] = sm.sgn[a] > 0 ? up : lo;
+                if (lane < nW)
+                    z[base + sm.W_idx[lane]] = sm.sgn[lane] > 0 ? up : lo;
             }
             else
             {
@@ -1159,9 +1188,8 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
                     recb[e] = v;
                 }
             }
-            if (lane == 0)
-                for (int a = 0; a < nW; ++a) // land exactly on the bound
-                    vv[sm.W_idx[a]] = sm.sgn[a] > 0 ? up : lo;
+            if (lane < nW) // land exactly on the bound
+                vv[sm.W_idx[lane]] = sm.sgn[lane] > 0 ? up : lo;
             __syncwarp();
         }
     }

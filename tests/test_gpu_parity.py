@@ -87,7 +87,7 @@ def test_solve_matches_exact_oracle(solver, free_tick):
 @pytest.mark.parametrize("free_tick", [False, True])
 def test_outputs_without_full_solution(free_tick):
     """Default mode of the structured kernel: outputs by superposition, no 588-vector written."""
-    B = 48
+    B = 192
     mpc, nom, per, traj = make(B, 0, near=0.3, full=False)
     mpc.configure(nom)
     if free_tick:
