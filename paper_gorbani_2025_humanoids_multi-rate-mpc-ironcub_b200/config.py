@@ -87,3 +87,11 @@ def hover_trajectories(n: int = 8) -> dict:
     z = np.zeros((3, n))
     return dict(alpha_fps=10, alphaGravity=np.ones((1, n)), traj_fps=10, positionCoM=z, velocityCoM=z.copy(),
                 RPY=z.copy(), RPYDot=z.copy())
+
+
+def load_trajectories_mat(alpha_path: str, position_path: str) -> dict:
+    """Load the two MAT-v7.3 files named by TRAJECTORY_MANAGER / POSITION_TRAJECTORY in the XML."""
+    from .mat73 import loadmat73
+    a, m = loadmat73(alpha_path), loadmat73(position_path)
+    return dict(alpha_fps=int(a["fps"][0, 0]), alphaGravity=a["alphaGravity"], traj_fps=int(m["fps"][0, 0]),
+                positionCoM=m["positionCoM"], velocityCoM=m["velocityCoM"], RPY=m["RPY"], RPYDot=m["RPYDot"])

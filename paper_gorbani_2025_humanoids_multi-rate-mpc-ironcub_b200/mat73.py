@@ -1,9 +1,10 @@
-"""Minimal pure-Python reader for the MATLAB v7.3 (HDF5, superblock v0) trajectory fixtures.
+"""Minimal pure-Python reader for MATLAB v7.3 (HDF5, superblock v0) trajectory files.
 
-TEST INFRASTRUCTURE ONLY (part of ``oracle/``): used once, in the build container, by
-``tools/make_fixtures.py`` to convert the reference's ``src/trajectories/*.mat`` into the small
-``tests/golden/trajectories.npz`` fixture.  It stands in for matio's ``Mat_VarRead`` as used by
-the reference's ``TrajectoryManager::loadTrajectoryFromFile`` (UT/src/TrajectoryManager.cpp:67-140).
+Host-side I/O of the drop-in: stands in for matio's ``Mat_VarRead`` as used by the reference's
+``TrajectoryManager::loadTrajectoryFromFile`` (utils/src/TrajectoryManager.cpp:67-140), so that the
+``trajectoryFile`` entries of ``vs_mcp_config.xml`` (:34-40) can be loaded without matio / h5py.
+``tools/make_fixtures.py`` uses it to convert the reference's ``src/trajectories/*.mat`` into
+``tests/golden/trajectories.npz``.
 
 Supports exactly what those two files need: v0 superblock, v1 object headers, v1 group B-trees +
 local heaps, contiguous and chunked (deflate) layouts of little-endian float64 datasets.

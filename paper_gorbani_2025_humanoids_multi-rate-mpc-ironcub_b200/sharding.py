@@ -1,0 +1,71 @@
+"""Multi-GPU layout: instances are independent, so a batch of B instances is split into contiguous
+ranges, one per rank / GPU (one process per GPU, torch.distributed).  There is NO collective in the
+solve; a collective is used only to collect the per-instance output rows (NCCL all_gather on GPUs,
+gloo in the CPU tests).  SURVEY.md §8(e)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous instance range [lo, hi) of `rank`: [g*B/G, (g+1)*B/G)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    lo = (rank * n_total) // world
+    hi = ((rank + 1) * n_total) // world
+    return lo, hi
+
+
+def gather_rows(local_rows, n_total: int, group=None):
+    """All-gather per-instance rows (torch tensor [n_local, C], any device) into [n_total, C] on every
+    rank.  Uneven shards are padded to the largest shard for the collective and trimmed afterwards."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in sizes)
+    C = local_rows.shape[1]
+    pad = torch.zeros((nmax, C), dtype=local_rows.dtype, device=local_rows.device)
+    pad[: local_rows.shape[0]] = local_rows
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+class ShardedVSMPC:
+    """The reference surface over a batch sharded across ranks.  Every rank passes the FULL SoA pack
+    (PACK_DOUBLES, B) — or only needs its own columns to be valid — and owns the instances of its range."""
+
+    def __init__(self, n_total: int, params, trajectories, rank: int, world: int, device: int = 0, solver: int = 0,
+                 factory=None):
+        self.n_total, self.rank, self.world = int(n_total), int(rank), int(world)
+        self.lo, self.hi = shard_range(n_total, rank, world)
+        if factory is None:
+            from .batched import BatchedVSMPC as factory
+        self.local = factory(self.hi - self.lo, params, trajectories, device=device, solver=solver)
+
+    def _cols(self, a):
+        return np.ascontiguousarray(np.asarray(a)[:, self.lo:self.hi])
+
+    def configure_pack(self, pack, joint_pos_sel, phase0=None):
+        ph = None if phase0 is None else np.ascontiguousarray(np.asarray(phase0)[self.lo:self.hi])
+        return self.local.configure_pack(self._cols(pack), self._cols(joint_pos_sel), ph)
+
+    def update_pack(self, pack):
+        return self.local.update_pack(self._cols(pack))
+
+    def solveMPC(self):
+        return self.local.solveMPC()
+
+    def get_output_local(self):
+        return self.local.get_output()
+
+    def get_output_all(self, group=None, device=None):
+        """Collect the output rows of every rank (the only communication of the whole path)."""
+        import torch
+        out, status = self.local.get_output()
+        dev = device if device is not None else "cpu"
+        rows = torch.from_numpy(np.concatenate([out, status[:, None].astype(np.float64)], axis=1)).to(dev)
+        full = gather_rows(rows, self.n_total, group).cpu().numpy()
+        return full[:, :-1], full[:, -1].astype(np.int32)

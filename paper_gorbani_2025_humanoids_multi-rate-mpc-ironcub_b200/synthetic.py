@@ -144,3 +144,16 @@ def make_states(B: int, seed: int = 20251002, perturbed: bool = True, robot: Syn
         joint_pos=np.tile(rb.joint_pos0, (B, 1)),
     )
     return state
+
+
+def apply_feedback(state: dict, out_rows: np.ndarray, sel=SEL) -> dict:
+    """What the reference driver feeds back into QPInput after every tick
+    (src/variable_sampling_mpc.py:124-131): throttle, desired thrust / thrust rate, joint references."""
+    s = dict(state)
+    s["throttle_prev"] = out_rows[:, 8:12].copy()
+    s["thrust_des"] = out_rows[:, 12:16].copy()
+    s["thrust_dot_des"] = out_rows[:, 16:20].copy()
+    q = state["q_cmd"].copy()
+    q[:, sel] = out_rows[:, 46:54]
+    s["q_cmd"] = q
+    return s

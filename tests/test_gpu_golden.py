@@ -1,0 +1,120 @@
+"""GPU: the CUDA path (through the C-ABI) against the frozen golden vectors of tests/golden/."""
+import numpy as np
+import pytest
+
+from helpers import golden, load_trajectories, pkg
+from oracle_driver import oracle_trajectories_to_product
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6   # north_star tolerance (FP64)
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_single_tick_golden(solver):
+    g = golden("golden_qp.npz")
+    bat = pkg("batched")
+    B = g["nom_pack"].shape[1]
+    for tag, free in (("pin", False), ("free", True)):
+        mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(load_trajectories()), solver=solver,
+                               full_solution=True)
+        mpc.configure_pack(g["nom_pack"], g["joint_pos_sel"])
+        if free:
+            mpc.debug_set_counters(-1, 19)
+        mpc.update_pack(g["per_pack"])
+        A, BJ, BT, c, _ = mpc.get_dynamics()
+        q, l, u = mpc.get_qp_vectors()
+        mpc.solveMPC()
+        z = mpc.getSolution()
+        out, status = mpc.get_output()
+        assert (status == 0).all()
+        assert rel_err(A, g[f"{tag}_A"]) < 1e-12 and rel_err(BJ, g[f"{tag}_BJ"]) < 1e-12
+        assert rel_err(BT, g[f"{tag}_BT"]) < 1e-12 and rel_err(c, g[f"{tag}_c"]) < 1e-12
+        assert rel_err(q, g[f"{tag}_q"]) < 1e-12 and rel_err(l, g[f"{tag}_l"]) < 1e-12 and rel_err(u, g[f"{tag}_u"]) < 1e-12
+        for i in range(B):
+            assert rel_err(z[i], g[f"{tag}_z"][i]) < REL
+            assert rel_err(out[i], g[f"{tag}_row"][i]) < REL
+        mpc.close()
+
+
+@pytest.mark.parametrize("solver,full", [(0, False), (0, True), (1, True)])
+def test_tick_sequence_golden(solver, full):
+    """24 consecutive ticks: reference-window shift and throttle release on tick 20, alpha_g cursor, RPY
+    unwrapping through +-pi, joint accumulator, output hold — all device-resident state."""
+    g = golden("golden_ticks.npz")
+    bat = pkg("batched")
+    B = g["nom_pack"].shape[1]
+    mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(load_trajectories()), solver=solver,
+                           full_solution=full)
+    mpc.configure_pack(g["nom_pack"], g["joint_pos_sel"])
+    for t in range(g["packs"].shape[0]):
+        mpc.update_pack(g["packs"][t])
+        mpc.solveMPC()
+        out, status = mpc.get_output()
+        assert (status == 0).all()
+        for i in range(B):
+            assert rel_err(out[i], g["rows"][t, i]) < REL, (t, i, rel_err(out[i], g["rows"][t, i]))
+        if full:
+            z = mpc.getSolution()
+            assert rel_err(z, g["z"][t]) < REL
+    mpc.close()
+
+
+def test_status_gate_holds_outputs_on_bad_input():
+    """Non-finite data -> status 2 and the previous outputs are held (variableSamplingMPC.cpp:91)."""
+    g = golden("golden_qp.npz")
+    bat = pkg("batched")
+    B = g["nom_pack"].shape[1]
+    mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(load_trajectories()))
+    mpc.configure_pack(g["nom_pack"], g["joint_pos_sel"])
+    mpc.update_pack(g["per_pack"])
+    mpc.solveMPC()
+    out0, st0 = mpc.get_output()
+    bad = g["per_pack"].copy()
+    bad[331, 2] = np.nan          # thrust of instance 2
+    mpc.update_pack(bad)
+    mpc.solveMPC()
+    out1, st1 = mpc.get_output()
+    assert st1[2] == 2 and (np.delete(st1, 2) == 0).all()
+    assert np.array_equal(out1[2], out0[2])            # held
+    assert not np.array_equal(out1[0][46:54], out0[0][46:54])   # the others accumulated a second increment
+    mpc.close()
+
+
+def test_single_instance_mirror_matches_batched():
+    from helpers import state_from_pack
+    g = golden("golden_qp.npz")
+    mp = pkg("mpc")
+    nom = state_from_pack(g["nom_pack"], g["joint_pos_sel"])
+    per = state_from_pack(g["per_pack"])
+    i = 3
+
+    def robot(st):
+        return dict(wRb=st["wRb"][i], base_pos=st["base_pos"][i], omega_world=st["omega_world"][i], rpy=st["rpy"][i],
+                    M_b=st["M_b"][i], p_com=st["p_com"][i], momentum_body=st["momentum_body"][i],
+                    A_mom_body=st["A_mom_body"][i], jet_axes=st["jet_axes"][i], jet_arms=st["jet_arms"][i],
+                    J_rel_body=st["J_rel_body"][i], J_jet_lin=st["J_jet_lin"][i], J_com=st["J_com"][i],
+                    thrust=st["thrust"][i], joint_pos=st["joint_pos"][i], gravity=st["gravity"][i])
+
+    def fill(qp, st):
+        qp.setThrottleMPC(st["throttle_prev"][i]); qp.setThrustDesMPC(st["thrust_des"][i])
+        qp.setThrustDotDesMPC(st["thrust_dot_des"][i]); qp.setEstimatedThrustDot(st["thrust_dot_est"][i])
+        qp.setOutputQPJointsPosition(st["q_cmd"][i])
+
+    r = mp.RobotState(**robot(nom))
+    qp = mp.QPInput(); qp.setRobot(r); qp.setRobotReference(r); qp.setEmptyJetModel(); fill(qp, nom)
+    m = mp.VariableSamplingMPC()
+    assert m.configure(pkg("config").default_params(), qp, oracle_trajectories_to_product(load_trajectories()))
+    r.setState(**robot(per)); fill(qp, per)
+    assert m.update(qp) and m.solveMPC()
+    row = g["pin_row"][i]
+    assert rel_err(m.getThrustReference(), row[12:16]) < REL
+    assert rel_err(m.getThrottleReference(), row[8:12]) < REL
+    assert rel_err(m.getThrustDotReference(), row[16:20]) < REL
+    assert rel_err(m.getJointsReferencePosition()[3:11], row[46:54]) < REL
+    assert m.getJointsReferencePosition().shape == (23,)
+    assert rel_err(m.getSolution(), g["pin_z"][i]) < REL
+    assert m.getNStatesMPC() == 26.0 and m.getNInputMPC() == 12.0 and m.getNOptimizationVariables() == 588

@@ -1,0 +1,122 @@
+"""CPU tests of the host layer: header <-> Python layout agreement, exported symbols, config reader,
+argument errors of the C-ABI (no compute call is made without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, pkg
+
+HEADER = open(os.path.join(ROOT, "include", "vsmpc.h")).read()
+
+
+def test_pack_offsets_match_header():
+    P = pkg("pack")
+    defs = dict(re.findall(r"#define\s+(VSMPC_PK_\w+)\s+(\d+)", HEADER))
+    names = {"wRb": "WRB", "omega_world": "OMEGA_WORLD", "rpy": "RPY", "mass": "MASS", "gravity": "GRAVITY",
+             "M_b": "MB", "base_pos": "BASE_POS", "p_com": "P_COM", "momentum_body": "MOMENTUM_BODY",
+             "A_mom_body": "AMOM_BODY", "jet_axes": "JET_AXES", "jet_arms": "JET_ARMS", "J_rel_ang": "J_REL_ANG",
+             "J_jet_lin": "J_JET_LIN", "J_com": "J_COM", "thrust": "THRUST", "thrust_dot_est": "THRUST_DOT_EST",
+             "thrust_des": "THRUST_DES", "thrust_dot_des": "THRUST_DOT_DES", "throttle_prev": "THROTTLE_PREV",
+             "q_cmd": "Q_CMD"}
+    for f, (off, size) in P.PACK_OFFSETS.items():
+        assert int(defs["VSMPC_PK_" + names[f]]) == off, f
+    m = re.search(r"#define\s+VSMPC_PACK_DOUBLES\s+(\d+)", HEADER)
+    assert int(m.group(1)) == P.PACK_DOUBLES == 359
+    L = pkg("_lib")
+    for k in ("DELTA_Q", "THROTTLE", "THRUST", "THRUST_DOT", "FINAL_STATE", "JOINTS_REF", "DOUBLES"):
+        v = int(re.search(rf"#define\s+VSMPC_OUT_{k}\s+(\d+)", HEADER).group(1))
+        assert v == getattr(L, "OUT_" + k)
+
+
+def test_library_exports_every_declared_symbol():
+    L = pkg("_lib")
+    lib = L.load()
+    declared = set(re.findall(r"\b(vsmpc_[a-z0-9_]+)\s*\(", HEADER))
+    declared -= {"vsmpc_handle", "vsmpc_config"}
+    assert declared, "no functions parsed from the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vsmpc.h but not exported"
+    assert set(L.EXPORTS) == declared
+
+
+def test_config_struct_layout_matches_c():
+    # the C side of the same struct, compiled here with gcc
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "vsmpc.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(vsmpc_config), offsetof(vsmpc_config, solver), offsetof(vsmpc_config, jet_coeff));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        sz, off_solver, off_jet = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    L = pkg("_lib")
+    assert C.sizeof(L.VsmpcConfig) == sz
+    assert L.VsmpcConfig.solver.offset == off_solver
+    assert L.VsmpcConfig.jet_coeff.offset == off_jet
+
+
+def test_create_argument_errors_without_gpu():
+    bat, L, cfg = pkg("batched"), pkg("_lib"), pkg("config")
+    traj = cfg.hover_trajectories()
+    with pytest.raises(bat.VsmpcError, match="nIterSmall"):
+        bat.BatchedVSMPC(4, dict(nIter=17, nIterSmall=7, controlHorizon=5), traj)
+    with pytest.raises(bat.VsmpcError, match="constant"):
+        bat.BatchedVSMPC(4, dict(jointsLambdaOption="constant"), traj)
+    with pytest.raises(bat.VsmpcError, match="unfiltered"):
+        bat.BatchedVSMPC(4, dict(jointsLambdaOption="bogus"), traj)
+    with pytest.raises(bat.VsmpcError, match="joint deltas"):
+        bat.BatchedVSMPC(4, dict(weightDeltaJoint=[1.0] * 7), traj)
+    lib = L.load()
+    assert lib.vsmpc_create(None, 4, 0, None) == L.ERR_ARG
+    assert lib.vsmpc_n_var(None) == -1
+    assert lib.vsmpc_solve(None) == L.ERR_ARG
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    bat, cfg = pkg("batched"), pkg("config")
+    with pytest.raises(bat.VsmpcError, match="cuda|CUDA|device"):
+        bat.BatchedVSMPC(4, None, cfg.hover_trajectories())
+
+
+def test_xml_config_reader(tmp_path):
+    cfg = pkg("config")
+    xml = tmp_path / "c.xml"
+    xml.write_text('''<?xml version="1.0" encoding="UTF-8" ?>
+<robot name="x"><device name="d" type="dummy"><group name="VS_MPC_CONFIG">
+<param name="useJetDynamic">true</param><param name="periodMPC">0.005</param><param name="nIter">17</param>
+<param name="controlledJoints">("l_shoulder_pitch", "l_elbow")</param>
+<param name="weightCoMPos">(500.0 500.0 5000.0)</param><param name="jointsLambdaOption">"unfiltered"</param>
+<group name="TRAJECTORY_MANAGER"><param name="trajectoryFile">"a.mat"</param></group>
+</group></device></robot>''')
+    p = cfg.read_xml_config(str(xml))
+    assert p["useJetDynamic"] is True and p["periodMPC"] == 0.005 and p["nIter"] == 17
+    assert p["controlledJoints"] == ["l_shoulder_pitch", "l_elbow"]
+    assert p["weightCoMPos"] == [500.0, 500.0, 5000.0] and p["jointsLambdaOption"] == "unfiltered"
+    assert p["TRAJECTORY_MANAGER"]["trajectoryFile"] == "a.mat"
+    d = cfg.default_params()
+    assert d["nIter"] == 17 and d["nIterSmall"] == 7 and d["controlHorizon"] == 12
+
+
+def test_pack_builder_roundtrip():
+    from helpers import state_from_pack
+    syn, P = pkg("synthetic"), pkg("pack")
+    st = syn.make_states(5, perturbed=True)
+    pack = P.build_pack(st)
+    assert pack.shape == (359, 5) and pack.dtype == np.float64
+    back = state_from_pack(pack)
+    assert np.array_equal(P.build_pack(back), pack)
+    with pytest.raises(ValueError):
+        bad = dict(st); bad["wRb"] = st["wRb"][:, :2]
+        P.build_pack(bad)
+
+
+def test_mat73_reader_on_npz_equivalent(tmp_path):
+    """The MAT-v7.3 reader is exercised against the reference files in tools/make_fixtures.py; here the
+    committed fixture must at least be self-consistent with what the loader returns."""
+    cfg = pkg("config")
+    t = cfg.load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+    assert t["alpha_fps"] == 10 and t["traj_fps"] == 10 and t["alphaGravity"].shape == (1, 351)

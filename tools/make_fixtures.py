@@ -17,7 +17,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.mat73 import loadmat73  # noqa: E402
+import importlib  # noqa: E402
+loadmat73 = importlib.import_module('paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub_b200.mat73').loadmat73
 
 REF = "/root/reference/src/trajectories"
 
