@@ -239,7 +239,7 @@ def run_ours(args):
                 "kernel_ms_per_launch": k2_s_per_launch * 1e3, "linearise_ms_per_launch": k1_ms / K,
                 "hbm_algorithmic_bytes_per_solve": 359 * 8 + 54 * 8,
                 "hbm_gbs_at_value": value * (359 * 8 + 54 * 8) / 1e9}
-    cpu = cpu_baseline(sample_solves=args.cpu_sample)
+    cpu = cpu_baseline(sample_solves=max(args.cpu_sample, min(1024, 4 * (os.cpu_count() or 1))), ticks=5)
     line = {
         "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -263,57 +263,38 @@ def run_ours(args):
 
 
 # =====================================================================================================
-def cpu_baseline(sample_solves=24, threads=None):
-    """Oracle ("port") timed on the host: per-instance update + solve, bounded sample."""
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from oracle_driver import OracleInstance  # noqa
-        from helpers import load_trajectories  # noqa
-    except Exception as e:  # pragma: no cover
-        return {"value": None, "unit": "solves/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
-    try:
-        from oracle import cbaseline  # C restatement (OSQP-style ADMM) if built
-        return cbaseline.time_baseline(sample_solves=max(sample_solves, 256), threads=threads)
-    except Exception:
-        pass
-    syn = pkg("synthetic")
-    n = sample_solves
-    nom = syn.make_states(n, perturbed=False)
-    per = syn.make_states(n, perturbed=True)
-    traj = load_trajectories()
-    inst = [OracleInstance(nom, i, trajectories=traj) for i in range(n)]
-    t0 = time.perf_counter()
-    for o in inst:
-        o.update(per)
-        o.solve()
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "solves/s", "cores": 1, "kind": "port",
-            "sample": f"{n} instances of the same workload, NumPy/SciPy oracle (dense assembly + exact sparse-KKT active set), 1 thread"}
+def cpu_baseline(sample_solves=256, threads=None, ticks=3):
+    """The oracle's C restatement of the reference tick ("port") timed on this box's host cores on a
+    bounded sample of the same workload.  bench.py executes oracle/ ONLY here and in --impl reference."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import cbaseline
+    return cbaseline.time_baseline(sample_solves=sample_solves, threads=threads, ticks=ticks)
 
 
 def run_reference(args):
+    """Reference arm: the CPU implementation of the path (oracle C port; the reference itself cannot be
+    built here) on all host cores; one step = one tick of a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import cbaseline
     K, Wm = args.steps, args.warmup
     cores = os.cpu_count() or 1
-    per_step = max(8, args.cpu_sample)
-    vals = []
-    res = None
-    for j in range(Wm + K):
-        res = cpu_baseline(sample_solves=per_step, threads=cores)
-        if j >= Wm:
-            vals.append(res["value"])
-    value = float(np.mean(vals))
-    res = dict(res)
-    res["value"] = value
+    n = max(args.cpu_sample, min(1024, 4 * cores))
+    runner = cbaseline.BaselineRunner(n, cores)
+    for _ in range(Wm):
+        runner.tick()
+    dt = sum(runner.tick() for _ in range(K))
+    value = n * K / dt
+    cpu = {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": f"{K} ticks x " + runner.describe()}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": Wm,
-            "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1] sample: same synthetic instances, CPU restatement of the reference path",
-                       "instances_per_step": per_step},
-            "cpu_baseline": res,
+            "config": {"workload": "configs[1] (bounded sample): same synthetic instances and perturbation model, "
+                                   "CPU restatement of the reference tick", "instances_per_step": n},
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -326,7 +307,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--solver", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=24)
+    ap.add_argument("--cpu-sample", type=int, default=256)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
