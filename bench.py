@@ -239,7 +239,8 @@ def run_ours(args):
                 "kernel_ms_per_launch": k2_s_per_launch * 1e3, "linearise_ms_per_launch": k1_ms / K,
                 "hbm_algorithmic_bytes_per_solve": 359 * 8 + 54 * 8,
                 "hbm_gbs_at_value": value * (359 * 8 + 54 * 8) / 1e9}
-    cpu = cpu_baseline(sample_solves=max(args.cpu_sample, min(1024, 4 * (os.cpu_count() or 1))), ticks=5)
+    cpu = None if args.no_cpu else cpu_baseline(
+        sample_solves=max(args.cpu_sample, min(1024, 4 * (os.cpu_count() or 1))), ticks=5)
     line = {
         "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -308,6 +309,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--solver", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
