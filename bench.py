@@ -202,6 +202,10 @@ def run_ours(args):
         e2e_s += time.perf_counter() - t0
     barrier()
     sampler.stop()
+    # ---------------- single-instance latency (BASELINE metric: "single-solve p50 latency") -----------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        latency = single_solve_latency(bat, L, local_rank, stream, n_ticks=400)
     # ---------------- reduce over ranks: max time --------------------------------------------------------
     t = torch.tensor([total_ms, e2e_s * 1e3, k1_ms, k2_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -256,11 +260,38 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / K, "timing": "host perf_counter around set_state+solve+get_output, synchronized"},
         "gpu_launches": 2 * K,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        "single_solve_latency": latency,
         "solved_fraction": solved_frac, "wall_ms_timed_loop": t_wall * 1e3,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def single_solve_latency(bat, L, device, stream, n_ticks=400):
+    """One MPC instance driven tick by tick through the C-ABI with host buffers (the reference controller's
+    use: update + solveMPC + getters, src/variable_sampling_mpc.py:110-127): per-tick wall time."""
+    import torch
+    nom_pack, jp, packs = make_workload(1, 4242, 8)
+    mpc = bat.BatchedVSMPC(1, None, load_traj(), device=device)
+    mpc.set_stream(stream.cuda_stream)
+    mpc.configure_pack(nom_pack, jp, None)
+    h_packs = [torch.from_numpy(p).pin_memory() for p in packs]
+    h_out = torch.empty((1, L.OUT_DOUBLES), dtype=torch.float64).pin_memory()
+    h_status = torch.empty((1,), dtype=torch.int32).pin_memory()
+    ts = []
+    for j in range(n_ticks + 20):
+        t0 = time.perf_counter()
+        mpc.update_ptr(h_packs[j % len(h_packs)].data_ptr())
+        mpc.solve_async()
+        mpc.get_output_into(h_out.data_ptr(), h_status.data_ptr())
+        ts.append(time.perf_counter() - t0)
+    mpc.close()
+    ts = np.array(ts[20:]) * 1e3
+    return {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)),
+            "mean_ms": float(ts.mean()), "ticks": int(n_ticks), "controller_period_ms": 5.0,
+            "reference_published_ms": 2.18,
+            "what": "vsmpc_set_state (H2D) + vsmpc_solve + vsmpc_get_output (D2H), B = 1, host wall clock"}
 
 
 # =====================================================================================================
@@ -309,6 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--solver", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-instance latency leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -1,0 +1,312 @@
+// vsmpc_adapter.hpp — header-only C++ host adapter over the C-ABI of include/vsmpc.h.
+//
+// vsmpc::VariableSamplingMPC keeps the method names, argument meaning and bool error convention of the
+// reference class `VariableSamplingMPC : IMPCProblem`
+//   (src/flight-controller/momentum-based-linear-mpc-lib/include/variableSamplingMPC/variableSamplingMPC.h:15-41,
+//    .../include/IMPCProblem/IMPCProblem.h:35-118)
+// for ONE MPC instance (n_instances = 1), so that the reference's C++ controller and its pybind module
+// (bindings/python/MPCPyBindings.cpp:22-90) can bind this class instead.  Getters take anything with
+// .data()/.size() (std::vector<double>, Eigen::VectorXd, Eigen::Ref<...>) and check the size exactly like
+// the reference getters (variableSamplingMPC.cpp:114-227).
+//
+// vsmpc::BatchedMPC is the same call sequence for B instances on one GPU (structure-of-arrays pack).
+//
+// Depends on the C++ standard library only.  All compute is in libvsmpc.so (CUDA); there is no CPU path.
+#ifndef VSMPC_ADAPTER_HPP
+#define VSMPC_ADAPTER_HPP
+
+#include <cstddef>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "vsmpc.h"
+
+namespace vsmpc
+{
+
+// ---- parameters: group VS_MPC_CONFIG of src/config/vs_mcp_config.xml:5-44, shipped values as defaults ----
+struct Params
+{
+    int nIter = 17, nIterSmall = 7, controlHorizon = 12;
+    double periodMPC = 0.005, periodMPCLargeSteps = 0.1, periodMPCSmallSteps = 0.005;
+    bool useJetDynamic = true, useEstimatedThrust = true;
+    std::string jointsLambdaOption = "unfiltered";
+    double weightCoMPos[3] = {500, 500, 5000};
+    double weightCoMPosError[3] = {25000, 25000, 50000};
+    double weightLinMom[3] = {1, 1, 1.5};
+    double weightRPY[3] = {1000, 1000, 1000};
+    double weightRPYError[3] = {10000, 10000, 10000};
+    double weightAngMom[3] = {80, 80, 80};
+    double weightDeltaJoint[VSMPC_NJ] = {65000, 65000, 65000, 65000, 65000, 65000, 65000, 65000};
+    double weightThrottle = 80000, weightInitialThrottle = 80000, weightRegularizationJointPos = 20;
+    double throttleMin = 0, throttleMax = 100;
+    // UT/src/JetModel.cpp:13-26
+    double jetCoeff[13] = {-4.64730485e-01, -8.13171858e+00, -6.19539230e+00, 6.61113140e-01, 1.67673231e+00,
+                           -4.83287064e-01, 8.77996617e+00, -1.01096376e+00, -5.86442286e-01, 5.19093322e-01,
+                           -4.23782666e-01, -1.45705257e+00, -7.83052261e-03};
+    double jetNorm[4] = {108.309, 65.793, 47.333, 31.483};
+    // trajectories (TrajectoryManager.cpp:67-140): alphaGravity[alphaLen]; 3 x trajLen arrays, sample-major
+    std::vector<double> alphaGravity;
+    int alphaFps = 10;
+    std::vector<double> positionCoM, velocityCoM, RPY, RPYDot;
+    int trajFps = 10;
+    int solver = 0;
+};
+
+// ---- one instance's input pack (what update(QPInput&) reads) ------------------------------
+class Pack
+{
+public:
+    double v[VSMPC_PACK_DOUBLES];
+    Pack() { std::memset(v, 0, sizeof(v)); }
+    double& operator[](int i) { return v[i]; }
+    const double& operator[](int i) const { return v[i]; }
+    // n contiguous doubles
+    void set(int off, const double* src, int n) { std::memcpy(v + off, src, sizeof(double) * n); }
+    // column-major r x c matrix (Eigen default) -> row-major block at off
+    void setRowMajorFromColMajor(int off, const double* src, int r, int c)
+    {
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < c; ++j)
+                v[off + i * c + j] = src[j * r + i];
+    }
+    // selected columns of a column-major r x c matrix -> row-major r x sel.size() block
+    void setRowMajorCols(int off, const double* src, int r, const std::vector<int>& sel)
+    {
+        const int n = static_cast<int>(sel.size());
+        for (int i = 0; i < r; ++i)
+            for (int j = 0; j < n; ++j)
+                v[off + i * n + j] = src[sel[j] * r + i];
+    }
+    void setSelected(int off, const double* src, const std::vector<int>& sel)
+    {
+        for (size_t j = 0; j < sel.size(); ++j)
+            v[off + j] = src[sel[j]];
+    }
+};
+
+namespace detail
+{
+inline void fill_config(const Params& p, vsmpc_config& c)
+{
+    std::memset(&c, 0, sizeof(c));
+    c.n_iter = p.nIter;
+    c.n_iter_small = p.nIterSmall;
+    c.control_horizon = p.controlHorizon;
+    c.period_mpc = p.periodMPC;
+    c.period_large = p.periodMPCLargeSteps;
+    c.period_small = p.periodMPCSmallSteps;
+    c.use_jet_dynamic = p.useJetDynamic ? 1 : 0;
+    c.use_estimated_thrust = p.useEstimatedThrust ? 1 : 0;
+    c.joints_lambda_option = p.jointsLambdaOption == "unfiltered" ? 0 : 1;
+    for (int a = 0; a < 3; ++a)
+    {
+        c.weight_com_pos[a] = p.weightCoMPos[a];
+        c.weight_com_pos_error[a] = p.weightCoMPosError[a];
+        c.weight_lin_mom[a] = p.weightLinMom[a];
+        c.weight_rpy[a] = p.weightRPY[a];
+        c.weight_rpy_error[a] = p.weightRPYError[a];
+        c.weight_ang_mom[a] = p.weightAngMom[a];
+    }
+    for (int a = 0; a < VSMPC_NJ; ++a)
+        c.weight_delta_joint[a] = p.weightDeltaJoint[a];
+    c.weight_throttle = p.weightThrottle;
+    c.weight_initial_throttle = p.weightInitialThrottle;
+    c.weight_regularization_joint_pos = p.weightRegularizationJointPos;
+    c.throttle_min = p.throttleMin;
+    c.throttle_max = p.throttleMax;
+    std::memcpy(c.jet_coeff, p.jetCoeff, sizeof(c.jet_coeff));
+    std::memcpy(c.jet_norm, p.jetNorm, sizeof(c.jet_norm));
+    c.alpha_gravity = p.alphaGravity.data();
+    c.alpha_len = static_cast<int>(p.alphaGravity.size());
+    c.alpha_fps = p.alphaFps;
+    c.position_com = p.positionCoM.data();
+    c.velocity_com = p.velocityCoM.data();
+    c.rpy = p.RPY.data();
+    c.rpy_dot = p.RPYDot.data();
+    c.traj_len = static_cast<int>(p.positionCoM.size() / 3);
+    c.traj_fps = p.trajFps;
+    c.solver = p.solver;
+}
+} // namespace detail
+
+// ---- B instances on one GPU -------------------------------------------------------------------------------
+class BatchedMPC
+{
+public:
+    BatchedMPC() = default;
+    BatchedMPC(const BatchedMPC&) = delete;
+    BatchedMPC& operator=(const BatchedMPC&) = delete;
+    ~BatchedMPC() { destroy(); }
+
+    bool create(const Params& p, int nInstances, int device = 0)
+    {
+        destroy();
+        if (p.positionCoM.size() != p.velocityCoM.size() || p.positionCoM.size() != p.RPY.size()
+            || p.positionCoM.size() != p.RPYDot.size() || p.positionCoM.size() % 3 != 0)
+            return error("trajectory arrays differ in length");
+        vsmpc_config c;
+        detail::fill_config(p, c);
+        const int rc = vsmpc_create(&c, nInstances, device, &m_h);
+        if (rc != VSMPC_OK)
+        {
+            const std::string msg = m_h ? vsmpc_last_error(m_h) : "vsmpc_create failed";
+            destroy();
+            return error(msg);
+        }
+        m_B = nInstances;
+        return true;
+    }
+    // pack: double[VSMPC_PACK_DOUBLES][B]; jointPosSel: double[8][B]; phase0: int[B] or nullptr
+    bool configure(const double* pack, const double* jointPosSel, const int* phase0 = nullptr)
+    {
+        return check(vsmpc_configure(m_h, pack, jointPosSel, phase0));
+    }
+    bool update(const double* pack) { return check(vsmpc_set_state(m_h, pack)); }
+    bool updateDevice(const double* packDev) { return check(vsmpc_set_state_device(m_h, packDev)); }
+    bool solveMPC() { return check(vsmpc_solve(m_h)); }
+    bool solveAsync() { return check(vsmpc_solve_async(m_h)); }
+    bool wait() { return check(vsmpc_wait(m_h)); }
+    // rows: double[B][VSMPC_OUT_DOUBLES], status: int[B]
+    bool getOutput(double* rows, int* status) { return check(vsmpc_get_output(m_h, rows, status)); }
+    bool setFullSolution(bool on) { return check(vsmpc_set_full_solution(m_h, on ? 1 : 0)); }
+    bool getSolution(double* z) { return check(vsmpc_get_full_solution(m_h, z)); }
+    int getNOptimizationVariables() const { return vsmpc_n_var(m_h); }
+    int getNConstraints() const { return vsmpc_n_constraints(m_h); }
+    int nInstances() const { return m_B; }
+    vsmpc_handle* handle() { return m_h; }
+    const std::string& lastError() const { return m_err; }
+
+private:
+    void destroy()
+    {
+        if (m_h)
+            vsmpc_destroy(m_h);
+        m_h = nullptr;
+        m_B = 0;
+    }
+    bool error(const std::string& msg)
+    {
+        m_err = msg;
+        std::cerr << "[vsmpc] " << msg << std::endl; // the reference logs through yError()
+        return false;
+    }
+    bool check(int rc)
+    {
+        if (rc == VSMPC_OK)
+            return true;
+        return error(m_h ? vsmpc_last_error(m_h) : "null handle");
+    }
+    vsmpc_handle* m_h = nullptr;
+    int m_B = 0;
+    std::string m_err;
+};
+
+// ---- drop-in for the reference class (one instance) ---------------------------------------------------------
+class VariableSamplingMPC
+{
+public:
+    // IMPCProblem::configure(parametersHandler, qpInput) (IMPCProblem.cpp:3-148).  `pack` carries what the
+    // costs/constraints read from QPInput/Robot at configure time; jointPos = Robot::getJointPos() (all
+    // joints); controlledJoints = indices of the 8 controlled joints in that vector
+    // (m_jointSelectorVector, variableSamplingMPC.cpp:25-37).
+    bool configure(const Params& p, const Pack& pack, const std::vector<double>& jointPos,
+                   const std::vector<int>& controlledJoints, int device = 0)
+    {
+        if (controlledJoints.size() != VSMPC_NJ)
+        {
+            std::cerr << "[vsmpc] The number of controlled joints defined in the systemDynamic.h file is different "
+                         "from the size of the 'controlledJoints' parameter"
+                      << std::endl; // variableSamplingMPC.cpp:18-23
+            return false;
+        }
+        for (int j : controlledJoints)
+            if (j < 0 || j >= static_cast<int>(jointPos.size()))
+                return false;
+        m_sel = controlledJoints;
+        m_jointsPositionReference = jointPos; // variableSamplingMPC.cpp:60
+        if (!m_impl.create(p, 1, device) || !m_impl.setFullSolution(true))
+            return false;
+        double jp[VSMPC_NJ];
+        for (int a = 0; a < VSMPC_NJ; ++a)
+            jp[a] = jointPos[m_sel[a]];
+        m_nIter = p.nIter;
+        m_ctrlHorizon = p.controlHorizon;
+        m_nThrottleBlocks = p.controlHorizon - p.nIterSmall + 1;
+        std::memset(m_out, 0, sizeof(m_out));
+        m_status = 0;
+        return m_impl.configure(pack.v, jp);
+    }
+    // IMPCProblem::update(QPInput&) (IMPCProblem.cpp:150-194)
+    bool update(const Pack& pack) { return m_impl.update(pack.v); }
+    // VariableSamplingMPC::solveMPC (variableSamplingMPC.cpp:88-112); like the reference it returns true
+    // also when the solver status is not "solved" (outputs are then held)
+    bool solveMPC()
+    {
+        if (!m_impl.solveMPC() || !m_impl.getOutput(m_out, &m_status))
+            return false;
+        for (int a = 0; a < VSMPC_NJ; ++a)
+            m_jointsPositionReference[m_sel[a]] = m_out[VSMPC_OUT_JOINTS_REF + a];
+        return true;
+    }
+    template <class V> bool getJointsReferencePosition(V&& out) const
+    {
+        return copyOut(out, m_jointsPositionReference.data(), m_jointsPositionReference.size(), "getJointsReferencePosition");
+    }
+    template <class V> bool getThrottleReference(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_THROTTLE, VSMPC_NT, "getThrottleReference"); }
+    template <class V> bool getThrustReference(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_THRUST, VSMPC_NT, "getThrustReference"); }
+    template <class V> bool getThrustDotReference(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_THRUST_DOT, VSMPC_NT, "getThrustDotReference"); }
+    template <class V> bool getFinalCoMPosition(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_FINAL_STATE + 0, 3, "getFinalCoMPosition"); }
+    template <class V> bool getFinalLinMom(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_FINAL_STATE + 3, 3, "getFinalLinMom"); }
+    template <class V> bool getFinalRPY(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_FINAL_STATE + 6, 3, "getFinalRPY"); }
+    template <class V> bool getFinalAngMom(V&& out) const { return copyOut(out, m_out + VSMPC_OUT_FINAL_STATE + 9, 3, "getFinalAngMom"); }
+    // the 120 inputs [dq_0..dq_11 | v_0..v_5] (the reference's size check at variableSamplingMPC.cpp:116 is
+    // inconsistent with its assignment; here the vector must have nInputs elements)
+    template <class V> bool getMPCSolution(V&& out)
+    {
+        const int nVar = m_impl.getNOptimizationVariables();
+        const int nIn = VSMPC_NJ * m_ctrlHorizon + VSMPC_NT * m_nThrottleBlocks;
+        if (static_cast<int>(out.size()) != nIn)
+            return false;
+        std::vector<double> z(nVar);
+        if (!m_impl.getSolution(z.data()))
+            return false;
+        std::memcpy(out.data(), z.data() + (nVar - nIn), sizeof(double) * nIn);
+        return true;
+    }
+    template <class V> bool getSolution(V&& out)
+    {
+        if (static_cast<int>(out.size()) != m_impl.getNOptimizationVariables())
+            return false;
+        return m_impl.getSolution(out.data());
+    }
+    double getNStatesMPC() const { return VSMPC_NX; }
+    double getNInputMPC() const { return VSMPC_NJ + VSMPC_NT; }
+    int getNOptimizationVariables() const { return m_impl.getNOptimizationVariables(); }
+    int getNConstraints() const { return m_impl.getNConstraints(); }
+    int getQPProblemStatus() const { return m_status; }
+    BatchedMPC& impl() { return m_impl; }
+
+private:
+    template <class V> static bool copyOut(V&& out, const double* src, size_t n, const char* who)
+    {
+        if (static_cast<size_t>(out.size()) != n)
+        {
+            std::cerr << "[vsmpc] VariableSamplingMPC::" << who << ": wrong size of the input vector" << std::endl;
+            return false;
+        }
+        std::memcpy(out.data(), src, sizeof(double) * n);
+        return true;
+    }
+    BatchedMPC m_impl;
+    std::vector<int> m_sel;
+    std::vector<double> m_jointsPositionReference;
+    double m_out[VSMPC_OUT_DOUBLES];
+    int m_status = 0;
+    int m_nIter = 0, m_ctrlHorizon = 0, m_nThrottleBlocks = 0;
+};
+
+} // namespace vsmpc
+#endif // VSMPC_ADAPTER_HPP

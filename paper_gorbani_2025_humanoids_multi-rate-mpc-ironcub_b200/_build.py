@@ -56,5 +56,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_examples(force: bool = False) -> str:
+    """C++ host example over include/vsmpc_adapter.hpp (g++ only; links libvsmpc.so by relative rpath)."""
+    src = os.path.join(ROOT, "examples", "cpp_controller.cpp")
+    out_dir = os.path.join(ROOT, "examples", "bin")
+    exe = os.path.join(out_dir, "cpp_controller")
+    deps = [src, os.path.join(ROOT, "include", "vsmpc_adapter.hpp"), os.path.join(ROOT, "include", "vsmpc.h"), LIB]
+    if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
+        return exe
+    os.makedirs(out_dir, exist_ok=True)
+    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), src,
+           "-L", HERE, "-lvsmpc", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE), "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
