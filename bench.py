@@ -236,7 +236,7 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": achieved / tf.value if tf.value > 0 else None, "traffic": traffic,
-                "kernel": "qp_structured_kernel" if args.solver == 0 else "qp_generic_kernel",
+                "kernel": {0: "qp_condensed_kernel", 1: "qp_generic_kernel", 2: "qp_structured_kernel"}[args.solver],
                 "peak_source": "DFMA microbenchmark on this device in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "dmma_peak_tflops": tf_dmma.value,
                 "flops_per_solve": F, "n_factor_mean": nf_mean, "n_solve_mean": ns_mean,
@@ -253,7 +253,7 @@ def run_ours(args):
                                "(17 knots, 7 fine + 10 coarse), perturbed states (SURVEY §8d Config 2)",
                    "instances_per_gpu": B, "n_var": mpc.n_var, "n_con": mpc.n_con,
                    "l2": "flushed (256 MiB memset) between timed steps", "pack_sets": n_sets,
-                   "solver": "structured" if args.solver == 0 else "generic-dense",
+                   "solver": {0: "condensed", 1: "generic-dense", 2: "structured"}[args.solver],
                    "phase": "20-tick phase staggered across instances"},
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(packs[0].nbytes),
                 "d2h_bytes_per_step": int(h_out.numel() * 8 + h_status.numel() * 4),

@@ -28,6 +28,11 @@ size_t structured_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_structured(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                  double* ws, double* scratch, double* z, double* st, double* out_rows, int* status,
                                  int* n_factor, int* n_solve, int want_z, cudaStream_t s);
+bool condensed_supported(const DeviceConfig& cfg);
+size_t condensed_ws_doubles(const DeviceConfig& cfg);
+cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
+                                double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
+                                int* n_solve, int want_z, cudaStream_t s);
 } // namespace vsmpc
 
 using namespace vsmpc;
@@ -199,12 +204,18 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
 
     h->B = n_instances;
     h->device = device;
+    // solver routing: 0 = default (condensed-throttle Riccati kernel; horizons it does not cover fall back to the
+    // structured one-warp kernel), 1 = generic dense variant, 2 = structured one-warp kernel
+    if (c->solver < 0 || c->solver > 2)
+        return bail(VSMPC_ERR_ARG, "solver must be 0 (default), 1 (generic) or 2 (structured)");
     h->solver = c->solver;
+    if (h->solver == 0 && !condensed_supported(g))
+        h->solver = 2;
     const int B = n_instances;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess)
         return bail(VSMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-    const size_t scratch = h->solver == 1 ? generic_scratch_doubles(g) : structured_scratch_doubles(g);
+    const size_t scratch = h->solver == 1 ? generic_scratch_doubles(g) : (h->solver == 2 ? structured_scratch_doubles(g) : 4);
     bool ok = true;
     auto A = [&](cudaError_t r) { ok = ok && (r == cudaSuccess); if (r != cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -221,7 +232,12 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(dalloc(&h->d_trpy, tr.size()));
     A(dalloc(&h->d_trpyd, td.size()));
     A(dalloc(&h->d_qd, (size_t)g.qd_stride * B));
-    A(dalloc(&h->d_ws, (size_t)g.N * WS_STAGE * B));
+    {
+        size_t wsd = (size_t)g.N * WS_STAGE;
+        if (condensed_ws_doubles(g) > wsd)
+            wsd = condensed_ws_doubles(g);
+        A(dalloc(&h->d_ws, wsd * B));
+    }
     A(dalloc(&h->d_scratch, scratch * B));
     A(dalloc(&h->d_z, (size_t)g.n_var * B));
     A(dalloc(&h->d_out, (size_t)VSMPC_OUT_DOUBLES * B));
@@ -357,7 +373,10 @@ int vsmpc_solve_async(vsmpc_handle* h)
     if (!h->has_state)
         return fail(h, VSMPC_ERR_STATE, "vsmpc_solve: no state set since configure (call vsmpc_set_state)");
     CK(cudaSetDevice(h->device));
-    if (h->solver == 1)
+    if (h->solver == 0)
+        CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
+                               h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+    else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));
     else

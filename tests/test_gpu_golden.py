@@ -13,7 +13,7 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
-@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("solver", [0, 1, 2])
 def test_single_tick_golden(solver):
     g = golden("golden_qp.npz")
     bat = pkg("batched")
@@ -40,7 +40,7 @@ def test_single_tick_golden(solver):
         mpc.close()
 
 
-@pytest.mark.parametrize("solver,full", [(0, False), (0, True), (1, True)])
+@pytest.mark.parametrize("solver,full", [(0, False), (0, True), (1, True), (2, False)])
 def test_tick_sequence_golden(solver, full):
     """24 consecutive ticks: reference-window shift and throttle release on tick 20, alpha_g cursor, RPY
     unwrapping through +-pi, joint accumulator, output hold — all device-resident state."""

@@ -29,7 +29,7 @@ def make(B, solver, seed=20251002, near=0.10, params=None, full=True):
     return mpc, nom, per, traj
 
 
-@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("solver", [0, 1, 2])
 def test_linearise_matches_oracle(solver):
     B = 24
     mpc, nom, per, traj = make(B, solver)
@@ -52,7 +52,7 @@ def test_linearise_matches_oracle(solver):
     mpc.close()
 
 
-@pytest.mark.parametrize("solver", [0, 1])
+@pytest.mark.parametrize("solver", [0, 1, 2])
 @pytest.mark.parametrize("free_tick", [False, True])
 def test_solve_matches_exact_oracle(solver, free_tick):
     B = 32
@@ -84,11 +84,12 @@ def test_solve_matches_exact_oracle(solver, free_tick):
     mpc.close()
 
 
+@pytest.mark.parametrize("solver", [0, 2])
 @pytest.mark.parametrize("free_tick", [False, True])
-def test_outputs_without_full_solution(free_tick):
+def test_outputs_without_full_solution(solver, free_tick):
     """Default mode of the structured kernel: outputs by superposition, no 588-vector written."""
     B = 192
-    mpc, nom, per, traj = make(B, 0, near=0.3, full=False)
+    mpc, nom, per, traj = make(B, solver, near=0.3, full=False)
     mpc.configure(nom)
     if free_tick:
         mpc.debug_set_counters(-1, 19)

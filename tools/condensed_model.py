@@ -1,0 +1,197 @@
+"""Development model (NumPy) of K2 v3: Riccati recursion on the 26 states with the throttle blocks carried
+as *parameter columns*, followed by a dense box-QP in the <= 24 throttle variables.
+
+NOT the oracle and NOT on the product path: the executable specification of csrc/vsmpc_qp_condensed.cu
+(tests/test_oracle.py compares it with the oracle's exact dense solve).
+
+Value function at knot k, theta = (v_0 .. v_{nblk-1}, 1, dq_held):
+    V_k(x; theta) = 1/2 x'P x + x'Psi theta + 1/2 theta'Om theta
+  * P   (26 x 26): the ordinary Riccati matrix of the joint-increment LQR (8 x 8 eliminations) — independent of
+    the throttle columns ("warp A" of the kernel);
+  * Psi (26 x 32), Om (32 x 32): linear propagation / rank-8 downdates ("warp B"); column l lives on lane l:
+    lanes 4b..4b+3 = throttle block b, lane 24 = affine column (references, c, gradients), and during the tail
+    (knots >= Nc-1, where joint block Nc-1 is held) lanes D0..D0+7 = the held joint increments.
+After knot 0:  reduced Hessian H_r = Om_vv + Laplacian + w_i E_0, gradient from Psi' x0 and the affine column;
+dual active set on the boxes with the explicit inverse G = H_r^-1; one forward pass with the stored gains
+K_k (8 x 26) and F_k (8 x 32).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NX, NJ, NT4 = 26, 8, 4
+NL = 32          # parameter columns = lanes of warp B
+AFF = 24         # affine column
+LA = [3, 4, 5, 9, 10, 11]   # rows of B_J that are non-zero (linear / angular momentum)
+
+
+def block_maps(N, Ns, Nc):
+    jb = [min(k, Nc - 1) for k in range(N)]
+    tb = [0 if k < Ns else (k - (Ns - 1) if k < Nc else Nc - Ns) for k in range(N)]
+    return jb, tb
+
+
+class CondensedQP:
+    def __init__(self, Ac, BJ, BT, c, dt, Qd, xref, Rqd, gq, w_t, w_i, vbar, pinned, vmin, vmax, x0,
+                 N, Ns, Nc):
+        self.__dict__.update(locals())
+        self.jb, self.tb = block_maps(N, Ns, Nc)
+        self.nblk = Nc - Ns + 1
+        assert 4 * self.nblk <= AFF
+        self.D0 = 0 if self.nblk >= 3 else 16     # lanes of the held joint block during the tail
+        self.held = Nc - 1 < N - 1                # joint block Nc-1 spans more than one knot
+
+    def _D(self, k):
+        """x+ = T x + B_u u + D theta: columns of D at knot k."""
+        D = np.zeros((NX, NL))
+        b = self.tb[k]
+        D[:, 4 * b:4 * b + 4] = self.dt[k] * self.BT
+        D[:, AFF] = self.dt[k] * self.c
+        if self.held and k >= self.Nc - 1:
+            D[:, self.D0:self.D0 + NJ] = self.dt[k] * self.BJ
+        return D
+
+    def factor(self):
+        N, Nc = self.N, self.Nc
+        P = np.zeros((NX, NX))
+        Psi = np.zeros((NX, NL))
+        Om = np.zeros((NL, NL))
+        self.K = [None] * N
+        self.F = [None] * N
+        I = np.eye(NX)
+        for k in range(N - 1, -1, -1):
+            T = I + self.dt[k] * self.Ac
+            Bu = self.dt[k] * self.BJ
+            D = self._D(k)
+            Pp = P + np.diag(self.Qd)                       # P'
+            Psp = Psi.copy()                                # Psi' incl. the tracking gradient of x_{k+1}
+            Psp[:, AFF] -= self.Qd * self.xref[k]
+            Ps2 = Psp + Pp @ D                              # Psi''
+            PT = T.T @ Pp @ T
+            PsT = T.T @ Ps2
+            OmT = Om + D.T @ Ps2 + Psp.T @ D
+            tail = self.held and k >= Nc - 1
+            if not tail:
+                # fresh joint block: eliminate inside the stage
+                Huu = np.diag(self.Rqd) + Bu.T @ Pp @ Bu
+                Hux = Bu.T @ Pp @ T
+                Hut = Bu.T @ Ps2
+                Hut[:, AFF] += self.gq
+            elif k == Nc - 1:
+                # held block: it was a parameter through the tail; Schur complement on its columns
+                d = slice(self.D0, self.D0 + NJ)
+                Huu = OmT[d, d] + np.diag(self.Rqd)
+                Hux = PsT[:, d].T.copy()
+                Hut = OmT[d, :].copy()
+                Hut[:, AFF] += self.gq
+                Hut[:, d] = 0.0
+                PsT[:, d] = 0.0
+                OmT[d, :] = 0.0
+                OmT[:, d] = 0.0
+            else:
+                P, Psi, Om = PT, PsT, OmT
+                continue
+            Hi = np.linalg.inv(Huu)
+            Kk = Hi @ Hux
+            Fk = Hi @ Hut
+            P = PT - Hux.T @ Kk
+            Psi = PsT - Hux.T @ Fk
+            Om = OmT - Hut.T @ Fk
+            self.K[k], self.F[k] = Kk, Fk
+        self.P0, self.Psi0, self.Om0 = P, Psi, Om
+
+    def reduced_qp(self):
+        """min 1/2 v'H v + g'v over the free throttle variables (block 0 removed when pinned)."""
+        nv = 4 * self.nblk
+        H = self.Om0[:nv, :nv].copy()
+        g = self.Psi0[:, :nv].T @ self.x0 + self.Om0[:nv, AFF]
+        L = np.zeros((self.nblk, self.nblk))
+        for b in range(self.nblk - 1):
+            L[b, b] += 1; L[b + 1, b + 1] += 1; L[b, b + 1] -= 1; L[b + 1, b] -= 1
+        H += self.w_t * np.kron(L, np.eye(4))
+        H[:4, :4] += self.w_i * np.eye(4)
+        g[:4] -= self.w_i * self.vbar
+        first = 4 if self.pinned else 0
+        if self.pinned:
+            g = g[4:] + H[4:, :4] @ self.vbar
+            H = H[4:, 4:]
+        return H, g, first
+
+    def solve_box(self, max_iter=200, tol=1e-10):
+        self.factor()
+        H, g, first = self.reduced_qp()
+        G = np.linalg.inv(H)
+        vv = -G @ g
+        lo, up = self.vmin, self.vmax
+        W, sgn, lam = [], [], []
+        status, it = 0, 0
+        while True:
+            viol_up, viol_lo = vv - up, lo - vv
+            viol = np.maximum(viol_up, viol_lo)
+            for i in W:
+                viol[i] = -np.inf
+            p = int(np.argmax(viol))
+            if viol[p] <= tol:
+                break
+            s = 1.0 if viol_up[p] > viol_lo[p] else -1.0
+            lam_p = 0.0
+            while True:
+                it += 1
+                if it > max_iter:
+                    status = 1
+                    break
+                gp = G[:, p]
+                if W:
+                    GWW = np.array([[G[i, j] * sgn[a] * sgn[b] for b, j in enumerate(W)] for a, i in enumerate(W)])
+                    GWp = np.array([gp[i] * sgn[a] * s for a, i in enumerate(W)])
+                    r = np.linalg.solve(GWW, GWp)
+                    zdir = s * gp - sum(r[a] * sgn[a] * G[:, j] for a, j in enumerate(W))
+                else:
+                    r = np.zeros(0)
+                    zdir = s * gp
+                zp = s * zdir[p]
+                t2 = (s * vv[p] - s * (up if s > 0 else lo)) / zp if zp > 1e-300 else np.inf
+                t1, drop = np.inf, -1
+                for a in range(len(W)):
+                    if r[a] > 0 and lam[a] / r[a] < t1:
+                        t1, drop = lam[a] / r[a], a
+                t = min(t1, t2)
+                if not np.isfinite(t):
+                    status = 2
+                    break
+                vv = vv - t * zdir
+                for a in range(len(W)):
+                    lam[a] -= t * r[a]
+                lam_p += t
+                if t == t2:
+                    W.append(p); sgn.append(s); lam.append(lam_p)
+                    break
+                W.pop(drop); sgn.pop(drop); lam.pop(drop)
+            if status:
+                break
+        for i, s in zip(W, sgn):
+            vv[i] = up if s > 0 else lo
+        self.active = list(zip(W, sgn, lam))
+        self.status = status
+        v = np.concatenate([self.vbar, vv]) if self.pinned else vv
+        return self.forward(v.reshape(self.nblk, 4))
+
+    def forward(self, v):
+        N = self.N
+        theta = np.zeros(NL)
+        theta[:4 * self.nblk] = v.reshape(-1)
+        theta[AFF] = 1.0
+        x = np.zeros((N + 1, NX))
+        dq = np.zeros((self.Nc, NJ))
+        x[0] = self.x0
+        I = np.eye(NX)
+        for k in range(N):
+            if self.K[k] is not None:
+                u = -self.K[k] @ x[k] - self.F[k] @ theta
+                dq[self.jb[k]] = u
+            u = dq[self.jb[k]]
+            x[k + 1] = (I + self.dt[k] * self.Ac) @ x[k] + self.dt[k] * (self.BJ @ u + self.BT @ v[self.tb[k]] + self.c)
+        return x, dq, v
+
+    def pack_z(self, x, dq, v):
+        return np.concatenate([x.reshape(-1), dq.reshape(-1), v.reshape(-1)])
