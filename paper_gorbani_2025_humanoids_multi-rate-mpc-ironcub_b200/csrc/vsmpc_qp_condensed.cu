@@ -285,7 +285,6 @@ __device__ __forceinline__ bool a_eliminate(const CdCtx& c, CdSlot& sl, double (
     return ok;
 }
 
-#define CD_DIAG_CASE(J) case J: p[J] += qd_lane; break;
 // propagation of P through knot k: P' = P + Q, publish P'D, P <- T'P'T; with elim also H_ux (published) and this
 // lane's pair of H_uu = R + B_u' P' B_u
 __device__ __forceinline__ void a_prop(const CdCtx& c, int k, bool elim, double (&p)[NX], double qd_lane,
@@ -296,15 +295,11 @@ __device__ __forceinline__ void a_prop(const CdCtx& c, int k, bool elim, double 
     const double* cf = sm.cf;
     const double dt = sm.dtk[k];
     CdSlot& sl = sm.slot[k & 1];
-    switch (lane)
-    { // P' = P + Q on the diagonal element this lane owns
-        CD_DIAG_CASE(0) CD_DIAG_CASE(1) CD_DIAG_CASE(2) CD_DIAG_CASE(3) CD_DIAG_CASE(4) CD_DIAG_CASE(5) CD_DIAG_CASE(6)
-        CD_DIAG_CASE(7) CD_DIAG_CASE(8) CD_DIAG_CASE(9) CD_DIAG_CASE(10) CD_DIAG_CASE(11) CD_DIAG_CASE(12)
-        CD_DIAG_CASE(13) CD_DIAG_CASE(14) CD_DIAG_CASE(15) CD_DIAG_CASE(16) CD_DIAG_CASE(17) CD_DIAG_CASE(18)
-        CD_DIAG_CASE(19) CD_DIAG_CASE(20) CD_DIAG_CASE(21) CD_DIAG_CASE(22) CD_DIAG_CASE(23) CD_DIAG_CASE(24)
-        CD_DIAG_CASE(25)
-    default: break;
-    }
+    // P' = P + Q on the diagonal element this lane owns (predicated add: keeps the compiler from turning the
+    // 26-way ownership test into a divergent jump table)
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+        asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q add.f64 %0, %0, %3; }" : "+d"(p[j]) : "r"(lane), "r"(j), "d"(qd_lane));
     if (lane < NX)
     {
         // P'D for the special columns of this knot
@@ -409,19 +404,30 @@ __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&
     __syncwarp();
     if (lane < NLO)
     {
+        // rows i0.. in groups of 3 (all loads of a group before its stores; two FMA chains per row)
 #pragma unroll 1
-        for (int i = i0; i < NLO; ++i)
+        for (int i = i0; i < NLO; i += 3)
         {
-            const double2* hr = reinterpret_cast<const double2*>(sm.Hut + i * LDH);
-            double acc = sm.Om[i * NLO + lane];
+            double acc0[3], acc1[3];
 #pragma unroll
-            for (int m = 0; m < NJ / 2; ++m)
+            for (int u = 0; u < 3; ++u)
             {
-                const double2 hh = hr[m];
-                acc = fma(-hh.x, F[2 * m], acc);
-                acc = fma(-hh.y, F[2 * m + 1], acc);
+                const int iu = min(i + u, NLO - 1);
+                const double2* hr = reinterpret_cast<const double2*>(sm.Hut + iu * LDH);
+                const double2 h0 = hr[0], h1 = hr[1], h2 = hr[2], h3 = hr[3];
+                acc0[u] = fma(-h0.x, F[0], sm.Om[iu * NLO + lane]);
+                acc1[u] = -h0.y * F[1];
+                acc0[u] = fma(-h1.x, F[2], acc0[u]);
+                acc1[u] = fma(-h1.y, F[3], acc1[u]);
+                acc0[u] = fma(-h2.x, F[4], acc0[u]);
+                acc1[u] = fma(-h2.y, F[5], acc1[u]);
+                acc0[u] = fma(-h3.x, F[6], acc0[u]);
+                acc1[u] = fma(-h3.y, F[7], acc1[u]);
             }
-            sm.Om[i * NLO + lane] = acc;
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (i + u < NLO)
+                    sm.Om[(i + u) * NLO + lane] = acc0[u] + acc1[u];
         }
     }
     __syncwarp();
