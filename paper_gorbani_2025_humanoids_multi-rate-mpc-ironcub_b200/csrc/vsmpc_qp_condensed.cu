@@ -55,12 +55,13 @@ struct alignas(16) CdSmem
     double Rqd[NJ];
     double dtk[CD_MAXN];
     double xref[12 * CD_MAXNC];
-    alignas(16) double Ks[NJ * NX];         // warp A: gain rows of the knot in flight
     CdSlot slot[2];             // A -> B mailbox, slot = knot & 1; after the factorisation: G and the working-set inverse
-    double Mt[NX * LDM];        // warp A: transposition buffer; after the factorisation: F theta, x, dq
+    alignas(16) double Mt[NX * LDM];        // warp A: transposition buffer, then the gain rows K [8][26] of the knot in
+                                // flight; after the factorisation: F theta, x, dq
     double Om[NLO * NLO];
     alignas(16) double Hut[NLO * LDH];      // warp B: H_utheta of the knot in flight; after the factorisation: active-set vectors
     alignas(16) double theta[NL];
+    unsigned short tri[NLO * (NLO + 1) / 2 + 3];   // (i << 8 | j) of the row-major upper triangle of Om
     int flags[4];
 };
 
@@ -249,29 +250,29 @@ __device__ __forceinline__ bool a_eliminate(const CdCtx& c, CdSlot& sl, double (
     if (lane < NX)
     {
         const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
-#pragma unroll
+#pragma unroll 1
         for (int a = 0; a < NJ; ++a)
         {
-            double v = 0.0;
+            double v0 = 0.0, v1 = 0.0;
 #pragma unroll
             for (int m = 0; m < NJ / 2; ++m)
             {
                 const double2 hh = hi[a * (NJ / 2) + m];
-                v = fma(hh.x, hux[2 * m], v);
-                v = fma(hh.y, hux[2 * m + 1], v);
+                v0 = fma(hh.x, hux[2 * m], v0);
+                v1 = fma(hh.y, hux[2 * m + 1], v1);
             }
-            sm.Ks[a * NX + lane] = v;
-            wsk[WSC_K + a * NX + lane] = v;
+            sm.Mt[a * NX + lane] = v0 + v1;
+            wsk[WSC_K + a * NX + lane] = v0 + v1;
         }
     }
     __syncwarp();
     if (lane < NX)
     {
-#pragma unroll
+#pragma unroll 2
         for (int m = 0; m < NJ; ++m)
         {
-            const double h = hux[m];
-            const double2* kr = reinterpret_cast<const double2*>(sm.Ks + m * NX);
+            const double h = sl.Hux[m * NX + lane];
+            const double2* kr = reinterpret_cast<const double2*>(sm.Mt + m * NX);
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j)
             {
@@ -302,38 +303,45 @@ __device__ __forceinline__ void a_prop(const CdCtx& c, int k, bool elim, double 
         asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q add.f64 %0, %0, %3; }" : "+d"(p[j]) : "r"(lane), "r"(j), "d"(qd_lane));
     if (lane < NX)
     {
-        // P'D for the special columns of this knot
+        // P'D for the throttle / affine columns of this knot
         const double jgt = cf[QD_JGT];
 #pragma unroll
         for (int q = 0; q < NT; ++q)
             sl.PD[lane * NPD + q] = dt * (cf[QD_JG + q] * p[IX_TD + q] + jgt * p[IX_T + q]);
         sl.PD[lane * NPD + 4] = c_dot(p, cf, dt);
-        double pdd[NJ];
-        bjT_dot(p, sm.lam, dt, pdd);
-#pragma unroll
-        for (int a = 0; a < NJ; ++a)
-            sl.PD[lane * NPD + 5 + a] = pdd[a];
-        applyTtx(p, cf, dt);                       // row i of M = P' T
-#pragma unroll
-        for (int j = 0; j < NX; ++j)
-            sm.Mt[lane * LDM + j] = p[j];
     }
-    __syncwarp();
-    if (lane < NX)
+    // pass 0: (P'D)_joint = dt P' B_J from row i of P', then row i of M = P'T, transposition;
+    // pass 1: H_ux[:, i] = B_u' M[:, i] from column i of M, then column i of T'M = row i of T'P'T
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass)
     {
+        if (lane < NX)
+        {
+            if (pass == 0 || elim)
+            {
+                bjT_dot(p, sm.lam, dt, hux);
+                double* dst = pass == 0 ? sl.PD + lane * NPD + 5 : sl.Hux + lane;
+                const int stride = pass == 0 ? 1 : NX;
 #pragma unroll
-        for (int j = 0; j < NX; ++j)
-            p[j] = sm.Mt[j * LDM + lane];          // column i of M
-    }
-    if (elim && lane < NX)
-    {
-        bjT_dot(p, sm.lam, dt, hux);               // H_ux[:, i] = B_u' M[:, i]
+                for (int a = 0; a < NJ; ++a)
+                    dst[a * stride] = hux[a];
+            }
+            applyTtx(p, cf, dt);
+            if (pass == 0)
+            {
 #pragma unroll
-        for (int m = 0; m < NJ; ++m)
-            sl.Hux[m * NX + lane] = hux[m];
+                for (int j = 0; j < NX; ++j)
+                    sm.Mt[lane * LDM + j] = p[j];
+            }
+        }
+        __syncwarp();
+        if (pass == 0 && lane < NX)
+        {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                p[j] = sm.Mt[j * LDM + lane];
+        }
     }
-    if (lane < NX)
-        applyTtx(p, cf, dt);                       // column i of T' M = row i of T' P' T
     if (elim)
     {
         // H_uu[r][2q..2q+1] = R + dt Lambda[:, r]' (P'D)_joint[momentum rows, 2q..2q+1]
@@ -358,41 +366,45 @@ __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&
 {
     CdSmem& sm = c.sm;
     const int lane = c.lane;
+    double* Fs = sl.PD;   // the P'D columns of this knot were consumed by b_prop: reuse as F [l][LDH]
     if (lane < NLO)
     {
 #pragma unroll
         for (int m = 0; m < NJ; ++m)
             sm.Hut[lane * LDH + m] = hut[m];
     }
-    double F[NJ];
     {
         const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
-#pragma unroll
+#pragma unroll 1
         for (int a = 0; a < NJ; ++a)
         {
-            double v = 0.0;
+            double v0 = 0.0, v1 = 0.0;
 #pragma unroll
             for (int m = 0; m < NJ / 2; ++m)
             {
                 const double2 hh = hi[a * (NJ / 2) + m];
-                v = fma(hh.x, hut[2 * m], v);
-                v = fma(hh.y, hut[2 * m + 1], v);
+                v0 = fma(hh.x, hut[2 * m], v0);
+                v1 = fma(hh.y, hut[2 * m + 1], v1);
             }
-            F[a] = v;
-            wsk[WSC_F + a * NL + lane] = v;
+            if (lane < NLO)
+                Fs[lane * LDH + a] = v0 + v1;
+            wsk[WSC_F + a * NL + lane] = v0 + v1;
         }
     }
-#pragma unroll
-    for (int m = 0; m < NJ; ++m)
+    if (lane < NLO)
     {
-        const double f = F[m];
-        const double2* hr = reinterpret_cast<const double2*>(sl.Hux + m * NX);
-#pragma unroll
-        for (int j = 0; j < NX / 2; ++j)
+#pragma unroll 2
+        for (int m = 0; m < NJ; ++m)
         {
-            const double2 hh = hr[j];
-            s[2 * j] = fma(-f, hh.x, s[2 * j]);
-            s[2 * j + 1] = fma(-f, hh.y, s[2 * j + 1]);
+            const double f = Fs[lane * LDH + m];
+            const double2* hr = reinterpret_cast<const double2*>(sl.Hux + m * NX);
+#pragma unroll
+            for (int j = 0; j < NX / 2; ++j)
+            {
+                const double2 hh = hr[j];
+                s[2 * j] = fma(-f, hh.x, s[2 * j]);
+                s[2 * j + 1] = fma(-f, hh.y, s[2 * j + 1]);
+            }
         }
     }
     if (clear_col)
@@ -402,32 +414,29 @@ __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&
             s[j] = 0.0;
     }
     __syncwarp();
-    if (lane < NLO)
+    // Om[i][j] -= H_ut[:, i]' F[:, j] on the upper triangle of the live rows (i0 <= i <= j), mirrored
     {
-        // rows i0.. in groups of 3 (all loads of a group before its stores; two FMA chains per row)
+        const int e0 = i0 * NLO - (i0 * (i0 - 1)) / 2;          // first entry of row i0 in the row-major triangle
 #pragma unroll 1
-        for (int i = i0; i < NLO; i += 3)
+        for (int e = e0 + lane; e < NLO * (NLO + 1) / 2; e += 32)
         {
-            double acc0[3], acc1[3];
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-            {
-                const int iu = min(i + u, NLO - 1);
-                const double2* hr = reinterpret_cast<const double2*>(sm.Hut + iu * LDH);
-                const double2 h0 = hr[0], h1 = hr[1], h2 = hr[2], h3 = hr[3];
-                acc0[u] = fma(-h0.x, F[0], sm.Om[iu * NLO + lane]);
-                acc1[u] = -h0.y * F[1];
-                acc0[u] = fma(-h1.x, F[2], acc0[u]);
-                acc1[u] = fma(-h1.y, F[3], acc1[u]);
-                acc0[u] = fma(-h2.x, F[4], acc0[u]);
-                acc1[u] = fma(-h2.y, F[5], acc1[u]);
-                acc0[u] = fma(-h3.x, F[6], acc0[u]);
-                acc1[u] = fma(-h3.y, F[7], acc1[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 3; ++u)
-                if (i + u < NLO)
-                    sm.Om[(i + u) * NLO + lane] = acc0[u] + acc1[u];
+            const int ij = sm.tri[e];
+            const int i = ij >> 8, j = ij & 255;
+            const double2* hr = reinterpret_cast<const double2*>(sm.Hut + i * LDH);
+            const double2* fr = reinterpret_cast<const double2*>(Fs + j * LDH);
+            const double2 h0 = hr[0], h1 = hr[1], h2 = hr[2], h3 = hr[3];
+            const double2 f0 = fr[0], f1 = fr[1], f2 = fr[2], f3 = fr[3];
+            double a0 = fma(-h0.x, f0.x, sm.Om[i * NLO + j]);
+            double a1 = -h0.y * f0.y;
+            a0 = fma(-h1.x, f1.x, a0);
+            a1 = fma(-h1.y, f1.y, a1);
+            a0 = fma(-h2.x, f2.x, a0);
+            a1 = fma(-h2.y, f2.y, a1);
+            a0 = fma(-h3.x, f3.x, a0);
+            a1 = fma(-h3.y, f3.y, a1);
+            const double v = a0 + a1;
+            sm.Om[i * NLO + j] = v;
+            sm.Om[j * NLO + i] = v;
         }
     }
     __syncwarp();
@@ -636,6 +645,13 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         sm.Rqd[threadIdx.x] = cfg.Rqd[threadIdx.x];
     if (threadIdx.x < N)
         sm.dtk[threadIdx.x] = cfg.dt[threadIdx.x];
+    if (threadIdx.x < NLO)
+    {
+        const int i = threadIdx.x;
+        const int e0 = i * NLO - (i * (i - 1)) / 2;
+        for (int j = i; j < NLO; ++j)
+            sm.tri[e0 + j - i] = (unsigned short)((i << 8) | j);
+    }
     for (int e = threadIdx.x; e < 6 * NJ; e += CD_THREADS)
         sm.lam[e] = qd[(e < 3 * NJ ? QD_LLIN : QD_LANG - 3 * NJ) + e];
     const bool all_fin = __syncthreads_and(fin);
