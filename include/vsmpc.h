@@ -172,6 +172,56 @@ int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve);
  * ThrottleConstraint::m_counter) of every instance; -1 leaves a counter unchanged */
 int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter);
 
+/* ---- device-resident closed loop (the loop body of src/variable_sampling_mpc.py:106-161) --------
+ * A SURROGATE plant replaces MuJoCo (not available): it integrates the MPC's own nonlinear model
+ * (centroidal momentum driven by the four jets, gravity, and the second-order jet model of
+ * src/mujoco_lib/jet_kalman_filter.py:30-45) with frozen body-frame kinematics, n_sub steps of dt_sim per
+ * controller tick, and rebuilds the pack from the plant state on the device.  Per tick: plant -> pack ->
+ * linearise kernel -> QP kernel -> feedback (:124-131); no host round trip. */
+#define VSMPC_PS_P_COM            0   /* 3  CoM position (world)                                         */
+#define VSMPC_PS_LIN_MOM_WORLD    3   /* 3  linear momentum (world)                                      */
+#define VSMPC_PS_RPY              6   /* 3  base roll / pitch / yaw                                      */
+#define VSMPC_PS_ANG_MOM_BODY     9   /* 3  angular momentum about the CoM (body)                        */
+#define VSMPC_PS_THRUST          12   /* 4  jet thrusts                                                  */
+#define VSMPC_PS_THRUST_DOT      16   /* 4  jet thrust rates                                             */
+#define VSMPC_PS_THROTTLE        20   /* 4  throttle command in effect [percent]  (QPInput::setThrottleMPC)     */
+#define VSMPC_PS_THRUST_DES      24   /* 4  QPInput::setThrustDesMPC                                     */
+#define VSMPC_PS_THRUST_DOT_DES  28   /* 4  QPInput::setThrustDotDesMPC                                  */
+#define VSMPC_PS_Q_CMD           32   /* 8  QPInput::setOutputQPJointsPosition (controlled joints)        */
+#define VSMPC_PLANT_STATE_DOUBLES 40
+#define VSMPC_PP_MASS             0   /* 1  total mass (float-rounded like Robot::m_totalMass)           */
+#define VSMPC_PP_INERTIA_BODY     1   /* 9  locked inertia about the CoM, body frame, row-major          */
+#define VSMPC_PP_THRUST_DISTURBANCE 10 /* 4 constant thrust disturbance added in the plant [N]            */
+#define VSMPC_PLANT_PARAM_DOUBLES 14
+/* recorded per instance and recorded tick: p_com(3) rpy(3) thrust(4) throttle(4) status(1) pad(1) */
+#define VSMPC_ROLLOUT_REC_DOUBLES 16
+
+typedef struct vsmpc_plant_model
+{
+    double com_from_base_body[3];
+    double jet_pos_body[12];      /* 4x3, jet positions relative to the CoM, body frame                  */
+    double jet_axes_body[12];     /* 4x3, thrust directions, body frame                                  */
+    double J_rel_ang_body[96];    /* 4x3x8 angular relative Jacobians of the jets, controlled joints     */
+    double J_jet_lin_body[96];    /* 4x3x8 linear Jacobians of the jet frames (body frame)               */
+    double J_com_body[24];        /* 3x8  CoM Jacobian, joint part (body frame)                          */
+    double gravity[3];
+    double dt_sim;                /* plant step (reference: MuJoCo timestep 1 ms)                        */
+    int n_sub;                    /* plant steps per controller tick (reference: periodMPC / dt = 5)     */
+} vsmpc_plant_model;
+
+/* upload the plant, build the first pack on the device and run configure (tick 0) from it.
+ * plant_state: double[VSMPC_PLANT_STATE_DOUBLES][B]; plant_param: double[VSMPC_PLANT_PARAM_DOUBLES][B];
+ * joint_pos_sel: double[8][B]; phase0: int[B] or NULL (as in vsmpc_configure) */
+int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const double* plant_state_host,
+                       const double* plant_param_host, const double* joint_pos_sel_host, const int* phase0_host);
+/* n_ticks closed-loop controller ticks.  record_every > 0: every record_every-th tick (after the plant step) a
+ * record row per instance is written; rec_host receives double[n_ticks / record_every][B][VSMPC_ROLLOUT_REC_DOUBLES].
+ * With use_graph != 0 the three kernels of a tick are captured once in a CUDA graph and replayed. */
+int vsmpc_rollout_run(vsmpc_handle* h, int n_ticks, int record_every, double* rec_host, int use_graph);
+int vsmpc_rollout_get_state(vsmpc_handle* h, double* plant_state_host);
+/* the pack the plant built for the next tick (double[VSMPC_PACK_DOUBLES][B]) — parity tests */
+int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host);
+
 /* measured FP64 throughput of `device` in TFLOP/s: kind 0 = DFMA on the CUDA cores, kind 1 = DMMA
  * (mma.sync.m8n8k4.f64).  Used as the roofline denominator of the QP kernel (bench.py). */
 int vsmpc_microbench_fp64(int device, int kind, double* tflops);

@@ -42,12 +42,28 @@ class VsmpcConfig(C.Structure):
     ]
 
 
+PLANT_STATE_DOUBLES, PLANT_PARAM_DOUBLES, ROLLOUT_REC_DOUBLES = 40, 14, 16
+PS_P_COM, PS_LIN_MOM_WORLD, PS_RPY, PS_ANG_MOM_BODY, PS_THRUST, PS_THRUST_DOT = 0, 3, 6, 9, 12, 16
+PS_THROTTLE, PS_THRUST_DES, PS_THRUST_DOT_DES, PS_Q_CMD = 20, 24, 28, 32
+PP_MASS, PP_INERTIA_BODY, PP_THRUST_DISTURBANCE = 0, 1, 10
+
+
+class VsmpcPlantModel(C.Structure):
+    _fields_ = [
+        ("com_from_base_body", C.c_double * 3), ("jet_pos_body", C.c_double * 12),
+        ("jet_axes_body", C.c_double * 12), ("J_rel_ang_body", C.c_double * 96),
+        ("J_jet_lin_body", C.c_double * 96), ("J_com_body", C.c_double * 24), ("gravity", C.c_double * 3),
+        ("dt_sim", C.c_double), ("n_sub", C.c_int),
+    ]
+
+
 EXPORTS = [
     "vsmpc_create", "vsmpc_destroy", "vsmpc_last_error", "vsmpc_set_stream", "vsmpc_n_var",
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
     "vsmpc_get_output_device", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
     "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_microbench_fp64",
+    "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_get_pack",
 ]
 
 _lib = None
@@ -84,6 +100,10 @@ def load() -> C.CDLL:
     lib.vsmpc_get_counts.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
     lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]
+    lib.vsmpc_rollout_init.argtypes = [H, C.POINTER(VsmpcPlantModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vsmpc_rollout_run.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.vsmpc_rollout_get_state.argtypes = [H, C.c_void_p]
+    lib.vsmpc_rollout_get_pack.argtypes = [H, C.c_void_p]
     for f in EXPORTS:
         if f != "vsmpc_last_error":
             getattr(lib, f).restype = C.c_int

@@ -9,9 +9,13 @@
 #include <vector>
 
 #include "vsmpc_common.cuh"
+#include "vsmpc_plant.cuh"
 
 namespace vsmpc
 {
+cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
+                         const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
+                         cudaStream_t s);
 cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
@@ -64,6 +68,12 @@ struct vsmpc_handle
     double* d_out = nullptr;
     int* d_status = nullptr;
     int *d_nf = nullptr, *d_ns = nullptr;
+    // device-resident closed loop
+    PlantModel* d_pm = nullptr;
+    double* d_ps = nullptr;
+    double* d_pp = nullptr;
+    bool rollout_ready = false;
+    cudaGraphExec_t tick_graph = nullptr;
     std::string err;
 };
 
@@ -108,6 +118,8 @@ template <typename T> cudaError_t dalloc(T** p, size_t n)
 } // namespace
 
 extern "C" {
+
+static int solve_launch(vsmpc_handle* h);
 
 const char* vsmpc_last_error(const vsmpc_handle* h)
 {
@@ -279,7 +291,9 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns};
+                    h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp};
+    if (h->tick_graph)
+        cudaGraphExecDestroy(h->tick_graph);
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -373,15 +387,11 @@ int vsmpc_solve_async(vsmpc_handle* h)
     if (!h->has_state)
         return fail(h, VSMPC_ERR_STATE, "vsmpc_solve: no state set since configure (call vsmpc_set_state)");
     CK(cudaSetDevice(h->device));
-    if (h->solver == 0)
-        CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
-                               h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
-    else if (h->solver == 1)
-        CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
-                             h->d_status, h->d_nf, h->d_ns, h->stream));
-    else
-        CK(launch_qp_structured(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
-                                h->d_status, h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+    {
+        const int rc = solve_launch(h);
+        if (rc)
+            return rc;
+    }
     h->has_state = false; // one solve per update, like the reference's tick
     return VSMPC_OK;
 }
@@ -526,6 +536,175 @@ int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_coun
         std::fill(v.begin(), v.end(), throttle_counter);
         CK(cudaMemcpy(h->d_si + (size_t)SI_THR_COUNTER * h->B, v.data(), (size_t)h->B * 4, cudaMemcpyHostToDevice));
     }
+    return VSMPC_OK;
+}
+
+// ---- device-resident closed loop ----------------------------------------------------------------------------------
+static_assert(sizeof(PlantModel) == sizeof(vsmpc_plant_model), "PlantModel must mirror vsmpc_plant_model");
+
+static int solve_launch(vsmpc_handle* h)
+{
+    if (h->solver == 0)
+        CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
+                               h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+    else if (h->solver == 1)
+        CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
+                             h->d_status, h->d_nf, h->d_ns, h->stream));
+    else
+        CK(launch_qp_structured(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
+                                h->d_status, h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const double* plant_state_host,
+                       const double* plant_param_host, const double* joint_pos_sel_host, const int* phase0_host)
+{
+    if (!h || h->B <= 0 || !model || !plant_state_host || !plant_param_host || !joint_pos_sel_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_init: null argument");
+    if (!(model->dt_sim > 0) || model->n_sub < 1)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_init: dt_sim must be positive and n_sub >= 1");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->B;
+    if (!h->d_pm)
+    {
+        CK(dalloc(&h->d_pm, 1));
+        CK(dalloc(&h->d_ps, (size_t)PS_ROWS * B));
+        CK(dalloc(&h->d_pp, (size_t)PP_ROWS * B));
+    }
+    if (h->tick_graph)
+    {
+        cudaGraphExecDestroy(h->tick_graph);
+        h->tick_graph = nullptr;
+    }
+    CK(cudaMemcpyAsync(h->d_pm, model, sizeof(PlantModel), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ps, plant_state_host, PS_ROWS * B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_pp, plant_param_host, PP_ROWS * B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_jpos, joint_pos_sel_host, NJ * B * 8, cudaMemcpyHostToDevice, h->stream));
+    if (phase0_host)
+    {
+        for (size_t i = 0; i < B; ++i)
+            if (phase0_host[i] < 0 || phase0_host[i] >= h->cfg.ratio)
+                return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_init: phase0 out of [0, ratio)");
+        CK(cudaMemcpyAsync(h->d_phase, phase0_host, B * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    else
+        CK(cudaMemsetAsync(h->d_phase, 0, B * 4, h->stream));
+    // first pack from the plant state, then IMPCProblem::configure on it (tick 0 of every counter)
+    CK(launch_plant(h->d_cfg, h->d_pm, h->B, 0, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, nullptr, h->stream));
+    int rc = run_linearise(h, 1);
+    if (rc)
+        return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->configured = true;
+    h->has_state = false;
+    h->rollout_ready = true;
+    return VSMPC_OK;
+}
+
+static int tick_launch(vsmpc_handle* h, double* rec)
+{
+    int rc = run_linearise(h, 0);
+    if (rc)
+        return rc;
+    rc = solve_launch(h);
+    if (rc)
+        return rc;
+    CK(launch_plant(h->d_cfg, h->d_pm, h->B, 1, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, rec, h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_rollout_run(vsmpc_handle* h, int n_ticks, int record_every, double* rec_host, int use_graph)
+{
+    if (!h || h->B <= 0 || n_ticks < 0 || record_every < 0)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_run: bad argument");
+    if (!h->rollout_ready)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_rollout_run: call vsmpc_rollout_init first");
+    if (record_every > 0 && !rec_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_run: rec_host missing");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->B;
+    const int n_rec = record_every > 0 ? n_ticks / record_every : 0;
+    double* d_rec = nullptr;
+    if (n_rec > 0)
+        CK(dalloc(&d_rec, (size_t)n_rec * B * PLANT_REC));
+    if (use_graph && !h->tick_graph)
+    {
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        int rc = e == cudaSuccess ? tick_launch(h, nullptr) : VSMPC_ERR_CUDA;
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
+        if (e != cudaSuccess || rc != VSMPC_OK || e2 != cudaSuccess)
+        {
+            if (g)
+                cudaGraphDestroy(g);
+            if (d_rec)
+                cudaFree(d_rec);
+            return fail(h, VSMPC_ERR_CUDA, "vsmpc_rollout_run: graph capture failed");
+        }
+        e = cudaGraphInstantiate(&h->tick_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess)
+        {
+            if (d_rec)
+                cudaFree(d_rec);
+            return cuda_fail(h, e, "cudaGraphInstantiate");
+        }
+    }
+    int rc = VSMPC_OK;
+    int rec_i = 0;
+    for (int t = 0; t < n_ticks && rc == VSMPC_OK; ++t)
+    {
+        const bool record = record_every > 0 && (t + 1) % record_every == 0 && rec_i < n_rec;
+        if (use_graph && !record)
+        {
+            cudaError_t e = cudaGraphLaunch(h->tick_graph, h->stream);
+            if (e != cudaSuccess)
+                rc = cuda_fail(h, e, "cudaGraphLaunch");
+        }
+        else
+        {
+            rc = tick_launch(h, record ? d_rec + (size_t)rec_i * B * PLANT_REC : nullptr);
+            if (record)
+                ++rec_i;
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (rc == VSMPC_OK && n_rec > 0)
+        e = cudaMemcpyAsync(rec_host, d_rec, (size_t)n_rec * B * PLANT_REC * 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(h->stream);
+    if (d_rec)
+        cudaFree(d_rec);
+    if (rc != VSMPC_OK)
+        return rc;
+    if (e != cudaSuccess)
+        return cuda_fail(h, e, "rollout record copy");
+    if (e3 != cudaSuccess)
+        return cuda_fail(h, e3, "vsmpc_rollout_run");
+    h->has_state = false;
+    return VSMPC_OK;
+}
+
+int vsmpc_rollout_get_state(vsmpc_handle* h, double* plant_state_host)
+{
+    if (!h || h->B <= 0 || !plant_state_host)
+        return VSMPC_ERR_ARG;
+    if (!h->rollout_ready)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_rollout_get_state: call vsmpc_rollout_init first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(plant_state_host, h->d_ps, (size_t)PS_ROWS * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host)
+{
+    if (!h || h->B <= 0 || !pack_host)
+        return VSMPC_ERR_ARG;
+    if (!h->rollout_ready)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_rollout_get_pack: call vsmpc_rollout_init first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(pack_host, h->d_pack, (size_t)VSMPC_PACK_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return VSMPC_OK;
 }
 

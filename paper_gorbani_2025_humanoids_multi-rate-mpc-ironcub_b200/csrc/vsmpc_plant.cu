@@ -1,0 +1,328 @@
+// Device-resident closed loop: surrogate plant + pack builder, one thread per instance.
+//
+// Replaces, for batched rollouts, the loop body of the reference driver around the MPC tick
+// (src/variable_sampling_mpc.py:106-161): sim.update_robot_state() -> [update + solveMPC] -> feedback of
+// throttle / desired thrust / desired thrust rate / joint references into QPInput (:124-131) -> sim.step(n).
+// MuJoCo, the URDF and iDynTree are outside the hot path and not available: the plant is a
+// SURROGATE that integrates the MPC's own nonlinear model with frozen body-frame kinematics:
+//   jets      : Tdd = sigma_T (f(T,Td) + g(T,Td) v(u)), semi-implicit Euler exactly as
+//               src/mujoco_lib/jet_kalman_filter.py:30-45 (Td += Tdd dt; T += Td dt)
+//   momentum  : h_lin^w' = m g + sum_i (T_i + dT_i) R a_i ;  h_ang^B' = -w_B x h_ang^B + sum_i (T_i + dT_i) r_i x a_i
+//   pose      : p' = h_lin^w / m ;  rpy' = W^-1(rpy) w_B,  w_B = I_B^-1 h_ang^B
+//   joints    : position-controlled, q = q_cmd (the accumulated MPC joint reference)
+// and rebuilds the getter-level pack (include/vsmpc.h VSMPC_PK_*) from the plant state every tick.
+#include "vsmpc_common.cuh"
+#include "vsmpc_plant.cuh"
+
+namespace vsmpc
+{
+
+__device__ __forceinline__ void rpy_to_R(const double* rpy, double* R)
+{
+    const double cr = cos(rpy[0]), sr = sin(rpy[0]), cp = cos(rpy[1]), sp = sin(rpy[1]), cy = cos(rpy[2]), sy = sin(rpy[2]);
+    R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+    R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+    R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+}
+
+__device__ __forceinline__ void mat3_vec(const double* M, const double* v, double* o)
+{
+    o[0] = M[0] * v[0] + M[1] * v[1] + M[2] * v[2];
+    o[1] = M[3] * v[0] + M[4] * v[1] + M[5] * v[2];
+    o[2] = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+}
+__device__ __forceinline__ void mat3T_vec(const double* M, const double* v, double* o)
+{
+    o[0] = M[0] * v[0] + M[3] * v[1] + M[6] * v[2];
+    o[1] = M[1] * v[0] + M[4] * v[1] + M[7] * v[2];
+    o[2] = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+}
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ bool inv3(const double* M, double* o)
+{
+    const double c0 = M[4] * M[8] - M[5] * M[7], c1 = M[5] * M[6] - M[3] * M[8], c2 = M[3] * M[7] - M[4] * M[6];
+    const double det = M[0] * c0 + M[1] * c1 + M[2] * c2;
+    const double id = 1.0 / det;
+    o[0] = c0 * id; o[1] = (M[2] * M[7] - M[1] * M[8]) * id; o[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    o[3] = c1 * id; o[4] = (M[0] * M[8] - M[2] * M[6]) * id; o[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    o[6] = c2 * id; o[7] = (M[1] * M[6] - M[0] * M[7]) * id; o[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+    return det != 0.0 && isfinite(id);
+}
+
+// mode 0: build the pack from the plant state only (tick 0 / configure)
+// mode 1: apply the MPC outputs of the tick just solved (feedback, src/variable_sampling_mpc.py:124-131),
+//         integrate n_sub plant steps, record, build the next pack
+__global__ void __launch_bounds__(128)
+plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict__ pmp, int B, int mode,
+             double* __restrict__ ps, const double* __restrict__ pp, const double* __restrict__ out_rows,
+             const int* __restrict__ status, double* __restrict__ pack, double* __restrict__ rec)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B)
+        return;
+    const DeviceConfig& cfg = *cfgp;
+    const PlantModel& pm = *pmp;
+    const Jet jet{cfg.jc, cfg.jn};
+#define PS(r) ps[(size_t)(r) * B + i]
+#define PP(r) pp[(size_t)(r) * B + i]
+#define PK(r) pack[(size_t)(r) * B + i]
+    double p[3], hl[3], rpy[3], ha[3], T[NT], Td[NT], u[NT], Tdes[NT], Tddes[NT], q[NJ];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        p[a] = PS(PS_PCOM + a);
+        hl[a] = PS(PS_HLIN_W + a);
+        rpy[a] = PS(PS_RPY + a);
+        ha[a] = PS(PS_HANG_B + a);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        T[j] = PS(PS_T + j);
+        Td[j] = PS(PS_TD + j);
+        u[j] = PS(PS_THROTTLE + j);
+        Tdes[j] = PS(PS_TDES + j);
+        Tddes[j] = PS(PS_TDDES + j);
+    }
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+        q[a] = PS(PS_QCMD + a);
+    const double mass = PP(PP_MASS);
+    double Ib[9], Ibinv[9], dT[NT];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+        Ib[a] = PP(PP_INERTIA + a);
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+        dT[j] = PP(PP_DTHRUST + j);
+    inv3(Ib, Ibinv);
+
+    if (mode == 1)
+    {
+        // feedback of the tick just solved; a non-solved instance holds its previous outputs, which is what
+        // out_rows still contains (variableSamplingMPC.cpp:91)
+        const double* o = out_rows + (size_t)i * VSMPC_OUT_DOUBLES;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+        {
+            u[j] = o[VSMPC_OUT_THROTTLE + j];
+            Tdes[j] = o[VSMPC_OUT_THRUST + j];
+            Tddes[j] = o[VSMPC_OUT_THRUST_DOT + j];
+        }
+#pragma unroll
+        for (int a = 0; a < NJ; ++a)
+            q[a] = o[VSMPC_OUT_JOINTS_REF + a];
+        // torque arms r_i x a_i (body, frozen)
+        double rxa[NT][3];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            cross3(pm.jet_pos_body + 3 * j, pm.jet_axes_body + 3 * j, rxa[j]);
+        const double dt = pm.dt_sim;
+        for (int sstep = 0; sstep < pm.n_sub; ++sstep)
+        {
+            double R[9];
+            rpy_to_R(rpy, R);
+            // jets (jet_kalman_filter.py:30-45)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+            {
+                const double Ts = jet.stdT(T[j]), Tds = jet.stdTd(Td[j]);
+                const double tdd = jet.f(Ts, Tds) + jet.g(Ts, Tds) * jet.v(jet.stdU(u[j]));
+                Td[j] += tdd * cfg.jn[1] * dt;
+                T[j] += Td[j] * dt;
+            }
+            // momentum
+            double fB[3] = {0, 0, 0}, tauB[3] = {0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+            {
+                const double Tj = T[j] + dT[j];
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                {
+                    fB[a] += Tj * pm.jet_axes_body[3 * j + a];
+                    tauB[a] += Tj * rxa[j][a];
+                }
+            }
+            double fW[3], wB[3], wxh[3];
+            mat3_vec(R, fB, fW);
+            mat3_vec(Ibinv, ha, wB);
+            cross3(wB, ha, wxh);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                hl[a] += dt * (mass * pm.gravity[a] + fW[a]);
+                ha[a] += dt * (tauB[a] - wxh[a]);
+            }
+            // pose
+            mat3_vec(Ibinv, ha, wB);
+            const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), t1 = tan(rpy[1]), c1 = cos(rpy[1]);
+            const double rd0 = wB[0] + s0 * t1 * wB[1] + c0 * t1 * wB[2];
+            const double rd1 = c0 * wB[1] - s0 * wB[2];
+            const double rd2 = (s0 * wB[1] + c0 * wB[2]) / c1;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                p[a] += dt * hl[a] / mass;
+            rpy[0] += dt * rd0;
+            rpy[1] += dt * rd1;
+            rpy[2] += dt * rd2;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            PS(PS_PCOM + a) = p[a];
+            PS(PS_HLIN_W + a) = hl[a];
+            PS(PS_RPY + a) = rpy[a];
+            PS(PS_HANG_B + a) = ha[a];
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+        {
+            PS(PS_T + j) = T[j];
+            PS(PS_TD + j) = Td[j];
+            PS(PS_THROTTLE + j) = u[j];
+            PS(PS_TDES + j) = Tdes[j];
+            PS(PS_TDDES + j) = Tddes[j];
+        }
+#pragma unroll
+        for (int a = 0; a < NJ; ++a)
+            PS(PS_QCMD + a) = q[a];
+        if (rec)
+        {
+            double* r = rec + (size_t)i * PLANT_REC;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+            {
+                r[a] = p[a];
+                r[3 + a] = rpy[a];
+            }
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+            {
+                r[6 + j] = T[j];
+                r[10 + j] = u[j];
+            }
+            r[14] = (double)status[i];
+            r[15] = 0.0;
+        }
+    }
+
+    // ---- pack of the current plant state (the formulas of the synthetic robot, synthetic.py::make_states) ----
+    double R[9], wB[3], v3[3], c[3];
+    rpy_to_R(rpy, R);
+    mat3_vec(Ibinv, ha, wB);
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+        PK(VSMPC_PK_WRB + a) = R[a];
+    mat3_vec(R, wB, v3);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        PK(VSMPC_PK_OMEGA_WORLD + a) = v3[a];
+        PK(VSMPC_PK_RPY + a) = rpy[a];
+        PK(VSMPC_PK_GRAVITY + a) = pm.gravity[a];
+        PK(VSMPC_PK_P_COM + a) = p[a];
+    }
+    PK(VSMPC_PK_MASS) = mass;
+    mat3_vec(R, pm.com_from_base_body, c);     // p_com - p_base, world
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        PK(VSMPC_PK_BASE_POS + a) = p[a] - c[a];
+    {
+        // M_b = [m I, -m S(c); m S(c), R I_B R' + m S(c)'S(c)]
+        const double S[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+        double RI[9], Iw[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                RI[a * 3 + b] = R[a * 3] * Ib[b] + R[a * 3 + 1] * Ib[3 + b] + R[a * 3 + 2] * Ib[6 + b];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                Iw[a * 3 + b] = RI[a * 3] * R[b * 3] + RI[a * 3 + 1] * R[b * 3 + 1] + RI[a * 3 + 2] * R[b * 3 + 2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+            {
+                const double StS = S[0 * 3 + a] * S[0 * 3 + b] + S[1 * 3 + a] * S[1 * 3 + b] + S[2 * 3 + a] * S[2 * 3 + b];
+                PK(VSMPC_PK_MB + a * 6 + b) = a == b ? mass : 0.0;
+                PK(VSMPC_PK_MB + a * 6 + 3 + b) = -mass * S[a * 3 + b];
+                PK(VSMPC_PK_MB + (3 + a) * 6 + b) = mass * S[a * 3 + b];
+                PK(VSMPC_PK_MB + (3 + a) * 6 + 3 + b) = Iw[a * 3 + b] + mass * StS;
+            }
+    }
+    mat3T_vec(R, hl, v3);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        PK(VSMPC_PK_MOMENTUM_BODY + a) = v3[a];
+        PK(VSMPC_PK_MOMENTUM_BODY + 3 + a) = ha[a];
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        double aw[3], rw[3], rxaw[3], t3[3];
+        mat3_vec(R, pm.jet_axes_body + 3 * j, aw);
+        mat3_vec(R, pm.jet_pos_body + 3 * j, rw);
+        cross3(rw, aw, rxaw);
+        // A_mom_body = [R'a_w ; R'(r_w x a_w)]  (Robot::getMatrixAmomJets(true), Robot.cpp:325-329)
+        mat3T_vec(R, aw, t3);
+        double t4[3];
+        mat3T_vec(R, rxaw, t4);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            PK(VSMPC_PK_JET_AXES + 3 * j + a) = aw[a];
+            PK(VSMPC_PK_JET_ARMS + 3 * j + a) = rw[a];
+            PK(VSMPC_PK_AMOM_BODY + a * NT + j) = t3[a];
+            PK(VSMPC_PK_AMOM_BODY + (3 + a) * NT + j) = t4[a];
+        }
+        // relative Jacobians: angular part is body-frame data; linear Jacobians are world-frame (R J_body)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < NJ; ++b)
+            {
+                PK(VSMPC_PK_J_REL_ANG + j * 24 + a * NJ + b) = pm.J_rel_ang_body[j * 24 + a * NJ + b];
+                PK(VSMPC_PK_J_JET_LIN + j * 24 + a * NJ + b) = R[a * 3] * pm.J_jet_lin_body[j * 24 + b]
+                                                              + R[a * 3 + 1] * pm.J_jet_lin_body[j * 24 + NJ + b]
+                                                              + R[a * 3 + 2] * pm.J_jet_lin_body[j * 24 + 2 * NJ + b];
+            }
+        PK(VSMPC_PK_THRUST + j) = T[j];
+        PK(VSMPC_PK_THRUST_DOT_EST + j) = Td[j];
+        PK(VSMPC_PK_THRUST_DES + j) = Tdes[j];
+        PK(VSMPC_PK_THRUST_DOT_DES + j) = Tddes[j];
+        PK(VSMPC_PK_THROTTLE_PREV + j) = u[j];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < NJ; ++b)
+            PK(VSMPC_PK_J_COM + a * NJ + b) = R[a * 3] * pm.J_com_body[b] + R[a * 3 + 1] * pm.J_com_body[NJ + b]
+                                              + R[a * 3 + 2] * pm.J_com_body[2 * NJ + b];
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+        PK(VSMPC_PK_Q_CMD + a) = q[a];
+#undef PS
+#undef PP
+#undef PK
+}
+
+cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
+                         const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
+                         cudaStream_t s)
+{
+    const int threads = 128;
+    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec);
+    return cudaGetLastError();
+}
+
+} // namespace vsmpc

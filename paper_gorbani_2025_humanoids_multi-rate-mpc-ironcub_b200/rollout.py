@@ -1,0 +1,102 @@
+"""Device-resident closed-loop rollouts of a batch of MPC instances (BASELINE.json configs[2]).
+
+``BatchedRollout`` drives the loop body of the reference driver (src/variable_sampling_mpc.py:106-161) for B
+instances without a host round trip: surrogate plant -> pack -> linearise kernel -> QP kernel -> feedback, all
+on the GPU (csrc/vsmpc_plant.cu; the plant is a SURROGATE for MuJoCo, see include/vsmpc.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .batched import BatchedVSMPC, VsmpcError
+from .pack import DEFAULT_JOINT_SELECTOR
+from .synthetic import SyntheticRobot
+
+
+def plant_model_from_robot(rb: SyntheticRobot, sel=None, dt_sim: float = 0.001, n_sub: int = 5) -> L.VsmpcPlantModel:
+    """Frozen body-frame kinematics of the (synthetic) robot for the surrogate plant."""
+    sel = list(DEFAULT_JOINT_SELECTOR if sel is None else sel)
+    m = L.VsmpcPlantModel()
+    m.com_from_base_body = (C.c_double * 3)(*rb.com_from_base_body)
+    m.jet_pos_body = (C.c_double * 12)(*rb.jet_pos_body.reshape(-1))
+    m.jet_axes_body = (C.c_double * 12)(*rb.jet_axes_body.reshape(-1))
+    m.J_rel_ang_body = (C.c_double * 96)(*rb.J_rel_body[:, 3:6, :][:, :, sel].reshape(-1))
+    m.J_jet_lin_body = (C.c_double * 96)(*rb.J_jet_lin_body[:, :, sel].reshape(-1))
+    m.J_com_body = (C.c_double * 24)(*rb.J_com_body[:, sel].reshape(-1))
+    m.gravity = (C.c_double * 3)(*rb.gravity)
+    m.dt_sim = float(dt_sim)
+    m.n_sub = int(n_sub)
+    return m
+
+
+def plant_state_from_states(state: dict, sel=None) -> np.ndarray:
+    """(PLANT_STATE_DOUBLES, B) SoA plant state from a getter-level batch (synthetic.make_states)."""
+    sel = list(DEFAULT_JOINT_SELECTOR if sel is None else sel)
+    B = state["wRb"].shape[0]
+    ps = np.zeros((L.PLANT_STATE_DOUBLES, B))
+    ps[L.PS_P_COM:L.PS_P_COM + 3] = state["p_com"].T
+    ps[L.PS_LIN_MOM_WORLD:L.PS_LIN_MOM_WORLD + 3] = np.einsum("bij,bj->bi", state["wRb"], state["momentum_body"][:, :3]).T
+    ps[L.PS_RPY:L.PS_RPY + 3] = state["rpy"].T
+    ps[L.PS_ANG_MOM_BODY:L.PS_ANG_MOM_BODY + 3] = state["momentum_body"][:, 3:].T
+    ps[L.PS_THRUST:L.PS_THRUST + 4] = state["thrust"].T
+    ps[L.PS_THRUST_DOT:L.PS_THRUST_DOT + 4] = state["thrust_dot_est"].T
+    ps[L.PS_THROTTLE:L.PS_THROTTLE + 4] = state["throttle_prev"].T
+    ps[L.PS_THRUST_DES:L.PS_THRUST_DES + 4] = state["thrust_des"].T
+    ps[L.PS_THRUST_DOT_DES:L.PS_THRUST_DOT_DES + 4] = state["thrust_dot_des"].T
+    ps[L.PS_Q_CMD:L.PS_Q_CMD + 8] = state["q_cmd"][:, sel].T
+    return ps
+
+
+def plant_params(B: int, rb: SyntheticRobot, mass_scale=None, inertia_scale=None, thrust_disturbance=None) -> np.ndarray:
+    pp = np.zeros((L.PLANT_PARAM_DOUBLES, B))
+    ms = np.ones(B) if mass_scale is None else np.asarray(mass_scale, float)
+    isc = np.ones(B) if inertia_scale is None else np.asarray(inertia_scale, float)
+    pp[L.PP_MASS] = np.float32(rb.mass * ms).astype(np.float64)      # Robot::m_totalMass is a float
+    pp[L.PP_INERTIA_BODY:L.PP_INERTIA_BODY + 9] = rb.I_body.reshape(9, 1) * isc[None, :]
+    if thrust_disturbance is not None:
+        pp[L.PP_THRUST_DISTURBANCE:L.PP_THRUST_DISTURBANCE + 4] = np.asarray(thrust_disturbance, float).T
+    return pp
+
+
+class BatchedRollout:
+    """B closed loops on one GPU.  ``mpc`` is a fresh (not yet configured) BatchedVSMPC."""
+
+    def __init__(self, mpc: BatchedVSMPC, robot: SyntheticRobot | None = None, dt_sim: float = 0.001, n_sub: int = 5):
+        self.mpc = mpc
+        self.robot = robot or SyntheticRobot()
+        self.model = plant_model_from_robot(self.robot, mpc.sel, dt_sim, n_sub)
+        self._lib = mpc._lib
+
+    def init(self, state0: dict, mass_scale=None, inertia_scale=None, thrust_disturbance=None, phase0=None):
+        """Start every loop at ``state0``; runs IMPCProblem::configure on the pack built from it."""
+        B = self.mpc.B
+        ps = np.ascontiguousarray(plant_state_from_states(state0, self.mpc.sel))
+        pp = np.ascontiguousarray(plant_params(B, self.robot, mass_scale, inertia_scale, thrust_disturbance))
+        jp = np.ascontiguousarray(state0["joint_pos"][:, self.mpc.sel].T)
+        ph = None if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
+        self.mpc._ck(self._lib.vsmpc_rollout_init(self.mpc._h, C.byref(self.model), ps.ctypes.data, pp.ctypes.data,
+                                                  jp.ctypes.data, ph.ctypes.data if ph is not None else None),
+                     "vsmpc_rollout_init")
+
+    def run(self, n_ticks: int, record_every: int = 0, use_graph: bool = True):
+        """n_ticks controller ticks; returns the record array (n_rec, B, 16) or None."""
+        rec = None
+        if record_every > 0:
+            rec = np.empty((n_ticks // record_every, self.mpc.B, L.ROLLOUT_REC_DOUBLES))
+        self.mpc._ck(self._lib.vsmpc_rollout_run(self.mpc._h, int(n_ticks), int(record_every),
+                                                 rec.ctypes.data if rec is not None else None, 1 if use_graph else 0),
+                     "vsmpc_rollout_run")
+        return rec
+
+    def plant_state(self) -> np.ndarray:
+        ps = np.empty((L.PLANT_STATE_DOUBLES, self.mpc.B))
+        self.mpc._ck(self._lib.vsmpc_rollout_get_state(self.mpc._h, ps.ctypes.data), "vsmpc_rollout_get_state")
+        return ps
+
+    def pack(self) -> np.ndarray:
+        pk = np.empty((L.PACK_DOUBLES, self.mpc.B))
+        self.mpc._ck(self._lib.vsmpc_rollout_get_pack(self.mpc._h, pk.ctypes.data), "vsmpc_rollout_get_pack")
+        return pk
