@@ -56,7 +56,8 @@ def test_oracle_plant_pack_matches_host_pack():
         pl = oracle_plant(rb, st, i, ms[i], isc[i], dT[i])
         a, b = pl.robot_data(), robot_data(st, i)
         for k, v in a.__dict__.items():
-            np.testing.assert_allclose(v, getattr(b, k), rtol=1e-13, atol=1e-13, err_msg=k)
+            if isinstance(v, np.ndarray):
+                np.testing.assert_allclose(v, getattr(b, k), rtol=1e-13, atol=1e-13, err_msg=k)
 
 
 def test_oracle_closed_loop_is_stable():
