@@ -138,6 +138,17 @@ int vsmpc_n_instances(const vsmpc_handle* h);
 int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* joint_pos_sel_host,
                     const int* phase0_host);
 
+/* Per-instance model parameters (BASELINE.json configs[4]: jet time constants / thrust limits sweeps): one SoA
+ * buffer double[VSMPC_INSTANCE_PARAM_DOUBLES][B] replacing the handle-wide jet_coeff / jet_norm / throttle_min /
+ * throttle_max of vsmpc_config (JetModel.cpp:13-26, vs_mcp_config.xml throttleMin/Max) for every later call;
+ * NULL returns to the handle-wide values.  Mass and inertia are per instance already (they are in the pack). */
+#define VSMPC_IP_JET_COEFF      0   /* 13 */
+#define VSMPC_IP_JET_NORM      13   /* 4  thrust mean, thrust std, throttle mean, throttle std */
+#define VSMPC_IP_THROTTLE_MIN  17   /* 1  [percent] */
+#define VSMPC_IP_THROTTLE_MAX  18   /* 1  [percent] */
+#define VSMPC_INSTANCE_PARAM_DOUBLES 19
+int vsmpc_set_instance_params(vsmpc_handle* h, const double* instance_params_host);
+
 /* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel. */
 int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);
 /* same, pack already resident on the handle's GPU */

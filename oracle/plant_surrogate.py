@@ -33,7 +33,8 @@ def _S(v):
 
 
 class SurrogatePlant:
-    def __init__(self, geometry: dict, mass: float, I_body, thrust_disturbance, state: dict, dt_sim=0.001, n_sub=5):
+    def __init__(self, geometry: dict, mass: float, I_body, thrust_disturbance, state: dict, dt_sim=0.001, n_sub=5,
+                 jet_model=None):
         """geometry: com_from_base_body(3), jet_pos_body(4,3), jet_axes_body(4,3), J_rel_body(4,6,nJ),
         J_jet_lin_body(4,3,nJ), J_com_body(3,nJ), gravity(3), joint_pos0(nJ).  state: p_com, lin_mom_world, rpy,
         ang_mom_body, thrust, thrust_dot, throttle, thrust_des, thrust_dot_des, q_cmd(nJ)."""
@@ -44,7 +45,7 @@ class SurrogatePlant:
         self.dT = np.array(thrust_disturbance, float)
         self.s = {k: np.array(v, float) for k, v in state.items()}
         self.dt, self.n_sub = dt_sim, n_sub
-        self.jet = JetModel()
+        self.jet = jet_model or JetModel()
 
     def step(self):
         s, g, jet = self.s, self.g, self.jet
@@ -107,7 +108,7 @@ class SurrogateLoop:
         self.qp = O.QPInput()
         self.qp.setRobot(self.robot)
         self.qp.setRobotReference(self.robot)
-        self.qp.setEmptyJetModel()
+        self.qp.setJetModel(plant.jet)
         self._feed()
         self.mpc = O.VariableSamplingMPC()
         p = dict(O.default_params())

@@ -122,6 +122,21 @@ class BatchedVSMPC:
             raise VsmpcError(f"expected array of shape {shape}, got {a.shape}")
         return a
 
+    def set_instance_params(self, jet_coeff=None, jet_norm=None, throttle_min=None, throttle_max=None):
+        """Per-instance jet model (B,13)/(B,4) and throttle limits (B,) — configs[4] parameter sweeps.  ``None``
+        fields keep the handle-wide value; all ``None`` switches the per-instance table off."""
+        if jet_coeff is None and jet_norm is None and throttle_min is None and throttle_max is None:
+            self._ck(self._lib.vsmpc_set_instance_params(self._h, None), "vsmpc_set_instance_params")
+            return
+        B = self.B
+        ip = np.empty((L.INSTANCE_PARAM_DOUBLES, B))
+        ip[L.IP_JET_COEFF:L.IP_JET_COEFF + 13] = np.asarray(self.params.get("jetCoeff", JET_COEFF), float)[:, None] if jet_coeff is None else self._f64(jet_coeff, (B, 13)).T
+        ip[L.IP_JET_NORM:L.IP_JET_NORM + 4] = np.asarray(self.params.get("jetNorm", JET_NORM), float)[:, None] if jet_norm is None else self._f64(jet_norm, (B, 4)).T
+        ip[L.IP_THROTTLE_MIN] = self.params["throttleMin"] if throttle_min is None else self._f64(throttle_min, (B,))
+        ip[L.IP_THROTTLE_MAX] = self.params["throttleMax"] if throttle_max is None else self._f64(throttle_max, (B,))
+        ip = np.ascontiguousarray(ip)
+        self._ck(self._lib.vsmpc_set_instance_params(self._h, ip.ctypes.data), "vsmpc_set_instance_params")
+
     # ---- reference surface -------------------------------------------------------------------------
     def configure_pack(self, pack: np.ndarray, joint_pos_sel: np.ndarray, phase0=None) -> bool:
         """IMPCProblem::configure with the SoA pack (PACK_DOUBLES, B) and joint_pos_sel (8, B)."""

@@ -15,11 +15,12 @@ namespace vsmpc
 {
 cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
                          const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
-                         cudaStream_t s);
+                         const double* ip, cudaStream_t s);
 cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
-                             const double* traj_rpy, const double* traj_rpyd, double* qd, cudaStream_t s);
+                             const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
+                             cudaStream_t s);
 cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const double* qd, double* A, double* BJ,
                                    double* BT, double* c, cudaStream_t s);
 cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
@@ -72,6 +73,8 @@ struct vsmpc_handle
     PlantModel* d_pm = nullptr;
     double* d_ps = nullptr;
     double* d_pp = nullptr;
+    double* d_ip = nullptr;   // per-instance jet model / throttle limits (optional)
+    bool use_ip = false;
     bool rollout_ready = false;
     cudaGraphExec_t tick_graph = nullptr;
     std::string err;
@@ -291,7 +294,7 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp};
+                    h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp, h->d_ip};
     if (h->tick_graph)
         cudaGraphExecDestroy(h->tick_graph);
     for (void* p : ptrs)
@@ -318,7 +321,8 @@ int vsmpc_n_instances(const vsmpc_handle* h) { return h ? h->B : -1; }
 static int run_linearise(vsmpc_handle* h, int mode)
 {
     CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
-                        h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->stream));
+                        h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd,
+                        h->use_ip ? h->d_ip : nullptr, h->stream));
     return VSMPC_OK;
 }
 
@@ -345,6 +349,32 @@ int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* join
     CK(cudaStreamSynchronize(h->stream));
     h->configured = true;
     h->has_state = false;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_instance_params(vsmpc_handle* h, const double* ip_host)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!ip_host)
+    {
+        h->use_ip = false;
+        return VSMPC_OK;
+    }
+    const size_t B = h->B;
+    for (size_t i = 0; i < B; ++i)
+    {
+        const double c12 = ip_host[(size_t)(IP_JC + 12) * B + i], sd = ip_host[(size_t)(IP_JN + 3) * B + i];
+        const double tmin = ip_host[(size_t)IP_TMIN * B + i], tmax = ip_host[(size_t)IP_TMAX * B + i];
+        if (!(c12 != 0.0) || !(sd > 0.0) || !(ip_host[(size_t)(IP_JN + 1) * B + i] > 0.0) || !(tmin < tmax))
+            return fail(h, VSMPC_ERR_ARG, "vsmpc_set_instance_params: need c12 != 0, positive standard deviations, throttle_min < throttle_max");
+    }
+    if (!h->d_ip)
+        CK(dalloc(&h->d_ip, (size_t)IP_ROWS * B));
+    CK(cudaMemcpyAsync(h->d_ip, ip_host, (size_t)IP_ROWS * B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->use_ip = true;
     return VSMPC_OK;
 }
 
@@ -590,7 +620,8 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
     else
         CK(cudaMemsetAsync(h->d_phase, 0, B * 4, h->stream));
     // first pack from the plant state, then IMPCProblem::configure on it (tick 0 of every counter)
-    CK(launch_plant(h->d_cfg, h->d_pm, h->B, 0, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, nullptr, h->stream));
+    CK(launch_plant(h->d_cfg, h->d_pm, h->B, 0, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, nullptr,
+                    h->use_ip ? h->d_ip : nullptr, h->stream));
     int rc = run_linearise(h, 1);
     if (rc)
         return rc;
@@ -609,7 +640,8 @@ static int tick_launch(vsmpc_handle* h, double* rec)
     rc = solve_launch(h);
     if (rc)
         return rc;
-    CK(launch_plant(h->d_cfg, h->d_pm, h->B, 1, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, rec, h->stream));
+    CK(launch_plant(h->d_cfg, h->d_pm, h->B, 1, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, rec,
+                    h->use_ip ? h->d_ip : nullptr, h->stream));
     return VSMPC_OK;
 }
 

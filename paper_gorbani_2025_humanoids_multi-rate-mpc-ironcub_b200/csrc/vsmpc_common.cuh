@@ -44,6 +44,9 @@ constexpr int QD_VMAX = 157;  // 1
 constexpr int QD_PINNED = 158; // 1  1.0 when throttle block 0 is pinned to vbar this tick
 constexpr int QD_JTT = 159;   // 1   A[T_i, Td_i] (1 with jet dynamics, 0 without)
 constexpr int QD_JGT = 160;   // 1   B_T[T_i, i]  (0 with jet dynamics, 1 without)
+constexpr int QD_JC12 = 161;  // 1   jet coefficient c12 of this instance   } throttle de-standardisation
+constexpr int QD_UMEAN = 162; // 1   throttle mean                           } (JetModel.cpp:93-109) in the
+constexpr int QD_USTD = 163;  // 1   throttle standard deviation             } epilogue of the QP kernels
 constexpr int QD_XREF = 164;  // 12*NC  rows: pos(3) linMom(3) rpy(3) angMom(3); NC reference columns each
 
 // ---- per-instance persistent state (SoA, row = scalar, column = instance) ------------------------
@@ -114,6 +117,10 @@ __host__ __device__ inline int knot_kind(int k, int Ns, int Nc)
 // column of the reference window used by knot k (costsVSMPC.cpp:191-200)
 __host__ __device__ inline int ref_col(int k, int Ns) { return k < Ns ? 0 : k - Ns; }
 
+// per-instance parameter rows (optional SoA buffer [IP_ROWS][B]; absent: the handle's vsmpc_config values)
+constexpr int IP_JC = VSMPC_IP_JET_COEFF, IP_JN = VSMPC_IP_JET_NORM, IP_TMIN = VSMPC_IP_THROTTLE_MIN,
+              IP_TMAX = VSMPC_IP_THROTTLE_MAX, IP_ROWS = VSMPC_INSTANCE_PARAM_DOUBLES;
+
 // jet model, UT/src/JetModel.cpp:29-79
 struct Jet
 {
@@ -147,5 +154,14 @@ struct Jet
         return u;
     }
 };
+
+// JetModel::destandardizeThrottle_u2T with the instance's constants from the QP data block
+__device__ inline double destd_throttle_qd(const double* __restrict__ cf, double vv)
+{
+    const double c12 = cf[QD_JC12];
+    double u = (-1.0 + sqrt(1.0 + 4.0 * c12 * vv)) / (2.0 * c12);
+    u = u * cf[QD_USTD] + cf[QD_UMEAN];
+    return u < 0.0 ? 0.0 : (u > 100.0 ? 100.0 : u);
+}
 
 } // namespace vsmpc

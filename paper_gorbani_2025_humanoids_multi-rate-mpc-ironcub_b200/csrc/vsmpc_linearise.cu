@@ -170,26 +170,30 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
                  const int* __restrict__ phase0, double* __restrict__ st, int* __restrict__ si,
                  const double* __restrict__ alpha_traj, const double* __restrict__ traj_pos,
                  const double* __restrict__ traj_vel, const double* __restrict__ traj_rpy,
-                 const double* __restrict__ traj_rpyd, double* __restrict__ qd)
+                 const double* __restrict__ traj_rpyd, double* __restrict__ qd, const double* __restrict__ ip)
 {
-    extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12]
+    extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12] | ipar[20]
     const DeviceConfig& cfg = *cfgp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * K1_WARPS + warp;
     if (i >= B)
         return;
     const int NC = cfg.NC;
-    const int per_warp = 360 + cfg.qd_stride + 12;
+    const int per_warp = 360 + cfg.qd_stride + 12 + 20;
     double* pk = k1_smem + (size_t)warp * per_warp;
     double* out = pk + 360;
     double* colbuf = out + cfg.qd_stride;
+    double* ipar = colbuf + 12;   // jet coefficients (13), normalisation (4), throttle min / max of this instance
     const size_t Bs = (size_t)B;
 #define ST(f) st[(size_t)(f) * Bs + i]
 #define SI(f) si[(size_t)(f) * Bs + i]
     for (int f = lane; f < VSMPC_PACK_DOUBLES; f += 32)
         pk[f] = pack[(size_t)f * Bs + i];
+    if (lane < IP_ROWS)
+        ipar[lane] = ip ? ip[(size_t)lane * Bs + i]
+                        : (lane < IP_JN ? cfg.jc[lane] : (lane < IP_TMIN ? cfg.jn[lane - IP_JN] : (lane == IP_TMIN ? cfg.throttle_min : cfg.throttle_max)));
     __syncwarp();
-    const Jet jet{cfg.jc, cfg.jn};
+    const Jet jet{ipar + IP_JC, ipar + IP_JN};
     double R[9], rpy[3], pcom[3];
 #pragma unroll
     for (int a = 0; a < 9; ++a)
@@ -372,11 +376,13 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
             out[QD_WI + a] = WI[a];
         // throttle box / pin (constraintsVSMPC.cpp:338-374)
         out[QD_PINNED] = (tc != cfg.ratio - 1) ? 1.0 : 0.0;
-        out[QD_VMIN] = jet.v(jet.stdU(cfg.throttle_min));
-        out[QD_VMAX] = jet.v(jet.stdU(cfg.throttle_max));
+        out[QD_VMIN] = jet.v(jet.stdU(ipar[IP_TMIN]));
+        out[QD_VMAX] = jet.v(jet.stdU(ipar[IP_TMAX]));
         out[QD_JTT] = cfg.use_jet_dynamic ? 1.0 : 0.0;
         out[QD_JGT] = cfg.use_jet_dynamic ? 0.0 : 1.0;
-        out[QD_JGT + 1] = out[QD_JGT + 2] = out[QD_JGT + 3] = 0.0;
+        out[QD_JC12] = ipar[IP_JC + 12];
+        out[QD_UMEAN] = ipar[IP_JN + 2];
+        out[QD_USTD] = ipar[IP_JN + 3];
     }
     if (lane < 9)
         out[QD_RM + lane] = (1.0 / mass) * pk[VSMPC_PK_WRB + lane]; // 1/m * wRb (:296-297)
@@ -462,8 +468,8 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
             const double dh_dTd = jet.df_dTd(Tb, Tdb) + jet.dg_dTd(Tb, Tdb) * vu;
             out[QD_JA + j] = dh_dT;
             out[QD_JB + j] = dh_dTd;
-            out[QD_JG + j] = jet.g(jet.stdT(Tdes), jet.stdTd(Tddes)) * cfg.jn[1];
-            out[QD_CTD + j] = jet.f(Tb, Tdb) * cfg.jn[1] - dh_dT * T - dh_dTd * Td;
+            out[QD_JG + j] = jet.g(jet.stdT(Tdes), jet.stdTd(Tddes)) * ipar[IP_JN + 1];
+            out[QD_CTD + j] = jet.f(Tb, Tdb) * ipar[IP_JN + 1] - dh_dT * T - dh_dTd * Td;
         }
         else
             out[QD_JA + j] = out[QD_JB + j] = out[QD_JG + j] = out[QD_CTD + j] = 0.0;
@@ -643,9 +649,10 @@ __global__ void expand_qp_vectors_kernel(const DeviceConfig* __restrict__ cfgp, 
 cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
-                             const double* traj_rpy, const double* traj_rpyd, double* qd, cudaStream_t s)
+                             const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
+                             cudaStream_t s)
 {
-    const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12) * sizeof(double);
+    const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12 + 20) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set)
     {
@@ -656,7 +663,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
         return cudaErrorInvalidValue;
     const int grid = (B + K1_WARPS - 1) / K1_WARPS;
     linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(d_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
-                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd);
+                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip);
     return cudaGetLastError();
 }
 

@@ -60,14 +60,19 @@ __device__ __forceinline__ bool inv3(const double* M, double* o)
 __global__ void __launch_bounds__(128)
 plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict__ pmp, int B, int mode,
              double* __restrict__ ps, const double* __restrict__ pp, const double* __restrict__ out_rows,
-             const int* __restrict__ status, double* __restrict__ pack, double* __restrict__ rec)
+             const int* __restrict__ status, double* __restrict__ pack, double* __restrict__ rec,
+             const double* __restrict__ ip)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B)
         return;
     const DeviceConfig& cfg = *cfgp;
     const PlantModel& pm = *pmp;
-    const Jet jet{cfg.jc, cfg.jn};
+    double jpar[IP_TMIN];   // jet coefficients (13) + normalisation (4) of this instance
+#pragma unroll
+    for (int a = 0; a < IP_TMIN; ++a)
+        jpar[a] = ip ? ip[(size_t)a * B + i] : (a < IP_JN ? cfg.jc[a] : cfg.jn[a - IP_JN]);
+    const Jet jet{jpar + IP_JC, jpar + IP_JN};
 #define PS(r) ps[(size_t)(r) * B + i]
 #define PP(r) pp[(size_t)(r) * B + i]
 #define PK(r) pack[(size_t)(r) * B + i]
@@ -133,7 +138,7 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
             {
                 const double Ts = jet.stdT(T[j]), Tds = jet.stdTd(Td[j]);
                 const double tdd = jet.f(Ts, Tds) + jet.g(Ts, Tds) * jet.v(jet.stdU(u[j]));
-                Td[j] += tdd * cfg.jn[1] * dt;
+                Td[j] += tdd * jpar[IP_JN + 1] * dt;
                 T[j] += Td[j] * dt;
             }
             // momentum
@@ -318,10 +323,10 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 
 cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
                          const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
-                         cudaStream_t s)
+                         const double* ip, cudaStream_t s)
 {
     const int threads = 128;
-    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec);
+    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec, ip);
     return cudaGetLastError();
 }
 

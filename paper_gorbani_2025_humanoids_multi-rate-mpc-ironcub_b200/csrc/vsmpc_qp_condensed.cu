@@ -1119,9 +1119,8 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         __syncwarp();
     }
     // remaining outputs (variableSamplingMPC.cpp:96-108,138-151)
-    const Jet jet{cfg.jc, cfg.jn};
     if (lane < NT)
-        o[VSMPC_OUT_THROTTLE + lane] = jet.destdU(sm.theta[lane]);
+        o[VSMPC_OUT_THROTTLE + lane] = destd_throttle_qd(sm.cf, sm.theta[lane]);
     if (lane < NJ)
     {
         const double dq = o[VSMPC_OUT_DELTA_Q + lane];

@@ -762,7 +762,6 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
     {
         double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
         const int ibase = NX * (N + 1);
-        const Jet jet{cfg.jc, cfg.jn};
         if (lane < NJ)
         {
             const double dq = z[ibase + lane];
@@ -773,7 +772,7 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
         }
         if (lane < NT)
         {
-            o[VSMPC_OUT_THROTTLE + lane] = jet.destdU(z[ibase + cfg.Nc * NJ + lane]);
+            o[VSMPC_OUT_THROTTLE + lane] = destd_throttle_qd(qd, z[ibase + cfg.Nc * NJ + lane]);
             o[VSMPC_OUT_THRUST + lane] = z[NX + IX_T + lane];
             o[VSMPC_OUT_THRUST_DOT + lane] = z[NX + IX_TD + lane];
         }

@@ -1203,7 +1203,6 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
     {
         // output extraction (variableSamplingMPC.cpp:88-112): recb = [dq_0, x_1[T,Td], x_N], vv = throttle blocks
         double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
-        const Jet jet{cfg.jc, cfg.jn};
         if (lane < NJ)
         {
             const double dq = recb[lane];
@@ -1214,7 +1213,7 @@ qp_structured_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double*
         }
         if (lane < NT)
         {
-            o[VSMPC_OUT_THROTTLE + lane] = jet.destdU(vv[lane]);
+            o[VSMPC_OUT_THROTTLE + lane] = destd_throttle_qd(sm.cf, vv[lane]);
             o[VSMPC_OUT_THRUST + lane] = recb[NJ + lane];
             o[VSMPC_OUT_THRUST_DOT + lane] = recb[NJ + NT + lane];
         }

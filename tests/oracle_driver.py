@@ -8,7 +8,7 @@ from oracle import vsmpc_oracle as O
 class OracleInstance:
     """One reference-style MPC object + its QPInput/Robot, driven like src/variable_sampling_mpc.py."""
 
-    def __init__(self, nominal_state, i, params=None, trajectories=None, qp_solver=None):
+    def __init__(self, nominal_state, i, params=None, trajectories=None, qp_solver=None, jet_model=None):
         self.i = i
         self.params = dict(O.default_params())
         self.params.update(params or {})
@@ -16,7 +16,10 @@ class OracleInstance:
         self.qp = O.QPInput()
         self.qp.setRobot(self.robot)
         self.qp.setRobotReference(self.robot)
-        self.qp.setEmptyJetModel()
+        if jet_model is not None:
+            self.qp.setJetModel(jet_model)
+        else:
+            self.qp.setEmptyJetModel()
         fill_qp_input(self.qp, nominal_state, i)
         self.mpc = O.VariableSamplingMPC(qp_solver=qp_solver)
         self.mpc.configure(self.params, self.qp, trajectories or load_trajectories())
