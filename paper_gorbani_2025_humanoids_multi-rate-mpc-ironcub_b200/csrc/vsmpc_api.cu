@@ -26,6 +26,7 @@ cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const doubl
 cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
                                      double* u, cudaStream_t s);
 size_t generic_scratch_doubles(const DeviceConfig& cfg);
+bool generic_supported(const DeviceConfig& cfg);
 cudaError_t launch_qp_generic(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                               double* ws, double* scratch, double* z, double* st, double* out_rows, int* status,
                               int* n_factor, int* n_solve, cudaStream_t s);
@@ -220,12 +221,16 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     h->B = n_instances;
     h->device = device;
     // solver routing: 0 = default (condensed-throttle Riccati kernel; horizons it does not cover fall back to the
-    // structured one-warp kernel), 1 = generic dense variant, 2 = structured one-warp kernel
+    // generic dense kernel), 1 = generic dense variant, 2 = structured one-warp kernel
     if (c->solver < 0 || c->solver > 2)
         return bail(VSMPC_ERR_ARG, "solver must be 0 (default), 1 (generic) or 2 (structured)");
     h->solver = c->solver;
     if (h->solver == 0 && !condensed_supported(g))
-        h->solver = 2;
+        h->solver = 1;   // horizons beyond the condensed kernel's 6 throttle blocks / 32 knots: generic dense kernel
+    if (h->solver == 1 && !generic_supported(g))
+        return bail(VSMPC_ERR_UNSUPPORTED, "horizons with more than 48 throttle blocks are not supported");
+    if (h->solver == 2 && (NT * g.nblk > 24 || g.N > 32))
+        return bail(VSMPC_ERR_UNSUPPORTED, "the structured one-warp kernel covers horizons with <= 6 throttle blocks and <= 32 knots");
     const int B = n_instances;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess)

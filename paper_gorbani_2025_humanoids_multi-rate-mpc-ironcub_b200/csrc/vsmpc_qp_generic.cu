@@ -20,7 +20,7 @@ namespace vsmpc
 
 constexpr int LDP = NZ + 1;       // 39: odd leading dimension, conflict-free row/column access
 constexpr int GEN_WARPS = 2;      // instances per CTA
-constexpr int MAXACT = 32;        // cap on the working-set size / lazily computed columns
+constexpr int GEN_MAXV = 192;     // most throttle variables one instance may have (working set / column slots)
 
 struct GenSmem
 {
@@ -40,10 +40,10 @@ struct GenSmem
     double M0inv[NT * NT];
     double p0v[NT];
     // active set
-    double GW[MAXACT * (MAXACT + 1)];
-    double r[MAXACT], lam[MAXACT], sgn[MAXACT];
-    int W_idx[MAXACT];
-    int col_of[MAXACT]; // variable index whose column is stored in slot
+    double* GW;             // working-set system [nv][nv + 1] (global scratch: it grows with the horizon)
+    double r[GEN_MAXV], lam[GEN_MAXV], sgn[GEN_MAXV];
+    int W_idx[GEN_MAXV];
+    int col_of[GEN_MAXV]; // variable index whose column is stored in slot
     int gi1;
     double gv1;
 };
@@ -102,7 +102,7 @@ struct GenCtx
     GenSmem& sm;
     const double* qd;
     double* ws;     // [N][WS_STAGE]
-    double* gcols;  // [MAXACT][nv]
+    double* gcols;  // [nv][nv]
     double* kff;    // [N][NU] feed-forward terms of the current solve (global scratch)
     double* zout;   // [n_var] full primal
     int lane;
@@ -472,10 +472,14 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
     const int N = cfg.N;
     const int nvtot = cfg.nblk * NT;
     double* scratch = scratch_all + (size_t)inst * scratch_stride;
-    double* gcols = scratch;                       // [MAXACT][nvtot]
+    const int MAXACT = nvtot;                      // every throttle variable may be active / need its column
+    double* gcols = scratch;                       // [nvtot][nvtot]
     double* kff = gcols + (size_t)MAXACT * nvtot;  // [N][NU]
     double* vv = kff + (size_t)N * NU;             // [nvtot] current throttle iterate
     double* vtmp = vv + nvtot;                     // [nvtot]
+    if (lane == 0)
+        sm.GW = vtmp + nvtot;                      // [nvtot][nvtot + 1]
+    __syncwarp();
     double* z = z_all + (size_t)inst * cfg.n_var;
     GenCtx c{cfg, sm, qd, ws_all + (size_t)inst * N * WS_STAGE, gcols, kff, z, lane};
 
@@ -584,7 +588,7 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
             bool fail = false;
             while (true)
             {
-                if (++iters > 4 * MAXACT)
+                if (++iters > 4 * MAXACT + 64)
                 {
                     stat = VSMPC_STATUS_MAX_ITER;
                     fail = true;
@@ -781,10 +785,15 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
     }
 }
 
+bool generic_supported(const DeviceConfig& cfg)
+{
+    return NT * cfg.nblk <= GEN_MAXV;
+}
+
 size_t generic_scratch_doubles(const DeviceConfig& cfg)
 {
     const int nvtot = cfg.nblk * NT;
-    size_t n = (size_t)MAXACT * nvtot + (size_t)cfg.N * NU + 2 * (size_t)nvtot;
+    size_t n = (size_t)nvtot * nvtot + (size_t)cfg.N * NU + 2 * (size_t)nvtot + (size_t)nvtot * (nvtot + 1);
     return (n + 3) & ~(size_t)3;
 }
 

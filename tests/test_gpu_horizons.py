@@ -1,0 +1,60 @@
+"""Horizon variants (BASELINE.json configs[3]: long-horizon variable-sampling variants, 2-4x the reference knot count
+with a coarse tail dt) and model options, every solver against the oracle.  The default solver routes itself:
+condensed kernel where the horizon has <= 6 throttle blocks, otherwise the generic dense kernel."""
+import numpy as np
+import pytest
+
+from helpers import load_trajectories, pkg
+from oracle_driver import OracleInstance, oracle_trajectories_to_product
+
+pytestmark = pytest.mark.gpu
+
+HORIZONS = [
+    dict(nIter=12, nIterSmall=5, controlHorizon=8),
+    dict(nIter=17, nIterSmall=7, controlHorizon=17),                       # no held joint block
+    dict(nIter=20, nIterSmall=7, controlHorizon=12),
+    dict(nIter=9, nIterSmall=7, controlHorizon=7),                         # a single throttle block
+    dict(nIter=34, nIterSmall=14, controlHorizon=24),                      # 2x knots (SURVEY §8d Config 4)
+    dict(nIter=51, nIterSmall=14, controlHorizon=36),                      # 3x knots
+    dict(nIter=34, nIterSmall=14, controlHorizon=24, periodMPCLargeSteps=0.2),   # coarse tail dt
+    dict(useJetDynamic=False),
+    dict(useEstimatedThrust=False),
+]
+
+
+@pytest.mark.parametrize("solver", [0, 1, 2])
+@pytest.mark.parametrize("variant", range(len(HORIZONS)))
+def test_horizon_variant_matches_oracle(solver, variant):
+    params = HORIZONS[variant]
+    B = 6
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=31 + variant, perturbed=True, near_bound_fraction=0.3)
+    try:
+        mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=solver, full_solution=True)
+    except bat.VsmpcError as e:
+        assert solver == 2 and "structured" in str(e)      # the one-warp structured kernel is reference-horizon only
+        return
+    mpc.configure(nom)
+    for free in (False, True):
+        if free:
+            mpc.debug_set_counters(-1, int(round(mpc.params["periodMPCLargeSteps"] / mpc.params["periodMPCSmallSteps"])) - 1)
+        mpc.update(per)
+        mpc.solveMPC()
+        z = mpc.getSolution()
+        out, status = mpc.get_output()
+        assert (status == 0).all(), status
+        if not free:
+            oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
+        for i, o in enumerate(oracles):
+            if free:
+                o.mpc.vectorConstraints[2].counter = o.mpc.vectorConstraints[2].ratio - 1 \
+                    if hasattr(o.mpc.vectorConstraints[2], "ratio") else 19
+            o.update(per)
+            zo = o.solve()
+            assert z.shape[1] == zo.size
+            assert np.abs(z[i] - zo).max() / max(1.0, np.abs(zo).max()) < 1e-6, (variant, solver, free, i)
+            row = o.output_row()
+            assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
+    mpc.close()
