@@ -162,6 +162,11 @@ int vsmpc_wait(vsmpc_handle* h);
 
 /* getters: out_rows double[B][VSMPC_OUT_DOUBLES], status int[B] (either may be NULL) */
 int vsmpc_get_output(vsmpc_handle* h, double* out_rows_host, int* status_host);
+/* pipelined variant: enqueue the device->host copies behind the solve on the handle's stream and return at once;
+ * vsmpc_wait_output(h, ticket) blocks until that copy has landed.  Two tickets are in flight at most, so a caller can
+ * enqueue tick j+1 (vsmpc_set_state stages its pack on a separate copy stream) before waiting for tick j. */
+int vsmpc_get_output_async(vsmpc_handle* h, double* out_rows_host, int* status_host, int* ticket);
+int vsmpc_wait_output(vsmpc_handle* h, int ticket);
 /* device pointers of the same buffers (valid for the handle's lifetime) */
 int vsmpc_get_output_device(vsmpc_handle* h, double** out_rows_dev, int** status_dev);
 /* IMPCProblem::getSolution: double[B][n_var].  The full 588-vector is optional output: the controller

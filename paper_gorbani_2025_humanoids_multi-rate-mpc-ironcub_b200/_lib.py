@@ -63,7 +63,7 @@ EXPORTS = [
     "vsmpc_create", "vsmpc_destroy", "vsmpc_last_error", "vsmpc_set_stream", "vsmpc_n_var",
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
-    "vsmpc_get_output_device", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
+    "vsmpc_get_output_device", "vsmpc_get_output_async", "vsmpc_wait_output", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
     "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_microbench_fp64",
     "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_get_pack",
 ]
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     for f in ("vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait"):
         getattr(lib, f).argtypes = [H]
     lib.vsmpc_get_output.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.vsmpc_get_output_async.argtypes = [H, C.c_void_p, C.c_void_p, c_int_p]
+    lib.vsmpc_wait_output.argtypes = [H, C.c_int]
     lib.vsmpc_get_output_device.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.vsmpc_set_full_solution.argtypes = [H, C.c_int]
     lib.vsmpc_get_full_solution.argtypes = [H, C.c_void_p]

@@ -194,6 +194,16 @@ class BatchedVSMPC:
     def get_output_into(self, out_ptr: int, status_ptr: int):
         self._ck(self._lib.vsmpc_get_output(self._h, C.c_void_p(out_ptr), C.c_void_p(status_ptr)), "vsmpc_get_output")
 
+    def get_output_async(self, out_ptr: int, status_ptr: int) -> int:
+        """Enqueue the D2H copies behind the solve; returns the ticket for ``wait_output``."""
+        t = C.c_int(-1)
+        self._ck(self._lib.vsmpc_get_output_async(self._h, C.c_void_p(out_ptr), C.c_void_p(status_ptr), C.byref(t)),
+                 "vsmpc_get_output_async")
+        return t.value
+
+    def wait_output(self, ticket: int):
+        self._ck(self._lib.vsmpc_wait_output(self._h, int(ticket)), "vsmpc_wait_output")
+
     def output_device_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()
         self._ck(self._lib.vsmpc_get_output_device(self._h, C.byref(a), C.byref(b)), "vsmpc_get_output_device")

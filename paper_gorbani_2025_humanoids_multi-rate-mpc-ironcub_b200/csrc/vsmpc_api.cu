@@ -55,6 +55,14 @@ struct vsmpc_handle
     bool want_full = false;   // write the full primal (IMPCProblem::getSolution) every solve
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // host -> device staging of vsmpc_set_state: its own copy stream and two pack buffers, so that the copy of tick
+    // j+1 overlaps the kernels of tick j
+    cudaStream_t copy_stream = nullptr;
+    double* d_pack_in[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr};
+    cudaEvent_t ev_out[2] = {nullptr, nullptr};
+    int pack_idx = 0, out_idx = 0;
     // device buffers
     double* d_pack = nullptr;
     double* d_jpos = nullptr;
@@ -240,6 +248,14 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     auto A = [&](cudaError_t r) { ok = ok && (r == cudaSuccess); if (r != cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    A(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q)
+    {
+        A(dalloc(&h->d_pack_in[q], (size_t)VSMPC_PACK_DOUBLES * B));
+        A(cudaEventCreateWithFlags(&h->ev_h2d[q], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&h->ev_k1[q], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&h->ev_out[q], cudaEventDisableTiming));
+    }
     A(dalloc(&h->d_cfg, 1));
     A(dalloc(&h->d_pack, (size_t)VSMPC_PACK_DOUBLES * B));
     A(dalloc(&h->d_jpos, (size_t)NJ * B));
@@ -299,7 +315,16 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp, h->d_ip};
+                    h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
+                    h->d_pack_in[0], h->d_pack_in[1]};
+    for (int q = 0; q < 2; ++q)
+    {
+        if (h->ev_h2d[q]) cudaEventDestroy(h->ev_h2d[q]);
+        if (h->ev_k1[q]) cudaEventDestroy(h->ev_k1[q]);
+        if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]);
+    }
+    if (h->copy_stream)
+        cudaStreamDestroy(h->copy_stream);
     if (h->tick_graph)
         cudaGraphExecDestroy(h->tick_graph);
     for (void* p : ptrs)
@@ -390,10 +415,21 @@ int vsmpc_set_state(vsmpc_handle* h, const double* pack_host)
     if (!h->configured)
         return fail(h, VSMPC_ERR_STATE, "vsmpc_set_state: configure first");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(h->d_pack, pack_host, (size_t)VSMPC_PACK_DOUBLES * h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    // stage the pack on the copy stream into the buffer the previous-but-one tick used (its linearise kernel must be
+    // done with it), then make the compute stream wait for the copy: H2D of this tick overlaps the QP kernel of the last
+    const int q = h->pack_idx ^= 1;
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1[q], 0));
+    CK(cudaMemcpyAsync(h->d_pack_in[q], pack_host, (size_t)VSMPC_PACK_DOUBLES * h->B * 8, cudaMemcpyHostToDevice,
+                       h->copy_stream));
+    CK(cudaEventRecord(h->ev_h2d[q], h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[q], 0));
+    double* saved = h->d_pack;
+    h->d_pack = h->d_pack_in[q];
     int rc = run_linearise(h, 0);
+    h->d_pack = saved;
     if (rc)
         return rc;
+    CK(cudaEventRecord(h->ev_k1[q], h->stream));
     h->has_state = true;
     return VSMPC_OK;
 }
@@ -456,6 +492,29 @@ int vsmpc_get_output(vsmpc_handle* h, double* out_rows_host, int* status_host)
     if (status_host)
         CK(cudaMemcpyAsync(status_host, h->d_status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_get_output_async(vsmpc_handle* h, double* out_rows_host, int* status_host, int* ticket)
+{
+    if (!h || h->B <= 0 || !ticket)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (out_rows_host)
+        CK(cudaMemcpyAsync(out_rows_host, h->d_out, (size_t)VSMPC_OUT_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (status_host)
+        CK(cudaMemcpyAsync(status_host, h->d_status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    const int q = h->out_idx ^= 1;
+    CK(cudaEventRecord(h->ev_out[q], h->stream));
+    *ticket = q;
+    return VSMPC_OK;
+}
+
+int vsmpc_wait_output(vsmpc_handle* h, int ticket)
+{
+    if (!h || h->B <= 0 || ticket < 0 || ticket > 1)
+        return VSMPC_ERR_ARG;
+    CK(cudaEventSynchronize(h->ev_out[ticket]));
     return VSMPC_OK;
 }
 
