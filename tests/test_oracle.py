@@ -160,6 +160,16 @@ def test_exact_solver_certificate_and_riccati_model(small_batch):
             zm = m.pack_z(*m.solve_box())
             assert m.status == 0 and len(m.active) == info["n_active"]
             assert np.abs(zm - z).max() / max(1.0, np.abs(z).max()) < 1e-10
+            # the specification of the default kernel (condensed-throttle Riccati, tools/condensed_model.py)
+            from condensed_model import CondensedQP
+            mc = CondensedQP(cs.A, cs.BJ, cs.BT, cs.c, cs.dt, np.diag(rt.Q).copy(), rt.stateReference.T.copy(),
+                             np.array(p["weightDeltaJoint"]) + p["weightRegularizationJointPos"],
+                             o.mpc.vectorCosts[3].gradient[468:476].copy(), p["weightThrottle"],
+                             p["weightInitialThrottle"], vbar, not free, tc.vMin, tc.vMax,
+                             o.mpc.vectorConstraints[1].initialState, 17, 7, 12)
+            zc = mc.pack_z(*mc.solve_box())
+            assert mc.status == 0 and len(mc.active) == info["n_active"]
+            assert np.abs(zc - z).max() / max(1.0, np.abs(z).max()) < 1e-10
 
 
 # ---- frozen golden vectors ---------------------------------------------------------------------------
