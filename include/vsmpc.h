@@ -238,6 +238,10 @@ int vsmpc_rollout_get_state(vsmpc_handle* h, double* plant_state_host);
 /* the pack the plant built for the next tick (double[VSMPC_PACK_DOUBLES][B]) — parity tests */
 int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host);
 
+/* development hook: per-instance clock64() stamps of the condensed kernel's phases of the last launch (long long
+ * [n][8]); returns VSMPC_ERR_UNSUPPORTED unless the library was built with -DVSMPC_PHASE_CLOCKS */
+int vsmpc_debug_phase_clocks(long long* clocks_host, int n_instances);
+
 /* measured FP64 throughput of `device` in TFLOP/s: kind 0 = DFMA on the CUDA cores, kind 1 = DMMA
  * (mma.sync.m8n8k4.f64).  Used as the roofline denominator of the QP kernel (bench.py). */
 int vsmpc_microbench_fp64(int device, int kind, double* tflops);

@@ -17,6 +17,8 @@ SOURCES = ["vsmpc_api.cu", "vsmpc_linearise.cu", "vsmpc_qp_generic.cu", "vsmpc_q
            "vsmpc_microbench.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"]
+if os.environ.get("VSMPC_PHASE_CLOCKS"):      # development build: per-phase clock stamps in the condensed kernel
+    NVCC_FLAGS.append("-DVSMPC_PHASE_CLOCKS")
 
 
 def _digest() -> str:

@@ -64,7 +64,7 @@ EXPORTS = [
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
     "vsmpc_get_output_device", "vsmpc_get_output_async", "vsmpc_wait_output", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
-    "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_microbench_fp64",
+    "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64",
     "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_get_pack",
 ]
 
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
     lib.vsmpc_get_qp_vectors.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_get_counts.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
+    lib.vsmpc_debug_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]
     lib.vsmpc_set_instance_params.argtypes = [H, C.c_void_p]
     lib.vsmpc_rollout_init.argtypes = [H, C.POINTER(VsmpcPlantModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -35,6 +35,7 @@ cudaError_t launch_qp_structured(const DeviceConfig* d_cfg, const DeviceConfig& 
                                  double* ws, double* scratch, double* z, double* st, double* out_rows, int* status,
                                  int* n_factor, int* n_solve, int want_z, cudaStream_t s);
 bool condensed_supported(const DeviceConfig& cfg);
+int condensed_phase_clocks(long long* host, int n);
 size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
@@ -610,6 +611,11 @@ int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve)
         CK(cudaMemcpyAsync(n_solve, h->d_ns, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return VSMPC_OK;
+}
+
+int vsmpc_debug_phase_clocks(long long* clocks_host, int n_instances)
+{
+    return condensed_phase_clocks(clocks_host, n_instances);
 }
 
 int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter)

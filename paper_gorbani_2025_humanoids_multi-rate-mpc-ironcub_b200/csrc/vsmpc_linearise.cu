@@ -172,23 +172,75 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
                  const double* __restrict__ traj_vel, const double* __restrict__ traj_rpy,
                  const double* __restrict__ traj_rpyd, double* __restrict__ qd, const double* __restrict__ ip)
 {
-    extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12] | ipar[20]
+    extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12] | ipar[20] | stc[st_rows] | sic[4]
     const DeviceConfig& cfg = *cfgp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * K1_WARPS + warp;
     if (i >= B)
         return;
     const int NC = cfg.NC;
-    const int per_warp = 360 + cfg.qd_stride + 12 + 20;
+    const int per_warp = 360 + cfg.qd_stride + 12 + 20 + ((cfg.st_rows + 4 + 3) & ~3);
     double* pk = k1_smem + (size_t)warp * per_warp;
     double* out = pk + 360;
     double* colbuf = out + cfg.qd_stride;
     double* ipar = colbuf + 12;   // jet coefficients (13), normalisation (4), throttle min / max of this instance
+    double* stc = ipar + 20;      // staged copy of the persistent state column: every global load of the tick is issued up
+                                  // front; writes go to the copy and to global memory
+    int* sic = reinterpret_cast<int*>(stc + cfg.st_rows);
     const size_t Bs = (size_t)B;
-#define ST(f) st[(size_t)(f) * Bs + i]
+#define STR(f) stc[(f)]
+#define STW(f, v)                         \
+    do                                    \
+    {                                     \
+        const double v__ = (v);           \
+        stc[(f)] = v__;                   \
+        st[(size_t)(f) * Bs + i] = v__;   \
+    } while (0)
 #define SI(f) si[(size_t)(f) * Bs + i]
-    for (int f = lane; f < VSMPC_PACK_DOUBLES; f += 32)
-        pk[f] = pack[(size_t)f * Bs + i];
+    {
+        // every global load of the tick is issued before the first one is consumed (one DRAM round trip, not twelve)
+        constexpr int NPK = (VSMPC_PACK_DOUBLES + 31) / 32;
+        double pv[NPK], sv[8];
+        int siv = 0;
+#pragma unroll
+        for (int t = 0; t < NPK; ++t)
+        {
+            const int f = lane + 32 * t;
+            pv[t] = f < VSMPC_PACK_DOUBLES ? pack[(size_t)f * Bs + i] : 0.0;
+        }
+        if (mode == 0)
+        {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+            {
+                const int f = lane + 32 * t;
+                sv[t] = f < cfg.st_rows ? st[(size_t)f * Bs + i] : 0.0;
+            }
+            if (lane < SI_COUNT)
+                siv = si[(size_t)lane * Bs + i];
+        }
+#pragma unroll
+        for (int t = 0; t < NPK; ++t)
+        {
+            const int f = lane + 32 * t;
+            if (f < VSMPC_PACK_DOUBLES)
+                pk[f] = pv[t];
+        }
+        if (mode == 0)
+        {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+            {
+                const int f = lane + 32 * t;
+                if (f < cfg.st_rows)
+                    stc[f] = sv[t];
+            }
+            for (int f = lane + 256; f < cfg.st_rows; f += 32) // horizons with more than 17 reference columns
+                stc[f] = st[(size_t)f * Bs + i];
+            if (lane < SI_COUNT)
+                sic[lane] = siv;
+        }
+    }
     if (lane < IP_ROWS)
         ipar[lane] = ip ? ip[(size_t)lane * Bs + i]
                         : (lane < IP_JN ? cfg.jc[lane] : (lane < IP_TMIN ? cfg.jn[lane - IP_JN] : (lane == IP_TMIN ? cfg.throttle_min : cfg.throttle_max)));
@@ -244,26 +296,26 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
         // constraintsVSMPC.cpp:184-204,326-336; systemDynamicsVSMPC.cpp:67; variableSamplingMPC.cpp:60)
         if (lane < 3)
         {
-            ST(ST_P_INIT + lane) = pcom[lane];
-            ST(ST_RPY_INIT + lane) = rpy[lane];
-            ST(ST_RPY_OLD + lane) = rpy[lane];
-            ST(ST_NTURNS + lane) = 0.0;
-            ST(ST_P_REF + lane) = 0.0;
-            ST(ST_RPY_REF + lane) = 0.0;
+            STW(ST_P_INIT + lane, pcom[lane]);
+            STW(ST_RPY_INIT + lane, rpy[lane]);
+            STW(ST_RPY_OLD + lane, rpy[lane]);
+            STW(ST_NTURNS + lane, 0.0);
+            STW(ST_P_REF + lane, 0.0);
+            STW(ST_RPY_REF + lane, 0.0);
         }
         if (lane < 6)
-            ST(ST_MOM_REF + lane) = 0.0;
+            STW(ST_MOM_REF + lane, 0.0);
         if (lane == 0)
-            ST(ST_ALPHA) = 0.0;
+            STW(ST_ALPHA, 0.0);
         if (lane < NJ)
         {
             const double q0 = joint_pos_sel[(size_t)lane * Bs + i];
-            ST(ST_QREF0 + lane) = q0;
-            ST(ST_QACC + lane) = q0;
+            STW(ST_QREF0 + lane, q0);
+            STW(ST_QACC + lane, q0);
         }
         ref_column(0, pcom, rpy);
         for (int e = lane; e < 12 * NC; e += 32)
-            ST(ST_WIN + e) = colbuf[e / NC];
+            STW(ST_WIN + e, colbuf[e / NC]);
         const int ph = phase0 ? phase0[i] : 0;
         // both 20-tick counters start at ratio-1 (costsVSMPC.cpp:118, constraintsVSMPC.cpp:335)
         rc = tc = (cfg.ratio - 1 + ph) % cfg.ratio;
@@ -272,17 +324,17 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
     }
     else
     {
-        rc = SI(SI_REF_COUNTER);
-        tc = SI(SI_THR_COUNTER);
-        aidx = SI(SI_ALPHA_IDX);
-        ridx = SI(SI_REF_IDX);
+        rc = sic[SI_REF_COUNTER];
+        tc = sic[SI_THR_COUNTER];
+        aidx = sic[SI_ALPHA_IDX];
+        ridx = sic[SI_REF_IDX];
     }
     double pinit[3], rinit[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
     {
-        pinit[a] = (mode == 1) ? pcom[a] : ST(ST_P_INIT + a);
-        rinit[a] = (mode == 1) ? rpy[a] : ST(ST_RPY_INIT + a);
+        pinit[a] = (mode == 1) ? pcom[a] : STR(ST_P_INIT + a);
+        rinit[a] = (mode == 1) ? rpy[a] : STR(ST_RPY_INIT + a);
     }
     // ---------------- costs (evaluated before the constraints, IMPCProblem.cpp:157-192) -------------
     const bool shift = rc == cfg.ratio - 1; // ReferenceTrackingCost, costsVSMPC.cpp:124-165
@@ -307,15 +359,15 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
             {
                 const int r = e / NC, cidx = e - r * NC;
                 if (shift)
-                    wv[t] = (cidx + 1 < NC) ? ST(ST_WIN + e + 1) : colbuf[r];
+                    wv[t] = (cidx + 1 < NC) ? STR(ST_WIN + e + 1) : colbuf[r];
                 else
-                    wv[t] = ST(ST_WIN + e);
+                    wv[t] = STR(ST_WIN + e);
             }
         }
         for (int e = lane + 160; e < 12 * NC; e += 32) // horizons with more than 13 reference columns
         {
             const int r = e / NC, cidx = e - r * NC;
-            const double v = shift ? ((cidx + 1 < NC) ? ST(ST_WIN + e + 1) : colbuf[r]) : ST(ST_WIN + e);
+            const double v = shift ? ((cidx + 1 < NC) ? STR(ST_WIN + e + 1) : colbuf[r]) : STR(ST_WIN + e);
             out[QD_XREF + e] = v;
         }
         __syncwarp();
@@ -327,34 +379,44 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
             {
                 out[QD_XREF + e] = wv[t];
                 if (shift)
-                    ST(ST_WIN + e) = wv[t];
+                    STW(ST_WIN + e, wv[t]);
             }
         }
         if (shift)
             for (int e = lane + 160; e < 12 * NC; e += 32)
-                ST(ST_WIN + e) = out[QD_XREF + e];
+                STW(ST_WIN + e, out[QD_XREF + e]);
         __syncwarp();
     }
     if (shift && lane < 3)
     { // publish the references into "QPInput" (costsVSMPC.cpp:155-160)
-        ST(ST_P_REF + lane) = out[QD_XREF + (0 + lane) * NC];
-        ST(ST_RPY_REF + lane) = out[QD_XREF + (6 + lane) * NC];
-        ST(ST_MOM_REF + lane) = out[QD_XREF + (3 + lane) * NC];
-        ST(ST_MOM_REF + 3 + lane) = out[QD_XREF + (9 + lane) * NC];
+        STW(ST_P_REF + lane, out[QD_XREF + (0 + lane) * NC]);
+        STW(ST_RPY_REF + lane, out[QD_XREF + (6 + lane) * NC]);
+        STW(ST_MOM_REF + lane, out[QD_XREF + (3 + lane) * NC]);
+        STW(ST_MOM_REF + 3 + lane, out[QD_XREF + (9 + lane) * NC]);
     }
     __syncwarp();
     double pref[3], rref[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
     {
-        pref[a] = ST(ST_P_REF + a);
-        rref[a] = ST(ST_RPY_REF + a);
+        pref[a] = STR(ST_P_REF + a);
+        rref[a] = STR(ST_RPY_REF + a);
     }
     if (lane < NT) // ThrottleInitialValueCost gradient, costsVSMPC.cpp:479-485
         out[QD_VBAR + lane] = jet.v(jet.stdU(pk[VSMPC_PK_THROTTLE_PREV + lane]));
     if (lane < NJ) // JointPositionRegularizationCost gradient, costsVSMPC.cpp:574-590
-        out[QD_GQ + lane] = cfg.w_reg_q * (pk[VSMPC_PK_Q_CMD + lane] - ST(ST_QREF0 + lane));
+        out[QD_GQ + lane] = cfg.w_reg_q * (pk[VSMPC_PK_Q_CMD + lane] - STR(ST_QREF0 + lane));
     // ---------------- dynamics ---------------------------------------------------------------------------
+    // one sincos for the whole warp (lanes 0,1: roll; lanes 2,3: pitch) instead of four serial calls on lane 0
+    double s0, c0, t1, c1;
+    {
+        double sv, cv;
+        sincos((lane & 3) < 2 ? rpy[0] : rpy[1], &sv, &cv);
+        s0 = __shfl_sync(0xffffffffu, sv, 0);
+        c0 = __shfl_sync(0xffffffffu, cv, 0);
+        t1 = __shfl_sync(0xffffffffu, sv / cv, 2);
+        c1 = __shfl_sync(0xffffffffu, cv, 2);
+    }
     if (lane == 0)
     {
         double omw[3], omB[3];
@@ -366,7 +428,6 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
         for (int a = 0; a < 3; ++a)
             out[QD_OMEGA + a] = omB[a];
         // A[rpy, angMom] = W^-1 * I^-1     (systemDynamicsVSMPC.cpp:86-87,140-147)
-        const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), t1 = tan(rpy[1]), c1 = cos(rpy[1]);
         double Wi[9] = {1.0, s0 * t1, c0 * t1, 0.0, c0, -s0, 0.0, s0 / c1, c0 / c1};
         double Ii[9], WI[9];
         mat3_inv(I3, Ii);
@@ -449,7 +510,7 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
         out[QD_CEP + lane] = -pref[lane];              // :316
         out[QD_CER + lane] = -rinit[lane];             // :100 (configure-time RPY)
         if (lane == 0)
-            ST(ST_ALPHA) = alpha;
+            STW(ST_ALPHA, alpha);
     }
     if (aidx < cfg.alpha_len - 1)
         aidx++;
@@ -480,15 +541,15 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
     { // initial state (constraintsVSMPC.cpp:206-247) incl. RPY unwrapping
         const double PI = 3.14159265358979323846;
         const int a = lane;
-        double nt = (mode == 1) ? 0.0 : ST(ST_NTURNS + a);
-        const double old = (mode == 1) ? rpy[a] : ST(ST_RPY_OLD + a);
+        double nt = (mode == 1) ? 0.0 : STR(ST_NTURNS + a);
+        const double old = (mode == 1) ? rpy[a] : STR(ST_RPY_OLD + a);
         const double cur = pk[VSMPC_PK_RPY + a];
         if (cur - old > PI)
             nt -= 1.0;
         else if (cur - old < -PI)
             nt += 1.0;
-        ST(ST_NTURNS + a) = nt;
-        ST(ST_RPY_OLD + a) = cur;
+        STW(ST_NTURNS + a, nt);
+        STW(ST_RPY_OLD + a, cur);
         const double unw = cur + 2 * PI * nt;
         const double pc = pk[VSMPC_PK_P_COM + a];
         out[QD_X0 + IX_COM + a] = pc;
@@ -506,7 +567,8 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
         SI(SI_ALPHA_IDX) = aidx;
         SI(SI_REF_IDX) = ridx;
     }
-#undef ST
+#undef STR
+#undef STW
 #undef SI
     for (int e = QD_XREF + 12 * NC + lane; e < cfg.qd_stride; e += 32)
         out[e] = 0.0; // padding
@@ -652,7 +714,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
                              cudaStream_t s)
 {
-    const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12 + 20) * sizeof(double);
+    const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12 + 20 + ((h_cfg.st_rows + 4 + 3) & ~3)) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set)
     {

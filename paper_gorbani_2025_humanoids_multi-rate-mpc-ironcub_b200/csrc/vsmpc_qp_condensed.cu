@@ -67,6 +67,13 @@ struct alignas(16) CdSmem
 
 enum : int { TK_NONE = 0, TK_STAGE = 1, TK_PROP = 2, TK_SCHUR = 3 };
 
+#ifdef VSMPC_PHASE_CLOCKS
+__device__ long long g_phase_clk[4096][8];
+#define PHASE_CLK(slot) do { if (lane == 0 && warp == (slot >= 4 ? 1 : 0) && inst < 4096) g_phase_clk[inst][slot] = clock64(); } while (0)
+#else
+#define PHASE_CLK(slot) do { } while (0)
+#endif
+
 // y <- T_x^T y,  T_x = I + dt A_c   (structure: SURVEY App. A-3)
 __device__ __forceinline__ void applyTtx(double (&y)[NX], const double* __restrict__ cf, double dt)
 {
@@ -626,6 +633,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     const bool held = Nc - 1 < N - 1;
     CdCtx c{cfg, sm, ws_all + (size_t)inst * ws_stride, lane, cfg.nblk >= 3 ? 0 : 16, held ? Nc - 1 : -1};
 
+    PHASE_CLK(0);
     // ---- stage the QP data: coefficients, reference window; finiteness gate --------------------------------------
     bool fin = true;
     for (int e = threadIdx.x; e < cfg.qd_stride; e += CD_THREADS)
@@ -657,6 +665,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     const bool all_fin = __syncthreads_and(fin);
     int stat = all_fin ? VSMPC_STATUS_SOLVED : VSMPC_STATUS_NUMERICAL;
 
+    PHASE_CLK(1);
     // ---- factorisation: warp A = P recursion, warp B = parameter columns, one knot apart --------------------------
     double y[NX];   // warp A: row `lane` of P ; warp B: column `lane` of Psi
 #pragma unroll
@@ -754,6 +763,8 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         }
         __syncthreads();
     }
+    PHASE_CLK(2);
+    PHASE_CLK(4);
     if (warp == 0 && lane == 0)
         sm.flags[0] = ok ? 0 : 1;
 
@@ -1014,6 +1025,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         sm.theta[lane] = th;
         if (lane == 0)
             sm.flags[1] = stat;
+        PHASE_CLK(5);
     }
     __syncthreads();
     if (sm.flags[0] != 0)
@@ -1041,6 +1053,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         fth[e] = acc;
     }
     __syncthreads();
+    PHASE_CLK(6);
     if (warp != 0)
         return;
 
@@ -1134,6 +1147,17 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         if (lane < nv)
             z[base + lane] = sm.theta[lane];
     }
+    PHASE_CLK(3);
+}
+
+int condensed_phase_clocks(long long* host, int n)
+{
+#ifdef VSMPC_PHASE_CLOCKS
+    return cudaMemcpyFromSymbol(host, g_phase_clk, sizeof(long long) * 8 * (n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
+#else
+    (void)host; (void)n;
+    return 3;
+#endif
 }
 
 bool condensed_supported(const DeviceConfig& cfg)

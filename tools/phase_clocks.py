@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""Development: per-phase cycle counts of the condensed kernel (library built with VSMPC_PHASE_CLOCKS=1)."""
+import ctypes as C, importlib, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+bat, L = bench.pkg("batched"), bench.pkg("_lib")
+nom_pack, jp, packs = bench.make_workload(B, 20251002, 2)
+mpc = bat.BatchedVSMPC(B, None, bench.load_traj())
+mpc.configure_pack(nom_pack, jp, (np.arange(B) % 20).astype(np.int32))
+for j in range(4):
+    mpc.update_pack(packs[j % 2]); mpc.solveMPC()
+n = min(B, 4096)
+clk = np.zeros((n, 8), dtype=np.int64)
+rc = L.load().vsmpc_debug_phase_clocks(clk.ctypes.data, n)
+assert rc == 0, rc
+t0 = clk[:, 0].min()
+names = ["head (stage data)", "factorisation loop (A)", "AS wait + ftheta + forward (A)"]
+d = np.stack([clk[:, 1] - clk[:, 0], clk[:, 2] - clk[:, 1], clk[:, 3] - clk[:, 2]], 1)
+print("instances", n, "kernel span (cycles, same-SM clocks only comparable per SM):")
+for i, nm in enumerate(names):
+    print(f"  {nm:34s} mean {d[:, i].mean():9.0f}  p50 {np.median(d[:, i]):9.0f}  max {d[:, i].max():9.0f}")
+b = np.stack([clk[:, 5] - clk[:, 4], clk[:, 6] - clk[:, 5]], 1)
+print(f"  {'reduced QP + active set (B)':34s} mean {b[:, 0].mean():9.0f}  p50 {np.median(b[:, 0]):9.0f}  max {b[:, 0].max():9.0f}")
+print(f"  {'F theta (both)':34s} mean {b[:, 1].mean():9.0f}")
+tot = clk[:, 3] - clk[:, 0]
+print(f"  total per instance mean {tot.mean():.0f} p50 {np.median(tot):.0f} max {tot.max():.0f}")
