@@ -191,19 +191,19 @@ __device__ __forceinline__ bool gj8(double* __restrict__ S, double2 own, int lan
     return ok;
 }
 
-// Gauss-Jordan inverse of an SPD 24 x 24 matrix in shared memory (ld LDG), in place, pivots p0..23 (rows/columns
-// below p0 are decoupled unit rows); lane l < 24 owns row l
-__device__ __forceinline__ bool gj24(double* __restrict__ S, int lane, int p0)
+// Gauss-Jordan inverse of an SPD matrix of order <= 24 in shared memory (leading dimension ld, rows 16-byte aligned),
+// in place, pivots p0..p1-1 (the other rows/columns must be decoupled unit rows); lane l < 24 owns row l
+__device__ __forceinline__ bool gj24(double* __restrict__ S, int ld, int lane, int p0, int p1)
 {
     bool ok = true;
     const int l = lane < CD_MAXW ? lane : 0;
-    const double2* rowl = reinterpret_cast<const double2*>(S + l * LDG);
+    const double2* rowl = reinterpret_cast<const double2*>(S + l * ld);
 #pragma unroll 1
-    for (int p = p0; p < CD_MAXW; ++p)
+    for (int p = p0; p < p1; ++p)
     {
-        const double d = S[p * LDG + p];
-        const double f = S[l * LDG + p];
-        const double2* rowp = reinterpret_cast<const double2*>(S + p * LDG);
+        const double d = S[p * ld + p];
+        const double f = S[l * ld + p];
+        const double2* rowp = reinterpret_cast<const double2*>(S + p * ld);
         double2 pr[CD_MAXW / 2], ow[CD_MAXW / 2];
 #pragma unroll
         for (int j = 0; j < CD_MAXW / 2; ++j)
@@ -218,7 +218,7 @@ __device__ __forceinline__ bool gj24(double* __restrict__ S, int lane, int p0)
         {
             const bool piv = l == p;
             const double ff = piv ? -dinv : f * dinv;
-            double2* wr = reinterpret_cast<double2*>(S + l * LDG);
+            double2* wr = reinterpret_cast<double2*>(S + l * ld);
 #pragma unroll
             for (int j = 0; j < CD_MAXW / 2; ++j)
             {
@@ -229,7 +229,7 @@ __device__ __forceinline__ bool gj24(double* __restrict__ S, int lane, int p0)
                 o.y = fma(-ff, pr[j].y, o.y);
                 wr[j] = o;
             }
-            S[l * LDG + p] = piv ? dinv : -ff;
+            S[l * ld + p] = piv ? dinv : -ff;
         }
         __syncwarp();
     }
@@ -836,7 +836,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                 gr[j] = make_double2(h[2 * j], h[2 * j + 1]);
         }
         __syncwarp();
-        const bool okG = gj24(G, lane, first);
+        const bool okG = gj24(G, LDG, lane, first, CD_MAXW);
         double v_e = 0.0;
         if (lane < CD_MAXW)
         {
@@ -1082,18 +1082,37 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     __syncwarp();
     const int ka = lane & 7, kq = lane >> 3;   // gain row / quarter of the state handled by this lane
     const int j0 = kq * 7, jn = kq == 3 ? 5 : 7;
+    // gain rows are prefetched one knot ahead: their addresses do not depend on the state
+    double kcur[7], knext[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t)
+        kcur[t] = t < jn ? c.ws[WSC_K + ka * NX + j0 + t] : 0.0;
     for (int k = 0; k < N; ++k)
     {
         const double dt = sm.dtk[k];
         const int tb = throttle_block(k, cfg.Ns, cfg.Nc);
-        if (k < Nc)
+        if (k + 1 < Nc)
         {
-            const double* __restrict__ Kr = c.ws + (size_t)k * WSC_STAGE + WSC_K + ka * NX + j0;
-            double part = 0.0;
+            const double* __restrict__ Kn = c.ws + (size_t)(k + 1) * WSC_STAGE + WSC_K + ka * NX + j0;
 #pragma unroll
             for (int t = 0; t < 7; ++t)
-                if (t < jn)
-                    part = fma(Kr[t], xs[j0 + t], part);
+                knext[t] = t < jn ? Kn[t] : 0.0;
+        }
+        if (k < Nc)
+        {
+            double part = 0.0, part2 = 0.0;
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+            {
+                if (t & 1)
+                    part2 = fma(kcur[t], xs[j0 + t], part2);
+                else
+                    part = fma(kcur[t], xs[j0 + t], part);
+            }
+            part += part2;
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+                kcur[t] = knext[t];
             part += __shfl_xor_sync(0xffffffffu, part, 8);
             part += __shfl_xor_sync(0xffffffffu, part, 16);
             const double u = -part - fth[k * NJ + ka];
