@@ -1071,7 +1071,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
     CdFwdTab tab;
     cd_build_fwd(tab, sm.cf, lane);
-    double* dqs = xs + NX;
+    double* dqs = xs + NY;
     double x = lane < NX ? sm.cf[QD_X0 + lane] : 0.0;
     if (lane < NX)
         xs[lane] = x;
@@ -1082,13 +1082,16 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     __syncwarp();
     const int ka = lane & 7, kq = lane >> 3;   // gain row / quarter of the state handled by this lane
     const int j0 = kq * 7, jn = kq == 3 ? 5 : 7;
-    // gain rows are prefetched one knot ahead: their addresses do not depend on the state
-    double kcur[7], knext[7];
+    // gain rows are prefetched one knot ahead (their addresses do not depend on the state) into the register set the
+    // other knot parity uses, so that no instruction of knot k waits for the loads of knot k+1
+    double kA[7], kB[7];
 #pragma unroll
     for (int t = 0; t < 7; ++t)
-        kcur[t] = t < jn ? c.ws[WSC_K + ka * NX + j0 + t] : 0.0;
-    for (int k = 0; k < N; ++k)
     {
+        kA[t] = t < jn ? c.ws[WSC_K + ka * NX + j0 + t] : 0.0;
+        kB[t] = 0.0;
+    }
+    auto knot = [&](int k, double (&kuse)[7], double (&kload)[7]) {
         const double dt = sm.dtk[k];
         const int tb = throttle_block(k, cfg.Ns, cfg.Nc);
         if (k + 1 < Nc)
@@ -1096,8 +1099,10 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
             const double* __restrict__ Kn = c.ws + (size_t)(k + 1) * WSC_STAGE + WSC_K + ka * NX + j0;
 #pragma unroll
             for (int t = 0; t < 7; ++t)
-                knext[t] = t < jn ? Kn[t] : 0.0;
+                kload[t] = t < jn ? Kn[t] : 0.0;
         }
+        if (lane < NT)
+            xs[NX + lane] = sm.theta[4 * tb + lane];
         if (k < Nc)
         {
             double part = 0.0, part2 = 0.0;
@@ -1105,14 +1110,11 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
             for (int t = 0; t < 7; ++t)
             {
                 if (t & 1)
-                    part2 = fma(kcur[t], xs[j0 + t], part2);
+                    part2 = fma(kuse[t], xs[j0 + t], part2);
                 else
-                    part = fma(kcur[t], xs[j0 + t], part);
+                    part = fma(kuse[t], xs[j0 + t], part);
             }
             part += part2;
-#pragma unroll
-            for (int t = 0; t < 7; ++t)
-                kcur[t] = knext[t];
             part += __shfl_xor_sync(0xffffffffu, part, 8);
             part += __shfl_xor_sync(0xffffffffu, part, 16);
             const double u = -part - fth[k * NJ + ka];
@@ -1124,15 +1126,13 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                 if (z)
                     z[NX * (N + 1) + k * NJ + lane] = u;
             }
-            __syncwarp();
         }
+        __syncwarp();
         double acc = 0.0;
 #pragma unroll
         for (int q = 0; q < CQF; ++q)
         {
-            const int src = tab.iw[q];
-            const double sval = (src < NX) ? xs[src] : (src < NY ? sm.theta[4 * tb + src - NX] : dqs[src - NY]);
-            acc = fma(tab.cw[q], sval, acc);
+            acc = fma(tab.cw[q], xs[tab.iw[q]], acc);   // xs = [x (26) | throttle block in effect (4) | dq in effect (8)]
         }
         const double other = __shfl_sync(0xffffffffu, acc, tab.helper < 0 ? lane : tab.helper);
         if (tab.helper >= 0)
@@ -1149,6 +1149,13 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         if (z && lane < NX)
             z[(k + 1) * NX + lane] = x;
         __syncwarp();
+    };
+#pragma unroll 1
+    for (int k = 0; k < N; k += 2)
+    {
+        knot(k, kA, kB);
+        if (k + 1 < N)
+            knot(k + 1, kB, kA);
     }
     // remaining outputs (variableSamplingMPC.cpp:96-108,138-151)
     if (lane < NT)
