@@ -35,7 +35,8 @@ constexpr int CD_MAXNC = 16;  // reference columns kept in shared memory
 constexpr int CD_MAXW = 24;
 constexpr int WSC_K = 0;              // per elimination knot in the workspace: K [8][26]
 constexpr int WSC_F = NJ * NX;        //                                     then F [8][32]
-constexpr int WSC_STAGE = NJ * NX + NJ * NL; // 464
+constexpr int WSC_H = NJ * NX + NJ * NL; //                                     then H_utheta [8][32]
+constexpr int WSC_STAGE = NJ * NX + 2 * NJ * NL; // 720
 
 struct alignas(16) CdSlot
 {
@@ -59,9 +60,8 @@ struct alignas(16) CdSmem
     alignas(16) double Mt[NX * LDM];        // warp A: transposition buffer, then the gain rows K [8][26] of the knot in
                                 // flight; after the factorisation: F theta, x, dq
     double Om[NLO * NLO];
-    alignas(16) double Hut[NLO * LDH];      // warp B: H_utheta of the knot in flight; after the factorisation: active-set vectors
+    alignas(16) double Hut[4 * CD_MAXW];    // active-set vectors (r, lambda, sign, index) after the factorisation
     alignas(16) double theta[NL];
-    unsigned short tri[NLO * (NLO + 1) / 2 + 3];   // (i << 8 | j) of the row-major upper triangle of Om
     int flags[4];
 };
 
@@ -236,6 +236,25 @@ __device__ __forceinline__ bool gj24(double* __restrict__ S, int ld, int lane, i
     return ok;
 }
 
+// exact max / min of NON-NEGATIVE doubles over the warp with two 32-bit REDUX each (non-negative doubles order like
+// their bit patterns); arg = lowest lane attaining it
+__device__ __forceinline__ double warp_max_nonneg(double v, int& arg)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    arg = __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+__device__ __forceinline__ double warp_min_nonneg(double v, int& arg)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    arg = __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+
 struct CdCtx
 {
     const DeviceConfig& cfg;
@@ -367,19 +386,17 @@ __device__ __forceinline__ void a_prop(const CdCtx& c, int k, bool elim, double 
 }
 
 // ---- warp B --------------------------------------------------------------------------------------------------
-// down-date of the parameter columns with the eliminated block: F = H_uu^-1 H_utheta, Psi -= H_ux' F, Om -= H_ut' F
+// down-date of the parameter columns with the eliminated block: F = H_uu^-1 H_utheta, Psi -= H_ux' F.  The matching
+// down-date of Om (Om -= H_utheta' F) is NOT done knot by knot: H_utheta and F of every elimination knot are stacked
+// in the workspace and contracted once after the recursion on the FP64 tensor cores (cd_omega_downdate).
 __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&s)[NX], const double (&hut)[NJ],
-                                           double* __restrict__ wsk, bool clear_col, int i0)
+                                           double* __restrict__ wsk, bool clear_col)
 {
-    CdSmem& sm = c.sm;
     const int lane = c.lane;
     double* Fs = sl.PD;   // the P'D columns of this knot were consumed by b_prop: reuse as F [l][LDH]
-    if (lane < NLO)
-    {
 #pragma unroll
-        for (int m = 0; m < NJ; ++m)
-            sm.Hut[lane * LDH + m] = hut[m];
-    }
+    for (int m = 0; m < NJ; ++m)
+        wsk[WSC_H + m * NL + lane] = hut[m];
     {
         const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
 #pragma unroll 1
@@ -421,32 +438,72 @@ __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&
             s[j] = 0.0;
     }
     __syncwarp();
-    // Om[i][j] -= H_ut[:, i]' F[:, j] on the upper triangle of the live rows (i0 <= i <= j), mirrored
+}
+
+// Om -= sum_k H_utheta_k' F_k = H' F with H, F the (8 Nc) x 32 stacks of the workspace: a dense 25 x 25 x (8 Nc)
+// contraction, run once on the FP64 tensor cores (mma.sync.m8n8k4.f64).  The symmetric result is computed on the ten
+// upper 8 x 8 tiles: tile rows {0, 3} by warp 0, {1, 2} by warp 1 (five tiles each); A fragment = H' (lane l: row l >> 2 of the tile,
+// stack row l & 3), B fragment = F (stack row l & 3, column l >> 2), C fragment: row l >> 2, columns 2 (l & 3) + {0, 1}.
+template <int TA0, int TA1>
+__device__ __forceinline__ void cd_omega_tile_rows(const double* __restrict__ ws, int n_rows, double* __restrict__ Om, int lane)
+{
+    // tile rows TA0 < TA1 of the upper triangle in one sweep over the stack, so that all their loads are in flight together
+    constexpr int N0 = 4 - TA0, N1 = 4 - TA1;      // tiles (TA0, TA0..3) and (TA1, TA1..3)
+    double c0[N0 + N1], c1[N0 + N1];
+#pragma unroll
+    for (int t = 0; t < N0 + N1; ++t)
+        c0[t] = c1[t] = 0.0;
+    const int lr = lane & 3, lc = lane >> 2;
+#pragma unroll 8
+    for (int r0 = 0; r0 < n_rows; r0 += 4)
     {
-        const int e0 = i0 * NLO - (i0 * (i0 - 1)) / 2;          // first entry of row i0 in the row-major triangle
-#pragma unroll 1
-        for (int e = e0 + lane; e < NLO * (NLO + 1) / 2; e += 32)
+        const int r = r0 + lr;
+        const double* __restrict__ row = ws + (size_t)(r >> 3) * WSC_STAGE + (r & 7) * NL;
+        const double a0 = row[WSC_H + 8 * TA0 + lc];
+        const double a1 = row[WSC_H + 8 * TA1 + lc];
+        double b[N0];
+#pragma unroll
+        for (int t = 0; t < N0; ++t)
+            b[t] = row[WSC_F + 8 * (TA0 + t) + lc];
+#pragma unroll
+        for (int t = 0; t < N0; ++t)
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c0[t]), "+d"(c1[t])
+                : "d"(a0), "d"(b[t]));
+#pragma unroll
+        for (int t = 0; t < N1; ++t)
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c0[N0 + t]), "+d"(c1[N0 + t])
+                : "d"(a1), "d"(b[TA1 - TA0 + t]));
+    }
+#pragma unroll
+    for (int q = 0; q < N0 + N1; ++q)
+    {
+        const int ti = q < N0 ? TA0 : TA1;
+        const int t = q < N0 ? q : q - N0;
+        const int gi = 8 * ti + lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
         {
-            const int ij = sm.tri[e];
-            const int i = ij >> 8, j = ij & 255;
-            const double2* hr = reinterpret_cast<const double2*>(sm.Hut + i * LDH);
-            const double2* fr = reinterpret_cast<const double2*>(Fs + j * LDH);
-            const double2 h0 = hr[0], h1 = hr[1], h2 = hr[2], h3 = hr[3];
-            const double2 f0 = fr[0], f1 = fr[1], f2 = fr[2], f3 = fr[3];
-            double a0 = fma(-h0.x, f0.x, sm.Om[i * NLO + j]);
-            double a1 = -h0.y * f0.y;
-            a0 = fma(-h1.x, f1.x, a0);
-            a1 = fma(-h1.y, f1.y, a1);
-            a0 = fma(-h2.x, f2.x, a0);
-            a1 = fma(-h2.y, f2.y, a1);
-            a0 = fma(-h3.x, f3.x, a0);
-            a1 = fma(-h3.y, f3.y, a1);
-            const double v = a0 + a1;
-            sm.Om[i * NLO + j] = v;
-            sm.Om[j * NLO + i] = v;
+            const int gj = 8 * (ti + t) + 2 * lr + e;
+            const double v = e == 0 ? c0[q] : c1[q];
+            if (gi < NLO && gj < NLO)
+            {
+                Om[gi * NLO + gj] -= v;
+                if (t > 0)
+                    Om[gj * NLO + gi] -= v;
+            }
         }
     }
-    __syncwarp();
+}
+
+__device__ __forceinline__ void cd_omega_downdate(const double* __restrict__ ws, int n_rows, double* __restrict__ Om,
+                                                  int warp, int lane)
+{
+    if (warp == 0)
+        cd_omega_tile_rows<0, 3>(ws, n_rows, Om, lane);
+    else
+        cd_omega_tile_rows<1, 2>(ws, n_rows, Om, lane);
 }
 
 // propagation of the parameter columns through knot k (Psi'' = Psi' + P'D, Om += D'Psi'' + Psi''D, Psi <- T'Psi'');
@@ -653,13 +710,6 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         sm.Rqd[threadIdx.x] = cfg.Rqd[threadIdx.x];
     if (threadIdx.x < N)
         sm.dtk[threadIdx.x] = cfg.dt[threadIdx.x];
-    if (threadIdx.x < NLO)
-    {
-        const int i = threadIdx.x;
-        const int e0 = i * NLO - (i * (i - 1)) / 2;
-        for (int j = i; j < NLO; ++j)
-            sm.tri[e0 + j - i] = (unsigned short)((i << 8) | j);
-    }
     for (int e = threadIdx.x; e < 6 * NJ; e += CD_THREADS)
         sm.lam[e] = qd[(e < 3 * NJ ? QD_LLIN : QD_LANG - 3 * NJ) + e];
     const bool all_fin = __syncthreads_and(fin);
@@ -744,8 +794,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                         hut[m] += sm.cf[QD_GQ + m];
                 }
                 const bool schur = tbk == TK_SCHUR;
-                b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD,
-                           schur ? 0 : 4 * throttle_block(kb, cfg.Ns, cfg.Nc));
+                b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD);
                 if (schur)
                 {
                     if (lane < NLO)
@@ -767,6 +816,17 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     PHASE_CLK(4);
     if (warp == 0 && lane == 0)
         sm.flags[0] = ok ? 0 : 1;
+    // Psi_0' x0 while warp B still holds its column, then the deferred down-date of Om on the tensor cores (both
+    // warps; the stores of H_utheta / F were made visible by the __syncthreads that closed the recursion)
+    double g_psi = 0.0;
+    if (warp == 1 && lane < nv)
+    {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            g_psi = fma(y[j], sm.cf[QD_X0 + j], g_psi);
+    }
+    cd_omega_downdate(c.ws, NJ * Nc, sm.Om, warp, lane);
+    __syncthreads();
 
     // ---- warp B: reduced QP in the throttle variables + dual active set ---------------------------------------------
     // after the factorisation the mailbox slots are dead: G (24 x 25) and the working-set inverse live there
@@ -782,14 +842,9 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     if (warp == 1)
     {
         // gradient and Hessian row of variable `lane`
-        double g = 0.0;
+        double g = g_psi;
         if (lane < nv)
-        {
-#pragma unroll
-            for (int j = 0; j < NX; ++j)
-                g = fma(y[j], sm.cf[QD_X0 + j], g);
             g += sm.Om[lane * NLO + AFFL];
-        }
         double h[CD_MAXW];
         const int blk = lane >> 2;
 #pragma unroll
@@ -862,19 +917,8 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         bool fail = stat != VSMPC_STATUS_SOLVED;
         while (!fail)
         {
-            double best = (isvar && wpos_e < 0) ? fmax(v_e - up, lo - v_e) : -1.0;
-            int p_idx = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, p_idx, o);
-                if (ov > best || (ov == best && oi < p_idx))
-                {
-                    best = ov;
-                    p_idx = oi;
-                }
-            }
+            int p_idx;
+            const double best = warp_max_nonneg((isvar && wpos_e < 0) ? fmax(fmax(v_e - up, lo - v_e), 0.0) : 0.0, p_idx);
             if (!(best > tol))
                 break;
             const double v_p0 = __shfl_sync(0xffffffffu, v_e, p_idx);
@@ -893,32 +937,37 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                 const int widx_a = lane < nW ? as_widx[lane] : 0;
                 const double sgn_a = lane < nW ? as_sgn[lane] : 0.0;
                 const double gwp_a = sgn_a * s * __shfl_sync(0xffffffffu, gp_e, widx_a);
+                // r = Minv gwp: gwp broadcast through shared memory, two FMA chains
+                if (lane < nW)
+                    as_lam[lane] = gwp_a;
+                __syncwarp();
                 double r_a = 0.0;
-                for (int b = 0; b < nW; ++b)
+                if (lane < nW)
                 {
-                    const double gb = __shfl_sync(0xffffffffu, gwp_a, b);
-                    if (lane < nW)
-                        r_a = fma(Minv[lane * CD_MAXW + b], gb, r_a);
+                    const double* mrow = Minv + lane * CD_MAXW;
+                    double r0 = 0.0, r1 = 0.0;
+                    int b = 0;
+#pragma unroll 2
+                    for (; b + 1 < nW; b += 2)
+                    {
+                        r0 = fma(mrow[b], as_lam[b], r0);
+                        r1 = fma(mrow[b + 1], as_lam[b + 1], r1);
+                    }
+                    if (b < nW)
+                        r0 = fma(mrow[b], as_lam[b], r0);
+                    r_a = r0 + r1;
                 }
                 double zsum = (lane < nW) ? r_a * gwp_a : 0.0;
-                double t1 = (lane < nW && r_a > 0.0) ? lamW / r_a : INFINITY;
-                int drop = lane;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1)
-                {
                     zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
-                    const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
-                    const int od = __shfl_xor_sync(0xffffffffu, drop, o);
-                    if (ot < t1 || (ot == t1 && od < drop))
-                    {
-                        t1 = ot;
-                        drop = od;
-                    }
-                }
+                int drop;
+                const double t1 = warp_min_nonneg((lane < nW && r_a > 0.0) ? fmax(lamW, 0.0) / r_a : INFINITY, drop);
                 const double gpp = __shfl_sync(0xffffffffu, gp_e, p_idx);
                 const double v_p = __shfl_sync(0xffffffffu, v_e, p_idx);
                 const double zp = gpp - zsum;
-                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) / zp : INFINITY;
+                const double izp = 1.0 / zp;
+                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) * izp : INFINITY;
                 const double tt = fmin(t1, t2);
                 if (!isfinite(tt))
                 {
@@ -930,11 +979,20 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                     as_r[lane] = r_a * sgn_a;
                 __syncwarp();
                 {
-                    double zd = s * gp_e;
-                    for (int a = 0; a < nW; ++a)
-                        if (lane < CD_MAXW)
+                    double zd = s * gp_e, zd1 = 0.0;
+                    if (lane < CD_MAXW)
+                    {
+                        int a = 0;
+#pragma unroll 2
+                        for (; a + 1 < nW; a += 2)
+                        {
                             zd = fma(-as_r[a], G[as_widx[a] * LDG + lane], zd);
-                    v_e = fma(-tt, zd, v_e);
+                            zd1 = fma(-as_r[a + 1], G[as_widx[a + 1] * LDG + lane], zd1);
+                        }
+                        if (a < nW)
+                            zd = fma(-as_r[a], G[as_widx[a] * LDG + lane], zd);
+                    }
+                    v_e = fma(-tt, zd + zd1, v_e);
                 }
                 if (lane < nW)
                     lamW -= tt * r_a;
@@ -947,12 +1005,13 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                         fail = true;
                         break;
                     }
-                    const double izp = 1.0 / zp;
+                    __syncwarp();
                     if (lane < nW)
                         as_lam[lane] = r_a;
                     __syncwarp();
                     if (lane < nW)
                     {
+#pragma unroll 4
                         for (int b = 0; b < nW; ++b)
                             Minv[lane * CD_MAXW + b] = fma(r_a * izp, as_lam[b], Minv[lane * CD_MAXW + b]);
                         Minv[lane * CD_MAXW + nW] = -r_a * izp;
@@ -981,6 +1040,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                         as_lam[lane] = Minv[drop * CD_MAXW + lane];
                     __syncwarp();
                     if (lane < nW)
+#pragma unroll 4
                         for (int b = 0; b < nW; ++b)
                             Minv[lane * CD_MAXW + b] = fma(-f, as_lam[b], Minv[lane * CD_MAXW + b]);
                     __syncwarp();
@@ -1026,6 +1086,10 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         if (lane == 0)
             sm.flags[1] = stat;
         PHASE_CLK(5);
+#ifdef VSMPC_PHASE_CLOCKS
+        if (lane == 0 && inst < 4096)
+            g_phase_clk[inst][7] = iters * 100 + nW;
+#endif
     }
     __syncthreads();
     if (sm.flags[0] != 0)

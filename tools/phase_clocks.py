@@ -27,3 +27,11 @@ print(f"  {'reduced QP + active set (B)':34s} mean {b[:, 0].mean():9.0f}  p50 {n
 print(f"  {'F theta (both)':34s} mean {b[:, 1].mean():9.0f}")
 tot = clk[:, 3] - clk[:, 0]
 print(f"  total per instance mean {tot.mean():.0f} p50 {np.median(tot):.0f} max {tot.max():.0f}")
+
+it, nw = clk[:, 7] // 100, clk[:, 7] % 100
+as_t = clk[:, 5] - clk[:, 4]
+print("GI iterations: mean %.1f p50 %d p90 %d max %d ; final |W| mean %.1f max %d" % (it.mean(), np.median(it), np.percentile(it, 90), it.max(), nw.mean(), nw.max()))
+for lo_, hi_ in ((0, 0), (1, 3), (4, 6), (7, 10), (11, 15), (16, 99)):
+    m = (it >= lo_) & (it <= hi_)
+    if m.any():
+        print(f"  iters {lo_:2d}-{hi_:2d}: {m.sum():4d} instances, AS phase mean {as_t[m].mean():8.0f} cycles")
