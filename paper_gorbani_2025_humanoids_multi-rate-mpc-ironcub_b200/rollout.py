@@ -100,3 +100,21 @@ class BatchedRollout:
         pk = np.empty((L.PACK_DOUBLES, self.mpc.B))
         self.mpc._ck(self._lib.vsmpc_rollout_get_pack(self.mpc._h, pk.ctypes.data), "vsmpc_rollout_get_pack")
         return pk
+
+
+def save_log_mat(path: str, rec: np.ndarray, instance: int, period_mpc: float = 0.005, record_every: int = 1) -> dict:
+    """Write one instance's rollout record in the layout of the reference driver's end-of-run log
+    (``scipy.io.savemat`` dictionary of src/variable_sampling_mpc.py:163-194), for the series the device loop
+    records: CoM position, base orientation (RPY), estimated thrust, throttle, solver status and the time axis."""
+    import scipy.io
+    r = np.asarray(rec)[:, instance, :]
+    data = {
+        "CoMPosition": r[:, 0:3],
+        "base_orientation": r[:, 3:6],
+        "estimated_thrust": r[:, 6:10],
+        "throttle": r[:, 10:14],
+        "qp_status": r[:, 14],
+        "time_controller": period_mpc * record_every * (1 + np.arange(r.shape[0])),
+    }
+    scipy.io.savemat(path, data)
+    return data

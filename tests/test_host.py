@@ -120,3 +120,15 @@ def test_mat73_reader_on_npz_equivalent(tmp_path):
     cfg = pkg("config")
     t = cfg.load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
     assert t["alpha_fps"] == 10 and t["traj_fps"] == 10 and t["alphaGravity"].shape == (1, 351)
+
+
+def test_rollout_log_writer_roundtrip(tmp_path):
+    """The rollout record is written with the reference driver's log keys (src/variable_sampling_mpc.py:163-194)."""
+    import scipy.io
+    ro = pkg("rollout")
+    rec = np.random.default_rng(0).normal(size=(12, 3, 16))
+    f = str(tmp_path / "log.mat")
+    ro.save_log_mat(f, rec, 1, record_every=2)
+    d = scipy.io.loadmat(f)
+    assert np.array_equal(d["CoMPosition"], rec[:, 1, 0:3]) and np.array_equal(d["throttle"], rec[:, 1, 10:14])
+    assert np.allclose(d["time_controller"].ravel(), 0.01 * (1 + np.arange(12)))
