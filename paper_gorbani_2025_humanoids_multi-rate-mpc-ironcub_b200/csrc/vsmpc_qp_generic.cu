@@ -40,10 +40,13 @@ struct GenSmem
     double M0inv[NT * NT];
     double p0v[NT];
     // active set
-    double* GW;             // working-set system [nv][nv + 1] (global scratch: it grows with the horizon)
+    double* GW;             // inverse of the signed working-set block of G, [nv][nv] (global scratch: grows with the horizon)
     double r[GEN_MAXV], lam[GEN_MAXV], sgn[GEN_MAXV];
+    double gw[GEN_MAXV];    // S G[W, p] of the candidate / row copies during the down-date
     int W_idx[GEN_MAXV];
-    int col_of[GEN_MAXV]; // variable index whose column is stored in slot
+    int slotW[GEN_MAXV];    // column slot of every working-set member
+    int slot_of[GEN_MAXV];  // variable -> column slot (-1: not computed yet)
+    int wpos[GEN_MAXV];     // variable -> position in the working set (-1: inactive)
     int gi1;
     double gv1;
 };
@@ -556,9 +559,18 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
         gen_solve(c, 0, nullptr, nullptr, false, vv, z);
         ns++;
         // ---- Goldfarb-Idnani dual active set on the throttle boxes ----
+        // working-set inverse Minv = (S G_WW S)^-1 kept in global scratch (ld = nvtot) and updated by bordering /
+        // down-dating: O(nW^2) per iteration for any horizon; var -> slot / position maps avoid list searches
         const double tol = 1e-10;
         int iters = 0;
         int* g_idx = sm.W_idx; // reused as the gamma index list for the final solve
+        double* Minv = sm.GW;
+        for (int e = lane; e < nvtot; e += 32)
+        {
+            sm.slot_of[e] = -1;
+            sm.wpos[e] = -1;
+        }
+        __syncwarp();
         while (true)
         {
             // most violated bound among variables not in W
@@ -566,10 +578,7 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
             int barg = -1;
             for (int e = first + lane; e < nvtot; e += 32)
             {
-                bool inW = false;
-                for (int a = 0; a < nW; ++a)
-                    inW = inW || (sm.W_idx[a] == e);
-                if (!inW)
+                if (sm.wpos[e] < 0)
                 {
                     const double v = fmax(vv[e] - up, lo - vv[e]);
                     if (v > best)
@@ -595,10 +604,7 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
                     break;
                 }
                 // column of G for p_idx (lazy: one homogeneous back-solve)
-                int qp = -1;
-                for (int q = 0; q < ncols; ++q)
-                    if (sm.col_of[q] == p_idx)
-                        qp = q;
+                int qp = sm.slot_of[p_idx];
                 if (qp < 0)
                 {
                     if (ncols >= MAXACT)
@@ -611,7 +617,7 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
                     __syncwarp();
                     if (lane == 0)
                     {
-                        sm.col_of[qp] = p_idx;
+                        sm.slot_of[p_idx] = qp;
                         sm.gi1 = p_idx;
                         sm.gv1 = 1.0;
                     }
@@ -624,62 +630,40 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
                     ns++;
                 }
                 const double* gp = gcols + (size_t)qp * nvtot;
-                // r = GWW^-1 GWp  (Gaussian elimination on the augmented nW x (nW+1) system)
-                if (nW > 0)
-                {
-                    const int ldg = nW + 1;
-                    for (int e = lane; e < nW * ldg; e += 32)
-                    {
-                        const int a = e / ldg, b = e - a * ldg;
-                        double v;
-                        if (b < nW)
-                        {
-                            int qb = 0;
-                            for (int q = 0; q < ncols; ++q)
-                                if (sm.col_of[q] == sm.W_idx[b])
-                                    qb = q;
-                            v = gcols[(size_t)qb * nvtot + sm.W_idx[a]] * sm.sgn[a] * sm.sgn[b];
-                        }
-                        else
-                            v = gp[sm.W_idx[a]] * sm.sgn[a] * s;
-                        sm.GW[e] = v;
-                    }
-                    __syncwarp();
-                    for (int pv = 0; pv < nW; ++pv)
-                    {
-                        const double dinv = 1.0 / sm.GW[pv * ldg + pv];
-                        __syncwarp();
-                        for (int e = lane; e < nW * ldg; e += 32)
-                        {
-                            const int a = e / ldg, b = e - a * ldg;
-                            if (a != pv && b > pv)
-                                sm.GW[e] -= sm.GW[a * ldg + pv] * dinv * sm.GW[pv * ldg + b];
-                        }
-                        __syncwarp();
-                    }
-                    for (int a = lane; a < nW; a += 32)
-                        sm.r[a] = sm.GW[a * ldg + nW] / sm.GW[a * ldg + a];
-                    __syncwarp();
-                }
-                // direction zdir = s*gp - sum_a r_a sgn_a col(W_a); zp = s * zdir[p]
-                double zp = s * (s * gp[p_idx]);
-                for (int a = 0; a < nW; ++a)
-                {
-                    int qa = 0;
-                    for (int q = 0; q < ncols; ++q)
-                        if (sm.col_of[q] == sm.W_idx[a])
-                            qa = q;
-                    zp -= s * sm.r[a] * sm.sgn[a] * gcols[(size_t)qa * nvtot + p_idx];
-                }
-                const double t2 = (zp > 1e-300) ? (s * vv[p_idx] - s * (s > 0 ? up : lo)) / zp : INFINITY;
-                double t1 = INFINITY;
+                // gw_a = sgn_a s G[W_a][p];  r = Minv gw  (Minv symmetric: column access is coalesced)
+                for (int a2 = lane; a2 < nW; a2 += 32)
+                    sm.gw[a2] = sm.sgn[a2] * s * gp[sm.W_idx[a2]];
+                __syncwarp();
+                double zpart = 0.0, t1 = INFINITY;
                 int drop = -1;
-                for (int a = 0; a < nW; ++a)
-                    if (sm.r[a] > 0.0 && sm.lam[a] / sm.r[a] < t1)
+                for (int a2 = lane; a2 < nW; a2 += 32)
+                {
+                    double acc = 0.0;
+                    for (int b2 = 0; b2 < nW; ++b2)
+                        acc = fma(Minv[(size_t)b2 * nvtot + a2], sm.gw[b2], acc);
+                    sm.r[a2] = acc;
+                    zpart = fma(acc, sm.gw[a2], zpart);
+                    if (acc > 0.0 && sm.lam[a2] / acc < t1)
                     {
-                        t1 = sm.lam[a] / sm.r[a];
-                        drop = a;
+                        t1 = sm.lam[a2] / acc;
+                        drop = a2;
                     }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    zpart += __shfl_xor_sync(0xffffffffu, zpart, o);
+                    const double ot = __shfl_xor_sync(0xffffffffu, t1, o);
+                    const int od = __shfl_xor_sync(0xffffffffu, drop, o);
+                    if (ot < t1 || (ot == t1 && od >= 0 && (drop < 0 || od < drop)))
+                    {
+                        t1 = ot;
+                        drop = od;
+                    }
+                }
+                __syncwarp();
+                const double zp = gp[p_idx] - zpart;
+                const double t2 = (zp > 1e-300) ? (s * vv[p_idx] - s * (s > 0 ? up : lo)) / zp : INFINITY;
                 const double t = fmin(t1, t2);
                 if (!isfinite(t))
                 {
@@ -687,54 +671,94 @@ qp_generic_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __
                     fail = true;
                     break;
                 }
-                __syncwarp();
+                // primal step along s G[:,p] - sum_a r_a sgn_a G[:,W_a]
                 for (int e = lane; e < nvtot; e += 32)
                 {
                     double zd = s * gp[e];
-                    for (int a = 0; a < nW; ++a)
-                    {
-                        int qa = 0;
-                        for (int q = 0; q < ncols; ++q)
-                            if (sm.col_of[q] == sm.W_idx[a])
-                                qa = q;
-                        zd -= sm.r[a] * sm.sgn[a] * gcols[(size_t)qa * nvtot + e];
-                    }
+                    for (int a2 = 0; a2 < nW; ++a2)
+                        zd = fma(-sm.r[a2] * sm.sgn[a2], gcols[(size_t)sm.slotW[a2] * nvtot + e], zd);
                     vv[e] -= t * zd;
                 }
-                __syncwarp();
-                if (lane == 0)
-                    for (int a = 0; a < nW; ++a)
-                        sm.lam[a] -= t * sm.r[a];
+                for (int a2 = lane; a2 < nW; a2 += 32)
+                    sm.lam[a2] -= t * sm.r[a2];
                 lam_p += t;
                 __syncwarp();
                 if (t2 <= t1)
-                { // full step: p becomes active
+                { // full step: p becomes active; bordered update of Minv (Schur complement = zp)
                     if (nW >= MAXACT)
                     {
                         stat = VSMPC_STATUS_MAX_ITER;
                         fail = true;
                         break;
                     }
+                    const double izp = 1.0 / zp;
+                    for (int a2 = 0; a2 < nW; ++a2)
+                    {
+                        const double ra = sm.r[a2] * izp;
+                        for (int b2 = lane; b2 < nW; b2 += 32)
+                            Minv[(size_t)a2 * nvtot + b2] = fma(ra, sm.r[b2], Minv[(size_t)a2 * nvtot + b2]);
+                    }
+                    for (int a2 = lane; a2 < nW; a2 += 32)
+                    {
+                        Minv[(size_t)a2 * nvtot + nW] = -sm.r[a2] * izp;
+                        Minv[(size_t)nW * nvtot + a2] = -sm.r[a2] * izp;
+                    }
                     if (lane == 0)
                     {
+                        Minv[(size_t)nW * nvtot + nW] = izp;
                         sm.W_idx[nW] = p_idx;
                         sm.sgn[nW] = s;
                         sm.lam[nW] = lam_p;
+                        sm.slotW[nW] = qp;
+                        sm.wpos[p_idx] = nW;
                     }
                     nW++;
                     __syncwarp();
                     break;
                 }
-                // partial step: drop the blocking constraint and retry p
-                if (lane == 0)
-                    for (int a = drop; a + 1 < nW; ++a)
+                // partial step: position `drop` leaves the working set; down-date Minv, move the last position
+                // into the hole
+                {
+                    const int last = nW - 1;
+                    for (int b2 = lane; b2 < nW; b2 += 32)
+                        sm.gw[b2] = Minv[(size_t)drop * nvtot + b2];      // row `drop`
+                    __syncwarp();
+                    const double imdd = 1.0 / sm.gw[drop];
+                    for (int a2 = 0; a2 < nW; ++a2)
                     {
-                        sm.W_idx[a] = sm.W_idx[a + 1];
-                        sm.sgn[a] = sm.sgn[a + 1];
-                        sm.lam[a] = sm.lam[a + 1];
+                        const double f = sm.gw[a2] * imdd;
+                        for (int b2 = lane; b2 < nW; b2 += 32)
+                            Minv[(size_t)a2 * nvtot + b2] = fma(-f, sm.gw[b2], Minv[(size_t)a2 * nvtot + b2]);
                     }
-                nW--;
-                __syncwarp();
+                    __syncwarp();
+                    if (drop != last)
+                    {
+                        for (int b2 = lane; b2 < nW; b2 += 32)
+                            sm.gw[b2] = Minv[(size_t)last * nvtot + b2];  // row `last`
+                        __syncwarp();
+                        for (int b2 = lane; b2 < nW; b2 += 32)
+                        {
+                            Minv[(size_t)drop * nvtot + b2] = sm.gw[b2];
+                            Minv[(size_t)b2 * nvtot + drop] = sm.gw[b2];
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0)
+                    {
+                        sm.wpos[sm.W_idx[drop]] = -1;
+                        if (drop != last)
+                        {
+                            Minv[(size_t)drop * nvtot + drop] = sm.gw[last];
+                            sm.W_idx[drop] = sm.W_idx[last];
+                            sm.sgn[drop] = sm.sgn[last];
+                            sm.lam[drop] = sm.lam[last];
+                            sm.slotW[drop] = sm.slotW[last];
+                            sm.wpos[sm.W_idx[drop]] = drop;
+                        }
+                    }
+                    nW--;
+                    __syncwarp();
+                }
             }
             if (fail)
                 break;
