@@ -102,7 +102,8 @@ FP64-peak microbenchmarks run after the timed region; the torch fill is the L2 f
 {chr(10).join(tbl)}
 
 DRAM traffic of the QP kernel: {traffic / 1e6:.2f} MB per 1024-instance launch (`profiles/traffic.json`) against 3.4 MB algorithmic
-(QP data in, outputs out) — HBM is not the bound (< 0.5 % of peak).
+(QP data in, outputs out); the excess is the per-knot gain stack written and re-read inside the launch.
+{traffic / max(float(qp['gpu__time_duration.sum']) * (1e-6 if qu['gpu__time_duration.sum'] == 'us' else 1e-3), 1e-12) / 1e9:.0f} GB/s = {100 * traffic / max(float(qp['gpu__time_duration.sum']) * (1e-6 if qu['gpu__time_duration.sum'] == 'us' else 1e-3), 1e-12) / 6544.7e9:.1f} % of the measured HBM peak — HBM is not the bound.
 """
 open(os.path.join(P, f"{tag}_ncu_summary.md"), "w").write(md)
 print(md)
