@@ -58,3 +58,46 @@ def test_horizon_variant_matches_oracle(solver, variant):
             row = o.output_row()
             assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
     mpc.close()
+
+
+# edge cases of the condensed kernel's knot schedule: single / many throttle blocks, control horizon of one knot,
+# held block starting at knot 0 or at the last knot, shortest fine grid, longest supported horizon
+EDGE = [
+    dict(nIter=10, nIterSmall=2, controlHorizon=7),     # 6 throttle blocks, 2 fine knots
+    dict(nIter=8, nIterSmall=2, controlHorizon=2),      # one throttle block, joint block 1 held over 7 knots
+    dict(nIter=6, nIterSmall=2, controlHorizon=6),      # nothing held
+    dict(nIter=32, nIterSmall=7, controlHorizon=12),    # longest horizon the condensed kernel covers
+    dict(nIter=12, nIterSmall=3, controlHorizon=4, periodMPCLargeSteps=0.05, periodMPCSmallSteps=0.005),  # ratio 10
+    dict(nIter=9, nIterSmall=4, controlHorizon=8),      # held block over the last two knots only
+]
+
+
+@pytest.mark.parametrize("variant", range(len(EDGE)))
+def test_condensed_schedule_edge_cases(variant):
+    params = EDGE[variant]
+    B = 4
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=57 + variant, perturbed=True, near_bound_fraction=0.5)
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=0, full_solution=True)
+    mpc.configure(nom)
+    oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
+    ratio = oracles[0].mpc.vectorConstraints[2].ratio
+    for tick in range(3):
+        if tick == 2:       # force a released tick
+            mpc.debug_set_counters(-1, ratio - 1)
+        mpc.update(per)
+        mpc.solveMPC()
+        z = mpc.getSolution()
+        out, status = mpc.get_output()
+        assert (status == 0).all(), status
+        for i, o in enumerate(oracles):
+            if tick == 2:
+                o.mpc.vectorConstraints[2].counter = ratio - 1
+            o.update(per)
+            zo = o.solve()
+            assert np.abs(z[i] - zo).max() / max(1.0, np.abs(zo).max()) < 1e-6, (variant, tick, i)
+            row = o.output_row()
+            assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
+    mpc.close()
