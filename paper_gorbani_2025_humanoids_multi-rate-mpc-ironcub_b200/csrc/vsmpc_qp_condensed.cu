@@ -68,10 +68,12 @@ struct alignas(16) CdSmem
 enum : int { TK_NONE = 0, TK_STAGE = 1, TK_PROP = 2, TK_SCHUR = 3 };
 
 #ifdef VSMPC_PHASE_CLOCKS
-__device__ long long g_phase_clk[4096][8];
+__device__ long long g_phase_clk[4096][16];
+#define SUBCLK(acc, t0) do { const long long t1__ = clock64(); acc += t1__ - t0; t0 = t1__; } while (0)
 #define PHASE_CLK(slot) do { if (lane == 0 && warp == (slot >= 4 ? 1 : 0) && inst < 4096) g_phase_clk[inst][slot] = clock64(); } while (0)
 #else
 #define PHASE_CLK(slot) do { } while (0)
+#define SUBCLK(acc, t0) do { } while (0)
 #endif
 
 // y <- T_x^T y,  T_x = I + dt A_c   (structure: SURVEY App. A-3)
@@ -131,62 +133,62 @@ __device__ __forceinline__ void bjT_dot(const double (&y)[NX], const double* __r
     }
 }
 
-// dt * c' y   (c: affine term of the dynamics; rows LIN, TD, EP, ER)
+// dt * c' y   (c: affine term of the dynamics; rows LIN, TD, EP, ER); three independent FMA chains
 __device__ __forceinline__ double c_dot(const double (&y)[NX], const double* __restrict__ cf, double dt)
 {
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
     for (int a = 0; a < 3; ++a)
     {
-        acc = fma(y[IX_LIN + a], cf[QD_CL + a], acc);
-        acc = fma(y[IX_EP + a], cf[QD_CEP + a], acc);
-        acc = fma(y[IX_ER + a], cf[QD_CER + a], acc);
+        a0 = fma(y[IX_LIN + a], cf[QD_CL + a], a0);
+        a1 = fma(y[IX_EP + a], cf[QD_CEP + a], a1);
+        a2 = fma(y[IX_ER + a], cf[QD_CER + a], a2);
     }
 #pragma unroll
     for (int j = 0; j < NT; ++j)
-        acc = fma(y[IX_TD + j], cf[QD_CTD + j], acc);
-    return dt * acc;
+    {
+        if (j & 1)
+            a1 = fma(y[IX_TD + j], cf[QD_CTD + j], a1);
+        else
+            a0 = fma(y[IX_TD + j], cf[QD_CTD + j], a0);
+    }
+    return dt * (a0 + a1 + a2);
 }
 
-// Gauss-Jordan inverse of an SPD 8 x 8 matrix in shared memory (row-major, ld 8, 16-byte aligned), in place, by one
-// warp: lane (r = lane & 7, q = lane >> 3) owns S[r][2q..2q+1]; pivot rows are broadcast through shared memory
-__device__ __forceinline__ bool gj8(double* __restrict__ S, double2 own, int lane)
+// Gauss-Jordan inverse of an SPD 8 x 8 matrix through shared memory by one warp: lane (r = lane & 7, q = lane >> 3)
+// owns element pair [r][2q..2q+1] in registers; every pivot step reads the pivot row / column from one buffer and
+// writes the updated pairs to the other (ping-pong S <-> T: one __syncwarp per pivot, no divergent branches); eight
+// pivots later the inverse is back in S.  S, T: row-major, ld 8, 16-byte aligned.
+__device__ __forceinline__ bool gj8(double* __restrict__ S, double* __restrict__ T, double2 own, int lane)
 {
     const int r = lane & 7, q = lane >> 3;
-    double2* S2 = reinterpret_cast<double2*>(S);
-    S2[r * 4 + q] = own;
+    reinterpret_cast<double2*>(S)[r * 4 + q] = own;
     __syncwarp();
     bool ok = true;
-#pragma unroll 1
+    double* src = S;
+    double* dst = T;
+#pragma unroll 2
     for (int p = 0; p < NJ; ++p)
     {
-        const double d = S[p * NJ + p];
-        const double f = S[r * NJ + p];
-        const double2 pr = S2[p * 4 + q];
-        ok = ok && (d > 0.0) && isfinite(d);
-        const double dinv = 1.0 / d;
+        const double d = src[p * NJ + p];
+        const double f = src[r * NJ + p];
+        const double2 pr = reinterpret_cast<const double2*>(src)[p * 4 + q];
+        ok = ok && (d > 0.0) && (d < 1e300);
+        const double dinv = __drcp_rn(d);
+        const bool piv = r == p;
+        const double coef = piv ? -dinv : f * dinv;      // pivot row: 0 - (-1/d) * row ; others: own - (f/d) * row
+        const double bx = piv ? 0.0 : own.x, by = piv ? 0.0 : own.y;
+        own.x = fma(-coef, pr.x, bx);
+        own.y = fma(-coef, pr.y, by);
+        const double val = piv ? dinv : -coef;           // column p of the inverse in progress
+        const bool mine = q == (p >> 1);
+        own.x = (mine && !(p & 1)) ? val : own.x;
+        own.y = (mine && (p & 1)) ? val : own.y;
+        reinterpret_cast<double2*>(dst)[r * 4 + q] = own;
         __syncwarp();
-        const double ff = f * dinv;
-        if (r == p)
-        {
-            own.x = pr.x * dinv;
-            own.y = pr.y * dinv;
-        }
-        else
-        {
-            own.x = fma(-ff, pr.x, own.x);
-            own.y = fma(-ff, pr.y, own.y);
-        }
-        if (q == (p >> 1))
-        {
-            const double val = (r == p) ? dinv : -ff;
-            if (p & 1)
-                own.y = val;
-            else
-                own.x = val;
-        }
-        S2[r * 4 + q] = own;
-        __syncwarp();
+        double* t = src;
+        src = dst;
+        dst = t;
     }
     return ok;
 }
@@ -272,11 +274,11 @@ __device__ __forceinline__ bool a_eliminate(const CdCtx& c, CdSlot& sl, double (
 {
     CdSmem& sm = c.sm;
     const int lane = c.lane;
-    const bool ok = gj8(sl.Hinv, own, lane);
+    const bool ok = gj8(sl.Hinv, sm.Mt, own, lane);   // Mt: free between the transposition and the gain rows
     if (lane < NX)
     {
         const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
-#pragma unroll 1
+#pragma unroll 2
         for (int a = 0; a < NJ; ++a)
         {
             double v0 = 0.0, v1 = 0.0;
@@ -546,31 +548,55 @@ __device__ __forceinline__ void b_prop(const CdCtx& c, int k, bool tail, double 
     }
     // a-terms: D_s' Psi''_l
     bjT_dot(s, sm.lam, dt, bj2);
+    // Om += D'Psi'' (rows of the special columns) then Om += Psi''D (columns of the special columns): the loads of a
+    // group before its stores (distinct entries), one warp barrier between the two phases
     if (lane < NLO)
     {
+        {
+            double ov[NT];
 #pragma unroll
-        for (int q = 0; q < NT; ++q)
-            sm.Om[(4 * tb + q) * NLO + lane] += dt * (cf[QD_JG + q] * s[IX_TD + q] + jgt * s[IX_T + q]);
-        sm.Om[AFFL * NLO + lane] += c_dot(s, cf, dt);
+            for (int q = 0; q < NT; ++q)
+                ov[q] = sm.Om[(4 * tb + q) * NLO + lane];
+            const double oa = sm.Om[AFFL * NLO + lane];
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+                sm.Om[(4 * tb + q) * NLO + lane] = ov[q] + dt * (cf[QD_JG + q] * s[IX_TD + q] + jgt * s[IX_T + q]);
+            sm.Om[AFFL * NLO + lane] = oa + c_dot(s, cf, dt);
+        }
         if (tail)
         {
+            double od[NJ];
 #pragma unroll
             for (int a = 0; a < NJ; ++a)
-                sm.Om[(c.D0 + a) * NLO + lane] += bj2[a];
+                od[a] = sm.Om[(c.D0 + a) * NLO + lane];
+#pragma unroll
+            for (int a = 0; a < NJ; ++a)
+                sm.Om[(c.D0 + a) * NLO + lane] = od[a] + bj2[a];
         }
     }
     __syncwarp();
     if (lane < NLO)
     {
+        {
+            double ov[NT];
 #pragma unroll
-        for (int q = 0; q < NT; ++q)
-            sm.Om[lane * NLO + 4 * tb + q] += bv[q];
-        sm.Om[lane * NLO + AFFL] += baff;
+            for (int q = 0; q < NT; ++q)
+                ov[q] = sm.Om[lane * NLO + 4 * tb + q];
+            const double oa = sm.Om[lane * NLO + AFFL];
+#pragma unroll
+            for (int q = 0; q < NT; ++q)
+                sm.Om[lane * NLO + 4 * tb + q] = ov[q] + bv[q];
+            sm.Om[lane * NLO + AFFL] = oa + baff;
+        }
         if (tail)
         {
+            double od[NJ];
 #pragma unroll
             for (int a = 0; a < NJ; ++a)
-                sm.Om[lane * NLO + c.D0 + a] += bd[a];
+                od[a] = sm.Om[lane * NLO + c.D0 + a];
+#pragma unroll
+            for (int a = 0; a < NJ; ++a)
+                sm.Om[lane * NLO + c.D0 + a] = od[a] + bd[a];
         }
     }
     __syncwarp();
@@ -723,6 +749,8 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
         y[j] = 0.0;
     const double qd_lane = lane < NX ? sm.Qd[lane] : 0.0;
     bool ok = true;
+    long long clkA0 = 0, clkA1 = 0, clkB0 = 0, clkB1 = 0;
+    (void)clkA0; (void)clkA1; (void)clkB0; (void)clkB1;
     const int n_it = c.kS < 0 ? N + 1 : (N - 1 - c.kS) + 3 + c.kS + 1;
     for (int t = 0; t < n_it; ++t)
     {
@@ -736,8 +764,13 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                 double hux[NJ];
                 double2 own;
                 const bool elim = ta == TK_STAGE && !(held && ka >= Nc - 1);
+                long long tclk = clock64();
+                (void)tclk;
                 if (ta != TK_SCHUR)
+                {
                     a_prop(c, ka, elim, y, qd_lane, hux, own);
+                    SUBCLK(clkA0, tclk);
+                }
                 else
                 {
                     // Schur step of the held joint block: H_ux = Psi_T[:, d]' (published by warp B),
@@ -752,6 +785,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                 __syncwarp();
                 if (elim || ta == TK_SCHUR)
                     ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * WSC_STAGE) && ok;
+                SUBCLK(clkA1, tclk);
             }
         }
         else if (tbk != TK_NONE)
@@ -761,9 +795,12 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
             const bool isD = lane >= c.D0 && lane < c.D0 + NJ;
             double hut[NJ];
             bool down = false;
+            long long tclk = clock64();
+            (void)tclk;
             if (tbk != TK_SCHUR)
             {
                 b_prop(c, kb, tail, y, hut);
+                SUBCLK(clkB0, tclk);
                 if (tbk == TK_PROP)
                 {
                     // publish H_ux = Psi_T[:, d]' for warp A's Schur step
@@ -795,6 +832,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
                 }
                 const bool schur = tbk == TK_SCHUR;
                 b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD);
+                SUBCLK(clkB1, tclk);
                 if (schur)
                 {
                     if (lane < NLO)
@@ -814,6 +852,13 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
     }
     PHASE_CLK(2);
     PHASE_CLK(4);
+#ifdef VSMPC_PHASE_CLOCKS
+    if (lane == 0 && inst < 4096)
+    {
+        if (warp == 0) { g_phase_clk[inst][8] = clkA0; g_phase_clk[inst][9] = clkA1; }
+        else { g_phase_clk[inst][10] = clkB0; g_phase_clk[inst][11] = clkB1; }
+    }
+#endif
     if (warp == 0 && lane == 0)
         sm.flags[0] = ok ? 0 : 1;
     // Psi_0' x0 while warp B still holds its column, then the deferred down-date of Om on the tensor cores (both
@@ -1243,7 +1288,7 @@ qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* 
 int condensed_phase_clocks(long long* host, int n)
 {
 #ifdef VSMPC_PHASE_CLOCKS
-    return cudaMemcpyFromSymbol(host, g_phase_clk, sizeof(long long) * 8 * (n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
+    return cudaMemcpyFromSymbol(host, g_phase_clk, sizeof(long long) * 16 * (n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
 #else
     (void)host; (void)n;
     return 3;

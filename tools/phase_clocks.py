@@ -13,7 +13,7 @@ mpc.configure_pack(nom_pack, jp, (np.arange(B) % 20).astype(np.int32))
 for j in range(4):
     mpc.update_pack(packs[j % 2]); mpc.solveMPC()
 n = min(B, 4096)
-clk = np.zeros((n, 8), dtype=np.int64)
+clk = np.zeros((n, 16), dtype=np.int64)
 rc = L.load().vsmpc_debug_phase_clocks(clk.ctypes.data, n)
 assert rc == 0, rc
 t0 = clk[:, 0].min()
@@ -35,3 +35,6 @@ for lo_, hi_ in ((0, 0), (1, 3), (4, 6), (7, 10), (11, 15), (16, 99)):
     m = (it >= lo_) & (it <= hi_)
     if m.any():
         print(f"  iters {lo_:2d}-{hi_:2d}: {m.sum():4d} instances, AS phase mean {as_t[m].mean():8.0f} cycles")
+
+print("warp A per launch: a_prop %.0f  a_eliminate %.0f ; warp B: b_prop %.0f  b_downdate %.0f (cycles summed over knots, mean over instances)" %
+      (clk[:, 8].mean(), clk[:, 9].mean(), clk[:, 10].mean(), clk[:, 11].mean()))
