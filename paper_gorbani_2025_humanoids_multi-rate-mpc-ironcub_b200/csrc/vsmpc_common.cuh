@@ -155,6 +155,21 @@ struct Jet
     }
 };
 
+// dynamic shared memory opt-in is a per-device function attribute: set it once per device a kernel is launched on
+template <typename K> inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, bool (&done)[64])
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    if (dev >= 0 && dev < 64 && done[dev])
+        return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64)
+        done[dev] = true;
+    return e;
+}
+
 // JetModel::destandardizeThrottle_u2T with the instance's constants from the QP data block
 __device__ inline double destd_throttle_qd(const double* __restrict__ cf, double vv)
 {

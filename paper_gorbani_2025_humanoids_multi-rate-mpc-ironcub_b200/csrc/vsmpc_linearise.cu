@@ -715,14 +715,14 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              cudaStream_t s)
 {
     const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12 + 20 + ((h_cfg.st_rows + 4 + 3) & ~3)) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        cudaFuncSetAttribute(linearise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    static bool attr_set[64] = {};
     if (smem > 200 * 1024)
         return cudaErrorInvalidValue;
+    {
+        const cudaError_t e = ensure_dynamic_smem(linearise_kernel, 200 * 1024, attr_set);
+        if (e != cudaSuccess)
+            return e;
+    }
     const int grid = (B + K1_WARPS - 1) / K1_WARPS;
     linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(d_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
                                                        alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip);

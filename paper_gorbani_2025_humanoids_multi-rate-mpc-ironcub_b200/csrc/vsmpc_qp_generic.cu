@@ -826,13 +826,11 @@ cudaError_t launch_qp_generic(const DeviceConfig* d_cfg, const DeviceConfig& h_c
                               int* n_factor, int* n_solve, cudaStream_t s)
 {
     const size_t smem = sizeof(GenSmem) * GEN_WARPS;
-    static bool attr_set = false;
-    if (!attr_set)
+    static bool attr_set[64] = {};
     {
-        cudaError_t e = cudaFuncSetAttribute(qp_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = ensure_dynamic_smem(qp_generic_kernel, (int)smem, attr_set);
         if (e != cudaSuccess)
             return e;
-        attr_set = true;
     }
     const int grid = (B + GEN_WARPS - 1) / GEN_WARPS;
     qp_generic_kernel<<<grid, 32 * GEN_WARPS, smem, s>>>(d_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor,

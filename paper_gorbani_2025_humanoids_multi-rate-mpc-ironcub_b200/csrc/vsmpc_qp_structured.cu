@@ -1234,13 +1234,11 @@ cudaError_t launch_qp_structured(const DeviceConfig* d_cfg, const DeviceConfig& 
                                  int* n_factor, int* n_solve, int want_z, cudaStream_t s)
 {
     const size_t smem = sizeof(StSmem) * SW;
-    static bool attr_set = false;
-    if (!attr_set)
+    static bool attr_set[64] = {};
     {
-        cudaError_t e = cudaFuncSetAttribute(qp_structured_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = ensure_dynamic_smem(qp_structured_kernel, (int)smem, attr_set);
         if (e != cudaSuccess)
             return e;
-        attr_set = true;
     }
     const int grid = (B + SW - 1) / SW;
     qp_structured_kernel<<<grid, 32 * SW, smem, s>>>(d_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor,
