@@ -59,6 +59,9 @@ struct vsmpc_handle
     // host -> device staging of vsmpc_set_state: its own copy stream and two pack buffers, so that the copy of tick
     // j+1 overlaps the kernels of tick j
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t out_stream = nullptr;   // device -> host read-back of vsmpc_get_output_async
+    cudaEvent_t ev_solved = nullptr;     // last QP kernel done
+    bool out_pending = false;            // a read-back on out_stream has not been ordered before the next solve yet
     double* d_pack_in[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};
@@ -250,6 +253,8 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     A(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&h->ev_solved, cudaEventDisableTiming));
     for (int q = 0; q < 2; ++q)
     {
         A(dalloc(&h->d_pack_in[q], (size_t)VSMPC_PACK_DOUBLES * B));
@@ -326,6 +331,10 @@ int vsmpc_destroy(vsmpc_handle* h)
     }
     if (h->copy_stream)
         cudaStreamDestroy(h->copy_stream);
+    if (h->out_stream)
+        cudaStreamDestroy(h->out_stream);
+    if (h->ev_solved)
+        cudaEventDestroy(h->ev_solved);
     if (h->tick_graph)
         cudaGraphExecDestroy(h->tick_graph);
     for (void* p : ptrs)
@@ -501,12 +510,17 @@ int vsmpc_get_output_async(vsmpc_handle* h, double* out_rows_host, int* status_h
     if (!h || h->B <= 0 || !ticket)
         return VSMPC_ERR_ARG;
     CK(cudaSetDevice(h->device));
+    // the read-back runs on its own stream behind the solve, so that the next tick's linearise kernel does not queue
+    // behind the copy; the next QP kernel (the only writer of these buffers) is ordered after it in solve_launch
+    CK(cudaEventRecord(h->ev_solved, h->stream));
+    CK(cudaStreamWaitEvent(h->out_stream, h->ev_solved, 0));
     if (out_rows_host)
-        CK(cudaMemcpyAsync(out_rows_host, h->d_out, (size_t)VSMPC_OUT_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(out_rows_host, h->d_out, (size_t)VSMPC_OUT_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->out_stream));
     if (status_host)
-        CK(cudaMemcpyAsync(status_host, h->d_status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(status_host, h->d_status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->out_stream));
     const int q = h->out_idx ^= 1;
-    CK(cudaEventRecord(h->ev_out[q], h->stream));
+    CK(cudaEventRecord(h->ev_out[q], h->out_stream));
+    h->out_pending = true;
     *ticket = q;
     return VSMPC_OK;
 }
@@ -644,6 +658,11 @@ static_assert(sizeof(PlantModel) == sizeof(vsmpc_plant_model), "PlantModel must 
 
 static int solve_launch(vsmpc_handle* h)
 {
+    if (h->out_pending)
+    { // an asynchronous read-back of the previous outputs must finish before they are overwritten
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out[h->out_idx], 0));
+        h->out_pending = false;
+    }
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
                                h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
