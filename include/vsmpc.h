@@ -190,8 +190,10 @@ int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_coun
 
 /* ---- device-resident closed loop (the loop body of src/variable_sampling_mpc.py:106-161) --------
  * A SURROGATE plant replaces MuJoCo (not available): it integrates the MPC's own nonlinear model
- * (centroidal momentum driven by the four jets, gravity, and the second-order jet model of
- * src/mujoco_lib/jet_kalman_filter.py:30-45) with frozen body-frame kinematics, n_sub steps of dt_sim per
+ * (centroidal momentum driven by the four jets, gravity scaled by the take-off factor alpha_g the MPC publishes — the
+ * ground carries the rest —, and the second-order jet model of
+ * src/mujoco_lib/jet_kalman_filter.py:30-45); the jet frames follow the (position-controlled) arm joints through
+ * first-order kinematics about the posture q0 with frozen relative Jacobians; n_sub steps of dt_sim per
  * controller tick, and rebuilds the pack from the plant state on the device.  Per tick: plant -> pack ->
  * linearise kernel -> QP kernel -> feedback (:124-131); no host round trip. */
 #define VSMPC_PS_P_COM            0   /* 3  CoM position (world)                                         */
@@ -221,6 +223,7 @@ typedef struct vsmpc_plant_model
     double J_jet_lin_body[96];    /* 4x3x8 linear Jacobians of the jet frames (body frame)               */
     double J_com_body[24];        /* 3x8  CoM Jacobian, joint part (body frame)                          */
     double gravity[3];
+    double q0[8];                 /* controlled-joint posture the frozen kinematics above refer to                */
     double dt_sim;                /* plant step (reference: MuJoCo timestep 1 ms)                        */
     int n_sub;                    /* plant steps per controller tick (reference: periodMPC / dt = 5)     */
 } vsmpc_plant_model;

@@ -4,9 +4,12 @@ The reference closes the loop through MuJoCo (src/mujoco_lib/ironcub_mujoco_simu
 available here; both the CUDA rollout (csrc/vsmpc_plant.cu) and this file integrate the SAME
 stated surrogate: the MPC's own nonlinear model with frozen body-frame kinematics,
   jets      : jet_kalman_filter.py:30-45  (Td += sigma_T (f + g v(u)) dt ; T += Td dt)
-  momentum  : h_lin^w' = m g + sum_i (T_i + dT_i) R a_i ;  h_ang^B' = -w_B x h_ang^B + sum_i (T_i + dT_i) r_i x a_i
+  momentum  : h_lin^w' = alpha_g m g + sum_i (T_i + dT_i) R a_i ;  h_ang^B' = -w_B x h_ang^B + sum_i (T_i + dT_i) r_i x a_i
   pose      : p' = h_lin^w / m ;  rpy' = W^-1(rpy) I_B^-1 h_ang^B
-  joints    : q = q_cmd
+  joints    : q = q_cmd (position control); the jet frames follow the controlled joints through FIRST-ORDER kinematics
+              about the configure-time posture q0 with frozen relative Jacobians (the same sensitivities the MPC's
+              Lambda matrices are built from, systemDynamicsVSMPC.cpp:159-226,321-350):
+              a_i(q) = a_i0 + (J^w_rel,i dq) x a_i0 ,  r_i(q) = r_i0 + (J^lin_i - J^CoM) dq ,  dq = q - q0
 ``SurrogateLoop`` drives one oracle MPC instance in closed loop exactly like the reference driver
 (src/variable_sampling_mpc.py:106-131).  Written independently of the product's Python (it shares no code
 with paper_..._b200/synthetic.py or rollout.py); only tests/ and bench.py's cpu_baseline may import it.
@@ -46,10 +49,24 @@ class SurrogatePlant:
         self.s = {k: np.array(v, float) for k, v in state.items()}
         self.dt, self.n_sub = dt_sim, n_sub
         self.jet = jet_model or JetModel()
+        self.sel = list(range(3, 11))
 
-    def step(self):
+    def jet_frames_body(self):
+        """Thrust axes / arms in the body frame at the current joint command (first-order kinematics)."""
+        g = self.g
+        dq = (self.s["q_cmd"] - g["joint_pos0"])[self.sel]
+        a = np.empty((4, 3)); r = np.empty((4, 3))
+        for i in range(4):
+            w = g["J_rel_body"][i][3:6][:, self.sel] @ dq
+            a[i] = g["jet_axes_body"][i] + np.cross(w, g["jet_axes_body"][i])
+            r[i] = g["jet_pos_body"][i] + (g["J_jet_lin_body"][i][:, self.sel] - g["J_com_body"][:, self.sel]) @ dq
+        return a, r
+
+    def step(self, alpha_g: float = 1.0):
+        """alpha_g: the gravity-compensation factor the MPC published this tick (the ground carries 1 - alpha_g)."""
         s, g, jet = self.s, self.g, self.jet
         sig = jet.getThrustStandardDeviation_u2T()
+        aB, rB = self.jet_frames_body()
         for _ in range(self.n_sub):
             R = _R(s["rpy"])
             for j in range(4):
@@ -59,10 +76,10 @@ class SurrogatePlant:
                 s["thrust_dot"][j] += tdd * sig * self.dt
                 s["thrust"][j] += s["thrust_dot"][j] * self.dt
             Tt = s["thrust"] + self.dT
-            fB = Tt @ g["jet_axes_body"]
-            tauB = Tt @ np.cross(g["jet_pos_body"], g["jet_axes_body"])
+            fB = Tt @ aB
+            tauB = Tt @ np.cross(rB, aB)
             wB = self.Iinv @ s["ang_mom_body"]
-            s["lin_mom_world"] = s["lin_mom_world"] + self.dt * (self.mass * g["gravity"] + R @ fB)
+            s["lin_mom_world"] = s["lin_mom_world"] + self.dt * (alpha_g * self.mass * g["gravity"] + R @ fB)
             s["ang_mom_body"] = s["ang_mom_body"] + self.dt * (tauB - np.cross(wB, s["ang_mom_body"]))
             wB = self.Iinv @ s["ang_mom_body"]
             r0, r1 = s["rpy"][0], s["rpy"][1]
@@ -82,8 +99,9 @@ class SurrogatePlant:
         M[:3, 3:] = -self.mass * Sc
         M[3:, :3] = self.mass * Sc
         M[3:, 3:] = R @ self.I @ R.T + self.mass * (Sc.T @ Sc)
-        aw = g["jet_axes_body"] @ R.T
-        rw = g["jet_pos_body"] @ R.T
+        aB, rB = self.jet_frames_body()
+        aw = aB @ R.T
+        rw = rB @ R.T
         A = np.zeros((6, 4))
         A[:3] = (aw @ R).T
         A[3:] = (np.cross(rw, aw) @ R).T
@@ -136,5 +154,5 @@ class SurrogateLoop:
         s["thrust_dot_des"] = np.array(self.mpc.getThrustDotReference(), float)
         s["q_cmd"] = np.array(self.mpc.getJointsReferencePosition(), float)
         self._feed()
-        self.plant.step()                                   # sim.step(n_steps)
+        self.plant.step(self.qp.getAlphaGravity())          # sim.step(n_steps)
         return np.concatenate([s["p_com"], s["rpy"], s["thrust"], s["throttle"]])

@@ -54,7 +54,7 @@ class VsmpcPlantModel(C.Structure):
     _fields_ = [
         ("com_from_base_body", C.c_double * 3), ("jet_pos_body", C.c_double * 12),
         ("jet_axes_body", C.c_double * 12), ("J_rel_ang_body", C.c_double * 96),
-        ("J_jet_lin_body", C.c_double * 96), ("J_com_body", C.c_double * 24), ("gravity", C.c_double * 3),
+        ("J_jet_lin_body", C.c_double * 96), ("J_com_body", C.c_double * 24), ("gravity", C.c_double * 3), ("q0", C.c_double * 8),
         ("dt_sim", C.c_double), ("n_sub", C.c_int),
     ]
 

@@ -15,7 +15,7 @@ namespace vsmpc
 {
 cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
                          const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
-                         const double* ip, cudaStream_t s);
+                         const double* ip, const double* st, cudaStream_t s);
 cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
@@ -710,7 +710,7 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
         CK(cudaMemsetAsync(h->d_phase, 0, B * 4, h->stream));
     // first pack from the plant state, then IMPCProblem::configure on it (tick 0 of every counter)
     CK(launch_plant(h->d_cfg, h->d_pm, h->B, 0, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, nullptr,
-                    h->use_ip ? h->d_ip : nullptr, h->stream));
+                    h->use_ip ? h->d_ip : nullptr, nullptr, h->stream));
     int rc = run_linearise(h, 1);
     if (rc)
         return rc;
@@ -730,7 +730,7 @@ static int tick_launch(vsmpc_handle* h, double* rec)
     if (rc)
         return rc;
     CK(launch_plant(h->d_cfg, h->d_pm, h->B, 1, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, rec,
-                    h->use_ip ? h->d_ip : nullptr, h->stream));
+                    h->use_ip ? h->d_ip : nullptr, h->d_st, h->stream));
     return VSMPC_OK;
 }
 

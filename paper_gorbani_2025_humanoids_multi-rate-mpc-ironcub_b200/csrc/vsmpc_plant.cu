@@ -7,9 +7,12 @@
 // SURROGATE that integrates the MPC's own nonlinear model with frozen body-frame kinematics:
 //   jets      : Tdd = sigma_T (f(T,Td) + g(T,Td) v(u)), semi-implicit Euler exactly as
 //               src/mujoco_lib/jet_kalman_filter.py:30-45 (Td += Tdd dt; T += Td dt)
-//   momentum  : h_lin^w' = m g + sum_i (T_i + dT_i) R a_i ;  h_ang^B' = -w_B x h_ang^B + sum_i (T_i + dT_i) r_i x a_i
+//   momentum  : h_lin^w' = alpha_g m g + sum_i (T_i + dT_i) R a_i ;  h_ang^B' = -w_B x h_ang^B + sum_i (T_i + dT_i) r_i x a_i
 //   pose      : p' = h_lin^w / m ;  rpy' = W^-1(rpy) w_B,  w_B = I_B^-1 h_ang^B
-//   joints    : position-controlled, q = q_cmd (the accumulated MPC joint reference)
+//   joints    : position-controlled, q = q_cmd (the accumulated MPC joint reference); the jet frames follow them through
+//               first-order kinematics about q0 with frozen relative Jacobians (the sensitivities behind the MPC's
+//               Lambda matrices, systemDynamicsVSMPC.cpp:159-226,321-350):
+//               a_i(q) = a_i0 + (J^w_rel,i dq) x a_i0 ,  r_i(q) = r_i0 + (J^lin_i - J^CoM) dq ,  dq = q - q0
 // and rebuilds the getter-level pack (include/vsmpc.h VSMPC_PK_*) from the plant state every tick.
 #include "vsmpc_common.cuh"
 #include "vsmpc_plant.cuh"
@@ -54,6 +57,41 @@ __device__ __forceinline__ bool inv3(const double* M, double* o)
     return det != 0.0 && isfinite(id);
 }
 
+// thrust axes / arms in the body frame at joint command q (first-order kinematics about pm.q0)
+__device__ __forceinline__ void jet_frames_body(const PlantModel& pm, const double* q, double (&aB)[NT][3], double (&rB)[NT][3])
+{
+    double dq[NJ];
+#pragma unroll
+    for (int b = 0; b < NJ; ++b)
+        dq[b] = q[b] - pm.q0[b];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        double w[3], d[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            double sw = 0.0, sd = 0.0;
+#pragma unroll
+            for (int b = 0; b < NJ; ++b)
+            {
+                sw = fma(pm.J_rel_ang_body[j * 24 + a * NJ + b], dq[b], sw);
+                sd = fma(pm.J_jet_lin_body[j * 24 + a * NJ + b] - pm.J_com_body[a * NJ + b], dq[b], sd);
+            }
+            w[a] = sw;
+            d[a] = sd;
+        }
+        double wxa[3];
+        cross3(w, pm.jet_axes_body + 3 * j, wxa);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            aB[j][a] = pm.jet_axes_body[3 * j + a] + wxa[a];
+            rB[j][a] = pm.jet_pos_body[3 * j + a] + d[a];
+        }
+    }
+}
+
 // mode 0: build the pack from the plant state only (tick 0 / configure)
 // mode 1: apply the MPC outputs of the tick just solved (feedback, src/variable_sampling_mpc.py:124-131),
 //         integrate n_sub plant steps, record, build the next pack
@@ -61,7 +99,7 @@ __global__ void __launch_bounds__(128)
 plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict__ pmp, int B, int mode,
              double* __restrict__ ps, const double* __restrict__ pp, const double* __restrict__ out_rows,
              const int* __restrict__ status, double* __restrict__ pack, double* __restrict__ rec,
-             const double* __restrict__ ip)
+             const double* __restrict__ ip, const double* __restrict__ st)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B)
@@ -122,12 +160,16 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 #pragma unroll
         for (int a = 0; a < NJ; ++a)
             q[a] = o[VSMPC_OUT_JOINTS_REF + a];
-        // torque arms r_i x a_i (body, frozen)
-        double rxa[NT][3];
+        // jet frames at the new joint command, torque arms r_i x a_i (body)
+        double aBm[NT][3], rBm[NT][3], rxa[NT][3];
+        jet_frames_body(pm, q, aBm, rBm);
 #pragma unroll
         for (int j = 0; j < NT; ++j)
-            cross3(pm.jet_pos_body + 3 * j, pm.jet_axes_body + 3 * j, rxa[j]);
+            cross3(rBm[j], aBm[j], rxa[j]);
         const double dt = pm.dt_sim;
+        // the ground carries the share (1 - alpha_g) of the weight during take-off: the plant uses the gravity
+        // compensation factor the MPC published for this tick (QPInput::setAlphaGravity, systemDynamicsVSMPC.cpp:307-311)
+        const double alpha_g = st ? st[(size_t)ST_ALPHA * B + i] : 1.0;
         for (int sstep = 0; sstep < pm.n_sub; ++sstep)
         {
             double R[9];
@@ -150,7 +192,7 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
                 {
-                    fB[a] += Tj * pm.jet_axes_body[3 * j + a];
+                    fB[a] += Tj * aBm[j][a];
                     tauB[a] += Tj * rxa[j][a];
                 }
             }
@@ -161,7 +203,7 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 #pragma unroll
             for (int a = 0; a < 3; ++a)
             {
-                hl[a] += dt * (mass * pm.gravity[a] + fW[a]);
+                hl[a] += dt * (alpha_g * mass * pm.gravity[a] + fW[a]);
                 ha[a] += dt * (tauB[a] - wxh[a]);
             }
             // pose
@@ -219,6 +261,8 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 
     // ---- pack of the current plant state (the formulas of the synthetic robot, synthetic.py::make_states) ----
     double R[9], wB[3], v3[3], c[3];
+    double aBp[NT][3], rBp[NT][3];
+    jet_frames_body(pm, q, aBp, rBp);
     rpy_to_R(rpy, R);
     mat3_vec(Ibinv, ha, wB);
 #pragma unroll
@@ -275,8 +319,8 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
     for (int j = 0; j < NT; ++j)
     {
         double aw[3], rw[3], rxaw[3], t3[3];
-        mat3_vec(R, pm.jet_axes_body + 3 * j, aw);
-        mat3_vec(R, pm.jet_pos_body + 3 * j, rw);
+        mat3_vec(R, aBp[j], aw);
+        mat3_vec(R, rBp[j], rw);
         cross3(rw, aw, rxaw);
         // A_mom_body = [R'a_w ; R'(r_w x a_w)]  (Robot::getMatrixAmomJets(true), Robot.cpp:325-329)
         mat3T_vec(R, aw, t3);
@@ -323,10 +367,10 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 
 cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
                          const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
-                         const double* ip, cudaStream_t s)
+                         const double* ip, const double* st, cudaStream_t s)
 {
     const int threads = 128;
-    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec, ip);
+    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec, ip, st);
     return cudaGetLastError();
 }
 

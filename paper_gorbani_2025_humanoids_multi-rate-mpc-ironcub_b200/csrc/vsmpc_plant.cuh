@@ -23,6 +23,7 @@ struct PlantModel
     double J_jet_lin_body[96];
     double J_com_body[24];
     double gravity[3];
+    double q0[8];
     double dt_sim;
     int n_sub;
 };

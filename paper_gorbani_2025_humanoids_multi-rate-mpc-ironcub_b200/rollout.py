@@ -27,6 +27,7 @@ def plant_model_from_robot(rb: SyntheticRobot, sel=None, dt_sim: float = 0.001, 
     m.J_jet_lin_body = (C.c_double * 96)(*rb.J_jet_lin_body[:, :, sel].reshape(-1))
     m.J_com_body = (C.c_double * 24)(*rb.J_com_body[:, sel].reshape(-1))
     m.gravity = (C.c_double * 3)(*rb.gravity)
+    m.q0 = (C.c_double * 8)(*rb.joint_pos0[sel])
     m.dt_sim = float(dt_sim)
     m.n_sub = int(n_sub)
     return m

@@ -41,6 +41,8 @@ def make_case(B, seed=11):
     st["thrust_des"] = st["thrust"].copy()
     st["thrust_dot_est"] = g.normal(0, 5.0, (B, 4))
     st["thrust_dot_des"] = np.zeros((B, 4))
+    # the loop starts at the posture the frozen kinematics refer to (the jet frames then follow q_cmd - q0)
+    st["q_cmd"] = np.tile(rb.joint_pos0, (B, 1))
     # the generator draws omega_B independently of the angular momentum; a plant state has w_B = I_B^-1 h_ang^B
     for i in range(B):
         wB = np.linalg.solve(rb.I_body * isc[i], st["momentum_body"][i, 3:])
@@ -61,14 +63,24 @@ def test_oracle_plant_pack_matches_host_pack():
 
 
 def test_oracle_closed_loop_is_stable():
-    """Sanity of the surrogate itself: the oracle loop hovers (CoM stays within 5 cm over 40 ticks)."""
+    """Sanity of the surrogate itself: in flight (alphaGravity = 1) from the hover thrust, the oracle loop keeps the CoM
+    within 8 cm and the attitude within 80 mrad over 120 ticks while it trims the asymmetric jet torques."""
     from oracle.plant_surrogate import SurrogateLoop
-    rb, st, ms, isc, dT = make_case(1, seed=3)
-    loop = SurrogateLoop(oracle_plant(rb, st, 0, 1.0, 1.0, np.zeros(4)), trajectories=load_trajectories())
+    syn = pkg("synthetic")
+    rb = syn.SyntheticRobot()
+    st = syn.make_states(1, perturbed=False)
+    st["thrust"][:] = rb.mass * 9.81 / 4.0
+    st["thrust_des"][:] = rb.mass * 9.81 / 4.0
+    st["throttle_prev"][:] = 76.0
+    traj = load_trajectories()
+    traj["TRAJECTORY_MANAGER"]["arrays"]["alphaGravity"] = np.ones_like(traj["TRAJECTORY_MANAGER"]["arrays"]["alphaGravity"])
+    loop = SurrogateLoop(oracle_plant(rb, st, 0, 1.0, 1.0, np.zeros(4)), trajectories=traj)
     p0 = loop.plant.s["p_com"].copy()
-    for _ in range(40):
+    worst_p = worst_a = 0.0
+    for _ in range(120):
         r = loop.tick()
-    assert np.all(np.isfinite(r)) and np.abs(r[:3] - p0).max() < 0.05
+        worst_p, worst_a = max(worst_p, np.abs(r[:3] - p0).max()), max(worst_a, np.abs(r[3:6]).max())
+    assert np.all(np.isfinite(r)) and worst_p < 0.08 and worst_a < 0.08, (worst_p, worst_a)
 
 
 @pytest.mark.gpu
