@@ -319,13 +319,18 @@ def closed_loop_leg(bat, B, device, stream, n_ticks, solver):
     syn, ro = pkg("synthetic"), pkg("rollout")
     rb = syn.SyntheticRobot()
     g = np.random.default_rng(20251002)
-    st = syn.make_states(B, seed=20251002, perturbed=True, near_bound_fraction=0.1)
+    st = syn.make_states(B, seed=20251002, perturbed=True, near_bound_fraction=0.0)
     st["thrust"] = np.full((B, 4), rb.mass * 9.81 / 4.0) + g.normal(0, 8.0, (B, 4))
     st["thrust_des"] = st["thrust"].copy()
-    mpc = bat.BatchedVSMPC(B, None, load_traj(), device=device, solver=solver)
+    st["throttle_prev"] = np.full((B, 4), 76.0) + g.normal(0, 3.0, (B, 4))
+    st["momentum_body"] *= 0.2
+    st["q_cmd"] = np.tile(rb.joint_pos0, (B, 1))
+    trj = dict(load_traj())
+    trj["alphaGravity"] = np.ones_like(trj["alphaGravity"])     # in flight: the surrogate has no ground contact
+    mpc = bat.BatchedVSMPC(B, None, trj, device=device, solver=solver)
     mpc.set_stream(stream.cuda_stream)
     loop = ro.BatchedRollout(mpc, rb)
-    loop.init(st, thrust_disturbance=g.normal(0, 10.0, (B, 4)))
+    loop.init(st, thrust_disturbance=g.normal(0, 10.0, (B, 4)), phase0=(np.arange(B) % 20).astype(np.int32))
     loop.run(5)                                     # warm-up + graph capture
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -340,7 +345,8 @@ def closed_loop_leg(bat, B, device, stream, n_ticks, solver):
             "ms_per_tick": ms / n_ticks, "kernels_per_tick": 3, "cuda_graph": True,
             "solved_fraction_last_tick": float((status == 0).mean()),
             "max_abs_com_drift_m": float(np.abs(ps[0:3].T - st["p_com"]).max()),
-            "what": "surrogate plant (5 x 1 ms) + linearise + QP per tick, all device-resident"}
+            "what": "in-flight closed loops (alphaGravity = 1, perturbed states, constant thrust disturbances): surrogate "
+                    "plant (5 x 1 ms) + linearise + QP per tick, all device-resident"}
 
 
 def single_solve_latency(bat, L, device, stream, n_ticks=400):
