@@ -109,9 +109,8 @@ __device__ void locked_inertia(const double* __restrict__ pack, int B, int i, co
 }
 
 // W(rpy): costsVSMPC.cpp:276-282
-__device__ __forceinline__ void W_of_rpy(const double* rpy, double* W)
+__device__ __forceinline__ void W_of_rpy(double s0, double c0, double s1, double c1, double* W)
 {
-    const double s0 = sin(rpy[0]), c0 = cos(rpy[0]), s1 = sin(rpy[1]), c1 = cos(rpy[1]);
     W[0] = 1.0; W[1] = 0.0; W[2] = -s1;
     W[3] = 0.0; W[4] = c0; W[5] = c1 * s0;
     W[6] = 0.0; W[7] = -s0; W[8] = c0 * c1;
@@ -259,7 +258,17 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
     const double mass = pk[VSMPC_PK_MASS];
     double I3[9], W[9];
     locked_inertia_sm(pk, R, I3);
-    W_of_rpy(rpy, W);
+    // one sincos for the whole warp (lanes 0,1: roll; lanes 2,3: pitch), shared by W(rpy) and W^-1(rpy) below
+    double s0, c0, s1, c1;
+    {
+        double sv, cv;
+        sincos((lane & 3) < 2 ? rpy[0] : rpy[1], &sv, &cv);
+        s0 = __shfl_sync(0xffffffffu, sv, 0);
+        c0 = __shfl_sync(0xffffffffu, cv, 0);
+        s1 = __shfl_sync(0xffffffffu, sv, 2);
+        c1 = __shfl_sync(0xffffffffu, cv, 2);
+    }
+    W_of_rpy(s0, c0, s1, c1, W);
 
     // new reference-window column at trajectory index idx (costsVSMPC.cpp:105-112,132-149) -> colbuf
     auto ref_column = [&](int idx, const double* pinit, const double* rinit) {
@@ -407,16 +416,7 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
     if (lane < NJ) // JointPositionRegularizationCost gradient, costsVSMPC.cpp:574-590
         out[QD_GQ + lane] = cfg.w_reg_q * (pk[VSMPC_PK_Q_CMD + lane] - STR(ST_QREF0 + lane));
     // ---------------- dynamics ---------------------------------------------------------------------------
-    // one sincos for the whole warp (lanes 0,1: roll; lanes 2,3: pitch) instead of four serial calls on lane 0
-    double s0, c0, t1, c1;
-    {
-        double sv, cv;
-        sincos((lane & 3) < 2 ? rpy[0] : rpy[1], &sv, &cv);
-        s0 = __shfl_sync(0xffffffffu, sv, 0);
-        c0 = __shfl_sync(0xffffffffu, cv, 0);
-        t1 = __shfl_sync(0xffffffffu, sv / cv, 2);
-        c1 = __shfl_sync(0xffffffffu, cv, 2);
-    }
+    const double t1 = s1 / c1;
     if (lane == 0)
     {
         double omw[3], omB[3];
