@@ -56,6 +56,24 @@ def test_config_struct_layout_matches_c():
     assert L.VsmpcConfig.jet_coeff.offset == off_jet
 
 
+def test_plant_model_struct_layout_matches_c():
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "vsmpc.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(vsmpc_plant_model), offsetof(vsmpc_plant_model, q0), offsetof(vsmpc_plant_model, n_sub));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        sz, off_q0, off_nsub = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    L = pkg("_lib")
+    assert C.sizeof(L.VsmpcPlantModel) == sz
+    assert L.VsmpcPlantModel.q0.offset == off_q0 and L.VsmpcPlantModel.n_sub.offset == off_nsub
+    # row offsets of the plant state / parameter / instance-parameter tables
+    for name, val in (("PS_P_COM", L.PS_P_COM), ("PS_Q_CMD", L.PS_Q_CMD), ("PLANT_STATE_DOUBLES", L.PLANT_STATE_DOUBLES),
+                      ("PP_THRUST_DISTURBANCE", L.PP_THRUST_DISTURBANCE), ("PLANT_PARAM_DOUBLES", L.PLANT_PARAM_DOUBLES),
+                      ("IP_THROTTLE_MAX", L.IP_THROTTLE_MAX), ("INSTANCE_PARAM_DOUBLES", L.INSTANCE_PARAM_DOUBLES),
+                      ("ROLLOUT_REC_DOUBLES", L.ROLLOUT_REC_DOUBLES)):
+        assert int(re.search(rf"#define\s+VSMPC_{name}\s+(\d+)", HEADER).group(1)) == val, name
+
+
 def test_create_argument_errors_without_gpu():
     bat, L, cfg = pkg("batched"), pkg("_lib"), pkg("config")
     traj = cfg.hover_trajectories()
