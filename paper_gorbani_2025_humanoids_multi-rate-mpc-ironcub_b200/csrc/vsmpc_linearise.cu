@@ -164,7 +164,7 @@ __device__ __forceinline__ void locked_inertia_sm(const double* __restrict__ pk,
 // with fully coalesced stores.
 // mode 0: update tick.  mode 1: configure (initialise persistent state, then run tick 0).
 __global__ void __launch_bounds__(32 * K1_WARPS)
-linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
+linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
                  const double* __restrict__ pack, const double* __restrict__ joint_pos_sel,
                  const int* __restrict__ phase0, double* __restrict__ st, int* __restrict__ si,
                  const double* __restrict__ alpha_traj, const double* __restrict__ traj_pos,
@@ -172,7 +172,7 @@ linearise_kernel(const DeviceConfig* __restrict__ cfgp, int B, int mode,
                  const double* __restrict__ traj_rpyd, double* __restrict__ qd, const double* __restrict__ ip)
 {
     extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12] | ipar[20] | stc[st_rows] | sic[4]
-    const DeviceConfig& cfg = *cfgp;
+    const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank): no global round trip for the configuration
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * K1_WARPS + warp;
     if (i >= B)
@@ -724,7 +724,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
             return e;
     }
     const int grid = (B + K1_WARPS - 1) / K1_WARPS;
-    linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(d_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
+    linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(h_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
                                                        alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip);
     return cudaGetLastError();
 }

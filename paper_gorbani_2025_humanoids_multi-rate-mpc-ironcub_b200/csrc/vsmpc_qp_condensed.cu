@@ -701,13 +701,13 @@ __device__ __forceinline__ void cd_schedule(int t, int N, int kS, int& ta, int& 
 }
 
 __global__ void __launch_bounds__(CD_THREADS, 8)
-qp_condensed_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __restrict__ qd_all,
+qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                     double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
                     double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
                     int* __restrict__ n_solve, size_t ws_stride, int want_z)
 {
     __shared__ CdSmem sm;
-    const DeviceConfig& cfg = *cfgp;
+    const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int inst = blockIdx.x;
     const double* qd = qd_all + (size_t)inst * cfg.qd_stride;
@@ -1309,7 +1309,7 @@ cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
                                 int* n_solve, int want_z, cudaStream_t s)
 {
-    qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(d_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve,
+    qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve,
                                                  condensed_ws_doubles(h_cfg), want_z);
     return cudaGetLastError();
 }
