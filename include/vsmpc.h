@@ -206,7 +206,9 @@ int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_coun
 #define VSMPC_PS_THRUST_DES      24   /* 4  QPInput::setThrustDesMPC                                     */
 #define VSMPC_PS_THRUST_DOT_DES  28   /* 4  QPInput::setThrustDotDesMPC                                  */
 #define VSMPC_PS_Q_CMD           32   /* 8  QPInput::setOutputQPJointsPosition (controlled joints)        */
-#define VSMPC_PLANT_STATE_DOUBLES 40
+#define VSMPC_PS_THRUST_NN       40   /* 4  thrust state of the neural jet plant (float32 values), jet-NN mode only      */
+#define VSMPC_PS_EKF_P           44   /* 16 per-jet 2x2 EKF covariance, row-major, jet-NN mode only                      */
+#define VSMPC_PLANT_STATE_DOUBLES 60
 #define VSMPC_PP_MASS             0   /* 1  total mass (float-rounded like Robot::m_totalMass)           */
 #define VSMPC_PP_INERTIA_BODY     1   /* 9  locked inertia about the CoM, body frame, row-major          */
 #define VSMPC_PP_THRUST_DISTURBANCE 10 /* 4 constant thrust disturbance added in the plant [N]            */
@@ -238,6 +240,19 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
  * With use_graph != 0 the three kernels of a tick are captured once in a CUDA graph and replayed. */
 int vsmpc_rollout_run(vsmpc_handle* h, int n_ticks, int record_every, double* rec_host, int use_graph);
 int vsmpc_rollout_get_state(vsmpc_handle* h, double* plant_state_host);
+/* Jet plant + estimator of the reference simulator instead of the second-order jet model: per 1 ms plant
+ * step and jet, the neural jet model (src/mujoco_lib/nn_jet_model.py:21-30,86-109 — an LSTM cell evaluated from a zero
+ * state, float32) advances its thrust state under the commanded throttle, and the per-jet EKF
+ * (src/mujoco_lib/jet_kalman_filter.py:56-65) fuses it with the second-order model; the EKF estimate is the thrust applied
+ * to the plant and reported to the MPC (ironcub_mujoco_simulator.py:129-133).  w_ih float[320][2], b_ih / b_hh float[320],
+ * fc_w float[80], fc_b float[1], norm = {thrust mean, thrust std, throttle mean, throttle std} of the checkpoint,
+ * ekf_R / ekf_Q double[4] (2x2 row-major).  Call before vsmpc_rollout_init; w_ih == NULL switches back. */
+int vsmpc_rollout_set_jet_nn(vsmpc_handle* h, const float* w_ih, const float* b_ih, const float* b_hh, const float* fc_w,
+                             const float* fc_b, const double* norm, const double* ekf_R, const double* ekf_Q);
+/* parity seam of the neural jet plant: one NeuralJetModel.get_state step (nn_jet_model.py:21-30) for n_groups x 4
+ * (thrust [N], throttle [percent]) pairs on the device; float[n_groups][4] each */
+int vsmpc_jet_nn_eval(vsmpc_handle* h, int n_groups, double dt, const float* T_host, const float* throttle_host,
+                      float* T_next_host, float* T_dot_host);
 /* the pack the plant built for the next tick (double[VSMPC_PACK_DOUBLES][B]) — parity tests */
 int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host);
 

@@ -37,7 +37,7 @@ def _S(v):
 
 class SurrogatePlant:
     def __init__(self, geometry: dict, mass: float, I_body, thrust_disturbance, state: dict, dt_sim=0.001, n_sub=5,
-                 jet_model=None):
+                 jet_model=None, jet_nn=None, ekf_R=None, ekf_Q=None):
         """geometry: com_from_base_body(3), jet_pos_body(4,3), jet_axes_body(4,3), J_rel_body(4,6,nJ),
         J_jet_lin_body(4,3,nJ), J_com_body(3,nJ), gravity(3), joint_pos0(nJ).  state: p_com, lin_mom_world, rpy,
         ang_mom_body, thrust, thrust_dot, throttle, thrust_des, thrust_dot_des, q_cmd(nJ)."""
@@ -50,6 +50,15 @@ class SurrogatePlant:
         self.dt, self.n_sub = dt_sim, n_sub
         self.jet = jet_model or JetModel()
         self.sel = list(range(3, 11))
+        # jet-NN mode: neural jet plant + per-jet EKF of the reference simulator
+        # (ironcub_mujoco_simulator.py:50-57,129-133)
+        self.jet_nn = jet_nn
+        if jet_nn is not None:
+            from .jet_nn_oracle import JetEKF
+            R = np.eye(2) * 0.5 if ekf_R is None else ekf_R
+            Q = np.eye(2) * 0.1 if ekf_Q is None else ekf_Q
+            self.ekf = [JetEKF(R, Q, np.eye(2) * 0.1, dt_sim, self.jet) for _ in range(4)]
+            self.T_nn = np.asarray(self.s["thrust"], np.float32).copy()
 
     def jet_frames_body(self):
         """Thrust axes / arms in the body frame at the current joint command (first-order kinematics)."""
@@ -69,12 +78,20 @@ class SurrogatePlant:
         aB, rB = self.jet_frames_body()
         for _ in range(self.n_sub):
             R = _R(s["rpy"])
-            for j in range(4):
-                Ts, Tds = jet.standardizeThrust_u2T(s["thrust"][j]), jet.standardizeThrustDot_u2T(s["thrust_dot"][j])
-                v = jet.compute_v(jet.standardizeThrottle_u2T(s["throttle"][j]))
-                tdd = jet.compute_f(Ts, Tds) + jet.compute_g(Ts, Tds) * v
-                s["thrust_dot"][j] += tdd * sig * self.dt
-                s["thrust"][j] += s["thrust_dot"][j] * self.dt
+            if self.jet_nn is not None:
+                from .jet_nn_oracle import nn_jet_step
+                u32 = np.asarray(s["throttle"], np.float32)          # the simulator keeps the throttle in float32
+                self.T_nn, Tdn = nn_jet_step(self.T_nn, u32, self.jet_nn, self.dt)
+                for j in range(4):
+                    x = self.ekf[j].update([s["thrust"][j], s["thrust_dot"][j]], float(u32[j]), [float(self.T_nn[j]), float(Tdn[j])])
+                    s["thrust"][j], s["thrust_dot"][j] = x[0], x[1]
+            else:
+                for j in range(4):
+                    Ts, Tds = jet.standardizeThrust_u2T(s["thrust"][j]), jet.standardizeThrustDot_u2T(s["thrust_dot"][j])
+                    v = jet.compute_v(jet.standardizeThrottle_u2T(s["throttle"][j]))
+                    tdd = jet.compute_f(Ts, Tds) + jet.compute_g(Ts, Tds) * v
+                    s["thrust_dot"][j] += tdd * sig * self.dt
+                    s["thrust"][j] += s["thrust_dot"][j] * self.dt
             Tt = s["thrust"] + self.dT
             fB = Tt @ aB
             tauB = Tt @ np.cross(rB, aB)

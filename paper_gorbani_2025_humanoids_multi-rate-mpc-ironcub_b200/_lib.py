@@ -44,7 +44,8 @@ class VsmpcConfig(C.Structure):
 
 INSTANCE_PARAM_DOUBLES = 19
 IP_JET_COEFF, IP_JET_NORM, IP_THROTTLE_MIN, IP_THROTTLE_MAX = 0, 13, 17, 18
-PLANT_STATE_DOUBLES, PLANT_PARAM_DOUBLES, ROLLOUT_REC_DOUBLES = 40, 14, 16
+PLANT_STATE_DOUBLES, PLANT_PARAM_DOUBLES, ROLLOUT_REC_DOUBLES = 60, 14, 16
+PS_THRUST_NN, PS_EKF_P = 40, 44
 PS_P_COM, PS_LIN_MOM_WORLD, PS_RPY, PS_ANG_MOM_BODY, PS_THRUST, PS_THRUST_DOT = 0, 3, 6, 9, 12, 16
 PS_THROTTLE, PS_THRUST_DES, PS_THRUST_DOT_DES, PS_Q_CMD = 20, 24, 28, 32
 PP_MASS, PP_INERTIA_BODY, PP_THRUST_DISTURBANCE = 0, 1, 10
@@ -65,7 +66,7 @@ EXPORTS = [
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
     "vsmpc_get_output_device", "vsmpc_get_output_async", "vsmpc_wait_output", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
     "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64",
-    "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_get_pack",
+    "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
 ]
 
 _lib = None
@@ -109,6 +110,8 @@ def load() -> C.CDLL:
     lib.vsmpc_rollout_init.argtypes = [H, C.POINTER(VsmpcPlantModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_rollout_run.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.vsmpc_rollout_get_state.argtypes = [H, C.c_void_p]
+    lib.vsmpc_rollout_set_jet_nn.argtypes = [H] + [C.c_void_p] * 8
+    lib.vsmpc_jet_nn_eval.argtypes = [H, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_rollout_get_pack.argtypes = [H, C.c_void_p]
     for f in EXPORTS:
         if f != "vsmpc_last_error":

@@ -15,7 +15,11 @@ namespace vsmpc
 {
 cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
                          const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
-                         const double* ip, const double* st, cudaStream_t s);
+                         const double* ip, const double* st, const double* thr_sub, cudaStream_t s);
+cudaError_t launch_jet_nn_eval(const JetNN* d_nn, int n_groups, float dt, const float* T_in, const float* u_in, float* T_out,
+                               float* Td_out, cudaStream_t s);
+cudaError_t launch_jet_nn_ekf(const DeviceConfig* d_cfg, const PlantModel* d_pm, const JetNN* d_nn, int B, double* ps,
+                              const double* out_rows, const double* ip, double* thr_sub, cudaStream_t s);
 cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
@@ -86,6 +90,9 @@ struct vsmpc_handle
     PlantModel* d_pm = nullptr;
     double* d_ps = nullptr;
     double* d_pp = nullptr;
+    JetNN* d_nn = nullptr;    // neural jet plant + EKF constants (jet-NN mode of the rollout)
+    double* d_thr_sub = nullptr;
+    bool use_nn = false;
     double* d_ip = nullptr;   // per-instance jet model / throttle limits (optional)
     bool use_ip = false;
     bool rollout_ready = false;
@@ -322,7 +329,7 @@ int vsmpc_destroy(vsmpc_handle* h)
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
                     h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
-                    h->d_pack_in[0], h->d_pack_in[1]};
+                    h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
         if (h->ev_h2d[q]) cudaEventDestroy(h->ev_h2d[q]);
@@ -680,8 +687,8 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
 {
     if (!h || h->B <= 0 || !model || !plant_state_host || !plant_param_host || !joint_pos_sel_host)
         return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_init: null argument");
-    if (!(model->dt_sim > 0) || model->n_sub < 1)
-        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_init: dt_sim must be positive and n_sub >= 1");
+    if (!(model->dt_sim > 0) || model->n_sub < 1 || model->n_sub > MAX_SUB)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_init: dt_sim must be positive and 1 <= n_sub <= 16");
     CK(cudaSetDevice(h->device));
     const size_t B = h->B;
     if (!h->d_pm)
@@ -710,7 +717,7 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
         CK(cudaMemsetAsync(h->d_phase, 0, B * 4, h->stream));
     // first pack from the plant state, then IMPCProblem::configure on it (tick 0 of every counter)
     CK(launch_plant(h->d_cfg, h->d_pm, h->B, 0, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, nullptr,
-                    h->use_ip ? h->d_ip : nullptr, nullptr, h->stream));
+                    h->use_ip ? h->d_ip : nullptr, nullptr, nullptr, h->stream));
     int rc = run_linearise(h, 1);
     if (rc)
         return rc;
@@ -729,8 +736,11 @@ static int tick_launch(vsmpc_handle* h, double* rec)
     rc = solve_launch(h);
     if (rc)
         return rc;
+    if (h->use_nn)
+        CK(launch_jet_nn_ekf(h->d_cfg, h->d_pm, h->d_nn, h->B, h->d_ps, h->d_out, h->use_ip ? h->d_ip : nullptr, h->d_thr_sub,
+                             h->stream));
     CK(launch_plant(h->d_cfg, h->d_pm, h->B, 1, h->d_ps, h->d_pp, h->d_out, h->d_status, h->d_pack, rec,
-                    h->use_ip ? h->d_ip : nullptr, h->d_st, h->stream));
+                    h->use_ip ? h->d_ip : nullptr, h->d_st, h->use_nn ? h->d_thr_sub : nullptr, h->stream));
     return VSMPC_OK;
 }
 
@@ -802,6 +812,69 @@ int vsmpc_rollout_run(vsmpc_handle* h, int n_ticks, int record_every, double* re
     if (e3 != cudaSuccess)
         return cuda_fail(h, e3, "vsmpc_rollout_run");
     h->has_state = false;
+    return VSMPC_OK;
+}
+
+int vsmpc_rollout_set_jet_nn(vsmpc_handle* h, const float* w_ih, const float* b_ih, const float* b_hh, const float* fc_w,
+                             const float* fc_b, const double* norm, const double* ekf_R, const double* ekf_Q)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->tick_graph)
+    {
+        cudaGraphExecDestroy(h->tick_graph);
+        h->tick_graph = nullptr;
+    }
+    if (!w_ih)
+    {
+        h->use_nn = false;
+        return VSMPC_OK;
+    }
+    if (!b_ih || !b_hh || !fc_w || !fc_b || !norm || !ekf_R || !ekf_Q)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_set_jet_nn: null argument");
+    if (!(norm[1] > 0.0) || !(norm[3] > 0.0))
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_rollout_set_jet_nn: normalisation standard deviations must be positive");
+    JetNN nn;
+    std::memcpy(nn.w_ih, w_ih, sizeof(nn.w_ih));
+    for (int e = 0; e < 4 * NN_HID; ++e)
+        nn.b[e] = b_ih[e] + b_hh[e];
+    std::memcpy(nn.fc_w, fc_w, sizeof(nn.fc_w));
+    nn.fc_b = fc_b[0];
+    nn.pad = 0.f;
+    std::memcpy(nn.norm, norm, sizeof(nn.norm));
+    std::memcpy(nn.R, ekf_R, sizeof(nn.R));
+    std::memcpy(nn.Q, ekf_Q, sizeof(nn.Q));
+    if (!h->d_nn)
+    {
+        CK(dalloc(&h->d_nn, 1));
+        CK(dalloc(&h->d_thr_sub, (size_t)2 * MAX_SUB * NT * h->B));
+    }
+    CK(cudaMemcpy(h->d_nn, &nn, sizeof(nn), cudaMemcpyHostToDevice));
+    h->use_nn = true;
+    return VSMPC_OK;
+}
+
+int vsmpc_jet_nn_eval(vsmpc_handle* h, int n_groups, double dt, const float* T_host, const float* throttle_host, float* T_next_host,
+                      float* T_dot_host)
+{
+    if (!h || h->B <= 0 || n_groups <= 0 || !T_host || !throttle_host || !T_next_host || !T_dot_host)
+        return VSMPC_ERR_ARG;
+    if (!h->use_nn)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_jet_nn_eval: call vsmpc_rollout_set_jet_nn first");
+    CK(cudaSetDevice(h->device));
+    float* d = nullptr;
+    const size_t n = (size_t)n_groups * NT;
+    CK(dalloc(&d, 4 * n));
+    cudaError_t e = cudaMemcpyAsync(d, T_host, n * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, throttle_host, n * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = launch_jet_nn_eval(h->d_nn, n_groups, (float)dt, d, d + n, d + 2 * n, d + 3 * n, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(T_next_host, d + 2 * n, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(T_dot_host, d + 3 * n, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return cuda_fail(h, e, "vsmpc_jet_nn_eval");
     return VSMPC_OK;
 }
 

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128)
 plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict__ pmp, int B, int mode,
              double* __restrict__ ps, const double* __restrict__ pp, const double* __restrict__ out_rows,
              const int* __restrict__ status, double* __restrict__ pack, double* __restrict__ rec,
-             const double* __restrict__ ip, const double* __restrict__ st)
+             const double* __restrict__ ip, const double* __restrict__ st, const double* __restrict__ thr_sub)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B)
@@ -174,14 +174,25 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
         {
             double R[9];
             rpy_to_R(rpy, R);
-            // jets (jet_kalman_filter.py:30-45)
+            if (thr_sub)
+            { // jet-NN mode: the EKF estimate of this plant step (jet_nn_ekf_kernel) is the applied thrust
 #pragma unroll
-            for (int j = 0; j < NT; ++j)
-            {
-                const double Ts = jet.stdT(T[j]), Tds = jet.stdTd(Td[j]);
-                const double tdd = jet.f(Ts, Tds) + jet.g(Ts, Tds) * jet.v(jet.stdU(u[j]));
-                Td[j] += tdd * jpar[IP_JN + 1] * dt;
-                T[j] += Td[j] * dt;
+                for (int j = 0; j < NT; ++j)
+                {
+                    T[j] = thr_sub[((size_t)(2 * sstep) * NT + j) * B + i];
+                    Td[j] = thr_sub[((size_t)(2 * sstep + 1) * NT + j) * B + i];
+                }
+            }
+            else
+            { // jets (jet_kalman_filter.py:30-45)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+                {
+                    const double Ts = jet.stdT(T[j]), Tds = jet.stdTd(Td[j]);
+                    const double tdd = jet.f(Ts, Tds) + jet.g(Ts, Tds) * jet.v(jet.stdU(u[j]));
+                    Td[j] += tdd * jpar[IP_JN + 1] * dt;
+                    T[j] += Td[j] * dt;
+                }
             }
             // momentum
             double fB[3] = {0, 0, 0}, tauB[3] = {0, 0, 0};
@@ -365,12 +376,186 @@ plant_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict
 #undef PK
 }
 
+// NeuralJetModel.get_state for four (thrust, normalised throttle) pairs by one warp (nn_jet_model.py:21-30,86-109): the
+// LSTM cell from a zero state in float32 — hidden units over the lanes, the fc dot product by warp reduction.
+// T is advanced in place; Td receives the thrust rate.
+__device__ __forceinline__ void nn_jet_step4(const JetNN& nn, float (&T)[NT], const float (&un)[NT], float dtf, int lane,
+                                             float (&Td)[NT])
+{
+    const float stdT = (float)nn.norm[1], meanT = (float)nn.norm[0];
+    float part[NT] = {0.f, 0.f, 0.f, 0.f};
+    float Tn[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+        Tn[j] = (float)(((double)T[j] - nn.norm[0]) / nn.norm[1]);
+    for (int hh = lane; hh < NN_HID; hh += 32)
+    {
+        const float wi0 = nn.w_ih[hh * 2], wi1 = nn.w_ih[hh * 2 + 1], bi = nn.b[hh];
+        const float wg0 = nn.w_ih[(2 * NN_HID + hh) * 2], wg1 = nn.w_ih[(2 * NN_HID + hh) * 2 + 1], bg = nn.b[2 * NN_HID + hh];
+        const float wo0 = nn.w_ih[(3 * NN_HID + hh) * 2], wo1 = nn.w_ih[(3 * NN_HID + hh) * 2 + 1], bo = nn.b[3 * NN_HID + hh];
+        const float fw = nn.fc_w[hh];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+        {
+            const float gi = 1.f / (1.f + expf(-(wi0 * Tn[j] + wi1 * un[j] + bi)));
+            const float gg = tanhf(wg0 * Tn[j] + wg1 * un[j] + bg);
+            const float go = 1.f / (1.f + expf(-(wo0 * Tn[j] + wo1 * un[j] + bo)));
+            part[j] = fmaf(fw, go * tanhf(gi * gg), part[j]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+            part[j] += __shfl_xor_sync(0xffffffffu, part[j], o);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        const float td = part[j] + nn.fc_b;
+        T[j] = (Tn[j] + td * dtf) * stdT + meanT;
+        Td[j] = td * stdT;
+    }
+}
+
+// parity seam: one network step for n groups of four (thrust, throttle) pairs, one warp per group
+__global__ void __launch_bounds__(128)
+jet_nn_eval_kernel(const JetNN* __restrict__ nnp, int n_groups, float dt, const float* __restrict__ T_in,
+                   const float* __restrict__ u_in, float* __restrict__ T_out, float* __restrict__ Td_out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gidx = blockIdx.x * 4 + warp;
+    if (gidx >= n_groups)
+        return;
+    const JetNN& nn = *nnp;
+    float T[NT], un[NT], Td[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        T[j] = T_in[gidx * NT + j];
+        un[j] = (float)(((double)u_in[gidx * NT + j] - nn.norm[2]) / nn.norm[3]);
+    }
+    nn_jet_step4(nn, T, un, dt, lane, Td);
+    if (lane < NT)
+    {
+        T_out[gidx * NT + lane] = lane == 0 ? T[0] : lane == 1 ? T[1] : lane == 2 ? T[2] : T[3];
+        Td_out[gidx * NT + lane] = lane == 0 ? Td[0] : lane == 1 ? Td[1] : lane == 2 ? Td[2] : Td[3];
+    }
+}
+
+cudaError_t launch_jet_nn_eval(const JetNN* d_nn, int n_groups, float dt, const float* T_in, const float* u_in, float* T_out,
+                               float* Td_out, cudaStream_t s)
+{
+    jet_nn_eval_kernel<<<(n_groups + 3) / 4, 128, 0, s>>>(d_nn, n_groups, dt, T_in, u_in, T_out, Td_out);
+    return cudaGetLastError();
+}
+
+// ---- neural jet plant + per-jet EKF, one warp per instance (jet-NN mode of the rollout) ----------------------------------
+// Per plant step: (1) NeuralJetModel.get_state for the four jets (nn_jet_model.py:21-30,86-109): the LSTM cell from a zero
+// state, float32 — hidden units over the lanes, the fc dot product by warp reduction; (2) SecondOrderJetModel.update per jet
+// (jet_kalman_filter.py:56-65) on lanes 0..3, float64; the estimate of every plant step goes to thr_sub for plant_kernel.
+__global__ void __launch_bounds__(128)
+jet_nn_ekf_kernel(const DeviceConfig* __restrict__ cfgp, const PlantModel* __restrict__ pmp, const JetNN* __restrict__ nnp,
+                  int B, double* __restrict__ ps, const double* __restrict__ out_rows, const double* __restrict__ ip,
+                  double* __restrict__ thr_sub)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + warp;
+    if (i >= B)
+        return;
+    const DeviceConfig& cfg = *cfgp;
+    const PlantModel& pm = *pmp;
+    const JetNN& nn = *nnp;
+#define PS(r) ps[(size_t)(r) * B + i]
+    double jpar[IP_TMIN];
+#pragma unroll
+    for (int a = 0; a < IP_TMIN; ++a)
+        jpar[a] = ip ? ip[(size_t)a * B + i] : (a < IP_JN ? cfg.jc[a] : cfg.jn[a - IP_JN]);
+    const Jet jet{jpar + IP_JC, jpar + IP_JN};
+    // this tick's throttle command (the feedback plant_kernel applies right after this kernel)
+    float un[NT], Tnn[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        // the simulator keeps the throttle as a float32 tensor (ironcub_mujoco_simulator.py:190)
+        const double uj = (double)(float)out_rows[(size_t)i * VSMPC_OUT_DOUBLES + VSMPC_OUT_THROTTLE + j];
+        un[j] = (float)((uj - nn.norm[2]) / nn.norm[3]);
+        Tnn[j] = (float)PS(PS_TNN + j);
+    }
+    // EKF state of jet `lane` (lanes 0..3)
+    const int jl = lane & 3;
+    double xe0 = PS(PS_T + jl), xe1 = PS(PS_TD + jl);
+    double P00 = PS(PS_EKFP + 4 * jl), P01 = PS(PS_EKFP + 4 * jl + 1), P10 = PS(PS_EKFP + 4 * jl + 2), P11 = PS(PS_EKFP + 4 * jl + 3);
+    const double ue = (double)(float)out_rows[(size_t)i * VSMPC_OUT_DOUBLES + VSMPC_OUT_THROTTLE + jl];
+    const double dt = pm.dt_sim;
+    const float dtf = (float)dt;
+    for (int sstep = 0; sstep < pm.n_sub; ++sstep)
+    {
+        // ---- neural jet plant ----
+        float Tdn[NT];
+        nn_jet_step4(nn, Tnn, un, dtf, lane, Tdn);
+        // ---- EKF of jet `lane` (lanes >= 4 compute a copy that is never stored) ----
+        const double z0 = (double)(jl == 0 ? Tnn[0] : jl == 1 ? Tnn[1] : jl == 2 ? Tnn[2] : Tnn[3]);
+        const double z1 = (double)(jl == 0 ? Tdn[0] : jl == 1 ? Tdn[1] : jl == 2 ? Tdn[2] : Tdn[3]);
+        {
+            const double v = jet.v(jet.stdU(ue));
+            double Ts = jet.stdT(xe0), Tds = jet.stdTd(xe1);
+            const double tdd = jet.f(Ts, Tds) + jet.g(Ts, Tds) * v;
+            xe1 += tdd * jpar[IP_JN + 1] * dt;          // predict (jet_kalman_filter.py:30-45)
+            xe0 += xe1 * dt;
+            Ts = jet.stdT(xe0);                          // Jacobian at the predicted state (:58)
+            Tds = jet.stdTd(xe1);
+            const double hT = jet.df_dT(Ts, Tds) + jet.dg_dT(Ts, Tds) * v, hTd = jet.df_dTd(Ts, Tds) + jet.dg_dTd(Ts, Tds) * v;
+            const double a10 = dt * hT, a11 = 1.0 + dt * hTd, a00 = 1.0 + dt * a10, a01 = dt * a11;
+            // P <- A P A' + Q
+            const double t00 = a00 * P00 + a01 * P10, t01 = a00 * P01 + a01 * P11, t10 = a10 * P00 + a11 * P10, t11 = a10 * P01 + a11 * P11;
+            P00 = t00 * a00 + t01 * a01 + nn.Q[0];
+            P01 = t00 * a10 + t01 * a11 + nn.Q[1];
+            P10 = t10 * a00 + t11 * a01 + nn.Q[2];
+            P11 = t10 * a10 + t11 * a11 + nn.Q[3];
+            // K = P (P + R)^-1 ; x += K (z - x) ; P <- (I - K) P
+            const double s00 = P00 + nn.R[0], s01 = P01 + nn.R[1], s10 = P10 + nn.R[2], s11 = P11 + nn.R[3];
+            const double idet = 1.0 / (s00 * s11 - s01 * s10);
+            const double i00 = s11 * idet, i01 = -s01 * idet, i10 = -s10 * idet, i11 = s00 * idet;
+            const double k00 = P00 * i00 + P01 * i10, k01 = P00 * i01 + P01 * i11, k10 = P10 * i00 + P11 * i10, k11 = P10 * i01 + P11 * i11;
+            const double e0 = z0 - xe0, e1 = z1 - xe1;
+            xe0 += k00 * e0 + k01 * e1;
+            xe1 += k10 * e0 + k11 * e1;
+            const double n00 = (1.0 - k00) * P00 - k01 * P10, n01 = (1.0 - k00) * P01 - k01 * P11;
+            const double n10 = -k10 * P00 + (1.0 - k11) * P10, n11 = -k10 * P01 + (1.0 - k11) * P11;
+            P00 = n00; P01 = n01; P10 = n10; P11 = n11;
+        }
+        if (lane < NT)
+        {
+            thr_sub[((size_t)(2 * sstep) * NT + lane) * B + i] = xe0;
+            thr_sub[((size_t)(2 * sstep + 1) * NT + lane) * B + i] = xe1;
+        }
+    }
+    if (lane < NT)
+    {
+        PS(PS_TNN + lane) = (double)(lane == 0 ? Tnn[0] : lane == 1 ? Tnn[1] : lane == 2 ? Tnn[2] : Tnn[3]);
+        PS(PS_EKFP + 4 * lane) = P00;
+        PS(PS_EKFP + 4 * lane + 1) = P01;
+        PS(PS_EKFP + 4 * lane + 2) = P10;
+        PS(PS_EKFP + 4 * lane + 3) = P11;
+    }
+#undef PS
+}
+
+cudaError_t launch_jet_nn_ekf(const DeviceConfig* d_cfg, const PlantModel* d_pm, const JetNN* d_nn, int B, double* ps,
+                              const double* out_rows, const double* ip, double* thr_sub, cudaStream_t s)
+{
+    jet_nn_ekf_kernel<<<(B + 3) / 4, 128, 0, s>>>(d_cfg, d_pm, d_nn, B, ps, out_rows, ip, thr_sub);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_plant(const DeviceConfig* d_cfg, const PlantModel* d_pm, int B, int mode, double* ps,
                          const double* pp, const double* out_rows, const int* status, double* pack, double* rec,
-                         const double* ip, const double* st, cudaStream_t s)
+                         const double* ip, const double* st, const double* thr_sub, cudaStream_t s)
 {
     const int threads = 128;
-    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec, ip, st);
+    plant_kernel<<<(B + threads - 1) / threads, threads, 0, s>>>(d_cfg, d_pm, B, mode, ps, pp, out_rows, status, pack, rec, ip, st, thr_sub);
     return cudaGetLastError();
 }
 

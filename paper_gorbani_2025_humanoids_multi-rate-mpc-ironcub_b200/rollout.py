@@ -48,6 +48,10 @@ def plant_state_from_states(state: dict, sel=None) -> np.ndarray:
     ps[L.PS_THRUST_DES:L.PS_THRUST_DES + 4] = state["thrust_des"].T
     ps[L.PS_THRUST_DOT_DES:L.PS_THRUST_DOT_DES + 4] = state["thrust_dot_des"].T
     ps[L.PS_Q_CMD:L.PS_Q_CMD + 8] = state["q_cmd"][:, sel].T
+    # jet-NN mode: the network's thrust state starts at the measured thrust, the EKF covariance at 0.1 I
+    # (ironcub_mujoco_simulator.py:53-57)
+    ps[L.PS_THRUST_NN:L.PS_THRUST_NN + 4] = state["thrust"].T.astype(np.float32)
+    ps[L.PS_EKF_P:L.PS_EKF_P + 16] = np.tile(np.array([0.1, 0.0, 0.0, 0.1]), 4)[:, None]
     return ps
 
 
@@ -81,6 +85,31 @@ class BatchedRollout:
         self.mpc._ck(self._lib.vsmpc_rollout_init(self.mpc._h, C.byref(self.model), ps.ctypes.data, pp.ctypes.data,
                                                   jp.ctypes.data, ph.ctypes.data if ph is not None else None),
                      "vsmpc_rollout_init")
+
+    def set_jet_nn(self, weights: dict | None, ekf_R=None, ekf_Q=None):
+        """Jet plant + estimator of the reference simulator: ``weights`` = dict(w_ih (320,2), b_ih, b_hh (320,), fc_w (80,),
+        fc_b (1,), norm (4,)) — the numerical content of the reference's ``jet_model_torch/model_7.pth`` — or None to go
+        back to the second-order jet model.  Defaults of R, Q: ironcub_mujoco_simulator.py:54-56."""
+        if weights is None:
+            self.mpc._ck(self._lib.vsmpc_rollout_set_jet_nn(self.mpc._h, *([None] * 8)), "vsmpc_rollout_set_jet_nn")
+            return
+        f32 = lambda a, n: np.ascontiguousarray(np.asarray(a, np.float32).reshape(n))
+        w_ih, b_ih, b_hh = f32(weights["w_ih"], 640), f32(weights["b_ih"], 320), f32(weights["b_hh"], 320)
+        fc_w, fc_b = f32(weights["fc_w"], 80), f32(weights["fc_b"], 1)
+        norm = np.ascontiguousarray(np.asarray(weights["norm"], np.float64).reshape(4))
+        R = np.ascontiguousarray(np.asarray(np.eye(2) * 0.5 if ekf_R is None else ekf_R, np.float64).reshape(4))
+        Q = np.ascontiguousarray(np.asarray(np.eye(2) * 0.1 if ekf_Q is None else ekf_Q, np.float64).reshape(4))
+        self._keep = (w_ih, b_ih, b_hh, fc_w, fc_b, norm, R, Q)
+        self.mpc._ck(self._lib.vsmpc_rollout_set_jet_nn(self.mpc._h, *[a.ctypes.data for a in self._keep]),
+                     "vsmpc_rollout_set_jet_nn")
+
+    def jet_nn_eval(self, T, throttle, dt: float = 0.001):
+        """One step of the neural jet plant on the device for (n, 4) float32 thrusts / throttles (parity seam)."""
+        T = np.ascontiguousarray(T, dtype=np.float32); u = np.ascontiguousarray(throttle, dtype=np.float32)
+        To, Td = np.empty_like(T), np.empty_like(T)
+        self.mpc._ck(self._lib.vsmpc_jet_nn_eval(self.mpc._h, T.shape[0], float(dt), T.ctypes.data, u.ctypes.data,
+                                                 To.ctypes.data, Td.ctypes.data), "vsmpc_jet_nn_eval")
+        return To, Td
 
     def run(self, n_ticks: int, record_every: int = 0, use_graph: bool = True):
         """n_ticks controller ticks; returns the record array (n_rec, B, 16) or None."""
