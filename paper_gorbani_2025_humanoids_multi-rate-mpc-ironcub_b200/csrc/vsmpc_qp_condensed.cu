@@ -855,7 +855,14 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
 #ifdef VSMPC_PHASE_CLOCKS
     if (lane == 0 && inst < 4096)
     {
-        if (warp == 0) { g_phase_clk[inst][8] = clkA0; g_phase_clk[inst][9] = clkA1; }
+        if (warp == 0)
+        {
+            unsigned smid;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_phase_clk[inst][8] = clkA0;
+            g_phase_clk[inst][9] = clkA1;
+            g_phase_clk[inst][12] = smid;
+        }
         else { g_phase_clk[inst][10] = clkB0; g_phase_clk[inst][11] = clkB1; }
     }
 #endif

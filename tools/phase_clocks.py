@@ -38,3 +38,16 @@ for lo_, hi_ in ((0, 0), (1, 3), (4, 6), (7, 10), (11, 15), (16, 99)):
 
 print("warp A per launch: a_prop %.0f  a_eliminate %.0f ; warp B: b_prop %.0f  b_downdate %.0f (cycles summed over knots, mean over instances)" %
       (clk[:, 8].mean(), clk[:, 9].mean(), clk[:, 10].mean(), clk[:, 11].mean()))
+
+sm = clk[:, 12]
+loop = clk[:, 2] - clk[:, 1]
+per_sm = {}
+for s_, l_, tt in zip(sm, loop, clk[:, 3] - clk[:, 0]):
+    per_sm.setdefault(int(s_), []).append((l_, tt))
+cnt = np.array([len(v) for v in per_sm.values()])
+lm = np.array([np.mean([a for a, _ in v]) for v in per_sm.values()])
+tm = np.array([np.max([b for _, b in v]) for v in per_sm.values()])
+print("SMs used", len(per_sm), "instances per SM min/max", cnt.min(), cnt.max())
+for c in sorted(set(cnt)):
+    m = cnt == c
+    print(f"  SMs with {c} CTAs: {m.sum():3d}; mean loop {lm[m].mean():8.0f} (min {lm[m].min():.0f}, max {lm[m].max():.0f}); slowest instance total: mean {tm[m].mean():.0f}, max {tm[m].max():.0f}")
