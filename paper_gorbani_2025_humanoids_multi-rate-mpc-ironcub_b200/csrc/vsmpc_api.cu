@@ -44,9 +44,17 @@ size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
                                 int* n_solve, int want_z, cudaStream_t s);
+bool condensed_wide_supported(const DeviceConfig& cfg);
+size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
+size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
+cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
+                                     double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
+                                     int want_z, cudaStream_t s);
 } // namespace vsmpc
 
 using namespace vsmpc;
+
+constexpr int SOLVER_WIDE = 3;   // internal: chosen by the default solver for long horizons
 
 struct vsmpc_handle
 {
@@ -54,7 +62,7 @@ struct vsmpc_handle
     DeviceConfig* d_cfg = nullptr;
     int B = 0;
     int device = 0;
-    int solver = 0;
+    int solver = 0;           // 0 condensed, 1 generic, 2 structured, SOLVER_WIDE condensed with several column warps
     bool configured = false;
     bool has_state = false;
     bool want_full = false;   // write the full primal (IMPCProblem::getSolution) every solve
@@ -244,8 +252,8 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     if (c->solver < 0 || c->solver > 2)
         return bail(VSMPC_ERR_ARG, "solver must be 0 (default), 1 (generic) or 2 (structured)");
     h->solver = c->solver;
-    if (h->solver == 0 && !condensed_supported(g))
-        h->solver = 1;   // horizons beyond the condensed kernel's 6 throttle blocks / 32 knots: generic dense kernel
+    if (h->solver == 0 && !condensed_supported(g))   // horizons beyond 6 throttle blocks / 32 knots: the condensed kernel
+        h->solver = condensed_wide_supported(g) ? SOLVER_WIDE : 1;   // with several column warps, else the generic one
     if (h->solver == 1 && !generic_supported(g))
         return bail(VSMPC_ERR_UNSUPPORTED, "horizons with more than 48 throttle blocks are not supported");
     if (h->solver == 2 && (NT * g.nblk > 24 || g.N > 32))
@@ -254,7 +262,9 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess)
         return bail(VSMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-    const size_t scratch = h->solver == 1 ? generic_scratch_doubles(g) : (h->solver == 2 ? structured_scratch_doubles(g) : 4);
+    const size_t scratch = h->solver == 1 ? generic_scratch_doubles(g)
+                           : (h->solver == 2 ? structured_scratch_doubles(g)
+                                             : (h->solver == SOLVER_WIDE ? condensed_wide_scratch_doubles(g) : 4));
     bool ok = true;
     auto A = [&](cudaError_t r) { ok = ok && (r == cudaSuccess); if (r != cudaSuccess) e = r; };
     A(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -283,8 +293,10 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(dalloc(&h->d_qd, (size_t)g.qd_stride * B));
     {
         size_t wsd = (size_t)g.N * WS_STAGE;
-        if (condensed_ws_doubles(g) > wsd)
+        if (h->solver == 0 && condensed_ws_doubles(g) > wsd)
             wsd = condensed_ws_doubles(g);
+        if (h->solver == SOLVER_WIDE)
+            wsd = condensed_wide_ws_doubles(g);
         A(dalloc(&h->d_ws, wsd * B));
     }
     A(dalloc(&h->d_scratch, scratch * B));
@@ -673,6 +685,9 @@ static int solve_launch(vsmpc_handle* h)
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
                                h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+    else if (h->solver == SOLVER_WIDE)
+        CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
+                                    h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
     else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));

@@ -1,0 +1,506 @@
+// Shared device code of the condensed-throttle Riccati kernels (vsmpc_qp_condensed.cu: <= 6 throttle blocks, one column
+// warp; vsmpc_qp_condensed_wide.cu: long horizons, several column warps): the structured application of
+// T = I + dt A_c, warp A's P recursion (propagation, 8 x 8 elimination), the knot schedule of the software pipeline and
+// the forward rollout.  The shared-memory struct is a template parameter (fields cf, lam, Rqd, dtk, slot, Mt).
+#pragma once
+#include "vsmpc_common.cuh"
+
+namespace vsmpc
+{
+
+constexpr int LDM = NX + 1;   // 27, odd: conflict-free transposition
+constexpr int NPD = 13;       // published P'D columns: throttle block (4), affine (1), joint block (8)
+constexpr int CCF = 164;      // coefficient block copied from the QP data (QD_RM .. QD_JGT, padded)
+constexpr int WSC_K = 0;      // per elimination knot in the workspace: K [8][26] first
+
+struct alignas(16) CdSlot
+{
+    double Hux[NJ * NX];    // [m][j]
+    double Hinv[NJ * NJ];   // [a][m]
+    double PD[NX * NPD];    // [i][col]
+};
+
+enum : int { TK_NONE = 0, TK_STAGE = 1, TK_PROP = 2, TK_SCHUR = 3 };
+
+// y <- T_x^T y,  T_x = I + dt A_c   (structure: SURVEY App. A-3)
+__device__ __forceinline__ void applyTtx(double (&y)[NX], const double* __restrict__ cf, double dt)
+{
+    const double c0 = y[IX_COM], c1 = y[IX_COM + 1], c2 = y[IX_COM + 2];
+    const double l0 = y[IX_LIN], l1 = y[IX_LIN + 1], l2 = y[IX_LIN + 2];
+    const double r0 = y[IX_RPY], r1 = y[IX_RPY + 1], r2 = y[IX_RPY + 2];
+    const double a0 = y[IX_ANG], a1 = y[IX_ANG + 1], a2 = y[IX_ANG + 2];
+    const double w0 = cf[QD_OMEGA], w1 = cf[QD_OMEGA + 1], w2 = cf[QD_OMEGA + 2];
+    const double jtt = cf[QD_JTT];
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+    {
+        y[IX_COM + b] += dt * y[IX_EP + b];
+        y[IX_RPY + b] += dt * y[IX_ER + b];
+    }
+    {
+        const double* Rm = cf + QD_RM;
+        const double* WI = cf + QD_WI;
+        y[IX_LIN + 0] = l0 + dt * (Rm[0] * c0 + Rm[3] * c1 + Rm[6] * c2 + (w1 * l2 - w2 * l1));
+        y[IX_LIN + 1] = l1 + dt * (Rm[1] * c0 + Rm[4] * c1 + Rm[7] * c2 + (w2 * l0 - w0 * l2));
+        y[IX_LIN + 2] = l2 + dt * (Rm[2] * c0 + Rm[5] * c1 + Rm[8] * c2 + (w0 * l1 - w1 * l0));
+        y[IX_ANG + 0] = a0 + dt * (WI[0] * r0 + WI[3] * r1 + WI[6] * r2 + (w1 * a2 - w2 * a1));
+        y[IX_ANG + 1] = a1 + dt * (WI[1] * r0 + WI[4] * r1 + WI[7] * r2 + (w2 * a0 - w0 * a2));
+        y[IX_ANG + 2] = a2 + dt * (WI[2] * r0 + WI[5] * r1 + WI[8] * r2 + (w0 * a1 - w1 * a0));
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        const double T = y[IX_T + j], Td = y[IX_TD + j];
+        const double al = cf[QD_ALIN + j] * l0 + cf[QD_ALIN + NT + j] * l1 + cf[QD_ALIN + 2 * NT + j] * l2;
+        const double aa = cf[QD_AANG + j] * a0 + cf[QD_AANG + NT + j] * a1 + cf[QD_AANG + 2 * NT + j] * a2;
+        y[IX_T + j] = T + dt * (al + aa + cf[QD_JA + j] * Td);
+        y[IX_TD + j] = Td + dt * (jtt * T + cf[QD_JB + j] * Td);
+    }
+}
+
+// out[a] = dt * B_J[:, a]' y  (B_J has the six momentum rows only; lam = [q][a] in shared memory, 16-byte aligned)
+__device__ __forceinline__ void bjT_dot(const double (&y)[NX], const double* __restrict__ lam, double dt, double (&out)[NJ])
+{
+    const double2* l2 = reinterpret_cast<const double2*>(lam);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+        out[a] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+    {
+        const double yv = dt * y[(q < 3 ? IX_LIN : IX_ANG - 3) + q];
+#pragma unroll
+        for (int a2 = 0; a2 < NJ / 2; ++a2)
+        {
+            const double2 lv = l2[q * (NJ / 2) + a2];
+            out[2 * a2] = fma(lv.x, yv, out[2 * a2]);
+            out[2 * a2 + 1] = fma(lv.y, yv, out[2 * a2 + 1]);
+        }
+    }
+}
+
+// dt * c' y   (c: affine term of the dynamics; rows LIN, TD, EP, ER); three independent FMA chains
+__device__ __forceinline__ double c_dot(const double (&y)[NX], const double* __restrict__ cf, double dt)
+{
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        a0 = fma(y[IX_LIN + a], cf[QD_CL + a], a0);
+        a1 = fma(y[IX_EP + a], cf[QD_CEP + a], a1);
+        a2 = fma(y[IX_ER + a], cf[QD_CER + a], a2);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+    {
+        if (j & 1)
+            a1 = fma(y[IX_TD + j], cf[QD_CTD + j], a1);
+        else
+            a0 = fma(y[IX_TD + j], cf[QD_CTD + j], a0);
+    }
+    return dt * (a0 + a1 + a2);
+}
+
+// Gauss-Jordan inverse of an SPD 8 x 8 matrix through shared memory by one warp: lane (r = lane & 7, q = lane >> 3)
+// owns element pair [r][2q..2q+1] in registers; every pivot step reads the pivot row / column from one buffer and
+// writes the updated pairs to the other (ping-pong S <-> T: one __syncwarp per pivot, no divergent branches); eight
+// pivots later the inverse is back in S.  S, T: row-major, ld 8, 16-byte aligned.
+__device__ __forceinline__ bool gj8(double* __restrict__ S, double* __restrict__ T, double2 own, int lane)
+{
+    const int r = lane & 7, q = lane >> 3;
+    reinterpret_cast<double2*>(S)[r * 4 + q] = own;
+    __syncwarp();
+    bool ok = true;
+    double* src = S;
+    double* dst = T;
+#pragma unroll 2
+    for (int p = 0; p < NJ; ++p)
+    {
+        const double d = src[p * NJ + p];
+        const double f = src[r * NJ + p];
+        const double2 pr = reinterpret_cast<const double2*>(src)[p * 4 + q];
+        ok = ok && (d > 0.0) && (d < 1e300);
+        const double dinv = __drcp_rn(d);
+        const bool piv = r == p;
+        const double coef = piv ? -dinv : f * dinv;      // pivot row: 0 - (-1/d) * row ; others: own - (f/d) * row
+        const double bx = piv ? 0.0 : own.x, by = piv ? 0.0 : own.y;
+        own.x = fma(-coef, pr.x, bx);
+        own.y = fma(-coef, pr.y, by);
+        const double val = piv ? dinv : -coef;           // column p of the inverse in progress
+        const bool mine = q == (p >> 1);
+        own.x = (mine && !(p & 1)) ? val : own.x;
+        own.y = (mine && (p & 1)) ? val : own.y;
+        reinterpret_cast<double2*>(dst)[r * 4 + q] = own;
+        __syncwarp();
+        double* t = src;
+        src = dst;
+        dst = t;
+    }
+    return ok;
+}
+
+// exact max / min of NON-NEGATIVE doubles over the warp with two 32-bit REDUX each (non-negative doubles order like
+// their bit patterns); arg = lowest lane attaining it
+__device__ __forceinline__ double warp_max_nonneg(double v, int& arg)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    arg = __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+__device__ __forceinline__ double warp_min_nonneg(double v, int& arg)
+{
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    arg = __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+
+template <class SM> struct CdCtxT
+{
+    const DeviceConfig& cfg;
+    SM& sm;
+    double* ws;   // per elimination knot: one stage (K first)
+    int lane;
+    int D0;       // first column of the held joint block during the tail
+    int kS;       // knot where the held joint block is eliminated (-1: none)
+};
+
+// ---- warp A --------------------------------------------------------------------------------------------------
+// steps i-k of a knot: invert H_uu (own = this lane's pair of it), K = H_uu^-1 H_ux, P <- P - H_ux' K
+template <class SM>
+__device__ __forceinline__ bool a_eliminate(const CdCtxT<SM>& c, CdSlot& sl, double (&p)[NX], const double (&hux)[NJ],
+                                            double2 own, double* __restrict__ wsk)
+{
+    SM& sm = c.sm;
+    const int lane = c.lane;
+    const bool ok = gj8(sl.Hinv, sm.Mt, own, lane);   // Mt: free between the transposition and the gain rows
+    if (lane < NX)
+    {
+        const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
+#pragma unroll 2
+        for (int a = 0; a < NJ; ++a)
+        {
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < NJ / 2; ++m)
+            {
+                const double2 hh = hi[a * (NJ / 2) + m];
+                v0 = fma(hh.x, hux[2 * m], v0);
+                v1 = fma(hh.y, hux[2 * m + 1], v1);
+            }
+            sm.Mt[a * NX + lane] = v0 + v1;
+            wsk[WSC_K + a * NX + lane] = v0 + v1;
+        }
+    }
+    __syncwarp();
+    if (lane < NX)
+    {
+#pragma unroll 2
+        for (int m = 0; m < NJ; ++m)
+        {
+            const double h = sl.Hux[m * NX + lane];
+            const double2* kr = reinterpret_cast<const double2*>(sm.Mt + m * NX);
+#pragma unroll
+            for (int j = 0; j < NX / 2; ++j)
+            {
+                const double2 kk = kr[j];
+                p[2 * j] = fma(-h, kk.x, p[2 * j]);
+                p[2 * j + 1] = fma(-h, kk.y, p[2 * j + 1]);
+            }
+        }
+    }
+    __syncwarp();
+    return ok;
+}
+
+// propagation of P through knot k: P' = P + Q, publish P'D, P <- T'P'T; with elim also H_ux (published) and this
+// lane's pair of H_uu = R + B_u' P' B_u
+template <class SM>
+__device__ __forceinline__ void a_prop(const CdCtxT<SM>& c, int k, bool elim, double (&p)[NX], double qd_lane,
+                                       double (&hux)[NJ], double2& own)
+{
+    SM& sm = c.sm;
+    const int lane = c.lane;
+    const double* cf = sm.cf;
+    const double dt = sm.dtk[k];
+    CdSlot& sl = sm.slot[k & 1];
+    // P' = P + Q on the diagonal element this lane owns (predicated add: keeps the compiler from turning the
+    // 26-way ownership test into a divergent jump table)
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+        asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q add.f64 %0, %0, %3; }" : "+d"(p[j]) : "r"(lane), "r"(j), "d"(qd_lane));
+    if (lane < NX)
+    {
+        // P'D for the throttle / affine columns of this knot
+        const double jgt = cf[QD_JGT];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+            sl.PD[lane * NPD + q] = dt * (cf[QD_JG + q] * p[IX_TD + q] + jgt * p[IX_T + q]);
+        sl.PD[lane * NPD + 4] = c_dot(p, cf, dt);
+    }
+    // pass 0: (P'D)_joint = dt P' B_J from row i of P', then row i of M = P'T, transposition;
+    // pass 1: H_ux[:, i] = B_u' M[:, i] from column i of M, then column i of T'M = row i of T'P'T
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        if (lane < NX)
+        {
+            if (pass == 0 || elim)
+            {
+                bjT_dot(p, sm.lam, dt, hux);
+                double* dst = pass == 0 ? sl.PD + lane * NPD + 5 : sl.Hux + lane;
+                const int stride = pass == 0 ? 1 : NX;
+#pragma unroll
+                for (int a = 0; a < NJ; ++a)
+                    dst[a * stride] = hux[a];
+            }
+            applyTtx(p, cf, dt);
+            if (pass == 0)
+            {
+#pragma unroll
+                for (int j = 0; j < NX; ++j)
+                    sm.Mt[lane * LDM + j] = p[j];
+            }
+        }
+        __syncwarp();
+        if (pass == 0 && lane < NX)
+        {
+#pragma unroll
+            for (int j = 0; j < NX; ++j)
+                p[j] = sm.Mt[j * LDM + lane];
+        }
+    }
+    if (elim)
+    {
+        // H_uu[r][2q..2q+1] = R + dt Lambda[:, r]' (P'D)_joint[momentum rows, 2q..2q+1]
+        const int r = lane & 7, q = lane >> 3;
+        double hx = (2 * q == r) ? sm.Rqd[r] : 0.0, hy = (2 * q + 1 == r) ? sm.Rqd[r] : 0.0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m)
+        {
+            const double lv = dt * sm.lam[m * NJ + r];
+            const double* pd = sl.PD + ((m < 3 ? IX_LIN : IX_ANG - 3) + m) * NPD + 5 + 2 * q;
+            hx = fma(lv, pd[0], hx);
+            hy = fma(lv, pd[1], hy);
+        }
+        own = make_double2(hx, hy);
+    }
+}
+
+// ---- per-lane sparse table of T_x (forward rollout), SURVEY App. A-3 ---------------------------------------------
+constexpr int CQF = 8;
+struct CdFwdTab
+{
+    double cw[CQF];
+    int iw[CQF];   // source index: 0..25 state, 26..29 throttle in effect, 30..37 joint increment in effect
+    double cc;
+    int helper;
+};
+
+static __device__ void cd_build_fwd(CdFwdTab& t, const double* __restrict__ cf, int lane)
+{
+#pragma unroll
+    for (int q = 0; q < CQF; ++q) { t.cw[q] = 0.0; t.iw[q] = 0; }
+    t.cc = 0.0;
+    t.helper = -1;
+    const double w[3] = {cf[QD_OMEGA], cf[QD_OMEGA + 1], cf[QD_OMEGA + 2]};
+    auto mS = [&](int a, int b) -> double {   // -S(w)[a][b]
+        if (a == b) return 0.0;
+        const int k = 3 - a - b;
+        const double sgn = ((b - a + 3) % 3 == 1) ? 1.0 : -1.0;
+        return sgn * w[k];
+    };
+    auto setw = [&](int q, double cv, int iv) {
+#pragma unroll
+        for (int qq = 0; qq < CQF; ++qq)
+            if (qq == q) { t.cw[qq] = cv; t.iw[qq] = iv; }
+    };
+    const int i = lane;
+    if (i < IX_LIN)
+        for (int b = 0; b < 3; ++b) setw(b, cf[QD_RM + i * 3 + b], IX_LIN + b);
+    else if (i < IX_RPY || (i >= IX_ANG && i < IX_T))
+    {
+        const bool lin = i < IX_RPY;
+        const int a = lin ? i - IX_LIN : i - IX_ANG;
+        const int base = lin ? IX_LIN : IX_ANG;
+        for (int b = 0; b < 3; ++b) setw(b, mS(a, b), base + b);
+        for (int q = 0; q < NT; ++q) setw(3 + q, cf[(lin ? QD_ALIN : QD_AANG) + a * NT + q], IX_T + q);
+        t.cc = lin ? cf[QD_CL + a] : 0.0;
+        t.helper = (lin ? NX : NX + 3) + a;
+    }
+    else if (i < IX_ANG)
+        for (int b = 0; b < 3; ++b) setw(b, cf[QD_WI + (i - IX_RPY) * 3 + b], IX_ANG + b);
+    else if (i < IX_TD)
+    {
+        const int q = i - IX_T;
+        setw(0, cf[QD_JTT], IX_TD + q);
+        setw(1, cf[QD_JGT], NX + q);
+    }
+    else if (i < IX_EP)
+    {
+        const int q = i - IX_TD;
+        setw(0, cf[QD_JA + q], IX_T + q);
+        setw(1, cf[QD_JB + q], IX_TD + q);
+        setw(2, cf[QD_JG + q], NX + q);
+        t.cc = cf[QD_CTD + q];
+    }
+    else if (i < IX_ER)
+    {
+        setw(0, 1.0, IX_COM + (i - IX_EP));
+        t.cc = cf[QD_CEP + (i - IX_EP)];
+    }
+    else if (i < NX)
+    {
+        setw(0, 1.0, IX_RPY + (i - IX_ER));
+        t.cc = cf[QD_CER + (i - IX_ER)];
+    }
+    else
+    { // helper lanes 26..28: Lambda_lin rows, 29..31: Lambda_ang rows
+        const int a = (i - NX) % 3;
+        const bool lin = i < NX + 3;
+        for (int b = 0; b < NJ; ++b) setw(b, cf[(lin ? QD_LLIN : QD_LANG) + a * NJ + b], NY + b);
+    }
+}
+
+// knot schedule of the two software-pipelined warps
+__device__ __forceinline__ void cd_schedule(int t, int N, int kS, int& ta, int& ka, int& tb_, int& kb)
+{
+    ta = tb_ = TK_NONE;
+    ka = kb = 0;
+    if (kS < 0)
+    {
+        if (t < N) { ta = TK_STAGE; ka = N - 1 - t; }
+        if (t >= 1 && t <= N) { tb_ = TK_STAGE; kb = N - t; }
+        return;
+    }
+    const int nTail = N - 1 - kS;
+    if (t < nTail) { ta = TK_STAGE; ka = N - 1 - t; }
+    else if (t == nTail) { ta = TK_PROP; ka = kS; }
+    else if (t == nTail + 2) { ta = TK_SCHUR; ka = kS; }
+    else if (t >= nTail + 3 && t < nTail + 3 + kS) { ta = TK_STAGE; ka = kS - 1 - (t - nTail - 3); }
+    if (t >= 1 && t <= nTail) { tb_ = TK_STAGE; kb = N - t; }
+    else if (t == nTail + 1) { tb_ = TK_PROP; kb = kS; }
+    else if (t == nTail + 3) { tb_ = TK_SCHUR; kb = kS; }
+    else if (t > nTail + 3 && t <= nTail + 3 + kS) { tb_ = TK_STAGE; kb = kS - (t - nTail - 3); }
+}
+
+// warp A: forward rollout with the stored gains (u_k = -K_k x - F_k theta*), outputs (variableSamplingMPC.cpp:88-112)
+// and, with z != nullptr, the full primal.  xs: 40 doubles of shared memory (x, throttle block in effect, dq in effect);
+// fth: F_k theta* [Nc][8]; theta: throttle variables (4 nblk); stage: doubles per elimination knot in ws (K first)
+template <class SM>
+__device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, const double* __restrict__ ws, int stage,
+                                           const double* __restrict__ theta, const double* __restrict__ fth,
+                                           double* __restrict__ xs, int lane, int B, int inst, double* __restrict__ z,
+                                           double* __restrict__ o, double* __restrict__ st)
+{
+    const int N = cfg.N, Nc = cfg.Nc, nv = 4 * cfg.nblk;
+    CdFwdTab tab;
+    cd_build_fwd(tab, sm.cf, lane);
+    double* dqs = xs + NY;
+    double x = lane < NX ? sm.cf[QD_X0 + lane] : 0.0;
+    if (lane < NX)
+        xs[lane] = x;
+    if (lane < NJ)
+        dqs[lane] = 0.0;
+    if (z && lane < NX)
+        z[lane] = x;
+    __syncwarp();
+    const int ka = lane & 7, kq = lane >> 3;   // gain row / quarter of the state handled by this lane
+    const int j0 = kq * 7, jn = kq == 3 ? 5 : 7;
+    // gain rows are prefetched one knot ahead (their addresses do not depend on the state) into the register set the
+    // other knot parity uses, so that no instruction of knot k waits for the loads of knot k+1
+    double kA[7], kB[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t)
+    {
+        kA[t] = t < jn ? ws[WSC_K + ka * NX + j0 + t] : 0.0;
+        kB[t] = 0.0;
+    }
+    auto knot = [&](int k, double (&kuse)[7], double (&kload)[7]) {
+        const double dt = sm.dtk[k];
+        const int tb = throttle_block(k, cfg.Ns, cfg.Nc);
+        if (k + 1 < Nc)
+        {
+            const double* __restrict__ Kn = ws + (size_t)(k + 1) * stage + WSC_K + ka * NX + j0;
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+                kload[t] = t < jn ? Kn[t] : 0.0;
+        }
+        if (lane < NT)
+            xs[NX + lane] = theta[4 * tb + lane];
+        if (k < Nc)
+        {
+            double part = 0.0, part2 = 0.0;
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+            {
+                if (t & 1)
+                    part2 = fma(kuse[t], xs[j0 + t], part2);
+                else
+                    part = fma(kuse[t], xs[j0 + t], part);
+            }
+            part += part2;
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            part += __shfl_xor_sync(0xffffffffu, part, 16);
+            const double u = -part - fth[k * NJ + ka];
+            if (lane < NJ)
+            {
+                dqs[lane] = u;
+                if (k == 0)
+                    o[VSMPC_OUT_DELTA_Q + lane] = u;
+                if (z)
+                    z[NX * (N + 1) + k * NJ + lane] = u;
+            }
+        }
+        __syncwarp();
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < CQF; ++q)
+        {
+            acc = fma(tab.cw[q], xs[tab.iw[q]], acc);   // xs = [x (26) | throttle block in effect (4) | dq in effect (8)]
+        }
+        const double other = __shfl_sync(0xffffffffu, acc, tab.helper < 0 ? lane : tab.helper);
+        if (tab.helper >= 0)
+            acc += other;
+        acc += tab.cc;
+        x = fma(dt, acc, x);
+        __syncwarp();
+        if (lane < NX)
+            xs[lane] = x;
+        if (k == 0 && lane >= IX_T && lane < IX_EP)
+            o[(lane < IX_TD ? VSMPC_OUT_THRUST - IX_T : VSMPC_OUT_THRUST_DOT - IX_TD) + lane] = x;
+        if (k == N - 1 && lane < NX)
+            o[VSMPC_OUT_FINAL_STATE + lane] = x;
+        if (z && lane < NX)
+            z[(k + 1) * NX + lane] = x;
+        __syncwarp();
+    };
+#pragma unroll 1
+    for (int k = 0; k < N; k += 2)
+    {
+        knot(k, kA, kB);
+        if (k + 1 < N)
+            knot(k + 1, kB, kA);
+    }
+    // remaining outputs (variableSamplingMPC.cpp:96-108,138-151)
+    if (lane < NT)
+        o[VSMPC_OUT_THROTTLE + lane] = destd_throttle_qd(sm.cf, theta[lane]);
+    if (lane < NJ)
+    {
+        const double dq = o[VSMPC_OUT_DELTA_Q + lane];
+        const double acc = st[(size_t)(ST_QACC + lane) * B + inst] + dq;
+        st[(size_t)(ST_QACC + lane) * B + inst] = acc;
+        o[VSMPC_OUT_JOINTS_REF + lane] = acc;
+    }
+    if (z)
+    {
+        const int base = NX * (N + 1) + Nc * NJ;
+        for (int e = lane; e < nv; e += 32)
+            z[base + e] = theta[e];
+    }
+}
+
+} // namespace vsmpc

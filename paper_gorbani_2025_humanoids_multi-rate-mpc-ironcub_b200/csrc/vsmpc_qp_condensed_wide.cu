@@ -1,0 +1,713 @@
+// K2 (long horizons) — condensed-throttle Riccati QP kernel with several column warps.  FP64 on the CUDA cores, the
+// deferred down-date of Om on the FP64 tensor cores.
+//
+// Same algorithm and the same replaced reference code as vsmpc_qp_condensed.cu (IMPCProblem::solve -> OsqpEigen,
+// MPC/src/IMPCProblem/IMPCProblem.cpp:196-298; VariableSamplingMPC::solveMPC output extraction,
+// variableSamplingMPC.cpp:88-112), for horizons beyond its 6 throttle blocks / 32 knots (BASELINE configs[3]: 2-4x
+// the reference knot count).  The value function V_k(x; theta) = 1/2 x'P x + x'Psi theta + 1/2 theta'Om theta now has
+// theta = (v_0 .. v_{nblk-1}, 1, held joint block) with up to 192 columns:
+// * warp 0 owns P and runs exactly the recursion of the narrow kernel (shared code: vsmpc_condensed_core.cuh);
+// * warps 1..G own 32 parameter columns each (lane = column, Psi column in registers).  The columns are independent
+//   given what warp 0 publishes per knot, so all column warps read one mailbox, one knot behind warp 0; only the
+//   updates of Om (dynamic shared memory, odd leading dimension) need a named barrier among them;
+// * the rank-8 down-dates of Om are stacked in the workspace and contracted once by all warps with
+//   mma.sync.m8n8k4.f64 over the upper 8 x 8 tiles;
+// * the reduced Hessian H_r (<= 183 x 183, in place in Om) is inverted by block-wide exchange pivots (x_q <-> y_q in
+//   y = H_r x); the Goldfarb-Idnani dual active set then keeps the SAME matrix as the principal pivot transform of H_r
+//   over the free variables: adding a bound to / dropping it from the working set is one more pivot on that index, and
+//   column p of the matrix holds both the primal direction (free rows) and the multiplier direction (active rows) —
+//   no working-set inverse, no back-solves; one variable per thread, three block barriers per iteration;
+// * F_k theta* by all warps, forward rollout by warp 0.
+#include "vsmpc_condensed_core.cuh"
+
+namespace vsmpc
+{
+
+constexpr int CW_MAXG = 6;                          // column warps
+constexpr int CW_MAXTHREADS = 32 * (1 + CW_MAXG);   // 224
+constexpr int CW_SMEM_LIMIT = 227 * 1024;           // opt-in shared memory per CTA on sm_100
+
+struct alignas(16) CwSmem
+{
+    double cf[CCF];
+    alignas(16) double lam[6 * NJ];   // dt-free B_J rows: [q][a]
+    double Qd[NX];
+    double Rqd[NJ];
+    double dtk[MAX_ITER];
+    CdSlot slot[2];                   // warp 0 -> column warps mailbox, slot = knot & 1
+    alignas(16) double Mt[NX * LDM];  // warp 0: transposition buffer, gain rows of the knot in flight
+    double xs[40];                    // forward rollout: x (26), throttle block in effect (4), dq in effect (8)
+    int flags[4];
+};
+
+struct CwLayout
+{
+    int G, ldc;                 // column warps, columns carried (32 G)
+    int nv, aff, D0, nlo, ldo;  // throttle variables, affine column, first held-joint column, order of Om, its ld (odd)
+    int nt;                     // 8 x 8 tiles per side of Om
+    int wsF, wsH, stage;        // workspace per elimination knot: K [8][26] | F [8][ldc] | H_utheta [8][ldc]
+    int om, fth, theta, vv, grad, rb, total;   // offsets (doubles) in dynamic shared memory
+};
+
+__host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
+{
+    CwLayout L;
+    const bool held = cfg.Nc - 1 < cfg.N - 1;
+    L.nv = NT * cfg.nblk;
+    L.aff = L.nv;
+    L.D0 = L.nv + 1;
+    L.nlo = L.nv + 1 + (held ? NJ : 0);
+    L.G = (L.nlo + 31) / 32;
+    L.ldc = 32 * L.G;
+    L.ldo = L.nlo | 1;
+    L.nt = (L.nlo + 7) / 8;
+    L.wsF = NJ * NX;
+    L.wsH = L.wsF + NJ * L.ldc;
+    L.stage = L.wsH + NJ * L.ldc;
+    int o = 0;
+    L.om = o;     o += (L.nlo * L.ldo + 1) & ~1;
+    L.fth = o;    o += cfg.Nc * NJ;
+    L.theta = o;  o += L.ldc;
+    L.vv = o;     o += L.nv;
+    L.grad = o;   o += L.nv;
+    L.rb = o;     o += 4 * 8;      // two block-reduction buffers: value [8], index [8] each
+    L.total = o;
+    return L;
+}
+
+using CwCtx = CdCtxT<CwSmem>;
+
+__device__ __forceinline__ void cw_bar_columns(int n_threads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+// propagation of the parameter columns through knot k (Psi'' = Psi' + P'D, Om += D'Psi'' + Psi''D, Psi <- T'Psi'');
+// returns dt B_J' Psi''[:, gc] in bj2.  gc: column of this lane
+__device__ __forceinline__ void w_prop(const CwCtx& c, const CwLayout& L, double* __restrict__ Om,
+                                       const double* __restrict__ qd, int k, bool tail, int gc, double (&s)[NX],
+                                       double (&bj2)[NJ])
+{
+    const DeviceConfig& cfg = c.cfg;
+    CwSmem& sm = c.sm;
+    const double* cf = sm.cf;
+    const double dt = sm.dtk[k];
+    CdSlot& sl = sm.slot[k & 1];
+    const int tb = throttle_block(k, cfg.Ns, cfg.Nc);
+    const int ldo = L.ldo;
+    const bool isAff = gc == L.aff;
+    const bool spV = gc < L.nv && (gc >> 2) == tb;
+    const bool isD = tail && gc >= L.D0 && gc < L.D0 + NJ;
+    const double jgt = cf[QD_JGT];
+    if (isAff)
+    {
+        const int rc = ref_col(k, cfg.Ns);
+#pragma unroll
+        for (int r = 0; r < 12; ++r)
+            s[r] = fma(-sm.Qd[r], qd[QD_XREF + r * cfg.NC + rc], s[r]);   // tracking gradient of x_{k+1}
+    }
+    double bv[NT], bd[NJ];
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+        bv[q] = dt * (cf[QD_JG + q] * s[IX_TD + q] + jgt * s[IX_T + q]);
+    const double baff = c_dot(s, cf, dt);
+    if (tail)
+        bjT_dot(s, sm.lam, dt, bd);
+    const int col = spV ? (gc & 3) : (isAff ? 4 : (isD ? 5 + gc - L.D0 : -1));
+    if (col >= 0)
+    {
+#pragma unroll
+        for (int r = 0; r < NX; ++r)
+            s[r] += sl.PD[r * NPD + col];
+    }
+    bjT_dot(s, sm.lam, dt, bj2);
+    // Om += D'Psi'' (rows of the special columns: every lane its own column), barrier among the column warps, then
+    // Om += Psi'D (columns of the special columns: every lane its own row)
+    if (gc < L.nlo)
+    {
+        double ov[NT];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+            ov[q] = Om[(4 * tb + q) * ldo + gc];
+        const double oa = Om[L.aff * ldo + gc];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+            Om[(4 * tb + q) * ldo + gc] = ov[q] + dt * (cf[QD_JG + q] * s[IX_TD + q] + jgt * s[IX_T + q]);
+        Om[L.aff * ldo + gc] = oa + c_dot(s, cf, dt);
+        if (tail)
+        {
+#pragma unroll
+            for (int a = 0; a < NJ; ++a)
+                Om[(L.D0 + a) * ldo + gc] += bj2[a];
+        }
+    }
+    cw_bar_columns(32 * L.G);
+    if (gc < L.nlo)
+    {
+        double ov[NT];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+            ov[q] = Om[gc * ldo + 4 * tb + q];
+        const double oa = Om[gc * ldo + L.aff];
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+            Om[gc * ldo + 4 * tb + q] = ov[q] + bv[q];
+        Om[gc * ldo + L.aff] = oa + baff;
+        if (tail)
+        {
+#pragma unroll
+            for (int a = 0; a < NJ; ++a)
+                Om[gc * ldo + L.D0 + a] += bd[a];
+        }
+    }
+    applyTtx(s, cf, dt);
+}
+
+// down-date of the parameter columns with the eliminated block: F = H_uu^-1 H_utheta, Psi -= H_ux' F; H_utheta and F go
+// to the workspace stacks for the deferred down-date of Om
+__device__ __forceinline__ void w_downdate(const CdSlot& sl, const CwLayout& L, int gc, double (&s)[NX],
+                                           const double (&hut)[NJ], double* __restrict__ wsk, bool clear_col)
+{
+    double f[NJ];
+#pragma unroll
+    for (int m = 0; m < NJ; ++m)
+        wsk[L.wsH + m * L.ldc + gc] = hut[m];
+    const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+    {
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NJ / 2; ++m)
+        {
+            const double2 hh = hi[a * (NJ / 2) + m];
+            v0 = fma(hh.x, hut[2 * m], v0);
+            v1 = fma(hh.y, hut[2 * m + 1], v1);
+        }
+        f[a] = v0 + v1;
+        wsk[L.wsF + a * L.ldc + gc] = f[a];
+    }
+    if (gc < L.nlo)
+    {
+#pragma unroll
+        for (int m = 0; m < NJ; ++m)
+        {
+            const double2* hr = reinterpret_cast<const double2*>(sl.Hux + m * NX);
+#pragma unroll
+            for (int j = 0; j < NX / 2; ++j)
+            {
+                const double2 hh = hr[j];
+                s[2 * j] = fma(-f[m], hh.x, s[2 * j]);
+                s[2 * j + 1] = fma(-f[m], hh.y, s[2 * j + 1]);
+            }
+        }
+    }
+    if (clear_col)
+    {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            s[j] = 0.0;
+    }
+}
+
+// Om -= H'F with H, F the (8 Nc) x ldc stacks of the workspace, on the upper 8 x 8 tiles; one work item = tile row ti,
+// four tile columns from tj0; A fragment = H' (lane l: row l >> 2 of the tile, stack row l & 3), B fragment = F (stack
+// row l & 3, column l >> 2), C fragment: row l >> 2, columns 2 (l & 3) + {0, 1}
+__device__ __forceinline__ void cw_omega_item(const double* __restrict__ ws, const CwLayout& L, int n_rows,
+                                              double* __restrict__ Om, int ti, int tj0, int lane)
+{
+    double c0[4], c1[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        c0[t] = c1[t] = 0.0;
+    const int lr = lane & 3, lc = lane >> 2;
+    int colb[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        colb[t] = 8 * min(tj0 + t, L.nt - 1) + lc;
+#pragma unroll 4
+    for (int r0 = 0; r0 < n_rows; r0 += 4)
+    {
+        const int r = r0 + lr;
+        const double* __restrict__ row = ws + (size_t)(r >> 3) * L.stage + (r & 7) * L.ldc;
+        const double a = row[L.wsH + 8 * ti + lc];
+        double b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            b[t] = row[L.wsF + colb[t]];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c0[t]), "+d"(c1[t])
+                : "d"(a), "d"(b[t]));
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+    {
+        const int tj = tj0 + t;
+        const int gi = 8 * ti + lc;
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+        {
+            const int gj = 8 * tj + 2 * lr + e;
+            const double v = e == 0 ? c0[t] : c1[t];
+            if (tj < L.nt && gi < L.nlo && gj < L.nlo)
+            {
+                Om[gi * L.ldo + gj] -= v;
+                if (tj > ti)
+                    Om[gj * L.ldo + gi] -= v;
+            }
+        }
+    }
+}
+
+// exchange pivot on index q of T = Om[first:nv, first:nv] by the whole block: in (outputs) = T (inputs) the roles of
+// input q and output q are swapped.  Pivoting every index turns H into H^-1; pivoting q again undoes it.  Warp w sweeps
+// rows first + w, first + w + nwarps, ...; lanes over the columns, row q held in registers
+__device__ __forceinline__ bool cw_pivot(double* __restrict__ Om, int ldo, int first, int nv, int q, int warp, int lane,
+                                         int nwarps, int nthr)
+{
+    const double d = Om[q * ldo + q];
+    const double dinv = 1.0 / d;
+    const double* rowq = Om + q * ldo;
+    double rq[CW_MAXG];
+#pragma unroll
+    for (int cc = 0; cc < CW_MAXG; ++cc)
+    {
+        const int j = first + lane + 32 * cc;
+        rq[cc] = (j < nv && j != q) ? rowq[j] : 0.0;
+    }
+    for (int i = first + warp; i < nv; i += nwarps)
+    {
+        if (i == q)
+            continue;
+        double* rowi = Om + i * ldo;
+        const double f = rowi[q] * dinv;
+#pragma unroll
+        for (int cc = 0; cc < CW_MAXG; ++cc)
+        {
+            const int j = first + lane + 32 * cc;
+            if (j < nv && j != q)
+                rowi[j] = fma(-f, rq[cc], rowi[j]);
+        }
+    }
+    __syncthreads();
+    for (int e = first + (int)threadIdx.x; e < nv; e += nthr)
+    {
+        if (e != q)
+        {
+            Om[q * ldo + e] *= -dinv;
+            Om[e * ldo + q] *= dinv;
+        }
+    }
+    if (threadIdx.x == 0)
+        Om[q * ldo + q] = dinv;
+    __syncthreads();
+    return (d > 0.0) && isfinite(d);
+}
+
+// block-wide max / min of non-negative doubles with the lowest thread attaining it (one barrier; rb: value [8] and
+// index [8], not reused before the next barrier)
+template <bool MAX>
+__device__ __forceinline__ double cw_block_best(double v, double* __restrict__ rb, int warp, int lane, int nwarps, int& arg)
+{
+    int a;
+    const double w = MAX ? warp_max_nonneg(v, a) : warp_min_nonneg(v, a);
+    int* rbi = reinterpret_cast<int*>(rb + 8);
+    if (lane == 0)
+    {
+        rb[warp] = w;
+        rbi[warp] = 32 * warp + a;
+    }
+    __syncthreads();
+    double best = rb[0];
+    arg = rbi[0];
+    for (int q = 1; q < nwarps; ++q)
+    {
+        const double o = rb[q];
+        if (MAX ? (o > best) : (o < best))
+        {
+            best = o;
+            arg = rbi[q];
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(CW_MAXTHREADS, 2)
+qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
+                         double* __restrict__ ws_all, double* __restrict__ scratch_all, double* __restrict__ z_all,
+                         double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
+                         int* __restrict__ n_factor, int* __restrict__ n_solve, size_t ws_stride, size_t scratch_stride,
+                         int want_z)
+{
+    extern __shared__ __align__(16) unsigned char cw_raw[];
+    CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
+    double* dyn = reinterpret_cast<double*>(cw_raw + sizeof(CwSmem));
+    const DeviceConfig& cfg = cfgv;
+    const CwLayout L = cw_layout(cfg);
+    double* Om = dyn + L.om;
+    double* fth = dyn + L.fth;
+    double* theta = dyn + L.theta;
+    double* vv = dyn + L.vv;
+    double* grad = dyn + L.grad;
+    double* rbA = dyn + L.rb;
+    double* rbB = dyn + L.rb + 16;
+
+    const int nthr = blockDim.x, nwarps = nthr >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int inst = blockIdx.x;
+    const double* qd = qd_all + (size_t)inst * cfg.qd_stride;
+    const int N = cfg.N, Nc = cfg.Nc;
+    const int nv = L.nv, ldo = L.ldo;
+    const bool held = Nc - 1 < N - 1;
+    const int gc = (warp - 1) * 32 + lane;     // column of this lane (warps >= 1)
+    CwCtx c{cfg, sm, ws_all + (size_t)inst * ws_stride, lane, L.D0, held ? Nc - 1 : -1};
+
+    // ---- stage the QP data; finiteness gate ----------------------------------------------------------------------
+    bool fin = true;
+    for (int e = threadIdx.x; e < cfg.qd_stride; e += nthr)
+    {
+        const double v = qd[e];
+        fin = fin && isfinite(v);
+        if (e < CCF)
+            sm.cf[e] = v;
+    }
+    for (int e = threadIdx.x; e < L.nlo * ldo; e += nthr)
+        Om[e] = 0.0;
+    if (threadIdx.x < NX)
+        sm.Qd[threadIdx.x] = cfg.Qd[threadIdx.x];
+    if (threadIdx.x < NJ)
+        sm.Rqd[threadIdx.x] = cfg.Rqd[threadIdx.x];
+    for (int e = threadIdx.x; e < N; e += nthr)
+        sm.dtk[e] = cfg.dt[e];
+    for (int e = threadIdx.x; e < 6 * NJ; e += nthr)
+        sm.lam[e] = qd[(e < 3 * NJ ? QD_LLIN : QD_LANG - 3 * NJ) + e];
+    const bool all_fin = __syncthreads_and(fin);
+    int stat = all_fin ? VSMPC_STATUS_SOLVED : VSMPC_STATUS_NUMERICAL;
+
+    // ---- factorisation: warp 0 = P recursion, warps 1..G = parameter columns, one knot apart ----------------------
+    double y[NX];   // warp 0: row `lane` of P ; column warps: column gc of Psi
+#pragma unroll
+    for (int j = 0; j < NX; ++j)
+        y[j] = 0.0;
+    const double qd_lane = lane < NX ? sm.Qd[lane] : 0.0;
+    bool ok = true;
+    const int n_it = c.kS < 0 ? N + 1 : (N - 1 - c.kS) + 3 + c.kS + 1;
+    for (int t = 0; t < n_it; ++t)
+    {
+        int ta, ka, tbk, kb;
+        cd_schedule(t, N, c.kS, ta, ka, tbk, kb);
+        if (warp == 0)
+        {
+            if (ta != TK_NONE)
+            {
+                CdSlot& sl = sm.slot[ka & 1];
+                double hux[NJ];
+                double2 own;
+                const bool elim = ta == TK_STAGE && !(held && ka >= Nc - 1);
+                if (ta != TK_SCHUR)
+                    a_prop(c, ka, elim, y, qd_lane, hux, own);
+                else
+                {
+                    // Schur step of the held joint block: H_ux = Psi_T[:, d]' (published by the column warps),
+                    // H_uu = Om_T[d, d] + R
+                    const int r = lane & 7, q = lane >> 3;
+#pragma unroll
+                    for (int m = 0; m < NJ; ++m)
+                        hux[m] = lane < NX ? sl.Hux[m * NX + lane] : 0.0;
+                    own.x = Om[(L.D0 + r) * ldo + L.D0 + 2 * q] + (2 * q == r ? sm.Rqd[r] : 0.0);
+                    own.y = Om[(L.D0 + r) * ldo + L.D0 + 2 * q + 1] + (2 * q + 1 == r ? sm.Rqd[r] : 0.0);
+                }
+                __syncwarp();
+                if (elim || ta == TK_SCHUR)
+                    ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * L.stage) && ok;
+            }
+        }
+        else if (tbk != TK_NONE)
+        {
+            CdSlot& sl = sm.slot[kb & 1];
+            const bool tail = held && kb >= Nc - 1;
+            const bool isD = held && gc >= L.D0 && gc < L.D0 + NJ;
+            double hut[NJ];
+            bool down = false;
+            if (tbk != TK_SCHUR)
+            {
+                w_prop(c, L, Om, qd, kb, tail, gc, y, hut);
+                if (tbk == TK_PROP)
+                {
+                    if (isD)
+                    {
+#pragma unroll
+                        for (int j = 0; j < NX; ++j)
+                            sl.Hux[(gc - L.D0) * NX + j] = y[j];
+                    }
+                }
+                else
+                    down = !tail;
+            }
+            else
+            {
+#pragma unroll
+                for (int m = 0; m < NJ; ++m)
+                    hut[m] = (gc < L.nlo && !isD) ? Om[(L.D0 + m) * ldo + gc] : 0.0;
+                down = true;
+            }
+            if (down)
+            {
+                if (gc == L.aff)
+                {
+#pragma unroll
+                    for (int m = 0; m < NJ; ++m)
+                        hut[m] += sm.cf[QD_GQ + m];
+                }
+                const bool schur = tbk == TK_SCHUR;
+                w_downdate(sl, L, gc, y, hut, c.ws + (size_t)kb * L.stage, schur && isD);
+                if (schur && gc < L.nlo)
+                {
+#pragma unroll
+                    for (int a = 0; a < NJ; ++a)
+                    {
+                        Om[(L.D0 + a) * ldo + gc] = 0.0;
+                        Om[gc * ldo + L.D0 + a] = 0.0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && lane == 0)
+        sm.flags[0] = ok ? 0 : 1;
+    // Psi_0' x0 while the column warps still hold their columns
+    double g_psi = 0.0;
+    if (warp >= 1 && gc < nv)
+    {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+            g_psi = fma(y[j], sm.cf[QD_X0 + j], g_psi);
+    }
+    // deferred down-date of Om on the tensor cores, work items dealt round-robin to the warps
+    {
+        int item = 0;
+        for (int ti = 0; ti < L.nt; ++ti)
+            for (int tj0 = ti; tj0 < L.nt; tj0 += 4, ++item)
+                if (item % nwarps == warp)
+                    cw_omega_item(c.ws, L, NJ * Nc, Om, ti, tj0, lane);
+    }
+    __syncthreads();
+
+    // ---- reduced QP in the throttle variables: gradient, Hessian (in place in Om), inverse ---------------------------
+    const bool pinned = sm.cf[QD_PINNED] != 0.0;
+    const int first = pinned ? NT : 0;
+    const double lo = sm.cf[QD_VMIN], up = sm.cf[QD_VMAX];
+    if (warp >= 1 && gc < nv)
+        grad[gc] = g_psi + Om[gc * ldo + L.aff] - (gc < NT ? cfg.w_i * sm.cf[QD_VBAR + gc] : 0.0);
+    for (int e = threadIdx.x; e < nv; e += nthr)
+    {
+        const int blk = e >> 2;
+        Om[e * ldo + e] += cfg.w_t * ((blk > 0 ? 1.0 : 0.0) + (blk < cfg.nblk - 1 ? 1.0 : 0.0)) + (blk == 0 ? cfg.w_i : 0.0);
+        if (blk > 0)
+            Om[e * ldo + e - NT] -= cfg.w_t;
+        if (blk < cfg.nblk - 1)
+            Om[e * ldo + e + NT] -= cfg.w_t;
+    }
+    __syncthreads();
+    if (pinned)
+    {
+        // block 0 is a parameter: fold it into the gradient
+        for (int e = NT + threadIdx.x; e < nv; e += nthr)
+        {
+            double g = grad[e];
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+                g = fma(Om[e * ldo + j], sm.cf[QD_VBAR + j], g);
+            grad[e] = g;
+        }
+        __syncthreads();
+    }
+    // inverse of H_r = Om[first:nv, first:nv] in place: exchange pivot on every index
+    bool okG = true;
+    for (int p = first; p < nv; ++p)
+        okG = cw_pivot(Om, ldo, first, nv, p, warp, lane, nwarps, nthr) && okG;
+    if (sm.flags[0] != 0 || !okG)
+        stat = stat == VSMPC_STATUS_SOLVED ? VSMPC_STATUS_NUMERICAL : stat;
+    // unconstrained minimiser v = -G g
+    for (int e = threadIdx.x; e < nv; e += nthr)
+    {
+        double v = 0.0;
+        if (e >= first)
+        {
+            const double* row = Om + e * ldo;
+            for (int j = first; j < nv; ++j)
+                v = fma(-row[j], grad[j], v);
+        }
+        vv[e] = v;
+    }
+    __syncthreads();
+
+    // ---- Goldfarb-Idnani dual active set on the boxes, one variable per thread -----------------------------------------
+    // T = Om[first:nv, first:nv] is kept as the principal pivot transform of H_r over the free set F (W = working set):
+    // (v_F, y_W) = T (y_F, v_W) with y = H_r v = -g - sum_a s_a lambda_a e_a.  For a violated free p with sign s, raising
+    // its multiplier by t moves v_F by -t s T[F, p] and lambda_a by -t r_a, r_a = -s_a s T[a, p]; T[p, p] is the step
+    // denominator.  A full step pivots p into W, a blocked step pivots the blocking index back into F.
+    {
+        const int e = threadIdx.x;
+        const bool isvar = e >= first && e < nv;
+        const double tol = 1e-10;
+        int act = 0;            // 0 free, +1 / -1 active at the upper / lower bound
+        double lam_e = 0.0;
+        int iters = 0;
+        bool fail = stat != VSMPC_STATUS_SOLVED;
+        while (!fail)
+        {
+            double viol = 0.0;
+            if (isvar && act == 0)
+            {
+                const double v = vv[e];
+                viol = fmax(fmax(v - up, lo - v), 0.0);
+            }
+            int p;
+            const double best = cw_block_best<true>(viol, rbA, warp, lane, nwarps, p);
+            if (!(best > tol))
+                break;
+            const double vp0 = vv[p];
+            const double s = (vp0 - up > lo - vp0) ? 1.0 : -1.0;
+            const double bound = s > 0 ? up : lo;
+            double lam_p = 0.0;
+            while (true)
+            {
+                if (++iters > 4 * nv + 64)
+                {
+                    stat = VSMPC_STATUS_MAX_ITER;
+                    fail = true;
+                    break;
+                }
+                const double c_e = isvar ? Om[e * ldo + p] : 0.0;
+                const double zp = Om[p * ldo + p];
+                const double v_p = vv[p];
+                const double r_e = act != 0 ? -(double)act * s * c_e : 0.0;
+                int drop;
+                const double t1 = cw_block_best<false>((act != 0 && r_e > 0.0) ? fmax(lam_e, 0.0) / r_e : INFINITY, rbB,
+                                                       warp, lane, nwarps, drop);
+                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) / zp : INFINITY;
+                const double tt = fmin(t1, t2);
+                if (!isfinite(tt))
+                {
+                    stat = VSMPC_STATUS_NUMERICAL;
+                    fail = true;
+                    break;
+                }
+                if (isvar)
+                {
+                    if (act == 0)
+                        vv[e] = fma(-tt * s, c_e, vv[e]);
+                    else
+                        lam_e -= tt * r_e;
+                }
+                lam_p += tt;
+                const bool full = t2 <= t1;
+                const int q = full ? p : drop;
+                if (e == q)
+                {
+                    if (full)
+                    {
+                        act = s > 0 ? 1 : -1;
+                        lam_e = lam_p;
+                        vv[e] = bound;      // exactly on the bound
+                    }
+                    else
+                    {
+                        act = 0;
+                        lam_e = 0.0;
+                    }
+                }
+                cw_pivot(Om, ldo, first, nv, q, warp, lane, nwarps, nthr);
+                if (full)
+                    break;
+            }
+        }
+        // theta*: throttle variables, affine 1, held block 0
+        if (e < L.ldc)
+        {
+            double th = 0.0;
+            if (e < nv)
+                th = (pinned && e < NT) ? sm.cf[QD_VBAR + e] : vv[e];
+            else if (e == L.aff)
+                th = 1.0;
+            theta[e] = th;
+        }
+    }
+    __syncthreads();
+
+    // ---- F_k theta* for every elimination knot: one warp per (knot, row), lanes over the columns ---------------------
+    for (int e = warp; e < Nc * NJ; e += nwarps)
+    {
+        const int k = e >> 3, a = e & 7;
+        const double* fr = c.ws + (size_t)k * L.stage + L.wsF + a * L.ldc;
+        double acc = 0.0;
+        for (int l = lane; l < L.ldc; l += 32)
+            acc = fma(fr[l], theta[l], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0)
+            fth[e] = acc;
+    }
+    __syncthreads();
+    if (warp != 0)
+        return;
+
+    // ---- warp 0: forward rollout and outputs ----------------------------------------------------------------------
+    double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
+    double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
+    if (lane == 0)
+    {
+        status[inst] = stat;
+        n_factor[inst] = 1;
+        n_solve[inst] = 1;
+    }
+    if (stat != VSMPC_STATUS_SOLVED)
+        return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
+    cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st);
+}
+
+static size_t cw_smem_bytes(const DeviceConfig& cfg)
+{
+    return sizeof(CwSmem) + (size_t)cw_layout(cfg).total * sizeof(double);
+}
+
+bool condensed_wide_supported(const DeviceConfig& cfg)
+{
+    if (cfg.nblk < 1 || cfg.N > MAX_ITER || cfg.Nc < 1)
+        return false;
+    const CwLayout L = cw_layout(cfg);
+    return L.G <= CW_MAXG && cw_smem_bytes(cfg) <= (size_t)CW_SMEM_LIMIT;
+}
+
+size_t condensed_wide_ws_doubles(const DeviceConfig& cfg)
+{
+    return (size_t)cfg.Nc * cw_layout(cfg).stage;
+}
+
+size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
+{
+    (void)cfg;
+    return 4;   // no global scratch beyond the workspace stacks
+}
+
+cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
+                                     double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
+                                     int want_z, cudaStream_t s)
+{
+    static bool attr_set[64] = {};
+    const cudaError_t e = ensure_dynamic_smem(qp_condensed_wide_kernel, CW_SMEM_LIMIT, attr_set);
+    if (e != cudaSuccess)
+        return e;
+    const CwLayout L = cw_layout(h_cfg);
+    qp_condensed_wide_kernel<<<B, 32 * (1 + L.G), cw_smem_bytes(h_cfg), s>>>(
+        h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, condensed_wide_ws_doubles(h_cfg),
+        condensed_wide_scratch_doubles(h_cfg), want_z);
+    return cudaGetLastError();
+}
+
+} // namespace vsmpc

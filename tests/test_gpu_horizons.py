@@ -1,6 +1,7 @@
 """Horizon variants (BASELINE.json configs[3]: long-horizon variable-sampling variants, 2-4x the reference knot count
 with a coarse tail dt) and model options, every solver against the oracle.  The default solver routes itself:
-condensed kernel where the horizon has <= 6 throttle blocks, otherwise the generic dense kernel."""
+condensed kernel where the horizon has <= 6 throttle blocks, the condensed kernel with several column warps
+(vsmpc_qp_condensed_wide.cu) for longer horizons, the generic dense kernel beyond that."""
 import numpy as np
 import pytest
 
@@ -94,6 +95,46 @@ def test_condensed_schedule_edge_cases(variant):
         assert (status == 0).all(), status
         for i, o in enumerate(oracles):
             if tick == 2:
+                o.mpc.vectorConstraints[2].counter = ratio - 1
+            o.update(per)
+            zo = o.solve()
+            assert np.abs(z[i] - zo).max() / max(1.0, np.abs(zo).max()) < 1e-6, (variant, tick, i)
+            row = o.output_row()
+            assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
+    mpc.close()
+
+
+# long horizons on the default solver (several column warps): 4x knots with 35 and 21 throttle blocks, a fully
+# controlled long horizon (no held block), pinned and released ticks
+LONG = [
+    dict(nIter=68, nIterSmall=14, controlHorizon=48),
+    dict(nIter=68, nIterSmall=28, controlHorizon=48, periodMPCLargeSteps=0.2),
+    dict(nIter=40, nIterSmall=10, controlHorizon=40),
+]
+
+
+@pytest.mark.parametrize("variant", range(len(LONG)))
+def test_long_horizon_default_solver(variant):
+    params = LONG[variant]
+    B = 3
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=71 + variant, perturbed=True, near_bound_fraction=0.4)
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=0, full_solution=True)
+    mpc.configure(nom)
+    oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
+    ratio = oracles[0].mpc.vectorConstraints[2].ratio
+    for tick in range(2):
+        if tick == 1:       # force a released tick
+            mpc.debug_set_counters(-1, ratio - 1)
+        mpc.update(per)
+        mpc.solveMPC()
+        z = mpc.getSolution()
+        out, status = mpc.get_output()
+        assert (status == 0).all(), status
+        for i, o in enumerate(oracles):
+            if tick == 1:
                 o.mpc.vectorConstraints[2].counter = ratio - 1
             o.update(per)
             zo = o.solve()
