@@ -136,7 +136,12 @@ def run_ours(args):
     K, Wm = args.steps, args.warmup
     n_sets = 4
     nom_pack, jp, packs = make_workload(B, 20251002 + rank, n_sets)
-    mpc = bat.BatchedVSMPC(B, None, load_traj(), device=local_rank, solver=args.solver)
+    params = None
+    if args.horizon:     # BASELINE configs[3]: long-horizon variant (the default run is configs[1], reference horizon)
+        hN, hNs, hNc = [int(x) for x in args.horizon.split(",")]
+        params = dict(nIter=hN, nIterSmall=hNs, controlHorizon=hNc)
+        args.no_latency, args.rollout_ticks, args.no_cpu = True, 0, True
+    mpc = bat.BatchedVSMPC(B, params, load_traj(), device=local_rank, solver=args.solver)
     stream = torch.cuda.Stream(device=dev)   # an explicit stream: events and kernels share it
     torch.cuda.set_stream(stream)
     mpc.set_stream(stream.cuda_stream)
@@ -261,19 +266,20 @@ def run_ours(args):
     tf_dmma = ctypes.c_double(0.0)
     lib.vsmpc_microbench_fp64(local_rank, 1, ctypes.byref(tf_dmma))
     nf_mean, ns_mean = float(nf.mean()), float(ns.mean())
-    F, parts = flops_per_solve(30, 12, 17, nf_mean, ns_mean)
+    F, parts = flops_per_solve(30, 12, params["nIter"] if params else 17, nf_mean, ns_mean)
     k2_s_per_launch = k2_ms * 1e-3 / K
     achieved = F * B / k2_s_per_launch / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not params:     # the committed capture is of the reference-horizon kernel
         try:
             traffic = json.load(open(tpath)).get("qp_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
     roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                 "frac": achieved / tf.value if tf.value > 0 else None, "traffic": traffic,
-                "kernel": {0: "qp_condensed_kernel", 1: "qp_generic_kernel", 2: "qp_structured_kernel"}[args.solver],
+                "kernel": ("qp_condensed_wide_kernel" if params and args.solver == 0 else
+                           {0: "qp_condensed_kernel", 1: "qp_generic_kernel", 2: "qp_structured_kernel"}[args.solver]),
                 "peak_source": "DFMA microbenchmark on this device in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "dmma_peak_tflops": tf_dmma.value,
                 "flops_per_solve": F, "n_factor_mean": nf_mean, "n_solve_mean": ns_mean,
@@ -286,7 +292,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: batch of 1024 independent MPC solves per GPU, reference horizon "
+        "config": {"workload": ("configs[3]: long-horizon variant, %d knots (%d fine), control horizon %d, batch per GPU"
+                                % (hN, hNs, hNc)) if params else
+                               "configs[1]: batch of 1024 independent MPC solves per GPU, reference horizon "
                                "(17 knots, 7 fine + 10 coarse), perturbed states (SURVEY §8d Config 2)",
                    "instances_per_gpu": B, "n_var": mpc.n_var, "n_con": mpc.n_con,
                    "l2": "value leg: flushed (256 MiB memset) between timed steps; e2e leg: host inputs cycle through > 126 MB",
@@ -420,6 +428,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--solver", type=int, default=0)
+    ap.add_argument("--horizon", default="", help="nIter,nIterSmall,controlHorizon of a horizon variant (configs[3]); "
+                                                  "default: the reference horizon")
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--rollout-ticks", type=int, default=40, help="ticks of the device-resident closed-loop leg (0: skip)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-instance latency leg")

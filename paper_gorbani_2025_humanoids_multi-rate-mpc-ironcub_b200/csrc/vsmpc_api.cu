@@ -40,6 +40,7 @@ cudaError_t launch_qp_structured(const DeviceConfig* d_cfg, const DeviceConfig& 
                                  int* n_factor, int* n_solve, int want_z, cudaStream_t s);
 bool condensed_supported(const DeviceConfig& cfg);
 int condensed_phase_clocks(long long* host, int n);
+int condensed_wide_phase_clocks(long long* host, int n);
 size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
@@ -55,6 +56,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
 using namespace vsmpc;
 
 constexpr int SOLVER_WIDE = 3;   // internal: chosen by the default solver for long horizons
+static int g_last_qp_solver = 0; // development (vsmpc_debug_phase_clocks): which kernel stamped its clocks last
 
 struct vsmpc_handle
 {
@@ -648,7 +650,8 @@ int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve)
 
 int vsmpc_debug_phase_clocks(long long* clocks_host, int n_instances)
 {
-    return condensed_phase_clocks(clocks_host, n_instances);
+    return g_last_qp_solver == SOLVER_WIDE ? condensed_wide_phase_clocks(clocks_host, n_instances)
+                                           : condensed_phase_clocks(clocks_host, n_instances);
 }
 
 int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter)
@@ -682,6 +685,7 @@ static int solve_launch(vsmpc_handle* h)
         CK(cudaStreamWaitEvent(h->stream, h->ev_out[h->out_idx], 0));
         h->out_pending = false;
     }
+    g_last_qp_solver = h->solver;
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
                                h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));

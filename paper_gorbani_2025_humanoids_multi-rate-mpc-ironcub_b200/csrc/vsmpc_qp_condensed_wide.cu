@@ -12,11 +12,14 @@
 //   updates of Om (dynamic shared memory, odd leading dimension) need a named barrier among them;
 // * the rank-8 down-dates of Om are stacked in the workspace and contracted once by all warps with
 //   mma.sync.m8n8k4.f64 over the upper 8 x 8 tiles;
-// * the reduced Hessian H_r (<= 183 x 183, in place in Om) is inverted by block-wide exchange pivots (x_q <-> y_q in
-//   y = H_r x); the Goldfarb-Idnani dual active set then keeps the SAME matrix as the principal pivot transform of H_r
-//   over the free variables: adding a bound to / dropping it from the working set is one more pivot on that index, and
-//   column p of the matrix holds both the primal direction (free rows) and the multiplier direction (active rows) —
-//   no working-set inverse, no back-solves; one variable per thread, three block barriers per iteration;
+// * the reduced Hessian H_r (in place in Om) is inverted by exchange pivots (x_q <-> y_q in y = H_r x); the
+//   Goldfarb-Idnani dual active set then keeps the SAME matrix as the principal pivot transform of H_r over the free
+//   variables: adding a bound to / dropping it from the working set is one more pivot on that index, and column p of
+//   the matrix holds both the primal direction (free rows) and the multiplier direction (active rows) — no working-set
+//   inverse, no back-solves; one variable per thread.  A pivot is a rank-1 change T' = T - (T[:,q] + e_q)(T[q,:] - e_q)'/d:
+//   pivots are DEFERRED as rows of two 8 x nv stacks (entries of T are read through the stacks) and applied eight at a
+//   time as one rank-8 update of the whole matrix on the FP64 tensor cores, which cuts the shared-memory traffic per
+//   pivot by eight;
 // * F_k theta* by all warps, forward rollout by warp 0.
 #include "vsmpc_condensed_core.cuh"
 
@@ -26,6 +29,7 @@ namespace vsmpc
 constexpr int CW_MAXG = 6;                          // column warps
 constexpr int CW_MAXTHREADS = 32 * (1 + CW_MAXG);   // 224
 constexpr int CW_SMEM_LIMIT = 227 * 1024;           // opt-in shared memory per CTA on sm_100
+constexpr int CW_MD = 8;                            // pivots deferred before one rank-8 update of the matrix
 
 struct alignas(16) CwSmem
 {
@@ -46,7 +50,8 @@ struct CwLayout
     int nv, aff, D0, nlo, ldo;  // throttle variables, affine column, first held-joint column, order of Om, its ld (odd)
     int nt;                     // 8 x 8 tiles per side of Om
     int wsF, wsH, stage;        // workspace per elimination knot: K [8][26] | F [8][ldc] | H_utheta [8][ldc]
-    int om, fth, theta, vv, grad, rb, total;   // offsets (doubles) in dynamic shared memory
+    int nvp, nvs;               // nv rounded up to 8; stride of the deferred-pivot stacks
+    int om, fth, theta, vv, grad, stk, xref, rb, total;   // offsets (doubles) in dynamic shared memory
 };
 
 __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
@@ -61,6 +66,8 @@ __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
     L.ldc = 32 * L.G;
     L.ldo = L.nlo | 1;
     L.nt = (L.nlo + 7) / 8;
+    L.nvp = (L.nv + 7) & ~7;
+    L.nvs = L.nvp + 4;          // + 4: the tensor-core fragments of the stacks are read without bank conflicts
     L.wsF = NJ * NX;
     L.wsH = L.wsF + NJ * L.ldc;
     L.stage = L.wsH + NJ * L.ldc;
@@ -70,12 +77,21 @@ __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
     L.theta = o;  o += L.ldc;
     L.vv = o;     o += L.nv;
     L.grad = o;   o += L.nv;
+    L.stk = o;    o += 2 * CW_MD * L.nvs;   // deferred pivots: A [8][nvs] then B [8][nvs]
+    L.xref = o;   o += 12 * cfg.NC;
     L.rb = o;     o += 4 * 8;      // two block-reduction buffers: value [8], index [8] each
     L.total = o;
     return L;
 }
 
 using CwCtx = CdCtxT<CwSmem>;
+
+#ifdef VSMPC_PHASE_CLOCKS
+__device__ long long g_wide_clk[4096][16];
+#define WCLK(slot) do { if (threadIdx.x == 0 && inst < 4096) g_wide_clk[inst][slot] = clock64(); } while (0)
+#else
+#define WCLK(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void cw_bar_columns(int n_threads)
 {
@@ -85,7 +101,7 @@ __device__ __forceinline__ void cw_bar_columns(int n_threads)
 // propagation of the parameter columns through knot k (Psi'' = Psi' + P'D, Om += D'Psi'' + Psi''D, Psi <- T'Psi'');
 // returns dt B_J' Psi''[:, gc] in bj2.  gc: column of this lane
 __device__ __forceinline__ void w_prop(const CwCtx& c, const CwLayout& L, double* __restrict__ Om,
-                                       const double* __restrict__ qd, int k, bool tail, int gc, double (&s)[NX],
+                                       const double* __restrict__ xref, int k, bool tail, int gc, double (&s)[NX],
                                        double (&bj2)[NJ])
 {
     const DeviceConfig& cfg = c.cfg;
@@ -104,7 +120,7 @@ __device__ __forceinline__ void w_prop(const CwCtx& c, const CwLayout& L, double
         const int rc = ref_col(k, cfg.Ns);
 #pragma unroll
         for (int r = 0; r < 12; ++r)
-            s[r] = fma(-sm.Qd[r], qd[QD_XREF + r * cfg.NC + rc], s[r]);   // tracking gradient of x_{k+1}
+            s[r] = fma(-sm.Qd[r], xref[r * cfg.NC + rc], s[r]);   // tracking gradient of x_{k+1}
     }
     double bv[NT], bd[NJ];
 #pragma unroll
@@ -261,48 +277,81 @@ __device__ __forceinline__ void cw_omega_item(const double* __restrict__ ws, con
     }
 }
 
-// exchange pivot on index q of T = Om[first:nv, first:nv] by the whole block: in (outputs) = T (inputs) the roles of
-// input q and output q are swapped.  Pivoting every index turns H into H^-1; pivoting q again undoes it.  Warp w sweeps
-// rows first + w, first + w + nwarps, ...; lanes over the columns, row q held in registers
-__device__ __forceinline__ bool cw_pivot(double* __restrict__ Om, int ldo, int first, int nv, int q, int warp, int lane,
-                                         int nwarps, int nthr)
+// ---- exchange pivots on T = Om[first:nv, first:nv], deferred ------------------------------------------------------
+// In (outputs) = T (inputs) a pivot on q swaps the roles of input q and output q: pivoting every index turns H into
+// H^-1, pivoting q again undoes it.  T_eff = T0 - sum_{m < M} A[m][:]' B[m][:] with T0 in Om and the M <= 8 pivots
+// since the last flush in the stacks A, B (rows >= M are zero).
+struct CwPiv
 {
-    const double d = Om[q * ldo + q];
+    double* Om;
+    double* As;
+    double* Bs;
+    int ldo, nvs, first, nv, nvp;
+};
+
+__device__ __forceinline__ double cw_teff(const CwPiv& P, int M, int i, int j)
+{
+    double t = P.Om[i * P.ldo + j];
+#pragma unroll
+    for (int m = 0; m < CW_MD; ++m)
+        if (m < M)
+            t = fma(-P.As[m * P.nvs + i], P.Bs[m * P.nvs + j], t);
+    return t;
+}
+
+// T0 -= A'B over all 8 x 8 tiles (mma.sync.m8n8k4.f64: A fragment = -A' (lane l: row l >> 2 of the tile, pivot l & 3),
+// B fragment = B (pivot l & 3, column l >> 2), C fragment = T0 tile (row l >> 2, columns 2 (l & 3) + {0, 1})), then the
+// stacks are cleared
+__device__ __forceinline__ void cw_flush(const CwPiv& P, int& M, int warp, int lane, int nwarps, int nthr)
+{
+    const int nt8 = P.nvp >> 3;
+    const int lr = lane & 3, lc = lane >> 2;
+    for (int tile = warp; tile < nt8 * nt8; tile += nwarps)
+    {
+        const int ti = tile / nt8, tj = tile - ti * nt8;
+        const int gi = 8 * ti + lc, gj = 8 * tj + 2 * lr;
+        const bool ok0 = gi < P.nv && gj < P.nv, ok1 = gi < P.nv && gj + 1 < P.nv;
+        double c0 = ok0 ? P.Om[gi * P.ldo + gj] : 0.0;
+        double c1 = ok1 ? P.Om[gi * P.ldo + gj + 1] : 0.0;
+#pragma unroll
+        for (int h = 0; h < CW_MD / 4; ++h)
+        {
+            const double a = -P.As[(4 * h + lr) * P.nvs + 8 * ti + lc];
+            const double b = P.Bs[(4 * h + lr) * P.nvs + 8 * tj + lc];
+            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                : "+d"(c0), "+d"(c1)
+                : "d"(a), "d"(b));
+        }
+        if (ok0)
+            P.Om[gi * P.ldo + gj] = c0;
+        if (ok1)
+            P.Om[gi * P.ldo + gj + 1] = c1;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * CW_MD * P.nvs; e += nthr)
+        P.As[e] = 0.0;      // A and B are contiguous
+    __syncthreads();
+    M = 0;
+}
+
+// pivot on q as the rank-1 change T' = T - (T[:, q] + e_q)(T[q, :] - e_q)' / T[q][q]: thread e appends its entries of the
+// two vectors to the stacks; one barrier, plus the flush every CW_MD pivots
+__device__ __forceinline__ bool cw_pivot(const CwPiv& P, int& M, int q, int warp, int lane, int nwarps, int nthr)
+{
+    const int e = threadIdx.x;
+    const double d = cw_teff(P, M, q, q);
     const double dinv = 1.0 / d;
-    const double* rowq = Om + q * ldo;
-    double rq[CW_MAXG];
-#pragma unroll
-    for (int cc = 0; cc < CW_MAXG; ++cc)
+    if (e >= P.first && e < P.nv)
     {
-        const int j = first + lane + 32 * cc;
-        rq[cc] = (j < nv && j != q) ? rowq[j] : 0.0;
-    }
-    for (int i = first + warp; i < nv; i += nwarps)
-    {
-        if (i == q)
-            continue;
-        double* rowi = Om + i * ldo;
-        const double f = rowi[q] * dinv;
-#pragma unroll
-        for (int cc = 0; cc < CW_MAXG; ++cc)
-        {
-            const int j = first + lane + 32 * cc;
-            if (j < nv && j != q)
-                rowi[j] = fma(-f, rq[cc], rowi[j]);
-        }
+        const double u = cw_teff(P, M, e, q), v = cw_teff(P, M, q, e);
+        const double one = e == q ? 1.0 : 0.0;
+        P.As[M * P.nvs + e] = (u + one) * dinv;
+        P.Bs[M * P.nvs + e] = v - one;
     }
     __syncthreads();
-    for (int e = first + (int)threadIdx.x; e < nv; e += nthr)
-    {
-        if (e != q)
-        {
-            Om[q * ldo + e] *= -dinv;
-            Om[e * ldo + q] *= dinv;
-        }
-    }
-    if (threadIdx.x == 0)
-        Om[q * ldo + q] = dinv;
-    __syncthreads();
+    ++M;
+    if (M == CW_MD)
+        cw_flush(P, M, warp, lane, nwarps, nthr);
     return (d > 0.0) && isfinite(d);
 }
 
@@ -351,6 +400,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     double* theta = dyn + L.theta;
     double* vv = dyn + L.vv;
     double* grad = dyn + L.grad;
+    const CwPiv P{Om, dyn + L.stk, dyn + L.stk + CW_MD * L.nvs, L.ldo, L.nvs, 0, L.nv, L.nvp};
+    double* xref = dyn + L.xref;
     double* rbA = dyn + L.rb;
     double* rbB = dyn + L.rb + 16;
 
@@ -364,6 +415,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     const int gc = (warp - 1) * 32 + lane;     // column of this lane (warps >= 1)
     CwCtx c{cfg, sm, ws_all + (size_t)inst * ws_stride, lane, L.D0, held ? Nc - 1 : -1};
 
+    WCLK(0);
     // ---- stage the QP data; finiteness gate ----------------------------------------------------------------------
     bool fin = true;
     for (int e = threadIdx.x; e < cfg.qd_stride; e += nthr)
@@ -372,9 +424,13 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         fin = fin && isfinite(v);
         if (e < CCF)
             sm.cf[e] = v;
+        else if (e >= QD_XREF && e < QD_XREF + 12 * cfg.NC)
+            xref[e - QD_XREF] = v;
     }
     for (int e = threadIdx.x; e < L.nlo * ldo; e += nthr)
         Om[e] = 0.0;
+    for (int e = threadIdx.x; e < 2 * CW_MD * L.nvs; e += nthr)
+        P.As[e] = 0.0;
     if (threadIdx.x < NX)
         sm.Qd[threadIdx.x] = cfg.Qd[threadIdx.x];
     if (threadIdx.x < NJ)
@@ -386,6 +442,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     const bool all_fin = __syncthreads_and(fin);
     int stat = all_fin ? VSMPC_STATUS_SOLVED : VSMPC_STATUS_NUMERICAL;
 
+    WCLK(1);
     // ---- factorisation: warp 0 = P recursion, warps 1..G = parameter columns, one knot apart ----------------------
     double y[NX];   // warp 0: row `lane` of P ; column warps: column gc of Psi
 #pragma unroll
@@ -433,7 +490,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             bool down = false;
             if (tbk != TK_SCHUR)
             {
-                w_prop(c, L, Om, qd, kb, tail, gc, y, hut);
+                w_prop(c, L, Om, xref, kb, tail, gc, y, hut);
                 if (tbk == TK_PROP)
                 {
                     if (isD)
@@ -476,6 +533,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         }
         __syncthreads();
     }
+    WCLK(2);
     if (warp == 0 && lane == 0)
         sm.flags[0] = ok ? 0 : 1;
     // Psi_0' x0 while the column warps still hold their columns
@@ -492,10 +550,16 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         for (int ti = 0; ti < L.nt; ++ti)
             for (int tj0 = ti; tj0 < L.nt; tj0 += 4, ++item)
                 if (item % nwarps == warp)
-                    cw_omega_item(c.ws, L, NJ * Nc, Om, ti, tj0, lane);
+                {
+                    // columns of tile row ti are zero in the stacks of the knots whose throttle block comes before
+                    // them (block b enters the value function at the last knot it acts on): staircase contraction
+                    const int k_end = (8 * ti + 7 >= nv) ? Nc : min(Nc, 2 * ti + cfg.Ns + 1);
+                    cw_omega_item(c.ws, L, NJ * k_end, Om, ti, tj0, lane);
+                }
     }
     __syncthreads();
 
+    WCLK(3);
     // ---- reduced QP in the throttle variables: gradient, Hessian (in place in Om), inverse ---------------------------
     const bool pinned = sm.cf[QD_PINNED] != 0.0;
     const int first = pinned ? NT : 0;
@@ -525,13 +589,39 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         }
         __syncthreads();
     }
-    // inverse of H_r = Om[first:nv, first:nv] in place: exchange pivot on every index
+    // equilibration to a unit diagonal (v = S v~, S = diag(H_r)^-1/2): the pivots stay O(1), which the deferred rank-1
+    // form needs (it rebuilds the pivot row / column by subtraction, exact only up to eps x max(d, 1 / d))
+    double S_e = 1.0;
+    {
+        const int e = threadIdx.x;
+        if (e >= first && e < nv)
+        {
+            const double hd = Om[e * ldo + e];
+            S_e = (hd > 0.0 && isfinite(hd)) ? rsqrt(hd) : 1.0;
+            vv[e] = S_e;
+            grad[e] *= S_e;
+        }
+        __syncthreads();
+        for (int i = first + warp; i < nv; i += nwarps)
+        {
+            const double si = vv[i];
+            for (int j = first + lane; j < nv; j += 32)
+                Om[i * ldo + j] *= si * vv[j];
+        }
+        __syncthreads();
+    }
+    // inverse of the scaled H_r = Om[first:nv, first:nv] in place: exchange pivot on every index
+    CwPiv Pv = P;
+    Pv.first = first;
+    int M = 0;
     bool okG = true;
     for (int p = first; p < nv; ++p)
-        okG = cw_pivot(Om, ldo, first, nv, p, warp, lane, nwarps, nthr) && okG;
+        okG = cw_pivot(Pv, M, p, warp, lane, nwarps, nthr) && okG;
+    if (M > 0)
+        cw_flush(Pv, M, warp, lane, nwarps, nthr);
     if (sm.flags[0] != 0 || !okG)
         stat = stat == VSMPC_STATUS_SOLVED ? VSMPC_STATUS_NUMERICAL : stat;
-    // unconstrained minimiser v = -G g
+    // unconstrained minimiser v~ = -G g~ (scaled variables); afterwards grad holds the scale factors for all threads
     for (int e = threadIdx.x; e < nv; e += nthr)
     {
         double v = 0.0;
@@ -544,7 +634,12 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         vv[e] = v;
     }
     __syncthreads();
+    double* scl = grad;
+    if (threadIdx.x < nv)
+        scl[threadIdx.x] = S_e;
+    __syncthreads();
 
+    WCLK(4);
     // ---- Goldfarb-Idnani dual active set on the boxes, one variable per thread -----------------------------------------
     // T = Om[first:nv, first:nv] is kept as the principal pivot transform of H_r over the free set F (W = working set):
     // (v_F, y_W) = T (y_F, v_W) with y = H_r v = -g - sum_a s_a lambda_a e_a.  For a violated free p with sign s, raising
@@ -554,6 +649,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         const int e = threadIdx.x;
         const bool isvar = e >= first && e < nv;
         const double tol = 1e-10;
+        const double lo_e = lo / S_e, up_e = up / S_e;      // bounds of the scaled variable
         int act = 0;            // 0 free, +1 / -1 active at the upper / lower bound
         double lam_e = 0.0;
         int iters = 0;
@@ -564,15 +660,15 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             if (isvar && act == 0)
             {
                 const double v = vv[e];
-                viol = fmax(fmax(v - up, lo - v), 0.0);
+                viol = S_e * fmax(fmax(v - up_e, lo_e - v), 0.0);     // measured in the unscaled variable
             }
             int p;
             const double best = cw_block_best<true>(viol, rbA, warp, lane, nwarps, p);
             if (!(best > tol))
                 break;
-            const double vp0 = vv[p];
-            const double s = (vp0 - up > lo - vp0) ? 1.0 : -1.0;
-            const double bound = s > 0 ? up : lo;
+            const double vp0 = vv[p], isp = 1.0 / scl[p];
+            const double s = (vp0 - up * isp > lo * isp - vp0) ? 1.0 : -1.0;
+            const double bound = (s > 0 ? up : lo) * isp;
             double lam_p = 0.0;
             while (true)
             {
@@ -582,8 +678,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                     fail = true;
                     break;
                 }
-                const double c_e = isvar ? Om[e * ldo + p] : 0.0;
-                const double zp = Om[p * ldo + p];
+                const double c_e = isvar ? cw_teff(Pv, M, e, p) : 0.0;
+                const double zp = cw_teff(Pv, M, p, p);
                 const double v_p = vv[p];
                 const double r_e = act != 0 ? -(double)act * s * c_e : 0.0;
                 int drop;
@@ -621,17 +717,27 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                         lam_e = 0.0;
                     }
                 }
-                cw_pivot(Om, ldo, first, nv, q, warp, lane, nwarps, nthr);
+                cw_pivot(Pv, M, q, warp, lane, nwarps, nthr);
                 if (full)
                     break;
             }
         }
+        WCLK(5);
+#ifdef VSMPC_PHASE_CLOCKS
+        if (threadIdx.x == 0 && inst < 4096)
+        {
+            unsigned smid;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_wide_clk[inst][8] = iters;
+            g_wide_clk[inst][12] = smid;
+        }
+#endif
         // theta*: throttle variables, affine 1, held block 0
         if (e < L.ldc)
         {
             double th = 0.0;
             if (e < nv)
-                th = (pinned && e < NT) ? sm.cf[QD_VBAR + e] : vv[e];
+                th = (pinned && e < NT) ? sm.cf[QD_VBAR + e] : (act != 0 ? (act > 0 ? up : lo) : S_e * vv[e]);
             else if (e == L.aff)
                 th = 1.0;
             theta[e] = th;
@@ -640,20 +746,31 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     __syncthreads();
 
     // ---- F_k theta* for every elimination knot: one warp per (knot, row), lanes over the columns ---------------------
-    for (int e = warp; e < Nc * NJ; e += nwarps)
+    for (int e0 = 4 * warp; e0 < Nc * NJ; e0 += 4 * nwarps)
     {
-        const int k = e >> 3, a = e & 7;
-        const double* fr = c.ws + (size_t)k * L.stage + L.wsF + a * L.ldc;
-        double acc = 0.0;
-        for (int l = lane; l < L.ldc; l += 32)
-            acc = fma(fr[l], theta[l], acc);
+        // four (knot, row) items per step: their loads are in flight together
+        double acc[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0)
-            fth[e] = acc;
+        for (int u = 0; u < 4; ++u)
+        {
+            const int e = min(e0 + u, Nc * NJ - 1);
+            const double* fr = c.ws + (size_t)(e >> 3) * L.stage + L.wsF + (e & 7) * L.ldc;
+            acc[u] = 0.0;
+            for (int l = lane; l < L.ldc; l += 32)
+                acc[u] = fma(fr[l], theta[l], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            if (lane == 0 && e0 + u < Nc * NJ)
+                fth[e0 + u] = acc[u];
+        }
     }
     __syncthreads();
+    WCLK(6);
     if (warp != 0)
         return;
 
@@ -669,6 +786,17 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     if (stat != VSMPC_STATUS_SOLVED)
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
     cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st);
+    WCLK(7);
+}
+
+int condensed_wide_phase_clocks(long long* host, int n)
+{
+#ifdef VSMPC_PHASE_CLOCKS
+    return cudaMemcpyFromSymbol(host, g_wide_clk, sizeof(long long) * 16 * (n < 4096 ? n : 4096)) == cudaSuccess ? 0 : 2;
+#else
+    (void)host; (void)n;
+    return 3;
+#endif
 }
 
 static size_t cw_smem_bytes(const DeviceConfig& cfg)
