@@ -89,8 +89,10 @@ using CwCtx = CdCtxT<CwSmem>;
 #ifdef VSMPC_PHASE_CLOCKS
 __device__ long long g_wide_clk[4096][16];
 #define WCLK(slot) do { if (threadIdx.x == 0 && inst < 4096) g_wide_clk[inst][slot] = clock64(); } while (0)
+#define WSUB(acc, t0) do { const long long t1__ = clock64(); acc += t1__ - t0; t0 = t1__; } while (0)
 #else
 #define WCLK(slot) do { } while (0)
+#define WSUB(acc, t0) do { } while (0)
 #endif
 
 __device__ __forceinline__ void cw_bar_columns(int n_threads)
@@ -383,7 +385,10 @@ __device__ __forceinline__ double cw_block_best(double v, double* __restrict__ r
     return best;
 }
 
-__global__ void __launch_bounds__(CW_MAXTHREADS, 2)
+// MINB = 2: registers capped for several CTAs per SM (short "long" horizons, Om small); MINB = 1: the register file
+// of the SM to one CTA (Om fills the shared memory anyway), no spills
+template <int MINB>
+__global__ void __launch_bounds__(CW_MAXTHREADS, MINB)
 qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                          double* __restrict__ ws_all, double* __restrict__ scratch_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
@@ -451,10 +456,14 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     const double qd_lane = lane < NX ? sm.Qd[lane] : 0.0;
     bool ok = true;
     const int n_it = c.kS < 0 ? N + 1 : (N - 1 - c.kS) + 3 + c.kS + 1;
+    long long wk0 = 0, wk1 = 0;
+    (void)wk0; (void)wk1;
     for (int t = 0; t < n_it; ++t)
     {
         int ta, ka, tbk, kb;
         cd_schedule(t, N, c.kS, ta, ka, tbk, kb);
+        long long tclk = clock64();
+        (void)tclk;
         if (warp == 0)
         {
             if (ta != TK_NONE)
@@ -464,7 +473,10 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                 double2 own;
                 const bool elim = ta == TK_STAGE && !(held && ka >= Nc - 1);
                 if (ta != TK_SCHUR)
+                {
                     a_prop(c, ka, elim, y, qd_lane, hux, own);
+                    WSUB(wk0, tclk);
+                }
                 else
                 {
                     // Schur step of the held joint block: H_ux = Psi_T[:, d]' (published by the column warps),
@@ -479,6 +491,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                 __syncwarp();
                 if (elim || ta == TK_SCHUR)
                     ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * L.stage) && ok;
+                WSUB(wk1, tclk);
             }
         }
         else if (tbk != TK_NONE)
@@ -491,6 +504,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             if (tbk != TK_SCHUR)
             {
                 w_prop(c, L, Om, xref, kb, tail, gc, y, hut);
+                WSUB(wk0, tclk);
                 if (tbk == TK_PROP)
                 {
                     if (isD)
@@ -520,6 +534,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                 }
                 const bool schur = tbk == TK_SCHUR;
                 w_downdate(sl, L, gc, y, hut, c.ws + (size_t)kb * L.stage, schur && isD);
+                WSUB(wk1, tclk);
                 if (schur && gc < L.nlo)
                 {
 #pragma unroll
@@ -534,6 +549,14 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         __syncthreads();
     }
     WCLK(2);
+#ifdef VSMPC_PHASE_CLOCKS
+    if (lane == 0 && inst < 4096 && (warp == 0 || warp == 1 || warp == nwarps - 1))
+    {
+        const int b = warp == 0 ? 9 : (warp == 1 ? 13 : 10);
+        g_wide_clk[inst][b] = wk0;
+        g_wide_clk[inst][b == 13 ? 14 : b + 2] = wk1;     // 9/11: warp 0; 10/12..: see the tool
+    }
+#endif
     if (warp == 0 && lane == 0)
         sm.flags[0] = ok ? 0 : 1;
     // Psi_0' x0 while the column warps still hold their columns
@@ -729,7 +752,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             unsigned smid;
             asm("mov.u32 %0, %%smid;" : "=r"(smid));
             g_wide_clk[inst][8] = iters;
-            g_wide_clk[inst][12] = smid;
+            g_wide_clk[inst][15] = smid;
         }
 #endif
         // theta*: throttle variables, affine 1, held block 0
@@ -827,14 +850,22 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
                                      int want_z, cudaStream_t s)
 {
-    static bool attr_set[64] = {};
-    const cudaError_t e = ensure_dynamic_smem(qp_condensed_wide_kernel, CW_SMEM_LIMIT, attr_set);
+    static bool attr_set2[64] = {}, attr_set1[64] = {};
+    const CwLayout L = cw_layout(h_cfg);
+    const size_t smem = cw_smem_bytes(h_cfg);
+    const bool one_cta = 2 * smem > (size_t)CW_SMEM_LIMIT;    // shared memory already limits the SM to one CTA
+    const cudaError_t e = one_cta ? ensure_dynamic_smem(qp_condensed_wide_kernel<1>, CW_SMEM_LIMIT, attr_set1)
+                                  : ensure_dynamic_smem(qp_condensed_wide_kernel<2>, CW_SMEM_LIMIT, attr_set2);
     if (e != cudaSuccess)
         return e;
-    const CwLayout L = cw_layout(h_cfg);
-    qp_condensed_wide_kernel<<<B, 32 * (1 + L.G), cw_smem_bytes(h_cfg), s>>>(
-        h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, condensed_wide_ws_doubles(h_cfg),
-        condensed_wide_scratch_doubles(h_cfg), want_z);
+    if (one_cta)
+        qp_condensed_wide_kernel<1><<<B, 32 * (1 + L.G), smem, s>>>(
+            h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, condensed_wide_ws_doubles(h_cfg),
+            condensed_wide_scratch_doubles(h_cfg), want_z);
+    else
+        qp_condensed_wide_kernel<2><<<B, 32 * (1 + L.G), smem, s>>>(
+            h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, condensed_wide_ws_doubles(h_cfg),
+            condensed_wide_scratch_doubles(h_cfg), want_z);
     return cudaGetLastError();
 }
 
