@@ -243,7 +243,7 @@ __device__ __forceinline__ void cw_omega_item(const double* __restrict__ ws, con
 #pragma unroll
     for (int t = 0; t < 4; ++t)
         colb[t] = 8 * min(tj0 + t, L.nt - 1) + lc;
-#pragma unroll 4
+#pragma unroll 8
     for (int r0 = 0; r0 < n_rows; r0 += 4)
     {
         const int r = r0 + lr;
@@ -306,28 +306,47 @@ __device__ __forceinline__ double cw_teff(const CwPiv& P, int M, int i, int j)
 // stacks are cleared
 __device__ __forceinline__ void cw_flush(const CwPiv& P, int& M, int warp, int lane, int nwarps, int nthr)
 {
-    const int nt8 = P.nvp >> 3;
+    const int nt8 = P.nvp >> 3, ngrp = (nt8 + 3) >> 2;
     const int lr = lane & 3, lc = lane >> 2;
-    for (int tile = warp; tile < nt8 * nt8; tile += nwarps)
+    // one work item = tile row ti, four tile columns: their loads and tensor-core instructions overlap
+    for (int item = warp; item < nt8 * ngrp; item += nwarps)
     {
-        const int ti = tile / nt8, tj = tile - ti * nt8;
-        const int gi = 8 * ti + lc, gj = 8 * tj + 2 * lr;
-        const bool ok0 = gi < P.nv && gj < P.nv, ok1 = gi < P.nv && gj + 1 < P.nv;
-        double c0 = ok0 ? P.Om[gi * P.ldo + gj] : 0.0;
-        double c1 = ok1 ? P.Om[gi * P.ldo + gj + 1] : 0.0;
+        const int ti = item / ngrp, tj0 = 4 * (item - ti * ngrp);
+        const int gi = 8 * ti + lc;
+        double a[CW_MD / 4];
 #pragma unroll
         for (int h = 0; h < CW_MD / 4; ++h)
+            a[h] = -P.As[(4 * h + lr) * P.nvs + gi];
+        double c0[4], c1[4], b[4][CW_MD / 4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
         {
-            const double a = -P.As[(4 * h + lr) * P.nvs + 8 * ti + lc];
-            const double b = P.Bs[(4 * h + lr) * P.nvs + 8 * tj + lc];
-            asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                : "+d"(c0), "+d"(c1)
-                : "d"(a), "d"(b));
+            const int tj = min(tj0 + t, nt8 - 1);
+            const int gj = 8 * tj + 2 * lr;
+            const bool on = tj0 + t < nt8 && gi < P.nv;
+            c0[t] = (on && gj < P.nv) ? P.Om[gi * P.ldo + gj] : 0.0;
+            c1[t] = (on && gj + 1 < P.nv) ? P.Om[gi * P.ldo + gj + 1] : 0.0;
+#pragma unroll
+            for (int h = 0; h < CW_MD / 4; ++h)
+                b[t][h] = P.Bs[(4 * h + lr) * P.nvs + 8 * tj + lc];
         }
-        if (ok0)
-            P.Om[gi * P.ldo + gj] = c0;
-        if (ok1)
-            P.Om[gi * P.ldo + gj + 1] = c1;
+#pragma unroll
+        for (int h = 0; h < CW_MD / 4; ++h)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                    : "+d"(c0[t]), "+d"(c1[t])
+                    : "d"(a[h]), "d"(b[t][h]));
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+        {
+            const int gj = 8 * (tj0 + t) + 2 * lr;
+            const bool on = tj0 + t < nt8 && gi < P.nv;
+            if (on && gj < P.nv)
+                P.Om[gi * P.ldo + gj] = c0[t];
+            if (on && gj + 1 < P.nv)
+                P.Om[gi * P.ldo + gj + 1] = c1[t];
+        }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < 2 * CW_MD * P.nvs; e += nthr)
@@ -385,10 +404,11 @@ __device__ __forceinline__ double cw_block_best(double v, double* __restrict__ r
     return best;
 }
 
-// MINB = 2: registers capped for several CTAs per SM (short "long" horizons, Om small); MINB = 1: the register file
-// of the SM to one CTA (Om fills the shared memory anyway), no spills
-template <int MINB>
-__global__ void __launch_bounds__(CW_MAXTHREADS, MINB)
+// THREADS / MINB: launch bounds per number of column warps, so that the register cap follows what shared memory allows
+// anyway (<96, 4>: two column warps, 168 registers; <128, 2> and <224, 1>: 255 registers) — the column warps keep a Psi
+// column plus three 8-vectors in registers, and spills there sit on the critical path of every knot
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                          double* __restrict__ ws_all, double* __restrict__ scratch_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
@@ -769,21 +789,31 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     __syncthreads();
 
     // ---- F_k theta* for every elimination knot: one warp per (knot, row), lanes over the columns ---------------------
-    for (int e0 = 4 * warp; e0 < Nc * NJ; e0 += 4 * nwarps)
+    constexpr int FB = 8;     // (knot, row) items per step: their loads are in flight together
+    for (int e0 = FB * warp; e0 < Nc * NJ; e0 += FB * nwarps)
     {
-        // four (knot, row) items per step: their loads are in flight together
-        double acc[4];
+        double acc[FB];
+        const double* fr[FB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < FB; ++u)
         {
             const int e = min(e0 + u, Nc * NJ - 1);
-            const double* fr = c.ws + (size_t)(e >> 3) * L.stage + L.wsF + (e & 7) * L.ldc;
+            fr[u] = c.ws + (size_t)(e >> 3) * L.stage + L.wsF + (e & 7) * L.ldc + lane;
             acc[u] = 0.0;
-            for (int l = lane; l < L.ldc; l += 32)
-                acc[u] = fma(fr[l], theta[l], acc[u]);
+        }
+        for (int l = 0; l < L.ldc; l += 32)
+        {
+            const double th = theta[l + lane];
+            double v[FB];
+#pragma unroll
+            for (int u = 0; u < FB; ++u)
+                v[u] = fr[u][l];
+#pragma unroll
+            for (int u = 0; u < FB; ++u)
+                acc[u] = fma(v[u], th, acc[u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < FB; ++u)
         {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
@@ -850,22 +880,32 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
                                      int want_z, cudaStream_t s)
 {
-    static bool attr_set2[64] = {}, attr_set1[64] = {};
+    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
     const CwLayout L = cw_layout(h_cfg);
     const size_t smem = cw_smem_bytes(h_cfg);
-    const bool one_cta = 2 * smem > (size_t)CW_SMEM_LIMIT;    // shared memory already limits the SM to one CTA
-    const cudaError_t e = one_cta ? ensure_dynamic_smem(qp_condensed_wide_kernel<1>, CW_SMEM_LIMIT, attr_set1)
-                                  : ensure_dynamic_smem(qp_condensed_wide_kernel<2>, CW_SMEM_LIMIT, attr_set2);
-    if (e != cudaSuccess)
-        return e;
-    if (one_cta)
-        qp_condensed_wide_kernel<1><<<B, 32 * (1 + L.G), smem, s>>>(
-            h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, condensed_wide_ws_doubles(h_cfg),
-            condensed_wide_scratch_doubles(h_cfg), want_z);
+    const size_t wsd = condensed_wide_ws_doubles(h_cfg), scd = condensed_wide_scratch_doubles(h_cfg);
+    cudaError_t e;
+    if (L.G <= 2)
+    {
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
+            return e;
+        qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, scratch, z, st, out_rows, status,
+                                                                       n_factor, n_solve, wsd, scd, want_z);
+    }
+    else if (L.G == 3)
+    {
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
+            return e;
+        qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, scratch, z, st, out_rows, status,
+                                                                        n_factor, n_solve, wsd, scd, want_z);
+    }
     else
-        qp_condensed_wide_kernel<2><<<B, 32 * (1 + L.G), smem, s>>>(
-            h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, condensed_wide_ws_doubles(h_cfg),
-            condensed_wide_scratch_doubles(h_cfg), want_z);
+    {
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<CW_MAXTHREADS, 1>, CW_SMEM_LIMIT, attr_c)) != cudaSuccess)
+            return e;
+        qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, 32 * (1 + L.G), smem, s>>>(
+            h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, wsd, scd, want_z);
+    }
     return cudaGetLastError();
 }
 
