@@ -115,7 +115,8 @@ typedef struct vsmpc_config
     const double* rpy_dot;
     int traj_len;
     int traj_fps;
-    int solver;               /* 0 = default (condensed-throttle Riccati kernel, two warps per instance);
+    int solver;               /* 0 = default (condensed-throttle Riccati kernel: two warps per instance at the reference
+                                 horizon, 1 + G warps for long horizons, generic kernel beyond ~37 throttle blocks);
                                  1 = generic dense variant; 2 = structured one-warp kernel (cross-checks) */
 } vsmpc_config;
 
