@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/<tag>_long_horizon.md from the files a tools/gpu_wide2.sh run left in gpurun_out/ (BASELINE configs[3]).
-usage: ncu_report_wide.py <tag>"""
+usage: ncu_report_wide.py <tag>   (the eight-GPU section of the committed r01f file was appended by hand)"""
 import collections, csv, io, json, os, shutil, subprocess, sys
 
 tag = sys.argv[1]
