@@ -767,6 +767,11 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         }
         WCLK(5);
 #ifdef VSMPC_PHASE_CLOCKS
+        {
+            const int n_act = __syncthreads_count(act != 0);
+            if (threadIdx.x == 0 && inst < 4096)
+                g_wide_clk[inst][14] = n_act;
+        }
         if (threadIdx.x == 0 && inst < 4096)
         {
             unsigned smid;

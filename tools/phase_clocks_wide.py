@@ -26,5 +26,6 @@ tot = clk[:, 7] - clk[:, 0]
 it = clk[:, 8]
 print(f"  total mean {tot.mean():.0f} max {tot.max():.0f}; active-set iterations mean {it.mean():.1f} p90 {np.percentile(it, 90):.0f} max {it.max()}")
 print(f"  recursion work summed over knots: warp 0 a_prop {clk[:, 9].mean():.0f} + a_eliminate {clk[:, 11].mean():.0f}; first column warp "
-      f"w_prop {clk[:, 13].mean():.0f} + w_downdate {clk[:, 14].mean():.0f}; last column warp w_prop {clk[:, 10].mean():.0f} + w_downdate {clk[:, 12].mean():.0f}")
+      f"w_prop {clk[:, 13].mean():.0f}; last column warp w_prop {clk[:, 10].mean():.0f} + w_downdate {clk[:, 12].mean():.0f}")
+print(f"  final working set: mean {clk[:, 14].mean():.1f} p10 {np.percentile(clk[:, 14], 10):.0f} p90 {np.percentile(clk[:, 14], 90):.0f} max {clk[:, 14].max()}")
 print(f"  cycles per active-set iteration: {((clk[:, 5] - clk[:, 4]).sum() / max(it.sum(), 1)):.0f}")
