@@ -124,3 +124,32 @@ def test_rollout_first_pack_matches_host_pack():
     loop.init(st, mass_scale=ms, inertia_scale=isc, thrust_disturbance=dT)
     np.testing.assert_allclose(loop.pack(), P.build_pack(st), rtol=1e-13, atol=1e-13)
     mpc.close()
+
+
+@pytest.mark.gpu
+def test_device_rollout_long_horizon_matches_oracle_loop():
+    """The device-resident loop on a 2x-knot horizon (default solver -> the condensed kernel with several column warps)
+    against the oracle loop: same bounds as the reference horizon, 22 ticks (one throttle release)."""
+    from oracle.plant_surrogate import SurrogateLoop
+    B, n_ticks = 3, 22
+    params = dict(nIter=34, nIterSmall=14, controlHorizon=24)
+    rb, st, ms, isc, dT = make_case(B, seed=23)
+    bat, ro = pkg("batched"), pkg("rollout")
+    traj = load_trajectories()
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj))
+    loop = ro.BatchedRollout(mpc, rb)
+    loop.init(st, mass_scale=ms, inertia_scale=isc, thrust_disturbance=dT)
+    rec = loop.run(n_ticks, record_every=1, use_graph=True)
+    assert (rec[:, :, 14] == 0).all()
+    worst_p = worst_a = worst_t = worst_u = 0.0
+    for i in range(B):
+        o = SurrogateLoop(oracle_plant(rb, st, i, ms[i], isc[i], dT[i]), trajectories=traj, params=params)
+        for t in range(n_ticks):
+            r = o.tick()
+            worst_p = max(worst_p, np.abs(rec[t, i, 0:3] - r[0:3]).max())
+            worst_a = max(worst_a, np.abs(rec[t, i, 3:6] - r[3:6]).max())
+            worst_t = max(worst_t, np.abs(rec[t, i, 6:10] - r[6:10]).max() / 100.0)
+            worst_u = max(worst_u, np.abs(rec[t, i, 10:14] - r[10:14]).max() / 100.0)
+    assert worst_p < 1e-7 and worst_a < 1e-7, (worst_p, worst_a)
+    assert worst_t < 1e-6 and worst_u < 1e-6, (worst_t, worst_u)
+    mpc.close()
