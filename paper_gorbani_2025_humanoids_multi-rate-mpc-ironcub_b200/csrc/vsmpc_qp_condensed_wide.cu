@@ -27,7 +27,7 @@ namespace vsmpc
 {
 
 constexpr int CW_MAXG = 6;                          // column warps
-constexpr int CW_MAXTHREADS = 32 * (1 + CW_MAXG);   // 224
+constexpr int CW_MAXTHREADS = 256;                  // 1 + CW_MAXG warps, rounded up to two warps per SM sub-partition
 constexpr int CW_SMEM_LIMIT = 227 * 1024;           // opt-in shared memory per CTA on sm_100
 constexpr int CW_MD = 8;                            // pivots deferred before one rank-8 update of the matrix
 
@@ -514,7 +514,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                 WSUB(wk1, tclk);
             }
         }
-        else if (tbk != TK_NONE)
+        else if (tbk != TK_NONE && warp <= L.G)   // (a CTA may carry idle warps that only join the block-wide phases)
         {
             CdSlot& sl = sm.slot[kb & 1];
             const bool tail = held && kb >= Nc - 1;
@@ -908,7 +908,9 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<CW_MAXTHREADS, 1>, CW_SMEM_LIMIT, attr_c)) != cudaSuccess)
             return e;
-        qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, 32 * (1 + L.G), smem, s>>>(
+        // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
+        // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
+        qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
             h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, wsd, scd, want_z);
     }
     return cudaGetLastError();
