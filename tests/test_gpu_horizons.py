@@ -110,6 +110,9 @@ LONG = [
     dict(nIter=68, nIterSmall=14, controlHorizon=48),
     dict(nIter=68, nIterSmall=28, controlHorizon=48, periodMPCLargeSteps=0.2),
     dict(nIter=40, nIterSmall=10, controlHorizon=40),
+    dict(nIter=36, nIterSmall=30, controlHorizon=36),     # 7 throttle blocks: a single column warp, nothing held
+    dict(nIter=20, nIterSmall=2, controlHorizon=12),      # 11 throttle blocks behind the shortest fine grid
+    dict(nIter=40, nIterSmall=12, controlHorizon=13),     # 2 throttle blocks, joint block 12 held over 27 knots
 ]
 
 
