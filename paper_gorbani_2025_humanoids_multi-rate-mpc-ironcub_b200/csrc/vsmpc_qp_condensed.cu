@@ -35,7 +35,6 @@ constexpr int WSC_H = NJ * NX + NJ * NL; //                                     
 constexpr int WSC_STAGE = NJ * NX + 2 * NJ * NL; // 720
 
 constexpr int CD_MAXN = 32;   // knots kept in shared memory (dt grid)
-constexpr int LDG = 26;       // leading dimension of the reduced Hessian / its inverse (16-byte aligned rows)
 
 struct alignas(16) CdSmem
 {
@@ -65,49 +64,40 @@ __device__ long long g_phase_clk[4096][16];
 #define SUBCLK(acc, t0) do { } while (0)
 #endif
 
-// Gauss-Jordan inverse of an SPD matrix of order <= 24 in shared memory (leading dimension ld, rows 16-byte aligned),
-// in place, pivots p0..p1-1 (the other rows/columns must be decoupled unit rows); lane l < 24 owns row l
-__device__ __forceinline__ bool gj24(double* __restrict__ S, int ld, int lane, int p0, int p1)
+// lane `mine` publishes its row of T (registers) in shared memory for the warp
+__device__ __forceinline__ void rp_publish(const double (&t)[CD_MAXW], double* __restrict__ rowq, bool mine)
 {
-    bool ok = true;
-    const int l = lane < CD_MAXW ? lane : 0;
-    const double2* rowl = reinterpret_cast<const double2*>(S + l * ld);
-#pragma unroll 1
-    for (int p = p0; p < p1; ++p)
+    if (mine)
     {
-        const double d = S[p * ld + p];
-        const double f = S[l * ld + p];
-        const double2* rowp = reinterpret_cast<const double2*>(S + p * ld);
-        double2 pr[CD_MAXW / 2], ow[CD_MAXW / 2];
+        double2* w2 = reinterpret_cast<double2*>(rowq);
 #pragma unroll
         for (int j = 0; j < CD_MAXW / 2; ++j)
-        {
-            pr[j] = rowp[j];
-            ow[j] = rowl[j];
-        }
-        ok = ok && (d > 0.0) && isfinite(d);
-        const double dinv = 1.0 / d;
-        __syncwarp();
-        if (lane < CD_MAXW)
-        {
-            const bool piv = l == p;
-            const double ff = piv ? -dinv : f * dinv;
-            double2* wr = reinterpret_cast<double2*>(S + l * ld);
-#pragma unroll
-            for (int j = 0; j < CD_MAXW / 2; ++j)
-            {
-                double2 o = ow[j];
-                if (piv)
-                    o = make_double2(0.0, 0.0);
-                o.x = fma(-ff, pr[j].x, o.x);
-                o.y = fma(-ff, pr[j].y, o.y);
-                wr[j] = o;
-            }
-            S[l * ld + p] = piv ? dinv : -ff;
-        }
-        __syncwarp();
+            w2[j] = make_double2(t[2 * j], t[2 * j + 1]);
     }
-    return ok;
+    __syncwarp();
+}
+
+// one exchange pivot on index q (row q published in rowq): lane l < 24 owns row l of T in registers;
+// sgn = +1 if lane l is in the same class as q (both exchanged or both not), -1 otherwise: T[l][q] = sgn T[q][l].
+//   T'[q][q] = 1/d, T'[q][j] = -T[q][j]/d, T'[l][q] = T[l][q]/d, T'[l][j] = T[l][j] - T[l][q] T[q][j]/d
+__device__ __forceinline__ void rp_pivot(double (&t)[CD_MAXW], const double* __restrict__ rowq, int q, int lane, double sgn,
+                                         double dinv)
+{
+    const double f = sgn * rowq[lane < CD_MAXW ? lane : 0] * dinv;
+    const bool isq = lane == q;
+    const double fm = isq ? dinv : f;          // multiplier of row q in this lane's row; lane q: t = 0 - (1/d) row
+    const double2* r2 = reinterpret_cast<const double2*>(rowq);
+#pragma unroll
+    for (int j = 0; j < CD_MAXW / 2; ++j)
+    {
+        const double2 rr = r2[j];
+        t[2 * j] = fma(-fm, rr.x, isq ? 0.0 : t[2 * j]);
+        t[2 * j + 1] = fma(-fm, rr.y, isq ? 0.0 : t[2 * j + 1]);
+    }
+    const double cq = isq ? dinv : f;          // entry of column q
+#pragma unroll
+    for (int j = 0; j < CD_MAXW; ++j)
+        asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q mov.f64 %0, %3; }" : "+d"(t[j]) : "r"(q), "r"(j), "d"(cq));
 }
 
 // ---- warp B --------------------------------------------------------------------------------------------------
@@ -507,13 +497,8 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     __syncthreads();
 
     // ---- warp B: reduced QP in the throttle variables + dual active set ---------------------------------------------
-    // after the factorisation the mailbox slots are dead: G (24 x 25) and the working-set inverse live there
-    double* G = reinterpret_cast<double*>(&sm.slot[0]);
-    double* Minv = G + CD_MAXW * LDG;
-    double* as_r = sm.Hut;
-    double* as_lam = as_r + CD_MAXW;
-    double* as_sgn = as_lam + CD_MAXW;
-    int* as_widx = reinterpret_cast<int*>(as_sgn + CD_MAXW);
+    double* gvec = sm.Hut;                 // gradient of the reduced QP
+    double* rowq = sm.Hut + CD_MAXW;       // the published pivot row (16-byte aligned)
     const bool pinned = sm.cf[QD_PINNED] != 0.0;
     const int first = pinned ? NT : 0;
     const double lo = sm.cf[QD_VMIN], up = sm.cf[QD_VMAX];
@@ -561,42 +546,55 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 g = 0.0;
         }
         if (lane < CD_MAXW)
-        {
-            as_r[lane] = g;
-            double2* gr = reinterpret_cast<double2*>(G + lane * LDG);
-#pragma unroll
-            for (int j = 0; j < CD_MAXW / 2; ++j)
-                gr[j] = make_double2(h[2 * j], h[2 * j + 1]);
-        }
+            gvec[lane] = g;
         __syncwarp();
-        const bool okG = gj24(G, LDG, lane, first, CD_MAXW);
+        // ---- inverse of H_r by exchange pivots: lane l keeps row l of T in registers (h[]) -------------------------
+        // In (outputs) = T (inputs) a pivot on q swaps input q and output q of y = H_r v; after all of them T = H_r^-1.
+        // T is symmetric within the exchanged set and within the rest, antisymmetric across: T[l][q] = +- T[q][l], so the
+        // published row q gives every lane its entry of column q without indexing its registers by q.
+        const bool isvar = lane >= first && lane < nv;
+        bool inF = false;      // exchanged already
+        bool okG = true;
+#pragma unroll 1
+        for (int p = first; p < nv; ++p)
+        {
+            rp_publish(h, rowq, lane == p);
+            const double d = rowq[p];
+            okG = okG && (d > 0.0) && isfinite(d);
+            rp_pivot(h, rowq, p, lane, inF ? -1.0 : 1.0, 1.0 / d);
+            if (lane == p)
+                inF = true;
+            __syncwarp();
+        }
         double v_e = 0.0;
         if (lane < CD_MAXW)
         {
-            const double2* gr = reinterpret_cast<const double2*>(G + lane * LDG);
-            const double2* g2 = reinterpret_cast<const double2*>(as_r);
+            const double2* g2 = reinterpret_cast<const double2*>(gvec);
+            double v1 = 0.0;
 #pragma unroll
             for (int j = 0; j < CD_MAXW / 2; ++j)
             {
-                const double2 gg = gr[j], rr = g2[j];
-                v_e = fma(-gg.x, rr.x, v_e);
-                v_e = fma(-gg.y, rr.y, v_e);
+                const double2 rr = g2[j];
+                v_e = fma(-h[2 * j], rr.x, v_e);
+                v1 = fma(-h[2 * j + 1], rr.y, v1);
             }
+            v_e += v1;
         }
-        __syncwarp();
         if (!okG)
             stat = VSMPC_STATUS_NUMERICAL;
-        // ---- Goldfarb-Idnani dual active set on the boxes, one variable per lane (G symmetric: column = row) ----
+        // ---- Goldfarb-Idnani dual active set on the boxes, one variable per lane ---------------------------------------
+        // T stays the principal pivot transform of H_r over the free set: activating a bound / dropping it is one more
+        // pivot on that index.  For a violated free p with sign s, raising its multiplier by t moves v_F by -t s T[F, p]
+        // and lambda_a by -t r_a, r_a = -s_a s T[a, p]; T[p][p] is the step denominator.  No working-set inverse.
         const double tol = 1e-10;
-        const bool isvar = lane >= first && lane < nv;
-        int wpos_e = -1;
-        double lamW = 0.0;
-        int nW = 0, iters = 0;
+        int act = 0;           // 0 free, +1 / -1 active at the upper / lower bound
+        double lam_e = 0.0;
+        int iters = 0;
         bool fail = stat != VSMPC_STATUS_SOLVED;
         while (!fail)
         {
             int p_idx;
-            const double best = warp_max_nonneg((isvar && wpos_e < 0) ? fmax(fmax(v_e - up, lo - v_e), 0.0) : 0.0, p_idx);
+            const double best = warp_max_nonneg((isvar && act == 0) ? fmax(fmax(v_e - up, lo - v_e), 0.0) : 0.0, p_idx);
             if (!(best > tol))
                 break;
             const double v_p0 = __shfl_sync(0xffffffffu, v_e, p_idx);
@@ -611,39 +609,14 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                     fail = true;
                     break;
                 }
-                const double gp_e = lane < CD_MAXW ? G[p_idx * LDG + lane] : 0.0; // G[:, p]
-                const int widx_a = lane < nW ? as_widx[lane] : 0;
-                const double sgn_a = lane < nW ? as_sgn[lane] : 0.0;
-                const double gwp_a = sgn_a * s * __shfl_sync(0xffffffffu, gp_e, widx_a);
-                // r = Minv gwp: gwp broadcast through shared memory, two FMA chains
-                if (lane < nW)
-                    as_lam[lane] = gwp_a;
-                __syncwarp();
-                double r_a = 0.0;
-                if (lane < nW)
-                {
-                    const double* mrow = Minv + lane * CD_MAXW;
-                    double r0 = 0.0, r1 = 0.0;
-                    int b = 0;
-#pragma unroll 2
-                    for (; b + 1 < nW; b += 2)
-                    {
-                        r0 = fma(mrow[b], as_lam[b], r0);
-                        r1 = fma(mrow[b + 1], as_lam[b + 1], r1);
-                    }
-                    if (b < nW)
-                        r0 = fma(mrow[b], as_lam[b], r0);
-                    r_a = r0 + r1;
-                }
-                double zsum = (lane < nW) ? r_a * gwp_a : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+                rp_publish(h, rowq, lane == p_idx);
+                const double rp = rowq[lane < CD_MAXW ? lane : 0];
+                const double zp = rowq[p_idx];
+                const double c_e = isvar ? (act == 0 ? rp : -rp) : 0.0;      // T[e][p], p free
+                const double r_e = act != 0 ? -(double)act * s * c_e : 0.0;
                 int drop;
-                const double t1 = warp_min_nonneg((lane < nW && r_a > 0.0) ? fmax(lamW, 0.0) / r_a : INFINITY, drop);
-                const double gpp = __shfl_sync(0xffffffffu, gp_e, p_idx);
+                const double t1 = warp_min_nonneg((act != 0 && r_e > 0.0) ? fmax(lam_e, 0.0) / r_e : INFINITY, drop);
                 const double v_p = __shfl_sync(0xffffffffu, v_e, p_idx);
-                const double zp = gpp - zsum;
                 const double izp = 1.0 / zp;
                 const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) * izp : INFINITY;
                 const double tt = fmin(t1, t2);
@@ -653,108 +626,42 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                     fail = true;
                     break;
                 }
-                if (lane < nW)
-                    as_r[lane] = r_a * sgn_a;
-                __syncwarp();
+                if (isvar)
                 {
-                    double zd = s * gp_e, zd1 = 0.0;
-                    if (lane < CD_MAXW)
-                    {
-                        int a = 0;
-#pragma unroll 2
-                        for (; a + 1 < nW; a += 2)
-                        {
-                            zd = fma(-as_r[a], G[as_widx[a] * LDG + lane], zd);
-                            zd1 = fma(-as_r[a + 1], G[as_widx[a + 1] * LDG + lane], zd1);
-                        }
-                        if (a < nW)
-                            zd = fma(-as_r[a], G[as_widx[a] * LDG + lane], zd);
-                    }
-                    v_e = fma(-tt, zd + zd1, v_e);
+                    if (act == 0)
+                        v_e = fma(-tt * s, c_e, v_e);
+                    else
+                        lam_e -= tt * r_e;
                 }
-                if (lane < nW)
-                    lamW -= tt * r_a;
                 lam_p += tt;
                 if (t2 <= t1)
                 {
-                    if (nW >= CD_MAXW)
-                    {
-                        stat = VSMPC_STATUS_MAX_ITER;
-                        fail = true;
-                        break;
-                    }
-                    __syncwarp();
-                    if (lane < nW)
-                        as_lam[lane] = r_a;
-                    __syncwarp();
-                    if (lane < nW)
-                    {
-#pragma unroll 4
-                        for (int b = 0; b < nW; ++b)
-                            Minv[lane * CD_MAXW + b] = fma(r_a * izp, as_lam[b], Minv[lane * CD_MAXW + b]);
-                        Minv[lane * CD_MAXW + nW] = -r_a * izp;
-                        Minv[nW * CD_MAXW + lane] = -r_a * izp;
-                    }
-                    if (lane == nW)
-                    {
-                        Minv[nW * CD_MAXW + nW] = izp;
-                        as_widx[nW] = p_idx;
-                        as_sgn[nW] = s;
-                        lamW = lam_p;
-                    }
+                    // full step: p becomes active (row p is published already)
+                    rp_pivot(h, rowq, p_idx, lane, act == 0 ? 1.0 : -1.0, izp);
                     if (lane == p_idx)
-                        wpos_e = nW;
-                    nW++;
+                    {
+                        act = s > 0 ? 1 : -1;
+                        lam_e = lam_p;
+                        v_e = bound;
+                    }
                     __syncwarp();
                     break;
                 }
+                // blocked step: the blocking bound leaves the working set
+                __syncwarp();
+                rp_publish(h, rowq, lane == drop);
+                rp_pivot(h, rowq, drop, lane, act != 0 ? 1.0 : -1.0, 1.0 / rowq[drop]);
+                if (lane == drop)
                 {
-                    const int last = nW - 1;
-                    const int var_d = as_widx[drop], var_l = as_widx[last];
-                    const double mdd = Minv[drop * CD_MAXW + drop];
-                    __syncwarp();
-                    const double f = lane < nW ? Minv[lane * CD_MAXW + drop] / mdd : 0.0;
-                    if (lane < nW)
-                        as_lam[lane] = Minv[drop * CD_MAXW + lane];
-                    __syncwarp();
-                    if (lane < nW)
-#pragma unroll 4
-                        for (int b = 0; b < nW; ++b)
-                            Minv[lane * CD_MAXW + b] = fma(-f, as_lam[b], Minv[lane * CD_MAXW + b]);
-                    __syncwarp();
-                    if (drop != last)
-                    {
-                        if (lane < nW)
-                            as_lam[lane] = Minv[last * CD_MAXW + lane];
-                        __syncwarp();
-                        if (lane < nW)
-                        {
-                            Minv[drop * CD_MAXW + lane] = as_lam[lane];
-                            Minv[lane * CD_MAXW + drop] = as_lam[lane];
-                        }
-                        __syncwarp();
-                        if (lane == 0)
-                        {
-                            Minv[drop * CD_MAXW + drop] = as_lam[last];
-                            as_widx[drop] = var_l;
-                            as_sgn[drop] = as_sgn[last];
-                        }
-                        const double lam_last = __shfl_sync(0xffffffffu, lamW, last);
-                        if (lane == drop)
-                            lamW = lam_last;
-                        if (lane == var_l)
-                            wpos_e = drop;
-                    }
-                    if (lane == var_d)
-                        wpos_e = -1;
-                    nW--;
-                    __syncwarp();
+                    act = 0;
+                    lam_e = 0.0;
                 }
+                __syncwarp();
             }
         }
         // theta*: throttle variables (active ones exactly on their bound), affine 1
-        if (wpos_e >= 0)
-            v_e = as_sgn[wpos_e] > 0 ? up : lo;
+        if (act != 0)
+            v_e = act > 0 ? up : lo;
         double th = 0.0;
         if (lane < nv)
             th = (pinned && lane < NT) ? sm.cf[QD_VBAR + lane] : v_e;
@@ -766,7 +673,7 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
         PHASE_CLK(5);
 #ifdef VSMPC_PHASE_CLOCKS
         if (lane == 0 && inst < 4096)
-            g_phase_clk[inst][7] = iters * 100 + nW;
+            g_phase_clk[inst][7] = iters * 100 + __popc(__ballot_sync(0xffffffffu, act != 0));
 #endif
     }
     __syncthreads();
