@@ -672,8 +672,11 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
             sm.flags[1] = stat;
         PHASE_CLK(5);
 #ifdef VSMPC_PHASE_CLOCKS
-        if (lane == 0 && inst < 4096)
-            g_phase_clk[inst][7] = iters * 100 + __popc(__ballot_sync(0xffffffffu, act != 0));
+        {
+            const int n_act = __popc(__ballot_sync(0xffffffffu, act != 0));     // all lanes: not under the lane-0 test
+            if (lane == 0 && inst < 4096)
+                g_phase_clk[inst][7] = iters * 100 + n_act;
+        }
 #endif
     }
     __syncthreads();
