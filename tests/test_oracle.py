@@ -204,3 +204,35 @@ def test_oracle_reproduces_golden_tick_sequence():
             o.solve()
             row = o.output_row()
             assert np.abs(row - g["rows"][t, i]).max() / max(1.0, np.abs(row).max()) < 1e-9, (t, i)
+
+
+def test_pivot_active_set_spec_on_random_box_qps():
+    """tools/condensed_model.box_qp_pivot (the active set of the condensed kernels: exchange pivots on the principal pivot
+    transform) against the KKT conditions of random strictly convex box QPs, from unconstrained to almost fully
+    saturated."""
+    from condensed_model import box_qp_pivot, exchange_pivot
+    rng = np.random.default_rng(7)
+    # the pivot is an involution and pivoting every index inverts
+    A = rng.normal(size=(9, 9)); H = A @ A.T + 9 * np.eye(9)
+    T = H.copy()
+    exchange_pivot(T, 3); exchange_pivot(T, 3)
+    assert np.abs(T - H).max() < 1e-12
+    for q in range(9):
+        exchange_pivot(T, q)
+    assert np.abs(T @ H - np.eye(9)).max() < 1e-12
+    for n, scale in ((8, 0.2), (24, 1.0), (24, 30.0), (60, 5.0), (140, 50.0)):
+        for rep in range(4):
+            A = rng.normal(size=(n, n))
+            H = A @ A.T / n + np.diag(rng.uniform(0.5, 2.0, n))
+            g = scale * rng.normal(size=n)
+            lo, up = -1.52115, 1.65096
+            v, active, status = box_qp_pivot(H, g, lo, up, max_iter=6 * n)
+            assert status == 0
+            y = H @ v + g                      # stationarity: y_F = 0, y_a = -s_a lam_a with lam_a >= 0
+            assert (v <= up + 1e-12).all() and (v >= lo - 1e-12).all()
+            free = np.ones(n, dtype=bool)
+            for i, sgn, lam in active:
+                free[i] = False
+                assert v[i] == (up if sgn > 0 else lo) and lam >= -1e-9
+                assert abs(y[i] + sgn * lam) < 1e-8 * max(1.0, abs(y[i]))
+            assert np.abs(y[free]).max(initial=0.0) < 1e-8 * max(1.0, np.abs(g).max())

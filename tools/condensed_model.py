@@ -12,7 +12,8 @@ Value function at knot k, theta = (v_0 .. v_{nblk-1}, 1, dq_held):
     lanes 4b..4b+3 = throttle block b, lane 24 = affine column (references, c, gradients), and during the tail
     (knots >= Nc-1, where joint block Nc-1 is held) lanes D0..D0+7 = the held joint increments.
 After knot 0:  reduced Hessian H_r = Om_vv + Laplacian + w_i E_0, gradient from Psi' x0 and the affine column;
-dual active set on the boxes with the explicit inverse G = H_r^-1; one forward pass with the stored gains
+dual active set on the boxes by exchange pivots on the principal pivot transform of H_r (box_qp_pivot below; the same
+routine is the specification of the long-horizon kernel's active set); one forward pass with the stored gains
 K_k (8 x 26) and F_k (8 x 32).
 """
 from __future__ import annotations
@@ -29,6 +30,73 @@ def block_maps(N, Ns, Nc):
     jb = [min(k, Nc - 1) for k in range(N)]
     tb = [0 if k < Ns else (k - (Ns - 1) if k < Nc else Nc - Ns) for k in range(N)]
     return jb, tb
+
+
+def exchange_pivot(T, q):
+    """In (outputs) = T (inputs): swap the roles of input q and output q.  Pivoting every index of H gives H^-1; pivoting
+    q twice is the identity.  This is the pivot of csrc/vsmpc_qp_condensed.cu (rp_pivot) and of the long-horizon kernel
+    (there as the rank-1 change T - (T[:, q] + e_q)(T[q, :] - e_q)' / T[q, q], deferred eight at a time)."""
+    d = T[q, q]
+    u, v = T[:, q].copy(), T[q, :].copy()
+    T -= np.outer(u, v) / d
+    T[q, :] = -v / d
+    T[:, q] = u / d
+    T[q, q] = 1.0 / d
+    return d
+
+
+def box_qp_pivot(H, g, lo, up, max_iter=200, tol=1e-10):
+    """min 1/2 v'Hv + g'v, lo <= v <= up: Goldfarb-Idnani dual active set on the principal pivot transform.
+    T starts as H^-1 (every index exchanged) and stays the transform of H over the free set F: (v_F, y_W) = T (y_F, v_W)
+    with y = Hv = -g - sum_a s_a lam_a e_a.  For a violated free p with sign s, raising its multiplier by t moves v_F by
+    -t s T[F, p] and lam_a by -t r_a, r_a = -s_a s T[a, p]; T[p, p] is the step denominator.  A full step pivots p into
+    the working set, a blocked step pivots the blocking index back out.  Returns (v, [(index, sign, multiplier)], status)."""
+    n = H.shape[0]
+    T = np.array(H, dtype=float)
+    for q in range(n):
+        if not exchange_pivot(T, q) > 0:
+            return np.zeros(n), [], 2
+    vv = -T @ g
+    act = np.zeros(n, dtype=int)
+    lam = np.zeros(n)
+    status, it = 0, 0
+    while True:
+        viol = np.where(act == 0, np.maximum(np.maximum(vv - up, lo - vv), 0.0), 0.0)
+        p = int(np.argmax(viol))
+        if not viol[p] > tol:
+            break
+        s = 1.0 if vv[p] - up > lo - vv[p] else -1.0
+        bound = up if s > 0 else lo
+        lam_p = 0.0
+        while True:
+            it += 1
+            if it > max_iter:
+                status = 1
+                break
+            c = T[:, p].copy()
+            zp = T[p, p]
+            r = np.where(act != 0, -act * s * c, 0.0)
+            cand = np.where((act != 0) & (r > 0), np.maximum(lam, 0.0) / np.where(r > 0, r, 1.0), np.inf)
+            drop = int(np.argmin(cand))
+            t1 = cand[drop]
+            t2 = (s * vv[p] - s * bound) / zp if zp > 1e-300 else np.inf
+            t = min(t1, t2)
+            if not np.isfinite(t):
+                status = 2
+                break
+            vv = np.where(act == 0, vv - t * s * c, vv)
+            lam = np.where(act != 0, lam - t * r, lam)
+            lam_p += t
+            if t2 <= t1:
+                exchange_pivot(T, p)
+                act[p], lam[p], vv[p] = (1 if s > 0 else -1), lam_p, bound
+                break
+            exchange_pivot(T, drop)
+            act[drop], lam[drop] = 0, 0.0
+        if status:
+            break
+    active = [(int(i), float(act[i]), float(lam[i])) for i in np.nonzero(act)[0]]
+    return vv, active, status
 
 
 class CondensedQP:
@@ -120,58 +188,8 @@ class CondensedQP:
     def solve_box(self, max_iter=200, tol=1e-10):
         self.factor()
         H, g, first = self.reduced_qp()
-        G = np.linalg.inv(H)
-        vv = -G @ g
-        lo, up = self.vmin, self.vmax
-        W, sgn, lam = [], [], []
-        status, it = 0, 0
-        while True:
-            viol_up, viol_lo = vv - up, lo - vv
-            viol = np.maximum(viol_up, viol_lo)
-            for i in W:
-                viol[i] = -np.inf
-            p = int(np.argmax(viol))
-            if viol[p] <= tol:
-                break
-            s = 1.0 if viol_up[p] > viol_lo[p] else -1.0
-            lam_p = 0.0
-            while True:
-                it += 1
-                if it > max_iter:
-                    status = 1
-                    break
-                gp = G[:, p]
-                if W:
-                    GWW = np.array([[G[i, j] * sgn[a] * sgn[b] for b, j in enumerate(W)] for a, i in enumerate(W)])
-                    GWp = np.array([gp[i] * sgn[a] * s for a, i in enumerate(W)])
-                    r = np.linalg.solve(GWW, GWp)
-                    zdir = s * gp - sum(r[a] * sgn[a] * G[:, j] for a, j in enumerate(W))
-                else:
-                    r = np.zeros(0)
-                    zdir = s * gp
-                zp = s * zdir[p]
-                t2 = (s * vv[p] - s * (up if s > 0 else lo)) / zp if zp > 1e-300 else np.inf
-                t1, drop = np.inf, -1
-                for a in range(len(W)):
-                    if r[a] > 0 and lam[a] / r[a] < t1:
-                        t1, drop = lam[a] / r[a], a
-                t = min(t1, t2)
-                if not np.isfinite(t):
-                    status = 2
-                    break
-                vv = vv - t * zdir
-                for a in range(len(W)):
-                    lam[a] -= t * r[a]
-                lam_p += t
-                if t == t2:
-                    W.append(p); sgn.append(s); lam.append(lam_p)
-                    break
-                W.pop(drop); sgn.pop(drop); lam.pop(drop)
-            if status:
-                break
-        for i, s in zip(W, sgn):
-            vv[i] = up if s > 0 else lo
-        self.active = list(zip(W, sgn, lam))
+        vv, active, status = box_qp_pivot(H, g, self.vmin, self.vmax, max_iter=max_iter, tol=tol)
+        self.active = active
         self.status = status
         v = np.concatenate([self.vbar, vv]) if self.pinned else vv
         return self.forward(v.reshape(self.nblk, 4))
