@@ -410,10 +410,9 @@ __device__ __forceinline__ double cw_block_best(double v, double* __restrict__ r
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
-                         double* __restrict__ ws_all, double* __restrict__ scratch_all, double* __restrict__ z_all,
+                         double* __restrict__ ws_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
-                         int* __restrict__ n_factor, int* __restrict__ n_solve, size_t ws_stride, size_t scratch_stride,
-                         int want_z)
+                         int* __restrict__ n_factor, int* __restrict__ n_solve, size_t ws_stride, int want_z)
 {
     extern __shared__ __align__(16) unsigned char cw_raw[];
     CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
@@ -664,7 +663,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         cw_flush(Pv, M, warp, lane, nwarps, nthr);
     if (sm.flags[0] != 0 || !okG)
         stat = stat == VSMPC_STATUS_SOLVED ? VSMPC_STATUS_NUMERICAL : stat;
-    // unconstrained minimiser v~ = -G g~ (scaled variables); afterwards grad holds the scale factors for all threads
+    // unconstrained minimiser v~ = -G g~ (scaled variables); afterwards grad holds the inverse scale factors for all threads
     for (int e = threadIdx.x; e < nv; e += nthr)
     {
         double v = 0.0;
@@ -677,9 +676,10 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         vv[e] = v;
     }
     __syncthreads();
-    double* scl = grad;
+    double* iscl = grad;          // 1 / S for all threads
+    const double iS_e = 1.0 / S_e;
     if (threadIdx.x < nv)
-        scl[threadIdx.x] = S_e;
+        iscl[threadIdx.x] = iS_e;
     __syncthreads();
 
     WCLK(4);
@@ -692,7 +692,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         const int e = threadIdx.x;
         const bool isvar = e >= first && e < nv;
         const double tol = 1e-10;
-        const double lo_e = lo / S_e, up_e = up / S_e;      // bounds of the scaled variable
+        const double lo_e = lo * iS_e, up_e = up * iS_e;    // bounds of the scaled variable
         int act = 0;            // 0 free, +1 / -1 active at the upper / lower bound
         double lam_e = 0.0;
         int iters = 0;
@@ -709,7 +709,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             const double best = cw_block_best<true>(viol, rbA, warp, lane, nwarps, p);
             if (!(best > tol))
                 break;
-            const double vp0 = vv[p], isp = 1.0 / scl[p];
+            const double vp0 = vv[p], isp = iscl[p];
             const double s = (vp0 - up * isp > lo * isp - vp0) ? 1.0 : -1.0;
             const double bound = (s > 0 ? up : lo) * isp;
             double lam_p = 0.0;
@@ -888,21 +888,22 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
     static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
     const CwLayout L = cw_layout(h_cfg);
     const size_t smem = cw_smem_bytes(h_cfg);
-    const size_t wsd = condensed_wide_ws_doubles(h_cfg), scd = condensed_wide_scratch_doubles(h_cfg);
+    const size_t wsd = condensed_wide_ws_doubles(h_cfg);
+    (void)scratch;     // no global scratch beyond the workspace stacks
     cudaError_t e;
     if (L.G <= 2)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
             return e;
-        qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, scratch, z, st, out_rows, status,
-                                                                       n_factor, n_solve, wsd, scd, want_z);
+        qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                       n_factor, n_solve, wsd, want_z);
     }
     else if (L.G == 3)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
-        qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, scratch, z, st, out_rows, status,
-                                                                        n_factor, n_solve, wsd, scd, want_z);
+        qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                        n_factor, n_solve, wsd, want_z);
     }
     else
     {
@@ -911,7 +912,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
         // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
         qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
-            h_cfg, B, qd, ws, scratch, z, st, out_rows, status, n_factor, n_solve, wsd, scd, want_z);
+            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, wsd, want_z);
     }
     return cudaGetLastError();
 }
