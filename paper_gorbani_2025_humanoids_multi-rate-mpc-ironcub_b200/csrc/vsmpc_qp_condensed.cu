@@ -620,7 +620,7 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 const double izp = 1.0 / zp;
                 const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) * izp : INFINITY;
                 const double tt = fmin(t1, t2);
-                if (!isfinite(tt))
+                if (!isfinite(tt) || !isfinite(zp))
                 {
                     stat = VSMPC_STATUS_NUMERICAL;
                     fail = true;
@@ -650,7 +650,14 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 // blocked step: the blocking bound leaves the working set
                 __syncwarp();
                 rp_publish(h, rowq, lane == drop);
-                rp_pivot(h, rowq, drop, lane, act != 0 ? 1.0 : -1.0, 1.0 / rowq[drop]);
+                const double dd = rowq[drop];
+                if (!(dd > 0.0) || !isfinite(dd))
+                {
+                    stat = VSMPC_STATUS_NUMERICAL;
+                    fail = true;
+                    break;
+                }
+                rp_pivot(h, rowq, drop, lane, act != 0 ? 1.0 : -1.0, 1.0 / dd);
                 if (lane == drop)
                 {
                     act = 0;
@@ -662,6 +669,9 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
         // theta*: throttle variables (active ones exactly on their bound), affine 1
         if (act != 0)
             v_e = act > 0 ? up : lo;
+        // a NaN iterate never shows up as a violated bound: gate it here (the status holds the outputs)
+        if (stat == VSMPC_STATUS_SOLVED && __any_sync(0xffffffffu, lane < nv && !isfinite(v_e)))
+            stat = VSMPC_STATUS_NUMERICAL;
         double th = 0.0;
         if (lane < nv)
             th = (pinned && lane < NT) ? sm.cf[QD_VBAR + lane] : v_e;

@@ -760,7 +760,12 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                         lam_e = 0.0;
                     }
                 }
-                cw_pivot(Pv, M, q, warp, lane, nwarps, nthr);
+                if (!cw_pivot(Pv, M, q, warp, lane, nwarps, nthr))
+                {
+                    stat = VSMPC_STATUS_NUMERICAL;     // non-positive pivot: same value in every thread
+                    fail = true;
+                    break;
+                }
                 if (full)
                     break;
             }
@@ -780,6 +785,9 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             g_wide_clk[inst][15] = smid;
         }
 #endif
+        // a NaN iterate never shows up as a violated bound: gate it here (the status holds the outputs)
+        if (__syncthreads_or(isvar && !isfinite(vv[e])) && stat == VSMPC_STATUS_SOLVED)
+            stat = VSMPC_STATUS_NUMERICAL;
         // theta*: throttle variables, affine 1, held block 0
         if (e < L.ldc)
         {

@@ -52,7 +52,14 @@ lines = [f"# Monte Carlo closed-loop sweep (configs[2] x configs[4]), rank {rank
          f"* solved at the last tick: {int((status==0).sum())} / {B}; ticks with status != 0 among the recorded rows: {int((rec[:,:,14]!=0).sum())}",
          "", "| t [s] | CoM distance from start: median / 95 % / max [m] | max |rpy|: median / 95 % / max [rad] |", "|---|---|---|"]
 for k in range(rec.shape[0]):
-    lines.append(f"| {(k+1)*(ticks//4)*0.005:.2f} | {np.median(err[k]):.3f} / {np.percentile(err[k],95):.3f} / {err[k].max():.3f} | "
-                 f"{np.median(att[k]):.3f} / {np.percentile(att[k],95):.3f} / {att[k].max():.3f} |")
+    fin = np.isfinite(err[k]) & np.isfinite(att[k])
+    e_, a_ = err[k][fin], att[k][fin]
+    lines.append(f"| {(k+1)*(ticks//4)*0.005:.2f} | {np.median(e_):.3f} / {np.percentile(e_,95):.3f} / {e_.max():.3f} | "
+                 f"{np.median(a_):.3f} / {np.percentile(a_,95):.3f} / {a_.max():.3f} |")
+    if not fin.all():
+        bad = ~fin
+        lines.append(f"| | {int(bad.sum())} loops with a non-finite plant state (left out of the row above); "
+                     f"status != 0 at that row for {int((rec[k, bad, 14] != 0).sum())} of them, at the last tick for "
+                     f"{int((status[bad] != 0).sum())} | |")
 open(os.path.join(ROOT, "gpurun_out", f"montecarlo_sweep_rank{rank}.md"), "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
