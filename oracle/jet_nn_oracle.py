@@ -3,7 +3,7 @@
 * neural jet plant: ``NeuralJetModel.get_state`` / ``JetModelTotal.get_state`` (src/mujoco_lib/nn_jet_model.py:21-30,
   86-109).  The reference feeds the LSTM one time step with a fresh zero state on every call, so the cell reduces to
   c = sigma(i) * tanh(g), h = sigma(o) * tanh(c) with gates = W_ih x + b_ih + b_hh; thrust rate = fc(h); float32.
-  PINNED against outputs of the reference module itself (tests/golden/jet_nn.npz, tools/make_jet_nn_golden.py).
+  PINNED against outputs of the reference module itself (tests/golden/jet_nn.npz, tests/golden/make_jet_nn_golden.py).
 * per-jet EKF: ``SecondOrderJetModel.update`` (src/mujoco_lib/jet_kalman_filter.py:30-65): predict with the second-order
   jet model, covariance with the Jacobian evaluated at the PREDICTED state (:58), measurement = (T_nn, Tdot_nn), H = I.
   CasADi is not installed here: parity of this part is unpinned (the Jacobian is written out analytically).

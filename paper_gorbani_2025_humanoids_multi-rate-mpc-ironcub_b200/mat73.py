@@ -3,7 +3,7 @@
 Host-side I/O of the drop-in: stands in for matio's ``Mat_VarRead`` as used by the reference's
 ``TrajectoryManager::loadTrajectoryFromFile`` (utils/src/TrajectoryManager.cpp:67-140), so that the
 ``trajectoryFile`` entries of ``vs_mcp_config.xml`` (:34-40) can be loaded without matio / h5py.
-``tools/make_fixtures.py`` uses it to convert the reference's ``src/trajectories/*.mat`` into
+``tests/golden/make_fixtures.py`` uses it to convert the reference's ``src/trajectories/*.mat`` into
 ``tests/golden/trajectories.npz``.
 
 Supports exactly what those two files need: v0 superblock, v1 object headers, v1 group B-trees +

@@ -3,7 +3,7 @@
 
 Runs ONLY in the build container (reads /root/reference, which does not exist on the GPU box):
 
-    python tools/make_fixtures.py
+    python tests/golden/make_fixtures.py
 
 Sources: /root/reference/src/trajectories/alphaGravity.mat (alphaGravity 1x351, fps 10) and
 minimumJerkTrajectory.mat (positionCoM, velocityCoM, RPY, RPYDot 3x1481, fps 10), referenced from
@@ -15,7 +15,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import importlib  # noqa: E402
 loadmat73 = importlib.import_module('paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub_b200.mat73').loadmat73

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Freeze golden vectors produced by the CPU oracle (oracle/vsmpc_oracle.py).
 
-    python tools/make_golden.py        # writes tests/golden/golden_qp.npz and golden_ticks.npz
+    python tests/golden/make_golden.py        # writes tests/golden/golden_qp.npz and golden_ticks.npz
 
 The reference ships no golden vectors for this path ("parity unpinned"), so these files
 pin the ORACLE: tests/test_oracle.py checks that it still reproduces them, tests/test_gpu_golden.py that
@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import load_trajectories, pkg  # noqa: E402

@@ -17,7 +17,7 @@ def pkg(sub: str = ""):
 
 
 def load_trajectories():
-    """Trajectory fixtures converted from the reference's .mat files (tools/make_fixtures.py)."""
+    """Trajectory fixtures converted from the reference's .mat files (tests/golden/make_fixtures.py)."""
     d = np.load(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
     return {
         "TRAJECTORY_MANAGER": dict(fps=int(d["alpha_fps"]), arrays={"alphaGravity": d["alphaGravity"]}),

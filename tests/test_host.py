@@ -133,7 +133,7 @@ def test_pack_builder_roundtrip():
 
 
 def test_mat73_reader_on_npz_equivalent(tmp_path):
-    """The MAT-v7.3 reader is exercised against the reference files in tools/make_fixtures.py; here the
+    """The MAT-v7.3 reader is exercised against the reference files in tests/golden/make_fixtures.py; here the
     committed fixture must at least be self-consistent with what the loader returns."""
     cfg = pkg("config")
     t = cfg.load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))

@@ -1,5 +1,5 @@
 """Neural jet plant + per-jet EKF.  The plant part is PINNED: tests/golden/jet_nn.npz holds outputs of the
-reference's own torch module (tools/make_jet_nn_golden.py imports src/mujoco_lib/nn_jet_model.py in the build container)."""
+reference's own torch module (tests/golden/make_jet_nn_golden.py imports src/mujoco_lib/nn_jet_model.py in the build container)."""
 import numpy as np
 import pytest
 

@@ -3,7 +3,7 @@
 The reference ships no tests for this path, so the oracle is pinned against: the reference's own
 fixtures (trajectory files), the second statement of the jet model in
 /root/reference/src/mujoco_lib/jet_kalman_filter.py:6-45, closed-form identities of SURVEY App. A,
-a KKT certificate of the exact solver, and frozen golden vectors (tools/make_golden.py).
+a KKT certificate of the exact solver, and frozen golden vectors (tests/golden/make_golden.py).
 """
 import math
 
