@@ -1,8 +1,9 @@
 """Build recipe of the oracle's C restatement (oracle/c/vsmpc_ref.c) -> oracle/_build/libvsmpc_ref.so.
 
-TEST INFRASTRUCTURE.  The reference itself cannot be compiled here (its hot-path translation units
+TEST INFRASTRUCTURE.  The reference's tick cannot be compiled here (its hot-path translation units
 include <OsqpEigen/OsqpEigen.h>, Eigen, iDynTree, YARP and BLF headers, none of which exist in this
-image — DESIGN.md "Oracle"), so there is no oracle/_ref; this library is the CPU "port" of the path.
+image — DESIGN.md "Oracle"; only its scalar jet model builds, oracle/build_ref.py -> oracle/_ref/);
+this library is the CPU "port" of the path.
 It is compiled with -O3 -march=native on the machine that uses it (rebuilt when the CPU differs).
 """
 import hashlib

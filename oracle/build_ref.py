@@ -1,0 +1,88 @@
+"""Build recipe of oracle/_ref/libjetmodel_ref.so: the reference's OWN jet model, compiled from its source where it lies.
+
+TEST INFRASTRUCTURE.  Of the hot path's translation units only ``src/flight-controller/utils/src/JetModel.cpp`` (rows a6 and
+a17 of SURVEY §8: f, g, their partial derivatives, the standardisations and ``destandardizeThrottle_u2T``) is
+self-contained arithmetic: it includes Eigen and YARP headers but uses nothing of them, so it compiles against the empty
+stand-in headers in oracle/ref_stubs/.  Every other unit on the path needs the real Eigen / OsqpEigen / iDynTree / BLF and is
+unbuildable here.  No reference source is copied: g++ reads it under /root/reference; the only output is
+oracle/_ref/libjetmodel_ref.so (git-ignored, travels to the GPU box).  Used by tests/test_oracle.py to validate the
+restatement (oracle.vsmpc_oracle.JetModel, oracle/c/vsmpc_ref.c) and by tests/golden/make_jet_model_golden.py.
+"""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_UT = "/root/reference/src/flight-controller/utils"
+OUT_DIR = os.path.join(HERE, "_ref")
+LIB = os.path.join(OUT_DIR, "libjetmodel_ref.so")
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(REF_UT, "src", "JetModel.cpp"))
+
+
+def build(force: bool = False) -> str:
+    """Compiles when /root/reference is present (the build container); elsewhere returns the prebuilt file or ''."""
+    if not available():
+        return LIB if os.path.exists(LIB) else ""
+    if os.path.exists(LIB) and not force:
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off",
+           "-I", os.path.join(HERE, "ref_stubs"), "-I", os.path.join(REF_UT, "include"),
+           "-o", LIB, os.path.join(REF_UT, "src", "JetModel.cpp"), os.path.join(HERE, "ref_shim.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return LIB
+
+
+REF_FC = "/root/reference/src/flight-controller"
+MPC_LIB = os.path.join(OUT_DIR, "libvsmpc_reference.so")
+MPC_SOURCES = ["momentum-based-linear-mpc-lib/src/variableSamplingMPC/variableSamplingMPC.cpp",
+               "momentum-based-linear-mpc-lib/src/variableSamplingMPC/systemDynamicsVSMPC.cpp",
+               "momentum-based-linear-mpc-lib/src/variableSamplingMPC/constraintsVSMPC.cpp",
+               "momentum-based-linear-mpc-lib/src/variableSamplingMPC/costsVSMPC.cpp",
+               "momentum-based-linear-mpc-lib/src/IMPCProblem/IMPCProblem.cpp",
+               "momentum-based-linear-mpc-lib/src/IMPCProblem/IQPUtilsMPC.cpp",
+               "momentum-based-linear-mpc-lib/src/IMPCProblem/systemDynamic.cpp",
+               "utils/src/QPInput.cpp", "utils/src/IQPCost.cpp", "utils/src/IQPConstraint.cpp",
+               "utils/src/FlightControlUtils.cpp", "utils/src/TrajectoryManager.cpp", "utils/src/JetModel.cpp"]
+
+
+def build_mpc(force: bool = False) -> str:
+    """oracle/_ref/libvsmpc_reference.so: the reference's VariableSamplingMPC (13 of its own translation units, compiled
+    where they lie) + oracle/ref_mpc_shim.cpp, against the stand-in headers of oracle/ref_stubs/."""
+    if not available():
+        return MPC_LIB if os.path.exists(MPC_LIB) else ""
+    shim = os.path.join(HERE, "ref_mpc_shim.cpp")
+    stubs = os.path.join(HERE, "ref_stubs")
+    newest = max([os.path.getmtime(shim)] + [os.path.getmtime(os.path.join(d, f)) for d, _, fs in os.walk(stubs) for f in fs])
+    if os.path.exists(MPC_LIB) and not force and os.path.getmtime(MPC_LIB) >= newest:
+        return MPC_LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-I", stubs,
+           "-I", os.path.join(REF_FC, "utils", "include"), "-I", os.path.join(REF_FC, "momentum-based-linear-mpc-lib", "include"),
+           "-o", MPC_LIB] + [os.path.join(REF_FC, f) for f in MPC_SOURCES] + [shim]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return MPC_LIB
+
+
+def load():
+    import ctypes
+    path = build()
+    if not path:
+        return None
+    lib = ctypes.CDLL(path)
+    for f, args in (("ref_jet_poly", [ctypes.c_int, ctypes.c_double, ctypes.c_double]),
+                    ("ref_jet_scalar", [ctypes.c_int, ctypes.c_double])):
+        getattr(lib, f).argtypes = args
+        getattr(lib, f).restype = ctypes.c_double
+    return lib
+
+
+if __name__ == "__main__":
+    print(build(force=True))
+    print(build_mpc(force=True))

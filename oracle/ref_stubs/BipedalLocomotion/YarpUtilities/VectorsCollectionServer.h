@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE — see standin_blf.h
+#pragma once
+#include <standin_blf.h>

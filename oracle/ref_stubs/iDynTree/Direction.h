@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE — see standin_idyntree.h
+#pragma once
+#include <standin_idyntree.h>

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE — see standin_yarp.h
+#pragma once
+#include <standin_yarp.h>

@@ -5,12 +5,14 @@ This file restates, class by class, what the reference computes on the path
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may import it; the
 product path (``paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub_b200``) never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or logs for this path
-and none of its third-party stack (Eigen, OSQP 1.0.0 / QDLDL 0.1.8 via osqp-eigen 0.11.0,
+PARITY UNPINNED for the tick as a whole: the reference ships no tests, golden vectors or logs for this path
+ and none of its third-party stack (Eigen, OSQP 1.0.0 / QDLDL 0.1.8 via osqp-eigen 0.11.0,
 iDynTree 14.0.2, BLF, YARP, matio) exists in the build container, so the reference binary cannot be
-run here.  What this oracle *is* pinned against: the reference's own fixtures
-(``src/trajectories/*.mat``), the second statement of the jet model in
-``src/mujoco_lib/jet_kalman_filter.py:6-45``, and closed-form identities (tests/test_oracle.py).
+run here.  What this oracle *is* pinned against: the reference's own object code for the jet model
+(``UT/src/JetModel.cpp`` compiled where it lies by oracle/build_ref.py; vectors frozen in
+tests/golden/jet_model_ref.npz), the reference's own fixtures (``src/trajectories/*.mat``), the second
+statement of the jet model in ``src/mujoco_lib/jet_kalman_filter.py:6-45``, and closed-form identities
+(tests/test_oracle.py).
 
 Reference paths (``MPC/`` = src/flight-controller/momentum-based-linear-mpc-lib,
 ``UT/`` = src/flight-controller/utils):
@@ -149,7 +151,10 @@ class JetModel:
         return (throttle - self.n[2]) / self.n[3]
 
     def destandardizeThrottle_u2T(self, v):
-        u = (-1 + math.sqrt(1 + 4 * self.c[12] * v)) / (2 * self.c[12])
+        d = 1 + 4 * self.c[12] * v
+        # std::sqrt of a negative argument is NaN and both comparisons below are then false (JetModel.cpp:97-108);
+        # unreachable from the MPC, whose v is boxed to [v(0 %), v(100 %)]
+        u = (-1 + (math.sqrt(d) if d >= 0 else math.nan)) / (2 * self.c[12])
         u = u * self.n[3] + self.n[2]
         if u < 0:
             u = 0.0

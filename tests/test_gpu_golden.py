@@ -1,4 +1,6 @@
-"""GPU: the CUDA path (through the C-ABI) against the frozen golden vectors of tests/golden/."""
+"""GPU: the CUDA path (through the C-ABI) against the frozen golden vectors of tests/golden/: golden_*.npz (frozen from the
+oracle) and reference_*.npz (frozen from the reference's own code compiled against stand-in headers,
+tests/golden/make_reference_golden.py — the same scenarios, every number from the reference)."""
 import numpy as np
 import pytest
 
@@ -13,12 +15,15 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
+@pytest.mark.parametrize("source", ["golden_qp.npz", "reference_qp.npz"])
 @pytest.mark.parametrize("solver", [0, 1, 2])
-def test_single_tick_golden(solver):
-    g = golden("golden_qp.npz")
+def test_single_tick_golden(solver, source):
+    g = golden(source)
     bat = pkg("batched")
     B = g["nom_pack"].shape[1]
     for tag, free in (("pin", False), ("free", True)):
+        if f"{tag}_z" not in g.files:       # the reference-made file holds the first tick after configure only
+            continue
         mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(load_trajectories()), solver=solver,
                                full_solution=True)
         mpc.configure_pack(g["nom_pack"], g["joint_pos_sel"])
@@ -31,8 +36,9 @@ def test_single_tick_golden(solver):
         z = mpc.getSolution()
         out, status = mpc.get_output()
         assert (status == 0).all()
-        assert rel_err(A, g[f"{tag}_A"]) < 1e-12 and rel_err(BJ, g[f"{tag}_BJ"]) < 1e-12
-        assert rel_err(BT, g[f"{tag}_BT"]) < 1e-12 and rel_err(c, g[f"{tag}_c"]) < 1e-12
+        if f"{tag}_A" in g.files:            # the continuous-time blocks are private members of the reference's classes
+            assert rel_err(A, g[f"{tag}_A"]) < 1e-12 and rel_err(BJ, g[f"{tag}_BJ"]) < 1e-12
+            assert rel_err(BT, g[f"{tag}_BT"]) < 1e-12 and rel_err(c, g[f"{tag}_c"]) < 1e-12
         assert rel_err(q, g[f"{tag}_q"]) < 1e-12 and rel_err(l, g[f"{tag}_l"]) < 1e-12 and rel_err(u, g[f"{tag}_u"]) < 1e-12
         for i in range(B):
             assert rel_err(z[i], g[f"{tag}_z"][i]) < REL
@@ -40,11 +46,12 @@ def test_single_tick_golden(solver):
         mpc.close()
 
 
+@pytest.mark.parametrize("source", ["golden_ticks.npz", "reference_ticks.npz"])
 @pytest.mark.parametrize("solver,full", [(0, False), (0, True), (1, True), (2, False)])
-def test_tick_sequence_golden(solver, full):
+def test_tick_sequence_golden(solver, full, source):
     """24 consecutive ticks: reference-window shift and throttle release on tick 20, alpha_g cursor, RPY
     unwrapping through +-pi, joint accumulator, output hold — all device-resident state."""
-    g = golden("golden_ticks.npz")
+    g = golden(source)
     bat = pkg("batched")
     B = g["nom_pack"].shape[1]
     mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(load_trajectories()), solver=solver,

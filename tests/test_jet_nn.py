@@ -1,5 +1,7 @@
-"""Neural jet plant + per-jet EKF.  The plant part is PINNED: tests/golden/jet_nn.npz holds outputs of the
-reference's own torch module (tests/golden/make_jet_nn_golden.py imports src/mujoco_lib/nn_jet_model.py in the build container)."""
+"""Neural jet plant + per-jet EKF.  Both are PINNED: tests/golden/jet_nn.npz holds outputs of the
+reference's own torch module (tests/golden/make_jet_nn_golden.py imports src/mujoco_lib/nn_jet_model.py in the build
+container), tests/golden/jet_ekf.npz outputs of the reference's own jet_kalman_filter.py executed over a CasADi stand-in
+(tests/golden/make_jet_ekf_golden.py)."""
 import numpy as np
 import pytest
 
@@ -29,6 +31,28 @@ def test_oracle_nn_sequence_matches_reference_outputs():
         T, Td = nn_jet_step(T, g["seq_u"][k], w, float(g["dt"]))
         np.testing.assert_allclose(T, g["seq_T"][k], rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(Td, g["seq_Td"][-1], rtol=1e-4, atol=1e-3)
+
+
+def test_oracle_ekf_matches_reference_outputs():
+    """The oracle's EKF against outputs of the reference's own jet_kalman_filter.py (executed unmodified over a CasADi
+    stand-in, tests/golden/make_jet_ekf_golden.py): model step, Jacobian, and the four-jet filter over 400 steps with
+    the simulator's covariances.  FP64 on both sides: 1e-10 relative."""
+    from oracle.jet_nn_oracle import JetEKF
+    g = golden("jet_ekf.npz")
+    dt = float(g["dt"])
+    e = JetEKF(g["R"], g["Q"], g["P0"], dt)
+    for k in range(g["pts_x"].shape[0]):
+        np.testing.assert_allclose(e.f(g["pts_x"][k], g["pts_u"][k]), g["pts_f"][k], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(e.A(g["pts_x"][k], g["pts_u"][k]), g["pts_A"][k], rtol=1e-10, atol=1e-12)
+    jets = [JetEKF(g["R"], g["Q"], g["P0"], dt) for _ in range(4)]
+    T, Td = g["T0"].copy(), g["Td0"].copy()
+    for k in range(g["seq_u"].shape[0]):
+        for i in range(4):
+            T[i], Td[i] = jets[i].update([T[i], Td[i]], g["seq_u"][k, i], [g["seq_zT"][k, i], g["seq_zTd"][k, i]])
+        np.testing.assert_allclose(T, g["seq_T"][k], rtol=1e-10, atol=1e-9)
+        np.testing.assert_allclose(Td, g["seq_Td"][k], rtol=1e-10, atol=1e-9)
+    for i in range(4):
+        np.testing.assert_allclose(jets[i].P, g["P_end"][i], rtol=1e-10, atol=1e-13)
 
 
 def test_ekf_jacobian_is_the_derivative_of_its_model():

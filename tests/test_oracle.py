@@ -49,6 +49,47 @@ def test_jet_model_matches_second_statement():
         assert jd.compute_dh_dTDot(T, Td, u) == pytest.approx(dTd, rel=1e-6, abs=1e-8)
 
 
+def _oracle_jet_tables(g):
+    j = O.JetModel()
+    poly = np.array([[getattr(j, str(n))(a, b) for a, b in zip(g["T_std"], g["Tdot_std"])] for n in g["poly_names"]])
+    fn = {"destandardizeThrust_u2T": lambda x: x * j.n[1] + j.n[0], "destandardizeThrustDot_u2T": lambda x: x * j.n[1]}
+    scal = np.array([[fn.get(str(n), getattr(j, str(n), None))(float(x)) for x in g["x"]] for n in g["scalar_names"]])
+    return j, poly, scal
+
+
+def test_jet_model_matches_reference_object_code():
+    """PINNED: the oracle's JetModel against outputs of the reference's own JetModel.cpp, compiled from
+    /root/reference by oracle/build_ref.py and frozen by tests/golden/make_jet_model_golden.py (rows a6 / a17:
+    f, g, the four partial derivatives, standardisations, destandardizeThrottle incl. both clips)."""
+    g = golden("jet_model_ref.npz")
+    j, poly, scal = _oracle_jet_tables(g)
+    np.testing.assert_allclose(poly, g["poly"], rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(scal, g["scalar"], rtol=1e-14, atol=1e-14, equal_nan=True)
+    assert j.getThrustStandardDeviation_u2T() == float(g["thrust_std"])
+    # destandardizeThrottle clips to [0, 100] % and is NaN beyond the root of its discriminant (v > 31.9), on both sides
+    u = scal[list(g["scalar_names"]).index("destandardizeThrottle_u2T")]
+    assert np.nanmin(u) == 0.0 and np.nanmax(u) == 100.0 and np.isnan(u).sum() == 2
+
+
+def test_golden_jet_vectors_are_what_the_compiled_reference_returns():
+    """Where oracle/_ref/libjetmodel_ref.so exists (built from the reference source in the build container; it travels
+    to the GPU box), the frozen vectors are re-derived from it bit for bit."""
+    import importlib.util
+    import os
+    import sys
+    from oracle import build_ref
+    lib = build_ref.load()
+    if lib is None:
+        pytest.skip("oracle/_ref/libjetmodel_ref.so not built (no /root/reference here)")
+    spec = importlib.util.spec_from_file_location(
+        "make_jet_model_golden", os.path.join(os.path.dirname(__file__), "golden", "make_jet_model_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    g = golden("jet_model_ref.npz")
+    poly, scal, sigma = m.evaluate(lib, g["T_std"], g["Tdot_std"], g["x"])
+    assert np.array_equal(poly, g["poly"]) and np.array_equal(scal, g["scalar"], equal_nan=True)
+    assert sigma == float(g["thrust_std"])
+
+
 def test_throttle_transform_roundtrip_and_bounds():
     jm = O.JetModel()
     for u in np.linspace(0, 100, 41):
