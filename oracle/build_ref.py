@@ -1,12 +1,17 @@
-"""Build recipe of oracle/_ref/libjetmodel_ref.so: the reference's OWN jet model, compiled from its source where it lies.
+"""Build recipes of oracle/_ref/: the reference's OWN sources, compiled from where they lie under /root/reference.
 
-TEST INFRASTRUCTURE.  Of the hot path's translation units only ``src/flight-controller/utils/src/JetModel.cpp`` (rows a6 and
-a17 of SURVEY §8: f, g, their partial derivatives, the standardisations and ``destandardizeThrottle_u2T``) is
-self-contained arithmetic: it includes Eigen and YARP headers but uses nothing of them, so it compiles against the empty
-stand-in headers in oracle/ref_stubs/.  Every other unit on the path needs the real Eigen / OsqpEigen / iDynTree / BLF and is
-unbuildable here.  No reference source is copied: g++ reads it under /root/reference; the only output is
-oracle/_ref/libjetmodel_ref.so (git-ignored, travels to the GPU box).  Used by tests/test_oracle.py to validate the
-restatement (oracle.vsmpc_oracle.JetModel, oracle/c/vsmpc_ref.c) and by tests/golden/make_jet_model_golden.py.
+TEST INFRASTRUCTURE.  The reference's build system (CMake + pixi) and its third-party libraries (Eigen, OsqpEigen / OSQP,
+iDynTree, YARP, BLF, matio, boost) are not available here, but the hot path's translation units only need the *headers* they
+include to exist.  oracle/ref_stubs/ provides stand-ins for those headers (see each file's first lines), and
+
+* ``build()``      -> oracle/_ref/libjetmodel_ref.so: ``utils/src/JetModel.cpp`` (rows a6 / a17 of SURVEY §8) + oracle/ref_shim.cpp;
+* ``build_mpc()``  -> oracle/_ref/libvsmpc_reference.so: the 13 translation units of ``VariableSamplingMPC`` (MPC_SOURCES
+  below: rows a1-a15, a17 and the call sequence of a16) + oracle/ref_mpc_shim.cpp.
+
+No reference source is copied: g++ reads the files under /root/reference; the only outputs are the two libraries
+(git-ignored, they travel to the GPU box, where /root/reference does not exist and the prebuilt files are used).
+Users: tests/test_reference_pinned.py, tests/test_oracle.py, tests/golden/make_reference_golden.py,
+tests/golden/make_jet_model_golden.py.
 """
 import os
 import subprocess

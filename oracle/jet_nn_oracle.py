@@ -6,7 +6,8 @@
   PINNED against outputs of the reference module itself (tests/golden/jet_nn.npz, tests/golden/make_jet_nn_golden.py).
 * per-jet EKF: ``SecondOrderJetModel.update`` (src/mujoco_lib/jet_kalman_filter.py:30-65): predict with the second-order
   jet model, covariance with the Jacobian evaluated at the PREDICTED state (:58), measurement = (T_nn, Tdot_nn), H = I.
-  CasADi is not installed here: parity of this part is unpinned (the Jacobian is written out analytically).
+  PINNED against outputs of the reference file itself, executed unmodified over a CasADi stand-in
+  (tests/golden/jet_ekf.npz, tests/golden/make_jet_ekf_golden.py; the Jacobian here is written out analytically).
 Only tests/ and bench.py's cpu_baseline may import this module."""
 from __future__ import annotations
 

@@ -5,14 +5,17 @@ This file restates, class by class, what the reference computes on the path
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg may import it; the
 product path (``paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub_b200``) never does.
 
-PARITY UNPINNED for the tick as a whole: the reference ships no tests, golden vectors or logs for this path
- and none of its third-party stack (Eigen, OSQP 1.0.0 / QDLDL 0.1.8 via osqp-eigen 0.11.0,
-iDynTree 14.0.2, BLF, YARP, matio) exists in the build container, so the reference binary cannot be
-run here.  What this oracle *is* pinned against: the reference's own object code for the jet model
-(``UT/src/JetModel.cpp`` compiled where it lies by oracle/build_ref.py; vectors frozen in
-tests/golden/jet_model_ref.npz), the reference's own fixtures (``src/trajectories/*.mat``), the second
-statement of the jet model in ``src/mujoco_lib/jet_kalman_filter.py:6-45``, and closed-form identities
-(tests/test_oracle.py).
+PARITY: PINNED against the reference's own code for everything except the OSQP iteration.  The reference
+ships no tests, golden vectors or logs for this path and its third-party stack (Eigen,
+OSQP 1.0.0 / QDLDL 0.1.8 via osqp-eigen 0.11.0, iDynTree 14.0.2, BLF, YARP, matio) is not in the build
+container — but its 13 hot-path translation units compile, where they lie, against the stand-in headers of
+oracle/ref_stubs/ (oracle/build_ref.py -> oracle/_ref/libvsmpc_reference.so), and tests/test_reference_pinned.py
+holds this file to what that library returns (dense P, q, A, l, u at 1e-12; minimiser and outputs at 1e-9;
+frozen in tests/golden/reference_{qp,ticks}.npz).  Further pins: the compiled ``UT/src/JetModel.cpp``
+(tests/golden/jet_model_ref.npz), the reference's fixtures (``src/trajectories/*.mat``), the second
+statement of the jet model in ``src/mujoco_lib/jet_kalman_filter.py:6-45``, closed-form identities
+(tests/test_oracle.py).  UNPINNED: the OSQP iteration (restated in oracle/c/vsmpc_ref.c from the published
+algorithm; the exact solver below is the arbiter of parity), iDynTree's kinematics (data here).
 
 Reference paths (``MPC/`` = src/flight-controller/momentum-based-linear-mpc-lib,
 ``UT/`` = src/flight-controller/utils):
