@@ -22,7 +22,9 @@ def raw(rep):
 
 
 qp, qu = raw(os.path.join(G, f"{tag}_qp.ncu-rep"))
-ln, lu = raw(os.path.join(G, f"{tag}_lin.ncu-rep"))
+# the linearise capture is optional (a short end-of-round run captures the QP kernel only)
+_lin = os.path.join(G, f"{tag}_lin.ncu-rep")
+ln, lu = raw(_lin) if os.path.exists(_lin) else ({}, {})
 keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__warps_active.avg.per_cycle_active',
@@ -67,7 +69,8 @@ traffic = unit_bytes(qp, qu, 'dram__bytes_read.sum') + unit_bytes(qp, qu, 'dram_
 json.dump({"qp_kernel_dram_bytes_per_launch": int(traffic), "kernel": qpk,
            "source": f"profiles/{tag}_ncu_summary.md (ncu --set full, B=1024)",
            "linearise_kernel_dram_bytes_per_launch": int(unit_bytes(ln, lu, 'dram__bytes_read.sum')
-                                                         + unit_bytes(ln, lu, 'dram__bytes_write.sum'))},
+                                                         + unit_bytes(ln, lu, 'dram__bytes_write.sum')) if ln
+           else json.load(open(os.path.join(P, "traffic.json"))).get("linearise_kernel_dram_bytes_per_launch")},
           open(os.path.join(P, "traffic.json"), "w"), indent=1)
 b = bench.get("bench", {})
 r = b.get("roofline", {})

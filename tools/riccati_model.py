@@ -2,8 +2,8 @@
 move-blocked inputs + Goldfarb-Idnani dual active set on the throttle boxes.
 
 This is NOT the oracle and NOT on the product path; it is the executable specification the CUDA
-kernel (csrc/vsmpc_kernels.cu) was written from, kept so the algorithm can be studied and
-unit-tested on CPU (tests/test_riccati_model.py compares it with the oracle's exact dense solve).
+kernel (csrc/vsmpc_qp_structured.cu) was written from, kept so the algorithm can be studied and
+unit-tested on CPU (tests/test_oracle.py compares it with the oracle's exact dense solve).
 
 Problem:  z = [x_0..x_N | dq_0..dq_{Nc-1} | v_0..v_{NT-1}],
   x_{k+1} = (I+dt_k A) x_k + dt_k B_J dq_{jb(k)} + dt_k B_T v_{tb(k)} + dt_k c,   x_0 given,
