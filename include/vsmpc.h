@@ -177,6 +177,14 @@ int vsmpc_set_full_solution(vsmpc_handle* h, int enable);
 int vsmpc_get_full_solution(vsmpc_handle* h, double* z_host);
 
 /* ---- inner seams, separately callable for parity tests -------------------------- */
+/* K1 alone — seam (ii), DynamicTemplateVariableSampling::updateInitialStates + the four getters
+ * (MPC/include/IMPCProblem/systemDynamic.h:39-65) plus a8-a14: copy the pack H2D and run the linearise kernel, nothing
+ * else (same work as vsmpc_set_state, whose name follows the outer surface).  Read its product with
+ * vsmpc_get_dynamics / vsmpc_get_qp_vectors. */
+int vsmpc_linearise(vsmpc_handle* h, const double* pack_host);
+/* K2 alone — seam (iii), the OsqpEigen calls of IMPCProblem::solve (IMPCProblem.cpp:225-279,296): solve the QP the last
+ * vsmpc_linearise / vsmpc_set_state left on the device and extract the outputs; blocks (same work as vsmpc_solve). */
+int vsmpc_solve_qp(vsmpc_handle* h);
 /* dense expansions of what the linearise kernel produced for the current tick:
  *   A double[B][26*26], BJ double[B][26*8], BT double[B][26*4], c double[B][26] (row-major),
  *   dt double[n_iter]  — SystemDynamicVS::get{A,BJoints,BThrottle}Matrix/getCVector + dt grid      */

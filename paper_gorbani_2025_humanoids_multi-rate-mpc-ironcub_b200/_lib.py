@@ -65,6 +65,7 @@ EXPORTS = [
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
     "vsmpc_get_output_device", "vsmpc_get_output_async", "vsmpc_wait_output", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
+    "vsmpc_linearise", "vsmpc_solve_qp",
     "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64",
     "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
 ]
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
         getattr(lib, f).argtypes = [H]
     lib.vsmpc_configure.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_set_state.argtypes = [H, C.c_void_p]
+    lib.vsmpc_linearise.argtypes = [H, C.c_void_p]
+    lib.vsmpc_solve_qp.argtypes = [H]
     lib.vsmpc_set_state_device.argtypes = [H, C.c_void_p]
     for f in ("vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait"):
         getattr(lib, f).argtypes = [H]

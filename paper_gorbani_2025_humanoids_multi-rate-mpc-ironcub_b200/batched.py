@@ -174,6 +174,17 @@ class BatchedVSMPC:
     def update(self, state: dict) -> bool:
         return self.update_pack(build_pack(state, self.sel))
 
+    def linearise(self, state: dict) -> bool:
+        """K1 alone (SURVEY §8b seam ii): pack + H2D + linearise kernel; read with get_dynamics / get_qp_vectors."""
+        pack = self._f64(build_pack(state, self.sel), (PACK_DOUBLES, self.B))
+        self._ck(self._lib.vsmpc_linearise(self._h, pack.ctypes.data), "vsmpc_linearise")
+        return True
+
+    def solve_qp(self) -> bool:
+        """K2 alone (SURVEY §8b seam iii): solve the QP the last linearise left on the device."""
+        self._ck(self._lib.vsmpc_solve_qp(self._h), "vsmpc_solve_qp")
+        return True
+
     def solveMPC(self) -> bool:
         self._ck(self._lib.vsmpc_solve(self._h), "vsmpc_solve")
         return True

@@ -513,6 +513,10 @@ int vsmpc_solve(vsmpc_handle* h)
     return rc ? rc : vsmpc_wait(h);
 }
 
+// SURVEY §8b names of the two inner seams (K1 alone, K2 alone); same host paths as the outer-surface entry points
+int vsmpc_linearise(vsmpc_handle* h, const double* pack_host) { return vsmpc_set_state(h, pack_host); }
+int vsmpc_solve_qp(vsmpc_handle* h) { return vsmpc_solve(h); }
+
 int vsmpc_get_output(vsmpc_handle* h, double* out_rows_host, int* status_host)
 {
     if (!h || h->B <= 0)

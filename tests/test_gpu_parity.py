@@ -84,6 +84,35 @@ def test_solve_matches_exact_oracle(solver, free_tick):
     mpc.close()
 
 
+def test_inner_seams_called_alone():
+    """K1 (vsmpc_linearise) and K2 (vsmpc_solve_qp) are separately callable; K1's product is checked
+    against the oracle's assembly before K2 runs on it, K2's minimiser against the oracle's exact solve."""
+    B = 16
+    mpc, nom, per, traj = make(B, 0, near=0.3)
+    mpc.configure(nom)
+    mpc.linearise(per)
+    A, BJ, BT, c, dt = mpc.get_dynamics()
+    q, l, u = mpc.get_qp_vectors()
+    oracles = []
+    for i in range(B):
+        o = OracleInstance(nom, i, trajectories=traj)
+        o.update(per)
+        oA, oBJ, oBT, oc, odt = o.dynamics()
+        assert max(rel_err(A[i], oA), rel_err(BJ[i], oBJ), rel_err(BT[i], oBT), rel_err(c[i], oc)) < REL_ASM
+        assert max(rel_err(q[i], o.mpc.gradient), rel_err(l[i], o.mpc.lowerBound), rel_err(u[i], o.mpc.upperBound)) < REL_ASM
+        oracles.append(o)
+    mpc.solve_qp()
+    z = mpc.getSolution()
+    _, status = mpc.get_output()
+    assert (status == 0).all()
+    for i, o in enumerate(oracles):
+        assert rel_err(z[i], o.solve()) < REL_SOL
+    # one solve per linearise, like the reference's tick
+    with pytest.raises(pkg("batched").VsmpcError):
+        mpc.solve_qp()
+    mpc.close()
+
+
 @pytest.mark.parametrize("solver", [0, 2])
 @pytest.mark.parametrize("free_tick", [False, True])
 def test_outputs_without_full_solution(solver, free_tick):
