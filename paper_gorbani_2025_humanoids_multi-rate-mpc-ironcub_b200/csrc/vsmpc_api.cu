@@ -597,12 +597,12 @@ int vsmpc_get_dynamics(vsmpc_handle* h, double* A, double* BJ, double* BT, doubl
         return fail(h, VSMPC_ERR_STATE, "vsmpc_get_dynamics: configure first");
     CK(cudaSetDevice(h->device));
     const size_t B = h->B;
-    double *dA, *dBJ, *dBT, *dc;
-    CK(dalloc(&dA, B * NX * NX));
-    CK(dalloc(&dBJ, B * NX * NJ));
-    CK(dalloc(&dBT, B * NX * NT));
-    CK(dalloc(&dc, B * NX));
-    cudaError_t e = launch_expand_dynamics(h->d_cfg, h->B, h->d_qd, dA, dBJ, dBT, dc, h->stream);
+    double *dA = nullptr, *dBJ = nullptr, *dBT = nullptr, *dc = nullptr; // freed on every path below
+    cudaError_t e = dalloc(&dA, B * NX * NX);
+    if (e == cudaSuccess) e = dalloc(&dBJ, B * NX * NJ);
+    if (e == cudaSuccess) e = dalloc(&dBT, B * NX * NT);
+    if (e == cudaSuccess) e = dalloc(&dc, B * NX);
+    if (e == cudaSuccess) e = launch_expand_dynamics(h->d_cfg, h->B, h->d_qd, dA, dBJ, dBT, dc, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(A, dA, B * NX * NX * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(BJ, dBJ, B * NX * NJ * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(BT, dBT, B * NX * NT * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -624,11 +624,11 @@ int vsmpc_get_qp_vectors(vsmpc_handle* h, double* q, double* l, double* u)
         return fail(h, VSMPC_ERR_STATE, "vsmpc_get_qp_vectors: configure first");
     CK(cudaSetDevice(h->device));
     const size_t B = h->B;
-    double *dq, *dl, *du;
-    CK(dalloc(&dq, B * h->cfg.n_var));
-    CK(dalloc(&dl, B * h->cfg.n_con));
-    CK(dalloc(&du, B * h->cfg.n_con));
-    cudaError_t e = launch_expand_qp_vectors(h->d_cfg, h->B, h->d_qd, dq, dl, du, h->stream);
+    double *dq = nullptr, *dl = nullptr, *du = nullptr; // freed on every path below
+    cudaError_t e = dalloc(&dq, B * h->cfg.n_var);
+    if (e == cudaSuccess) e = dalloc(&dl, B * h->cfg.n_con);
+    if (e == cudaSuccess) e = dalloc(&du, B * h->cfg.n_con);
+    if (e == cudaSuccess) e = launch_expand_qp_vectors(h->d_cfg, h->B, h->d_qd, dq, dl, du, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(q, dq, B * h->cfg.n_var * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(l, dl, B * h->cfg.n_con * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(u, du, B * h->cfg.n_con * 8, cudaMemcpyDeviceToHost, h->stream);
