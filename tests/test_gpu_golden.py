@@ -125,3 +125,45 @@ def test_single_instance_mirror_matches_batched():
     assert m.getJointsReferencePosition().shape == (23,)
     assert rel_err(m.getSolution(), g["pin_z"][i]) < REL
     assert m.getNStatesMPC() == 26.0 and m.getNInputMPC() == 12.0 and m.getNOptimizationVariables() == 588
+
+
+@pytest.mark.parametrize("params", [None, dict(nIter=34, nIterSmall=14, controlHorizon=24), dict(useEstimatedThrust=False)])
+def test_cuda_against_the_live_compiled_reference(params):
+    """The CUDA path and the reference's own code (oracle/_ref/libvsmpc_reference.so, compiled from the reference's sources —
+    it travels to the GPU box) side by side on states no golden file holds: consecutive ticks with a new perturbed state
+    every tick (throttle release and reference-window shift included), gradient and bounds at 1e-12 on every tick, minimiser
+    and the getters at the north-star tolerance."""
+    import reference_driver
+    if reference_driver.lib() is None:
+        pytest.skip("oracle/_ref/libvsmpc_reference.so not built (no /root/reference here)")
+    syn, bat, L = pkg("synthetic"), pkg("batched"), pkg("_lib")
+    traj = load_trajectories()
+    B, ticks = 3, 24
+    nom = syn.make_states(B, seed=11, perturbed=False)
+    refs = [reference_driver.ReferenceInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), full_solution=True)
+    mpc.configure(nom)
+    assert all((r.n_var, r.n_con) == (mpc.n_var, mpc.n_con) for r in refs)
+    sel = pkg("pack").DEFAULT_JOINT_SELECTOR
+    for t in range(ticks):
+        st = syn.make_states(B, seed=7000 + t, perturbed=True, near_bound_fraction=0.5)
+        mpc.update(st)
+        q, l, u = mpc.get_qp_vectors()
+        mpc.solveMPC()
+        z = mpc.getSolution()
+        out, status = mpc.get_output()
+        assert (status == 0).all(), (t, status)
+        for i, r in enumerate(refs):
+            r.update(st)
+            _, rq, _, rl, ru = r.qp()
+            assert rel_err(q[i], rq) < 1e-12 and rel_err(l[i], rl) < 1e-12 and rel_err(u[i], ru) < 1e-12, (t, i)
+            assert rel_err(z[i], r.solve()) < REL, (t, i)
+            o = r.output()
+            assert o["status"] == 1
+            assert rel_err(out[i, L.OUT_THROTTLE:L.OUT_THROTTLE + 4], o["throttle"]) < REL
+            assert rel_err(out[i, L.OUT_THRUST:L.OUT_THRUST + 4], o["thrust"]) < REL
+            assert rel_err(out[i, L.OUT_THRUST_DOT:L.OUT_THRUST_DOT + 4], o["thrust_dot"]) < REL
+            assert rel_err(out[i, L.OUT_JOINTS_REF:L.OUT_JOINTS_REF + 8], o["joints"][sel]) < REL
+    for r in refs:
+        r.close()
+    mpc.close()
