@@ -6,6 +6,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._lib import OUT_DOUBLES
+
 
 def shard_range(n_total: int, rank: int, world: int):
     """Contiguous instance range [lo, hi) of `rank`: [g*B/G, (g+1)*B/G)."""
@@ -43,28 +45,35 @@ class ShardedVSMPC:
         self.lo, self.hi = shard_range(n_total, rank, world)
         if factory is None:
             from .batched import BatchedVSMPC as factory
-        self.local = factory(self.hi - self.lo, params, trajectories, device=device, solver=solver)
+        # a batch smaller than the world leaves some ranks without instances: they hold no handle (vsmpc_create rejects
+        # an empty batch) and only take part in the collection of the output rows
+        self.local = factory(self.hi - self.lo, params, trajectories, device=device, solver=solver) \
+            if self.hi > self.lo else None
 
     def _cols(self, a):
         return np.ascontiguousarray(np.asarray(a)[:, self.lo:self.hi])
 
     def configure_pack(self, pack, joint_pos_sel, phase0=None):
+        if self.local is None:
+            return True
         ph = None if phase0 is None else np.ascontiguousarray(np.asarray(phase0)[self.lo:self.hi])
         return self.local.configure_pack(self._cols(pack), self._cols(joint_pos_sel), ph)
 
     def update_pack(self, pack):
-        return self.local.update_pack(self._cols(pack))
+        return True if self.local is None else self.local.update_pack(self._cols(pack))
 
     def solveMPC(self):
-        return self.local.solveMPC()
+        return True if self.local is None else self.local.solveMPC()
 
     def get_output_local(self):
+        if self.local is None:
+            return np.zeros((0, OUT_DOUBLES)), np.zeros(0, dtype=np.int32)
         return self.local.get_output()
 
     def get_output_all(self, group=None, device=None):
         """Collect the output rows of every rank (the only communication of the whole path)."""
         import torch
-        out, status = self.local.get_output()
+        out, status = self.get_output_local()
         dev = device if device is not None else "cpu"
         rows = torch.from_numpy(np.concatenate([out, status[:, None].astype(np.float64)], axis=1)).to(dev)
         full = gather_rows(rows, self.n_total, group).cpu().numpy()

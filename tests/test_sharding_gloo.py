@@ -67,12 +67,12 @@ def _worker(rank, world, port, n_total, q):
     ref = FakeLocal(n_total, None, None)
     ref.update_pack(pack)
     ro, rs = ref.get_output()
-    ok = np.array_equal(out, ro) and np.array_equal(status, rs) and (m.hi - m.lo) in (n_total // world, n_total // world + 1)
+    ok = out.shape == ro.shape and np.array_equal(out, ro) and np.array_equal(status, rs) and (m.hi - m.lo) in (n_total // world, n_total // world + 1)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_total", [64, 37])
+@pytest.mark.parametrize("n_total", [64, 37, 1])     # 1: rank 0 owns no instance and only joins the gather
 def test_sharded_gather_world_size_2(n_total):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
