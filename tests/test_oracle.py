@@ -277,3 +277,39 @@ def test_pivot_active_set_spec_on_random_box_qps():
                 assert v[i] == (up if sgn > 0 else lo) and lam >= -1e-9
                 assert abs(y[i] + sgn * lam) < 1e-8 * max(1.0, abs(y[i]))
             assert np.abs(y[free]).max(initial=0.0) < 1e-8 * max(1.0, np.abs(g).max())
+
+
+def test_warm_started_pivot_active_set_spec():
+    """tools/condensed_model.box_qp_pivot_warm (specification of the warm start planned for the long-horizon kernel: start
+    from a guessed working set, T = H and only the guessed-free indices pivoted, drop phase, then the dual iterations):
+    whatever the guess — exact, none, a vertex, noisy, random — it returns the minimiser of the cold method, and an exact
+    guess of an almost saturated problem costs a small fraction of the cold method's pivots."""
+    from condensed_model import box_qp_pivot, box_qp_pivot_warm
+    rng = np.random.default_rng(11)
+    lo, up = -1.52115, 1.65096
+    saved = []
+    for n, scale, shift in ((6, 0.3, 0.0), (24, 1.0, 0.0), (44, 3.0, 2.0), (92, 10.0, -3.0), (140, 30.0, 20.0)):
+        for rep in range(3):
+            A = rng.normal(size=(n, n + 3))
+            H = A @ A.T / (n + 3) + rng.uniform(1e-3, 0.2) * np.eye(n)
+            g = scale * rng.normal(size=n) + shift
+            v, active, status = box_qp_pivot(H, g, lo, up, max_iter=20 * n)
+            assert status == 0
+            exact = np.zeros(n, dtype=int)
+            for i, sgn, _ in active:
+                exact[i] = int(sgn)
+            guesses = dict(exact=exact, none=np.zeros(n, dtype=int), all_lo=-np.ones(n, dtype=int), all_up=np.ones(n, dtype=int),
+                           noisy=np.where(rng.random(n) < 0.15, rng.integers(-1, 2, n), exact), random=rng.integers(-1, 2, n))
+            for name, a0 in guesses.items():
+                w, aw, sw, pivots = box_qp_pivot_warm(H, g, lo, up, a0, max_iter=40 * n)
+                assert sw == 0, (n, name)
+                assert np.abs(w - v).max() < 1e-8, (n, name)
+                assert {(i, int(s)) for i, s, _ in aw} == {(i, int(s)) for i, s, _ in active}, (n, name)
+                assert all(lam >= -1e-9 for _, _, lam in aw)
+                if name == "exact":
+                    assert pivots == n - len(active)          # only the free indices are pivoted, nothing else happens
+                    saved.append((n + len(active), pivots))
+                if name == "none":
+                    assert pivots >= n                        # = the cold method (inverse, then the dual iterations)
+    cold, warm = (sum(x) for x in zip(*saved))
+    assert warm < 0.5 * cold

@@ -45,20 +45,10 @@ def exchange_pivot(T, q):
     return d
 
 
-def box_qp_pivot(H, g, lo, up, max_iter=200, tol=1e-10):
-    """min 1/2 v'Hv + g'v, lo <= v <= up: Goldfarb-Idnani dual active set on the principal pivot transform.
-    T starts as H^-1 (every index exchanged) and stays the transform of H over the free set F: (v_F, y_W) = T (y_F, v_W)
-    with y = Hv = -g - sum_a s_a lam_a e_a.  For a violated free p with sign s, raising its multiplier by t moves v_F by
-    -t s T[F, p] and lam_a by -t r_a, r_a = -s_a s T[a, p]; T[p, p] is the step denominator.  A full step pivots p into
-    the working set, a blocked step pivots the blocking index back out.  Returns (v, [(index, sign, multiplier)], status)."""
-    n = H.shape[0]
-    T = np.array(H, dtype=float)
-    for q in range(n):
-        if not exchange_pivot(T, q) > 0:
-            return np.zeros(n), [], 2
-    vv = -T @ g
-    act = np.zeros(n, dtype=int)
-    lam = np.zeros(n)
+def _dual_pivot_loop(T, vv, act, lam, lo, up, max_iter, tol):
+    """Goldfarb-Idnani dual iterations on the principal pivot transform, from any S-pair: T = transform of H over the free
+    set {act == 0}, vv = minimiser of the sub-problem with the working set held at its bounds, lam >= 0 on the working set.
+    Returns (status, iterations); T, vv, act, lam are updated in place."""
     status, it = 0, 0
     while True:
         viol = np.where(act == 0, np.maximum(np.maximum(vv - up, lo - vv), 0.0), 0.0)
@@ -84,8 +74,8 @@ def box_qp_pivot(H, g, lo, up, max_iter=200, tol=1e-10):
             if not np.isfinite(t):
                 status = 2
                 break
-            vv = np.where(act == 0, vv - t * s * c, vv)
-            lam = np.where(act != 0, lam - t * r, lam)
+            vv[:] = np.where(act == 0, vv - t * s * c, vv)
+            lam[:] = np.where(act != 0, lam - t * r, lam)
             lam_p += t
             if t2 <= t1:
                 exchange_pivot(T, p)
@@ -95,8 +85,63 @@ def box_qp_pivot(H, g, lo, up, max_iter=200, tol=1e-10):
             act[drop], lam[drop] = 0, 0.0
         if status:
             break
+    return status, it
+
+
+def box_qp_pivot(H, g, lo, up, max_iter=200, tol=1e-10):
+    """min 1/2 v'Hv + g'v, lo <= v <= up: Goldfarb-Idnani dual active set on the principal pivot transform.
+    T starts as H^-1 (every index exchanged) and stays the transform of H over the free set F: (v_F, y_W) = T (y_F, v_W)
+    with y = Hv = -g - sum_a s_a lam_a e_a.  For a violated free p with sign s, raising its multiplier by t moves v_F by
+    -t s T[F, p] and lam_a by -t r_a, r_a = -s_a s T[a, p]; T[p, p] is the step denominator.  A full step pivots p into
+    the working set, a blocked step pivots the blocking index back out.  Returns (v, [(index, sign, multiplier)], status)."""
+    n = H.shape[0]
+    T = np.array(H, dtype=float)
+    for q in range(n):
+        if not exchange_pivot(T, q) > 0:
+            return np.zeros(n), [], 2
+    vv = -T @ g
+    act = np.zeros(n, dtype=int)
+    lam = np.zeros(n)
+    status, _ = _dual_pivot_loop(T, vv, act, lam, lo, up, max_iter, tol)
     active = [(int(i), float(act[i]), float(lam[i])) for i in np.nonzero(act)[0]]
     return vv, active, status
+
+
+def box_qp_pivot_warm(H, g, lo, up, act0, max_iter=200, tol=1e-10):
+    """The same problem started from a guessed working set act0 (+1: at `up`, -1: at `lo`, 0: free; e.g. the working set of the
+    previous controller tick) — NOT yet in the CUDA kernels, the specification of the next step for the long horizons.
+    T starts as H itself (every index in the working set: no inverse) and only the guessed-free indices are pivoted:
+    |F0| pivots instead of n + |W|.
+      phase 1 (drop only, finite): solve the sub-problem on the guessed set, (v_F, y_W) = T (-g_F, b_W),
+        lam_a = -s_a (y_a + g_a); while some lam_a < 0, pivot the most negative one out of the working set and re-solve.
+        It ends on an S-pair (sub-problem optimum, lam >= 0) whatever the guess was;
+      phase 2: the dual iterations of box_qp_pivot from that S-pair (adds the bounds still violated).
+    Returns (v, [(index, sign, multiplier)], status, pivots) with pivots = exchange pivots executed in total."""
+    n = H.shape[0]
+    lo_v, up_v = np.broadcast_to(np.asarray(lo, float), (n,)), np.broadcast_to(np.asarray(up, float), (n,))
+    act = np.array(act0, dtype=int).copy()
+    T = np.array(H, dtype=float)
+    pivots = 0
+    for q in np.flatnonzero(act == 0):
+        pivots += 1
+        if not exchange_pivot(T, q) > 0:
+            return np.zeros(n), [], 2, pivots
+    while True:
+        b = np.where(act > 0, up_v, lo_v)
+        out = T @ np.where(act == 0, -g, b)
+        lam = np.where(act != 0, -act * (out + g), 0.0)
+        a = int(np.argmin(lam))
+        if not lam[a] < -tol:
+            break
+        pivots += 1
+        if not exchange_pivot(T, a) > 0:
+            return np.zeros(n), [], 2, pivots
+        act[a] = 0
+    vv = np.where(act == 0, out, b)
+    lam = np.maximum(lam, 0.0)
+    status, it = _dual_pivot_loop(T, vv, act, lam, lo, up, max_iter, tol)
+    active = [(int(i), float(act[i]), float(lam[i])) for i in np.nonzero(act)[0]]
+    return vv, active, status, pivots + it
 
 
 class CondensedQP:
