@@ -193,6 +193,27 @@ int vsmpc_get_dynamics(vsmpc_handle* h, double* A, double* BJ, double* BT, doubl
 int vsmpc_get_qp_vectors(vsmpc_handle* h, double* q, double* l, double* u);
 /* executed Riccati factorisations / back-solves per instance in the last solve (int[B] each) */
 int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve);
+/* exchange pivots of the reduced throttle QP executed per instance in the last solve (inverse of the reduced Hessian +
+ * dual active-set iterations; int[B]; the condensed kernels report it, the cross-check kernels leave 0) */
+int vsmpc_get_pivot_counts(vsmpc_handle* h, int* n_pivot);
+
+/* ---- the QPInput fields the path WRITES (what a caller of update(QPInput&) reads back afterwards) ---------------
+ * ReferenceTrackingCost::computeHessianAndGradient publishes the tracked references on every window shift
+ * (costsVSMPC.cpp:155-160: QPInput::setPosCoMReference / setRPYReference / setMomentumReference) and
+ * LinearMomentumDynamicVS publishes the gravity-compensation factor every tick (systemDynamicsVSMPC.cpp:310:
+ * QPInput::setAlphaGravity).  refs: double[B][VSMPC_REF_DOUBLES], valid after vsmpc_configure / vsmpc_set_state. */
+#define VSMPC_REF_ALPHA_GRAVITY  0   /* 1  QPInput::getAlphaGravity()      */
+#define VSMPC_REF_POS_COM        1   /* 3  QPInput::getPosCoMReference()   */
+#define VSMPC_REF_RPY            4   /* 3  QPInput::getRPYReference()      */
+#define VSMPC_REF_MOMENTUM       7   /* 6  QPInput::getMomentumReference() (linear, angular) */
+#define VSMPC_REF_DOUBLES       13
+int vsmpc_get_references(vsmpc_handle* h, double* refs_host);
+/* IMPCProblem::getHessian (IMPCProblem.h:88): dense n_var x n_var, row-major, of one instance (constant after configure,
+ * IMPCProblem.cpp:152-175) */
+int vsmpc_get_hessian(vsmpc_handle* h, int instance, double* P_host);
+/* IMPCProblem::getLinearConstraintMatrix (IMPCProblem.h:100): dense n_con x n_var, row-major, of one instance for the
+ * current tick, in the reference's row order (dynamics, initial state, throttle; variableSamplingMPC.cpp:77-84) */
+int vsmpc_get_constraint_matrix(vsmpc_handle* h, int instance, double* A_host);
 /* test hook: overwrite the two 20-tick phase counters (ReferenceTrackingCost::m_counter,
  * ThrottleConstraint::m_counter) of every instance; -1 leaves a counter unchanged */
 int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter);

@@ -171,6 +171,13 @@ public:
     bool wait() { return check(vsmpc_wait(m_h)); }
     // rows: double[B][VSMPC_OUT_DOUBLES], status: int[B]
     bool getOutput(double* rows, int* status) { return check(vsmpc_get_output(m_h, rows, status)); }
+    // refs: double[B][VSMPC_REF_DOUBLES] — the QPInput fields update() writes (costsVSMPC.cpp:155-160,
+    // systemDynamicsVSMPC.cpp:310)
+    bool getReferences(double* refs) { return check(vsmpc_get_references(m_h, refs)); }
+    // IMPCProblem::getHessian / getLinearConstraintMatrix / getGradient / getLowerBound / getUpperBound (IMPCProblem.h:88-112)
+    bool getHessian(int instance, double* P) { return check(vsmpc_get_hessian(m_h, instance, P)); }
+    bool getLinearConstraintMatrix(int instance, double* A) { return check(vsmpc_get_constraint_matrix(m_h, instance, A)); }
+    bool getQPVectors(double* q, double* l, double* u) { return check(vsmpc_get_qp_vectors(m_h, q, l, u)); }
     bool setFullSolution(bool on) { return check(vsmpc_set_full_solution(m_h, on ? 1 : 0)); }
     bool getSolution(double* z) { return check(vsmpc_get_full_solution(m_h, z)); }
     int getNOptimizationVariables() const { return vsmpc_n_var(m_h); }
@@ -236,11 +243,18 @@ public:
         m_ctrlHorizon = p.controlHorizon;
         m_nThrottleBlocks = p.controlHorizon - p.nIterSmall + 1;
         std::memset(m_out, 0, sizeof(m_out));
+        for (int a = 0; a < VSMPC_NJ; ++a)
+            m_out[VSMPC_OUT_JOINTS_REF + a] = jp[a];
         m_status = 0;
-        return m_impl.configure(pack.v, jp);
+        return m_impl.configure(pack.v, jp) && m_impl.getReferences(m_refs);
     }
-    // IMPCProblem::update(QPInput&) (IMPCProblem.cpp:150-194)
-    bool update(const Pack& pack) { return m_impl.update(pack.v); }
+    // IMPCProblem::update(QPInput&) (IMPCProblem.cpp:150-194); afterwards the published QPInput fields are current
+    bool update(const Pack& pack) { return m_impl.update(pack.v) && m_impl.getReferences(m_refs); }
+    // the QPInput fields the path writes during configure / update
+    double getAlphaGravity() const { return m_refs[VSMPC_REF_ALPHA_GRAVITY]; }
+    template <class V> bool getPosCoMReference(V&& out) const { return copyOut(out, m_refs + VSMPC_REF_POS_COM, 3, "getPosCoMReference"); }
+    template <class V> bool getRPYReference(V&& out) const { return copyOut(out, m_refs + VSMPC_REF_RPY, 3, "getRPYReference"); }
+    template <class V> bool getMomentumReference(V&& out) const { return copyOut(out, m_refs + VSMPC_REF_MOMENTUM, 6, "getMomentumReference"); }
     // VariableSamplingMPC::solveMPC (variableSamplingMPC.cpp:88-112); like the reference it returns true
     // also when the solver status is not "solved" (outputs are then held)
     bool solveMPC()
@@ -287,6 +301,20 @@ public:
     int getNOptimizationVariables() const { return m_impl.getNOptimizationVariables(); }
     int getNConstraints() const { return m_impl.getNConstraints(); }
     int getQPProblemStatus() const { return m_status; }
+    // dense row-major copies (the reference returns Eigen::Ref to column-major members; same entries)
+    template <class V> bool getHessian(V&& out)
+    {
+        const size_t n = static_cast<size_t>(getNOptimizationVariables());
+        return static_cast<size_t>(out.size()) == n * n && m_impl.getHessian(0, out.data());
+    }
+    template <class V> bool getLinearConstraintMatrix(V&& out)
+    {
+        const size_t n = static_cast<size_t>(getNOptimizationVariables()), m = static_cast<size_t>(getNConstraints());
+        return static_cast<size_t>(out.size()) == n * m && m_impl.getLinearConstraintMatrix(0, out.data());
+    }
+    template <class V> bool getGradient(V&& out) { return qpVector(out, 0); }
+    template <class V> bool getLowerBound(V&& out) { return qpVector(out, 1); }
+    template <class V> bool getUpperBound(V&& out) { return qpVector(out, 2); }
     BatchedMPC& impl() { return m_impl; }
 
 private:
@@ -300,10 +328,23 @@ private:
         std::memcpy(out.data(), src, sizeof(double) * n);
         return true;
     }
+    template <class V> bool qpVector(V&& out, int which)
+    {
+        const size_t n = static_cast<size_t>(getNOptimizationVariables()), m = static_cast<size_t>(getNConstraints());
+        if (static_cast<size_t>(out.size()) != (which == 0 ? n : m))
+            return false;
+        std::vector<double> q(n), l(m), u(m);
+        if (!m_impl.getQPVectors(q.data(), l.data(), u.data()))
+            return false;
+        const std::vector<double>& src = which == 0 ? q : (which == 1 ? l : u);
+        std::memcpy(out.data(), src.data(), sizeof(double) * src.size());
+        return true;
+    }
     BatchedMPC m_impl;
     std::vector<int> m_sel;
     std::vector<double> m_jointsPositionReference;
     double m_out[VSMPC_OUT_DOUBLES];
+    double m_refs[VSMPC_REF_DOUBLES] = {};
     int m_status = 0;
     int m_nIter = 0, m_ctrlHorizon = 0, m_nThrottleBlocks = 0;
 };

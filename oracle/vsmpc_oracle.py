@@ -1025,7 +1025,10 @@ class IMPCProblem:
         self.qp_solver = qp_solver
         self.statusQPProblem = None
 
-    def configure(self, params, qpInput, trajectories):  # :3-148
+    def configure(self, params, qpInput, trajectories, phase0=0):  # :3-148
+        """phase0 (NOT in the reference; mirrors the phase0 argument of vsmpc_configure): number of ticks by which the two
+        20-tick counters (ReferenceTrackingCost::m_counter, ThrottleConstraint::m_counter) start ahead, so that a batch can
+        be checked with staggered throttle-release phases.  0 = reference behaviour."""
         self.setCostAndConstraints(params, qpInput)
         for c in self.vectorCosts:
             c.readConfigParameters(params, qpInput, trajectories)
@@ -1036,6 +1039,8 @@ class IMPCProblem:
         for c in self.vectorCosts:
             c.configureDynVectorsSize(qpInput)
             c.configureSizeHessianAndGradient()
+            if phase0 and hasattr(c, "counter") and hasattr(c, "ratio"):
+                c.counter = (c.ratio - 1 + int(phase0)) % c.ratio
         for c in self.vectorCosts:
             c.computeHessianAndGradient(qpInput)
             self.hessian += c.hessian
@@ -1044,6 +1049,8 @@ class IMPCProblem:
         for c in self.vectorConstraints:
             c.configureDynVectorsSize(qpInput)
             c.configureSizeConstraintMatrixAndBounds()
+            if phase0 and hasattr(c, "counter") and hasattr(c, "ratio"):
+                c.counter = (c.ratio - 1 + int(phase0)) % c.ratio
             n += c.getNConstraints()
         self.linearMatrix = np.zeros((n, self.nVar))
         self.lowerBound = np.zeros(n)

@@ -17,6 +17,8 @@ OUT_DOUBLES = 54
 OUT_DELTA_Q, OUT_THROTTLE, OUT_THRUST, OUT_THRUST_DOT, OUT_FINAL_STATE, OUT_JOINTS_REF = 0, 8, 12, 16, 20, 46
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_NUMERICAL = 0, 1, 2
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, 1, 2, 3, 4
+REF_DOUBLES = 13
+REF_ALPHA_GRAVITY, REF_POS_COM, REF_RPY, REF_MOMENTUM = 0, 1, 4, 7
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -66,7 +68,8 @@ EXPORTS = [
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",
     "vsmpc_get_output_device", "vsmpc_get_output_async", "vsmpc_wait_output", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
     "vsmpc_linearise", "vsmpc_solve_qp",
-    "vsmpc_get_counts", "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64",
+    "vsmpc_get_counts", "vsmpc_get_pivot_counts", "vsmpc_get_references", "vsmpc_get_hessian", "vsmpc_get_constraint_matrix",
+    "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64",
     "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
 ]
 
@@ -106,6 +109,10 @@ def load() -> C.CDLL:
     lib.vsmpc_get_dynamics.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_get_qp_vectors.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_get_counts.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.vsmpc_get_pivot_counts.argtypes = [H, C.c_void_p]
+    lib.vsmpc_get_references.argtypes = [H, C.c_void_p]
+    lib.vsmpc_get_hessian.argtypes = [H, C.c_int, C.c_void_p]
+    lib.vsmpc_get_constraint_matrix.argtypes = [H, C.c_int, C.c_void_p]
     lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
     lib.vsmpc_debug_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]

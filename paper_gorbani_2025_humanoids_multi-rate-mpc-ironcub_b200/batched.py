@@ -255,5 +255,32 @@ class BatchedVSMPC:
         self._ck(self._lib.vsmpc_get_counts(self._h, nf.ctypes.data, ns.ctypes.data), "vsmpc_get_counts")
         return nf, ns
 
+    def get_pivot_counts(self):
+        """Exchange pivots of the reduced throttle QP per instance in the last solve (inverse + active set)."""
+        n = np.empty(self.B, dtype=np.int32)
+        self._ck(self._lib.vsmpc_get_pivot_counts(self._h, n.ctypes.data), "vsmpc_get_pivot_counts")
+        return n
+
+    def get_references(self) -> dict:
+        """The QPInput fields the path writes (costsVSMPC.cpp:155-160, systemDynamicsVSMPC.cpp:310), per instance:
+        alphaGravity (B,), posCoMReference (B,3), RPYReference (B,3), momentumReference (B,6)."""
+        r = np.empty((self.B, L.REF_DOUBLES))
+        self._ck(self._lib.vsmpc_get_references(self._h, r.ctypes.data), "vsmpc_get_references")
+        return dict(alphaGravity=r[:, L.REF_ALPHA_GRAVITY].copy(), posCoMReference=r[:, L.REF_POS_COM:L.REF_POS_COM + 3].copy(),
+                    RPYReference=r[:, L.REF_RPY:L.REF_RPY + 3].copy(),
+                    momentumReference=r[:, L.REF_MOMENTUM:L.REF_MOMENTUM + 6].copy())
+
+    def getHessian(self, instance: int = 0) -> np.ndarray:
+        """IMPCProblem::getHessian of one instance, dense (n_var, n_var)."""
+        P = np.empty((self.n_var, self.n_var))
+        self._ck(self._lib.vsmpc_get_hessian(self._h, int(instance), P.ctypes.data), "vsmpc_get_hessian")
+        return P
+
+    def getLinearConstraintMatrix(self, instance: int = 0) -> np.ndarray:
+        """IMPCProblem::getLinearConstraintMatrix of one instance for the current tick, dense (n_con, n_var)."""
+        A = np.empty((self.n_con, self.n_var))
+        self._ck(self._lib.vsmpc_get_constraint_matrix(self._h, int(instance), A.ctypes.data), "vsmpc_get_constraint_matrix")
+        return A
+
     def debug_set_counters(self, ref_counter: int = -1, throttle_counter: int = -1):
         self._ck(self._lib.vsmpc_debug_set_counters(self._h, ref_counter, throttle_counter), "vsmpc_debug_set_counters")

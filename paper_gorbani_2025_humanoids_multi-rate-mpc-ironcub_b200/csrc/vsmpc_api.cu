@@ -1,6 +1,7 @@
 // C-ABI host layer (include/vsmpc.h): owns the device buffers of one batch of MPC instances on one
 // GPU and launches the kernels.  Mirrors the call sequence of the reference's
 // VariableSamplingMPC (configure -> update -> solveMPC -> getters).
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -29,6 +30,9 @@ cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const doubl
                                    double* BT, double* c, cudaStream_t s);
 cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
                                      double* u, cudaStream_t s);
+cudaError_t launch_expand_hessian(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, double* P, cudaStream_t s);
+cudaError_t launch_expand_constraint_matrix(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, const double* qd_inst,
+                                            double* scratch, double* M, cudaStream_t s);
 size_t generic_scratch_doubles(const DeviceConfig& cfg);
 bool generic_supported(const DeviceConfig& cfg);
 cudaError_t launch_qp_generic(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
@@ -44,19 +48,19 @@ int condensed_wide_phase_clocks(long long* host, int n);
 size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
-                                int* n_solve, int want_z, cudaStream_t s);
+                                int* n_solve, int* n_pivot, int want_z, cudaStream_t s);
 bool condensed_wide_supported(const DeviceConfig& cfg);
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
-                                     int want_z, cudaStream_t s);
+                                     int* n_pivot, int want_z, cudaStream_t s);
 } // namespace vsmpc
 
 using namespace vsmpc;
 
 constexpr int SOLVER_WIDE = 3;   // internal: chosen by the default solver for long horizons
-static int g_last_qp_solver = 0; // development (vsmpc_debug_phase_clocks): which kernel stamped its clocks last
+static std::atomic<int> g_last_qp_solver{0}; // development (vsmpc_debug_phase_clocks, handle-less): which kernel stamped its clocks last
 
 struct vsmpc_handle
 {
@@ -95,7 +99,8 @@ struct vsmpc_handle
     double* d_z = nullptr;
     double* d_out = nullptr;
     int* d_status = nullptr;
-    int *d_nf = nullptr, *d_ns = nullptr;
+    int *d_nf = nullptr, *d_ns = nullptr, *d_np = nullptr;   // factorisations, forward passes, exchange pivots of the last solve
+    cudaEvent_t ev_stream = nullptr;     // orders a new stream behind the old one in vsmpc_set_stream
     // device-resident closed loop
     PlantModel* d_pm = nullptr;
     double* d_ps = nullptr;
@@ -150,6 +155,39 @@ template <typename T> cudaError_t dalloc(T** p, size_t n)
 }
 } // namespace
 
+// VariableSamplingMPC::configure (variableSamplingMPC.cpp:56-60): the held outputs start from zero and the joint
+// reference from Robot::getJointPos(), so that a tick that fails before any success holds the configure-time posture
+// (ps != nullptr: rollout — the commands in effect in the plant state are what a failed first tick holds)
+__global__ void seed_outputs_kernel(int B, const double* __restrict__ jpos, const double* __restrict__ ps,
+                                    double* __restrict__ out_rows, int* __restrict__ status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B)
+        return;
+    double* o = out_rows + (size_t)i * VSMPC_OUT_DOUBLES;
+    for (int e = 0; e < VSMPC_OUT_DOUBLES; ++e)
+        o[e] = 0.0;
+    for (int a = 0; a < NJ; ++a)
+        o[VSMPC_OUT_JOINTS_REF + a] = jpos[(size_t)a * B + i];
+    if (ps)
+        for (int j = 0; j < NT; ++j)
+        {
+            o[VSMPC_OUT_THROTTLE + j] = ps[(size_t)(PS_THROTTLE + j) * B + i];
+            o[VSMPC_OUT_THRUST + j] = ps[(size_t)(PS_TDES + j) * B + i];
+            o[VSMPC_OUT_THRUST_DOT + j] = ps[(size_t)(PS_TDDES + j) * B + i];
+        }
+    status[i] = VSMPC_STATUS_SOLVED;
+}
+
+static void drop_tick_graph(vsmpc_handle* h)
+{ // the captured tick bakes the kernel arguments in (per-instance table, full-solution flag, jet-NN mode)
+    if (h->tick_graph)
+    {
+        cudaGraphExecDestroy(h->tick_graph);
+        h->tick_graph = nullptr;
+    }
+}
+
 extern "C" {
 
 static int solve_launch(vsmpc_handle* h);
@@ -184,6 +222,17 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         return bail(VSMPC_ERR_ARG, "trajectory arrays missing");
     if (!(c->period_mpc > 0) || !(c->period_large > 0) || !(c->period_small > 0))
         return bail(VSMPC_ERR_ARG, "periods must be positive");
+    // the resampling loops divide by the file rates and the kernels by the 20-tick ratio: reject what the reference
+    // would loop or divide by zero on (TrajectoryManager.cpp:23-39, costsVSMPC.cpp:68-69)
+    if (c->alpha_fps <= 0 || c->traj_fps <= 0)
+        return bail(VSMPC_ERR_ARG, "trajectory rates (alpha_fps, traj_fps) must be positive");
+    if ((int)(1 / c->period_mpc) <= 0 || (int)(1 / c->period_large) <= 0)
+        return bail(VSMPC_ERR_ARG, "1/periodMPC and 1/periodMPCLargeSteps must be at least 1 Hz");
+    if (std::lround(c->period_large / c->period_small) < 1 || c->period_large / c->period_small > 1e6)
+        return bail(VSMPC_ERR_ARG, "periodMPCLargeSteps / periodMPCSmallSteps must round to a ratio in [1, 1e6]");
+    if ((double)c->alpha_len * (1 / c->period_mpc) / c->alpha_fps > 5e7
+        || (double)c->traj_len * (1 / c->period_large) / c->traj_fps > 5e7)
+        return bail(VSMPC_ERR_ARG, "resampled trajectory too long");
 
     DeviceConfig& g = h->cfg;
     g.N = c->n_iter;
@@ -274,6 +323,7 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     A(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
     A(cudaEventCreateWithFlags(&h->ev_solved, cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&h->ev_stream, cudaEventDisableTiming));
     for (int q = 0; q < 2; ++q)
     {
         A(dalloc(&h->d_pack_in[q], (size_t)VSMPC_PACK_DOUBLES * B));
@@ -307,6 +357,7 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(dalloc(&h->d_status, (size_t)B));
     A(dalloc(&h->d_nf, (size_t)B));
     A(dalloc(&h->d_ns, (size_t)B));
+    A(dalloc(&h->d_np, (size_t)B));
     if (ok)
     {
         A(cudaMemcpy(h->d_cfg, &g, sizeof(g), cudaMemcpyHostToDevice));
@@ -320,6 +371,7 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         A(cudaMemset(h->d_z, 0, (size_t)g.n_var * B * 8));
         A(cudaMemset(h->d_nf, 0, (size_t)B * 4));
         A(cudaMemset(h->d_ns, 0, (size_t)B * 4));
+        A(cudaMemset(h->d_np, 0, (size_t)B * 4));
     }
     if (!ok)
     {
@@ -342,7 +394,7 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
+                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
                     h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -356,8 +408,9 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaStreamDestroy(h->out_stream);
     if (h->ev_solved)
         cudaEventDestroy(h->ev_solved);
-    if (h->tick_graph)
-        cudaGraphExecDestroy(h->tick_graph);
+    if (h->ev_stream)
+        cudaEventDestroy(h->ev_stream);
+    drop_tick_graph(h);
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -371,7 +424,15 @@ int vsmpc_set_stream(vsmpc_handle* h, void* s)
 {
     if (!h || h->B <= 0)
         return VSMPC_ERR_ARG;
-    h->stream = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+    cudaStream_t ns = s ? reinterpret_cast<cudaStream_t>(s) : h->own_stream;
+    if (ns != h->stream)
+    { // work already queued on the old stream (a linearise kernel between set_state and solve) stays ordered before
+      // whatever the new stream runs next
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventRecord(h->ev_stream, h->stream));
+        CK(cudaStreamWaitEvent(ns, h->ev_stream, 0));
+    }
+    h->stream = ns;
     return VSMPC_OK;
 }
 
@@ -407,6 +468,8 @@ int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* join
     int rc = run_linearise(h, 1);
     if (rc)
         return rc;
+    seed_outputs_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->d_jpos, nullptr, h->d_out, h->d_status);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     h->configured = true;
     h->has_state = false;
@@ -418,6 +481,7 @@ int vsmpc_set_instance_params(vsmpc_handle* h, const double* ip_host)
     if (!h || h->B <= 0)
         return VSMPC_ERR_ARG;
     CK(cudaSetDevice(h->device));
+    drop_tick_graph(h);
     if (!ip_host)
     {
         h->use_ip = false;
@@ -573,6 +637,8 @@ int vsmpc_set_full_solution(vsmpc_handle* h, int enable)
 {
     if (!h || h->B <= 0)
         return VSMPC_ERR_ARG;
+    if (h->want_full != (enable != 0))
+        drop_tick_graph(h);
     h->want_full = enable != 0;
     return VSMPC_OK;
 }
@@ -652,9 +718,79 @@ int vsmpc_get_counts(vsmpc_handle* h, int* n_factor, int* n_solve)
     return VSMPC_OK;
 }
 
+int vsmpc_get_pivot_counts(vsmpc_handle* h, int* n_pivot)
+{
+    if (!h || h->B <= 0 || !n_pivot)
+        return VSMPC_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(n_pivot, h->d_np, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_get_references(vsmpc_handle* h, double* refs_host)
+{
+    if (!h || h->B <= 0 || !refs_host)
+        return VSMPC_ERR_ARG;
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_get_references: configure first");
+    CK(cudaSetDevice(h->device));
+    // the four published fields are 13 consecutive rows of the device-resident tick state (SoA): one copy, transposed here
+    static_assert(ST_RPY_REF == ST_P_REF + 3 && ST_MOM_REF == ST_P_REF + 6 && ST_ALPHA == ST_P_REF + 12, "row order");
+    const size_t B = h->B;
+    std::vector<double> rows(13 * B);
+    CK(cudaMemcpyAsync(rows.data(), h->d_st + (size_t)ST_P_REF * B, 13 * B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < B; ++i)
+    {
+        double* o = refs_host + i * VSMPC_REF_DOUBLES;
+        o[VSMPC_REF_ALPHA_GRAVITY] = rows[12 * B + i];
+        for (int a = 0; a < 12; ++a)
+            o[VSMPC_REF_POS_COM + a] = rows[(size_t)a * B + i];
+    }
+    return VSMPC_OK;
+}
+
+int vsmpc_get_hessian(vsmpc_handle* h, int instance, double* P_host)
+{
+    if (!h || h->B <= 0 || !P_host || instance < 0 || instance >= h->B)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_get_hessian: bad argument");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cfg.n_var * h->cfg.n_var;
+    double* d = nullptr;
+    cudaError_t e = dalloc(&d, n);
+    if (e == cudaSuccess) e = launch_expand_hessian(h->d_cfg, h->cfg, d, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P_host, d, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return cuda_fail(h, e, "vsmpc_get_hessian");
+    return VSMPC_OK;
+}
+
+int vsmpc_get_constraint_matrix(vsmpc_handle* h, int instance, double* A_host)
+{
+    if (!h || h->B <= 0 || !A_host || instance < 0 || instance >= h->B)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_get_constraint_matrix: bad argument");
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_get_constraint_matrix: configure first");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->cfg.n_con * h->cfg.n_var, ns = NX * NX + NX * NJ + NX * NT + NX;
+    double* d = nullptr;
+    cudaError_t e = dalloc(&d, n + ns);
+    if (e == cudaSuccess)
+        e = launch_expand_constraint_matrix(h->d_cfg, h->cfg, h->d_qd + (size_t)instance * h->cfg.qd_stride, d + n, d, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(A_host, d, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess)
+        return cuda_fail(h, e, "vsmpc_get_constraint_matrix");
+    return VSMPC_OK;
+}
+
 int vsmpc_debug_phase_clocks(long long* clocks_host, int n_instances)
 {
-    return g_last_qp_solver == SOLVER_WIDE ? condensed_wide_phase_clocks(clocks_host, n_instances)
+    return g_last_qp_solver.load(std::memory_order_relaxed) == SOLVER_WIDE ? condensed_wide_phase_clocks(clocks_host, n_instances)
                                            : condensed_phase_clocks(clocks_host, n_instances);
 }
 
@@ -689,13 +825,13 @@ static int solve_launch(vsmpc_handle* h)
         CK(cudaStreamWaitEvent(h->stream, h->ev_out[h->out_idx], 0));
         h->out_pending = false;
     }
-    g_last_qp_solver = h->solver;
+    g_last_qp_solver.store(h->solver, std::memory_order_relaxed);
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
-                               h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+                               h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->stream));
     else if (h->solver == SOLVER_WIDE)
         CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
-                                    h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+                                    h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->stream));
     else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));
@@ -720,11 +856,7 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
         CK(dalloc(&h->d_ps, (size_t)PS_ROWS * B));
         CK(dalloc(&h->d_pp, (size_t)PP_ROWS * B));
     }
-    if (h->tick_graph)
-    {
-        cudaGraphExecDestroy(h->tick_graph);
-        h->tick_graph = nullptr;
-    }
+    drop_tick_graph(h);
     CK(cudaMemcpyAsync(h->d_pm, model, sizeof(PlantModel), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_ps, plant_state_host, PS_ROWS * B * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_pp, plant_param_host, PP_ROWS * B * 8, cudaMemcpyHostToDevice, h->stream));
@@ -744,6 +876,8 @@ int vsmpc_rollout_init(vsmpc_handle* h, const vsmpc_plant_model* model, const do
     int rc = run_linearise(h, 1);
     if (rc)
         return rc;
+    seed_outputs_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->d_jpos, h->d_ps, h->d_out, h->d_status);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     h->configured = true;
     h->has_state = false;
@@ -844,11 +978,7 @@ int vsmpc_rollout_set_jet_nn(vsmpc_handle* h, const float* w_ih, const float* b_
     if (!h || h->B <= 0)
         return VSMPC_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    if (h->tick_graph)
-    {
-        cudaGraphExecDestroy(h->tick_graph);
-        h->tick_graph = nullptr;
-    }
+    drop_tick_graph(h);
     if (!w_ih)
     {
         h->use_nn = false;

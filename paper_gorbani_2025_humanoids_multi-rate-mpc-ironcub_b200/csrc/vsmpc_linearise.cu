@@ -116,7 +116,15 @@ __device__ __forceinline__ void W_of_rpy(double s0, double c0, double s1, double
     W[6] = 0.0; W[7] = -s0; W[8] = c0 * c1;
 }
 
-constexpr int K1_WARPS = 4; // instances per CTA (one warp each)
+constexpr int K1_WARPS = 8; // instances per CTA (one warp each): 8 adjacent SoA columns = 64 contiguous bytes per pack row
+
+// doubles of shared memory per instance: pk[360] | out[qd_stride] | col[12] | ipar[20] | stc[st_rows] | sic[4 ints], padded
+// to 2 (mod 16) so that the tile-transposed staging stores (8 instances x 2 rows per half-warp) hit 16 distinct bank pairs
+__host__ __device__ inline int k1_per_warp(const DeviceConfig& cfg)
+{
+    const int n = 360 + cfg.qd_stride + 12 + 20 + ((cfg.st_rows + 4 + 3) & ~3);
+    return ((n + 13) & ~15) + 2;
+}
 
 // (X^T M_b X).block(3,3,3,3) from the pack row staged in shared memory
 __device__ __forceinline__ void locked_inertia_sm(const double* __restrict__ pk, const double* R, double* I3)
@@ -158,10 +166,12 @@ __device__ __forceinline__ void locked_inertia_sm(const double* __restrict__ pk,
         }
 }
 
-// One warp per MPC instance.  The instance's pack column (359 doubles, strided by B in the SoA buffer)
-// is staged in shared memory, the lanes split the work (lane = 8*jet + joint for the Lambda matrices,
-// one lane per jet / per state entry elsewhere), and the instance-major QP data block is written back
-// with fully coalesced stores.
+// One warp per MPC instance, eight instances per CTA.  The CTA stages the [359][8] tile of the SoA pack (and the
+// [st_rows][8] tile of the persistent state) cooperatively: consecutive threads read the 8 adjacent columns of a row, i.e.
+// 64 contiguous bytes = two fully used 32-byte sectors per row (4 doubles per sector; a warp-per-column read touched one
+// sector per double), transposed into one shared-memory column per instance.  Then the lanes of a warp split the work
+// (lane = 8*jet + joint for the Lambda matrices, one lane per jet / per state entry elsewhere), and the instance-major
+// QP data block is written back with fully coalesced stores.
 // mode 0: update tick.  mode 1: configure (initialise persistent state, then run tick 0).
 __global__ void __launch_bounds__(32 * K1_WARPS)
 linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
@@ -175,10 +185,67 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank): no global round trip for the configuration
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * K1_WARPS + warp;
+    const int NC = cfg.NC;
+    const int per_warp = k1_per_warp(cfg);
+    const size_t Bs = (size_t)B;
+    {
+        // ---- cooperative tile staging: thread -> (row f, column c) with c fastest; every global load of the tick is
+        // issued before the first one is consumed (one DRAM round trip)
+        constexpr int TPB = 32 * K1_WARPS;
+        constexpr int NPK = (VSMPC_PACK_DOUBLES * K1_WARPS + TPB - 1) / TPB;   // 12
+        constexpr int NSV = 6;                                                   // state rows staged in registers: 6 * 32
+        const int c = threadIdx.x & (K1_WARPS - 1), r0 = threadIdx.x / K1_WARPS; // r0 < 32
+        const int ic = blockIdx.x * K1_WARPS + c;
+        const bool on = ic < B;
+        const int st_stage = 360 + cfg.qd_stride + 12 + 20;
+        double pv[NPK], sv[NSV];
+        int siv = 0;
+#pragma unroll
+        for (int t = 0; t < NPK; ++t)
+        {
+            const int f = r0 + 32 * t;
+            pv[t] = (on && f < VSMPC_PACK_DOUBLES) ? pack[(size_t)f * Bs + ic] : 0.0;
+        }
+        const double ipv = (ip && on && r0 < IP_ROWS) ? ip[(size_t)r0 * Bs + ic] : 0.0;
+        if (mode == 0)
+        {
+#pragma unroll
+            for (int t = 0; t < NSV; ++t)
+            {
+                const int f = r0 + 32 * t;
+                sv[t] = (on && f < cfg.st_rows) ? st[(size_t)f * Bs + ic] : 0.0;
+            }
+            if (on && r0 < SI_COUNT)
+                siv = si[(size_t)r0 * Bs + ic];
+        }
+        double* pkc = k1_smem + (size_t)c * per_warp;
+#pragma unroll
+        for (int t = 0; t < NPK; ++t)
+        {
+            const int f = r0 + 32 * t;
+            if (f < VSMPC_PACK_DOUBLES)
+                pkc[f] = pv[t];
+        }
+        if (ip && r0 < IP_ROWS)
+            pkc[st_stage - 20 + r0] = ipv;
+        if (mode == 0)
+        {
+#pragma unroll
+            for (int t = 0; t < NSV; ++t)
+            {
+                const int f = r0 + 32 * t;
+                if (f < cfg.st_rows)
+                    pkc[st_stage + f] = sv[t];
+            }
+            for (int f = r0 + 32 * NSV; f < cfg.st_rows; f += 32) // horizons with more than 13 reference columns
+                pkc[st_stage + f] = on ? st[(size_t)f * Bs + ic] : 0.0;
+            if (r0 < SI_COUNT)
+                reinterpret_cast<int*>(pkc + st_stage + cfg.st_rows)[r0] = siv;
+        }
+    }
+    __syncthreads();
     if (i >= B)
         return;
-    const int NC = cfg.NC;
-    const int per_warp = 360 + cfg.qd_stride + 12 + 20 + ((cfg.st_rows + 4 + 3) & ~3);
     double* pk = k1_smem + (size_t)warp * per_warp;
     double* out = pk + 360;
     double* colbuf = out + cfg.qd_stride;
@@ -186,7 +253,6 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
     double* stc = ipar + 20;      // staged copy of the persistent state column: every global load of the tick is issued up
                                   // front; writes go to the copy and to global memory
     int* sic = reinterpret_cast<int*>(stc + cfg.st_rows);
-    const size_t Bs = (size_t)B;
 #define STR(f) stc[(f)]
 #define STW(f, v)                         \
     do                                    \
@@ -196,53 +262,8 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
         st[(size_t)(f) * Bs + i] = v__;   \
     } while (0)
 #define SI(f) si[(size_t)(f) * Bs + i]
-    {
-        // every global load of the tick is issued before the first one is consumed (one DRAM round trip, not twelve)
-        constexpr int NPK = (VSMPC_PACK_DOUBLES + 31) / 32;
-        double pv[NPK], sv[8];
-        int siv = 0;
-#pragma unroll
-        for (int t = 0; t < NPK; ++t)
-        {
-            const int f = lane + 32 * t;
-            pv[t] = f < VSMPC_PACK_DOUBLES ? pack[(size_t)f * Bs + i] : 0.0;
-        }
-        if (mode == 0)
-        {
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-            {
-                const int f = lane + 32 * t;
-                sv[t] = f < cfg.st_rows ? st[(size_t)f * Bs + i] : 0.0;
-            }
-            if (lane < SI_COUNT)
-                siv = si[(size_t)lane * Bs + i];
-        }
-#pragma unroll
-        for (int t = 0; t < NPK; ++t)
-        {
-            const int f = lane + 32 * t;
-            if (f < VSMPC_PACK_DOUBLES)
-                pk[f] = pv[t];
-        }
-        if (mode == 0)
-        {
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-            {
-                const int f = lane + 32 * t;
-                if (f < cfg.st_rows)
-                    stc[f] = sv[t];
-            }
-            for (int f = lane + 256; f < cfg.st_rows; f += 32) // horizons with more than 17 reference columns
-                stc[f] = st[(size_t)f * Bs + i];
-            if (lane < SI_COUNT)
-                sic[lane] = siv;
-        }
-    }
-    if (lane < IP_ROWS)
-        ipar[lane] = ip ? ip[(size_t)lane * Bs + i]
-                        : (lane < IP_JN ? cfg.jc[lane] : (lane < IP_TMIN ? cfg.jn[lane - IP_JN] : (lane == IP_TMIN ? cfg.throttle_min : cfg.throttle_max)));
+    if (!ip && lane < IP_ROWS)
+        ipar[lane] = lane < IP_JN ? cfg.jc[lane] : (lane < IP_TMIN ? cfg.jn[lane - IP_JN] : (lane == IP_TMIN ? cfg.throttle_min : cfg.throttle_max));
     __syncwarp();
     const Jet jet{ipar + IP_JC, ipar + IP_JN};
     double R[9], rpy[3], pcom[3];
@@ -707,6 +728,76 @@ __global__ void expand_qp_vectors_kernel(const DeviceConfig* __restrict__ cfgp, 
         }
 }
 
+// IMPCProblem::getHessian (IMPCProblem.h:88) of ONE instance, dense n_var x n_var row-major: the constant cost
+// blocks of costsVSMPC.cpp:78-93,166-173 (tracking), :375-409 (joint increments, throttle Laplacian), :472-478
+// (initial throttle), :564-571 (joint position regularisation).  One thread per row.
+__global__ void expand_hessian_kernel(const DeviceConfig* __restrict__ cfgp, double* __restrict__ P)
+{
+    const DeviceConfig& cfg = *cfgp;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cfg.n_var)
+        return;
+    double* row = P + (size_t)r * cfg.n_var;
+    for (int e = 0; e < cfg.n_var; ++e)
+        row[e] = 0.0;
+    const int nxs = NX * (cfg.N + 1), njs = NJ * cfg.Nc;
+    if (r < nxs)
+    {
+        if (r >= NX)
+            row[r] = cfg.Qd[r % NX];
+    }
+    else if (r < nxs + njs)
+        row[r] = cfg.Rqd[(r - nxs) % NJ];
+    else
+    {
+        const int e = r - nxs - njs, blk = e / NT;
+        row[r] = cfg.w_t * ((blk > 0 ? 1.0 : 0.0) + (blk < cfg.nblk - 1 ? 1.0 : 0.0)) + (blk == 0 ? cfg.w_i : 0.0);
+        if (blk > 0)
+            row[r - NT] = -cfg.w_t;
+        if (blk < cfg.nblk - 1)
+            row[r + NT] = -cfg.w_t;
+    }
+}
+
+// IMPCProblem::getLinearConstraintMatrix (IMPCProblem.h:100) of ONE instance, dense n_con x n_var row-major, in the
+// reference's row order (variableSamplingMPC.cpp:77-84): dynamics rows (constraintsVSMPC.cpp:76-128), initial-state rows
+// (IQPUtilsMPC.cpp:71-92), throttle rows (constraintsVSMPC.cpp:338-350; the rows beyond the nblk blocks stay zero).
+// One thread per row; A, BJ, BT: the dense expansions of this instance (expand_dense).
+__global__ void expand_constraint_matrix_kernel(const DeviceConfig* __restrict__ cfgp, const double* __restrict__ A,
+                                                const double* __restrict__ BJ, const double* __restrict__ BT,
+                                                double* __restrict__ M)
+{
+    const DeviceConfig& cfg = *cfgp;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= cfg.n_con)
+        return;
+    double* row = M + (size_t)r * cfg.n_var;
+    for (int e = 0; e < cfg.n_var; ++e)
+        row[e] = 0.0;
+    const int N = cfg.N, nxs = NX * (N + 1), njs = NJ * cfg.Nc;
+    if (r < NX * N)
+    {
+        const int k = r / NX, i = r - k * NX;
+        const double dt = cfg.dt[k];
+        for (int j = 0; j < NX; ++j)
+            row[k * NX + j] = (i == j ? 1.0 : 0.0) + dt * A[i * NX + j];
+        row[(k + 1) * NX + i] = -1.0;
+        const int jb = joint_block(k, cfg.Nc), tb = throttle_block(k, cfg.Ns, cfg.Nc);
+        for (int a = 0; a < NJ; ++a)
+            row[nxs + jb * NJ + a] = dt * BJ[i * NJ + a];
+        for (int a = 0; a < NT; ++a)
+            row[nxs + njs + tb * NT + a] = dt * BT[i * NT + a];
+    }
+    else if (r < NX * N + NX)
+        row[r - NX * N] = 1.0;
+    else
+    {
+        const int e = r - NX * N - NX;
+        if (e < NT * cfg.nblk)
+            row[nxs + njs + e] = 1.0;
+    }
+}
+
 // ---- host-side launchers ---------------------------------------------------------------------------
 cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, int mode,
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
@@ -714,7 +805,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
                              cudaStream_t s)
 {
-    const size_t smem = (size_t)K1_WARPS * (360 + h_cfg.qd_stride + 12 + 20 + ((h_cfg.st_rows + 4 + 3) & ~3)) * sizeof(double);
+    const size_t smem = (size_t)K1_WARPS * k1_per_warp(h_cfg) * sizeof(double);
     static bool attr_set[64] = {};
     if (smem > 200 * 1024)
         return cudaErrorInvalidValue;
@@ -740,6 +831,22 @@ cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const dou
                                      double* u, cudaStream_t s)
 {
     expand_qp_vectors_kernel<<<(B + 63) / 64, 64, 0, s>>>(d_cfg, B, qd, q, l, u);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expand_hessian(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, double* P, cudaStream_t s)
+{
+    expand_hessian_kernel<<<(h_cfg.n_var + 63) / 64, 64, 0, s>>>(d_cfg, P);
+    return cudaGetLastError();
+}
+
+// scratch: NX*NX + NX*NJ + NX*NT + NX doubles
+cudaError_t launch_expand_constraint_matrix(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, const double* qd_inst,
+                                            double* scratch, double* M, cudaStream_t s)
+{
+    double *A = scratch, *BJ = A + NX * NX, *BT = BJ + NX * NJ, *c = BT + NX * NT;
+    expand_dynamics_kernel<<<1, 64, 0, s>>>(d_cfg, 1, qd_inst, A, BJ, BT, c);
+    expand_constraint_matrix_kernel<<<(h_cfg.n_con + 63) / 64, 64, 0, s>>>(d_cfg, A, BJ, BT, M);
     return cudaGetLastError();
 }
 

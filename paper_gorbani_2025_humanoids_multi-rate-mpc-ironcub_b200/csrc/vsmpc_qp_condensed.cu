@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(CD_THREADS, 8)
 qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                     double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
                     double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
-                    int* __restrict__ n_solve, size_t ws_stride, int want_z)
+                    int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z)
 {
     __shared__ CdSmem sm;
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank)
@@ -679,7 +679,10 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
             th = 1.0;
         sm.theta[lane] = th;
         if (lane == 0)
+        {
             sm.flags[1] = stat;
+            sm.flags[2] = (nv - first) + iters;   // exchange pivots executed: inverse + one per active-set iteration
+        }
         PHASE_CLK(5);
 #ifdef VSMPC_PHASE_CLOCKS
         {
@@ -726,8 +729,9 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     if (lane == 0)
     {
         status[inst] = stat;
-        n_factor[inst] = 1;
-        n_solve[inst] = 1;
+        n_factor[inst] = 1;              // one backward recursion (no re-factorisation: the active set works on H_r)
+        n_solve[inst] = solved ? 1 : 0;  // one forward pass, skipped for a held instance
+        n_pivot[inst] = sm.flags[2];
     }
     if (!solved)
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
@@ -757,9 +761,9 @@ size_t condensed_ws_doubles(const DeviceConfig& cfg)
 
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
-                                int* n_solve, int want_z, cudaStream_t s)
+                                int* n_solve, int* n_pivot, int want_z, cudaStream_t s)
 {
-    qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve,
+    qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot,
                                                  condensed_ws_doubles(h_cfg), want_z);
     return cudaGetLastError();
 }

@@ -412,7 +412,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
 qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                          double* __restrict__ ws_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
-                         int* __restrict__ n_factor, int* __restrict__ n_solve, size_t ws_stride, int want_z)
+                         int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride,
+                         int want_z)
 {
     extern __shared__ __align__(16) unsigned char cw_raw[];
     CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
@@ -788,6 +789,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         // a NaN iterate never shows up as a violated bound: gate it here (the status holds the outputs)
         if (__syncthreads_or(isvar && !isfinite(vv[e])) && stat == VSMPC_STATUS_SOLVED)
             stat = VSMPC_STATUS_NUMERICAL;
+        if (threadIdx.x == 0)
+            sm.flags[2] = (nv - first) + iters;   // exchange pivots executed: inverse + one per active-set iteration
         // theta*: throttle variables, affine 1, held block 0
         if (e < L.ldc)
         {
@@ -847,7 +850,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     {
         status[inst] = stat;
         n_factor[inst] = 1;
-        n_solve[inst] = 1;
+        n_solve[inst] = stat == VSMPC_STATUS_SOLVED ? 1 : 0;
+        n_pivot[inst] = sm.flags[2];
     }
     if (stat != VSMPC_STATUS_SOLVED)
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
@@ -891,7 +895,7 @@ size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
 
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
-                                     int want_z, cudaStream_t s)
+                                     int* n_pivot, int want_z, cudaStream_t s)
 {
     static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
     const CwLayout L = cw_layout(h_cfg);
@@ -904,14 +908,14 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                       n_factor, n_solve, wsd, want_z);
+                                                                       n_factor, n_solve, n_pivot, wsd, want_z);
     }
     else if (L.G == 3)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                        n_factor, n_solve, wsd, want_z);
+                                                                        n_factor, n_solve, n_pivot, wsd, want_z);
     }
     else
     {
@@ -920,7 +924,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
         // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
         qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
-            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, wsd, want_z);
+            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z);
     }
     return cudaGetLastError();
 }

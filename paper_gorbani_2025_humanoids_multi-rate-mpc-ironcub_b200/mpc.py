@@ -109,6 +109,11 @@ class QPInput:
     def getRPYReference(self): return self._RPYReference
     def getMomentumReference(self): return self._momentumReference
     def getAlphaGravity(self): return self._alphaGravity
+    # written by the MPC's update (costsVSMPC.cpp:155-160, systemDynamicsVSMPC.cpp:310)
+    def setPosCoMReference(self, v): self._posCoMReference = np.array(v, dtype=np.float64).reshape(3)
+    def setRPYReference(self, v): self._RPYReference = np.array(v, dtype=np.float64).reshape(3)
+    def setMomentumReference(self, v): self._momentumReference = np.array(v, dtype=np.float64).reshape(6)
+    def setAlphaGravity(self, v): self._alphaGravity = float(v)
 
 
 def _state_dict(qp: QPInput) -> dict:
@@ -188,11 +193,24 @@ class VariableSamplingMPC:
         self._qp = qpInput
         self._jointsPositionReference = np.array(robot.getJointPos(), dtype=np.float64).copy()
         self._impl.configure(_state_dict(qpInput))
+        self._publish(qpInput)
         self._status = 0
+        self._out = np.zeros(54)
+        self._out[46:54] = self._jointsPositionReference[self._sel]
         return True
+
+    def _publish(self, qpInput: QPInput):
+        """The QPInput fields update() writes: tracked references (costsVSMPC.cpp:155-160) and the gravity-compensation
+        factor (systemDynamicsVSMPC.cpp:310), read back from the device-resident tick state."""
+        r = self._impl.get_references()
+        qpInput.setPosCoMReference(r["posCoMReference"][0])
+        qpInput.setRPYReference(r["RPYReference"][0])
+        qpInput.setMomentumReference(r["momentumReference"][0])
+        qpInput.setAlphaGravity(r["alphaGravity"][0])
 
     def update(self, qpInput: QPInput) -> bool:
         self._impl.update(_state_dict(qpInput))
+        self._publish(qpInput)
         return True
 
     def solveMPC(self) -> bool:
@@ -221,3 +239,5 @@ class VariableSamplingMPC:
     def getGradient(self): return self._impl.get_qp_vectors()[0][0]
     def getLowerBound(self): return self._impl.get_qp_vectors()[1][0]
     def getUpperBound(self): return self._impl.get_qp_vectors()[2][0]
+    def getHessian(self): return self._impl.getHessian(0)
+    def getLinearConstraintMatrix(self): return self._impl.getLinearConstraintMatrix(0)

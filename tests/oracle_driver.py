@@ -8,7 +8,7 @@ from oracle import vsmpc_oracle as O
 class OracleInstance:
     """One reference-style MPC object + its QPInput/Robot, driven like src/variable_sampling_mpc.py."""
 
-    def __init__(self, nominal_state, i, params=None, trajectories=None, qp_solver=None, jet_model=None):
+    def __init__(self, nominal_state, i, params=None, trajectories=None, qp_solver=None, jet_model=None, phase0=0):
         self.i = i
         self.params = dict(O.default_params())
         self.params.update(params or {})
@@ -22,7 +22,7 @@ class OracleInstance:
             self.qp.setEmptyJetModel()
         fill_qp_input(self.qp, nominal_state, i)
         self.mpc = O.VariableSamplingMPC(qp_solver=qp_solver)
-        self.mpc.configure(self.params, self.qp, trajectories or load_trajectories())
+        self.mpc.configure(self.params, self.qp, trajectories or load_trajectories(), phase0=phase0)
 
     def update(self, state):
         set_robot_state(self.robot, state, self.i)

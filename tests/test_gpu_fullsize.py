@@ -68,3 +68,47 @@ def test_ragged_batches_reproduce_the_big_batch_bit_for_bit(solver):
         z, out, status, _, _ = run(n, solver, states=(sub(nom), sub(per)))
         assert (status == 0).all()
         assert np.array_equal(z, zb[off20:off20 + n]) and np.array_equal(out, outb[off20:off20 + n])
+
+
+def test_kkt_certificate_and_sampled_oracle_at_the_bench_configuration():
+    """BASELINE configs[1] exactly as bench.py runs it (B = 1024, staggered 20-tick phases): a KKT certificate for ALL
+    instances + the oracle's exact solve on a seeded sample of 64 of them, per physical quantity at 1e-6."""
+    from helpers import assert_output_rows_close, assert_solution_close, kkt_certificate, split_hessian
+    from oracle_driver import OracleInstance
+    syn, bat, P = pkg("synthetic"), pkg("batched"), pkg("pack")
+    B = 1024
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=20251002, perturbed=True)            # bench.py: make_workload(B, 20251002 + rank, ...)
+    mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(traj), solver=0, full_solution=True)
+    phase0 = (np.arange(B) % 20).astype(np.int32)
+    mpc.configure_pack(P.build_pack(nom), np.ascontiguousarray(nom["joint_pos"][:, P.DEFAULT_JOINT_SELECTOR].T), phase0)
+    mpc.update(per)
+    A, BJ, BT, c, dt = mpc.get_dynamics()
+    q, l, u = mpc.get_qp_vectors()
+    H = mpc.getHessian(0)
+    mpc.solveMPC()
+    z = mpc.getSolution()
+    out, status = mpc.get_output()
+    piv = mpc.get_pivot_counts()
+    mpc.close()
+    assert (status == 0).all()
+    Pd, w_t = split_hessian(H, N, NC_)
+    k = kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, N, NS, NC_)
+    assert k["stationarity_dq"].max() < 1e-9, k["stationarity_dq"].max()
+    assert k["complementarity"].max() < 1e-9, k["complementarity"].max()
+    assert k["dual_sign"].max() < 1e-9, k["dual_sign"].max()
+    assert k["box"].max() < 1e-12
+    assert k["n_at_bound"] > 50 and k["n_inside"] > 1000          # the workload exercises the active set
+    assert piv.min() >= 20 and piv.max() > 24                      # pinned ticks invert 20 variables; active bounds add pivots
+    # the oracle on a seeded sample of the same batch (its phase counters started ahead like the product's)
+    sample = np.random.default_rng(64).choice(B, 64, replace=False)
+    sample = np.unique(np.concatenate([sample, np.flatnonzero(l[:, 468] != u[:, 468])[:4]]))   # + released ticks
+    for i in sample:
+        o = OracleInstance(nom, int(i), trajectories=traj, phase0=int(phase0[i]))
+        o.update(per)
+        zo = o.solve()
+        assert np.abs(q[i] - o.mpc.gradient).max() <= 1e-12 * np.abs(o.mpc.gradient).max()
+        assert np.abs(l[i] - o.mpc.lowerBound).max() <= 1e-12 * max(1.0, np.abs(o.mpc.lowerBound).max())
+        assert_solution_close(z[i], zo, 1e-6, what=("z", int(i)))
+        assert_output_rows_close(out[i], o.output_row(), 1e-6, what=("row", int(i)))

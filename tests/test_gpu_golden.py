@@ -4,7 +4,7 @@ tests/golden/make_reference_golden.py — the same scenarios, every number from 
 import numpy as np
 import pytest
 
-from helpers import golden, load_trajectories, pkg
+from helpers import assert_output_rows_close, assert_solution_close, field_rel, golden, load_trajectories, pkg
 from oracle_driver import oracle_trajectories_to_product
 
 pytestmark = pytest.mark.gpu
@@ -40,9 +40,9 @@ def test_single_tick_golden(solver, source):
             assert rel_err(A, g[f"{tag}_A"]) < 1e-12 and rel_err(BJ, g[f"{tag}_BJ"]) < 1e-12
             assert rel_err(BT, g[f"{tag}_BT"]) < 1e-12 and rel_err(c, g[f"{tag}_c"]) < 1e-12
         assert rel_err(q, g[f"{tag}_q"]) < 1e-12 and rel_err(l, g[f"{tag}_l"]) < 1e-12 and rel_err(u, g[f"{tag}_u"]) < 1e-12
-        for i in range(B):
-            assert rel_err(z[i], g[f"{tag}_z"][i]) < REL
-            assert rel_err(out[i], g[f"{tag}_row"][i]) < REL
+        for i in range(B):       # every physical quantity against its own magnitude
+            assert_solution_close(z[i], g[f"{tag}_z"][i], REL, what=(tag, "z", i))
+        assert_output_rows_close(out, g[f"{tag}_row"], REL, what=(tag, "row"))
         mpc.close()
 
 
@@ -62,11 +62,11 @@ def test_tick_sequence_golden(solver, full, source):
         mpc.solveMPC()
         out, status = mpc.get_output()
         assert (status == 0).all()
-        for i in range(B):
-            assert rel_err(out[i], g["rows"][t, i]) < REL, (t, i, rel_err(out[i], g["rows"][t, i]))
+        assert_output_rows_close(out, g["rows"][t], REL, what=("tick", t))
         if full:
             z = mpc.getSolution()
-            assert rel_err(z, g["z"][t]) < REL
+            for i in range(B):
+                assert_solution_close(z[i], g["z"][t][i], REL, what=("tick", t, "z", i))
     mpc.close()
 
 
@@ -88,6 +88,31 @@ def test_status_gate_holds_outputs_on_bad_input():
     assert st1[2] == 2 and (np.delete(st1, 2) == 0).all()
     assert np.array_equal(out1[2], out0[2])            # held
     assert not np.array_equal(out1[0][46:54], out0[0][46:54])   # the others accumulated a second increment
+    mpc.close()
+
+
+def test_failed_first_tick_holds_the_configure_time_posture():
+    """A tick that fails before any success must hold what configure() left: the joint reference is Robot::getJointPos()
+    at configure time (variableSamplingMPC.cpp:60,91), the other getters are zero — not an uninitialised or stale row.  A
+    re-configure resets the rows of a previous run."""
+    g = golden("golden_qp.npz")
+    bat, mp = pkg("batched"), pkg("mpc")
+    B = g["nom_pack"].shape[1]
+    mpc = bat.BatchedVSMPC(B, None, oracle_trajectories_to_product(load_trajectories()))
+    for attempt in range(2):
+        mpc.configure_pack(g["nom_pack"], g["joint_pos_sel"])
+        out, st = mpc.get_output()
+        assert (st == 0).all() and np.array_equal(out[:, 46:54], g["joint_pos_sel"].T) and not out[:, :46].any()
+        bad = g["per_pack"].copy()
+        bad[331, 1] = np.nan                       # thrust of instance 1
+        mpc.update_pack(bad)
+        mpc.solveMPC()
+        out, st = mpc.get_output()
+        assert st[1] == 2 and (np.delete(st, 1) == 0).all()
+        assert np.array_equal(out[1, 46:54], g["joint_pos_sel"][:, 1]) and not out[1, :46].any()
+        assert np.abs(out[0, 8:12]).max() > 0      # the others solved
+        mpc.update_pack(g["per_pack"])             # run on, so that the second configure has something to reset
+        mpc.solveMPC()
     mpc.close()
 
 
@@ -145,25 +170,40 @@ def test_cuda_against_the_live_compiled_reference(params):
     mpc.configure(nom)
     assert all((r.n_var, r.n_con) == (mpc.n_var, mpc.n_con) for r in refs)
     sel = pkg("pack").DEFAULT_JOINT_SELECTOR
+    N, Nc = mpc.params["nIter"], mpc.params["controlHorizon"]
+    nblk = Nc - mpc.params["nIterSmall"] + 1
     for t in range(ticks):
         st = syn.make_states(B, seed=7000 + t, perturbed=True, near_bound_fraction=0.5)
         mpc.update(st)
         q, l, u = mpc.get_qp_vectors()
+        pub = mpc.get_references()      # the QPInput fields update() writes (costsVSMPC.cpp:155-160, systemDynamicsVSMPC.cpp:310)
         mpc.solveMPC()
         z = mpc.getSolution()
         out, status = mpc.get_output()
         assert (status == 0).all(), (t, status)
         for i, r in enumerate(refs):
             r.update(st)
-            _, rq, _, rl, ru = r.qp()
+            rP, rq, rA, rl, ru = r.qp()
             assert rel_err(q[i], rq) < 1e-12 and rel_err(l[i], rl) < 1e-12 and rel_err(u[i], ru) < 1e-12, (t, i)
-            assert rel_err(z[i], r.solve()) < REL, (t, i)
+            if t in (0, 19, 20) and i == 0:
+                # IMPCProblem::getHessian / getLinearConstraintMatrix, entry by entry incl. the sparsity pattern
+                P, A = mpc.getHessian(i), mpc.getLinearConstraintMatrix(i)
+                assert np.array_equal(P != 0, rP != 0) and np.abs(P - rP).max() <= 1e-12 * np.abs(rP).max()
+                assert np.array_equal(A != 0, rA != 0), (t, np.argwhere((A != 0) != (rA != 0))[:5])
+                assert np.abs(A - rA).max() <= 1e-12 * max(1.0, np.abs(rA).max())
+            assert_solution_close(z[i], r.solve(), REL, N=N, Nc=Nc, nblk=nblk, what=(t, i))
             o = r.output()
             assert o["status"] == 1
-            assert rel_err(out[i, L.OUT_THROTTLE:L.OUT_THROTTLE + 4], o["throttle"]) < REL
-            assert rel_err(out[i, L.OUT_THRUST:L.OUT_THRUST + 4], o["thrust"]) < REL
-            assert rel_err(out[i, L.OUT_THRUST_DOT:L.OUT_THRUST_DOT + 4], o["thrust_dot"]) < REL
-            assert rel_err(out[i, L.OUT_JOINTS_REF:L.OUT_JOINTS_REF + 8], o["joints"][sel]) < REL
+            assert field_rel(out[i, L.OUT_THROTTLE:L.OUT_THROTTLE + 4], o["throttle"]) < REL
+            assert field_rel(out[i, L.OUT_THRUST:L.OUT_THRUST + 4], o["thrust"]) < REL
+            assert field_rel(out[i, L.OUT_THRUST_DOT:L.OUT_THRUST_DOT + 4], o["thrust_dot"]) < REL
+            assert field_rel(out[i, L.OUT_JOINTS_REF:L.OUT_JOINTS_REF + 8], o["joints"][sel]) < REL
+            for f in range(4):      # getFinalCoMPosition / LinMom / RPY / AngMom
+                assert field_rel(out[i, L.OUT_FINAL_STATE + 3 * f:L.OUT_FINAL_STATE + 3 * f + 3], o["final"][3 * f:3 * f + 3]) < REL
+            # the 13 published values: alphaGravity, posCoMReference, RPYReference, momentumReference
+            mine = np.concatenate([[pub["alphaGravity"][i]], pub["posCoMReference"][i], pub["RPYReference"][i],
+                                   pub["momentumReference"][i]])
+            assert np.abs(mine - o["qp_input"]).max() <= 1e-12 * max(1.0, np.abs(o["qp_input"]).max()), (t, i, mine, o["qp_input"])
     for r in refs:
         r.close()
     mpc.close()

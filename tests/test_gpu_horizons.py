@@ -5,7 +5,7 @@ condensed kernel where the horizon has <= 6 throttle blocks, the condensed kerne
 import numpy as np
 import pytest
 
-from helpers import load_trajectories, pkg
+from helpers import assert_output_rows_close, assert_solution_close, load_trajectories, pkg
 from oracle_driver import OracleInstance, oracle_trajectories_to_product
 
 pytestmark = pytest.mark.gpu
@@ -55,9 +55,9 @@ def test_horizon_variant_matches_oracle(solver, variant):
             o.update(per)
             zo = o.solve()
             assert z.shape[1] == zo.size
-            assert np.abs(z[i] - zo).max() / max(1.0, np.abs(zo).max()) < 1e-6, (variant, solver, free, i)
-            row = o.output_row()
-            assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
+            hz = dict(N=o.params["nIter"], Nc=o.params["controlHorizon"], nblk=o.params["controlHorizon"] - o.params["nIterSmall"] + 1)
+            assert_solution_close(z[i], zo, 1e-6, what=(variant, solver, free, i), **hz)     # per physical quantity
+            assert_output_rows_close(out[i], o.output_row(), 1e-6, what=(variant, solver, free, i))
     mpc.close()
 
 
@@ -98,9 +98,9 @@ def test_condensed_schedule_edge_cases(variant):
                 o.mpc.vectorConstraints[2].counter = ratio - 1
             o.update(per)
             zo = o.solve()
-            assert np.abs(z[i] - zo).max() / max(1.0, np.abs(zo).max()) < 1e-6, (variant, tick, i)
-            row = o.output_row()
-            assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
+            hz = dict(N=o.params["nIter"], Nc=o.params["controlHorizon"], nblk=o.params["controlHorizon"] - o.params["nIterSmall"] + 1)
+            assert_solution_close(z[i], zo, 1e-6, what=(variant, tick, i), **hz)     # per physical quantity
+            assert_output_rows_close(out[i], o.output_row(), 1e-6, what=(variant, tick, i))
     mpc.close()
 
 
@@ -141,7 +141,7 @@ def test_long_horizon_default_solver(variant):
                 o.mpc.vectorConstraints[2].counter = ratio - 1
             o.update(per)
             zo = o.solve()
-            assert np.abs(z[i] - zo).max() / max(1.0, np.abs(zo).max()) < 1e-6, (variant, tick, i)
-            row = o.output_row()
-            assert np.abs(out[i] - row).max() / max(1.0, np.abs(row).max()) < 1e-6
+            hz = dict(N=o.params["nIter"], Nc=o.params["controlHorizon"], nblk=o.params["controlHorizon"] - o.params["nIterSmall"] + 1)
+            assert_solution_close(z[i], zo, 1e-6, what=(variant, tick, i), **hz)     # per physical quantity
+            assert_output_rows_close(out[i], o.output_row(), 1e-6, what=(variant, tick, i))
     mpc.close()

@@ -93,3 +93,32 @@ def test_rollout_with_parameter_sweep():
             assert np.abs(rec[t, i, 0:6] - r[0:6]).max() < 1e-7
             assert np.abs(rec[t, i, 6:14] - r[6:14]).max() / 100.0 < 1e-6
     mpc.close()
+
+
+def test_cuda_graph_of_the_tick_follows_later_setters():
+    """The captured tick bakes kernel arguments in (per-instance table pointer, full-solution flag): changing them after a
+    graph run must not replay the stale arguments.  Two handles run the same loop, one switching its per-instance table
+    on between two graph runs, the other from the start without graphs: identical plant states."""
+    syn, bat, ro = pkg("synthetic"), pkg("batched"), pkg("rollout")
+    B = 6
+    rb = syn.SyntheticRobot()
+    g = np.random.default_rng(3)
+    st = syn.make_states(B, seed=3, perturbed=True, near_bound_fraction=0.0)
+    st["thrust"] = np.full((B, 4), rb.mass * 9.81 / 4.0)
+    st["thrust_des"] = st["thrust"].copy()
+    st["q_cmd"] = np.tile(rb.joint_pos0, (B, 1))
+    tmax = g.uniform(80, 95, B)
+    trj = oracle_trajectories_to_product(load_trajectories())
+
+    def loop(use_graph):
+        mpc = bat.BatchedVSMPC(B, None, trj)
+        lp = ro.BatchedRollout(mpc, rb)
+        lp.init(st)
+        lp.run(3, use_graph=use_graph)
+        mpc.set_instance_params(throttle_max=tmax)          # after the graph was captured
+        lp.run(3, use_graph=use_graph)
+        ps = lp.plant_state()
+        mpc.close()
+        return ps
+
+    assert np.array_equal(loop(True), loop(False))

@@ -85,8 +85,19 @@ def test_create_argument_errors_without_gpu():
         bat.BatchedVSMPC(4, dict(jointsLambdaOption="bogus"), traj)
     with pytest.raises(bat.VsmpcError, match="joint deltas"):
         bat.BatchedVSMPC(4, dict(weightDeltaJoint=[1.0] * 7), traj)
+    # rates / periods the resampling loops and the 20-tick ratio would loop or divide by zero on
+    with pytest.raises(bat.VsmpcError, match="rates"):
+        bat.BatchedVSMPC(4, None, dict(traj, alpha_fps=0))
+    with pytest.raises(bat.VsmpcError, match="rates"):
+        bat.BatchedVSMPC(4, None, dict(traj, traj_fps=-10))
+    with pytest.raises(bat.VsmpcError, match="ratio"):
+        bat.BatchedVSMPC(4, dict(periodMPCLargeSteps=0.001, periodMPCSmallSteps=0.005), traj)
+    with pytest.raises(bat.VsmpcError, match="1 Hz"):
+        bat.BatchedVSMPC(4, dict(periodMPC=2.0), traj)
     lib = L.load()
     assert lib.vsmpc_create(None, 4, 0, None) == L.ERR_ARG
+    assert lib.vsmpc_get_references(None, None) == L.ERR_ARG and lib.vsmpc_get_hessian(None, 0, None) == L.ERR_ARG
+    assert lib.vsmpc_get_constraint_matrix(None, 0, None) == L.ERR_ARG and lib.vsmpc_get_pivot_counts(None, None) == L.ERR_ARG
     assert lib.vsmpc_n_var(None) == -1
     assert lib.vsmpc_solve(None) == L.ERR_ARG
 

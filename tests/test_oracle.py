@@ -313,3 +313,39 @@ def test_warm_started_pivot_active_set_spec():
                     assert pivots >= n                        # = the cold method (inverse, then the dual iterations)
     cold, warm = (sum(x) for x in zip(*saved))
     assert warm < 0.5 * cold
+
+
+def test_kkt_certificate_helper_on_oracle_solutions():
+    """tests/helpers.kkt_certificate (used at the bench size on the GPU, where the oracle is too slow for all 1024
+    instances) accepts the oracle's exact minimisers and rejects perturbed ones."""
+    from helpers import kkt_certificate, split_hessian
+    syn = pkg("synthetic")
+    B = 6
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=5, perturbed=True, near_bound_fraction=0.5)
+    zs, As, BJs, BTs, qs, ls, us = [], [], [], [], [], [], []
+    for i in range(B):
+        o = OracleInstance(nom, i, trajectories=traj, phase0=(0 if i % 2 else 19))    # pinned and released ticks
+        o.update(per)
+        zs.append(o.solve().copy())
+        A, BJ, BT, c, dt = o.dynamics()
+        As.append(A.copy()); BJs.append(BJ.copy()); BTs.append(BT.copy())
+        qs.append(o.mpc.gradient.copy()); ls.append(o.mpc.lowerBound.copy()); us.append(o.mpc.upperBound.copy())
+        H = o.mpc.hessian
+    Pd, w_t = split_hessian(H, 17, 12)
+    assert w_t == 80000.0
+    arr = lambda x: np.array(x)
+    k = kkt_certificate(arr(zs), arr(As), arr(BJs), arr(BTs), dt, arr(qs), arr(ls), arr(us), Pd, w_t)
+    assert k["stationarity_dq"].max() < 1e-10 and k["complementarity"].max() < 1e-10 and k["dual_sign"].max() < 1e-10
+    assert k["box"].max() < 1e-12 and k["n_at_bound"] > 0 and k["n_inside"] > 0
+    # a feasible but non-optimal point: shift one joint-increment block (the states follow the dynamics)
+    z_bad = arr(zs).copy()
+    z_bad[:, 26 * 18 + 3] += 1e-4
+    kb = kkt_certificate(z_bad, arr(As), arr(BJs), arr(BTs), dt, arr(qs), arr(ls), arr(us), Pd, w_t)
+    assert kb["stationarity_dq"].min() > 1e-6
+    # an interior throttle variable moved: complementarity is violated
+    z_bad = arr(zs).copy()
+    z_bad[:, 26 * 18 + 96 + 20] += 1e-3
+    kb = kkt_certificate(z_bad, arr(As), arr(BJs), arr(BTs), dt, arr(qs), arr(ls), arr(us), Pd, w_t)
+    assert max(kb["complementarity"].max(), kb["dual_sign"].max()) > 1e-6
