@@ -1,0 +1,597 @@
+// K2f — fallback QP kernel: pivoted LU of the equality-constrained KKT system in a bordered-band ordering.
+//
+// Replaces, for the instances the Riccati kernels give up on, the same reference code as they do (IMPCProblem::solve ->
+// OsqpEigen::Solver, MPC/src/IMPCProblem/IMPCProblem.cpp:196-298; output extraction of VariableSamplingMPC::solveMPC,
+// variableSamplingMPC.cpp:88-112).  tools/kkt_lu_model.py is the executable NumPy specification.
+//
+// Why.  The Riccati recursion is a block elimination without pivoting in backward time order.  When the open-loop
+// transition T_k = I + dt_k A_c expands — a vehicle spinning at |omega_B| >~ 30 rad/s makes the explicit-Euler momentum
+// block I - dt S(omega_B) grow by |1 + i dt omega| ~ 10 per coarse knot — the cost-to-go grows by that factor squared per
+// knot and the rank-8 down-dates cancel catastrophically: non-positive pivots, status 2 (0.2 % of the Monte Carlo loops of
+// BASELINE configs[2]; profiles/r02_nonsolved_adjudication.md).  The QP stays well posed — the oracle's pivoted sparse-KKT
+// solve and the reference's OSQP both return its minimiser — so the condensed kernels append such an instance to a device
+// list and this kernel solves it with ROW pivoting, which decides per unknown whether a dynamics row is resolved forward
+// (for x_{k+1}) or backward (for x_k).
+//
+// Ordering  [ mu | stage 0 | ... | stage N | border ],  stage k = [ x_k | dq_k | v_b(k) | nu_k ]:  half bandwidth 64;
+// the border (<= 20 unknowns) holds the input blocks acting over several knots and the pin rows of throttle block 0.
+// One CTA per listed instance: the matrix [K | rhs, e_v...] lives in global scratch (dense storage, only the band window and
+// the border are touched), elimination column by column with the pivot searched inside the band window, back-substitution
+// with one warp per right-hand side, then the SAME Goldfarb-Idnani dual active set as the condensed kernels on
+// T = (K^-1)_vv (= the fully exchanged principal pivot transform of the reduced throttle Hessian) and
+// z = z_unc - sum_a s_a lam_a K^-1 e_a.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "vsmpc_common.cuh"
+
+namespace vsmpc
+{
+
+constexpr int FB_THREADS = 256;
+constexpr int FB_MAXROWS = 160;   // band window + border rows eliminated per column (bw + border + slack)
+
+struct FbLayout
+{
+    int n, nb, bw, nv, ld;        // unknowns, band part, half bandwidth, throttle variables, leading dimension of [K | R]
+    int o_x, o_dq, o_v, o_nu, o_mu, o_pin, n_pos;   // offsets into the position table
+};
+
+static void fb_host_layout(const DeviceConfig& g, FbLayout& L, std::vector<int>& pos)
+{
+    const int N = g.N, Nc = g.Nc, Ns = g.Ns, nblk = g.nblk;
+    std::vector<int> span_j(Nc, 0), span_t(nblk, 0);
+    for (int k = 0; k < N; ++k)
+    {
+        span_j[joint_block(k, Nc)]++;
+        span_t[throttle_block(k, Ns, Nc)]++;
+    }
+    L.o_x = 0;
+    L.o_dq = L.o_x + (N + 1) * NX;
+    L.o_v = L.o_dq + Nc * NJ;
+    L.o_nu = L.o_v + nblk * NT;
+    L.o_mu = L.o_nu + N * NX;
+    L.o_pin = L.o_mu + NX;
+    L.n_pos = L.o_pin + NT;
+    pos.assign(L.n_pos, -1);
+    int o = 0;
+    for (int i = 0; i < NX; ++i)
+        pos[L.o_mu + i] = o++;
+    for (int k = 0; k <= N; ++k)
+    {
+        for (int i = 0; i < NX; ++i)
+            pos[L.o_x + k * NX + i] = o++;
+        if (k < N)
+        {
+            const int j = joint_block(k, Nc), b = throttle_block(k, Ns, Nc);
+            if (span_j[j] == 1)
+                for (int a = 0; a < NJ; ++a)
+                    pos[L.o_dq + j * NJ + a] = o++;
+            if (span_t[b] == 1 && b != 0)
+                for (int a = 0; a < NT; ++a)
+                    pos[L.o_v + b * NT + a] = o++;
+            for (int i = 0; i < NX; ++i)
+                pos[L.o_nu + k * NX + i] = o++;
+        }
+    }
+    L.nb = o;
+    for (int e = 0; e < Nc * NJ; ++e)
+        if (pos[L.o_dq + e] < 0)
+            pos[L.o_dq + e] = o++;
+    for (int e = 0; e < nblk * NT; ++e)
+        if (pos[L.o_v + e] < 0)
+            pos[L.o_v + e] = o++;
+    for (int a = 0; a < NT; ++a)
+        pos[L.o_pin + a] = o++;
+    L.n = o;
+    L.nv = NT * nblk;
+    L.ld = (L.n + 1 + L.nv + 3) & ~3;
+    // half bandwidth of the band part: a dynamics row of knot k reaches from x_k to x_{k+1} (and the in-stage inputs)
+    int bw = 0;
+    for (int k = 0; k < N; ++k)
+        for (int i = 0; i < NX; ++i)
+        {
+            const int row = pos[L.o_nu + k * NX + i];
+            auto reach = [&](int p) { if (p < L.nb) bw = std::max(bw, std::abs(row - p)); };
+            for (int j = 0; j < NX; ++j)
+                reach(pos[L.o_x + k * NX + j]);
+            reach(pos[L.o_x + (k + 1) * NX + i]);
+            for (int a = 0; a < NJ; ++a)
+                reach(pos[L.o_dq + joint_block(k, Nc) * NJ + a]);
+            for (int a = 0; a < NT; ++a)
+                reach(pos[L.o_v + throttle_block(k, Ns, Nc) * NT + a]);
+        }
+    for (int i = 0; i < NX; ++i)
+        bw = std::max(bw, std::abs(pos[L.o_mu + i] - pos[L.o_x + i]));
+    for (int b = 0; b + 1 < nblk; ++b)      // throttle Laplacian between in-band blocks
+        for (int a = 0; a < NT; ++a)
+        {
+            const int p = pos[L.o_v + b * NT + a], q = pos[L.o_v + (b + 1) * NT + a];
+            if (p < L.nb && q < L.nb)
+                bw = std::max(bw, std::abs(p - q));
+        }
+    L.bw = bw;
+}
+
+__device__ __forceinline__ void fb_set(double* __restrict__ M, int ld, int r, int c, double v)
+{
+    M[(size_t)r * ld + c] = v;
+    M[(size_t)c * ld + r] = v;
+}
+
+// per-slot scratch: M [n][ld] | T [nv][nv] | zs [n]
+__global__ void __launch_bounds__(FB_THREADS)
+qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, int B, const double* __restrict__ qd_all,
+                   const int* __restrict__ fb_list, const int* __restrict__ fb_count, const int* __restrict__ pos,
+                   double* __restrict__ scratch, size_t slot_doubles, double* __restrict__ z_all, double* __restrict__ st,
+                   double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
+                   int* __restrict__ n_solve, int* __restrict__ n_pivot, int want_z)
+{
+    const DeviceConfig& cfg = cfgv;
+    __shared__ double A[NX * NX], BJ[NX * NJ], BT[NX * NT], cv[NX];
+    __shared__ double prow[FB_MAXROWS * 3 + 256];   // pivot row cache: band window (<= 2 bw + 1) + border + right-hand sides
+    __shared__ double lmul[FB_MAXROWS];
+    __shared__ int lrow[FB_MAXROWS];
+    __shared__ double red_v[FB_THREADS / 32];
+    __shared__ int red_i[FB_THREADS / 32];
+    __shared__ double s_val[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int count = min(*fb_count, B);
+    const int n = L.n, nb = L.nb, bw = L.bw, ld = L.ld, N = cfg.N, Nc = cfg.Nc, nblk = cfg.nblk;
+    double* M = scratch + (size_t)blockIdx.x * slot_doubles;
+    double* T = M + (size_t)n * ld;
+    double* zs = T + (size_t)L.nv * L.nv;
+    const int* px = pos + L.o_x;
+    const int* pq = pos + L.o_dq;
+    const int* pv = pos + L.o_v;
+    const int* pnu = pos + L.o_nu;
+    const int* pmu = pos + L.o_mu;
+    const int* ppin = pos + L.o_pin;
+
+    for (int li = blockIdx.x; li < count; li += gridDim.x)
+    {
+        const int inst = fb_list[li];
+        const double* qd = qd_all + (size_t)inst * cfg.qd_stride;
+        const bool pinned = qd[QD_PINNED] != 0.0;
+        const int first = pinned ? NT : 0;
+        const int nvf = L.nv - first, nrhs = 1 + nvf;
+        const int ncol = n + nrhs;             // columns in use (<= ld)
+        if (tid == 0)
+            expand_dense(qd, A, BJ, BT, cv);
+        // ---- zero the band window, the border and the right-hand sides --------------------------------------------------
+        for (int r = warp; r < n; r += FB_THREADS / 32)
+        {
+            double* row = M + (size_t)r * ld;
+            if (r < nb)
+            {
+                const int c0 = max(0, r - bw), c1 = min(nb - 1, r + 2 * bw);
+                for (int c = c0 + lane; c <= c1; c += 32)
+                    row[c] = 0.0;
+                for (int c = nb + lane; c < ncol; c += 32)
+                    row[c] = 0.0;
+            }
+            else
+                for (int c = lane; c < ncol; c += 32)
+                    row[c] = 0.0;
+        }
+        __syncthreads();
+        // ---- assemble K and the right-hand sides (tools/kkt_lu_model.assemble_kkt) ---------------------------------------
+        for (int e = tid; e < N * NX; e += FB_THREADS)
+        { // tracking cost on x_1 .. x_N: K = Q, rhs = Q xref
+            const int k = 1 + e / NX, i = e - (k - 1) * NX;
+            const int p = px[k * NX + i];
+            M[(size_t)p * ld + p] = cfg.Qd[i];
+            M[(size_t)p * ld + n] = i < 12 ? cfg.Qd[i] * qd[QD_XREF + i * cfg.NC + ref_col(k - 1, cfg.Ns)] : 0.0;
+        }
+        for (int e = tid; e < Nc * NJ; e += FB_THREADS)
+        {
+            const int p = pq[e];
+            M[(size_t)p * ld + p] = cfg.Rqd[e % NJ];
+            M[(size_t)p * ld + n] = -qd[QD_GQ + e % NJ];
+        }
+        for (int e = tid; e < L.nv; e += FB_THREADS)
+        {
+            const int b = e / NT, p = pv[e];
+            M[(size_t)p * ld + p] = cfg.w_t * ((b > 0 ? 1.0 : 0.0) + (b < nblk - 1 ? 1.0 : 0.0)) + (b == 0 ? cfg.w_i : 0.0);
+            if (b > 0)
+                M[(size_t)p * ld + pv[e - NT]] = -cfg.w_t;
+            if (b < nblk - 1)
+                M[(size_t)p * ld + pv[e + NT]] = -cfg.w_t;
+            if (b == 0)
+                M[(size_t)p * ld + n] = cfg.w_i * qd[QD_VBAR + e];
+            if (e >= first)
+                M[(size_t)p * ld + n + 1 + (e - first)] = 1.0;      // unit right-hand side of throttle variable e
+        }
+        for (int e = tid; e < N * NX; e += FB_THREADS)
+        { // dynamics rows: T x_k - x_{k+1} + dt B_J dq + dt B_T v = -dt c
+            const int k = e / NX, i = e - k * NX;
+            const double dt = cfg.dt[k];
+            const int row = pnu[e];
+            for (int j = 0; j < NX; ++j)
+            {
+                const double t = (i == j ? 1.0 : 0.0) + dt * A[i * NX + j];
+                if (t != 0.0)
+                    fb_set(M, ld, row, px[k * NX + j], t);
+            }
+            fb_set(M, ld, row, px[(k + 1) * NX + i], -1.0);
+            const int jb = joint_block(k, Nc), tb = throttle_block(k, cfg.Ns, Nc);
+            for (int a = 0; a < NJ; ++a)
+                if (BJ[i * NJ + a] != 0.0)
+                    fb_set(M, ld, row, pq[jb * NJ + a], dt * BJ[i * NJ + a]);
+            for (int a = 0; a < NT; ++a)
+                if (BT[i * NT + a] != 0.0)
+                    fb_set(M, ld, row, pv[tb * NT + a], dt * BT[i * NT + a]);
+            M[(size_t)row * ld + n] = -dt * cv[i];
+        }
+        if (tid < NX)
+        {
+            fb_set(M, ld, pmu[tid], px[tid], 1.0);
+            M[(size_t)pmu[tid] * ld + n] = qd[QD_X0 + tid];
+        }
+        if (tid < NT)
+        {
+            if (pinned)
+            {
+                fb_set(M, ld, ppin[tid], pv[tid], 1.0);
+                M[(size_t)ppin[tid] * ld + n] = qd[QD_VBAR + tid];
+            }
+            else
+                M[(size_t)ppin[tid] * ld + ppin[tid]] = 1.0;
+        }
+        __syncthreads();
+        // ---- elimination with row pivoting inside the band window -------------------------------------------------------
+        bool ok = true;
+        for (int k = 0; k < n && ok; ++k)
+        {
+            const int hi = k < nb ? min(k + bw, nb - 1) : n - 1;
+            // pivot: largest |M[r][k]|, r in [k, hi]
+            double best = -1.0;
+            int arg = k;
+            for (int r = k + tid; r <= hi; r += FB_THREADS)
+            {
+                const double a = fabs(M[(size_t)r * ld + k]);
+                if (a > best) { best = a; arg = r; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            if (lane == 0) { red_v[warp] = best; red_i[warp] = arg; }
+            __syncthreads();
+            best = red_v[0]; arg = red_i[0];
+            for (int w = 1; w < FB_THREADS / 32; ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < arg)) { best = red_v[w]; arg = red_i[w]; }
+            if (!(best > 0.0) || !isfinite(best))
+            {
+                ok = false;
+                break;
+            }
+            // columns touched by this step: (k, cmax] in the band part, then the border and the right-hand sides
+            const int cmax = k < nb ? min(k + 2 * bw, nb - 1) : n - 1;
+            const int nc1 = cmax - k;                       // band columns k+1 .. cmax
+            const int c2 = k < nb ? nb : n;                 // first column of the second segment
+            const int c2s = max(c2, k + 1);
+            const int nc2 = ncol - c2s;
+            const int nct = nc1 + nc2;
+            double* rk = M + (size_t)k * ld;
+            double* rp = M + (size_t)arg * ld;
+            const double piv = rp[k];
+            // swap rows k <-> arg over the touched columns, cache the pivot row
+            for (int e = tid; e < nct + 1; e += FB_THREADS)
+            {
+                const int c = e == nct ? k : (e < nc1 ? k + 1 + e : c2s + (e - nc1));
+                const double a = rp[c];
+                if (arg != k)
+                {
+                    rp[c] = rk[c];
+                    rk[c] = a;
+                }
+                if (e < nct)
+                    prow[e] = a;
+            }
+            // rows to eliminate: band window below k, then the border rows
+            const int nr1 = hi - k;
+            const int r2s = k < nb ? nb : n;
+            const int nr2 = k < nb ? n - nb : 0;
+            __syncthreads();
+            const double ipiv = 1.0 / piv;
+            for (int e = tid; e < nr1 + nr2; e += FB_THREADS)
+            {
+                const int r = e < nr1 ? k + 1 + e : r2s + (e - nr1);
+                const double a = M[(size_t)r * ld + k];
+                lmul[e] = a * ipiv;
+                lrow[e] = a != 0.0 ? r : -1;
+            }
+            __syncthreads();
+            // rank-1 update: one warp per row, lanes over the columns
+            for (int e = warp; e < nr1 + nr2; e += FB_THREADS / 32)
+            {
+                const int r = lrow[e];
+                if (r < 0)
+                    continue;
+                const double l = lmul[e];
+                double* row = M + (size_t)r * ld;
+                for (int q = lane; q < nct; q += 32)
+                {
+                    const int c = q < nc1 ? k + 1 + q : c2s + (q - nc1);
+                    row[c] = fma(-l, prow[q], row[c]);
+                }
+            }
+            __syncthreads();
+        }
+        if (!ok)
+        { // structurally or numerically singular: the instance keeps status 2 and its held outputs
+            __syncthreads();
+            continue;
+        }
+        // ---- back-substitution: one warp per right-hand side, X overwrites the right-hand-side columns --------------------
+        for (int j = warp; j < nrhs; j += FB_THREADS / 32)
+        {
+            const int cj = n + j;
+            for (int k = n - 1; k >= 0; --k)
+            {
+                const double* rk = M + (size_t)k * ld;
+                const int cmax = k < nb ? min(k + 2 * bw, nb - 1) : n - 1;
+                double acc = 0.0;
+                for (int c = k + 1 + lane; c <= cmax; c += 32)
+                    acc = fma(rk[c], M[(size_t)c * ld + cj], acc);
+                if (k < nb)
+                    for (int c = nb + lane; c < n; c += 32)
+                        acc = fma(rk[c], M[(size_t)c * ld + cj], acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0)
+                    M[(size_t)k * ld + cj] = (rk[cj] - acc) / rk[k];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ---- dual active set on T = (K^-1)_vv (tools/condensed_model._dual_pivot_loop), one variable per thread ----------
+        const double lo = qd[QD_VMIN], up = qd[QD_VMAX];
+        const double tol = 1e-10;
+        for (int e = tid; e < nvf * nvf; e += FB_THREADS)
+        {
+            const int i = e / nvf, j = e - i * nvf;
+            T[e] = 0.5 * (M[(size_t)pv[first + i] * ld + n + 1 + j] + M[(size_t)pv[first + j] * ld + n + 1 + i]);
+        }
+        const bool isvar = tid < nvf;
+        double v_e = isvar ? M[(size_t)pv[first + tid] * ld + n] : 0.0;
+        double lam_e = 0.0;
+        int act = 0, iters = 0, stat = VSMPC_STATUS_SOLVED;
+        double* vbuf = prow;                  // nvf values
+        double* cbuf = prow + FB_MAXROWS;     // column p of T
+        double* rbuf = prow + 2 * FB_MAXROWS; // row p of T
+        __syncthreads();
+        auto block_best = [&](double v, bool want_max, int& arg_out) -> double {
+            // exact block-wide max / min with the lowest thread attaining it
+            double bv = v;
+            int ba = tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                const double ob = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, ba, o);
+                if (want_max ? (ob > bv || (ob == bv && oa < ba)) : (ob < bv || (ob == bv && oa < ba))) { bv = ob; ba = oa; }
+            }
+            __syncthreads();
+            if (lane == 0) { red_v[warp] = bv; red_i[warp] = ba; }
+            __syncthreads();
+            bv = red_v[0]; ba = red_i[0];
+            for (int w = 1; w < FB_THREADS / 32; ++w)
+                if (want_max ? (red_v[w] > bv || (red_v[w] == bv && red_i[w] < ba)) : (red_v[w] < bv || (red_v[w] == bv && red_i[w] < ba)))
+                { bv = red_v[w]; ba = red_i[w]; }
+            arg_out = ba;
+            return bv;
+        };
+        auto pivot = [&](int q) -> bool {
+            // exchange pivot on q: T' = T - u v'/d off row / column q, T'[q,:] = -v/d, T'[:,q] = u/d, T'[q,q] = 1/d
+            __syncthreads();
+            if (tid < nvf)
+            {
+                cbuf[tid] = T[tid * nvf + q];
+                rbuf[tid] = T[q * nvf + tid];
+            }
+            __syncthreads();
+            const double d = rbuf[q];
+            if (!(d > 0.0) || !isfinite(d))
+                return false;
+            const double id = 1.0 / d;
+            for (int e = tid; e < nvf * nvf; e += FB_THREADS)
+            {
+                const int i = e / nvf, j = e - i * nvf;
+                double t;
+                if (i == q)
+                    t = j == q ? id : -rbuf[j] * id;
+                else if (j == q)
+                    t = cbuf[i] * id;
+                else
+                    t = fma(-cbuf[i] * id, rbuf[j], T[e]);
+                T[e] = t;
+            }
+            __syncthreads();
+            return true;
+        };
+        bool fail = false;
+        while (!fail && nvf > 0)
+        {
+            int p;
+            const double best = block_best((isvar && act == 0) ? fmax(fmax(v_e - up, lo - v_e), 0.0) : 0.0, true, p);
+            if (!(best > tol))
+                break;
+            if (tid == p)
+                s_val[0] = v_e;
+            __syncthreads();
+            const double v_p0 = s_val[0];
+            const double s = (v_p0 - up > lo - v_p0) ? 1.0 : -1.0;
+            const double bound = s > 0 ? up : lo;
+            double lam_p = 0.0;
+            while (true)
+            {
+                if (++iters > 6 * L.nv + 64)
+                {
+                    stat = VSMPC_STATUS_MAX_ITER;
+                    fail = true;
+                    break;
+                }
+                const double c_e = isvar ? T[tid * nvf + p] : 0.0;
+                const double zp = T[p * nvf + p];
+                const double r_e = act != 0 ? -(double)act * s * c_e : 0.0;
+                int drop;
+                const double t1 = block_best((act != 0 && r_e > 0.0) ? fmax(lam_e, 0.0) / r_e : INFINITY, false, drop);
+                if (tid == p)
+                    s_val[1] = v_e;
+                __syncthreads();
+                const double v_p = s_val[1];
+                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) / zp : INFINITY;
+                const double tt = fmin(t1, t2);
+                if (!isfinite(tt))
+                {
+                    stat = VSMPC_STATUS_NUMERICAL;
+                    fail = true;
+                    break;
+                }
+                if (isvar)
+                {
+                    if (act == 0)
+                        v_e = fma(-tt * s, c_e, v_e);
+                    else
+                        lam_e -= tt * r_e;
+                }
+                lam_p += tt;
+                const bool full = t2 <= t1;
+                const int q = full ? p : drop;
+                if (tid == q)
+                {
+                    if (full)
+                    {
+                        act = s > 0 ? 1 : -1;
+                        lam_e = lam_p;
+                        v_e = bound;
+                    }
+                    else
+                    {
+                        act = 0;
+                        lam_e = 0.0;
+                    }
+                }
+                if (!pivot(q))
+                {
+                    stat = VSMPC_STATUS_NUMERICAL;
+                    fail = true;
+                    break;
+                }
+                if (full)
+                    break;
+            }
+        }
+        // ---- z = z_unc - sum_a s_a lam_a K^-1 e_a; active variables exactly on their bound ----------------------------------
+        __syncthreads();
+        if (isvar)
+            vbuf[tid] = act != 0 ? (double)act * lam_e : 0.0;
+        __syncthreads();
+        bool fin = true;
+        for (int r = tid; r < n; r += FB_THREADS)
+        {
+            const double* row = M + (size_t)r * ld + n;
+            double z = row[0];
+            for (int a = 0; a < nvf; ++a)
+            {
+                const double w = vbuf[a];
+                if (w != 0.0)
+                    z = fma(-w, row[1 + a], z);
+            }
+            zs[r] = z;
+            fin = fin && isfinite(z);
+        }
+        if (isvar && act != 0)
+            zs[pv[first + tid]] = act > 0 ? up : lo;
+        const bool all_fin = __syncthreads_and(fin);
+        if (!all_fin && stat == VSMPC_STATUS_SOLVED)
+            stat = VSMPC_STATUS_NUMERICAL;
+        // ---- outputs (variableSamplingMPC.cpp:88-112,138-151) ------------------------------------------------------------
+        if (tid == 0)
+        {
+            status[inst] = stat;
+            n_factor[inst] = 2;       // the Riccati attempt + this LU factorisation
+            n_solve[inst] = nrhs;     // right-hand sides back-substituted
+            n_pivot[inst] = iters;
+        }
+        if (stat == VSMPC_STATUS_SOLVED)
+        {
+            double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
+            if (tid < NJ)
+            {
+                const double dq = zs[pq[tid]];
+                o[VSMPC_OUT_DELTA_Q + tid] = dq;
+                const double acc = st[(size_t)(ST_QACC + tid) * B + inst] + dq;
+                st[(size_t)(ST_QACC + tid) * B + inst] = acc;
+                o[VSMPC_OUT_JOINTS_REF + tid] = acc;
+            }
+            if (tid < NT)
+            {
+                o[VSMPC_OUT_THROTTLE + tid] = destd_throttle_qd(qd, zs[pv[tid]]);
+                o[VSMPC_OUT_THRUST + tid] = zs[px[NX + IX_T + tid]];
+                o[VSMPC_OUT_THRUST_DOT + tid] = zs[px[NX + IX_TD + tid]];
+            }
+            if (tid < NX)
+                o[VSMPC_OUT_FINAL_STATE + tid] = zs[px[N * NX + tid]];
+            if (want_z)
+            {
+                double* z = z_all + (size_t)inst * cfg.n_var;
+                for (int e = tid; e < cfg.n_var; e += FB_THREADS)
+                    z[e] = zs[pos[L.o_x + e]];     // x | dq | v are consecutive in the position table, in the reference's order
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+struct FallbackPlan
+{
+    FbLayout L;
+    std::vector<int> pos;
+    size_t slot_doubles;
+};
+
+static FallbackPlan fb_plan(const DeviceConfig& cfg)
+{
+    FallbackPlan P;
+    fb_host_layout(cfg, P.L, P.pos);
+    P.slot_doubles = (size_t)P.L.n * P.L.ld + (size_t)P.L.nv * P.L.nv + P.L.n + 8;
+    return P;
+}
+
+bool fallback_supported(const DeviceConfig& cfg)
+{
+    const FallbackPlan P = fb_plan(cfg);
+    // the pivot-row cache and the per-thread active set bound the sizes (nv <= 160: up to 40 throttle blocks)
+    return P.L.nv <= FB_MAXROWS && P.L.bw + (P.L.n - P.L.nb) + 8 <= FB_MAXROWS
+           && 2 * P.L.bw + 1 + (P.L.n - P.L.nb) + 1 + P.L.nv <= FB_MAXROWS * 3 + 256 && P.L.nv <= FB_THREADS;
+}
+
+size_t fallback_slot_doubles(const DeviceConfig& cfg) { return fb_plan(cfg).slot_doubles; }
+size_t fallback_pos_ints(const DeviceConfig& cfg) { return fb_plan(cfg).pos.size(); }
+void fallback_positions(const DeviceConfig& cfg, int* out)
+{
+    const FallbackPlan P = fb_plan(cfg);
+    for (size_t i = 0; i < P.pos.size(); ++i)
+        out[i] = P.pos[i];
+}
+
+cudaError_t launch_qp_fallback(const DeviceConfig& h_cfg, int B, int n_slots, const double* qd, const int* fb_list,
+                               const int* fb_count, const int* pos, double* scratch, double* z, double* st, double* out_rows,
+                               int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, cudaStream_t s)
+{
+    const FallbackPlan P = fb_plan(h_cfg);
+    qp_fallback_kernel<<<n_slots, FB_THREADS, 0, s>>>(h_cfg, P.L, B, qd, fb_list, fb_count, pos, scratch, P.slot_doubles, z, st,
+                                                     out_rows, status, n_factor, n_solve, n_pivot, want_z);
+    return cudaGetLastError();
+}
+
+} // namespace vsmpc
