@@ -75,6 +75,39 @@ def build_mpc(force: bool = False) -> str:
     return MPC_LIB
 
 
+GLUE_LIB = os.path.join(OUT_DIR, "libvsmpc_reference_glue.so")
+
+
+def build_glue(force: bool = False) -> str:
+    """oracle/_ref/libvsmpc_reference_glue.so: the same 13 reference translation units + oracle/ref_mpc_shim.cpp compiled with
+    -DVSMPC_WITH_GLUE, i.e. together with the PRODUCT's reference-side binding include/vsmpc_reference_glue.hpp (the class a
+    maintainer drops into the reference tree: configure(weak_ptr<IParametersHandler>, QPInput&) / update(QPInput&) / solveMPC /
+    getters over libvsmpc.so), so that tests/test_reference_glue.py can drive the reference's VariableSamplingMPC and the
+    GPU-backed class on ONE QPInput object.  Links libvsmpc.so by relative rpath."""
+    root = os.path.dirname(HERE)
+    pkg = os.path.join(root, "paper_gorbani_2025_humanoids_multi-rate-mpc-ironcub_b200")
+    if not available():
+        return GLUE_LIB if os.path.exists(GLUE_LIB) else ""
+    shim = os.path.join(HERE, "ref_mpc_shim.cpp")
+    stubs = os.path.join(HERE, "ref_stubs")
+    inc = os.path.join(root, "include")
+    deps = [shim, os.path.join(inc, "vsmpc_reference_glue.hpp"), os.path.join(inc, "vsmpc_adapter.hpp"), os.path.join(inc, "vsmpc.h")]
+    newest = max([os.path.getmtime(d) for d in deps] + [os.path.getmtime(os.path.join(d, f)) for d, _, fs in os.walk(stubs) for f in fs])
+    if os.path.exists(GLUE_LIB) and not force and os.path.getmtime(GLUE_LIB) >= newest:
+        return GLUE_LIB
+    if not os.path.exists(os.path.join(pkg, "libvsmpc.so")):
+        return ""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-DVSMPC_WITH_GLUE", "-I", stubs, "-I", inc,
+           "-I", os.path.join(REF_FC, "utils", "include"), "-I", os.path.join(REF_FC, "momentum-based-linear-mpc-lib", "include"),
+           "-o", GLUE_LIB] + [os.path.join(REF_FC, f) for f in MPC_SOURCES] + [shim] \
+        + ["-L", pkg, "-lvsmpc", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(pkg)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return GLUE_LIB
+
+
 def load():
     import ctypes
     path = build()
@@ -91,3 +124,4 @@ def load():
 if __name__ == "__main__":
     print(build(force=True))
     print(build_mpc(force=True))
+    print(build_glue(force=True))

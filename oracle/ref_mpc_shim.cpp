@@ -66,9 +66,18 @@ const std::vector<Eigen::Vector3d>& Robot::getMatrixOfJetArms() const { return m
 const std::vector<std::string>& Robot::getAxesList() const { return m_axesList; }
 const std::vector<std::string>& Robot::getJetsList() const { return m_jetsList; }
 
+#ifdef VSMPC_WITH_GLUE
+// the product's reference-side binding (include/vsmpc_reference_glue.hpp), compiled against the same stand-in headers and the
+// reference's own QPInput.cpp: oracle/build_ref.build_glue() -> oracle/_ref/libvsmpc_reference_glue.so (links libvsmpc.so)
+#include <vsmpc_reference_glue.hpp>
+#endif
+
 // ---- the handle ---------------------------------------------------------------------------------------------------------
 struct RefMpc
 {
+#ifdef VSMPC_WITH_GLUE
+    vsmpc::VariableSamplingMPCOnGpu gpu;   // driven on the SAME QPInput object as the reference class below
+#endif
     std::shared_ptr<Robot> robot = std::make_shared<Robot>();
     std::shared_ptr<BipedalLocomotion::ParametersHandler::YarpImplementation> params
         = std::make_shared<BipedalLocomotion::ParametersHandler::YarpImplementation>();
@@ -286,5 +295,66 @@ void ref_mpc_get_output(void* p, double* jointsRef, double* throttle, double* th
     copyOut(h->qpInput.getRPYReference(), qpInputOut + 4);
     copyOut(h->qpInput.getMomentumReference(), qpInputOut + 7);
 }
+
+#ifdef VSMPC_WITH_GLUE
+// ---- the same call sequence on vsmpc::VariableSamplingMPCOnGpu: configure / update / solveMPC with the reference's own
+// argument types (weak_ptr<IParametersHandler>, QPInput&), getters through Eigen::Ref -------------------------------------
+int ref_glue_configure(void* p)
+{
+    RefMpc* h = static_cast<RefMpc*>(p);
+    return h->gpu.configure(h->params, h->qpInput) ? 0 : 1;
+}
+int ref_glue_update(void* p)
+{
+    RefMpc* h = static_cast<RefMpc*>(p);
+    return h->gpu.update(h->qpInput) ? 0 : 1;
+}
+int ref_glue_solve(void* p) { return static_cast<RefMpc*>(p)->gpu.solveMPC() ? 0 : 1; }
+int ref_glue_status(void* p) { return static_cast<RefMpc*>(p)->gpu.getQPProblemStatus(); }
+int ref_glue_nvar(void* p) { return int(static_cast<RefMpc*>(p)->gpu.getNOptimizationVariables()); }
+int ref_glue_ncon(void* p) { return int(static_cast<RefMpc*>(p)->gpu.getNConstraints()); }
+// same layout as ref_mpc_get_output; qpInputOut is read from the shared QPInput object (what the glue's update() wrote)
+int ref_glue_get_output(void* p, double* jointsRef, double* throttle, double* thrust, double* thrustDot, double* finalState,
+                        double* solution, double* qpInputOut)
+{
+    RefMpc* h = static_cast<RefMpc*>(p);
+    Eigen::VectorXd j(h->nJ), t(h->nJets), T(h->nJets), Td(h->nJets), v3(3), z(Eigen::Index(h->gpu.getNOptimizationVariables()));
+    bool ok = h->gpu.getJointsReferencePosition(j) && h->gpu.getThrottleReference(t) && h->gpu.getThrustReference(T)
+              && h->gpu.getThrustDotReference(Td) && h->gpu.getSolution(z);
+    copyOut(j, jointsRef); copyOut(t, throttle); copyOut(T, thrust); copyOut(Td, thrustDot); copyOut(z, solution);
+    ok = ok && h->gpu.getFinalCoMPosition(v3); copyOut(v3, finalState + 0);
+    ok = ok && h->gpu.getFinalLinMom(v3); copyOut(v3, finalState + 3);
+    ok = ok && h->gpu.getFinalRPY(v3); copyOut(v3, finalState + 6);
+    ok = ok && h->gpu.getFinalAngMom(v3); copyOut(v3, finalState + 9);
+    // wrong sizes must be refused like the reference's getters (variableSamplingMPC.cpp:114-227)
+    Eigen::VectorXd bad(h->nJets + 1);
+    ok = ok && !h->gpu.getThrustReference(bad);
+    qpInputOut[0] = h->qpInput.getAlphaGravity();
+    copyOut(h->qpInput.getPosCoMReference(), qpInputOut + 1);
+    copyOut(h->qpInput.getRPYReference(), qpInputOut + 4);
+    copyOut(h->qpInput.getMomentumReference(), qpInputOut + 7);
+    return ok ? 0 : 1;
+}
+// overwrite the four published QPInput fields (so that a test sees which class wrote them last)
+void ref_glue_clear_published(void* p, double v)
+{
+    RefMpc* h = static_cast<RefMpc*>(p);
+    Eigen::Vector3d a; a << v, v, v;
+    Eigen::Vector6d m; m << v, v, v, v, v, v;
+    h->qpInput.setPosCoMReference(a);
+    h->qpInput.setRPYReference(a);
+    h->qpInput.setMomentumReference(m);
+    h->qpInput.setAlphaGravity(v);
+}
+// the pack vsmpc::fillPack builds from the QPInput / Robot getters (compared with the Python pack builder)
+int ref_glue_fill_pack(void* p, const int* sel, double* pack359)
+{
+    RefMpc* h = static_cast<RefMpc*>(p);
+    vsmpc::Pack pk;
+    if (!vsmpc::fillPack(h->qpInput, std::vector<int>(sel, sel + 8), pk)) return 1;
+    std::memcpy(pack359, pk.v, sizeof(pk.v));
+    return 0;
+}
+#endif
 
 } // extern "C"

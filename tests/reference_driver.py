@@ -13,6 +13,7 @@ _QP_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINT
                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double))
 _DP = ctypes.POINTER(ctypes.c_double)
 _lib = None
+_glue = False
 _keep = []
 
 
@@ -24,13 +25,24 @@ def _c(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def lib():
-    global _lib
+def lib(glue=False):
+    """glue=True: oracle/_ref/libvsmpc_reference_glue.so — the same library compiled together with the product's reference-side
+    binding (include/vsmpc_reference_glue.hpp); it links libvsmpc.so.  One library per process (both define the same symbols)."""
+    global _lib, _glue
+    if _lib is not None and glue and not _glue:
+        raise RuntimeError("reference_driver: the plain reference library is already loaded in this process")
     if _lib is None:
-        path = build_ref.build_mpc()
+        path = build_ref.build_glue() if glue else build_ref.build_mpc()
         if not path:
             return None
+        _glue = bool(glue)
         L = ctypes.CDLL(path)
+        if glue:
+            for f in ("ref_glue_configure", "ref_glue_update", "ref_glue_solve", "ref_glue_status", "ref_glue_nvar", "ref_glue_ncon"):
+                getattr(L, f).argtypes = [ctypes.c_void_p]
+            L.ref_glue_get_output.argtypes = [ctypes.c_void_p] + [_DP] * 7
+            L.ref_glue_clear_published.argtypes = [ctypes.c_void_p, ctypes.c_double]
+            L.ref_glue_fill_pack.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), _DP]
         L.ref_mpc_create.restype = ctypes.c_void_p
         L.ref_mpc_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
         for f in ("ref_mpc_destroy", "ref_mpc_configure", "ref_mpc_update", "ref_mpc_solve", "ref_mpc_nvar", "ref_mpc_ncon",
@@ -78,8 +90,8 @@ def register_trajectories(L, traj):
 class ReferenceInstance:
     """Same call sequence as tests/oracle_driver.OracleInstance, on the compiled reference."""
 
-    def __init__(self, nominal_state, i, params=None, trajectories=None):
-        self.L = lib()
+    def __init__(self, nominal_state, i, params=None, trajectories=None, glue=False):
+        self.L = lib(glue)
         self.i = i
         p = dict(O.default_params())
         p.update(params or {})
@@ -131,6 +143,40 @@ class ReferenceInstance:
                                                                "qp_input")])
         o["status"] = self.L.ref_mpc_status(self.h)
         return o
+
+    # ---- the product's reference-side binding on the same QPInput object (glue library only) ------------------------------
+    def glue_configure(self):
+        return self.L.ref_glue_configure(self.h) == 0
+
+    def glue_update(self, state=None):
+        if state is not None:
+            self._set(state)
+        return self.L.ref_glue_update(self.h) == 0
+
+    def glue_solve(self):
+        return self.L.ref_glue_solve(self.h) == 0
+
+    def glue_output(self):
+        n = self.L.ref_glue_nvar(self.h)
+        o = dict(joints=np.zeros(self.nJ), throttle=np.zeros(4), thrust=np.zeros(4), thrust_dot=np.zeros(4),
+                 final=np.zeros(12), solution=np.zeros(n), qp_input=np.zeros(13))
+        rc = self.L.ref_glue_get_output(self.h, *[_p(o[k]) for k in ("joints", "throttle", "thrust", "thrust_dot", "final",
+                                                                     "solution", "qp_input")])
+        o["ok"] = rc == 0
+        o["status"] = self.L.ref_glue_status(self.h)
+        return o
+
+    def glue_fill_pack(self, sel):
+        pk = np.zeros(359)
+        s = (ctypes.c_int * 8)(*[int(j) for j in sel])
+        assert self.L.ref_glue_fill_pack(self.h, s, _p(pk)) == 0
+        return pk
+
+    def clear_published(self, v=-7.0):
+        self.L.ref_glue_clear_published(self.h, float(v))
+
+    def set_state(self, state):
+        self._set(state)
 
     def close(self):
         if self.h:
