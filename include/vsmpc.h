@@ -20,6 +20,8 @@
 #ifndef VSMPC_H
 #define VSMPC_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -155,6 +157,13 @@ int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);
 /* same, pack already resident on the handle's GPU */
 int vsmpc_set_state_device(vsmpc_handle* h, const double* pack_dev);
 
+/* the same two calls for a COLUMN WINDOW of a larger SoA batch: row r of this handle's instances starts at
+ * pack_host + r * row_stride (joint_pos_sel likewise; row_stride >= n_instances, in doubles).  This is how one host batch is
+ * split over several devices without repacking (vsmpc_multi_* below). */
+int vsmpc_configure_strided(vsmpc_handle* h, const double* pack_host, const double* joint_pos_sel_host, const int* phase0_host,
+                            size_t row_stride);
+int vsmpc_set_state_strided(vsmpc_handle* h, const double* pack_host, size_t row_stride);
+
 /* VariableSamplingMPC::solveMPC (variableSamplingMPC.cpp:88-112): structured QP solve + output
  * extraction + joint accumulator.  vsmpc_solve blocks; _async + vsmpc_wait split it. */
 int vsmpc_solve(vsmpc_handle* h);
@@ -285,6 +294,30 @@ int vsmpc_jet_nn_eval(vsmpc_handle* h, int n_groups, double dt, const float* T_h
                       float* T_next_host, float* T_dot_host);
 /* the pack the plant built for the next tick (double[VSMPC_PACK_DOUBLES][B]) — parity tests */
 int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host);
+
+/* ---- one process, several GPUs (SURVEY §8b "vsmpc_create(cfg, n_instances, n_gpus, ...)", §8e) -----------------------------
+ * B instances sharded in contiguous ranges [g B / G, (g + 1) B / G) over G devices (devices == NULL: 0 .. G-1; an entry may
+ * repeat, e.g. {0, 0} puts two shards on one GPU), one vsmpc_handle with its own streams per shard, driven by ONE host
+ * thread: every call below enqueues on all shards before it waits on any, and there is no inter-GPU traffic — the only
+ * gather is vsmpc_multi_get_output, where every device copies its own rows into the caller's [B][54] array.  All host
+ * arrays have the single-GPU layouts for the WHOLE batch. */
+typedef struct vsmpc_multi vsmpc_multi;
+int vsmpc_create_multi(const vsmpc_config* cfg, int n_instances, int n_gpus, const int* devices, vsmpc_multi** out);
+int vsmpc_multi_destroy(vsmpc_multi* m);
+const char* vsmpc_multi_last_error(const vsmpc_multi* m);
+int vsmpc_multi_n_shards(const vsmpc_multi* m);
+int vsmpc_multi_n_instances(const vsmpc_multi* m);
+/* instance range and per-device handle of one shard (handle == NULL for a shard without instances) */
+int vsmpc_multi_shard(const vsmpc_multi* m, int shard, int* first, int* count, vsmpc_handle** handle);
+int vsmpc_multi_configure(vsmpc_multi* m, const double* pack_host, const double* joint_pos_sel_host, const int* phase0_host);
+int vsmpc_multi_set_instance_params(vsmpc_multi* m, const double* instance_params_host);
+int vsmpc_multi_set_state(vsmpc_multi* m, const double* pack_host);
+int vsmpc_multi_solve(vsmpc_multi* m);
+int vsmpc_multi_solve_async(vsmpc_multi* m);
+int vsmpc_multi_wait(vsmpc_multi* m);
+int vsmpc_multi_get_output(vsmpc_multi* m, double* out_rows_host, int* status_host);
+int vsmpc_multi_set_full_solution(vsmpc_multi* m, int enable);
+int vsmpc_multi_get_full_solution(vsmpc_multi* m, double* z_host);
 
 /* development hook: per-instance clock64() stamps of the condensed kernel's phases of the last launch (long long
  * [n][8]); returns VSMPC_ERR_UNSUPPORTED unless the library was built with -DVSMPC_PHASE_CLOCKS */

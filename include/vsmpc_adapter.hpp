@@ -211,6 +211,120 @@ private:
     std::string m_err;
 };
 
+// ---- a batch of instances as structure-of-arrays host buffers (what vsmpc_configure / vsmpc_set_state take) -------
+// The C++ host layer of north_star (a): every MPC instance hands over its own Pack (array-of-structures: one robot, one
+// QPInput), PackBatch scatters it into column i of the SoA pack double[VSMPC_PACK_DOUBLES][B] (row = scalar, column =
+// instance) so that the device reads it coalesced; jointPosSel double[8][B] likewise.
+class PackBatch
+{
+public:
+    explicit PackBatch(int nInstances) : m_B(nInstances), m_pack((size_t)VSMPC_PACK_DOUBLES * nInstances, 0.0),
+                                         m_jpos((size_t)VSMPC_NJ * nInstances, 0.0) {}
+    int size() const { return m_B; }
+    bool set(int i, const Pack& p)
+    {
+        if (i < 0 || i >= m_B)
+            return false;
+        for (int r = 0; r < VSMPC_PACK_DOUBLES; ++r)
+            m_pack[(size_t)r * m_B + i] = p.v[r];
+        return true;
+    }
+    // one field of one instance (n scalars at row offset off), e.g. only what changed since the last tick
+    bool setField(int i, int off, const double* src, int n)
+    {
+        if (i < 0 || i >= m_B || off < 0 || off + n > VSMPC_PACK_DOUBLES)
+            return false;
+        for (int r = 0; r < n; ++r)
+            m_pack[(size_t)(off + r) * m_B + i] = src[r];
+        return true;
+    }
+    // Robot::getJointPos() of instance i restricted to the controlled joints (configure only)
+    bool setJointPos(int i, const std::vector<double>& jointPos, const std::vector<int>& controlledJoints)
+    {
+        if (i < 0 || i >= m_B || controlledJoints.size() != VSMPC_NJ)
+            return false;
+        for (int a = 0; a < VSMPC_NJ; ++a)
+        {
+            if (controlledJoints[a] < 0 || controlledJoints[a] >= static_cast<int>(jointPos.size()))
+                return false;
+            m_jpos[(size_t)a * m_B + i] = jointPos[controlledJoints[a]];
+        }
+        return true;
+    }
+    Pack get(int i) const
+    {
+        Pack p;
+        for (int r = 0; r < VSMPC_PACK_DOUBLES; ++r)
+            p.v[r] = m_pack[(size_t)r * m_B + i];
+        return p;
+    }
+    const double* pack() const { return m_pack.data(); }
+    double* pack() { return m_pack.data(); }
+    const double* jointPosSel() const { return m_jpos.data(); }
+
+private:
+    int m_B;
+    std::vector<double> m_pack, m_jpos;
+};
+
+// ---- B instances sharded over several GPUs of one box, one host thread (vsmpc_multi_*) ---------------------------
+class MultiGpuMPC
+{
+public:
+    MultiGpuMPC() = default;
+    MultiGpuMPC(const MultiGpuMPC&) = delete;
+    MultiGpuMPC& operator=(const MultiGpuMPC&) = delete;
+    ~MultiGpuMPC() { destroy(); }
+    // devices: one entry per shard (empty: 0 .. nGpus-1); an index may repeat
+    bool create(const Params& p, int nInstances, int nGpus, const std::vector<int>& devices = {})
+    {
+        destroy();
+        if (!devices.empty() && static_cast<int>(devices.size()) != nGpus)
+            return error("one device index per shard");
+        vsmpc_config c;
+        detail::fill_config(p, c);
+        const int rc = vsmpc_create_multi(&c, nInstances, nGpus, devices.empty() ? nullptr : devices.data(), &m_h);
+        if (rc != VSMPC_OK)
+        {
+            const std::string msg = m_h ? vsmpc_multi_last_error(m_h) : "vsmpc_create_multi failed";
+            destroy();
+            return error(msg);
+        }
+        m_B = nInstances;
+        return true;
+    }
+    bool configure(const PackBatch& b, const int* phase0 = nullptr)
+    {
+        return b.size() == m_B && check(vsmpc_multi_configure(m_h, b.pack(), b.jointPosSel(), phase0));
+    }
+    bool update(const PackBatch& b) { return b.size() == m_B && check(vsmpc_multi_set_state(m_h, b.pack())); }
+    bool solveMPC() { return check(vsmpc_multi_solve(m_h)); }
+    bool getOutput(double* rows, int* status) { return check(vsmpc_multi_get_output(m_h, rows, status)); }
+    int nInstances() const { return m_B; }
+    int nShards() const { return vsmpc_multi_n_shards(m_h); }
+    bool shard(int g, int& first, int& count) const { return vsmpc_multi_shard(m_h, g, &first, &count, nullptr) == VSMPC_OK; }
+    const std::string& lastError() const { return m_err; }
+
+private:
+    void destroy()
+    {
+        if (m_h)
+            vsmpc_multi_destroy(m_h);
+        m_h = nullptr;
+        m_B = 0;
+    }
+    bool error(const std::string& msg)
+    {
+        m_err = msg;
+        std::cerr << "[vsmpc] " << msg << std::endl;
+        return false;
+    }
+    bool check(int rc) { return rc == VSMPC_OK ? true : error(m_h ? vsmpc_multi_last_error(m_h) : "null handle"); }
+    vsmpc_multi* m_h = nullptr;
+    int m_B = 0;
+    std::string m_err;
+};
+
 // ---- drop-in for the reference class (one instance) ---------------------------------------------------------
 class VariableSamplingMPC
 {

@@ -60,20 +60,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_examples(force: bool = False) -> str:
-    """C++ host example over include/vsmpc_adapter.hpp (g++ only; links libvsmpc.so by relative rpath)."""
-    src = os.path.join(ROOT, "examples", "cpp_controller.cpp")
+    """C++ host examples over include/vsmpc_adapter.hpp (g++ only; link libvsmpc.so by relative rpath): the single-instance
+    controller loop and the one-process multi-GPU batch.  Returns the path of the first."""
     out_dir = os.path.join(ROOT, "examples", "bin")
-    exe = os.path.join(out_dir, "cpp_controller")
-    deps = [src, os.path.join(ROOT, "include", "vsmpc_adapter.hpp"), os.path.join(ROOT, "include", "vsmpc.h"), LIB]
-    if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
-        return exe
     os.makedirs(out_dir, exist_ok=True)
-    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), src,
-           "-L", HERE, "-lvsmpc", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE), "-o", exe]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
-    return exe
+    exes = []
+    for name in ("cpp_controller", "cpp_multi_gpu"):
+        src = os.path.join(ROOT, "examples", name + ".cpp")
+        exe = os.path.join(out_dir, name)
+        exes.append(exe)
+        deps = [src, os.path.join(ROOT, "include", "vsmpc_adapter.hpp"), os.path.join(ROOT, "include", "vsmpc.h"), LIB]
+        if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
+            continue
+        cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), src,
+               "-L", HERE, "-lvsmpc", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE), "-o", exe]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return exes[0]
 
 
 if __name__ == "__main__":

@@ -69,7 +69,12 @@ EXPORTS = [
     "vsmpc_get_output_device", "vsmpc_get_output_async", "vsmpc_wait_output", "vsmpc_set_full_solution", "vsmpc_get_full_solution", "vsmpc_get_dynamics", "vsmpc_get_qp_vectors",
     "vsmpc_linearise", "vsmpc_solve_qp",
     "vsmpc_get_counts", "vsmpc_get_pivot_counts", "vsmpc_get_references", "vsmpc_get_hessian", "vsmpc_get_constraint_matrix",
-    "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64",
+    "vsmpc_debug_set_counters", "vsmpc_debug_phase_clocks", "vsmpc_microbench_fp64", "vsmpc_set_fallback",
+    "vsmpc_configure_strided", "vsmpc_set_state_strided",
+    "vsmpc_create_multi", "vsmpc_multi_destroy", "vsmpc_multi_last_error", "vsmpc_multi_n_shards", "vsmpc_multi_n_instances",
+    "vsmpc_multi_shard", "vsmpc_multi_configure", "vsmpc_multi_set_instance_params", "vsmpc_multi_set_state", "vsmpc_multi_solve",
+    "vsmpc_multi_solve_async", "vsmpc_multi_wait", "vsmpc_multi_get_output", "vsmpc_multi_set_full_solution",
+    "vsmpc_multi_get_full_solution",
     "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
 ]
 
@@ -114,6 +119,7 @@ def load() -> C.CDLL:
     lib.vsmpc_get_hessian.argtypes = [H, C.c_int, C.c_void_p]
     lib.vsmpc_get_constraint_matrix.argtypes = [H, C.c_int, C.c_void_p]
     lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
+    lib.vsmpc_set_fallback.argtypes = [H, C.c_int]
     lib.vsmpc_debug_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]
     lib.vsmpc_set_instance_params.argtypes = [H, C.c_void_p]
@@ -123,8 +129,23 @@ def load() -> C.CDLL:
     lib.vsmpc_rollout_set_jet_nn.argtypes = [H] + [C.c_void_p] * 8
     lib.vsmpc_jet_nn_eval.argtypes = [H, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_rollout_get_pack.argtypes = [H, C.c_void_p]
+    lib.vsmpc_configure_strided.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.vsmpc_set_state_strided.argtypes = [H, C.c_void_p, C.c_size_t]
+    lib.vsmpc_create_multi.argtypes = [C.POINTER(VsmpcConfig), C.c_int, C.c_int, C.c_void_p, C.POINTER(H)]
+    lib.vsmpc_multi_last_error.argtypes = [H]
+    lib.vsmpc_multi_last_error.restype = C.c_char_p
+    for f in ("vsmpc_multi_destroy", "vsmpc_multi_n_shards", "vsmpc_multi_n_instances", "vsmpc_multi_solve",
+              "vsmpc_multi_solve_async", "vsmpc_multi_wait"):
+        getattr(lib, f).argtypes = [H]
+    lib.vsmpc_multi_shard.argtypes = [H, C.c_int, c_int_p, c_int_p, C.POINTER(H)]
+    lib.vsmpc_multi_configure.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.vsmpc_multi_set_instance_params.argtypes = [H, C.c_void_p]
+    lib.vsmpc_multi_set_state.argtypes = [H, C.c_void_p]
+    lib.vsmpc_multi_get_output.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.vsmpc_multi_set_full_solution.argtypes = [H, C.c_int]
+    lib.vsmpc_multi_get_full_solution.argtypes = [H, C.c_void_p]
     for f in EXPORTS:
-        if f != "vsmpc_last_error":
+        if f not in ("vsmpc_last_error", "vsmpc_multi_last_error"):
             getattr(lib, f).restype = C.c_int
     _lib = lib
     return lib

@@ -284,3 +284,92 @@ class BatchedVSMPC:
 
     def debug_set_counters(self, ref_counter: int = -1, throttle_counter: int = -1):
         self._ck(self._lib.vsmpc_debug_set_counters(self._h, ref_counter, throttle_counter), "vsmpc_debug_set_counters")
+
+
+class MultiGpuVSMPC:
+    """B instances sharded over several GPUs inside ONE process (C-ABI ``vsmpc_multi_*``: contiguous ranges, one handle and
+    stream set per device, no inter-GPU traffic; ``devices`` may repeat an index to put several shards on one GPU).  Same
+    call sequence and array layouts as ``BatchedVSMPC`` for the whole batch."""
+
+    def __init__(self, n_instances: int, params: dict | None, trajectories: dict, n_gpus: int, devices=None, solver: int = 0,
+                 full_solution: bool = False):
+        self._lib = L.load()
+        self.B, self.n_gpus = int(n_instances), int(n_gpus)
+        self.params = dict(default_params())
+        self.params.update(params or {})
+        keep: list = []
+        cfg = _cfg_struct(self.params, trajectories, solver, keep)
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        if dev is not None and dev.shape != (self.n_gpus,):
+            raise VsmpcError("devices must have one entry per shard")
+        h = C.c_void_p()
+        rc = self._lib.vsmpc_create_multi(C.byref(cfg), self.B, self.n_gpus, dev.ctypes.data if dev is not None else None,
+                                          C.byref(h))
+        self._h = h
+        if rc != L.OK:
+            msg = self._lib.vsmpc_multi_last_error(h).decode() if h else "vsmpc_create_multi failed"
+            if h:
+                self._lib.vsmpc_multi_destroy(h)
+            self._h = None
+            raise VsmpcError(f"vsmpc_create_multi: {msg} (code {rc})")
+        self.sel = list(DEFAULT_JOINT_SELECTOR)
+        N, Ns, Nc = int(self.params["nIter"]), int(self.params["nIterSmall"]), int(self.params["controlHorizon"])
+        self.n_var = 26 * (N + 1) + 8 * Nc + 4 * (Nc - Ns + 1)
+        self._ck(self._lib.vsmpc_multi_set_full_solution(h, 1 if full_solution else 0), "vsmpc_multi_set_full_solution")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vsmpc_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != L.OK:
+            raise VsmpcError(f"{what}: {self._lib.vsmpc_multi_last_error(self._h).decode()} (code {rc})")
+
+    def shards(self):
+        out = []
+        for g in range(self._lib.vsmpc_multi_n_shards(self._h)):
+            a, b = C.c_int(), C.c_int()
+            self._ck(self._lib.vsmpc_multi_shard(self._h, g, C.byref(a), C.byref(b), None), "vsmpc_multi_shard")
+            out.append((a.value, b.value))
+        return out
+
+    def configure_pack(self, pack, joint_pos_sel, phase0=None):
+        pack = BatchedVSMPC._f64(pack, (PACK_DOUBLES, self.B))
+        jp = BatchedVSMPC._f64(joint_pos_sel, (L.NJ, self.B))
+        ph = None if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
+        self._ck(self._lib.vsmpc_multi_configure(self._h, pack.ctypes.data, jp.ctypes.data,
+                                                 ph.ctypes.data if ph is not None else None), "vsmpc_multi_configure")
+        return True
+
+    def configure(self, state: dict, phase0=None):
+        return self.configure_pack(build_pack(state, self.sel), np.ascontiguousarray(state["joint_pos"][:, self.sel].T), phase0)
+
+    def update_pack(self, pack):
+        pack = BatchedVSMPC._f64(pack, (PACK_DOUBLES, self.B))
+        self._ck(self._lib.vsmpc_multi_set_state(self._h, pack.ctypes.data), "vsmpc_multi_set_state")
+        return True
+
+    def update(self, state: dict):
+        return self.update_pack(build_pack(state, self.sel))
+
+    def solveMPC(self):
+        self._ck(self._lib.vsmpc_multi_solve(self._h), "vsmpc_multi_solve")
+        return True
+
+    def get_output(self):
+        out = np.empty((self.B, L.OUT_DOUBLES))
+        status = np.empty(self.B, dtype=np.int32)
+        self._ck(self._lib.vsmpc_multi_get_output(self._h, out.ctypes.data, status.ctypes.data), "vsmpc_multi_get_output")
+        return out, status
+
+    def getSolution(self):
+        z = np.empty((self.B, self.n_var))
+        self._ck(self._lib.vsmpc_multi_get_full_solution(self._h, z.ctypes.data), "vsmpc_multi_get_full_solution")
+        return z

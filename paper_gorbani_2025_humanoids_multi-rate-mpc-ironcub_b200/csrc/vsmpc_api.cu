@@ -188,6 +188,14 @@ static void drop_tick_graph(vsmpc_handle* h)
     }
 }
 
+// host SoA [rows][stride] (column window of a larger batch) -> device SoA [rows][B]
+static cudaError_t copy_soa_h2d(double* dst, const double* src, int rows, size_t B, size_t stride, cudaStream_t s)
+{
+    if (stride == B)
+        return cudaMemcpyAsync(dst, src, (size_t)rows * B * 8, cudaMemcpyHostToDevice, s);
+    return cudaMemcpy2DAsync(dst, B * 8, src, stride * 8, B * 8, rows, cudaMemcpyHostToDevice, s);
+}
+
 extern "C" {
 
 static int solve_launch(vsmpc_handle* h);
@@ -450,12 +458,18 @@ static int run_linearise(vsmpc_handle* h, int mode)
 
 int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* joint_pos_sel_host, const int* phase0_host)
 {
-    if (!h || h->B <= 0 || !pack_host || !joint_pos_sel_host)
-        return fail(h, VSMPC_ERR_ARG, "vsmpc_configure: null argument");
+    return vsmpc_configure_strided(h, pack_host, joint_pos_sel_host, phase0_host, h ? (size_t)h->B : 0);
+}
+
+int vsmpc_configure_strided(vsmpc_handle* h, const double* pack_host, const double* joint_pos_sel_host, const int* phase0_host,
+                            size_t row_stride)
+{
+    if (!h || h->B <= 0 || !pack_host || !joint_pos_sel_host || row_stride < (size_t)h->B)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_configure: null argument or row stride smaller than the batch");
     CK(cudaSetDevice(h->device));
     const size_t B = h->B;
-    CK(cudaMemcpyAsync(h->d_pack, pack_host, VSMPC_PACK_DOUBLES * B * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_jpos, joint_pos_sel_host, NJ * B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(copy_soa_h2d(h->d_pack, pack_host, VSMPC_PACK_DOUBLES, B, row_stride, h->stream));
+    CK(copy_soa_h2d(h->d_jpos, joint_pos_sel_host, NJ, B, row_stride, h->stream));
     if (phase0_host)
     {
         for (size_t i = 0; i < B; ++i)
@@ -505,8 +519,13 @@ int vsmpc_set_instance_params(vsmpc_handle* h, const double* ip_host)
 
 int vsmpc_set_state(vsmpc_handle* h, const double* pack_host)
 {
-    if (!h || h->B <= 0 || !pack_host)
-        return fail(h, VSMPC_ERR_ARG, "vsmpc_set_state: null argument");
+    return vsmpc_set_state_strided(h, pack_host, h ? (size_t)h->B : 0);
+}
+
+int vsmpc_set_state_strided(vsmpc_handle* h, const double* pack_host, size_t row_stride)
+{
+    if (!h || h->B <= 0 || !pack_host || row_stride < (size_t)h->B)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_set_state: null argument or row stride smaller than the batch");
     if (!h->configured)
         return fail(h, VSMPC_ERR_STATE, "vsmpc_set_state: configure first");
     CK(cudaSetDevice(h->device));
@@ -514,8 +533,7 @@ int vsmpc_set_state(vsmpc_handle* h, const double* pack_host)
     // done with it), then make the compute stream wait for the copy: H2D of this tick overlaps the QP kernel of the last
     const int q = h->pack_idx ^= 1;
     CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1[q], 0));
-    CK(cudaMemcpyAsync(h->d_pack_in[q], pack_host, (size_t)VSMPC_PACK_DOUBLES * h->B * 8, cudaMemcpyHostToDevice,
-                       h->copy_stream));
+    CK(copy_soa_h2d(h->d_pack_in[q], pack_host, VSMPC_PACK_DOUBLES, (size_t)h->B, row_stride, h->copy_stream));
     CK(cudaEventRecord(h->ev_h2d[q], h->copy_stream));
     CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[q], 0));
     double* saved = h->d_pack;
@@ -1054,5 +1072,192 @@ int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host)
     CK(cudaStreamSynchronize(h->stream));
     return VSMPC_OK;
 }
+
+// ---- one process, several GPUs: contiguous instance ranges, one handle + stream per device ---------------
+struct vsmpc_multi
+{
+    std::vector<vsmpc_handle*> h;
+    std::vector<int> lo;       // first instance of every shard, and B at the end
+    int B = 0;
+    std::string err;
+};
+
+static int mfail(vsmpc_multi* m, int code, const std::string& msg)
+{
+    if (m)
+        m->err = msg;
+    return code;
+}
+
+int vsmpc_create_multi(const vsmpc_config* cfg, int n_instances, int n_gpus, const int* devices, vsmpc_multi** out)
+{
+    if (!cfg || !out || n_instances <= 0 || n_gpus <= 0)
+        return VSMPC_ERR_ARG;
+    *out = nullptr;
+    vsmpc_multi* m = new (std::nothrow) vsmpc_multi();
+    if (!m)
+        return VSMPC_ERR_ARG;
+    *out = m;      // kept alive on failure so that the message can be read
+    m->B = n_instances;
+    // shard g owns [g B / G, (g + 1) B / G); a device without instances (B < G) holds no handle
+    for (int g = 0; g <= n_gpus; ++g)
+        m->lo.push_back((int)(((long long)g * n_instances) / n_gpus));
+    m->h.assign(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g)
+    {
+        const int n = m->lo[g + 1] - m->lo[g];
+        if (n == 0)
+            continue;
+        const int rc = vsmpc_create(cfg, n, devices ? devices[g] : g, &m->h[g]);
+        if (rc != VSMPC_OK)
+        {
+            m->err = std::string("shard ") + std::to_string(g) + ": " + (m->h[g] ? vsmpc_last_error(m->h[g]) : "vsmpc_create failed");
+            for (vsmpc_handle*& q : m->h)
+            {
+                if (q)
+                    vsmpc_destroy(q);
+                q = nullptr;
+            }
+            m->B = 0;
+            return rc;
+        }
+    }
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_destroy(vsmpc_multi* m)
+{
+    if (!m)
+        return VSMPC_OK;
+    for (vsmpc_handle* q : m->h)
+        if (q)
+            vsmpc_destroy(q);
+    delete m;
+    return VSMPC_OK;
+}
+
+const char* vsmpc_multi_last_error(const vsmpc_multi* m) { return m ? m->err.c_str() : "null handle"; }
+int vsmpc_multi_n_shards(const vsmpc_multi* m) { return m ? (int)m->h.size() : -1; }
+int vsmpc_multi_n_instances(const vsmpc_multi* m) { return m ? m->B : -1; }
+
+int vsmpc_multi_shard(const vsmpc_multi* m, int shard, int* first, int* count, vsmpc_handle** handle)
+{
+    if (!m || shard < 0 || shard >= (int)m->h.size())
+        return VSMPC_ERR_ARG;
+    if (first)
+        *first = m->lo[shard];
+    if (count)
+        *count = m->lo[shard + 1] - m->lo[shard];
+    if (handle)
+        *handle = m->h[shard];
+    return VSMPC_OK;
+}
+
+#define MEACH(call, what)                                                                                     \
+    for (size_t g = 0; g < m->h.size(); ++g)                                                                  \
+        if (m->h[g])                                                                                          \
+        {                                                                                                     \
+            const int lo = m->lo[g];                                                                          \
+            (void)lo;                                                                                         \
+            const int rc__ = (call);                                                                          \
+            if (rc__ != VSMPC_OK)                                                                             \
+                return mfail(m, rc__, std::string(what) + ", shard " + std::to_string(g) + ": " + vsmpc_last_error(m->h[g])); \
+        }
+
+int vsmpc_multi_configure(vsmpc_multi* m, const double* pack_host, const double* joint_pos_sel_host, const int* phase0_host)
+{
+    if (!m || m->B <= 0 || !pack_host || !joint_pos_sel_host)
+        return mfail(m, VSMPC_ERR_ARG, "vsmpc_multi_configure: null argument");
+    MEACH(vsmpc_configure_strided(m->h[g], pack_host + lo, joint_pos_sel_host + lo, phase0_host ? phase0_host + lo : nullptr,
+                                  (size_t)m->B), "vsmpc_multi_configure");
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_set_instance_params(vsmpc_multi* m, const double* instance_params_host)
+{
+    if (!m || m->B <= 0)
+        return VSMPC_ERR_ARG;
+    for (size_t g = 0; g < m->h.size(); ++g)
+    {
+        if (!m->h[g])
+            continue;
+        if (!instance_params_host)
+        {
+            vsmpc_set_instance_params(m->h[g], nullptr);
+            continue;
+        }
+        // the per-device call takes a contiguous table: gather the shard's columns
+        const int lo = m->lo[g], n = m->lo[g + 1] - lo;
+        std::vector<double> t((size_t)IP_ROWS * n);
+        for (int r = 0; r < IP_ROWS; ++r)
+            std::memcpy(t.data() + (size_t)r * n, instance_params_host + (size_t)r * m->B + lo, sizeof(double) * n);
+        const int rc = vsmpc_set_instance_params(m->h[g], t.data());
+        if (rc != VSMPC_OK)
+            return mfail(m, rc, std::string("vsmpc_multi_set_instance_params, shard ") + std::to_string(g) + ": " + vsmpc_last_error(m->h[g]));
+    }
+    return VSMPC_OK;
+}
+
+// update on every device: the copies and linearise kernels of all shards are in flight together
+int vsmpc_multi_set_state(vsmpc_multi* m, const double* pack_host)
+{
+    if (!m || m->B <= 0 || !pack_host)
+        return mfail(m, VSMPC_ERR_ARG, "vsmpc_multi_set_state: null argument");
+    MEACH(vsmpc_set_state_strided(m->h[g], pack_host + lo, (size_t)m->B), "vsmpc_multi_set_state");
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_solve_async(vsmpc_multi* m)
+{
+    if (!m || m->B <= 0)
+        return VSMPC_ERR_ARG;
+    MEACH(vsmpc_solve_async(m->h[g]), "vsmpc_multi_solve");
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_wait(vsmpc_multi* m)
+{
+    if (!m || m->B <= 0)
+        return VSMPC_ERR_ARG;
+    MEACH(vsmpc_wait(m->h[g]), "vsmpc_multi_wait");
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_solve(vsmpc_multi* m)
+{
+    const int rc = vsmpc_multi_solve_async(m);
+    return rc ? rc : vsmpc_multi_wait(m);
+}
+
+// the only gather of the path: every device copies its contiguous range of rows into the caller's arrays
+int vsmpc_multi_get_output(vsmpc_multi* m, double* out_rows_host, int* status_host)
+{
+    if (!m || m->B <= 0)
+        return VSMPC_ERR_ARG;
+    int tickets[64];
+    if (m->h.size() > 64)
+        return mfail(m, VSMPC_ERR_ARG, "vsmpc_multi_get_output: more than 64 shards");
+    MEACH(vsmpc_get_output_async(m->h[g], out_rows_host ? out_rows_host + (size_t)lo * VSMPC_OUT_DOUBLES : nullptr,
+                                 status_host ? status_host + lo : nullptr, &tickets[g]), "vsmpc_multi_get_output");
+    MEACH(vsmpc_wait_output(m->h[g], tickets[g]), "vsmpc_multi_get_output");
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_set_full_solution(vsmpc_multi* m, int enable)
+{
+    if (!m || m->B <= 0)
+        return VSMPC_ERR_ARG;
+    MEACH(vsmpc_set_full_solution(m->h[g], enable), "vsmpc_multi_set_full_solution");
+    return VSMPC_OK;
+}
+
+int vsmpc_multi_get_full_solution(vsmpc_multi* m, double* z_host)
+{
+    if (!m || m->B <= 0 || !z_host)
+        return VSMPC_ERR_ARG;
+    MEACH(vsmpc_get_full_solution(m->h[g], z_host + (size_t)lo * vsmpc_n_var(m->h[g])), "vsmpc_multi_get_full_solution");
+    return VSMPC_OK;
+}
+#undef MEACH
 
 } // extern "C"

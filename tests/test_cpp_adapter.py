@@ -76,3 +76,81 @@ def test_cpp_controller_matches_python_host(tmp_path):
                               out[L.OUT_FINAL_STATE:L.OUT_FINAL_STATE + 12], [float(st[0])]])
         np.testing.assert_allclose(got[t], exp, rtol=1e-12, atol=1e-12)
     mpc.close()
+
+
+def _batch_inputs(tmp_path, B, n_ticks):
+    syn, pack = pkg("synthetic"), pkg("pack")
+    d = np.load(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+    nom = syn.make_states(B, perturbed=False)
+    sel = list(pack.DEFAULT_JOINT_SELECTOR)
+    packs = [pack.build_pack(syn.make_states(B, seed=300 + t, perturbed=True, near_bound_fraction=0.3)) for t in range(n_ticks)]
+    blob = np.concatenate([
+        [d["alphaGravity"].size, d["positionCoM"].shape[1], n_ticks, nom["joint_pos"].shape[1], B],
+        d["alphaGravity"].ravel(), d["positionCoM"].T.ravel(), d["velocityCoM"].T.ravel(), d["RPY"].T.ravel(),
+        d["RPYDot"].T.ravel(), np.array(sel, dtype=np.float64), nom["joint_pos"].ravel(),
+        pack.build_pack(nom).T.ravel()] + [p.T.ravel() for p in packs]).astype(np.float64)     # instance-major records
+    fin = str(tmp_path / "in_batch.bin")
+    blob.tofile(fin)
+    return fin, nom, packs, sel
+
+
+@pytest.mark.gpu
+def test_cpp_one_process_multi_gpu_batch(tmp_path):
+    """examples/cpp_multi_gpu.cpp: vsmpc::PackBatch (per-instance records -> SoA) + vsmpc::MultiGpuMPC (vsmpc_create_multi)
+    in one process.  On a one-GPU box the shards share device 0 — the same host path, the same split of the SoA by column
+    range —; with two or more GPUs they go to devices 0 and 1.  The program itself checks bit-identity with the single-device
+    batch on every tick; here its rows are compared with the Python host layer."""
+    import torch
+    pkg("_build").build_examples()
+    exe = os.path.join(ROOT, "examples", "bin", "cpp_multi_gpu")
+    B, n_ticks = 37, 3           # ragged: shards of 12 / 12 / 13
+    fin, nom, packs, sel = _batch_inputs(tmp_path, B, n_ticks)
+    for devices in (["0", "0", "0"], ["0", "1"] if torch.cuda.device_count() >= 2 else ["0", "0"]):
+        fout = str(tmp_path / "out_batch.bin")
+        res = subprocess.run([exe, fin, fout, ",".join(devices)], capture_output=True, text=True)
+        assert res.returncode == 0, (res.returncode, res.stderr)
+        assert "bit-identical" in res.stdout
+        got = np.fromfile(fout).reshape(n_ticks, B, 55)
+        bat, P, L = pkg("batched"), pkg("pack"), pkg("_lib")
+        traj = pkg("config").load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+        mpc = bat.BatchedVSMPC(B, None, traj)
+        mpc.configure(nom, phase0=(np.arange(B) % 20).astype(np.int32))
+        off = P.PACK_OFFSETS
+        out = None
+        for t in range(n_ticks):
+            pk = packs[t].copy()
+            if t > 0:
+                pk[off["throttle_prev"][0]:off["throttle_prev"][0] + 4] = out[:, L.OUT_THROTTLE:L.OUT_THROTTLE + 4].T
+                pk[off["thrust_des"][0]:off["thrust_des"][0] + 4] = out[:, L.OUT_THRUST:L.OUT_THRUST + 4].T
+                pk[off["thrust_dot_des"][0]:off["thrust_dot_des"][0] + 4] = out[:, L.OUT_THRUST_DOT:L.OUT_THRUST_DOT + 4].T
+                pk[off["q_cmd"][0]:off["q_cmd"][0] + 8] = out[:, L.OUT_JOINTS_REF:L.OUT_JOINTS_REF + 8].T
+            mpc.update_pack(np.ascontiguousarray(pk))
+            mpc.solveMPC()
+            out, st = mpc.get_output()
+            assert np.array_equal(got[t, :, :54], out) and np.array_equal(got[t, :, 54], st.astype(float))
+        mpc.close()
+
+
+@pytest.mark.gpu
+def test_python_multi_handle_matches_single(tmp_path):
+    """vsmpc_multi_* through ctypes: ragged shards (incl. a shard without instances when B < G), per-instance parameters
+    split by column range, full solution gathered — bit-identical to one handle."""
+    import torch
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = pkg("config").load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+    ndev = torch.cuda.device_count()
+    for B, G in ((50, 4), (3, 5)):
+        nom = syn.make_states(B, perturbed=False)
+        per = syn.make_states(B, seed=12, perturbed=True, near_bound_fraction=0.4)
+        one = bat.BatchedVSMPC(B, None, traj, full_solution=True)
+        multi = bat.MultiGpuVSMPC(B, None, traj, n_gpus=G, devices=[g % ndev for g in range(G)], full_solution=True)
+        assert sum(c for _, c in multi.shards()) == B
+        ph = (np.arange(B) % 20).astype(np.int32)
+        one.configure(nom, ph); multi.configure(nom, ph)
+        for _ in range(2):
+            one.update(per); multi.update(per)
+            one.solveMPC(); multi.solveMPC()
+            (o1, s1), (o2, s2) = one.get_output(), multi.get_output()
+            assert np.array_equal(o1, o2) and np.array_equal(s1, s2) and (s1 == 0).all()
+            assert np.array_equal(one.getSolution(), multi.getSolution())
+        one.close(); multi.close()
