@@ -223,6 +223,12 @@ int vsmpc_get_hessian(vsmpc_handle* h, int instance, double* P_host);
 /* IMPCProblem::getLinearConstraintMatrix (IMPCProblem.h:100): dense n_con x n_var, row-major, of one instance for the
  * current tick, in the reference's row order (dynamics, initial state, throttle; variableSamplingMPC.cpp:77-84) */
 int vsmpc_get_constraint_matrix(vsmpc_handle* h, int instance, double* A_host);
+/* Fallback QP kernel of the default solver.  The Riccati recursion of the condensed kernels breaks down (status 2 on finite
+ * data) when the open-loop transition of the linearised model expands strongly — |omega_B| >~ 30 rad/s, a lost vehicle —
+ * although the QP stays well posed (the reference's OSQP returns its minimiser).  Such instances are solved by a pivoted LU
+ * of the KKT system (csrc/vsmpc_qp_fallback.cu) launched behind the QP kernel.  mode 0: off (status 2 holds the outputs),
+ * 1: on (default), 2: EVERY instance goes through the fallback kernel (parity tests of the fallback itself). */
+int vsmpc_set_fallback(vsmpc_handle* h, int mode);
 /* test hook: overwrite the two 20-tick phase counters (ReferenceTrackingCost::m_counter,
  * ThrottleConstraint::m_counter) of every instance; -1 leaves a counter unchanged */
 int vsmpc_debug_set_counters(vsmpc_handle* h, int ref_counter, int throttle_counter);

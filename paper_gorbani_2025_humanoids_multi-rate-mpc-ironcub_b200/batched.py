@@ -282,6 +282,10 @@ class BatchedVSMPC:
         self._ck(self._lib.vsmpc_get_constraint_matrix(self._h, int(instance), A.ctypes.data), "vsmpc_get_constraint_matrix")
         return A
 
+    def set_fallback(self, mode: int):
+        """Fallback QP kernel (pivoted LU of the KKT system): 0 off, 1 on (default), 2 every instance (tests)."""
+        self._ck(self._lib.vsmpc_set_fallback(self._h, int(mode)), "vsmpc_set_fallback")
+
     def debug_set_counters(self, ref_counter: int = -1, throttle_counter: int = -1):
         self._ck(self._lib.vsmpc_debug_set_counters(self._h, ref_counter, throttle_counter), "vsmpc_debug_set_counters")
 

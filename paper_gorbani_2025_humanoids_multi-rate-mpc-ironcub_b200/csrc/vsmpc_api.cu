@@ -1,6 +1,7 @@
 // C-ABI host layer (include/vsmpc.h): owns the device buffers of one batch of MPC instances on one
 // GPU and launches the kernels.  Mirrors the call sequence of the reference's
 // VariableSamplingMPC (configure -> update -> solveMPC -> getters).
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -25,7 +26,14 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
                              const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
-                             cudaStream_t s);
+                             int* fb_count, cudaStream_t s);
+bool fallback_supported(const DeviceConfig& cfg);
+size_t fallback_slot_doubles(const DeviceConfig& cfg);
+size_t fallback_pos_ints(const DeviceConfig& cfg);
+void fallback_positions(const DeviceConfig& cfg, int* out);
+cudaError_t launch_qp_fallback(const DeviceConfig& h_cfg, int B, int n_slots, const double* qd, const int* fb_list,
+                               const int* fb_count, const int* pos, double* scratch, double* z, double* st, double* out_rows,
+                               int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, cudaStream_t s);
 cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const double* qd, double* A, double* BJ,
                                    double* BT, double* c, cudaStream_t s);
 cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
@@ -48,13 +56,14 @@ int condensed_wide_phase_clocks(long long* host, int n);
 size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
-                                int* n_solve, int* n_pivot, int want_z, cudaStream_t s);
+                                int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
+                                cudaStream_t s);
 bool condensed_wide_supported(const DeviceConfig& cfg);
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
-                                     int* n_pivot, int want_z, cudaStream_t s);
+                                     int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, cudaStream_t s);
 } // namespace vsmpc
 
 using namespace vsmpc;
@@ -101,6 +110,13 @@ struct vsmpc_handle
     int* d_status = nullptr;
     int *d_nf = nullptr, *d_ns = nullptr, *d_np = nullptr;   // factorisations, forward passes, exchange pivots of the last solve
     cudaEvent_t ev_stream = nullptr;     // orders a new stream behind the old one in vsmpc_set_stream
+    // fallback QP kernel (vsmpc_qp_fallback.cu): instances the Riccati recursion breaks down on
+    int* d_fb_list = nullptr;            // int[B]
+    int* d_fb_count = nullptr;           // zeroed by the linearise kernel, filled by the QP kernel
+    int* d_fb_pos = nullptr;             // bordered-band positions of the KKT unknowns
+    double* d_fb_scratch = nullptr;      // n_slots x fallback_slot_doubles
+    int fb_slots = 0;
+    int fb_mode = 0;                     // 0 off, 1 on (default where supported), 2 every instance (tests)
     // device-resident closed loop
     PlantModel* d_pm = nullptr;
     double* d_ps = nullptr;
@@ -366,6 +382,27 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(dalloc(&h->d_nf, (size_t)B));
     A(dalloc(&h->d_ns, (size_t)B));
     A(dalloc(&h->d_np, (size_t)B));
+    if ((h->solver == 0 || h->solver == SOLVER_WIDE) && fallback_supported(g))
+    {
+        // slots: concurrent fallback solves; a slot holds the dense [K | R] of one instance (9 MB at the reference horizon)
+        const size_t per = fallback_slot_doubles(g) * sizeof(double);
+        size_t slots = std::max<size_t>(2, std::min<size_t>(64, (size_t)B / 256));
+        slots = std::max<size_t>(1, std::min(slots, ((size_t)640 << 20) / per));
+        slots = std::min(slots, (size_t)B);
+        h->fb_slots = (int)slots;
+        std::vector<int> pos(fallback_pos_ints(g));
+        fallback_positions(g, pos.data());
+        A(dalloc(&h->d_fb_list, (size_t)B));
+        A(dalloc(&h->d_fb_count, 1));
+        A(dalloc(&h->d_fb_pos, pos.size()));
+        A(dalloc(&h->d_fb_scratch, fallback_slot_doubles(g) * slots));
+        if (ok)
+        {
+            A(cudaMemcpy(h->d_fb_pos, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+            A(cudaMemset(h->d_fb_count, 0, sizeof(int)));
+        }
+        h->fb_mode = 1;
+    }
     if (ok)
     {
         A(cudaMemcpy(h->d_cfg, &g, sizeof(g), cudaMemcpyHostToDevice));
@@ -402,7 +439,7 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
+                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
                     h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -452,7 +489,7 @@ static int run_linearise(vsmpc_handle* h, int mode)
 {
     CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
                         h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd,
-                        h->use_ip ? h->d_ip : nullptr, h->stream));
+                        h->use_ip ? h->d_ip : nullptr, h->d_fb_count, h->stream));
     return VSMPC_OK;
 }
 
@@ -806,6 +843,18 @@ int vsmpc_get_constraint_matrix(vsmpc_handle* h, int instance, double* A_host)
     return VSMPC_OK;
 }
 
+int vsmpc_set_fallback(vsmpc_handle* h, int mode)
+{
+    if (!h || h->B <= 0 || mode < 0 || mode > 2)
+        return VSMPC_ERR_ARG;
+    if (mode != 0 && !h->d_fb_list)
+        return fail(h, VSMPC_ERR_UNSUPPORTED, "vsmpc_set_fallback: the fallback QP kernel belongs to the default solver");
+    if (mode != h->fb_mode)
+        drop_tick_graph(h);
+    h->fb_mode = mode;
+    return VSMPC_OK;
+}
+
 int vsmpc_debug_phase_clocks(long long* clocks_host, int n_instances)
 {
     return g_last_qp_solver.load(std::memory_order_relaxed) == SOLVER_WIDE ? condensed_wide_phase_clocks(clocks_host, n_instances)
@@ -846,16 +895,22 @@ static int solve_launch(vsmpc_handle* h)
     g_last_qp_solver.store(h->solver, std::memory_order_relaxed);
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
-                               h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->stream));
+                               h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count, h->fb_mode,
+                               h->stream));
     else if (h->solver == SOLVER_WIDE)
         CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
-                                    h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->stream));
+                                    h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count,
+                                    h->fb_mode, h->stream));
     else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));
     else
         CK(launch_qp_structured(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                                 h->d_status, h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
+    if (h->fb_mode != 0 && (h->solver == 0 || h->solver == SOLVER_WIDE))
+        CK(launch_qp_fallback(h->cfg, h->B, h->fb_slots, h->d_qd, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch,
+                              h->d_z, h->d_st, h->d_out, h->d_status, h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0,
+                              h->stream));
     return VSMPC_OK;
 }
 

@@ -179,4 +179,62 @@ __device__ inline double destd_throttle_qd(const double* __restrict__ cf, double
     return u < 0.0 ? 0.0 : (u > 100.0 ? 100.0 : u);
 }
 
+__device__ __forceinline__ void skew3(const double* v, double* S)
+{ // UT/src/FlightControlUtils.cpp:77-85
+    S[0] = 0.0; S[1] = -v[2]; S[2] = v[1];
+    S[3] = v[2]; S[4] = 0.0; S[5] = -v[0];
+    S[6] = -v[1]; S[7] = v[0]; S[8] = 0.0;
+}
+
+
+// dense (A, B_J, B_T, c) of one instance from its QP data block (SystemDynamicVS::get{A,BJoints,BThrottle}Matrix / getCVector)
+__device__ inline void expand_dense(const double* __restrict__ q, double* A, double* BJ, double* BT, double* c)
+{
+    for (int e = 0; e < NX * NX; ++e)
+        A[e] = 0.0;
+    for (int e = 0; e < NX * NJ; ++e)
+        BJ[e] = 0.0;
+    for (int e = 0; e < NX * NT; ++e)
+        BT[e] = 0.0;
+    for (int e = 0; e < NX; ++e)
+        c[e] = 0.0;
+    double S[9];
+    skew3(q + QD_OMEGA, S);
+    for (int a = 0; a < 3; ++a)
+    {
+        for (int b = 0; b < 3; ++b)
+        {
+            A[(IX_COM + a) * NX + IX_LIN + b] = q[QD_RM + a * 3 + b];
+            A[(IX_LIN + a) * NX + IX_LIN + b] = (S[a * 3 + b] == 0.0) ? 0.0 : -S[a * 3 + b];
+            A[(IX_RPY + a) * NX + IX_ANG + b] = q[QD_WI + a * 3 + b];
+            A[(IX_ANG + a) * NX + IX_ANG + b] = (S[a * 3 + b] == 0.0) ? 0.0 : -S[a * 3 + b];
+        }
+        for (int j = 0; j < NT; ++j)
+        {
+            A[(IX_LIN + a) * NX + IX_T + j] = q[QD_ALIN + a * NT + j];
+            A[(IX_ANG + a) * NX + IX_T + j] = q[QD_AANG + a * NT + j];
+        }
+        for (int b = 0; b < NJ; ++b)
+        {
+            BJ[(IX_LIN + a) * NJ + b] = q[QD_LLIN + a * NJ + b];
+            BJ[(IX_ANG + a) * NJ + b] = q[QD_LANG + a * NJ + b];
+        }
+        A[(IX_EP + a) * NX + IX_COM + a] = 1.0;
+        A[(IX_ER + a) * NX + IX_RPY + a] = 1.0;
+        c[IX_LIN + a] = q[QD_CL + a];
+        c[IX_EP + a] = q[QD_CEP + a];
+        c[IX_ER + a] = q[QD_CER + a];
+    }
+    for (int j = 0; j < NT; ++j)
+    {
+        A[(IX_T + j) * NX + IX_TD + j] = q[QD_JTT];
+        A[(IX_TD + j) * NX + IX_T + j] = q[QD_JA + j];
+        A[(IX_TD + j) * NX + IX_TD + j] = q[QD_JB + j];
+        BT[(IX_TD + j) * NT + j] = q[QD_JG + j];
+        BT[(IX_T + j) * NT + j] = q[QD_JGT];
+        c[IX_TD + j] = q[QD_CTD + j];
+    }
+}
+
+
 } // namespace vsmpc

@@ -26,13 +26,6 @@ __device__ __forceinline__ void mat3T_vec(const double* R, const double* v, doub
     o[2] = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
 }
 
-__device__ __forceinline__ void skew3(const double* v, double* S)
-{ // UT/src/FlightControlUtils.cpp:77-85
-    S[0] = 0.0; S[1] = -v[2]; S[2] = v[1];
-    S[3] = v[2]; S[4] = 0.0; S[5] = -v[0];
-    S[6] = -v[1]; S[7] = v[0]; S[8] = 0.0;
-}
-
 __device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C)
 {
 #pragma unroll
@@ -179,7 +172,8 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
                  const int* __restrict__ phase0, double* __restrict__ st, int* __restrict__ si,
                  const double* __restrict__ alpha_traj, const double* __restrict__ traj_pos,
                  const double* __restrict__ traj_vel, const double* __restrict__ traj_rpy,
-                 const double* __restrict__ traj_rpyd, double* __restrict__ qd, const double* __restrict__ ip)
+                 const double* __restrict__ traj_rpyd, double* __restrict__ qd, const double* __restrict__ ip,
+                 int* __restrict__ fb_count)
 {
     extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12] | ipar[20] | stc[st_rows] | sic[4]
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank): no global round trip for the configuration
@@ -188,6 +182,8 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
     const int NC = cfg.NC;
     const int per_warp = k1_per_warp(cfg);
     const size_t Bs = (size_t)B;
+    if (fb_count && blockIdx.x == 0 && threadIdx.x == 0)
+        *fb_count = 0;   // the list of instances for the fallback QP kernel is refilled by this tick's QP kernel
     {
         // ---- cooperative tile staging: thread -> (row f, column c) with c fastest; every global load of the tick is
         // issued before the first one is consumed (one DRAM round trip)
@@ -602,54 +598,6 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
 
 
 // ---- dense expansion for parity tests (vsmpc_get_dynamics / vsmpc_get_qp_vectors) ----------------
-__device__ void expand_dense(const double* __restrict__ q, double* A, double* BJ, double* BT, double* c)
-{
-    for (int e = 0; e < NX * NX; ++e)
-        A[e] = 0.0;
-    for (int e = 0; e < NX * NJ; ++e)
-        BJ[e] = 0.0;
-    for (int e = 0; e < NX * NT; ++e)
-        BT[e] = 0.0;
-    for (int e = 0; e < NX; ++e)
-        c[e] = 0.0;
-    double S[9];
-    skew3(q + QD_OMEGA, S);
-    for (int a = 0; a < 3; ++a)
-    {
-        for (int b = 0; b < 3; ++b)
-        {
-            A[(IX_COM + a) * NX + IX_LIN + b] = q[QD_RM + a * 3 + b];
-            A[(IX_LIN + a) * NX + IX_LIN + b] = (S[a * 3 + b] == 0.0) ? 0.0 : -S[a * 3 + b];
-            A[(IX_RPY + a) * NX + IX_ANG + b] = q[QD_WI + a * 3 + b];
-            A[(IX_ANG + a) * NX + IX_ANG + b] = (S[a * 3 + b] == 0.0) ? 0.0 : -S[a * 3 + b];
-        }
-        for (int j = 0; j < NT; ++j)
-        {
-            A[(IX_LIN + a) * NX + IX_T + j] = q[QD_ALIN + a * NT + j];
-            A[(IX_ANG + a) * NX + IX_T + j] = q[QD_AANG + a * NT + j];
-        }
-        for (int b = 0; b < NJ; ++b)
-        {
-            BJ[(IX_LIN + a) * NJ + b] = q[QD_LLIN + a * NJ + b];
-            BJ[(IX_ANG + a) * NJ + b] = q[QD_LANG + a * NJ + b];
-        }
-        A[(IX_EP + a) * NX + IX_COM + a] = 1.0;
-        A[(IX_ER + a) * NX + IX_RPY + a] = 1.0;
-        c[IX_LIN + a] = q[QD_CL + a];
-        c[IX_EP + a] = q[QD_CEP + a];
-        c[IX_ER + a] = q[QD_CER + a];
-    }
-    for (int j = 0; j < NT; ++j)
-    {
-        A[(IX_T + j) * NX + IX_TD + j] = q[QD_JTT];
-        A[(IX_TD + j) * NX + IX_T + j] = q[QD_JA + j];
-        A[(IX_TD + j) * NX + IX_TD + j] = q[QD_JB + j];
-        BT[(IX_TD + j) * NT + j] = q[QD_JG + j];
-        BT[(IX_T + j) * NT + j] = q[QD_JGT];
-        c[IX_TD + j] = q[QD_CTD + j];
-    }
-}
-
 __global__ void expand_dynamics_kernel(const DeviceConfig* __restrict__ cfgp, int B, const double* __restrict__ qd,
                                        double* A, double* BJ, double* BT, double* c)
 {
@@ -803,7 +751,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
                              const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
-                             cudaStream_t s)
+                             int* fb_count, cudaStream_t s)
 {
     const size_t smem = (size_t)K1_WARPS * k1_per_warp(h_cfg) * sizeof(double);
     static bool attr_set[64] = {};
@@ -816,7 +764,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
     }
     const int grid = (B + K1_WARPS - 1) / K1_WARPS;
     linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(h_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
-                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip);
+                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip, fb_count);
     return cudaGetLastError();
 }
 

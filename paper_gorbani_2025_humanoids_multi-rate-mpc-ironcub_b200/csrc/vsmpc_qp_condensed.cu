@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(CD_THREADS, 8)
 qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                     double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
                     double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
-                    int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z)
+                    int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,
+                    int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode)
 {
     __shared__ CdSmem sm;
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank)
@@ -725,9 +726,15 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     // ---- warp A: forward rollout ---------------------------------------------------------------------------------------
     double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
     double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
+    if (fb_mode == 2 && all_fin)
+        stat = VSMPC_STATUS_NUMERICAL;   // test hook: every instance goes through the fallback kernel
     const bool solved = stat == VSMPC_STATUS_SOLVED;
     if (lane == 0)
     {
+        // the recursion broke down on finite data (expanding open-loop dynamics, vsmpc_qp_fallback.cu): hand the instance to
+        // the pivoted-LU kernel that runs behind this one; until it succeeds the status stays and the outputs are held
+        if (!solved && all_fin && fb_mode != 0)
+            fb_list[atomicAdd(fb_count, 1)] = inst;
         status[inst] = stat;
         n_factor[inst] = 1;              // one backward recursion (no re-factorisation: the active set works on H_r)
         n_solve[inst] = solved ? 1 : 0;  // one forward pass, skipped for a held instance
@@ -761,10 +768,12 @@ size_t condensed_ws_doubles(const DeviceConfig& cfg)
 
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
-                                int* n_solve, int* n_pivot, int want_z, cudaStream_t s)
+                                int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
+                                cudaStream_t s)
 {
     qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot,
-                                                 condensed_ws_doubles(h_cfg), want_z);
+                                                 condensed_ws_doubles(h_cfg), want_z, fb_list, fb_count,
+                                                 fb_list && fb_count ? fb_mode : 0);
     return cudaGetLastError();
 }
 

@@ -413,7 +413,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                          double* __restrict__ ws_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
                          int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride,
-                         int want_z)
+                         int want_z, int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode)
 {
     extern __shared__ __align__(16) unsigned char cw_raw[];
     CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
@@ -846,8 +846,12 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     // ---- warp 0: forward rollout and outputs ----------------------------------------------------------------------
     double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
     double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
+    if (fb_mode == 2 && all_fin)
+        stat = VSMPC_STATUS_NUMERICAL;   // test hook: every instance goes through the fallback kernel
     if (lane == 0)
     {
+        if (stat != VSMPC_STATUS_SOLVED && all_fin && fb_mode != 0)   // see vsmpc_qp_fallback.cu
+            fb_list[atomicAdd(fb_count, 1)] = inst;
         status[inst] = stat;
         n_factor[inst] = 1;
         n_solve[inst] = stat == VSMPC_STATUS_SOLVED ? 1 : 0;
@@ -895,27 +899,28 @@ size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
 
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
-                                     int* n_pivot, int want_z, cudaStream_t s)
+                                     int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, cudaStream_t s)
 {
     static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
     const CwLayout L = cw_layout(h_cfg);
     const size_t smem = cw_smem_bytes(h_cfg);
     const size_t wsd = condensed_wide_ws_doubles(h_cfg);
     (void)scratch;     // no global scratch beyond the workspace stacks
+    const int fbm = fb_list && fb_count ? fb_mode : 0;
     cudaError_t e;
     if (L.G <= 2)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                       n_factor, n_solve, n_pivot, wsd, want_z);
+                                                                       n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm);
     }
     else if (L.G == 3)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                        n_factor, n_solve, n_pivot, wsd, want_z);
+                                                                        n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm);
     }
     else
     {
@@ -924,7 +929,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
         // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
         qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
-            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z);
+            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm);
     }
     return cudaGetLastError();
 }

@@ -22,6 +22,8 @@ for s in $STEPS; do
     ncu_list) timeout 200 $CMD > $O/${TAG}_plain.log 2>&1 && timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launches.log 2>&1;;
     ncu_k1) timeout 200 $CMD > $O/${TAG}_plain.log 2>&1 && timeout 400 ncu --set full --clock-control none --import-source on -k regex:linearise -s 4 -c 1 -o $O/${TAG}_lin -f $CMD > $O/${TAG}_ncu_lin.log 2>&1;;
     ncu_k2) timeout 200 $CMD > $O/${TAG}_plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:qp_condensed -s 4 -c 1 -o $O/${TAG}_qp -f $CMD > $O/${TAG}_ncu_qp.log 2>&1;;
+    fb_sanitize) timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_fallback.py -x -q -k "every_instance and (0 or 3)" > $O/${TAG}_fb_sanitize.log 2>&1; echo "rc=$?" >> $O/${TAG}_fb_sanitize.log; tail -25 $O/${TAG}_fb_sanitize.log;;
+    fb_tests) timeout 900 python -m pytest tests/test_gpu_fallback.py -q --maxfail 20 > $O/${TAG}_fb_tests.log 2>&1; echo "rc=$?" >> $O/${TAG}_fb_tests.log; tail -40 $O/${TAG}_fb_tests.log;;
     *) echo "unknown step $s";;
   esac
 done
