@@ -120,6 +120,15 @@ typedef struct vsmpc_config
     int solver;               /* 0 = default (condensed-throttle Riccati kernel: two warps per instance at the reference
                                  horizon, 1 + G warps for long horizons, generic kernel beyond ~37 throttle blocks);
                                  1 = generic dense variant; 2 = structured one-warp kernel (cross-checks) */
+    /* Optional joint-limit rows (BASELINE configs[4] "per-instance constraint sets"): the reference's JointPositionConstraint
+     * (constraintsVSMPC.cpp:388-468; present but not registered in the shipped problem, its parameters jointPos_max /
+     * jointPos_min [degrees, :421-423] are absent from the XML).  When enabled, 8 * nIter rows are appended after the throttle
+     * rows (:391), block i < controlHorizon bounding dq_i — the displacement from the commanded posture acting on knot i — by
+     * jointPos_min - q_cmd <= dq_i <= jointPos_max - q_cmd (:450-453), per block.  The reference's m_firstIteriation slip
+     * (:440-449, identity rows only for block 0) is fixed, not ported.  Default solver only. */
+    int use_joint_limits;
+    double joint_pos_min_deg[VSMPC_NJ];   /* jointPos_min of the controlled joints */
+    double joint_pos_max_deg[VSMPC_NJ];   /* jointPos_max */
 } vsmpc_config;
 
 /* lifecycle ------------------------------------------------------------------------------------ */
@@ -151,6 +160,10 @@ int vsmpc_configure(vsmpc_handle* h, const double* pack_host, const double* join
 #define VSMPC_IP_THROTTLE_MAX  18   /* 1  [percent] */
 #define VSMPC_INSTANCE_PARAM_DOUBLES 19
 int vsmpc_set_instance_params(vsmpc_handle* h, const double* instance_params_host);
+
+/* per-instance joint limits [rad] of the controlled joints, SoA double[8][B] each, replacing the handle-wide jointPos_min /
+ * jointPos_max for every later call (NULL, NULL: back to the handle-wide values); needs use_joint_limits at create */
+int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const double* q_max_host);
 
 /* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel. */
 int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);

@@ -53,6 +53,10 @@ struct Params
     std::vector<double> positionCoM, velocityCoM, RPY, RPYDot;
     int trajFps = 10;
     int solver = 0;
+    // optional joint-limit rows (JointPositionConstraint, constraintsVSMPC.cpp:388-468; degrees like jointPos_max / jointPos_min)
+    bool useJointLimits = false;
+    double jointPosMin[VSMPC_NJ] = {-180, -180, -180, -180, -180, -180, -180, -180};
+    double jointPosMax[VSMPC_NJ] = {180, 180, 180, 180, 180, 180, 180, 180};
 };
 
 // ---- one instance's input pack (what update(QPInput&) reads) ------------------------------
@@ -129,6 +133,12 @@ inline void fill_config(const Params& p, vsmpc_config& c)
     c.traj_len = static_cast<int>(p.positionCoM.size() / 3);
     c.traj_fps = p.trajFps;
     c.solver = p.solver;
+    c.use_joint_limits = p.useJointLimits ? 1 : 0;
+    for (int a = 0; a < VSMPC_NJ; ++a)
+    {
+        c.joint_pos_min_deg[a] = p.jointPosMin[a];
+        c.joint_pos_max_deg[a] = p.jointPosMax[a];
+    }
 }
 } // namespace detail
 

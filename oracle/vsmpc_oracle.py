@@ -927,6 +927,51 @@ class ThrottleConstraint(_Constraint):
         return True
 
 
+class JointPositionConstraint(_Constraint):
+    """constraintsVSMPC.cpp:388-468 — present in the reference but NOT registered in the shipped problem
+    (variableSamplingMPC.cpp:77-84 lists three constraints) and its XML has no jointPos_max / jointPos_min; offered here as the
+    optional per-instance joint-limit rows of BASELINE configs[4] (SURVEY §8d Config 5), registered after the throttle rows
+    when the parameters carry `jointPos_max` / `jointPos_min` [degrees, :421-423].
+
+    Semantics kept: the class is sized nJoints * nIter rows (:391), block i < controlHorizon bounds dq_i — the displacement of
+    the controlled joints from the commanded posture that acts on knot i — by
+        jointPos_min - q_cmd[controlled] <= dq_i <= jointPos_max - q_cmd[controlled]              (:450-453)
+    for EVERY block (per block, not cumulative: dq_i is a displacement, the accumulation over ticks happens in q_cmd).
+    Deliberately NOT ported: the `m_firstIteriation = false` inside the loop (:440-449), which leaves the identity rows of
+    blocks 1.. unset and turns their bounds into constraints on all-zero rows (infeasible whenever q_cmd leaves the limits)."""
+
+    def __init__(self, nVar, nStates, nJoints, nIter):
+        super().__init__(nVar, nJoints * nIter)
+        self.nIter, self.nStates, self.nJoints = nIter, nStates, nJoints
+
+    def readConfigParameters(self, p, qpInput, trajectories):
+        self.jointPositionMax = np.asarray(p["jointPos_max"], float) * math.pi / 180.0
+        self.jointPositionMin = np.asarray(p["jointPos_min"], float) * math.pi / 180.0
+        assert self.jointPositionMax.shape == (self.nJoints,) and self.jointPositionMin.shape == (self.nJoints,)
+        self.ctrlHorizon = p["controlHorizon"]
+        self.controlledJoints = list(p["controlledJoints"])
+
+    def configureDynVectorsSize(self, qpInput):  # :428-433
+        self.robot = qpInput.getRobot()
+        # the reference indexes getOutputQPJointsPosition().segment(3, nJoints) (:451): the controlled joints of the shipped
+        # robot; here by name, like every other class of the problem
+        self.sel = [i for name in self.controlledJoints for i in range(self.robot.getNJoints())
+                    if name == self.robot.joint_names[i]]
+
+    def computeConstraintsMatrixAndBounds(self, qpInput):  # :434-456
+        self.linearMatrix[:] = 0
+        self.lowerBound[:] = 0
+        self.upperBound[:] = 0
+        nJ = self.nJoints
+        base = self.nStates * (self.nIter + 1)
+        qcmd = np.asarray(qpInput.getOutputQPJointsPosition(), float)[self.sel]
+        for i in range(self.ctrlHorizon):
+            self.linearMatrix[i * nJ:(i + 1) * nJ, base + i * nJ: base + (i + 1) * nJ] = np.eye(nJ)
+            self.lowerBound[i * nJ:(i + 1) * nJ] = self.jointPositionMin - qcmd
+            self.upperBound[i * nJ:(i + 1) * nJ] = self.jointPositionMax - qcmd
+        return True
+
+
 # =================================================================================================
 #  Exact QP solve: the arbiter at "matched KKT tolerance" (SURVEY §8c).
 # =================================================================================================
@@ -1140,6 +1185,9 @@ class VariableSamplingMPC(IMPCProblem):
         self.vectorConstraints = [ConstraintSystemDynamicVS(nV, nS, nJ, nT, self.nIter),
                                   ConstraintInitialState(nS, nV),
                                   ThrottleConstraint(nV, nS, self.nIter, self.nIterSmall)]
+        if p.get("jointPos_max") is not None and p.get("jointPos_min") is not None:
+            # optional extension (not in the shipped problem): per-block joint-limit rows, see JointPositionConstraint
+            self.vectorConstraints.append(JointPositionConstraint(nV, nS, nJ, self.nIter))
         return True
 
     def solveMPC(self):  # :88-112

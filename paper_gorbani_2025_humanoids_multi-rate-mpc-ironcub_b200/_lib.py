@@ -41,6 +41,7 @@ class VsmpcConfig(C.Structure):
         ("position_com", c_double_p), ("velocity_com", c_double_p), ("rpy", c_double_p),
         ("rpy_dot", c_double_p), ("traj_len", C.c_int), ("traj_fps", C.c_int),
         ("solver", C.c_int),
+        ("use_joint_limits", C.c_int), ("joint_pos_min_deg", C.c_double * 8), ("joint_pos_max_deg", C.c_double * 8),
     ]
 
 
@@ -75,7 +76,7 @@ EXPORTS = [
     "vsmpc_multi_shard", "vsmpc_multi_configure", "vsmpc_multi_set_instance_params", "vsmpc_multi_set_state", "vsmpc_multi_solve",
     "vsmpc_multi_solve_async", "vsmpc_multi_wait", "vsmpc_multi_get_output", "vsmpc_multi_set_full_solution",
     "vsmpc_multi_get_full_solution",
-    "vsmpc_set_instance_params", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
+    "vsmpc_set_instance_params", "vsmpc_set_joint_limits", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
 ]
 
 _lib = None
@@ -123,6 +124,7 @@ def load() -> C.CDLL:
     lib.vsmpc_debug_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]
     lib.vsmpc_set_instance_params.argtypes = [H, C.c_void_p]
+    lib.vsmpc_set_joint_limits.argtypes = [H, C.c_void_p, C.c_void_p]
     lib.vsmpc_rollout_init.argtypes = [H, C.POINTER(VsmpcPlantModel), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.vsmpc_rollout_run.argtypes = [H, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.vsmpc_rollout_get_state.argtypes = [H, C.c_void_p]

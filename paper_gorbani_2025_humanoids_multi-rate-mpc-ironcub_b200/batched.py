@@ -67,6 +67,17 @@ def _cfg_struct(params: dict, traj: dict, solver: int, keep: list) -> L.VsmpcCon
         raise VsmpcError("trajectory arrays differ in length")
     c.traj_len, c.traj_fps = n, int(traj["traj_fps"])
     c.solver = int(solver)
+    # optional joint-limit rows (JointPositionConstraint, constraintsVSMPC.cpp:388-468; parameters jointPos_max / jointPos_min
+    # in degrees, :421-423 — absent from the shipped XML, hence off by default)
+    jmax, jmin = p.get("jointPos_max"), p.get("jointPos_min")
+    if (jmax is None) != (jmin is None):
+        raise VsmpcError("Parameters 'jointPos_max' and 'jointPos_min' go together")
+    if jmax is not None:
+        if len(jmax) != 8 or len(jmin) != 8:
+            raise VsmpcError("The size of the vector containing the joint position limits is not correct.")
+        c.use_joint_limits = 1
+        c.joint_pos_min_deg = (C.c_double * 8)(*[float(x) for x in jmin])
+        c.joint_pos_max_deg = (C.c_double * 8)(*[float(x) for x in jmax])
     return c
 
 
@@ -136,6 +147,16 @@ class BatchedVSMPC:
         ip[L.IP_THROTTLE_MAX] = self.params["throttleMax"] if throttle_max is None else self._f64(throttle_max, (B,))
         ip = np.ascontiguousarray(ip)
         self._ck(self._lib.vsmpc_set_instance_params(self._h, ip.ctypes.data), "vsmpc_set_instance_params")
+
+    def set_joint_limits(self, q_min=None, q_max=None):
+        """Per-instance joint limits [rad] of the controlled joints, (B, 8) each — configs[4] "per-instance constraint
+        sets"; needs jointPos_max / jointPos_min in the parameters.  ``None, None``: back to the handle-wide limits."""
+        if q_min is None and q_max is None:
+            self._ck(self._lib.vsmpc_set_joint_limits(self._h, None, None), "vsmpc_set_joint_limits")
+            return
+        lo = np.ascontiguousarray(self._f64(q_min, (self.B, 8)).T)
+        hi = np.ascontiguousarray(self._f64(q_max, (self.B, 8)).T)
+        self._ck(self._lib.vsmpc_set_joint_limits(self._h, lo.ctypes.data, hi.ctypes.data), "vsmpc_set_joint_limits")
 
     # ---- reference surface -------------------------------------------------------------------------
     def configure_pack(self, pack: np.ndarray, joint_pos_sel: np.ndarray, phase0=None) -> bool:

@@ -26,7 +26,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
                              const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
-                             int* fb_count, cudaStream_t s);
+                             int* fb_count, const double* jl, cudaStream_t s);
 bool fallback_supported(const DeviceConfig& cfg);
 size_t fallback_slot_doubles(const DeviceConfig& cfg);
 size_t fallback_pos_ints(const DeviceConfig& cfg);
@@ -126,6 +126,8 @@ struct vsmpc_handle
     bool use_nn = false;
     double* d_ip = nullptr;   // per-instance jet model / throttle limits (optional)
     bool use_ip = false;
+    double* d_jl = nullptr;   // per-instance joint limits [rad], SoA double[16][B]: 8 lower rows, 8 upper rows (optional)
+    bool use_jl_table = false;
     bool rollout_ready = false;
     cudaGraphExec_t tick_graph = nullptr;
     std::string err;
@@ -269,6 +271,18 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     g.ratio = (int)std::lround(c->period_large / c->period_small);    // costsVSMPC.cpp:69
     g.use_jet_dynamic = c->use_jet_dynamic;
     g.use_estimated_thrust = c->use_estimated_thrust;
+    g.use_jl = c->use_joint_limits ? 1 : 0;
+    if (g.use_jl)
+    { // JointPositionConstraint (optional rows): nJoints * nIter rows after the throttle rows, constraintsVSMPC.cpp:391
+        g.n_con += NJ * g.N;
+        for (int a = 0; a < NJ; ++a)
+        {
+            g.jl_min[a] = c->joint_pos_min_deg[a] * M_PI / 180.0;    // :421-423
+            g.jl_max[a] = c->joint_pos_max_deg[a] * M_PI / 180.0;
+            if (!(g.jl_min[a] < g.jl_max[a]))
+                return bail(VSMPC_ERR_ARG, "joint limits: need jointPos_min < jointPos_max for every controlled joint");
+        }
+    }
     g.qd_stride = (QD_XREF + 12 * g.NC + 3) & ~3;
     g.st_rows = ST_WIN + 12 * g.NC;
     for (int i = 0; i < NX; ++i)
@@ -333,6 +347,8 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         return bail(VSMPC_ERR_UNSUPPORTED, "horizons with more than 48 throttle blocks are not supported");
     if (h->solver == 2 && (NT * g.nblk > 24 || g.N > 32))
         return bail(VSMPC_ERR_UNSUPPORTED, "the structured one-warp kernel covers horizons with <= 6 throttle blocks and <= 32 knots");
+    if (g.use_jl && !((h->solver == 0 || h->solver == SOLVER_WIDE) && fallback_supported(g)))
+        return bail(VSMPC_ERR_UNSUPPORTED, "joint-limit rows need the default solver on a horizon the fallback kernel covers");
     const int B = n_instances;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess)
@@ -439,7 +455,7 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip,
+                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl,
                     h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -489,7 +505,7 @@ static int run_linearise(vsmpc_handle* h, int mode)
 {
     CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
                         h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd,
-                        h->use_ip ? h->d_ip : nullptr, h->d_fb_count, h->stream));
+                        h->use_ip ? h->d_ip : nullptr, h->d_fb_count, h->use_jl_table ? h->d_jl : nullptr, h->stream));
     return VSMPC_OK;
 }
 
@@ -551,6 +567,34 @@ int vsmpc_set_instance_params(vsmpc_handle* h, const double* ip_host)
     CK(cudaMemcpyAsync(h->d_ip, ip_host, (size_t)IP_ROWS * B * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->use_ip = true;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const double* q_max_host)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    if (!h->cfg.use_jl)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_set_joint_limits: the handle was created without use_joint_limits");
+    CK(cudaSetDevice(h->device));
+    drop_tick_graph(h);
+    if (!q_min_host && !q_max_host)
+    {
+        h->use_jl_table = false;
+        return VSMPC_OK;
+    }
+    if (!q_min_host || !q_max_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_set_joint_limits: give both tables or neither");
+    const size_t n = (size_t)NJ * h->B;
+    for (size_t e = 0; e < n; ++e)
+        if (!(q_min_host[e] < q_max_host[e]))
+            return fail(h, VSMPC_ERR_ARG, "vsmpc_set_joint_limits: need q_min < q_max for every joint of every instance");
+    if (!h->d_jl)
+        CK(dalloc(&h->d_jl, 2 * n));
+    CK(cudaMemcpyAsync(h->d_jl, q_min_host, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_jl + n, q_max_host, n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->use_jl_table = true;
     return VSMPC_OK;
 }
 

@@ -47,7 +47,10 @@ constexpr int QD_JGT = 160;   // 1   B_T[T_i, i]  (0 with jet dynamics, 1 withou
 constexpr int QD_JC12 = 161;  // 1   jet coefficient c12 of this instance   } throttle de-standardisation
 constexpr int QD_UMEAN = 162; // 1   throttle mean                           } (JetModel.cpp:93-109) in the
 constexpr int QD_USTD = 163;  // 1   throttle standard deviation             } epilogue of the QP kernels
-constexpr int QD_XREF = 164;  // 12*NC  rows: pos(3) linMom(3) rpy(3) angMom(3); NC reference columns each
+constexpr int QD_JLIM = 164;  // 1   1.0 when the joint-limit rows are on (optional extension, constraintsVSMPC.cpp:388-468)
+constexpr int QD_JLO = 165;   // 8   jointPos_min - q_cmd   (lower bound of every dq block, :450-451)
+constexpr int QD_JHI = 173;   // 8   jointPos_max - q_cmd   (:452-453)
+constexpr int QD_XREF = 184;  // 12*NC  rows: pos(3) linMom(3) rpy(3) angMom(3); NC reference columns each
 
 // ---- per-instance persistent state (SoA, row = scalar, column = instance) ------------------------
 constexpr int ST_P_INIT = 0;    // 3  ReferenceTrackingCost::m_initialCoMPos
@@ -82,6 +85,7 @@ struct DeviceConfig
     int n_var, n_con;
     int ratio;         // round(periodLarge / periodSmall)
     int use_jet_dynamic, use_estimated_thrust;
+    int use_jl;        // joint-limit rows on (JointPositionConstraint, optional)
     int qd_stride, st_rows;
     int alpha_len, traj_len;
     double Qd[NX];
@@ -91,6 +95,7 @@ struct DeviceConfig
     double throttle_min, throttle_max;
     double jc[13];
     double jn[4];
+    double jl_min[NJ], jl_max[NJ];   // handle-wide joint limits [rad]
     double dt[MAX_ITER];
 };
 

@@ -389,12 +389,17 @@ __device__ __forceinline__ void cd_schedule(int t, int N, int kS, int& ta, int& 
 
 // warp A: forward rollout with the stored gains (u_k = -K_k x - F_k theta*), outputs (variableSamplingMPC.cpp:88-112)
 // and, with z != nullptr, the full primal.  xs: 40 doubles of shared memory (x, throttle block in effect, dq in effect);
-// fth: F_k theta* [Nc][8]; theta: throttle variables (4 nblk); stage: doubles per elimination knot in ws (K first)
+// fth: F_k theta* [Nc][8]; theta: throttle variables (4 nblk); stage: doubles per elimination knot in ws (K first);
+// ostage: 48 doubles of shared memory — the outputs are staged there and committed at the end, because with the optional
+// joint-limit rows on (jl != nullptr: QD_JLO / QD_JHI of this instance) a joint increment outside its box means that the
+// minimiser of the problem WITHOUT those rows is not the answer: nothing is committed, the function returns true and the
+// caller hands the instance to the fallback kernel, which carries the joint boxes in its active set.
 template <class SM>
-__device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, const double* __restrict__ ws, int stage,
+__device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, const double* __restrict__ ws, int stage,
                                            const double* __restrict__ theta, const double* __restrict__ fth,
                                            double* __restrict__ xs, int lane, int B, int inst, double* __restrict__ z,
-                                           double* __restrict__ o, double* __restrict__ st)
+                                           double* __restrict__ o, double* __restrict__ st, double* __restrict__ ostage,
+                                           const double* __restrict__ jl)
 {
     const int N = cfg.N, Nc = cfg.Nc, nv = 4 * cfg.nblk;
     CdFwdTab tab;
@@ -410,6 +415,8 @@ __device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, cons
     __syncwarp();
     const int ka = lane & 7, kq = lane >> 3;   // gain row / quarter of the state handled by this lane
     const int j0 = kq * 7, jn = kq == 3 ? 5 : 7;
+    const double jlo = jl ? jl[ka] - 1e-9 : -INFINITY, jhi = jl ? jl[NJ + ka] + 1e-9 : INFINITY;
+    bool viol = false;
     // gain rows are prefetched one knot ahead (their addresses do not depend on the state) into the register set the
     // other knot parity uses, so that no instruction of knot k waits for the loads of knot k+1
     double kA[7], kB[7];
@@ -446,11 +453,12 @@ __device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, cons
             part += __shfl_xor_sync(0xffffffffu, part, 8);
             part += __shfl_xor_sync(0xffffffffu, part, 16);
             const double u = -part - fth[k * NJ + ka];
+            viol = viol || !(u >= jlo && u <= jhi);
             if (lane < NJ)
             {
                 dqs[lane] = u;
                 if (k == 0)
-                    o[VSMPC_OUT_DELTA_Q + lane] = u;
+                    ostage[VSMPC_OUT_DELTA_Q + lane] = u;
                 if (z)
                     z[NX * (N + 1) + k * NJ + lane] = u;
             }
@@ -471,9 +479,9 @@ __device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, cons
         if (lane < NX)
             xs[lane] = x;
         if (k == 0 && lane >= IX_T && lane < IX_EP)
-            o[(lane < IX_TD ? VSMPC_OUT_THRUST - IX_T : VSMPC_OUT_THRUST_DOT - IX_TD) + lane] = x;
+            ostage[(lane < IX_TD ? VSMPC_OUT_THRUST - IX_T : VSMPC_OUT_THRUST_DOT - IX_TD) + lane] = x;
         if (k == N - 1 && lane < NX)
-            o[VSMPC_OUT_FINAL_STATE + lane] = x;
+            ostage[VSMPC_OUT_FINAL_STATE + lane] = x;
         if (z && lane < NX)
             z[(k + 1) * NX + lane] = x;
         __syncwarp();
@@ -485,12 +493,18 @@ __device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, cons
         if (k + 1 < N)
             knot(k + 1, kB, kA);
     }
-    // remaining outputs (variableSamplingMPC.cpp:96-108,138-151)
+    if (__any_sync(0xffffffffu, viol))
+        return true;     // a joint increment left its box: nothing committed (z holds the unconstrained minimiser)
+    // remaining outputs (variableSamplingMPC.cpp:96-108,138-151), then the commit of the staged ones
+    __syncwarp();
+    for (int e = lane; e < VSMPC_OUT_JOINTS_REF; e += 32)
+        if (e < VSMPC_OUT_THROTTLE || e >= VSMPC_OUT_THRUST)
+            o[e] = ostage[e];
     if (lane < NT)
         o[VSMPC_OUT_THROTTLE + lane] = destd_throttle_qd(sm.cf, theta[lane]);
     if (lane < NJ)
     {
-        const double dq = o[VSMPC_OUT_DELTA_Q + lane];
+        const double dq = ostage[VSMPC_OUT_DELTA_Q + lane];
         const double acc = st[(size_t)(ST_QACC + lane) * B + inst] + dq;
         st[(size_t)(ST_QACC + lane) * B + inst] = acc;
         o[VSMPC_OUT_JOINTS_REF + lane] = acc;
@@ -501,6 +515,7 @@ __device__ __forceinline__ void cd_forward(const DeviceConfig& cfg, SM& sm, cons
         for (int e = lane; e < nv; e += 32)
             z[base + e] = theta[e];
     }
+    return false;
 }
 
 } // namespace vsmpc

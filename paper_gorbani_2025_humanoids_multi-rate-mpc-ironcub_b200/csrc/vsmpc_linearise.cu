@@ -173,7 +173,7 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
                  const double* __restrict__ alpha_traj, const double* __restrict__ traj_pos,
                  const double* __restrict__ traj_vel, const double* __restrict__ traj_rpy,
                  const double* __restrict__ traj_rpyd, double* __restrict__ qd, const double* __restrict__ ip,
-                 int* __restrict__ fb_count)
+                 int* __restrict__ fb_count, const double* __restrict__ jl)
 {
     extern __shared__ double k1_smem[]; // per warp: pk[360] | out[qd_stride] | col[12] | ipar[20] | stc[st_rows] | sic[4]
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank): no global round trip for the configuration
@@ -258,6 +258,10 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
         st[(size_t)(f) * Bs + i] = v__;   \
     } while (0)
 #define SI(f) si[(size_t)(f) * Bs + i]
+    // joint limits of this instance (optional rows): lanes 0-7 lower, 8-15 upper; consumed at the end of the tick
+    double jl_v = 0.0;
+    if (cfg.use_jl && lane < 2 * NJ)
+        jl_v = jl ? jl[(size_t)lane * Bs + i] : (lane < NJ ? cfg.jl_min[lane] : cfg.jl_max[lane - NJ]);
     if (!ip && lane < IP_ROWS)
         ipar[lane] = lane < IP_JN ? cfg.jc[lane] : (lane < IP_TMIN ? cfg.jn[lane - IP_JN] : (lane == IP_TMIN ? cfg.throttle_min : cfg.throttle_max));
     __syncwarp();
@@ -432,6 +436,13 @@ linearise_kernel(const __grid_constant__ DeviceConfig cfgv, int B, int mode,
         out[QD_VBAR + lane] = jet.v(jet.stdU(pk[VSMPC_PK_THROTTLE_PREV + lane]));
     if (lane < NJ) // JointPositionRegularizationCost gradient, costsVSMPC.cpp:574-590
         out[QD_GQ + lane] = cfg.w_reg_q * (pk[VSMPC_PK_Q_CMD + lane] - STR(ST_QREF0 + lane));
+    // JointPositionConstraint bounds (optional rows, constraintsVSMPC.cpp:450-453): limits - q_cmd, the same for every block
+    if (lane < 2 * NJ)
+        out[QD_JLO + lane] = cfg.use_jl ? jl_v - pk[VSMPC_PK_Q_CMD + (lane & (NJ - 1))] : 0.0;
+    if (lane == 2 * NJ)
+        out[QD_JLIM] = cfg.use_jl ? 1.0 : 0.0;
+    if (lane > 2 * NJ && lane < 2 * NJ + 4)
+        out[QD_JLIM + 2 * NJ + (lane - 2 * NJ)] = 0.0;   // padding up to QD_XREF
     // ---------------- dynamics ---------------------------------------------------------------------------
     const double t1 = s1 / c1;
     if (lane == 0)
@@ -674,6 +685,16 @@ __global__ void expand_qp_vectors_kernel(const DeviceConfig* __restrict__ cfgp, 
                 ui[t0 + b * NT + a] = d[QD_VMAX];
             }
         }
+    if (cfg.use_jl)
+    { // JointPositionConstraint rows (optional), after the NT (N - Ns + 1) throttle rows: blocks 0 .. Nc-1, the rest zero
+        const int j0 = t0 + NT * (N - cfg.Ns + 1);
+        for (int b = 0; b < cfg.Nc; ++b)
+            for (int a = 0; a < NJ; ++a)
+            {
+                li[j0 + b * NJ + a] = d[QD_JLO + a];
+                ui[j0 + b * NJ + a] = d[QD_JHI + a];
+            }
+    }
 }
 
 // IMPCProblem::getHessian (IMPCProblem.h:88) of ONE instance, dense n_var x n_var row-major: the constant cost
@@ -743,6 +764,9 @@ __global__ void expand_constraint_matrix_kernel(const DeviceConfig* __restrict__
         const int e = r - NX * N - NX;
         if (e < NT * cfg.nblk)
             row[nxs + njs + e] = 1.0;
+        const int ej = e - NT * (N - cfg.Ns + 1);       // joint-limit rows (optional): identity on dq blocks 0 .. Nc-1
+        if (cfg.use_jl && ej >= 0 && ej < NJ * cfg.Nc)
+            row[nxs + ej] = 1.0;
     }
 }
 
@@ -751,7 +775,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
                              const double* pack, const double* joint_pos_sel, const int* phase0, double* st,
                              int* si, const double* alpha_traj, const double* traj_pos, const double* traj_vel,
                              const double* traj_rpy, const double* traj_rpyd, double* qd, const double* ip,
-                             int* fb_count, cudaStream_t s)
+                             int* fb_count, const double* jl, cudaStream_t s)
 {
     const size_t smem = (size_t)K1_WARPS * k1_per_warp(h_cfg) * sizeof(double);
     static bool attr_set[64] = {};
@@ -764,7 +788,7 @@ cudaError_t launch_linearise(const DeviceConfig* d_cfg, const DeviceConfig& h_cf
     }
     const int grid = (B + K1_WARPS - 1) / K1_WARPS;
     linearise_kernel<<<grid, 32 * K1_WARPS, smem, s>>>(h_cfg, B, mode, pack, joint_pos_sel, phase0, st, si,
-                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip, fb_count);
+                                                       alpha_traj, traj_pos, traj_vel, traj_rpy, traj_rpyd, qd, ip, fb_count, jl);
     return cudaGetLastError();
 }
 

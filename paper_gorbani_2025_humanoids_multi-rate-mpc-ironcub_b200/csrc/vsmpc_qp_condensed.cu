@@ -742,7 +742,16 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     }
     if (!solved)
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
-    cd_forward(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st);
+    const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
+    if (cd_forward(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl) && lane == 0)
+    {
+        // a joint box is active at the minimiser: the fallback kernel solves the problem with the joint boxes in its active
+        // set; until then the outputs are held
+        status[inst] = VSMPC_STATUS_NUMERICAL;
+        n_solve[inst] = 0;
+        if (fb_mode != 0)
+            fb_list[atomicAdd(fb_count, 1)] = inst;
+    }
     PHASE_CLK(3);
 }
 

@@ -41,6 +41,7 @@ struct alignas(16) CwSmem
     CdSlot slot[2];                   // warp 0 -> column warps mailbox, slot = knot & 1
     alignas(16) double Mt[NX * LDM];  // warp 0: transposition buffer, gain rows of the knot in flight
     double xs[40];                    // forward rollout: x (26), throttle block in effect (4), dq in effect (8)
+    double ostage[48];                // outputs staged until the forward rollout has checked the optional joint boxes
     int flags[4];
 };
 
@@ -859,7 +860,14 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     }
     if (stat != VSMPC_STATUS_SOLVED)
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
-    cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st);
+    const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
+    if (cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st, sm.ostage, jl) && lane == 0)
+    {
+        status[inst] = VSMPC_STATUS_NUMERICAL;       // see vsmpc_qp_condensed.cu: a joint box is active, fallback kernel
+        n_solve[inst] = 0;
+        if (fb_mode != 0)
+            fb_list[atomicAdd(fb_count, 1)] = inst;
+    }
     WCLK(7);
 }
 

@@ -35,6 +35,7 @@ constexpr int FB_MAXROWS = 160;   // band window + border rows eliminated per co
 struct FbLayout
 {
     int n, nb, bw, nv, ld;        // unknowns, band part, half bandwidth, throttle variables, leading dimension of [K | R]
+    int nq, nbox;                 // joint-increment variables; boxed variables at most (nv, + nq with the joint-limit rows)
     int o_x, o_dq, o_v, o_nu, o_mu, o_pin, n_pos;   // offsets into the position table
 };
 
@@ -86,7 +87,9 @@ static void fb_host_layout(const DeviceConfig& g, FbLayout& L, std::vector<int>&
         pos[L.o_pin + a] = o++;
     L.n = o;
     L.nv = NT * nblk;
-    L.ld = (L.n + 1 + L.nv + 3) & ~3;
+    L.nq = NJ * Nc;
+    L.nbox = L.nv + (g.use_jl ? L.nq : 0);
+    L.ld = (L.n + 1 + L.nbox + 3) & ~3;
     // half bandwidth of the band part: a dynamics row of knot k reaches from x_k to x_{k+1} (and the in-stage inputs)
     int bw = 0;
     for (int k = 0; k < N; ++k)
@@ -120,7 +123,7 @@ __device__ __forceinline__ void fb_set(double* __restrict__ M, int ld, int r, in
     M[(size_t)c * ld + r] = v;
 }
 
-// per-slot scratch: M [n][ld] | T [nv][nv] | zs [n]
+// per-slot scratch: M [n][ld] | T [nbox][nbox] | zs [n]
 __global__ void __launch_bounds__(FB_THREADS)
 qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, int B, const double* __restrict__ qd_all,
                    const int* __restrict__ fb_list, const int* __restrict__ fb_count, const int* __restrict__ pos,
@@ -131,6 +134,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
     const DeviceConfig& cfg = cfgv;
     __shared__ double A[NX * NX], BJ[NX * NJ], BT[NX * NT], cv[NX];
     __shared__ double prow[FB_MAXROWS * 3 + 256];   // pivot row cache: band window (<= 2 bw + 1) + border + right-hand sides
+    __shared__ double vbuf[FB_THREADS], cbuf[FB_THREADS], rbuf[FB_THREADS];   // active set: one boxed variable per thread
     __shared__ double lmul[FB_MAXROWS];
     __shared__ int lrow[FB_MAXROWS];
     __shared__ double red_v[FB_THREADS / 32];
@@ -141,7 +145,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
     const int n = L.n, nb = L.nb, bw = L.bw, ld = L.ld, N = cfg.N, Nc = cfg.Nc, nblk = cfg.nblk;
     double* M = scratch + (size_t)blockIdx.x * slot_doubles;
     double* T = M + (size_t)n * ld;
-    double* zs = T + (size_t)L.nv * L.nv;
+    double* zs = T + (size_t)L.nbox * L.nbox;
     const int* px = pos + L.o_x;
     const int* pq = pos + L.o_dq;
     const int* pv = pos + L.o_v;
@@ -155,7 +159,11 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
         const double* qd = qd_all + (size_t)inst * cfg.qd_stride;
         const bool pinned = qd[QD_PINNED] != 0.0;
         const int first = pinned ? NT : 0;
-        const int nvf = L.nv - first, nrhs = 1 + nvf;
+        const int nvf = L.nv - first;
+        // boxed variables: the free throttle variables and, with the optional joint-limit rows on, every joint increment
+        // (box e < nqb: joint variable e, bounds QD_JLO / QD_JHI; else throttle variable first + e - nqb)
+        const int nqb = (cfg.use_jl && qd[QD_JLIM] != 0.0) ? L.nq : 0;
+        const int nbx = nqb + nvf, nrhs = 1 + nbx;
         const int ncol = n + nrhs;             // columns in use (<= ld)
         if (tid == 0)
             expand_dense(qd, A, BJ, BT, cv);
@@ -189,6 +197,8 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
             const int p = pq[e];
             M[(size_t)p * ld + p] = cfg.Rqd[e % NJ];
             M[(size_t)p * ld + n] = -qd[QD_GQ + e % NJ];
+            if (nqb)
+                M[(size_t)p * ld + n + 1 + e] = 1.0;                 // unit right-hand side of joint variable e
         }
         for (int e = tid; e < L.nv; e += FB_THREADS)
         {
@@ -201,7 +211,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
             if (b == 0)
                 M[(size_t)p * ld + n] = cfg.w_i * qd[QD_VBAR + e];
             if (e >= first)
-                M[(size_t)p * ld + n + 1 + (e - first)] = 1.0;      // unit right-hand side of throttle variable e
+                M[(size_t)p * ld + n + 1 + nqb + (e - first)] = 1.0;   // unit right-hand side of throttle variable e
         }
         for (int e = tid; e < N * NX; e += FB_THREADS)
         { // dynamics rows: T x_k - x_{k+1} + dt B_J dq + dt B_T v = -dt c
@@ -352,20 +362,22 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
         }
         __syncthreads();
         // ---- dual active set on T = (K^-1)_vv (tools/condensed_model._dual_pivot_loop), one variable per thread ----------
-        const double lo = qd[QD_VMIN], up = qd[QD_VMAX];
         const double tol = 1e-10;
-        for (int e = tid; e < nvf * nvf; e += FB_THREADS)
+        const bool isvar = tid < nbx;
+        const int pos_e = isvar ? (tid < nqb ? pq[tid] : pv[first + tid - nqb]) : 0;     // KKT position of this thread's variable
+        const double lo = !isvar ? 0.0 : (tid < nqb ? qd[QD_JLO + tid % NJ] : qd[QD_VMIN]);
+        const double up = !isvar ? 0.0 : (tid < nqb ? qd[QD_JHI + tid % NJ] : qd[QD_VMAX]);
+        if (isvar)
+            vbuf[tid] = (double)pos_e;
+        __syncthreads();
+        for (int e = tid; e < nbx * nbx; e += FB_THREADS)
         {
-            const int i = e / nvf, j = e - i * nvf;
-            T[e] = 0.5 * (M[(size_t)pv[first + i] * ld + n + 1 + j] + M[(size_t)pv[first + j] * ld + n + 1 + i]);
+            const int i = e / nbx, j = e - i * nbx;
+            T[e] = 0.5 * (M[(size_t)(int)vbuf[i] * ld + n + 1 + j] + M[(size_t)(int)vbuf[j] * ld + n + 1 + i]);
         }
-        const bool isvar = tid < nvf;
-        double v_e = isvar ? M[(size_t)pv[first + tid] * ld + n] : 0.0;
+        double v_e = isvar ? M[(size_t)pos_e * ld + n] : 0.0;
         double lam_e = 0.0;
         int act = 0, iters = 0, stat = VSMPC_STATUS_SOLVED;
-        double* vbuf = prow;                  // nvf values
-        double* cbuf = prow + FB_MAXROWS;     // column p of T
-        double* rbuf = prow + 2 * FB_MAXROWS; // row p of T
         __syncthreads();
         auto block_best = [&](double v, bool want_max, int& arg_out) -> double {
             // exact block-wide max / min with the lowest thread attaining it
@@ -391,19 +403,19 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
         auto pivot = [&](int q) -> bool {
             // exchange pivot on q: T' = T - u v'/d off row / column q, T'[q,:] = -v/d, T'[:,q] = u/d, T'[q,q] = 1/d
             __syncthreads();
-            if (tid < nvf)
+            if (tid < nbx)
             {
-                cbuf[tid] = T[tid * nvf + q];
-                rbuf[tid] = T[q * nvf + tid];
+                cbuf[tid] = T[tid * nbx + q];
+                rbuf[tid] = T[q * nbx + tid];
             }
             __syncthreads();
             const double d = rbuf[q];
             if (!(d > 0.0) || !isfinite(d))
                 return false;
             const double id = 1.0 / d;
-            for (int e = tid; e < nvf * nvf; e += FB_THREADS)
+            for (int e = tid; e < nbx * nbx; e += FB_THREADS)
             {
-                const int i = e / nvf, j = e - i * nvf;
+                const int i = e / nbx, j = e - i * nbx;
                 double t;
                 if (i == q)
                     t = j == q ? id : -rbuf[j] * id;
@@ -417,29 +429,31 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
             return true;
         };
         bool fail = false;
-        while (!fail && nvf > 0)
+        while (!fail && nbx > 0)
         {
             int p;
             const double best = block_best((isvar && act == 0) ? fmax(fmax(v_e - up, lo - v_e), 0.0) : 0.0, true, p);
             if (!(best > tol))
                 break;
             if (tid == p)
-                s_val[0] = v_e;
+            { // sign and bound of the violated variable (its own box)
+                s_val[0] = (v_e - up > lo - v_e) ? 1.0 : -1.0;
+                s_val[2] = (v_e - up > lo - v_e) ? up : lo;
+            }
             __syncthreads();
-            const double v_p0 = s_val[0];
-            const double s = (v_p0 - up > lo - v_p0) ? 1.0 : -1.0;
-            const double bound = s > 0 ? up : lo;
+            const double s = s_val[0];
+            const double bound = s_val[2];
             double lam_p = 0.0;
             while (true)
             {
-                if (++iters > 6 * L.nv + 64)
+                if (++iters > 6 * L.nbox + 64)
                 {
                     stat = VSMPC_STATUS_MAX_ITER;
                     fail = true;
                     break;
                 }
-                const double c_e = isvar ? T[tid * nvf + p] : 0.0;
-                const double zp = T[p * nvf + p];
+                const double c_e = isvar ? T[tid * nbx + p] : 0.0;
+                const double zp = T[p * nbx + p];
                 const double r_e = act != 0 ? -(double)act * s * c_e : 0.0;
                 int drop;
                 const double t1 = block_best((act != 0 && r_e > 0.0) ? fmax(lam_e, 0.0) / r_e : INFINITY, false, drop);
@@ -491,6 +505,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
         }
         // ---- z = z_unc - sum_a s_a lam_a K^-1 e_a; active variables exactly on their bound ----------------------------------
         __syncthreads();
+        __syncthreads();
         if (isvar)
             vbuf[tid] = act != 0 ? (double)act * lam_e : 0.0;
         __syncthreads();
@@ -499,7 +514,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
         {
             const double* row = M + (size_t)r * ld + n;
             double z = row[0];
-            for (int a = 0; a < nvf; ++a)
+            for (int a = 0; a < nbx; ++a)
             {
                 const double w = vbuf[a];
                 if (w != 0.0)
@@ -508,8 +523,9 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
             zs[r] = z;
             fin = fin && isfinite(z);
         }
+        __syncthreads();
         if (isvar && act != 0)
-            zs[pv[first + tid]] = act > 0 ? up : lo;
+            zs[pos_e] = act > 0 ? up : lo;
         const bool all_fin = __syncthreads_and(fin);
         if (!all_fin && stat == VSMPC_STATUS_SOLVED)
             stat = VSMPC_STATUS_NUMERICAL;
@@ -563,7 +579,7 @@ static FallbackPlan fb_plan(const DeviceConfig& cfg)
 {
     FallbackPlan P;
     fb_host_layout(cfg, P.L, P.pos);
-    P.slot_doubles = (size_t)P.L.n * P.L.ld + (size_t)P.L.nv * P.L.nv + P.L.n + 8;
+    P.slot_doubles = (size_t)P.L.n * P.L.ld + (size_t)P.L.nbox * P.L.nbox + P.L.n + 8;
     return P;
 }
 
@@ -571,8 +587,8 @@ bool fallback_supported(const DeviceConfig& cfg)
 {
     const FallbackPlan P = fb_plan(cfg);
     // the pivot-row cache and the per-thread active set bound the sizes (nv <= 160: up to 40 throttle blocks)
-    return P.L.nv <= FB_MAXROWS && P.L.bw + (P.L.n - P.L.nb) + 8 <= FB_MAXROWS
-           && 2 * P.L.bw + 1 + (P.L.n - P.L.nb) + 1 + P.L.nv <= FB_MAXROWS * 3 + 256 && P.L.nv <= FB_THREADS;
+    return P.L.bw + (P.L.n - P.L.nb) + 8 <= FB_MAXROWS
+           && 2 * P.L.bw + 1 + (P.L.n - P.L.nb) + 1 + P.L.nbox <= FB_MAXROWS * 3 + 256 && P.L.nbox <= FB_THREADS;
 }
 
 size_t fallback_slot_doubles(const DeviceConfig& cfg) { return fb_plan(cfg).slot_doubles; }

@@ -1,0 +1,156 @@
+"""Optional joint-limit rows (BASELINE configs[4] "per-instance constraint sets"; north_star: "... and joint limits").
+
+The reference carries a JointPositionConstraint (constraintsVSMPC.cpp:388-468) that the shipped problem never registers
+(variableSamplingMPC.cpp:77-84) and whose parameters jointPos_max / jointPos_min are absent from the XML.  Offered here as an
+extension: 8 * nIter rows after the throttle rows, block i < controlHorizon bounding dq_i by limits - q_cmd (:450-453) for
+every block (the m_firstIteriation slip of :440-449 is fixed, not ported).  The oracle registers the same class when the two
+parameters are given; the product solves instances whose unconstrained joint increments stay inside the box with the
+condensed kernels and hands the others to the KKT fallback kernel, whose active set then carries the joint boxes.
+  * CPU: the oracle's rows, bounds and minimiser (KKT certificate of the exact solver, boxes respected, bounds active);
+  * GPU: gradient / bounds / constraint matrix against the oracle's assembly, the minimiser and every output field per
+    physical quantity (1e-6 relative) on a workload where well over 10 % of the instances have an active joint bound,
+    handle-wide and per-instance limits, a 2x horizon (wide kernel hand-over), a closed tick sequence (accumulated q_cmd)."""
+import numpy as np
+import pytest
+
+from helpers import assert_output_rows_close, assert_solution_close, load_trajectories, pkg
+from oracle_driver import OracleInstance, oracle_trajectories_to_product
+
+# degrees, around the synthetic commanded posture (shoulder pitch / roll / yaw, elbow; left then right)
+JMIN = [-30.0, 5.0, 20.0, 5.0, -30.0, 5.0, 20.0, 5.0]
+JMAX = [-8.0, 30.0, 42.0, 28.0, -8.0, 30.0, 42.0, 28.0]
+LIMITS = dict(jointPos_min=JMIN, jointPos_max=JMAX)
+SEL = list(range(3, 11))
+
+
+def n_active_joint_bounds(z, lo, hi, N, Nc, tol=1e-9):
+    dq = z[26 * (N + 1):26 * (N + 1) + 8 * Nc].reshape(Nc, 8)
+    return int(((dq <= lo + tol) | (dq >= hi - tol)).sum())
+
+
+def test_oracle_joint_limit_rows_cpu():
+    syn = pkg("synthetic")
+    traj = load_trajectories()
+    nom = syn.make_states(2, perturbed=False)
+    per = syn.make_states(2, seed=5, perturbed=True, near_bound_fraction=0.3)
+    o = OracleInstance(nom, 0, params=LIMITS, trajectories=traj)
+    free = OracleInstance(nom, 0, trajectories=traj)
+    o.update(per)
+    free.update(per)
+    m = o.mpc
+    assert m.nConstraints == free.mpc.nConstraints + 8 * 17          # nJoints * nIter rows (:391)
+    z = o.solve()
+    zf = free.solve()
+    lo = np.radians(JMIN) - per["q_cmd"][0][SEL]
+    hi = np.radians(JMAX) - per["q_cmd"][0][SEL]
+    dq = z[26 * 18:26 * 18 + 96].reshape(12, 8)
+    assert (dq >= lo - 1e-9).all() and (dq <= hi + 1e-9).all()
+    assert n_active_joint_bounds(z, lo, hi, 17, 12) > 0
+    assert np.abs(z - zf).max() > 1e-3                               # the rows change the minimiser
+    # rows: identity on dq block i for i < controlHorizon, zero rows with zero bounds after (sized nIter blocks)
+    A = m.linearMatrix[-8 * 17:]
+    for i in range(17):
+        blk = A[8 * i:8 * i + 8]
+        if i < 12:
+            assert np.array_equal(blk[:, 26 * 18 + 8 * i:26 * 18 + 8 * i + 8], np.eye(8)) and np.count_nonzero(blk) == 8
+            assert np.allclose(m.lowerBound[-8 * 17:][8 * i:8 * i + 8], lo, atol=0, rtol=1e-15)
+        else:
+            assert np.count_nonzero(blk) == 0 and not m.lowerBound[-8 * 17:][8 * i:8 * i + 8].any()
+
+
+def _compare_tick(mpc, oracles, per, N, Nc, nblk, what):
+    mpc.update(per)
+    q, l, u = mpc.get_qp_vectors()
+    mpc.solveMPC()
+    z = mpc.getSolution()
+    out, status = mpc.get_output()
+    assert (status == 0).all(), (what, status)
+    n_act = 0
+    for i, o in enumerate(oracles):
+        o.update(per)
+        zo = o.solve()
+        m = o.mpc
+        assert np.abs(q[i] - m.gradient).max() <= 1e-12 * max(1.0, np.abs(m.gradient).max())
+        assert np.abs(l[i] - m.lowerBound).max() <= 1e-12 * max(1.0, np.abs(m.lowerBound).max()), what
+        assert np.abs(u[i] - m.upperBound).max() <= 1e-12 * max(1.0, np.abs(m.upperBound).max()), what
+        assert_solution_close(z[i], zo, 1e-6, N=N, Nc=Nc, nblk=nblk, what=(what, i))
+        assert_output_rows_close(out[i], o.output_row(), 1e-6, what=(what, i))
+        jl = m.vectorConstraints[3]
+        lo, hi = jl.lowerBound[:8], jl.upperBound[:8]
+        n_act += n_active_joint_bounds(zo, lo, hi, N, Nc) > 0
+    return n_act
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("horizon", [None, dict(nIter=34, nIterSmall=14, controlHorizon=24)])
+def test_joint_limit_rows_match_oracle(horizon):
+    B = 10
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = load_trajectories()
+    params = dict(LIMITS)
+    params.update(horizon or {})
+    nom = syn.make_states(B, perturbed=False)
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), full_solution=True)
+    mpc.configure(nom)
+    oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
+    p = oracles[0].params
+    N, Nc, nblk = p["nIter"], p["controlHorizon"], p["controlHorizon"] - p["nIterSmall"] + 1
+    assert mpc.n_con == oracles[0].mpc.nConstraints
+    total = 0
+    for tick in range(3):
+        per = syn.make_states(B, seed=90 + tick, perturbed=True, near_bound_fraction=0.3)
+        if tick == 2:
+            mpc.debug_set_counters(-1, oracles[0].mpc.vectorConstraints[2].ratio - 1)      # a released tick
+            for o in oracles:
+                o.mpc.vectorConstraints[2].counter = o.mpc.vectorConstraints[2].ratio - 1
+        total += _compare_tick(mpc, oracles, per, N, Nc, nblk, ("tick", tick))
+        if tick == 0:
+            A, Ao = mpc.getLinearConstraintMatrix(1), oracles[1].mpc.linearMatrix
+            assert np.array_equal(A != 0, Ao != 0) and np.abs(A - Ao).max() <= 1e-12 * np.abs(Ao).max()
+    assert total >= 0.1 * 3 * B, total       # well over 10 % of the solves have an active joint bound
+    mpc.close()
+
+
+@pytest.mark.gpu
+def test_per_instance_joint_limits_match_oracle():
+    """vsmpc_set_joint_limits: every instance its own box (some wide open, some tight around the commanded posture)."""
+    B = 12
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=17, perturbed=True, near_bound_fraction=0.3)
+    rng = np.random.default_rng(3)
+    width = np.where(np.arange(B)[:, None] % 3 == 0, 3.0, rng.uniform(0.02, 0.3, (B, 8)))   # rad; every third instance open
+    qc = nom["q_cmd"][:, SEL]
+    lo, hi = qc - width, qc + width * rng.uniform(0.5, 1.5, (B, 8))
+    mpc = bat.BatchedVSMPC(B, LIMITS, oracle_trajectories_to_product(traj), full_solution=True)
+    mpc.set_joint_limits(lo, hi)
+    mpc.configure(nom)
+    oracles = []
+    for i in range(B):
+        pi = dict(jointPos_min=list(np.degrees(lo[i])), jointPos_max=list(np.degrees(hi[i])))
+        oracles.append(OracleInstance(nom, i, params=pi, trajectories=traj))
+    n_act = _compare_tick(mpc, oracles, per, 17, 12, 6, "per-instance")
+    nf, _ = mpc.get_counts()
+    assert 2 <= n_act < B          # both routes in one batch: condensed kernel alone and the hand-over
+    assert (nf == 2).sum() >= n_act and (nf == 1).sum() >= 1
+    # back to the handle-wide limits
+    mpc.set_joint_limits(None, None)
+    oracles = [OracleInstance(nom, i, params=LIMITS, trajectories=traj) for i in range(B)]
+    mpc.configure(nom)
+    _compare_tick(mpc, oracles, per, 17, 12, 6, "handle-wide again")
+    mpc.close()
+
+
+@pytest.mark.gpu
+def test_joint_limits_need_the_flag_and_the_default_solver():
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = oracle_trajectories_to_product(load_trajectories())
+    with pytest.raises(bat.VsmpcError):
+        bat.BatchedVSMPC(2, LIMITS, traj, solver=2)
+    mpc = bat.BatchedVSMPC(2, None, traj)
+    with pytest.raises(bat.VsmpcError):
+        mpc.set_joint_limits(np.zeros((2, 8)) - 1, np.zeros((2, 8)) + 1)
+    mpc.close()
+    with pytest.raises(bat.VsmpcError):
+        bat.BatchedVSMPC(2, dict(jointPos_min=JMAX, jointPos_max=JMIN), traj)
