@@ -248,6 +248,12 @@ def run_ours(args):
     closed = None
     if rank == 0 and args.rollout_ticks > 0:
         closed = closed_loop_leg(bat, B, local_rank, stream, args.rollout_ticks, args.solver)
+    # ---------------- the other BASELINE configurations, every rank (skipped by --no-extras / --horizon) ------------
+    gather = long_h = monte = None
+    if not args.no_extras and not params:
+        gather = gather_leg(mpc, B, world, dev, stream, h_out, h_status)
+        long_h = long_horizon_leg(bat, lib, d_packs, nom_pack, jp, phase0, B, local_rank, stream, flush, world, dev, args.solver)
+        monte = monte_carlo_leg(bat, args.mc_instances, args.mc_ticks, rank, world, local_rank, stream, dev)
     # ---------------- reduce over ranks: max time --------------------------------------------------------
     t = torch.tensor([total_ms, e2e_s * 1e3, k1_ms, k2_ms, e2e_blocking_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -313,11 +319,163 @@ def run_ours(args):
         "gpu_launches": 2 * K,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "single_solve_latency": latency, "closed_loop": closed,
+        "monte_carlo": monte, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
         "solved_fraction": solved_frac, "wall_ms_timed_loop": t_wall * 1e3,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _max_over_ranks(values, world, dev):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def gather_leg(mpc, B, world, dev, stream, h_out, h_status, reps=20):
+    """Collecting the [B x 54] output rows (the only communication of the path): (a) NCCL all-gather
+    straight from the device-resident rows of every rank (vsmpc_get_output_device, no host round trip), (b) every rank
+    reading its own rows back into pinned host memory.  CUDA events / host clock, max over ranks."""
+    import torch
+    sh = pkg("sharding")
+    res = {"rows_per_rank": int(B), "row_bytes": 54 * 8 + 4, "reps": reps}
+    if world > 1:
+        for _ in range(3):
+            sh.gather_output_device(mpc, world * B)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            rows, st = sh.gather_output_device(mpc, world * B)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = _max_over_ranks([e0.elapsed_time(e1) / reps], world, dev)[0]
+        res["nccl_all_gather_ms"] = ms
+        res["nccl_all_gather_GBps_per_rank_in"] = (world - 1) * B * (54 * 8 + 4) / (ms * 1e-3) / 1e9
+        res["gathered_rows"] = int(rows.shape[0])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        mpc.get_output_into(h_out.data_ptr(), h_status.data_ptr())
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    res["pinned_d2h_ms"] = _max_over_ranks([ms], world, dev)[0]
+    res["what"] = ("nccl_all_gather_ms: all_gather_into_tensor of rows + status from the library's device buffers on "
+                   "every rank (world > 1 only); pinned_d2h_ms: vsmpc_get_output into pinned host memory per rank")
+    return res
+
+
+def long_horizon_leg(bat, lib, d_packs, nom_pack, jp, phase0, B, device, stream, flush, world, dev, solver, steps=10):
+    """BASELINE configs[3]: 2x / 3x / 4x the reference knot count (coarse tail), B instances per GPU on every rank (weak
+    scaling), same packs as the main leg (the pack does not depend on the horizon), CUDA events, L2 flushed."""
+    import torch
+    out = []
+    for hN, hNs, hNc in ((34, 14, 24), (51, 14, 36), (68, 14, 48)):
+        mpc = bat.BatchedVSMPC(B, dict(nIter=hN, nIterSmall=hNs, controlHorizon=hNc), load_traj(), device=device, solver=solver)
+        mpc.set_stream(stream.cuda_stream)
+        mpc.configure_pack(nom_pack, jp, phase0)
+        for j in range(3):
+            mpc.update_device_ptr(d_packs[j % len(d_packs)].data_ptr())
+            mpc.solve_async()
+        torch.cuda.synchronize()
+        ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
+        for j in range(steps):
+            flush.zero_()
+            e0, e1, e2 = ev[j]
+            e0.record(stream)
+            mpc.update_device_ptr(d_packs[j % len(d_packs)].data_ptr())
+            e1.record(stream)
+            mpc.solve_async()
+            e2.record(stream)
+        torch.cuda.synchronize()
+        tot = sum(a.elapsed_time(c) for a, _, c in ev)
+        k2 = sum(b.elapsed_time(c) for _, b, c in ev)
+        nf, ns = mpc.get_counts()
+        _, status = mpc.get_output()
+        tot, k2 = _max_over_ranks([tot, k2], world, dev)
+        F, _ = flops_per_solve(30, 12, hN, float(nf.mean()), float(ns.mean()))
+        out.append({"knots": hN, "fine_knots": hNs, "control_horizon": hNc, "n_var": mpc.n_var, "instances_per_gpu": int(B),
+                    "value": world * B * steps / (tot * 1e-3), "unit": "solves/s", "ms_per_step": tot / steps,
+                    "kernel_ms_per_launch": k2 / steps, "flops_per_solve": F, "steps": steps,
+                    "solved_fraction": float((status == 0).mean())})
+        mpc.close()
+    return out
+
+
+def finish_long_horizon(rows, peak_tflops):
+    if not rows:
+        return None
+    for r in rows:
+        ach = r["flops_per_solve"] * r["instances_per_gpu"] / (r["kernel_ms_per_launch"] * 1e-3) / 1e12
+        r["roofline_frac"] = ach / peak_tflops if peak_tflops > 0 else None
+    return {"scaling": "weak", "variants": rows,
+            "what": "configs[3]: qp_condensed_wide_kernel, same synthetic packs as the main leg, L2 flushed between steps"}
+
+
+def monte_carlo_leg(bat, n_total, ticks, rank, world, device, stream, dev):
+    """BASELINE configs[2] x configs[4]: a Monte Carlo closed-loop sweep of n_total instances IN TOTAL (contiguous
+    ranges over the ranks: strong scaling) over initial states, constant thrust disturbances and per-instance model
+    parameters (jet coefficients / normalisation, mass, inertia, throttle limits), `ticks` controller ticks each,
+    entirely on the device (surrogate plant); CUDA events, max over ranks."""
+    import torch
+    ro, syn, cfg, sh = pkg("rollout"), pkg("synthetic"), pkg("config"), pkg("sharding")
+    lo, hi = sh.shard_range(n_total, rank, world)
+    Bl = hi - lo
+    rb = syn.SyntheticRobot()
+    g = np.random.default_rng(20251002 + 7 * rank)
+    ms_, isc = g.uniform(0.9, 1.1, Bl), g.uniform(0.8, 1.2, Bl)
+    st = syn.make_states(Bl, seed=20251002 + 7 * rank, perturbed=True, near_bound_fraction=0.0, mass_scale=ms_, inertia_scale=isc)
+    st["thrust"] = (rb.mass * ms_ * 9.81 / 4.0)[:, None] + g.normal(0, 8.0, (Bl, 4))
+    st["thrust_des"] = st["thrust"].copy()
+    st["thrust_dot_est"] = g.normal(0, 5.0, (Bl, 4))
+    st["thrust_dot_des"] = np.zeros((Bl, 4))
+    st["throttle_prev"] = np.full((Bl, 4), 76.0) + g.normal(0, 3.0, (Bl, 4))
+    st["momentum_body"] *= 0.2
+    st["q_cmd"] = np.tile(rb.joint_pos0, (Bl, 1))
+    coeff = np.tile(np.asarray(cfg.JET_COEFF), (Bl, 1))
+    norm = np.tile(np.asarray(cfg.JET_NORM), (Bl, 1))
+    coeff[:, 1] *= g.uniform(0.9, 1.1, Bl)
+    coeff[:, 2] *= g.uniform(0.9, 1.1, Bl)
+    norm[:, 0] *= g.uniform(0.9, 1.1, Bl)
+    norm[:, 1] *= g.uniform(0.9, 1.1, Bl)
+    trj = dict(load_traj())
+    trj["alphaGravity"] = np.ones_like(trj["alphaGravity"])      # in flight: the surrogate has no ground contact
+    mpc = bat.BatchedVSMPC(Bl, None, trj, device=device)
+    mpc.set_stream(stream.cuda_stream)
+    mpc.set_instance_params(coeff, norm, g.uniform(0.0, 20.0, Bl), g.uniform(80.0, 100.0, Bl))
+    loop = ro.BatchedRollout(mpc, rb)
+    loop.init(st, mass_scale=ms_, inertia_scale=isc, thrust_disturbance=g.normal(0, 10.0, (Bl, 4)),
+              phase0=(np.arange(Bl) % 20).astype(np.int32))
+    loop.run(3)                                     # warm-up + graph capture
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    loop.run(ticks)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    _, status = mpc.get_output()
+    ps = loop.plant_state()
+    fin = np.isfinite(ps).all(axis=0)
+    drift = np.linalg.norm(ps[0:3].T - st["p_com"], axis=1)
+    mpc.close()
+    import torch.distributed as dist
+    cnt = torch.tensor([float((status == 0).sum()), float(fin.sum()), float(Bl)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max = _max_over_ranks([ms], world, dev)[0]
+    solved, finite, total = [float(x) for x in cnt.tolist()]
+    return {"value": total * ticks / (ms_max * 1e-3), "unit": "closed-loop solves/s", "scaling": "strong",
+            "instances_total": int(total), "instances_per_rank": int(Bl), "ticks": int(ticks), "ms_total": ms_max,
+            "ms_per_tick": ms_max / ticks, "kernels_per_tick": 3, "cuda_graph": True,
+            "solved_fraction_last_tick": solved / total, "finite_plant_states": finite / total,
+            "rank0_median_com_drift_m": float(np.median(drift[fin])),
+            "what": "per-instance initial state, thrust disturbance N(0, 10 N), mass x U(0.9, 1.1), inertia x U(0.8, 1.2), jet "
+                    "c1, c2, mu_T, sigma_T x U(0.9, 1.1), throttleMin U(0, 20), throttleMax U(80, 100); surrogate plant "
+                    "(5 x 1 ms) + linearise + QP per tick, device-resident, staggered 20-tick phases"}
 
 
 def closed_loop_leg(bat, B, device, stream, n_ticks, solver):
@@ -434,6 +592,9 @@ def main():
     ap.add_argument("--rollout-ticks", type=int, default=40, help="ticks of the device-resident closed-loop leg (0: skip)")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-instance latency leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the gather / long-horizon / Monte Carlo legs")
+    ap.add_argument("--mc-instances", type=int, default=65536, help="Monte Carlo sweep: instances in total over all ranks")
+    ap.add_argument("--mc-ticks", type=int, default=200)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

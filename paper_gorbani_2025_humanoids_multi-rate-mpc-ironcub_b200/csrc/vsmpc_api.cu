@@ -88,12 +88,15 @@ struct vsmpc_handle
     cudaStream_t copy_stream = nullptr;
     cudaStream_t out_stream = nullptr;   // device -> host read-back of vsmpc_get_output_async
     cudaEvent_t ev_solved = nullptr;     // last QP kernel done
-    bool out_pending = false;            // a read-back on out_stream has not been ordered before the next solve yet
     double* d_pack_in[2] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};
     cudaEvent_t ev_out[2] = {nullptr, nullptr};
     int pack_idx = 0, out_idx = 0;
+    // asynchronous read-back: the rows are snapshotted on the compute stream into one of two staging buffers and copied to
+    // the host from there, so that the next QP kernel (which rewrites d_out in place: held outputs) does not wait for PCIe
+    double* d_out_stage[2] = {nullptr, nullptr};
+    int* d_status_stage[2] = {nullptr, nullptr};
     // device buffers
     double* d_pack = nullptr;
     double* d_jpos = nullptr;
@@ -456,7 +459,7 @@ int vsmpc_destroy(vsmpc_handle* h)
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
                     h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl,
-                    h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
+                    h->d_out_stage[0], h->d_out_stage[1], h->d_status_stage[0], h->d_status_stage[1], h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
         if (h->ev_h2d[q]) cudaEventDestroy(h->ev_h2d[q]);
@@ -698,17 +701,28 @@ int vsmpc_get_output_async(vsmpc_handle* h, double* out_rows_host, int* status_h
     if (!h || h->B <= 0 || !ticket)
         return VSMPC_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    // the read-back runs on its own stream behind the solve, so that the next tick's linearise kernel does not queue
-    // behind the copy; the next QP kernel (the only writer of these buffers) is ordered after it in solve_launch
+    // snapshot on the compute stream (device-to-device, a few microseconds), read-back of the snapshot on its own stream:
+    // neither the next linearise kernel nor the next QP kernel (which rewrites d_out in place) waits for the PCIe copy
+    const int q = h->out_idx ^= 1;
+    const size_t nb_out = (size_t)VSMPC_OUT_DOUBLES * h->B * 8, nb_st = (size_t)h->B * 4;
+    for (int e = 0; e < 2; ++e)
+        if (!h->d_out_stage[e])
+        {
+            CK(dalloc(&h->d_out_stage[e], (size_t)VSMPC_OUT_DOUBLES * h->B));
+            CK(dalloc(&h->d_status_stage[e], (size_t)h->B));
+        }
+    CK(cudaStreamWaitEvent(h->stream, h->ev_out[q], 0));   // the read-back that used this staging buffer two calls ago
+    if (out_rows_host)
+        CK(cudaMemcpyAsync(h->d_out_stage[q], h->d_out, nb_out, cudaMemcpyDeviceToDevice, h->stream));
+    if (status_host)
+        CK(cudaMemcpyAsync(h->d_status_stage[q], h->d_status, nb_st, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaEventRecord(h->ev_solved, h->stream));
     CK(cudaStreamWaitEvent(h->out_stream, h->ev_solved, 0));
     if (out_rows_host)
-        CK(cudaMemcpyAsync(out_rows_host, h->d_out, (size_t)VSMPC_OUT_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->out_stream));
+        CK(cudaMemcpyAsync(out_rows_host, h->d_out_stage[q], nb_out, cudaMemcpyDeviceToHost, h->out_stream));
     if (status_host)
-        CK(cudaMemcpyAsync(status_host, h->d_status, (size_t)h->B * 4, cudaMemcpyDeviceToHost, h->out_stream));
-    const int q = h->out_idx ^= 1;
+        CK(cudaMemcpyAsync(status_host, h->d_status_stage[q], nb_st, cudaMemcpyDeviceToHost, h->out_stream));
     CK(cudaEventRecord(h->ev_out[q], h->out_stream));
-    h->out_pending = true;
     *ticket = q;
     return VSMPC_OK;
 }
@@ -931,11 +945,6 @@ static_assert(sizeof(PlantModel) == sizeof(vsmpc_plant_model), "PlantModel must 
 
 static int solve_launch(vsmpc_handle* h)
 {
-    if (h->out_pending)
-    { // an asynchronous read-back of the previous outputs must finish before they are overwritten
-        CK(cudaStreamWaitEvent(h->stream, h->ev_out[h->out_idx], 0));
-        h->out_pending = false;
-    }
     g_last_qp_solver.store(h->solver, std::memory_order_relaxed);
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,

@@ -12,11 +12,13 @@ constexpr int LDM = NX + 1;   // 27, odd: conflict-free transposition
 constexpr int NPD = 13;       // published P'D columns: throttle block (4), affine (1), joint block (8)
 constexpr int CCF = 164;      // coefficient block copied from the QP data (QD_RM .. QD_JGT, padded)
 constexpr int WSC_K = 0;      // per elimination knot in the workspace: K [8][26] first
+constexpr int GJ_LD = 10;     // leading dimension of the 8 x 8 tiles of gj8 in doubles; GJ_LD2 = 5 in double2 units
+constexpr int GJ_LD2 = GJ_LD / 2;
 
 struct alignas(16) CdSlot
 {
     double Hux[NJ * NX];    // [m][j]
-    double Hinv[NJ * NJ];   // [a][m]
+    double Hinv[NJ * GJ_LD]; // [a][m], rows padded to GJ_LD doubles (conflict-free Gauss-Jordan, see gj8)
     double PD[NX * NPD];    // [i][col]
 };
 
@@ -104,11 +106,14 @@ __device__ __forceinline__ double c_dot(const double (&y)[NX], const double* __r
 // Gauss-Jordan inverse of an SPD 8 x 8 matrix through shared memory by one warp: lane (r = lane & 7, q = lane >> 3)
 // owns element pair [r][2q..2q+1] in registers; every pivot step reads the pivot row / column from one buffer and
 // writes the updated pairs to the other (ping-pong S <-> T: one __syncwarp per pivot, no divergent branches); eight
-// pivots later the inverse is back in S.  S, T: row-major, ld 8, 16-byte aligned.
+// pivots later the inverse is back in S.  S, T: row-major, leading dimension GJ_LD = 10 doubles, 16-byte aligned: with
+// rows 80 bytes apart the eight rows of a quarter-warp's STS.128 fall on eight distinct groups of four banks and the
+// column reads S[r][p] on eight distinct bank pairs (ld 8 put rows 0, 2, 4, 6 on the same banks: the stores took 16
+// wavefronts instead of 4 and the column reads 8 instead of 2 — 10 % of the kernel's shared-memory traffic, r01h capture).
 __device__ __forceinline__ bool gj8(double* __restrict__ S, double* __restrict__ T, double2 own, int lane)
 {
     const int r = lane & 7, q = lane >> 3;
-    reinterpret_cast<double2*>(S)[r * 4 + q] = own;
+    reinterpret_cast<double2*>(S)[r * GJ_LD2 + q] = own;
     __syncwarp();
     bool ok = true;
     double* src = S;
@@ -116,9 +121,9 @@ __device__ __forceinline__ bool gj8(double* __restrict__ S, double* __restrict__
 #pragma unroll 2
     for (int p = 0; p < NJ; ++p)
     {
-        const double d = src[p * NJ + p];
-        const double f = src[r * NJ + p];
-        const double2 pr = reinterpret_cast<const double2*>(src)[p * 4 + q];
+        const double d = src[p * GJ_LD + p];
+        const double f = src[r * GJ_LD + p];
+        const double2 pr = reinterpret_cast<const double2*>(src)[p * GJ_LD2 + q];
         ok = ok && (d > 0.0) && (d < 1e300);
         const double dinv = __drcp_rn(d);
         const bool piv = r == p;
@@ -130,7 +135,7 @@ __device__ __forceinline__ bool gj8(double* __restrict__ S, double* __restrict__
         const bool mine = q == (p >> 1);
         own.x = (mine && !(p & 1)) ? val : own.x;
         own.y = (mine && (p & 1)) ? val : own.y;
-        reinterpret_cast<double2*>(dst)[r * 4 + q] = own;
+        reinterpret_cast<double2*>(dst)[r * GJ_LD2 + q] = own;
         __syncwarp();
         double* t = src;
         src = dst;
@@ -187,7 +192,7 @@ __device__ __forceinline__ bool a_eliminate(const CdCtxT<SM>& c, CdSlot& sl, dou
 #pragma unroll
             for (int m = 0; m < NJ / 2; ++m)
             {
-                const double2 hh = hi[a * (NJ / 2) + m];
+                const double2 hh = hi[a * GJ_LD2 + m];
                 v0 = fma(hh.x, hux[2 * m], v0);
                 v1 = fma(hh.y, hux[2 * m + 1], v1);
             }

@@ -27,7 +27,7 @@ constexpr int CD_THREADS = 64;
 constexpr int NL = 32;        // parameter columns (lanes of warp B)
 constexpr int NLO = 25;       // rows/columns of Om in use: 24 throttle variables + affine (held block aliases lanes)
 constexpr int AFFL = 24;      // lane of the affine column
-constexpr int LDH = 10;       // leading dimension of Hut rows (16-byte aligned)
+constexpr int LDH = 9;        // leading dimension of the F rows parked in shared memory (odd: conflict-free per lane)
 constexpr int CD_MAXNC = 16;  // reference columns kept in shared memory
 constexpr int CD_MAXW = 24;
 constexpr int WSC_F = NJ * NX;        //                                     then F [8][32]
@@ -121,7 +121,7 @@ __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&
 #pragma unroll
             for (int m = 0; m < NJ / 2; ++m)
             {
-                const double2 hh = hi[a * (NJ / 2) + m];
+                const double2 hh = hi[a * GJ_LD2 + m];
                 v0 = fma(hh.x, hut[2 * m], v0);
                 v1 = fma(hh.y, hut[2 * m + 1], v1);
             }

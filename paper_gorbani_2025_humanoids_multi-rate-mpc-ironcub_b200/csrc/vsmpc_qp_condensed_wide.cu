@@ -199,7 +199,7 @@ __device__ __forceinline__ void w_downdate(const CdSlot& sl, const CwLayout& L, 
 #pragma unroll
         for (int m = 0; m < NJ / 2; ++m)
         {
-            const double2 hh = hi[a * (NJ / 2) + m];
+            const double2 hh = hi[a * GJ_LD2 + m];
             v0 = fma(hh.x, hut[2 * m], v0);
             v1 = fma(hh.y, hut[2 * m + 1], v1);
         }

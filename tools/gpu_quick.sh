@@ -4,7 +4,7 @@ O=gpurun_out; mkdir -p $O
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 > $O/quick_pytest.log
 cat $O/quick_pytest.log
 for args in "--solver 0" "--solver 2" "--solver 0 --batch 16384 --steps 20" "--solver 0 --batch 4096 --steps 20"; do
-  timeout 600 python bench.py $args --no-cpu --no-latency --rollout-ticks 0 > $O/quick_bench.json 2> $O/quick_bench.err || tail -5 $O/quick_bench.err
+  timeout 600 python bench.py $args --no-cpu --no-latency --rollout-ticks 0 --no-extras > $O/quick_bench.json 2> $O/quick_bench.err || tail -5 $O/quick_bench.err
   python - <<PY
 import json
 try:

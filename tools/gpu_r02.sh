@@ -6,7 +6,7 @@ STEPS=${@:-tests bench}
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $O/${TAG}_gpu.txt
-CMD="python bench.py --steps 5 --warmup 3 --cpu-sample 8 --no-cpu --no-latency --rollout-ticks 0"
+CMD="python bench.py --steps 5 --warmup 3 --cpu-sample 8 --no-cpu --no-latency --rollout-ticks 0 --no-extras"
 for s in $STEPS; do
   case $s in
     smoke) timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> $O/${TAG}_smoke.log; tail -2 $O/${TAG}_smoke.log;;
@@ -14,8 +14,8 @@ for s in $STEPS; do
     tests_all) timeout 1500 python -m pytest tests -q -m gpu --maxfail 30 > $O/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_gpu.log; tail -60 $O/${TAG}_pytest_gpu.log;;
     pinned) timeout 300 python -m pytest tests/test_reference_pinned.py -q > $O/${TAG}_pytest_reference_pinned.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest_reference_pinned.log; tail -3 $O/${TAG}_pytest_reference_pinned.log;;
     bench) timeout 400 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; cut -c1-600 $O/${TAG}_bench.json; tail -3 $O/${TAG}_bench.err;;
-    benchq) timeout 300 python bench.py --no-cpu --no-latency --rollout-ticks 0 > $O/${TAG}_benchq.json 2> $O/${TAG}_benchq.err; python tools/bench_brief.py $O/${TAG}_benchq.json; tail -3 $O/${TAG}_benchq.err;;
-    bench16k) timeout 400 python bench.py --batch 16384 --steps 20 --no-cpu --no-latency --rollout-ticks 0 > $O/${TAG}_bench_b16384.json 2> $O/${TAG}_bench_b16384.err; python tools/bench_brief.py $O/${TAG}_bench_b16384.json;;
+    benchq) timeout 300 python bench.py --no-cpu --no-latency --rollout-ticks 0 --no-extras > $O/${TAG}_benchq.json 2> $O/${TAG}_benchq.err; python tools/bench_brief.py $O/${TAG}_benchq.json; tail -3 $O/${TAG}_benchq.err;;
+    bench16k) timeout 400 python bench.py --batch 16384 --steps 20 --no-cpu --no-latency --rollout-ticks 0 --no-extras > $O/${TAG}_bench_b16384.json 2> $O/${TAG}_bench_b16384.err; python tools/bench_brief.py $O/${TAG}_bench_b16384.json;;
     reference) timeout 300 python bench.py --impl reference --steps 5 --warmup 3 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; cut -c1-300 $O/${TAG}_bench_reference.json;;
     horizons) for h in 34,14,24 51,14,36 68,14,48; do timeout 300 python bench.py --horizon $h --steps 10 > $O/${TAG}_bench_h${h%%,*}.json 2> $O/${TAG}_bench_h${h%%,*}.err; python tools/bench_brief.py $O/${TAG}_bench_h${h%%,*}.json; done;;
     adjudicate) timeout 900 python tests/adjudicate_nonsolved.py 16384 199 > $O/${TAG}_adjudicate.log 2>&1; tail -30 $O/${TAG}_adjudicate.log;;

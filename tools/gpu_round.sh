@@ -11,7 +11,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err
 timeout 600 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
 timeout 600 python bench.py --batch 16384 --steps 20 > $O/${TAG}_bench_b16384.json 2> $O/${TAG}_bench_b16384.err
-CMD="python bench.py --steps 5 --warmup 3 --cpu-sample 8 --no-cpu --no-latency --rollout-ticks 0"
+CMD="python bench.py --steps 5 --warmup 3 --cpu-sample 8 --no-cpu --no-latency --rollout-ticks 0 --no-extras"
 timeout 600 $CMD > $O/${TAG}_plain.log 2>&1 || exit 1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qp_condensed -s 4 -c 1 -o $O/${TAG}_qp -f $CMD > $O/${TAG}_ncu_qp.log 2>&1

@@ -25,6 +25,9 @@ for i, nm in enumerate(names):
 b = np.stack([clk[:, 5] - clk[:, 4], clk[:, 6] - clk[:, 5]], 1)
 print(f"  {'reduced QP + active set (B)':34s} mean {b[:, 0].mean():9.0f}  p50 {np.median(b[:, 0]):9.0f}  max {b[:, 0].max():9.0f}")
 print(f"  {'F theta (both)':34s} mean {b[:, 1].mean():9.0f}")
+if clk[:, 13].any():
+    print(f"    of which: Omega down-date (both warps) mean {(clk[:, 13] - clk[:, 4]).mean():.0f}, reduced QP build + inverse mean {(clk[:, 14] - clk[:, 13]).mean():.0f}, "
+          f"active set mean {(clk[:, 5] - clk[:, 14]).mean():.0f} max {(clk[:, 5] - clk[:, 14]).max():.0f}")
 tot = clk[:, 3] - clk[:, 0]
 print(f"  total per instance mean {tot.mean():.0f} p50 {np.median(tot):.0f} max {tot.max():.0f}")
 
