@@ -560,7 +560,7 @@ def run_reference(args):
     from oracle import cbaseline
     K, Wm = args.steps, args.warmup
     cores = os.cpu_count() or 1
-    n = max(args.cpu_sample, min(1024, 4 * cores))
+    n = args.batch            # the same 1024 instances per step as the GPU arm (configs[1])
     runner = cbaseline.BaselineRunner(n, cores)
     for _ in range(Wm):
         runner.tick()
@@ -571,8 +571,10 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": Wm,
             "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "configs[1] (bounded sample): same synthetic instances and perturbation model, "
-                                   "CPU restatement of the reference tick", "instances_per_step": n},
+            "config": {"workload": "configs[1]: batch of %d independent MPC solves per step, reference horizon, same synthetic "
+                                   "instances and perturbation model as the GPU arm; CPU restatement of the reference tick "
+                                   "(OSQP-style ADMM), OpenMP over instances on all host cores" % n,
+                       "instances_per_gpu": n, "instances_per_step": n},
             "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -165,6 +165,14 @@ int vsmpc_set_instance_params(vsmpc_handle* h, const double* instance_params_hos
  * jointPos_max for every later call (NULL, NULL: back to the handle-wide values); needs use_joint_limits at create */
 int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const double* q_max_host);
 
+/* Long horizons (more than 6 throttle blocks): the active set of the reduced throttle QP starts from the working set the
+ * instance ended its previous solve with (device-resident; all-lower vertex after vsmpc_configure) — the counterpart of the
+ * reference running OSQP with setWarmStart(true) (IMPCProblem.cpp:140).  Any guess gives the same minimiser;
+ * enable = 0 starts every solve cold (tests, A/B timing).  Default: on.  No effect at the reference horizon. */
+int vsmpc_set_warm_start(vsmpc_handle* h, int enable);
+/* tests: overwrite the stored working sets, signed char[B][4 * throttle blocks] (+1 upper bound, -1 lower bound, 0 free) */
+int vsmpc_debug_set_working_set(vsmpc_handle* h, const signed char* working_set_host);
+
 /* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel. */
 int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);
 /* same, pack already resident on the handle's GPU */

@@ -307,6 +307,18 @@ class BatchedVSMPC:
         """Fallback QP kernel (pivoted LU of the KKT system): 0 off, 1 on (default), 2 every instance (tests)."""
         self._ck(self._lib.vsmpc_set_fallback(self._h, int(mode)), "vsmpc_set_fallback")
 
+    def set_warm_start(self, enable: bool):
+        """Long horizons: start the active set from the previous solve's working set (default) or cold."""
+        self._ck(self._lib.vsmpc_set_warm_start(self._h, 1 if enable else 0), "vsmpc_set_warm_start")
+
+    def debug_set_working_set(self, wset):
+        """Tests: overwrite the stored working sets, (B, 4 * throttle blocks) of +1 / -1 / 0."""
+        nblk = int(self.params["controlHorizon"]) - int(self.params["nIterSmall"]) + 1
+        w = np.ascontiguousarray(wset, dtype=np.int8)
+        if w.shape != (self.B, 4 * nblk):
+            raise VsmpcError(f"expected working sets of shape {(self.B, 4 * nblk)}")
+        self._ck(self._lib.vsmpc_debug_set_working_set(self._h, w.ctypes.data), "vsmpc_debug_set_working_set")
+
     def debug_set_counters(self, ref_counter: int = -1, throttle_counter: int = -1):
         self._ck(self._lib.vsmpc_debug_set_counters(self._h, ref_counter, throttle_counter), "vsmpc_debug_set_counters")
 

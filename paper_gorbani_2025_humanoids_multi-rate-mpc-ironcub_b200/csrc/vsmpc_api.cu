@@ -63,7 +63,9 @@ size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
-                                     int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, cudaStream_t s);
+                                     int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
+                                     int warm, cudaStream_t s);
+size_t condensed_wide_wset_bytes(const DeviceConfig& cfg);
 } // namespace vsmpc
 
 using namespace vsmpc;
@@ -129,6 +131,9 @@ struct vsmpc_handle
     bool use_nn = false;
     double* d_ip = nullptr;   // per-instance jet model / throttle limits (optional)
     bool use_ip = false;
+    signed char* d_wset = nullptr;   // long-horizon kernel: working set of the last solve per instance (warm start)
+    size_t wset_bytes = 0;
+    bool warm = true;
     double* d_jl = nullptr;   // per-instance joint limits [rad], SoA double[16][B]: 8 lower rows, 8 upper rows (optional)
     bool use_jl_table = false;
     bool rollout_ready = false;
@@ -395,6 +400,13 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         A(dalloc(&h->d_ws, wsd * B));
     }
     A(dalloc(&h->d_scratch, scratch * B));
+    if (h->solver == SOLVER_WIDE)
+    {
+        h->wset_bytes = condensed_wide_wset_bytes(g) * B;
+        A(dalloc(&h->d_wset, h->wset_bytes));
+        if (ok)
+            A(cudaMemset(h->d_wset, 0xFF, h->wset_bytes));     // all-lower vertex
+    }
     A(dalloc(&h->d_z, (size_t)g.n_var * B));
     A(dalloc(&h->d_out, (size_t)VSMPC_OUT_DOUBLES * B));
     A(dalloc(&h->d_status, (size_t)B));
@@ -458,7 +470,7 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl,
+                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset,
                     h->d_out_stage[0], h->d_out_stage[1], h->d_status_stage[0], h->d_status_stage[1], h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -506,6 +518,8 @@ int vsmpc_n_instances(const vsmpc_handle* h) { return h ? h->B : -1; }
 
 static int run_linearise(vsmpc_handle* h, int mode)
 {
+    if (mode == 1 && h->d_wset)     // IMPCProblem::configure: no previous solve, the guess is the all-lower vertex
+        CK(cudaMemsetAsync(h->d_wset, 0xFF, h->wset_bytes, h->stream));
     CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
                         h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd,
                         h->use_ip ? h->d_ip : nullptr, h->d_fb_count, h->use_jl_table ? h->d_jl : nullptr, h->stream));
@@ -598,6 +612,29 @@ int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const doub
     CK(cudaMemcpyAsync(h->d_jl + n, q_max_host, n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->use_jl_table = true;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_warm_start(vsmpc_handle* h, int enable)
+{
+    if (!h || h->B <= 0)
+        return VSMPC_ERR_ARG;
+    if (h->warm != (enable != 0))
+        drop_tick_graph(h);
+    h->warm = enable != 0;
+    return VSMPC_OK;
+}
+
+int vsmpc_debug_set_working_set(vsmpc_handle* h, const signed char* wset_host)
+{
+    if (!h || h->B <= 0 || !wset_host)
+        return VSMPC_ERR_ARG;
+    if (!h->d_wset)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_debug_set_working_set: this horizon does not use the long-horizon kernel");
+    CK(cudaSetDevice(h->device));
+    const size_t nv = (size_t)NT * h->cfg.nblk, pitch = h->wset_bytes / h->B;
+    CK(cudaMemcpy2DAsync(h->d_wset, pitch, wset_host, nv, nv, h->B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return VSMPC_OK;
 }
 
@@ -953,7 +990,7 @@ static int solve_launch(vsmpc_handle* h)
     else if (h->solver == SOLVER_WIDE)
         CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
                                     h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count,
-                                    h->fb_mode, h->stream));
+                                    h->fb_mode, h->d_wset, h->warm ? 1 : 0, h->stream));
     else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));

@@ -52,7 +52,7 @@ struct CwLayout
     int nt;                     // 8 x 8 tiles per side of Om
     int wsF, wsH, stage;        // workspace per elimination knot: K [8][26] | F [8][ldc] | H_utheta [8][ldc]
     int nvp, nvs;               // nv rounded up to 8; stride of the deferred-pivot stacks
-    int om, fth, theta, vv, grad, stk, xref, rb, total;   // offsets (doubles) in dynamic shared memory
+    int om, fth, theta, vv, grad, stk, xref, rb, actg, total;   // offsets (doubles) in dynamic shared memory
 };
 
 __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
@@ -81,6 +81,7 @@ __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
     L.stk = o;    o += 2 * CW_MD * L.nvs;   // deferred pivots: A [8][nvs] then B [8][nvs]
     L.xref = o;   o += 12 * cfg.NC;
     L.rb = o;     o += 4 * 8;      // two block-reduction buffers: value [8], index [8] each
+    L.actg = o;   o += (L.nvp + 1) / 2 + 2;   // working-set guess, int [nvp]; then two doubles broadcast by the dropping thread
     L.total = o;
     return L;
 }
@@ -414,7 +415,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                          double* __restrict__ ws_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
                          int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride,
-                         int want_z, int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode)
+                         int want_z, int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode,
+                         signed char* __restrict__ wset_all, int warm)
 {
     extern __shared__ __align__(16) unsigned char cw_raw[];
     CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
@@ -654,34 +656,102 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         }
         __syncthreads();
     }
-    // inverse of the scaled H_r = Om[first:nv, first:nv] in place: exchange pivot on every index
+    // Working-set guess: the working set this instance ended its previous solve with (device-resident state, all-lower
+    // after configure; `warm` off: empty, which is the cold method — invert H_r, then add bounds one at a time).
+    // tools/condensed_model.box_qp_pivot_warm is the specification: T starts as H_r itself (every index in the working
+    // set) and only the guessed-free indices are pivoted — |F0| pivots instead of n + |W|; a drop phase removes the
+    // wrong-signed multipliers of the guess (it ends on an S-pair whatever the guess was), then the dual iterations add
+    // the bounds still violated.  Any guess gives the same minimiser.
+    int* actg = reinterpret_cast<int*>(dyn + L.actg);
+    double* bc = dyn + L.actg + (L.nvp + 1) / 2;      // two doubles broadcast by the dropping thread
+    signed char* wset = wset_all + (size_t)inst * L.nvp;
+    int act = 0;            // 0 free, +1 / -1 in the working set at the upper / lower bound
+    if (threadIdx.x < nv)
+    {
+        const int a = (warm && threadIdx.x >= first) ? (int)wset[threadIdx.x] : 0;
+        actg[threadIdx.x] = a;
+        act = a;
+    }
+    __syncthreads();
     CwPiv Pv = P;
     Pv.first = first;
     int M = 0;
+    int n_piv0 = 0;
     bool okG = true;
     for (int p = first; p < nv; ++p)
-        okG = cw_pivot(Pv, M, p, warp, lane, nwarps, nthr) && okG;
+        if (actg[p] == 0)
+        {
+            okG = cw_pivot(Pv, M, p, warp, lane, nwarps, nthr) && okG;
+            ++n_piv0;
+        }
     if (M > 0)
         cw_flush(Pv, M, warp, lane, nwarps, nthr);
     if (sm.flags[0] != 0 || !okG)
         stat = stat == VSMPC_STATUS_SOLVED ? VSMPC_STATUS_NUMERICAL : stat;
-    // unconstrained minimiser v~ = -G g~ (scaled variables); afterwards grad holds the inverse scale factors for all threads
-    for (int e = threadIdx.x; e < nv; e += nthr)
+    // sub-problem on the guessed set, one matrix-vector product (scaled variables): out = T (-g_F, b_W) = v on the free
+    // set, y = H_r v on the working set; afterwards grad holds the inverse scale factors for all threads
+    const double iS_e = 1.0 / S_e;
+    const double lo_e = lo * iS_e, up_e = up * iS_e;    // bounds of the scaled variable
+    const bool isvar = threadIdx.x >= first && threadIdx.x < nv;
+    const double g_e = isvar ? grad[threadIdx.x] : 0.0;
+    double b_e = act > 0 ? up_e : lo_e;
+    if (threadIdx.x < nv)
+        vv[threadIdx.x] = isvar ? (act == 0 ? -g_e : b_e) : 0.0;
+    __syncthreads();
+    double out_e = 0.0;
+    if (isvar)
     {
-        double v = 0.0;
-        if (e >= first)
-        {
-            const double* row = Om + e * ldo;
-            for (int j = first; j < nv; ++j)
-                v = fma(-row[j], grad[j], v);
-        }
-        vv[e] = v;
+        const double* row = Om + threadIdx.x * ldo;
+        for (int j = first; j < nv; ++j)
+            out_e = fma(row[j], vv[j], out_e);
     }
     __syncthreads();
     double* iscl = grad;          // 1 / S for all threads
-    const double iS_e = 1.0 / S_e;
     if (threadIdx.x < nv)
         iscl[threadIdx.x] = iS_e;
+    // drop phase: while a multiplier of the guessed working set has the wrong sign, pivot the worst one out.  The pivot only
+    // relabels input a (was v_a = b_a) and output a (was y_a); then the new input y_a moves to its free-variable value -g_a
+    // and every output follows column a of the new transform: no second matrix-vector product.
+    double lam_e = 0.0;
+    int iters = 0;
+    bool fail = stat != VSMPC_STATUS_SOLVED;
+    while (!fail)
+    {
+        lam_e = (isvar && act != 0) ? -(double)act * (out_e + g_e) : 0.0;      // multiplier of the scaled variable
+        int a;
+        const double worst = cw_block_best<true>(fmax(-lam_e * S_e, 0.0), rbA, warp, lane, nwarps, a);
+        if (!(worst > 1e-10))
+            break;
+        if (++iters > 4 * nv + 64)
+        {
+            stat = VSMPC_STATUS_MAX_ITER;
+            fail = true;
+            break;
+        }
+        if (threadIdx.x == a)
+        {
+            bc[0] = -g_e - out_e;
+            bc[1] = b_e;
+        }
+        if (!cw_pivot(Pv, M, a, warp, lane, nwarps, nthr))
+        {
+            stat = VSMPC_STATUS_NUMERICAL;
+            fail = true;
+            break;
+        }
+        const double delta = bc[0];
+        const double col_e = isvar ? cw_teff(Pv, M, threadIdx.x, a) : 0.0;
+        if (threadIdx.x == a)
+        {
+            out_e = fma(col_e, delta, bc[1]);
+            act = 0;
+        }
+        else
+            out_e = fma(col_e, delta, out_e);
+    }
+    lam_e = fmax(lam_e, 0.0);
+    if (threadIdx.x < nv)
+        vv[threadIdx.x] = isvar ? (act == 0 ? out_e : b_e) : 0.0;
     __syncthreads();
 
     WCLK(4);
@@ -692,13 +762,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     // denominator.  A full step pivots p into W, a blocked step pivots the blocking index back into F.
     {
         const int e = threadIdx.x;
-        const bool isvar = e >= first && e < nv;
         const double tol = 1e-10;
-        const double lo_e = lo * iS_e, up_e = up * iS_e;    // bounds of the scaled variable
-        int act = 0;            // 0 free, +1 / -1 active at the upper / lower bound
-        double lam_e = 0.0;
-        int iters = 0;
-        bool fail = stat != VSMPC_STATUS_SOLVED;
         while (!fail)
         {
             double viol = 0.0;
@@ -791,7 +855,10 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         if (__syncthreads_or(isvar && !isfinite(vv[e])) && stat == VSMPC_STATUS_SOLVED)
             stat = VSMPC_STATUS_NUMERICAL;
         if (threadIdx.x == 0)
-            sm.flags[2] = (nv - first) + iters;   // exchange pivots executed: inverse + one per active-set iteration
+            sm.flags[2] = n_piv0 + iters;         // exchange pivots executed: guessed-free set + one per active-set iteration
+        // the working set this solve ended with is the guess of the next one
+        if (stat == VSMPC_STATUS_SOLVED && e < nv)
+            wset[e] = (signed char)(e >= first ? act : 0);
         // theta*: throttle variables, affine 1, held block 0
         if (e < L.ldc)
         {
@@ -899,6 +966,11 @@ size_t condensed_wide_ws_doubles(const DeviceConfig& cfg)
     return (size_t)cfg.Nc * cw_layout(cfg).stage;
 }
 
+size_t condensed_wide_wset_bytes(const DeviceConfig& cfg)
+{
+    return (size_t)cw_layout(cfg).nvp;     // working set of the last solve per instance: one signed char per throttle variable
+}
+
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
 {
     (void)cfg;
@@ -907,7 +979,8 @@ size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
 
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
-                                     int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, cudaStream_t s)
+                                     int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
+                                     int warm, cudaStream_t s)
 {
     static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
     const CwLayout L = cw_layout(h_cfg);
@@ -921,14 +994,14 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                       n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm);
+                                                                       n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm);
     }
     else if (L.G == 3)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                        n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm);
+                                                                        n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm);
     }
     else
     {
@@ -937,7 +1010,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
         // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
         qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
-            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm);
+            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm);
     }
     return cudaGetLastError();
 }

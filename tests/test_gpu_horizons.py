@@ -145,3 +145,53 @@ def test_long_horizon_default_solver(variant):
             assert_solution_close(z[i], zo, 1e-6, what=(variant, tick, i), **hz)     # per physical quantity
             assert_output_rows_close(out[i], o.output_row(), 1e-6, what=(variant, tick, i))
     mpc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 2, 4])
+def test_warm_started_working_set_any_guess_same_minimiser(variant):
+    """The long-horizon kernel starts its active set from the working set of the instance's previous solve
+    (tools/condensed_model.box_qp_pivot_warm).  A tick sequence that jumps between unrelated states — every guess is the
+    working set of ANOTHER state — with a throttle release in the middle, then adversarial guesses written into the device
+    state (every bound upper, every bound lower, all free, random): every solve lands on the oracle's minimiser, and the
+    cold start (vsmpc_set_warm_start 0) gives the same rows with more pivots."""
+    params = LONG[variant]
+    B = 4
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    states = [syn.make_states(B, seed=300 + 17 * k + variant, perturbed=True, near_bound_fraction=0.1 + 0.2 * (k % 4)) for k in range(4)]
+    nblk = params["controlHorizon"] - params["nIterSmall"] + 1
+    hz = dict(N=params["nIter"], Nc=params["controlHorizon"], nblk=nblk)
+    rng = np.random.default_rng(5)
+    guesses = {4: np.ones((B, 4 * nblk)), 5: -np.ones((B, 4 * nblk)), 6: np.zeros((B, 4 * nblk)),
+               7: rng.integers(-1, 2, (B, 4 * nblk))}
+    pivots = {}
+    for warm in (True, False):
+        mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), solver=0, full_solution=True)
+        mpc.set_warm_start(warm)
+        mpc.configure(nom)
+        oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
+        ratio = oracles[0].mpc.vectorConstraints[2].ratio
+        pivots[warm] = 0
+        for tick in range(8):
+            per = states[tick % len(states)]
+            if tick == 3:       # a released tick: block 0 joins the variables, the stored set has no entry for it
+                mpc.debug_set_counters(-1, ratio - 1)
+            if warm and tick in guesses:
+                mpc.debug_set_working_set(guesses[tick])
+            mpc.update(per)
+            mpc.solveMPC()
+            z = mpc.getSolution()
+            out, status = mpc.get_output()
+            assert (status == 0).all(), (warm, tick, status)
+            pivots[warm] += int(mpc.get_pivot_counts().sum())
+            for i, o in enumerate(oracles):
+                if tick == 3:
+                    o.mpc.vectorConstraints[2].counter = ratio - 1
+                o.update(per)
+                zo = o.solve()
+                assert_solution_close(z[i], zo, 1e-6, what=(variant, warm, tick, i), **hz)
+                assert_output_rows_close(out[i], o.output_row(), 1e-6, what=(variant, warm, tick, i))
+        mpc.close()
+    print("exchange pivots over the sequence: warm", pivots[True], "cold", pivots[False])

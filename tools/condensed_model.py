@@ -109,7 +109,7 @@ def box_qp_pivot(H, g, lo, up, max_iter=200, tol=1e-10):
 
 def box_qp_pivot_warm(H, g, lo, up, act0, max_iter=200, tol=1e-10):
     """The same problem started from a guessed working set act0 (+1: at `up`, -1: at `lo`, 0: free; e.g. the working set of the
-    previous controller tick) — NOT yet in the CUDA kernels, the specification of the next step for the long horizons.
+    previous controller tick) — the specification of the warm start of csrc/vsmpc_qp_condensed_wide.cu.
     T starts as H itself (every index in the working set: no inverse) and only the guessed-free indices are pivoted:
     |F0| pivots instead of n + |W|.
       phase 1 (drop only, finite): solve the sub-problem on the guessed set, (v_F, y_W) = T (-g_F, b_W),
@@ -126,9 +126,9 @@ def box_qp_pivot_warm(H, g, lo, up, act0, max_iter=200, tol=1e-10):
         pivots += 1
         if not exchange_pivot(T, q) > 0:
             return np.zeros(n), [], 2, pivots
+    b = np.where(act > 0, up_v, lo_v)
+    out = T @ np.where(act == 0, -g, b)         # the one matrix-vector product: v on the free set, y = Hv on the working set
     while True:
-        b = np.where(act > 0, up_v, lo_v)
-        out = T @ np.where(act == 0, -g, b)
         lam = np.where(act != 0, -act * (out + g), 0.0)
         a = int(np.argmin(lam))
         if not lam[a] < -tol:
@@ -136,6 +136,13 @@ def box_qp_pivot_warm(H, g, lo, up, act0, max_iter=200, tol=1e-10):
         pivots += 1
         if not exchange_pivot(T, a) > 0:
             return np.zeros(n), [], 2, pivots
+        # a leaves the working set.  The pivot only relabels input a (was v_a = b_a) and output a (was y_a = out_a): the
+        # same point satisfies the new relation; then the new input y_a moves from out_a to its free-variable value -g_a and
+        # every output follows column a of the new transform (what the kernel does: no second matrix-vector product)
+        delta = -g[a] - out[a]
+        col = T[:, a].copy()
+        out = out + col * delta
+        out[a] = b[a] + col[a] * delta
         act[a] = 0
     vv = np.where(act == 0, out, b)
     lam = np.maximum(lam, 0.0)
