@@ -322,6 +322,49 @@ int vsmpc_jet_nn_eval(vsmpc_handle* h, int n_groups, double dt, const float* T_h
 /* the pack the plant built for the next tick (double[VSMPC_PACK_DOUBLES][B]) — parity tests */
 int vsmpc_rollout_get_pack(vsmpc_handle* h, double* pack_host);
 
+/* ---- batched reduced kinematics: the part of Robot::setState the path consumes ----------------------------
+ * UT/src/Robot.cpp:212-278,325-332 computes, through iDynTree, the kinematic rows of the pack (base block of the mass matrix,
+ * CoM, centroidal momentum, jet axes / arms, A_mom, relative / free-floating / CoM Jacobians of the controlled joints).  Here
+ * the same rows are computed ON THE DEVICE for the whole batch from a kinematic tree given as arrays, so that the host sends
+ * the 18 + 2 n_dof + 28 doubles of a robot state per instance (92 for the 23-joint robot) instead of the 359-double pack.
+ * Conventions: iDynTree's MIXED velocity representation (oracle/kinematics_oracle.py states them); parity against iDynTree
+ * itself is unpinned — neither the library nor the iRonCub URDF is available; the oracle is checked against closed forms and
+ * finite differences of its own forward kinematics. */
+#define VSMPC_KIN_MAX_LINKS 32
+typedef struct vsmpc_kin_model
+{
+    int n_links;                                /* link 0 = floating base; every other link hangs on one revolute joint   */
+    int n_dof;                                  /* length of the joint vector (axesList order, robot.toml:3-27)           */
+    int parent[VSMPC_KIN_MAX_LINKS];            /* parent[0] = -1, parent[l] < l                                          */
+    int dof[VSMPC_KIN_MAX_LINKS];               /* position of link l's joint in the joint vector, dof[0] = -1            */
+    double R0[VSMPC_KIN_MAX_LINKS][9];          /* rotation parent link frame -> joint frame at q = 0, row-major          */
+    double p0[VSMPC_KIN_MAX_LINKS][3];          /* joint origin in the parent link frame                                  */
+    double axis[VSMPC_KIN_MAX_LINKS][3];        /* unit joint axis in the joint (= child link) frame                      */
+    double mass[VSMPC_KIN_MAX_LINKS];
+    double com[VSMPC_KIN_MAX_LINKS][3];         /* link CoM in the link frame                                             */
+    double inertia[VSMPC_KIN_MAX_LINKS][9];     /* link inertia about its CoM, link axes, row-major                       */
+    int jet_link[VSMPC_NT];                     /* link carrying jet i                                                    */
+    double jet_pos[VSMPC_NT][3];                /* jet frame origin in that link's frame                                  */
+    double jet_axis[VSMPC_NT][3];               /* thrust axis in that link's frame (Robot::m_jetsAxesLocalFrames)        */
+    double delta_com[3];                        /* Robot::m_deltaCoM (base axes), Robot.cpp:253-255                       */
+    double gravity[3];
+    int sel[VSMPC_NJ];                          /* controlled joints as positions in the joint vector                     */
+} vsmpc_kin_model;
+/* robot state of one tick, SoA double[vsmpc_kin_state_doubles][B]: rows in this order */
+#define VSMPC_KS_WRB          0   /* 9  base rotation, row-major                    */
+#define VSMPC_KS_BASE_POS     9   /* 3                                              */
+#define VSMPC_KS_BASE_LIN_VEL 12  /* 3  velocity of the base origin, world axes     */
+#define VSMPC_KS_OMEGA_WORLD  15  /* 3                                              */
+#define VSMPC_KS_Q            18  /* n_dof joint positions, then n_dof joint velocities, then the 28 QPInput rows of the pack
+                                     (VSMPC_PK_THRUST .. VSMPC_PK_Q_CMD, same order) */
+int vsmpc_set_kin_model(vsmpc_handle* h, const vsmpc_kin_model* model);
+int vsmpc_kin_state_doubles(const vsmpc_handle* h);          /* 18 + 2 n_dof + 28, -1 before vsmpc_set_kin_model */
+/* vsmpc_configure / vsmpc_set_state with the pack built on the device by the kinematics kernel (joint_pos_sel = q[sel]) */
+int vsmpc_configure_kinematics(vsmpc_handle* h, const double* kin_state_host, const int* phase0_host);
+int vsmpc_set_state_kinematics(vsmpc_handle* h, const double* kin_state_host);
+/* the pack of the last vsmpc_*_kinematics call (double[VSMPC_PACK_DOUBLES][B]) — parity tests */
+int vsmpc_get_kinematics_pack(vsmpc_handle* h, double* pack_host);
+
 /* ---- one process, several GPUs (SURVEY §8b "vsmpc_create(cfg, n_instances, n_gpus, ...)", §8e) -----------------------------
  * B instances sharded in contiguous ranges [g B / G, (g + 1) B / G) over G devices (devices == NULL: 0 .. G-1; an entry may
  * repeat, e.g. {0, 0} puts two shards on one GPU), one vsmpc_handle with its own streams per shard, driven by ONE host

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libvsmpc.so")
 STAMP = os.path.join(HERE, ".libvsmpc.stamp")
 
 SOURCES = ["vsmpc_api.cu", "vsmpc_linearise.cu", "vsmpc_qp_generic.cu", "vsmpc_qp_structured.cu", "vsmpc_qp_condensed.cu", "vsmpc_qp_condensed_wide.cu", "vsmpc_qp_fallback.cu",
-           "vsmpc_plant.cu",
+           "vsmpc_plant.cu", "vsmpc_kinematics.cu",
            "vsmpc_microbench.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"]

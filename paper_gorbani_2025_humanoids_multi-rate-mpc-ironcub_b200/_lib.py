@@ -76,7 +76,7 @@ EXPORTS = [
     "vsmpc_multi_shard", "vsmpc_multi_configure", "vsmpc_multi_set_instance_params", "vsmpc_multi_set_state", "vsmpc_multi_solve",
     "vsmpc_multi_solve_async", "vsmpc_multi_wait", "vsmpc_multi_get_output", "vsmpc_multi_set_full_solution",
     "vsmpc_multi_get_full_solution",
-    "vsmpc_set_instance_params", "vsmpc_set_joint_limits", "vsmpc_set_warm_start", "vsmpc_debug_set_working_set", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
+    "vsmpc_set_instance_params", "vsmpc_set_joint_limits", "vsmpc_set_warm_start", "vsmpc_set_kin_model", "vsmpc_kin_state_doubles", "vsmpc_configure_kinematics", "vsmpc_set_state_kinematics", "vsmpc_get_kinematics_pack", "vsmpc_debug_set_working_set", "vsmpc_rollout_init", "vsmpc_rollout_run", "vsmpc_rollout_get_state", "vsmpc_rollout_set_jet_nn", "vsmpc_jet_nn_eval", "vsmpc_rollout_get_pack",
 ]
 
 _lib = None
@@ -122,6 +122,11 @@ def load() -> C.CDLL:
     lib.vsmpc_debug_set_counters.argtypes = [H, C.c_int, C.c_int]
     lib.vsmpc_set_fallback.argtypes = [H, C.c_int]
     lib.vsmpc_set_warm_start.argtypes = [H, C.c_int]
+    lib.vsmpc_set_kin_model.argtypes = [H, C.c_void_p]
+    lib.vsmpc_kin_state_doubles.argtypes = [H]
+    lib.vsmpc_configure_kinematics.argtypes = [H, C.c_void_p, C.c_void_p]
+    lib.vsmpc_set_state_kinematics.argtypes = [H, C.c_void_p]
+    lib.vsmpc_get_kinematics_pack.argtypes = [H, C.c_void_p]
     lib.vsmpc_debug_set_working_set.argtypes = [H, C.c_void_p]
     lib.vsmpc_debug_phase_clocks.argtypes = [C.c_void_p, C.c_int]
     lib.vsmpc_microbench_fp64.argtypes = [C.c_int, C.c_int, c_double_p]

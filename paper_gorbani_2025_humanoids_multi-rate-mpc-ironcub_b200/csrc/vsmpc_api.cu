@@ -66,6 +66,12 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
                                      int warm, cudaStream_t s);
 size_t condensed_wide_wset_bytes(const DeviceConfig& cfg);
+struct KinModelDev;
+const char* kin_prepare(const vsmpc_kin_model& m, KinModelDev& K);
+size_t kin_model_bytes();
+int kin_state_rows(const KinModelDev& K);
+cudaError_t launch_kinematics(const KinModelDev* d_model, int ks_rows, int B, const double* ks, double* pack, double* jpos,
+                              cudaStream_t s);
 } // namespace vsmpc
 
 using namespace vsmpc;
@@ -131,6 +137,10 @@ struct vsmpc_handle
     bool use_nn = false;
     double* d_ip = nullptr;   // per-instance jet model / throttle limits (optional)
     bool use_ip = false;
+    // batched reduced kinematics (vsmpc_kinematics.cu): the pack is built on the device from the robot state
+    KinModelDev* d_kin = nullptr;
+    double* d_ks[2] = {nullptr, nullptr};   // robot-state staging, double[ks_rows][B] each (pipelined like the pack)
+    int ks_rows = 0;
     signed char* d_wset = nullptr;   // long-horizon kernel: working set of the last solve per instance (warm start)
     size_t wset_bytes = 0;
     bool warm = true;
@@ -470,7 +480,7 @@ int vsmpc_destroy(vsmpc_handle* h)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset,
+                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset, h->d_kin, h->d_ks[0], h->d_ks[1],
                     h->d_out_stage[0], h->d_out_stage[1], h->d_status_stage[0], h->d_status_stage[1], h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -622,6 +632,108 @@ int vsmpc_set_warm_start(vsmpc_handle* h, int enable)
     if (h->warm != (enable != 0))
         drop_tick_graph(h);
     h->warm = enable != 0;
+    return VSMPC_OK;
+}
+
+// ---- batched reduced kinematics: robot state in, pack built on the device -------------------------------------
+int vsmpc_set_kin_model(vsmpc_handle* h, const vsmpc_kin_model* model)
+{
+    if (!h || h->B <= 0 || !model)
+        return VSMPC_ERR_ARG;
+    std::vector<unsigned char> buf(kin_model_bytes());
+    KinModelDev& K = *reinterpret_cast<KinModelDev*>(buf.data());
+    const char* why = kin_prepare(*model, K);
+    if (why[0])
+        return fail(h, VSMPC_ERR_ARG, std::string("vsmpc_set_kin_model: ") + why);
+    CK(cudaSetDevice(h->device));
+    drop_tick_graph(h);
+    const int rows = kin_state_rows(K);
+    if (!h->d_kin)
+        CK(cudaMalloc(reinterpret_cast<void**>(&h->d_kin), buf.size()));
+    if (rows != h->ks_rows)
+        for (int q = 0; q < 2; ++q)
+        {
+            if (h->d_ks[q])
+                cudaFree(h->d_ks[q]);
+            h->d_ks[q] = nullptr;
+            CK(dalloc(&h->d_ks[q], (size_t)rows * h->B));
+        }
+    h->ks_rows = rows;
+    CK(cudaMemcpyAsync(h->d_kin, buf.data(), buf.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return VSMPC_OK;
+}
+
+int vsmpc_kin_state_doubles(const vsmpc_handle* h) { return (h && h->ks_rows > 0) ? h->ks_rows : -1; }
+
+int vsmpc_configure_kinematics(vsmpc_handle* h, const double* kin_state_host, const int* phase0_host)
+{
+    if (!h || h->B <= 0 || !kin_state_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_configure_kinematics: null argument");
+    if (!h->d_kin)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_configure_kinematics: vsmpc_set_kin_model first");
+    CK(cudaSetDevice(h->device));
+    const size_t B = h->B;
+    CK(cudaMemcpyAsync(h->d_ks[0], kin_state_host, (size_t)h->ks_rows * B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_kinematics(h->d_kin, h->ks_rows, h->B, h->d_ks[0], h->d_pack, h->d_jpos, h->stream));
+    if (phase0_host)
+    {
+        for (size_t i = 0; i < B; ++i)
+            if (phase0_host[i] < 0 || phase0_host[i] >= h->cfg.ratio)
+                return fail(h, VSMPC_ERR_ARG, "vsmpc_configure_kinematics: phase0 out of [0, ratio)");
+        CK(cudaMemcpyAsync(h->d_phase, phase0_host, B * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    else
+        CK(cudaMemsetAsync(h->d_phase, 0, B * 4, h->stream));
+    int rc = run_linearise(h, 1);
+    if (rc)
+        return rc;
+    seed_outputs_kernel<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->d_jpos, nullptr, h->d_out, h->d_status);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->configured = true;
+    h->has_state = false;
+    return VSMPC_OK;
+}
+
+int vsmpc_set_state_kinematics(vsmpc_handle* h, const double* kin_state_host)
+{
+    if (!h || h->B <= 0 || !kin_state_host)
+        return fail(h, VSMPC_ERR_ARG, "vsmpc_set_state_kinematics: null argument");
+    if (!h->d_kin)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_set_state_kinematics: vsmpc_set_kin_model first");
+    if (!h->configured)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_set_state_kinematics: configure first");
+    CK(cudaSetDevice(h->device));
+    // same pipeline as vsmpc_set_state: the (four times smaller) robot state is staged on the copy stream, the kinematics
+    // kernel builds the pack of this tick in the staging pack buffer, then the linearise kernel runs on it
+    const int q = h->pack_idx ^= 1;
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1[q], 0));
+    CK(cudaMemcpyAsync(h->d_ks[q], kin_state_host, (size_t)h->ks_rows * h->B * 8, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->ev_h2d[q], h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[q], 0));
+    CK(launch_kinematics(h->d_kin, h->ks_rows, h->B, h->d_ks[q], h->d_pack_in[q], nullptr, h->stream));
+    double* saved = h->d_pack;
+    h->d_pack = h->d_pack_in[q];
+    int rc = run_linearise(h, 0);
+    h->d_pack = saved;
+    if (rc)
+        return rc;
+    CK(cudaEventRecord(h->ev_k1[q], h->stream));
+    h->has_state = true;
+    return VSMPC_OK;
+}
+
+int vsmpc_get_kinematics_pack(vsmpc_handle* h, double* pack_host)
+{
+    if (!h || h->B <= 0 || !pack_host)
+        return VSMPC_ERR_ARG;
+    if (!h->d_kin)
+        return fail(h, VSMPC_ERR_STATE, "vsmpc_get_kinematics_pack: vsmpc_set_kin_model first");
+    CK(cudaSetDevice(h->device));
+    const double* src = h->has_state ? h->d_pack_in[h->pack_idx] : h->d_pack;
+    CK(cudaMemcpyAsync(pack_host, src, (size_t)VSMPC_PACK_DOUBLES * h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return VSMPC_OK;
 }
 
