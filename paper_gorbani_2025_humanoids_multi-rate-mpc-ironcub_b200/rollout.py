@@ -132,11 +132,95 @@ class BatchedRollout:
         return pk
 
 
-def save_log_mat(path: str, rec: np.ndarray, instance: int, period_mpc: float = 0.005, record_every: int = 1) -> dict:
-    """Write one instance's rollout record in the layout of the reference driver's end-of-run log
-    (``scipy.io.savemat`` dictionary of src/variable_sampling_mpc.py:163-194), for the series the device loop
-    records: CoM position, base orientation (RPY), estimated thrust, throttle, solver status and the time axis."""
+LOG_KEYS = ("CoMPosition", "CoMPosition_desired", "base_orientation_desired", "base_position", "base_orientation",
+            "base_lin_vel", "base_ang_vel", "base_lin_vel_filtered", "base_ang_vel_filtered", "joints_pos_meas",
+            "joints_pos_ref", "linear_momentum", "angular_momentum", "momentum_reference", "estimated_thrust",
+            "estimated_thrust_dot", "thrust_desired", "thrust_desired_dot", "alpha_gravity", "throttle", "mom_dot",
+            "time_controller", "time_MPC")      # the 23 series of src/variable_sampling_mpc.py:163-186
+
+
+def run_logged(loop: BatchedRollout, n_ticks: int, instance: int = 0, period_mpc: float = 0.005) -> dict:
+    """Advance the device-resident loops tick by tick and log ONE instance with the reference driver's 23 series
+    (src/variable_sampling_mpc.py:139-161 appends, :163-186 keys; same moment of the tick: measured state and the
+    outputs of the tick it produced, before the plant steps on).  A logging run reads the device state back every tick
+    (plant pack, output row, published references) — meant for inspecting one loop, not for throughput.
+    What the surrogate plant cannot supply is said here: it has no velocity filter (``*_filtered`` = the raw values) and
+    its base velocity is the CoM velocity minus omega x (R com_from_base); joints are position-controlled, so the measured
+    joint vector is the commanded one (non-controlled joints at the posture of ``SyntheticRobot``)."""
+    import time
+    from .pack import PACK_OFFSETS as PO
+    mpc, rb = loop.mpc, loop.robot
+    sel = list(mpc.sel)
+    i = int(instance)
+    f = lambda pk, name: pk[PO[name][0]:PO[name][0] + PO[name][1], i].copy()
+    log = {k: [] for k in LOG_KEYS}
+    # initial rows of the series the driver seeds before its loop (:73-92)
+    pk = loop.pack()
+    refs = mpc.get_references()
+    log["CoMPosition"].append(f(pk, "p_com"))
+    log["CoMPosition_desired"].append(refs["posCoMReference"][i])
+    log["base_orientation_desired"].append(refs["RPYReference"][i])
+    log["linear_momentum"].append(f(pk, "momentum_body")[:3])
+    log["angular_momentum"].append(f(pk, "momentum_body")[3:])
+    log["momentum_reference"].append(refs["momentumReference"][i])
+    q_full = np.array(rb.joint_pos0, float)
+    for k in range(int(n_ticks)):
+        t0 = time.perf_counter()
+        loop.run(1, use_graph=False)
+        out, status = mpc.get_output()
+        log["time_MPC"].append(time.perf_counter() - t0)
+        pk = loop.pack()
+        refs = mpc.get_references()
+        R = f(pk, "wRb").reshape(3, 3)
+        mass = f(pk, "mass")[0]
+        mom = f(pk, "momentum_body")
+        w = f(pk, "omega_world")
+        v_com = R @ mom[:3] / mass
+        v_base = v_com - np.cross(w, f(pk, "p_com") - f(pk, "base_pos"))
+        thrust = f(pk, "thrust")
+        A_body = f(pk, "A_mom_body").reshape(6, 4)
+        A_world = np.vstack([R @ A_body[:3], R @ A_body[3:]])          # Robot::getMatrixAmomJets() (world axes)
+        qm, qr = q_full.copy(), q_full.copy()
+        qm[sel] = f(pk, "q_cmd")
+        qr[sel] = out[i, L.OUT_JOINTS_REF:L.OUT_JOINTS_REF + 8]
+        log["CoMPosition"].append(f(pk, "p_com"))
+        log["CoMPosition_desired"].append(refs["posCoMReference"][i])
+        log["estimated_thrust"].append(thrust)
+        log["estimated_thrust_dot"].append(f(pk, "thrust_dot_est"))
+        log["thrust_desired"].append(out[i, L.OUT_THRUST:L.OUT_THRUST + 4].copy())
+        log["thrust_desired_dot"].append(out[i, L.OUT_THRUST_DOT:L.OUT_THRUST_DOT + 4].copy())
+        log["base_position"].append(f(pk, "base_pos"))
+        log["base_orientation"].append(f(pk, "rpy"))
+        log["base_orientation_desired"].append(refs["RPYReference"][i])
+        log["base_lin_vel"].append(v_base)
+        log["base_ang_vel"].append(w)
+        log["base_lin_vel_filtered"].append(v_base)
+        log["base_ang_vel_filtered"].append(w)
+        log["linear_momentum"].append(mom[:3])
+        log["angular_momentum"].append(mom[3:])
+        log["momentum_reference"].append(refs["momentumReference"][i])
+        log["alpha_gravity"].append(float(refs["alphaGravity"][i]))
+        log["joints_pos_meas"].append(qm)
+        log["joints_pos_ref"].append(qr)
+        log["time_controller"].append(period_mpc * (k + 1))
+        log["throttle"].append(out[i, L.OUT_THROTTLE:L.OUT_THROTTLE + 4].copy())
+        log["mom_dot"].append(A_world @ thrust)
+    data = {k: np.asarray(v, float) for k, v in log.items()}
+    data["qp_status"] = np.asarray(status[i])       # extra: status of the last tick
+    return data
+
+
+def save_log_mat(path: str, rec, instance: int = 0, period_mpc: float = 0.005, record_every: int = 1) -> dict:
+    """Write a log in the layout of the reference driver's end-of-run file (``scipy.io.savemat`` of the dictionary of
+    src/variable_sampling_mpc.py:163-194).  ``rec``: the dict of ``run_logged`` (all 23 series) or the (n_rec, B, 16) record
+    array of ``BatchedRollout.run`` (the six series the device loop records by itself)."""
     import scipy.io
+    if isinstance(rec, dict):
+        missing = [k for k in LOG_KEYS if k not in rec]
+        if missing:
+            raise ValueError(f"log dictionary lacks {missing}")
+        scipy.io.savemat(path, rec)
+        return rec
     r = np.asarray(rec)[:, instance, :]
     data = {
         "CoMPosition": r[:, 0:3],

@@ -151,6 +151,19 @@ def test_mat73_reader_on_npz_equivalent(tmp_path):
     assert t["alpha_fps"] == 10 and t["traj_fps"] == 10 and t["alphaGravity"].shape == (1, 351)
 
 
+def test_mat73_reader_on_a_committed_v73_file():
+    """mat73.loadmat73 on a MAT-v7.3 (HDF5) file: tests/golden/alphaGravity_v73.mat is the reference's own
+    src/trajectories/alphaGravity.mat (5 kB, byte copy made by tests/golden/make_fixtures.py — h5py is not in this image, so
+    no v7.3 file can be generated in-test); what the reader returns must equal the converted fixture the GPU tests use."""
+    m73, cfg = pkg("mat73"), pkg("config")
+    d = m73.loadmat73(os.path.join(ROOT, "tests", "golden", "alphaGravity_v73.mat"))
+    t = cfg.load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+    assert int(d["fps"][0, 0]) == t["alpha_fps"]
+    assert d["alphaGravity"].shape == t["alphaGravity"].shape and np.array_equal(d["alphaGravity"], t["alphaGravity"])
+    with pytest.raises(ValueError):
+        m73.Mat73(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))      # not an HDF5 file
+
+
 def test_rollout_log_writer_roundtrip(tmp_path):
     """The rollout record is written with the reference driver's log keys (src/variable_sampling_mpc.py:163-194)."""
     import scipy.io

@@ -153,3 +153,41 @@ def test_device_rollout_long_horizon_matches_oracle_loop():
     assert worst_p < 1e-7 and worst_a < 1e-7, (worst_p, worst_a)
     assert worst_t < 1e-6 and worst_u < 1e-6, (worst_t, worst_u)
     mpc.close()
+
+
+@pytest.mark.gpu
+def test_logged_rollout_writes_the_reference_log_keys(tmp_path):
+    """rollout.run_logged + save_log_mat: the 23 series of the reference driver's end-of-run .mat file
+    (src/variable_sampling_mpc.py:163-186), consistent with the device loop's own record of the same loop."""
+    import scipy.io
+    syn, bat, ro = pkg("synthetic"), pkg("batched"), pkg("rollout")
+    B, n = 2, 25
+    traj = dict(oracle_trajectories_to_product(load_trajectories()))
+    traj["alphaGravity"] = np.ones_like(traj["alphaGravity"])
+    st = syn.make_states(B, seed=77, perturbed=True, near_bound_fraction=0.0)
+    runs = []
+    for logged in (True, False):
+        mpc = bat.BatchedVSMPC(B, None, traj)
+        loop = ro.BatchedRollout(mpc, syn.SyntheticRobot())
+        loop.init(st)
+        runs.append(ro.run_logged(loop, n, instance=1) if logged else loop.run(n, record_every=1, use_graph=False))
+        mpc.close()
+    log, rec = runs
+    f = str(tmp_path / "log.mat")
+    ro.save_log_mat(f, log)
+    d = scipy.io.loadmat(f)
+    assert all(k in d for k in ro.LOG_KEYS) and len(ro.LOG_KEYS) == 23
+    for k, cols, rows in (("CoMPosition", 3, n + 1), ("CoMPosition_desired", 3, n + 1), ("base_orientation_desired", 3, n + 1),
+                          ("linear_momentum", 3, n + 1), ("angular_momentum", 3, n + 1), ("momentum_reference", 6, n + 1),
+                          ("base_position", 3, n), ("base_orientation", 3, n), ("base_lin_vel", 3, n), ("base_ang_vel", 3, n),
+                          ("joints_pos_meas", 23, n), ("joints_pos_ref", 23, n), ("estimated_thrust", 4, n), ("thrust_desired", 4, n),
+                          ("thrust_desired_dot", 4, n), ("estimated_thrust_dot", 4, n), ("throttle", 4, n), ("mom_dot", 6, n)):
+        assert d[k].shape == (rows, cols), (k, d[k].shape)
+    assert d["alpha_gravity"].size == n and d["time_MPC"].size == n
+    assert np.allclose(d["time_controller"].ravel(), 0.005 * (1 + np.arange(n)))
+    # the same loop recorded by the device: CoM, attitude, thrust and throttle agree tick by tick
+    assert np.allclose(d["CoMPosition"][1:], rec[:, 1, 0:3], rtol=0, atol=1e-12)
+    assert np.allclose(d["base_orientation"], rec[:, 1, 3:6], rtol=0, atol=1e-12)
+    assert np.allclose(d["estimated_thrust"], rec[:, 1, 6:10], rtol=0, atol=1e-9)
+    # (the record's throttle is the one in effect during the plant steps, which the plant switches on its own schedule)
+    assert np.isfinite(d["throttle"]).all() and (d["throttle"] >= 0).all() and (d["throttle"] <= 100).all()
