@@ -427,8 +427,10 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     {
         // slots: concurrent fallback solves; a slot holds the dense [K | R] of one instance (9 MB at the reference horizon)
         const size_t per = fallback_slot_doubles(g) * sizeof(double);
-        size_t slots = std::max<size_t>(2, std::min<size_t>(64, (size_t)B / 256));
-        slots = std::max<size_t>(1, std::min(slots, ((size_t)640 << 20) / per));
+        // one slot per 128 instances (0.2 % of a Monte Carlo sweep needs the fallback every tick: one round instead of three at
+        // 65 536 instances), at most 512 slots and 6 GB of the 180 GB
+        size_t slots = std::max<size_t>(2, std::min<size_t>(512, (size_t)B / 128));
+        slots = std::max<size_t>(1, std::min(slots, ((size_t)6 << 30) / per));
         slots = std::min(slots, (size_t)B);
         h->fb_slots = (int)slots;
         std::vector<int> pos(fallback_pos_ints(g));

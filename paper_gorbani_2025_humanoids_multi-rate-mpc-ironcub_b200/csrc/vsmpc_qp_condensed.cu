@@ -79,25 +79,34 @@ __device__ __forceinline__ void rp_publish(const double (&t)[CD_MAXW], double* _
 
 // one exchange pivot on index q (row q published in rowq): lane l < 24 owns row l of T in registers;
 // sgn = +1 if lane l is in the same class as q (both exchanged or both not), -1 otherwise: T[l][q] = sgn T[q][l].
-//   T'[q][q] = 1/d, T'[q][j] = -T[q][j]/d, T'[l][q] = T[l][q]/d, T'[l][j] = T[l][j] - T[l][q] T[q][j]/d
-__device__ __forceinline__ void rp_pivot(double (&t)[CD_MAXW], const double* __restrict__ rowq, int q, int lane, double sgn,
-                                         double dinv)
+// The pivot is applied as the rank-1 change  T' = T - (T[:, q] + e_q)(T[q, :] - e_q)' / d,  d = T[q][q]  — it gives
+// T'[q][q] = 1/d, T'[q][j] = -T[q][j]/d, T'[l][q] = T[l][q]/d and the Schur update of the rest in ONE uniform update of every
+// row: lane q only lowers its published diagonal by one (shared memory, indexed by q at run time, which registers cannot
+// be) and uses the multiplier (d + 1)/d.  The earlier form wrote row q / column q by case distinction, which cost 24
+// predicated register writes per pivot — three instructions each, more than the 24 FMAs of the update itself.  The rank-1
+// form is exact up to eps x max(d, 1/d): H_r is equilibrated to a unit diagonal first (the long-horizon kernel does the same).
+// Tried and rejected (profiles/r02_k2_experiments.md): two indices per step (block pivot; same time — the phase is bound by
+// instructions issued per index, not by round trips), row q by warp shuffles with a warp-uniform switch for the
+// run-time register index (slower: the switches compile to predicated chains).
+__device__ __forceinline__ bool rp_pivot(double (&t)[CD_MAXW], double* __restrict__ rowq, int q, int lane, double sgn)
 {
-    const double f = sgn * rowq[lane < CD_MAXW ? lane : 0] * dinv;
-    const bool isq = lane == q;
-    const double fm = isq ? dinv : f;          // multiplier of row q in this lane's row; lane q: t = 0 - (1/d) row
+    if (lane == q)
+        rowq[q] -= 1.0;
+    __syncwarp();
+    const double dm1 = rowq[q];
+    const double d = dm1 + 1.0;
+    const double dinv = __drcp_rn(d);
+    const double f = (lane == q) ? (d + 1.0) * dinv : sgn * rowq[lane < CD_MAXW ? lane : 0] * dinv;
     const double2* r2 = reinterpret_cast<const double2*>(rowq);
 #pragma unroll
     for (int j = 0; j < CD_MAXW / 2; ++j)
     {
         const double2 rr = r2[j];
-        t[2 * j] = fma(-fm, rr.x, isq ? 0.0 : t[2 * j]);
-        t[2 * j + 1] = fma(-fm, rr.y, isq ? 0.0 : t[2 * j + 1]);
+        t[2 * j] = fma(-f, rr.x, t[2 * j]);
+        t[2 * j + 1] = fma(-f, rr.y, t[2 * j + 1]);
     }
-    const double cq = isq ? dinv : f;          // entry of column q
-#pragma unroll
-    for (int j = 0; j < CD_MAXW; ++j)
-        asm("{ .reg .pred q; setp.eq.s32 q, %1, %2; @q mov.f64 %0, %3; }" : "+d"(t[j]) : "r"(q), "r"(j), "d"(cq));
+    __syncwarp();
+    return (d > 0.0) && (d < 1e300);
 }
 
 // ---- warp B --------------------------------------------------------------------------------------------------
@@ -496,6 +505,7 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     }
     cd_omega_downdate(c.ws, NJ * Nc, sm.Om, warp, lane);
     __syncthreads();
+    PHASE_CLK(13);
 
     // ---- warp B: reduced QP in the throttle variables + dual active set ---------------------------------------------
     double* gvec = sm.Hut;                 // gradient of the reduced QP
@@ -510,6 +520,7 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
         if (lane < nv)
             g += sm.Om[lane * NLO + AFFL];
         double h[CD_MAXW];
+        double hd = 1.0;       // diagonal entry of this lane's row
         const int blk = lane >> 2;
 #pragma unroll
         for (int j = 0; j < CD_MAXW; ++j)
@@ -521,6 +532,8 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                     v += cfg.w_t * ((blk > 0 ? 1.0 : 0.0) + (blk < cfg.nblk - 1 ? 1.0 : 0.0)) + (blk == 0 ? cfg.w_i : 0.0);
                 if ((j == lane - NT && blk > 0) || (j == lane + NT && blk < cfg.nblk - 1))
                     v -= cfg.w_t;
+                if (j == lane)
+                    hd = v;
             }
             h[j] = v;
         }
@@ -546,6 +559,27 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
             if (lane < NT)
                 g = 0.0;
         }
+        // equilibration to a unit diagonal, v = S v~ with S = diag(H_r)^-1/2 (pinned block and unused lanes: 1): the pivots
+        // stay O(1), which the rank-1 pivot form needs; bounds and gradient of the scaled variable per lane
+        const bool isvar = lane >= first && lane < nv;
+        const double S_e = (isvar && hd > 0.0 && hd < 1e300) ? rsqrt(hd) : 1.0;
+        const double iS_e = 1.0 / S_e;
+        double* ssm = sm.Hut + 2 * CD_MAXW;
+        if (lane < CD_MAXW)
+            ssm[lane] = S_e;
+        __syncwarp();
+        {
+            const double2* s2 = reinterpret_cast<const double2*>(ssm);
+#pragma unroll
+            for (int j = 0; j < CD_MAXW / 2; ++j)
+            {
+                const double2 sj = s2[j];
+                h[2 * j] *= S_e * sj.x;
+                h[2 * j + 1] *= S_e * sj.y;
+            }
+        }
+        g *= S_e;
+        const double lo_e = lo * iS_e, up_e = up * iS_e;
         if (lane < CD_MAXW)
             gvec[lane] = g;
         __syncwarp();
@@ -553,20 +587,15 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
         // In (outputs) = T (inputs) a pivot on q swaps input q and output q of y = H_r v; after all of them T = H_r^-1.
         // T is symmetric within the exchanged set and within the rest, antisymmetric across: T[l][q] = +- T[q][l], so the
         // published row q gives every lane its entry of column q without indexing its registers by q.
-        const bool isvar = lane >= first && lane < nv;
-        bool inF = false;      // exchanged already
-        bool okG = true;
+        bool okG = __all_sync(0xffffffffu, isvar ? (hd > 0.0 && hd < 1e300) : true);
 #pragma unroll 1
         for (int p = first; p < nv; ++p)
         {
             rp_publish(h, rowq, lane == p);
-            const double d = rowq[p];
-            okG = okG && (d > 0.0) && isfinite(d);
-            rp_pivot(h, rowq, p, lane, inF ? -1.0 : 1.0, 1.0 / d);
-            if (lane == p)
-                inF = true;
-            __syncwarp();
+            // exchanged already: first .. p - 1
+            okG = rp_pivot(h, rowq, p, lane, (lane >= first && lane < p) ? -1.0 : 1.0) && okG;
         }
+        PHASE_CLK(14);
         double v_e = 0.0;
         if (lane < CD_MAXW)
         {
@@ -595,12 +624,12 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
         while (!fail)
         {
             int p_idx;
-            const double best = warp_max_nonneg((isvar && act == 0) ? fmax(fmax(v_e - up, lo - v_e), 0.0) : 0.0, p_idx);
+            // violation measured in the unscaled variable; the iteration itself runs on the scaled box QP (bounds per lane)
+            const double best = warp_max_nonneg((isvar && act == 0) ? S_e * fmax(fmax(v_e - up_e, lo_e - v_e), 0.0) : 0.0, p_idx);
             if (!(best > tol))
                 break;
-            const double v_p0 = __shfl_sync(0xffffffffu, v_e, p_idx);
-            const double s = (v_p0 - up > lo - v_p0) ? 1.0 : -1.0;
-            const double bound = s > 0 ? up : lo;
+            const double s = __shfl_sync(0xffffffffu, (v_e - up_e > lo_e - v_e) ? 1.0 : -1.0, p_idx);
+            const double bound = __shfl_sync(0xffffffffu, (v_e - up_e > lo_e - v_e) ? up_e : lo_e, p_idx);
             double lam_p = 0.0;
             while (true)
             {
@@ -618,8 +647,7 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 int drop;
                 const double t1 = warp_min_nonneg((act != 0 && r_e > 0.0) ? fmax(lam_e, 0.0) / r_e : INFINITY, drop);
                 const double v_p = __shfl_sync(0xffffffffu, v_e, p_idx);
-                const double izp = 1.0 / zp;
-                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) * izp : INFINITY;
+                const double t2 = (zp > 1e-300) ? (s * v_p - s * bound) / zp : INFINITY;
                 const double tt = fmin(t1, t2);
                 if (!isfinite(tt) || !isfinite(zp))
                 {
@@ -638,7 +666,7 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 if (t2 <= t1)
                 {
                     // full step: p becomes active (row p is published already)
-                    rp_pivot(h, rowq, p_idx, lane, act == 0 ? 1.0 : -1.0, izp);
+                    rp_pivot(h, rowq, p_idx, lane, act == 0 ? 1.0 : -1.0);
                     if (lane == p_idx)
                     {
                         act = s > 0 ? 1 : -1;
@@ -651,14 +679,12 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 // blocked step: the blocking bound leaves the working set
                 __syncwarp();
                 rp_publish(h, rowq, lane == drop);
-                const double dd = rowq[drop];
-                if (!(dd > 0.0) || !isfinite(dd))
+                if (!rp_pivot(h, rowq, drop, lane, act != 0 ? 1.0 : -1.0))
                 {
                     stat = VSMPC_STATUS_NUMERICAL;
                     fail = true;
                     break;
                 }
-                rp_pivot(h, rowq, drop, lane, act != 0 ? 1.0 : -1.0, 1.0 / dd);
                 if (lane == drop)
                 {
                     act = 0;
@@ -667,9 +693,8 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
                 __syncwarp();
             }
         }
-        // theta*: throttle variables (active ones exactly on their bound), affine 1
-        if (act != 0)
-            v_e = act > 0 ? up : lo;
+        // theta*: throttle variables back in their own scale (active ones exactly on their bound), affine 1
+        v_e = act != 0 ? (act > 0 ? up : lo) : S_e * v_e;
         // a NaN iterate never shows up as a violated bound: gate it here (the status holds the outputs)
         if (stat == VSMPC_STATUS_SOLVED && __any_sync(0xffffffffu, lane < nv && !isfinite(v_e)))
             stat = VSMPC_STATUS_NUMERICAL;

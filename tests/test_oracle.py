@@ -349,3 +349,19 @@ def test_kkt_certificate_helper_on_oracle_solutions():
     z_bad[:, 26 * 18 + 96 + 20] += 1e-3
     kb = kkt_certificate(z_bad, arr(As), arr(BJs), arr(BTs), dt, arr(qs), arr(ls), arr(us), Pd, w_t)
     assert max(kb["complementarity"].max(), kb["dual_sign"].max()) > 1e-6
+
+
+def test_block_exchange_pivot_equals_two_single_pivots():
+    """tools/condensed_model.block_exchange_pivot (the two-indices-per-step inverse of the reference-horizon kernel)."""
+    from condensed_model import block_exchange_pivot, exchange_pivot
+    g = np.random.default_rng(12)
+    for n in (8, 20, 24):
+        A = g.normal(size=(n, n))
+        H = A @ A.T + n * np.eye(n)
+        T1, T2 = H.copy(), H.copy()
+        for p in range(0, n, 2):
+            exchange_pivot(T1, p)
+            exchange_pivot(T1, p + 1)
+            assert block_exchange_pivot(T2, p, p + 1) > 0
+            assert np.abs(T1 - T2).max() <= 1e-12 * np.abs(T1).max()
+        assert np.abs(T2 - np.linalg.inv(H)).max() <= 1e-12 * np.abs(T2).max()

@@ -45,6 +45,21 @@ def exchange_pivot(T, q):
     return d
 
 
+def block_exchange_pivot(T, q1, q2):
+    """Exchange pivot on two indices at once (both in the same class): T' = [[D^-1, -D^-1 V], [U D^-1, T - U D^-1 V]] with
+    D = T[Q, Q].  Equal to exchange_pivot(T, q1) followed by exchange_pivot(T, q2); the inverse phase of
+    csrc/vsmpc_qp_condensed.cu pivots two indices per step this way (half the publish / read / reciprocal round trips)."""
+    Q = [q1, q2]
+    D = T[np.ix_(Q, Q)].copy()
+    Di = np.linalg.inv(D)
+    U, V = T[:, Q].copy(), T[Q, :].copy()
+    T -= U @ Di @ V
+    T[Q, :] = -Di @ V
+    T[:, Q] = U @ Di
+    T[np.ix_(Q, Q)] = Di
+    return np.linalg.det(D)
+
+
 def _dual_pivot_loop(T, vv, act, lam, lo, up, max_iter, tol):
     """Goldfarb-Idnani dual iterations on the principal pivot transform, from any S-pair: T = transform of H over the free
     set {act == 0}, vv = minimiser of the sub-problem with the working set held at its bounds, lam >= 0 on the working set.
