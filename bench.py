@@ -52,38 +52,43 @@ def flops_per_solve(nx, nu, N, n_f, n_s):
     return F_l + n_f * F_f + n_s * F_s, dict(F_f=F_f, F_s=F_s, F_l=F_l)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs.  The sampler is a child process writing to
+    a file that is parsed afterwards: a Python reader thread would take the GIL away from the host loop being timed."""
 
     def __init__(self, gpu_index: int):
-        super().__init__(daemon=True)
+        import tempfile
         self.gpu = gpu_index
         self.samples = []
-        self._stop = threading.Event()
         self.proc = None
+        self.path = tempfile.mktemp(prefix="vsmpc_clocks_", suffix=".csv")
 
-    def run(self):
+    def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
+            self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self._stop.is_set():
-                    break
-                self.samples.append([s.strip() for s in line.split(",")])
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
-            pass
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
         if self.proc:
             try:
                 self.proc.terminate()
+                self.proc.wait(timeout=5)
             except Exception:
                 pass
+        try:
+            self.out.close()
+            with open(self.path) as f:
+                self.samples = [[x.strip() for x in line.split(",")] for line in f if line.strip()]
+            os.remove(self.path)
+        except Exception:
+            pass
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -168,6 +173,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # host buffers of the end-to-end leg, built BEFORE any timed leg: generating them takes seconds of host time, and a GPU
+    # left idle that long drops its clocks — the e2e leg would then be timed while they ramp up again
+    pack_bytes = packs[0].nbytes
+    n_e2e = max(n_sets, int(np.ceil(140e6 / pack_bytes)))
+    syn, packm = pkg("synthetic"), pkg("pack")
+    h_e2e = list(h_packs)
+    for j in range(n_sets, n_e2e):
+        h_e2e.append(torch.from_numpy(packm.build_pack(
+            syn.make_states(B, seed=20251002 + rank + 7919 * j, perturbed=True))).pin_memory())
+    h_out2 = [torch.empty((B, L.OUT_DOUBLES), dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_status2 = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    # the first DMA out of a freshly pinned buffer is slower than the following ones (its pages are mapped for the device on
+    # first use: +17 us per 2.9 MB pack, profiles/r02z_e2e.txt): touch every host buffer once, as part of allocating it
+    scratch = torch.empty_like(d_packs[0])
+    for t in h_e2e:
+        scratch.copy_(t, non_blocking=True)
+    torch.cuda.synchronize()
+    del scratch
+
     # ---------------- device-resident leg -------------------------------------------------------------
     for j in range(Wm):
         step_dev(j)
@@ -199,16 +223,6 @@ def run_ours(args):
     # stream) -> vsmpc_solve_async -> vsmpc_get_output_async (D2H of the step's 54-double rows + status) and the host
     # waits for the result of the step before: two steps in flight, the copy of step j+1 overlaps the QP kernel of
     # step j.  The host packs cycle through more bytes than the 126 MB L2 (no flush kernel in this loop).
-    pack_bytes = packs[0].nbytes
-    n_e2e = max(n_sets, int(np.ceil(140e6 / pack_bytes)))
-    syn, packm = pkg("synthetic"), pkg("pack")
-    h_e2e = list(h_packs)
-    for j in range(n_sets, n_e2e):
-        h_e2e.append(torch.from_numpy(packm.build_pack(
-            syn.make_states(B, seed=20251002 + rank + 7919 * j, perturbed=True))).pin_memory())
-    h_out2 = [torch.empty((B, L.OUT_DOUBLES), dtype=torch.float64).pin_memory() for _ in range(2)]
-    h_status2 = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
-
     def e2e_loop(n):
         prev = None
         for j in range(n):

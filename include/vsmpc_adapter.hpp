@@ -190,6 +190,19 @@ public:
     bool getQPVectors(double* q, double* l, double* u) { return check(vsmpc_get_qp_vectors(m_h, q, l, u)); }
     bool setFullSolution(bool on) { return check(vsmpc_set_full_solution(m_h, on ? 1 : 0)); }
     bool getSolution(double* z) { return check(vsmpc_get_full_solution(m_h, z)); }
+    // per-instance model parameters / joint limits (BASELINE configs[4]): double[19][B]; double[8][B] each [rad]
+    bool setInstanceParams(const double* table) { return check(vsmpc_set_instance_params(m_h, table)); }
+    bool setJointLimits(const double* qMin, const double* qMax) { return check(vsmpc_set_joint_limits(m_h, qMin, qMax)); }
+    bool setWarmStart(bool on) { return check(vsmpc_set_warm_start(m_h, on ? 1 : 0)); }
+    // robot states instead of packs (Robot::setState on the device, UT/src/Robot.cpp:212-332): the kinematic tree once, then
+    // double[kinStateDoubles()][B] per tick (VSMPC_KS_* rows)
+    bool setKinModel(const vsmpc_kin_model& model) { return check(vsmpc_set_kin_model(m_h, &model)); }
+    int kinStateDoubles() const { return vsmpc_kin_state_doubles(m_h); }
+    bool configureKinematics(const double* kinState, const int* phase0 = nullptr)
+    {
+        return check(vsmpc_configure_kinematics(m_h, kinState, phase0));
+    }
+    bool updateKinematics(const double* kinState) { return check(vsmpc_set_state_kinematics(m_h, kinState)); }
     int getNOptimizationVariables() const { return vsmpc_n_var(m_h); }
     int getNConstraints() const { return vsmpc_n_constraints(m_h); }
     int nInstances() const { return m_B; }

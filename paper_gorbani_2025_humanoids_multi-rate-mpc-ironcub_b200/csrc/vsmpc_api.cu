@@ -215,6 +215,17 @@ __global__ void seed_outputs_kernel(int B, const double* __restrict__ jpos, cons
     status[i] = VSMPC_STATUS_SOLVED;
 }
 
+// snapshot of the output rows + status for the asynchronous read-back: one launch instead of two device-to-device copies
+__global__ void snapshot_outputs_kernel(size_t n_rows_doubles, int B, const double* __restrict__ rows, const int* __restrict__ status,
+                                        double* __restrict__ rows_out, int* __restrict__ status_out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_rows_doubles / 2; e += stride)
+        reinterpret_cast<double2*>(rows_out)[e] = reinterpret_cast<const double2*>(rows)[e];
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)B; e += stride)
+        status_out[e] = status[e];
+}
+
 static void drop_tick_graph(vsmpc_handle* h)
 { // the captured tick bakes the kernel arguments in (per-instance table, full-solution flag, jet-NN mode)
     if (h->tick_graph)
@@ -863,10 +874,13 @@ int vsmpc_get_output_async(vsmpc_handle* h, double* out_rows_host, int* status_h
             CK(dalloc(&h->d_status_stage[e], (size_t)h->B));
         }
     CK(cudaStreamWaitEvent(h->stream, h->ev_out[q], 0));   // the read-back that used this staging buffer two calls ago
-    if (out_rows_host)
-        CK(cudaMemcpyAsync(h->d_out_stage[q], h->d_out, nb_out, cudaMemcpyDeviceToDevice, h->stream));
-    if (status_host)
-        CK(cudaMemcpyAsync(h->d_status_stage[q], h->d_status, nb_st, cudaMemcpyDeviceToDevice, h->stream));
+    {
+        const int threads = 256;
+        const int blocks = (int)std::min<size_t>(592, (nb_out / 16 + threads - 1) / threads);
+        snapshot_outputs_kernel<<<blocks, threads, 0, h->stream>>>(nb_out / 8, h->B, h->d_out, h->d_status, h->d_out_stage[q],
+                                                                   h->d_status_stage[q]);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(h->ev_solved, h->stream));
     CK(cudaStreamWaitEvent(h->out_stream, h->ev_solved, 0));
     if (out_rows_host)

@@ -29,7 +29,8 @@
 namespace vsmpc
 {
 
-constexpr int FB_THREADS = 256;
+constexpr int FB_THREADS = 512;   // 16 warps: the rank-1 updates of a column are spread over the rows of the band window
+constexpr int FB_MAXBOX = 256;    // boxed variables (throttle + joint increments with the joint-limit rows)
 constexpr int FB_MAXROWS = 160;   // band window + border rows eliminated per column (bw + border + slack)
 
 struct FbLayout
@@ -134,7 +135,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
     const DeviceConfig& cfg = cfgv;
     __shared__ double A[NX * NX], BJ[NX * NJ], BT[NX * NT], cv[NX];
     __shared__ double prow[FB_MAXROWS * 3 + 256];   // pivot row cache: band window (<= 2 bw + 1) + border + right-hand sides
-    __shared__ double vbuf[FB_THREADS], cbuf[FB_THREADS], rbuf[FB_THREADS];   // active set: one boxed variable per thread
+    __shared__ double vbuf[FB_MAXBOX], cbuf[FB_MAXBOX], rbuf[FB_MAXBOX];   // active set: one boxed variable per thread
     __shared__ double lmul[FB_MAXROWS];
     __shared__ int lrow[FB_MAXROWS];
     __shared__ double red_v[FB_THREADS / 32];
@@ -324,11 +325,23 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
                 if (r < 0)
                     continue;
                 const double l = lmul[e];
-                double* row = M + (size_t)r * ld;
-                for (int q = lane; q < nct; q += 32)
+                double* __restrict__ row = M + (size_t)r * ld;
+                // four columns per lane in flight: the loads of a row are independent, the matrix lives in L2 / HBM
+                for (int q0 = lane; q0 < nct; q0 += 128)
                 {
-                    const int c = q < nc1 ? k + 1 + q : c2s + (q - nc1);
-                    row[c] = fma(-l, prow[q], row[c]);
+                    double v[4];
+                    int cc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        const int q = q0 + 32 * u;
+                        cc[u] = q < nct ? (q < nc1 ? k + 1 + q : c2s + (q - nc1)) : -1;
+                        v[u] = cc[u] >= 0 ? row[cc[u]] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (cc[u] >= 0)
+                            row[cc[u]] = fma(-l, prow[q0 + 32 * u], v[u]);
                 }
             }
             __syncthreads();
@@ -588,7 +601,7 @@ bool fallback_supported(const DeviceConfig& cfg)
     const FallbackPlan P = fb_plan(cfg);
     // the pivot-row cache and the per-thread active set bound the sizes (nv <= 160: up to 40 throttle blocks)
     return P.L.bw + (P.L.n - P.L.nb) + 8 <= FB_MAXROWS
-           && 2 * P.L.bw + 1 + (P.L.n - P.L.nb) + 1 + P.L.nbox <= FB_MAXROWS * 3 + 256 && P.L.nbox <= FB_THREADS;
+           && 2 * P.L.bw + 1 + (P.L.n - P.L.nb) + 1 + P.L.nbox <= FB_MAXROWS * 3 + 256 && P.L.nbox <= FB_MAXBOX && P.L.nbox <= FB_THREADS;
 }
 
 size_t fallback_slot_doubles(const DeviceConfig& cfg) { return fb_plan(cfg).slot_doubles; }
