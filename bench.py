@@ -263,8 +263,9 @@ def run_ours(args):
     if rank == 0 and args.rollout_ticks > 0:
         closed = closed_loop_leg(bat, B, local_rank, stream, args.rollout_ticks, args.solver)
     # ---------------- the other BASELINE configurations, every rank (skipped by --no-extras / --horizon) ------------
-    gather = long_h = monte = None
+    gather = long_h = monte = e2e_kin = None
     if not args.no_extras and not params:
+        e2e_kin = e2e_kinematics_leg(bat, L, B, world, rank, local_rank, stream, dev, K, Wm)
         gather = gather_leg(mpc, B, world, dev, stream, h_out, h_status)
         long_h = long_horizon_leg(bat, lib, d_packs, nom_pack, jp, phase0, B, local_rank, stream, flush, world, dev, args.solver)
         monte = monte_carlo_leg(bat, args.mc_instances, args.mc_ticks, rank, world, local_rank, stream, dev)
@@ -333,7 +334,7 @@ def run_ours(args):
         "gpu_launches": 2 * K,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "single_solve_latency": latency, "closed_loop": closed,
-        "monte_carlo": monte, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
+        "e2e_kinematics": e2e_kin, "monte_carlo": monte, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
         "solved_fraction": solved_frac, "wall_ms_timed_loop": t_wall * 1e3,
     }
     print(json.dumps(line))
@@ -380,6 +381,64 @@ def gather_leg(mpc, B, world, dev, stream, h_out, h_status, reps=20):
     res["what"] = ("nccl_all_gather_ms: all_gather_into_tensor of rows + status from the library's device buffers on "
                    "every rank (world > 1 only); pinned_d2h_ms: vsmpc_get_output into pinned host memory per rank")
     return res
+
+
+def e2e_kinematics_leg(bat, L, B, world, rank, device, stream, dev, K, Wm):
+    """End to end with ROBOT STATES as the host input: the kinematics kernel builds the pack on the device
+    (Robot::setState, UT/src/Robot.cpp:212-332), so a step uploads 92 doubles per instance instead of 359.  Same pipelined
+    call sequence as the e2e leg: vsmpc_set_state_kinematics -> vsmpc_solve_async -> vsmpc_get_output_async."""
+    import torch
+    kin, syn = pkg("kinematics"), pkg("synthetic")
+    model = kin.synthetic_humanoid()
+    nd = model["n_dof"]
+    q0 = syn.SyntheticRobot().joint_pos0[:nd]
+    hover = float(np.sum(model["mass"])) * 9.81 / 4.0
+
+    def states(seed, perturbed):
+        g = np.random.default_rng(seed)
+        z = (lambda *s: g.normal(0, 1.0, (B,) + s)) if perturbed else (lambda *s: np.zeros((B,) + s))
+        return dict(wRb=syn.rpy_to_R(0.05 * z(3)), base_pos=np.array([0.0, 0.0, 1.0]) + 0.05 * z(3), base_lin_vel=0.05 * z(3),
+                    omega_world=0.1 * z(3), q=q0[None] + 0.02 * z(nd), qd=0.05 * z(nd), thrust=hover + 8.0 * z(4),
+                    thrust_dot_est=20.0 * z(4), thrust_des=hover + 8.0 * z(4), thrust_dot_des=10.0 * z(4),
+                    throttle_prev=60.0 + 10.0 * z(4), q_cmd=q0[None] + 0.02 * z(nd))
+
+    mpc = bat.BatchedVSMPC(B, None, load_traj(), device=device)
+    mpc.set_stream(stream.cuda_stream)
+    fe = kin.KinematicsFrontEnd(mpc, model)
+    fe.configure(kin.build_kin_state(model, states(1, False)), (np.arange(B) % 20).astype(np.int32))
+    n_sets = 8
+    h_ks = [torch.from_numpy(kin.build_kin_state(model, states(20251002 + rank + 31 * j, True))).pin_memory() for j in range(n_sets)]
+    scratch = torch.empty_like(h_ks[0], device=dev)
+    for t in h_ks:
+        scratch.copy_(t, non_blocking=True)
+    h_out = [torch.empty((B, L.OUT_DOUBLES), dtype=torch.float64).pin_memory() for _ in range(2)]
+    h_st = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    views = [t.numpy() for t in h_ks]
+
+    def loop(n):
+        prev = None
+        for j in range(n):
+            fe.update(views[j % n_sets])
+            mpc.solve_async()
+            t = mpc.get_output_async(h_out[j & 1].data_ptr(), h_st[j & 1].data_ptr())
+            if prev is not None:
+                mpc.wait_output(prev)
+            prev = t
+        mpc.wait_output(prev)
+
+    loop(Wm)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loop(K)
+    torch.cuda.synchronize()
+    ms = _max_over_ranks([(time.perf_counter() - t0) * 1e3], world, dev)[0]
+    solved = float((h_st[(K - 1) & 1].numpy() == 0).mean())
+    mpc.close()
+    return {"value": world * B * K / (ms * 1e-3), "unit": "solves/s", "ms_per_step": ms / K,
+            "h2d_bytes_per_step": int(h_ks[0].numel() * 8), "d2h_bytes_per_step": int(B * (L.OUT_DOUBLES * 8 + 4)),
+            "gpu_launches_per_step": 3, "solved_fraction_last_step": solved,
+            "what": "robot states (base pose and twist, 23 joint positions and velocities, 28 QPInput scalars: 92 doubles per "
+                    "instance) from pinned host memory; kinematics kernel + linearise + QP on the device; synthetic 24-link tree"}
 
 
 def long_horizon_leg(bat, lib, d_packs, nom_pack, jp, phase0, B, device, stream, flush, world, dev, solver, steps=10):

@@ -173,7 +173,13 @@ int vsmpc_set_warm_start(vsmpc_handle* h, int enable);
 /* tests: overwrite the stored working sets, signed char[B][4 * throttle blocks] (+1 upper bound, -1 lower bound, 0 free) */
 int vsmpc_debug_set_working_set(vsmpc_handle* h, const signed char* working_set_host);
 
-/* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel. */
+/* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel.
+ * Asynchronous: the call returns once the copy and the kernel are ENQUEUED (copy on the handle's own copy stream into one of
+ * two staging buffers, so that it overlaps the QP kernel of the tick before).  From pinned host memory the copy itself is
+ * still in flight when the call returns: pack_host must stay untouched until vsmpc_wait / vsmpc_wait_output / a blocking
+ * getter of THIS tick has returned (pageable memory is staged by the driver before the call returns).  A handle is driven by
+ * one host thread; vsmpc_set_stream between vsmpc_set_state and vsmpc_solve keeps the order (the new stream waits for the
+ * old one). */
 int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);
 /* same, pack already resident on the handle's GPU */
 int vsmpc_set_state_device(vsmpc_handle* h, const double* pack_dev);

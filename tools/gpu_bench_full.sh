@@ -10,6 +10,6 @@ import json
 d=json.loads(open("$O/${TAG}_bench.json").read().strip().splitlines()[-1])
 r=d["roofline"]
 print("value %.3f M/s e2e %.3f M/s blocking %.3f M/s k2 %.1f us k1 %.1f us frac %.3f" % (d["value"]/1e6, d["e2e"]["value"]/1e6, d["e2e"]["blocking_value"]/1e6, r["kernel_ms_per_launch"]*1e3, r["linearise_ms_per_launch"]*1e3, r["frac"]))
-for k in ("gather","long_horizon","monte_carlo","closed_loop","single_solve_latency","cpu_baseline"):
+for k in ("e2e_kinematics","gather","long_horizon","monte_carlo","closed_loop","single_solve_latency","cpu_baseline"):
     print(k, json.dumps(d.get(k))[:900])
 PY
