@@ -20,6 +20,8 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"]
 if os.environ.get("VSMPC_PHASE_CLOCKS"):      # development build: per-phase clock stamps in the condensed kernel
     NVCC_FLAGS.append("-DVSMPC_PHASE_CLOCKS")
+if os.environ.get("VSMPC_FB_CLOCKS"):         # development build: the fallback kernel prints its phase times
+    NVCC_FLAGS.append("-DVSMPC_FB_CLOCKS")
 
 
 def _digest() -> str:

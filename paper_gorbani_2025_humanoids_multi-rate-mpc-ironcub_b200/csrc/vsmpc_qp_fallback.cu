@@ -22,6 +22,7 @@
 // z = z_unc - sum_a s_a lam_a K^-1 e_a.
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <vector>
 
 #include "vsmpc_common.cuh"
@@ -31,7 +32,7 @@ namespace vsmpc
 
 constexpr int FB_THREADS = 512;   // 16 warps: the rank-1 updates of a column are spread over the rows of the band window
 constexpr int FB_MAXBOX = 256;    // boxed variables (throttle + joint increments with the joint-limit rows)
-constexpr int FB_MAXROWS = 160;   // band window + border rows eliminated per column (bw + border + slack)
+constexpr size_t FB_WINDOW_LIMIT = 200 * 1024;   // dynamic shared memory for the elimination window (227 KB per CTA on sm_100, ~15 KB static)
 
 struct FbLayout
 {
@@ -130,14 +131,12 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
                    const int* __restrict__ fb_list, const int* __restrict__ fb_count, const int* __restrict__ pos,
                    double* __restrict__ scratch, size_t slot_doubles, double* __restrict__ z_all, double* __restrict__ st,
                    double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
-                   int* __restrict__ n_solve, int* __restrict__ n_pivot, int want_z)
+                   int* __restrict__ n_solve, int* __restrict__ n_pivot, int want_z, int use_window)
 {
     const DeviceConfig& cfg = cfgv;
     __shared__ double A[NX * NX], BJ[NX * NJ], BT[NX * NT], cv[NX];
-    __shared__ double prow[FB_MAXROWS * 3 + 256];   // pivot row cache: band window (<= 2 bw + 1) + border + right-hand sides
+    extern __shared__ double fb_dyn[];               // the sliding elimination window, (bw + 1 + border) x (2 bw + 1 + border + rhs)
     __shared__ double vbuf[FB_MAXBOX], cbuf[FB_MAXBOX], rbuf[FB_MAXBOX];   // active set: one boxed variable per thread
-    __shared__ double lmul[FB_MAXROWS];
-    __shared__ int lrow[FB_MAXROWS];
     __shared__ double red_v[FB_THREADS / 32];
     __shared__ int red_i[FB_THREADS / 32];
     __shared__ double s_val[4];
@@ -154,6 +153,12 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
     const int* pmu = pos + L.o_mu;
     const int* ppin = pos + L.o_pin;
 
+#ifdef VSMPC_FB_CLOCKS
+#define FBCLK(name) do { if (tid == 0 && blockIdx.x == 0) { const long long t__ = clock64(); printf("fallback %-28s %10lld cycles\n", name, t__ - fbt0); fbt0 = t__; } } while (0)
+    long long fbt0 = clock64();
+#else
+#define FBCLK(name) do { } while (0)
+#endif
     for (int li = blockIdx.x; li < count; li += gridDim.x)
     {
         const int inst = fb_list[li];
@@ -251,129 +256,411 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
                 M[(size_t)ppin[tid] * ld + ppin[tid]] = 1.0;
         }
         __syncthreads();
-        // ---- elimination with row pivoting inside the band window -------------------------------------------------------
+        FBCLK("zero + assemble");
+        // ---- elimination with row pivoting inside the band window ----------------------------------------------------------
+        // use_window: the window lives in SHARED memory — rows k .. k + bw of the band part and the border rows, columns
+        // k .. k + 2 bw of the band part (circular slots c mod (2 bw + 1)), the border columns and the right-hand sides: 85 x 175
+        // doubles at the reference horizon.  Per column: every warp finds the pivot by itself (no block reduction), updates
+        // its rows against the pivot row where it lies (row interchanges are entries of a slot map, not copies), one barrier;
+        // then the finished row goes to global memory for the back-substitution and the next band row / column (original
+        // data, not touched so far, prefetched at the start of the step) slides into the freed slot, second barrier.
+        // Otherwise (window larger than the shared memory: joint-limit rows on a long horizon) the matrix is updated in global
+        // memory.  profiles/r02_fallback.md has the times of the versions.
         bool ok = true;
-        for (int k = 0; k < n && ok; ++k)
+        if (use_window)
         {
-            const int hi = k < nb ? min(k + bw, nb - 1) : n - 1;
-            // pivot: largest |M[r][k]|, r in [k, hi]
-            double best = -1.0;
-            int arg = k;
-            for (int r = k + tid; r <= hi; r += FB_THREADS)
+            const int WB = 2 * bw + 1, RB = bw + 1, nbord = n - nb;
+            const int wcols = WB + nbord + nrhs;            // column slots in use
+            const int WCp = (WB + nbord + 1 + L.nbox) | 1;  // leading dimension (odd), sized for the largest right-hand side
+            double* W = fb_dyn;
+            int* smap = reinterpret_cast<int*>(fb_dyn + (size_t)(RB + nbord) * WCp);   // physical slot of band row r: smap[r % RB]
+            // initial window: band rows 0 .. bw, border rows; band columns 0 .. 2 bw
+            for (int e = tid; e < (RB + nbord) * wcols; e += FB_THREADS)
             {
-                const double a = fabs(M[(size_t)r * ld + k]);
-                if (a > best) { best = a; arg = r; }
+                const int rs = e / wcols, cs = e - rs * wcols;
+                const int r = rs < RB ? rs : nb + (rs - RB);
+                const int c = cs < WB ? cs : nb + (cs - WB);
+                W[rs * WCp + cs] = ((cs >= WB || c < nb) && (rs >= RB || r < nb)) ? M[(size_t)r * ld + c] : 0.0;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-            }
-            if (lane == 0) { red_v[warp] = best; red_i[warp] = arg; }
+            if (tid < RB)
+                smap[tid] = tid;
             __syncthreads();
-            best = red_v[0]; arg = red_i[0];
-            for (int w = 1; w < FB_THREADS / 32; ++w)
-                if (red_v[w] > best || (red_v[w] == best && red_i[w] < arg)) { best = red_v[w]; arg = red_i[w]; }
-            if (!(best > 0.0) || !isfinite(best))
+#ifdef VSMPC_FB_CLOCKS
+            long long cA = 0, cB = 0, cC = 0, cD = 0, ct = clock64();
+#define FBSUB(acc) do { const long long t__ = clock64(); acc += t__ - ct; ct = t__; } while (0)
+#else
+#define FBSUB(acc) do { } while (0)
+#endif
+            // residues kept incrementally: an integer division per index costs more than the arithmetic it serves here
+            int kWB = 0, kRB = 0;     // k mod WB, k mod RB
+            for (int k = 0; k < n && ok; ++k, kWB = kWB + 1 == WB ? 0 : kWB + 1, kRB = kRB + 1 == RB ? 0 : kRB + 1)
             {
-                ok = false;
-                break;
-            }
-            // columns touched by this step: (k, cmax] in the band part, then the border and the right-hand sides
-            const int cmax = k < nb ? min(k + 2 * bw, nb - 1) : n - 1;
-            const int nc1 = cmax - k;                       // band columns k+1 .. cmax
-            const int c2 = k < nb ? nb : n;                 // first column of the second segment
-            const int c2s = max(c2, k + 1);
-            const int nc2 = ncol - c2s;
-            const int nct = nc1 + nc2;
-            double* rk = M + (size_t)k * ld;
-            double* rp = M + (size_t)arg * ld;
-            const double piv = rp[k];
-            // swap rows k <-> arg over the touched columns, cache the pivot row
-            for (int e = tid; e < nct + 1; e += FB_THREADS)
-            {
-                const int c = e == nct ? k : (e < nc1 ? k + 1 + e : c2s + (e - nc1));
-                const double a = rp[c];
-                if (arg != k)
+                const bool band = k < nb;
+                const int hi = band ? min(k + bw, nb - 1) : n - 1;
+                const int csk = band ? kWB : WB + (k - nb);              // column slot of column k
+                // prefetch what slides in at the end of this step (original entries, not touched by the elimination so far)
+                const int rn = k + bw + 1, cn = k + 2 * bw + 1;
+                double pf_row = 0.0, pf_col = 0.0;
+                if (band && rn < nb && tid < wcols)
                 {
-                    rp[c] = rk[c];
-                    rk[c] = a;
-                }
-                if (e < nct)
-                    prow[e] = a;
-            }
-            // rows to eliminate: band window below k, then the border rows
-            const int nr1 = hi - k;
-            const int r2s = k < nb ? nb : n;
-            const int nr2 = k < nb ? n - nb : 0;
-            __syncthreads();
-            const double ipiv = 1.0 / piv;
-            for (int e = tid; e < nr1 + nr2; e += FB_THREADS)
-            {
-                const int r = e < nr1 ? k + 1 + e : r2s + (e - nr1);
-                const double a = M[(size_t)r * ld + k];
-                lmul[e] = a * ipiv;
-                lrow[e] = a != 0.0 ? r : -1;
-            }
-            __syncthreads();
-            // rank-1 update: one warp per row, lanes over the columns
-            for (int e = warp; e < nr1 + nr2; e += FB_THREADS / 32)
-            {
-                const int r = lrow[e];
-                if (r < 0)
-                    continue;
-                const double l = lmul[e];
-                double* __restrict__ row = M + (size_t)r * ld;
-                // four columns per lane in flight: the loads of a row are independent, the matrix lives in L2 / HBM
-                for (int q0 = lane; q0 < nct; q0 += 128)
-                {
-                    double v[4];
-                    int cc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
+                    int c;      // slot tid of the new row: the band column of [k + 1, k + 2 bw + 1] with c mod WB = tid, or border / rhs
+                    if (tid < WB)
                     {
-                        const int q = q0 + 32 * u;
-                        cc[u] = q < nct ? (q < nc1 ? k + 1 + q : c2s + (q - nc1)) : -1;
-                        v[u] = cc[u] >= 0 ? row[cc[u]] : 0.0;
+                        const int k1 = kWB + 1 == WB ? 0 : kWB + 1;          // (k + 1) mod WB
+                        const int off = tid - k1;
+                        c = k + 1 + (off < 0 ? off + WB : off);
+                        c = c < nb ? c : -1;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (cc[u] >= 0)
-                            row[cc[u]] = fma(-l, prow[q0 + 32 * u], v[u]);
+                    else
+                        c = nb + (tid - WB);
+                    pf_row = c >= 0 ? M[(size_t)rn * ld + c] : 0.0;
                 }
+                if (band && cn < nb && tid >= FB_THREADS - nbord)
+                    pf_col = M[(size_t)(nb + (tid - (FB_THREADS - nbord))) * ld + cn];
+                // pivot: largest |W[r][k]|, r in [k, hi]; every warp by itself
+                double best = -1.0;
+                int arg = k;
+                for (int r = k + lane; r <= hi; r += 32)
+                {
+                    int rr = kRB + (r - k);                                  // r mod RB: r - k <= bw < RB
+                    rr = rr >= RB ? rr - RB : rr;
+                    const int rs = band ? smap[rr] : RB + (r - nb);
+                    const double a = fabs(W[rs * WCp + csk]);
+                    if (a > best) { best = a; arg = r; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                }
+                if (!(best > 0.0) || !isfinite(best))
+                {
+                    ok = false;
+                    break;
+                }
+                FBSUB(cA);
+                // physical slots of the pivot row and of the row that sat at position k; in the border phase rows are
+                // interchanged by copying (20 rows at most)
+                int ps, ks;
+                int aRB = kRB + (arg - k);
+                aRB = aRB >= RB ? aRB - RB : aRB;                            // arg mod RB
+                if (band)
+                {
+                    ps = smap[aRB];
+                    ks = smap[kRB];
+                }
+                else
+                {
+                    ps = RB + (k - nb);
+                    ks = ps;
+                    const int as = RB + (arg - nb);
+                    if (arg != k)
+                    {
+                        __syncthreads();
+                        if (tid < wcols)
+                        {
+                            const double a = W[as * WCp + tid];
+                            W[as * WCp + tid] = W[ps * WCp + tid];
+                            W[ps * WCp + tid] = a;
+                        }
+                        __syncthreads();
+                    }
+                }
+                const double* __restrict__ prw = W + ps * WCp;
+                const double ipiv = 1.0 / prw[csk];
+                // rank-1 update of the other rows of the window and of the border rows: one warp per row, the pivot row's
+                // entries of this lane's columns in registers (the window fills in within a few steps: nearly every row has a
+                // non-zero in column k, the update is bound by the shared-memory bytes of the rows)
+                constexpr int PC = 16;      // column slots per lane: wcols <= 512
+                double pr[PC];
+#pragma unroll
+                for (int t = 0; t < PC; ++t)
+                {
+                    const int cs = lane + 32 * t;
+                    pr[t] = (cs < wcols && cs != csk) ? prw[cs] : 0.0;
+                }
+                const int nr1 = band ? RB : hi - k, nr2 = band ? nbord : 0;
+                for (int e = warp; e < nr1 + nr2; e += FB_THREADS / 32)
+                {
+                    const int rs = band ? (e < nr1 ? e : RB + (e - nr1)) : RB + (k + 1 + e - nb);
+                    if (rs == ps)
+                        continue;
+                    double* __restrict__ row = W + rs * WCp;
+                    const double l = row[csk] * ipiv;
+                    if (l != 0.0)
+                    {
+#pragma unroll
+                        for (int t = 0; t < PC; ++t)
+                        {
+                            const int cs = lane + 32 * t;
+                            if (cs < wcols)
+                                row[cs] = fma(-l, pr[t], row[cs]);
+                        }
+                    }
+                }
+                FBSUB(cB);
+                __syncthreads();
+                FBSUB(cC);
+                // the finished row k: to global memory (row k of U and its right-hand sides) for the back-substitution
+                if (tid < wcols)
+                {
+                    int c;
+                    if (tid < WB)
+                    {
+                        const int off = tid - csk;
+                        c = band ? k + (off < 0 ? off + WB : off) : -1;
+                        c = c < nb ? c : -1;
+                    }
+                    else
+                        c = nb + (tid - WB);
+                    if (c >= k)
+                        M[(size_t)k * ld + c] = prw[tid];
+                }
+                if (band)
+                {
+                    // slide: column k leaves (its slot takes column k + 2 bw + 1: zero in the band rows of the window, original
+                    // entries in the border rows), row k leaves (the pivot row's slot takes row k + bw + 1)
+                    if (tid < RB && tid != ps)
+                        W[tid * WCp + csk] = 0.0;
+                    if (tid >= FB_THREADS - nbord)
+                        W[(RB + tid - (FB_THREADS - nbord)) * WCp + csk] = cn < nb ? pf_col : 0.0;
+                    if (tid < wcols)
+                        W[ps * WCp + tid] = rn < nb ? pf_row : 0.0;
+                    if (tid == 0)
+                    {
+                        smap[aRB] = ks;           // the row that sat at position k now sits at position arg
+                        smap[kRB] = ps;           // position k + bw + 1 (same residue) gets the freed slot
+                    }
+                    __syncthreads();
+                }
+                FBSUB(cD);
             }
-            __syncthreads();
+#ifdef VSMPC_FB_CLOCKS
+            if (tid == 0 && blockIdx.x == 0)
+                printf("fallback elimination: prefetch + pivot search %lld, update %lld, barrier %lld, write + slide %lld cycles\n", cA, cB, cC, cD);
+#endif
+        }
+        else
+        {
+            double* prow = fb_dyn;                                        // pivot row cache
+            double* lmul = prow + 2 * bw + 1 + (n - nb) + 1 + L.nbox + 8;
+            int* lrow = reinterpret_cast<int*>(lmul + bw + (n - nb) + 8);
+                for (int k = 0; k < n && ok; ++k)
+            {
+                const int hi = k < nb ? min(k + bw, nb - 1) : n - 1;
+                // pivot: largest |M[r][k]|, r in [k, hi]
+                double best = -1.0;
+                int arg = k;
+                for (int r = k + tid; r <= hi; r += FB_THREADS)
+                {
+                    const double a = fabs(M[(size_t)r * ld + k]);
+                    if (a > best) { best = a; arg = r; }
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                }
+                if (lane == 0) { red_v[warp] = best; red_i[warp] = arg; }
+                __syncthreads();
+                best = red_v[0]; arg = red_i[0];
+                for (int w = 1; w < FB_THREADS / 32; ++w)
+                    if (red_v[w] > best || (red_v[w] == best && red_i[w] < arg)) { best = red_v[w]; arg = red_i[w]; }
+                if (!(best > 0.0) || !isfinite(best))
+                {
+                    ok = false;
+                    break;
+                }
+                // columns touched by this step: (k, cmax] in the band part, then the border and the right-hand sides
+                const int cmax = k < nb ? min(k + 2 * bw, nb - 1) : n - 1;
+                const int nc1 = cmax - k;                       // band columns k+1 .. cmax
+                const int c2 = k < nb ? nb : n;                 // first column of the second segment
+                const int c2s = max(c2, k + 1);
+                const int nc2 = ncol - c2s;
+                const int nct = nc1 + nc2;
+                double* rk = M + (size_t)k * ld;
+                double* rp = M + (size_t)arg * ld;
+                const double piv = rp[k];
+                // swap rows k <-> arg over the touched columns, cache the pivot row
+                for (int e = tid; e < nct + 1; e += FB_THREADS)
+                {
+                    const int c = e == nct ? k : (e < nc1 ? k + 1 + e : c2s + (e - nc1));
+                    const double a = rp[c];
+                    if (arg != k)
+                    {
+                        rp[c] = rk[c];
+                        rk[c] = a;
+                    }
+                    if (e < nct)
+                        prow[e] = a;
+                }
+                // rows to eliminate: band window below k, then the border rows
+                const int nr1 = hi - k;
+                const int r2s = k < nb ? nb : n;
+                const int nr2 = k < nb ? n - nb : 0;
+                __syncthreads();
+                const double ipiv = 1.0 / piv;
+                for (int e = tid; e < nr1 + nr2; e += FB_THREADS)
+                {
+                    const int r = e < nr1 ? k + 1 + e : r2s + (e - nr1);
+                    const double a = M[(size_t)r * ld + k];
+                    lmul[e] = a * ipiv;
+                    lrow[e] = a != 0.0 ? r : -1;
+                }
+                __syncthreads();
+                // rank-1 update: one warp per row, lanes over the columns
+                for (int e = warp; e < nr1 + nr2; e += FB_THREADS / 32)
+                {
+                    const int r = lrow[e];
+                    if (r < 0)
+                        continue;
+                    const double l = lmul[e];
+                    double* __restrict__ row = M + (size_t)r * ld;
+                    // four columns per lane in flight: the loads of a row are independent, the matrix lives in L2 / HBM
+                    for (int q0 = lane; q0 < nct; q0 += 128)
+                    {
+                        double v[4];
+                        int cc[4];
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const int q = q0 + 32 * u;
+                            cc[u] = q < nct ? (q < nc1 ? k + 1 + q : c2s + (q - nc1)) : -1;
+                            v[u] = cc[u] >= 0 ? row[cc[u]] : 0.0;
+                        }
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (cc[u] >= 0)
+                                row[cc[u]] = fma(-l, prow[q0 + 32 * u], v[u]);
+                    }
+                }
+                __syncthreads();
+            }
         }
         if (!ok)
         { // structurally or numerically singular: the instance keeps status 2 and its held outputs
             __syncthreads();
             continue;
         }
+        FBCLK("elimination");
         // ---- back-substitution: one warp per right-hand side, X overwrites the right-hand-side columns --------------------
-        for (int j = warp; j < nrhs; j += FB_THREADS / 32)
+        if (use_window)
         {
-            const int cj = n + j;
-            for (int k = n - 1; k >= 0; --k)
+            // the part of x a row needs (2 bw band entries behind it, the border) sits in shared memory per warp, circular like
+            // the elimination window; row k - 1 of U is loaded while row k is reduced.  (Reading x back through global memory
+            // cost a dependent L2 round trip per row: 3.0 of the 7.7 ms of a fallback solve.)
+            const int WB = 2 * bw + 1, nbord = n - nb;
+            const int XL = WB + nbord;
+            constexpr int UE = 8;      // entries of a U row per lane: 2 bw + border <= 32 UE
+            __syncthreads();
+            for (int j = warp; j < nrhs; j += 2 * (FB_THREADS / 32))
             {
-                const double* rk = M + (size_t)k * ld;
-                const int cmax = k < nb ? min(k + 2 * bw, nb - 1) : n - 1;
-                double acc = 0.0;
-                for (int c = k + 1 + lane; c <= cmax; c += 32)
-                    acc = fma(rk[c], M[(size_t)c * ld + cj], acc);
-                if (k < nb)
-                    for (int c = nb + lane; c < n; c += 32)
-                        acc = fma(rk[c], M[(size_t)c * ld + cj], acc);
+                // two right-hand sides per warp and pass (they share the loads of the rows of U)
+                const int j2 = j + FB_THREADS / 32;
+                const bool two = j2 < nrhs;
+                const int cj = n + j, cj2 = n + (two ? j2 : j);
+                double* xw = fb_dyn + (size_t)(2 * warp) * XL;
+                double* xw2 = xw + XL;
+                auto load_row = [&](int k, double (&u)[UE], double& dk, double& bk, double& bk2) {
+                    const double* rk = M + (size_t)k * ld;
+                    const int nbnd = k < nb ? min(2 * bw, nb - 1 - k) : 0;          // band entries behind the diagonal
+                    const int ntot = k < nb ? nbnd + nbord : n - 1 - k;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                    acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0)
-                    M[(size_t)k * ld + cj] = (rk[cj] - acc) / rk[k];
-                __syncwarp();
+                    for (int t = 0; t < UE; ++t)
+                    {
+                        const int e = lane + 32 * t;
+                        const int c = k < nb ? (e < nbnd ? k + 1 + e : nb + (e - nbnd)) : k + 1 + e;
+                        u[t] = e < ntot ? rk[c] : 0.0;
+                    }
+                    dk = rk[k];
+                    bk = rk[cj];
+                    bk2 = rk[cj2];
+                };
+                double u[UE], un[UE], dk, bk, bk2, dn = 1.0, bn = 0.0, bn2 = 0.0;
+                load_row(n - 1, u, dk, bk, bk2);
+                int k1WB = nb % WB;        // (k + 1) mod WB for the band rows, kept incrementally from k = nb - 1 down
+                for (int k = n - 1; k >= 0; --k)
+                {
+                    if (k > 0)
+                        load_row(k - 1, un, dn, bn, bn2);
+                    const int nbnd = k < nb ? min(2 * bw, nb - 1 - k) : 0;
+                    const int ntot = k < nb ? nbnd + nbord : n - 1 - k;
+                    double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+                    for (int t = 0; t < UE; ++t)
+                    {
+                        const int e = lane + 32 * t;
+                        if (e < ntot)
+                        {
+                            int xs;      // slot of x[c] in this warp's windows
+                            if (k < nb)
+                            {
+                                const int b = k1WB + e;                     // (k + 1 + e) mod WB, e < 2 bw < WB
+                                xs = e < nbnd ? (b >= WB ? b - WB : b) : WB + (e - nbnd);
+                            }
+                            else
+                                xs = WB + (k + 1 + e - nb);
+                            acc = fma(u[t], xw[xs], acc);
+                            acc2 = fma(u[t], xw2[xs], acc2);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                    {
+                        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+                    }
+                    const double idk = 1.0 / dk;
+                    const double xk = (bk - acc) * idk, xk2 = (bk2 - acc2) * idk;
+                    if (k < nb)
+                        k1WB = k1WB == 0 ? WB - 1 : k1WB - 1;           // now k mod WB = the (k + 1) mod WB of the next row
+                    if (lane == 0)
+                    {
+                        const int xs = k < nb ? k1WB : WB + (k - nb);
+                        xw[xs] = xk;
+                        xw2[xs] = xk2;
+                        M[(size_t)k * ld + cj] = xk;
+                        if (two)
+                            M[(size_t)k * ld + cj2] = xk2;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < UE; ++t)
+                        u[t] = un[t];
+                    dk = dn;
+                    bk = bn;
+                    bk2 = bn2;
+                }
             }
         }
+        else
+            for (int j = warp; j < nrhs; j += FB_THREADS / 32)
+            {
+                const int cj = n + j;
+                for (int k = n - 1; k >= 0; --k)
+                {
+                    const double* rk = M + (size_t)k * ld;
+                    const int cmax = k < nb ? min(k + 2 * bw, nb - 1) : n - 1;
+                    double acc = 0.0;
+                    for (int c = k + 1 + lane; c <= cmax; c += 32)
+                        acc = fma(rk[c], M[(size_t)c * ld + cj], acc);
+                    if (k < nb)
+                        for (int c = nb + lane; c < n; c += 32)
+                            acc = fma(rk[c], M[(size_t)c * ld + cj], acc);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0)
+                        M[(size_t)k * ld + cj] = (rk[cj] - acc) / rk[k];
+                    __syncwarp();
+                }
+            }
         __syncthreads();
+        FBCLK("back-substitution");
         // ---- dual active set on T = (K^-1)_vv (tools/condensed_model._dual_pivot_loop), one variable per thread ----------
         const double tol = 1e-10;
         const bool isvar = tid < nbx;
@@ -516,6 +803,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
                     break;
             }
         }
+        FBCLK("active set");
         // ---- z = z_unc - sum_a s_a lam_a K^-1 e_a; active variables exactly on their bound ----------------------------------
         __syncthreads();
         __syncthreads();
@@ -542,6 +830,7 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
         const bool all_fin = __syncthreads_and(fin);
         if (!all_fin && stat == VSMPC_STATUS_SOLVED)
             stat = VSMPC_STATUS_NUMERICAL;
+        FBCLK("z");
         // ---- outputs (variableSamplingMPC.cpp:88-112,138-151) ------------------------------------------------------------
         if (tid == 0)
         {
@@ -596,12 +885,36 @@ static FallbackPlan fb_plan(const DeviceConfig& cfg)
     return P;
 }
 
+static size_t fb_window_bytes(const FbLayout& L)
+{ // (bw + 1 + border rows) x (2 bw + 1 + border + 1 + nbox | 1) doubles + the slot map, as the kernel lays it out
+    const size_t rows = (size_t)L.bw + 1 + (L.n - L.nb);
+    const size_t cols = (size_t)((2 * L.bw + 1 + (L.n - L.nb) + 1 + L.nbox) | 1);
+    return rows * cols * sizeof(double) + (((size_t)L.bw + 1) * sizeof(int) + 15) / 16 * 16;
+}
+
+// the elimination window fits the shared memory and the per-thread loops of the window path cover it
+static bool fb_use_window(const FbLayout& L)
+{
+    const int nbord = L.n - L.nb;
+    return fb_window_bytes(L) <= FB_WINDOW_LIMIT && 2 * L.bw + 1 + nbord + 1 + L.nbox <= FB_THREADS && L.bw + 1 <= FB_THREADS - nbord
+           && 2 * L.bw + nbord <= 256 && L.bw + 1 + nbord <= 128;
+}
+
+// dynamic shared memory of the launch: the window, or the pivot-row cache / multipliers / row list of the global-memory path
+static size_t fb_dyn_bytes(const FbLayout& L)
+{
+    if (fb_use_window(L))
+        return fb_window_bytes(L);
+    const size_t nbord = L.n - L.nb;
+    return (2 * L.bw + 1 + nbord + 1 + L.nbox + 8 + 2 * (L.bw + nbord + 8)) * sizeof(double);
+}
+
 bool fallback_supported(const DeviceConfig& cfg)
 {
     const FallbackPlan P = fb_plan(cfg);
     // the pivot-row cache and the per-thread active set bound the sizes (nv <= 160: up to 40 throttle blocks)
-    return P.L.bw + (P.L.n - P.L.nb) + 8 <= FB_MAXROWS
-           && 2 * P.L.bw + 1 + (P.L.n - P.L.nb) + 1 + P.L.nbox <= FB_MAXROWS * 3 + 256 && P.L.nbox <= FB_MAXBOX && P.L.nbox <= FB_THREADS;
+    // the active set has one boxed variable per thread; the elimination runs in a shared-memory window when it fits
+    return P.L.nbox <= FB_MAXBOX && P.L.nbox <= FB_THREADS && fb_dyn_bytes(P.L) <= FB_WINDOW_LIMIT;
 }
 
 size_t fallback_slot_doubles(const DeviceConfig& cfg) { return fb_plan(cfg).slot_doubles; }
@@ -618,8 +931,13 @@ cudaError_t launch_qp_fallback(const DeviceConfig& h_cfg, int B, int n_slots, co
                                int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, cudaStream_t s)
 {
     const FallbackPlan P = fb_plan(h_cfg);
-    qp_fallback_kernel<<<n_slots, FB_THREADS, 0, s>>>(h_cfg, P.L, B, qd, fb_list, fb_count, pos, scratch, P.slot_doubles, z, st,
-                                                     out_rows, status, n_factor, n_solve, n_pivot, want_z);
+    static bool attr_set[64] = {};
+    cudaError_t e = ensure_dynamic_smem(qp_fallback_kernel, (int)FB_WINDOW_LIMIT, attr_set);
+    if (e != cudaSuccess)
+        return e;
+    qp_fallback_kernel<<<n_slots, FB_THREADS, fb_dyn_bytes(P.L), s>>>(h_cfg, P.L, B, qd, fb_list, fb_count, pos, scratch, P.slot_doubles,
+                                                                     z, st, out_rows, status, n_factor, n_solve, n_pivot, want_z,
+                                                                     fb_use_window(P.L) ? 1 : 0);
     return cudaGetLastError();
 }
 
