@@ -331,7 +331,11 @@ def run_ours(args):
                 "solved_fraction_last_step": float((h_status2[(K - 1) & 1].numpy() == 0).mean()),
                 "blocking_value": world * B * K / (e2e_blk_ms * 1e-3),
                 "blocking_note": "same calls with a blocking read-back every step (no copy/compute overlap)"},
-        "gpu_launches": 2 * K,
+        # kernels of this repository launched inside the device-timed region: linearise + QP (+ the fallback kernel behind the
+        # condensed kernels: it runs every tick and finds its list empty on this workload)
+        "gpu_launches": (3 if args.solver == 0 else 2) * K,
+        "gpu_launches_per_step": ["linearise_kernel", "qp_condensed_kernel" if not params else "qp_condensed_wide_kernel",
+                                  "qp_fallback_kernel"] if args.solver == 0 else 2,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "single_solve_latency": latency, "closed_loop": closed,
         "e2e_kinematics": e2e_kin, "monte_carlo": monte, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
