@@ -39,13 +39,6 @@ def main():
     dst = os.path.join(ROOT, "tests", "golden", "trajectories.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst), "bytes")
-    # the smaller of the two MAT-v7.3 data files, byte for byte: the committed input of the mat73 reader test
-    # (tests/test_host.py::test_mat73_reader_on_a_committed_v73_file; h5py is not available to write one)
-    import shutil
-    v73 = os.path.join(ROOT, "tests", "golden", "alphaGravity_v73.mat")
-    shutil.copyfile(os.path.join(REF, "alphaGravity.mat"), v73)
-    os.chmod(v73, 0o644)
-    print("copied", v73, os.path.getsize(v73), "bytes")
 
 
 if __name__ == "__main__":

@@ -151,15 +151,27 @@ def test_mat73_reader_on_npz_equivalent(tmp_path):
     assert t["alpha_fps"] == 10 and t["traj_fps"] == 10 and t["alphaGravity"].shape == (1, 351)
 
 
-def test_mat73_reader_on_a_committed_v73_file():
-    """mat73.loadmat73 on a MAT-v7.3 (HDF5) file: tests/golden/alphaGravity_v73.mat is the reference's own
-    src/trajectories/alphaGravity.mat (5 kB, byte copy made by tests/golden/make_fixtures.py — h5py is not in this image, so
-    no v7.3 file can be generated in-test); what the reader returns must equal the converted fixture the GPU tests use."""
+def test_mat73_reader_on_v73_files_generated_in_test(tmp_path):
+    """mat73.loadmat73 / config.load_trajectories_mat on MAT-v7.3 (HDF5) files written by the test itself (tests/hdf5_min.py:
+    h5py is not in this image): contiguous and chunked + deflate float64 datasets, the two files and variable names of the
+    reference's TrajectoryManager (UT/src/TrajectoryManager.cpp:67-140: fps, alphaGravity; fps, positionCoM, velocityCoM,
+    RPY, RPYDot), the shapes of the reference's own files (1 x 351, 3 x 1481)."""
+    from hdf5_min import write_mat73
     m73, cfg = pkg("mat73"), pkg("config")
-    d = m73.loadmat73(os.path.join(ROOT, "tests", "golden", "alphaGravity_v73.mat"))
-    t = cfg.load_trajectories_npz(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
-    assert int(d["fps"][0, 0]) == t["alpha_fps"]
-    assert d["alphaGravity"].shape == t["alphaGravity"].shape and np.array_equal(d["alphaGravity"], t["alphaGravity"])
+    g = np.random.default_rng(5)
+    a = {"fps": np.array([[10.0]]), "alphaGravity": g.random((1, 351))}
+    t = {"fps": np.array([[10.0]]), "positionCoM": g.normal(size=(3, 1481)), "velocityCoM": g.normal(size=(3, 1481)),
+         "RPY": g.normal(size=(3, 1481)), "RPYDot": g.normal(size=(3, 1481))}
+    fa, ft = str(tmp_path / "alphaGravity.mat"), str(tmp_path / "minimumJerkTrajectory.mat")
+    write_mat73(fa, a)
+    write_mat73(ft, t, chunked={"positionCoM": 500, "RPYDot": 1481, "velocityCoM": 7})
+    d = m73.loadmat73(ft)
+    assert set(d) == set(t)
+    for k in t:
+        assert d[k].shape == t[k].shape and np.array_equal(d[k], t[k]), k
+    tr = cfg.load_trajectories_mat(fa, ft)
+    assert tr["alpha_fps"] == 10 and tr["traj_fps"] == 10
+    assert np.array_equal(tr["alphaGravity"], a["alphaGravity"]) and np.array_equal(tr["RPY"], t["RPY"])
     with pytest.raises(ValueError):
         m73.Mat73(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))      # not an HDF5 file
 
