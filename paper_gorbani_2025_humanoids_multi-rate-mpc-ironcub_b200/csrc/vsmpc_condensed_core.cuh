@@ -224,14 +224,13 @@ __device__ __forceinline__ bool a_eliminate(const CdCtxT<SM>& c, CdSlot& sl, dou
 // propagation of P through knot k: P' = P + Q, publish P'D, P <- T'P'T; with elim also H_ux (published) and this
 // lane's pair of H_uu = R + B_u' P' B_u
 template <class SM>
-__device__ __forceinline__ void a_prop(const CdCtxT<SM>& c, int k, bool elim, double (&p)[NX], double qd_lane,
+__device__ __forceinline__ void a_prop(const CdCtxT<SM>& c, int k, CdSlot& sl, bool elim, double (&p)[NX], double qd_lane,
                                        double (&hux)[NJ], double2& own)
 {
     SM& sm = c.sm;
     const int lane = c.lane;
     const double* cf = sm.cf;
     const double dt = sm.dtk[k];
-    CdSlot& sl = sm.slot[k & 1];
     // P' = P + Q on the diagonal element this lane owns (predicated add: keeps the compiler from turning the
     // 26-way ownership test into a divergent jump table)
 #pragma unroll

@@ -18,6 +18,8 @@
 // * one forward pass with the stored gains K_k (8 x 26) and F_k (8 x 32) produces the outputs.
 // Compared with vsmpc_qp_structured.cu (one warp, 38-dim augmented state, one Riccati back-solve per active
 // bound) the serial depth drops from (1 + n_s) x 34 knot steps to 17 + 17.
+#include <cstdlib>
+
 #include "vsmpc_condensed_core.cuh"
 
 namespace vsmpc
@@ -36,7 +38,35 @@ constexpr int WSC_STAGE = NJ * NX + 2 * NJ * NL; // 720
 
 constexpr int CD_MAXN = 32;   // knots kept in shared memory (dt grid)
 
-struct alignas(16) CdSmem
+// mbarriers (shared memory) of the decoupled A -> B pipeline (small batches, see qp_condensed_kernel): every lane of the posting
+// warp arrives (count 32), the waiting warp polls the phase parity with mbarrier.try_wait (default .acquire.cta / .release.cta
+// semantics order the published data).  FULL + s: slot s published (A posts, B waits); FREE + s: slot s consumed (B posts, A
+// waits); B2A: warp B's propagation of the held-block knot done (A waits before the Schur step); SCHUR: Schur step published.
+constexpr int CD_PIPE_SLOTS = 3;
+constexpr int MB_FULL = 0, MB_FREE = CD_PIPE_SLOTS, MB_B2A = 2 * CD_PIPE_SLOTS, MB_SCHUR = 2 * CD_PIPE_SLOTS + 1,
+              MB_COUNT = 2 * CD_PIPE_SLOTS + 2;
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_post(unsigned long long* b)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    unsigned done;
+    do
+    {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+template <int NSLOT> struct alignas(16) CdSmemT
 {
     double cf[CCF];
     alignas(16) double lam[6 * NJ];         // dt-free B_J rows: [q][a], q = 0..2 linear, 3..5 angular momentum
@@ -44,16 +74,15 @@ struct alignas(16) CdSmem
     double Rqd[NJ];
     double dtk[CD_MAXN];
     double xref[12 * CD_MAXNC];
-    CdSlot slot[2];             // A -> B mailbox, slot = knot & 1; after the factorisation: G and the working-set inverse
+    CdSlot slot[NSLOT];         // A -> B mailbox: slot = knot & 1 (lock step) or publication j % 3 (decoupled pipeline)
     alignas(16) double Mt[NX * LDM];        // warp A: transposition buffer, then the gain rows K [8][26] of the knot in
                                 // flight; after the factorisation: F theta, x, dq
     double Om[NLO * NLO];
     alignas(16) double Hut[4 * CD_MAXW];    // active-set vectors (r, lambda, sign, index) after the factorisation
     alignas(16) double theta[NL];
+    unsigned long long mbar[MB_COUNT];
     int flags[4];
 };
-
-using CdCtx = CdCtxT<CdSmem>;
 
 #ifdef VSMPC_PHASE_CLOCKS
 __device__ long long g_phase_clk[4096][16];
@@ -113,6 +142,7 @@ __device__ __forceinline__ bool rp_pivot(double (&t)[CD_MAXW], double* __restric
 // down-date of the parameter columns with the eliminated block: F = H_uu^-1 H_utheta, Psi -= H_ux' F.  The matching
 // down-date of Om (Om -= H_utheta' F) is NOT done knot by knot: H_utheta and F of every elimination knot are stacked
 // in the workspace and contracted once after the recursion on the FP64 tensor cores (cd_omega_downdate).
+template <class CdCtx>
 __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&s)[NX], const double (&hut)[NJ],
                                            double* __restrict__ wsk, bool clear_col)
 {
@@ -232,14 +262,14 @@ __device__ __forceinline__ void cd_omega_downdate(const double* __restrict__ ws,
 
 // propagation of the parameter columns through knot k (Psi'' = Psi' + P'D, Om += D'Psi'' + Psi''D, Psi <- T'Psi'');
 // returns dt B_J' Psi''[:, l] (= H_utheta column without the gradient term) in bj2
-__device__ __forceinline__ void b_prop(const CdCtx& c, int k, bool tail, double (&s)[NX], double (&bj2)[NJ])
+template <class CdCtx>
+__device__ __forceinline__ void b_prop(const CdCtx& c, int k, CdSlot& sl, bool tail, double (&s)[NX], double (&bj2)[NJ])
 {
     const DeviceConfig& cfg = c.cfg;
-    CdSmem& sm = c.sm;
+    auto& sm = c.sm;
     const int lane = c.lane;
     const double* cf = sm.cf;
     const double dt = sm.dtk[k];
-    CdSlot& sl = sm.slot[k & 1];
     const int tb = throttle_block(k, cfg.Ns, cfg.Nc);
     const bool isAff = lane == AFFL;
     const bool spV = lane < 4 * cfg.nblk && (lane >> 2) == tb;
@@ -325,13 +355,23 @@ __device__ __forceinline__ void b_prop(const CdCtx& c, int k, bool tail, double 
     applyTtx(s, cf, dt);
 }
 
-__global__ void __launch_bounds__(CD_THREADS, 8)
-qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
-                    double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
-                    double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
-                    int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,
-                    int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode)
+// PIPE = false: the two warps advance in lock step, one __syncthreads per knot (the throughput configuration: 25 KB of shared
+// memory, eight CTAs per SM).  PIPE = true: decoupled pipeline for SMALL batches (at most four CTAs per SM, 232 registers: no spills) — warp A publishes
+// knot N-1-j in slot j % 3 of a mailbox ring and may run two knots ahead, warp B consumes in order and hands the slot back
+// (mbarriers); the one place where warp A needs warp B is the Schur step of the held joint block.  With one CTA per SM warp A
+// spends a quarter of the recursion waiting at the common barrier (132 k cycles against 99 k busy); without contention that
+// wait is pure latency of a single solve.  At B = 1024 (seven CTAs per SM) the same pipeline gained nothing and its 30 KB of
+// shared memory cost the eighth CTA per SM (profiles/r02_k2_experiments.md), so the launcher uses it for small batches only.
+template <bool PIPE>
+__device__ __forceinline__ void
+qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd_all,
+                  double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
+                  double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
+                  int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,
+                  int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode)
 {
+    using CdSmem = CdSmemT<PIPE ? CD_PIPE_SLOTS : 2>;
+    using CdCtx = CdCtxT<CdSmem>;
     __shared__ CdSmem sm;
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,6 +404,8 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
         sm.dtk[threadIdx.x] = cfg.dt[threadIdx.x];
     for (int e = threadIdx.x; e < 6 * NJ; e += CD_THREADS)
         sm.lam[e] = qd[(e < 3 * NJ ? QD_LLIN : QD_LANG - 3 * NJ) + e];
+    if (PIPE && threadIdx.x < MB_COUNT)
+        mbar_init(&sm.mbar[threadIdx.x], 32);
     const bool all_fin = __syncthreads_and(fin);
     int stat = all_fin ? VSMPC_STATUS_SOLVED : VSMPC_STATUS_NUMERICAL;
 
@@ -377,104 +419,211 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     bool ok = true;
     long long clkA0 = 0, clkA1 = 0, clkB0 = 0, clkB1 = 0;
     (void)clkA0; (void)clkA1; (void)clkB0; (void)clkB1;
-    const int n_it = c.kS < 0 ? N + 1 : (N - 1 - c.kS) + 3 + c.kS + 1;
-    for (int t = 0; t < n_it; ++t)
+    if constexpr (PIPE)
     {
-        int ta, ka, tbk, kb;
-        cd_schedule(t, N, c.kS, ta, ka, tbk, kb);
         if (warp == 0)
         {
-            if (ta != TK_NONE)
+#pragma unroll 1
+            for (int j = 0; j < N; ++j)
             {
-                CdSlot& sl = sm.slot[ka & 1];
+                const int ka = N - 1 - j, s = j % CD_PIPE_SLOTS;
+                CdSlot& sl = sm.slot[s];
                 double hux[NJ];
                 double2 own;
-                const bool elim = ta == TK_STAGE && !(held && ka >= Nc - 1);
+                const bool elim = !(held && ka >= Nc - 1);
+                if (j >= CD_PIPE_SLOTS)
+                    mbar_wait(&sm.mbar[MB_FREE + s], (j / CD_PIPE_SLOTS - 1) & 1);
                 long long tclk = clock64();
                 (void)tclk;
-                if (ta != TK_SCHUR)
+                a_prop(c, ka, sl, elim, y, qd_lane, hux, own);
+                SUBCLK(clkA0, tclk);
+                __syncwarp();
+                if (elim)
+                    ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * WSC_STAGE) && ok;
+                SUBCLK(clkA1, tclk);
+                mbar_post(&sm.mbar[MB_FULL + s]);
+                if (ka == c.kS)
                 {
-                    a_prop(c, ka, elim, y, qd_lane, hux, own);
-                    SUBCLK(clkA0, tclk);
-                }
-                else
-                {
-                    // Schur step of the held joint block: H_ux = Psi_T[:, d]' (published by warp B),
+                    // Schur step of the held joint block: H_ux = Psi_T[:, d]' (published by warp B in this slot),
                     // H_uu = Om_T[d, d] + R
+                    mbar_wait(&sm.mbar[MB_B2A], 0);
+                    tclk = clock64();
                     const int r = lane & 7, q = lane >> 3;
 #pragma unroll
                     for (int m = 0; m < NJ; ++m)
                         hux[m] = lane < NX ? sl.Hux[m * NX + lane] : 0.0;
                     own.x = sm.Om[(c.D0 + r) * NLO + c.D0 + 2 * q] + (2 * q == r ? sm.Rqd[r] : 0.0);
                     own.y = sm.Om[(c.D0 + r) * NLO + c.D0 + 2 * q + 1] + (2 * q + 1 == r ? sm.Rqd[r] : 0.0);
-                }
-                __syncwarp();
-                if (elim || ta == TK_SCHUR)
+                    __syncwarp();
                     ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * WSC_STAGE) && ok;
-                SUBCLK(clkA1, tclk);
+                    SUBCLK(clkA1, tclk);
+                    mbar_post(&sm.mbar[MB_SCHUR]);
+                }
             }
         }
-        else if (tbk != TK_NONE)
+        else
         {
-            CdSlot& sl = sm.slot[kb & 1];
-            const bool tail = held && kb >= Nc - 1;
-            const bool isD = lane >= c.D0 && lane < c.D0 + NJ;
-            double hut[NJ];
-            bool down = false;
-            long long tclk = clock64();
-            (void)tclk;
-            if (tbk != TK_SCHUR)
+#pragma unroll 1
+            for (int j = 0; j < N; ++j)
             {
-                b_prop(c, kb, tail, y, hut);
+                const int kb = N - 1 - j, s = j % CD_PIPE_SLOTS;
+                CdSlot& sl = sm.slot[s];
+                const bool tail = held && kb >= Nc - 1;
+                const bool schur = kb == c.kS;
+                const bool isD = lane >= c.D0 && lane < c.D0 + NJ;
+                double hut[NJ];
+                mbar_wait(&sm.mbar[MB_FULL + s], (j / CD_PIPE_SLOTS) & 1);
+                long long tclk = clock64();
+                (void)tclk;
+                b_prop(c, kb, sl, tail, y, hut);
                 SUBCLK(clkB0, tclk);
-                if (tbk == TK_PROP)
+                if (schur)
                 {
-                    // publish H_ux = Psi_T[:, d]' for warp A's Schur step
+                    // publish H_ux = Psi_T[:, d]' for warp A's Schur step, wait for its H_uu^-1
                     if (isD)
                     {
 #pragma unroll
-                        for (int j = 0; j < NX; ++j)
-                            sl.Hux[(lane - c.D0) * NX + j] = y[j];
+                        for (int jj = 0; jj < NX; ++jj)
+                            sl.Hux[(lane - c.D0) * NX + jj] = y[jj];
                     }
-                }
-                else
-                    down = !tail;
-            }
-            else
-            {
-#pragma unroll
-                for (int m = 0; m < NJ; ++m)
-                    hut[m] = (lane < NLO && !isD) ? sm.Om[(c.D0 + m) * NLO + lane] : 0.0;
-                __syncwarp();
-                down = true;
-            }
-            if (down)
-            {
-                if (lane == AFFL)
-                {
+                    mbar_post(&sm.mbar[MB_B2A]);
+                    mbar_wait(&sm.mbar[MB_SCHUR], 0);
+                    tclk = clock64();
 #pragma unroll
                     for (int m = 0; m < NJ; ++m)
-                        hut[m] += sm.cf[QD_GQ + m];
-                }
-                const bool schur = tbk == TK_SCHUR;
-                b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD);
-                SUBCLK(clkB1, tclk);
-                if (schur)
-                {
-                    if (lane < NLO)
-                    {
-#pragma unroll
-                        for (int a = 0; a < NJ; ++a)
-                        {
-                            sm.Om[(c.D0 + a) * NLO + lane] = 0.0;
-                            sm.Om[lane * NLO + c.D0 + a] = 0.0;
-                        }
-                    }
+                        hut[m] = (lane < NLO && !isD) ? sm.Om[(c.D0 + m) * NLO + lane] : 0.0;
                     __syncwarp();
                 }
+                if (schur || !tail)
+                {
+                    if (lane == AFFL)
+                    {
+#pragma unroll
+                        for (int m = 0; m < NJ; ++m)
+                            hut[m] += sm.cf[QD_GQ + m];
+                    }
+                    b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD);
+                    SUBCLK(clkB1, tclk);
+                    if (schur)
+                    {
+                        if (lane < NLO)
+                        {
+#pragma unroll
+                            for (int a = 0; a < NJ; ++a)
+                            {
+                                sm.Om[(c.D0 + a) * NLO + lane] = 0.0;
+                                sm.Om[lane * NLO + c.D0 + a] = 0.0;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                mbar_post(&sm.mbar[MB_FREE + s]);
             }
         }
         __syncthreads();
+    }
+    else
+    {
+        const int n_it = c.kS < 0 ? N + 1 : (N - 1 - c.kS) + 3 + c.kS + 1;
+        for (int t = 0; t < n_it; ++t)
+        {
+            int ta, ka, tbk, kb;
+            cd_schedule(t, N, c.kS, ta, ka, tbk, kb);
+            if (warp == 0)
+            {
+                if (ta != TK_NONE)
+                {
+                    CdSlot& sl = sm.slot[ka & 1];
+                    double hux[NJ];
+                    double2 own;
+                    const bool elim = ta == TK_STAGE && !(held && ka >= Nc - 1);
+                    long long tclk = clock64();
+                    (void)tclk;
+                    if (ta != TK_SCHUR)
+                    {
+                        a_prop(c, ka, sl, elim, y, qd_lane, hux, own);
+                        SUBCLK(clkA0, tclk);
+                    }
+                    else
+                    {
+                        // Schur step of the held joint block: H_ux = Psi_T[:, d]' (published by warp B),
+                        // H_uu = Om_T[d, d] + R
+                        const int r = lane & 7, q = lane >> 3;
+    #pragma unroll
+                        for (int m = 0; m < NJ; ++m)
+                            hux[m] = lane < NX ? sl.Hux[m * NX + lane] : 0.0;
+                        own.x = sm.Om[(c.D0 + r) * NLO + c.D0 + 2 * q] + (2 * q == r ? sm.Rqd[r] : 0.0);
+                        own.y = sm.Om[(c.D0 + r) * NLO + c.D0 + 2 * q + 1] + (2 * q + 1 == r ? sm.Rqd[r] : 0.0);
+                    }
+                    __syncwarp();
+                    if (elim || ta == TK_SCHUR)
+                        ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * WSC_STAGE) && ok;
+                    SUBCLK(clkA1, tclk);
+                }
+            }
+            else if (tbk != TK_NONE)
+            {
+                CdSlot& sl = sm.slot[kb & 1];
+                const bool tail = held && kb >= Nc - 1;
+                const bool isD = lane >= c.D0 && lane < c.D0 + NJ;
+                double hut[NJ];
+                bool down = false;
+                long long tclk = clock64();
+                (void)tclk;
+                if (tbk != TK_SCHUR)
+                {
+                    b_prop(c, kb, sl, tail, y, hut);
+                    SUBCLK(clkB0, tclk);
+                    if (tbk == TK_PROP)
+                    {
+                        // publish H_ux = Psi_T[:, d]' for warp A's Schur step
+                        if (isD)
+                        {
+    #pragma unroll
+                            for (int j = 0; j < NX; ++j)
+                                sl.Hux[(lane - c.D0) * NX + j] = y[j];
+                        }
+                    }
+                    else
+                        down = !tail;
+                }
+                else
+                {
+    #pragma unroll
+                    for (int m = 0; m < NJ; ++m)
+                        hut[m] = (lane < NLO && !isD) ? sm.Om[(c.D0 + m) * NLO + lane] : 0.0;
+                    __syncwarp();
+                    down = true;
+                }
+                if (down)
+                {
+                    if (lane == AFFL)
+                    {
+    #pragma unroll
+                        for (int m = 0; m < NJ; ++m)
+                            hut[m] += sm.cf[QD_GQ + m];
+                    }
+                    const bool schur = tbk == TK_SCHUR;
+                    b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD);
+                    SUBCLK(clkB1, tclk);
+                    if (schur)
+                    {
+                        if (lane < NLO)
+                        {
+    #pragma unroll
+                            for (int a = 0; a < NJ; ++a)
+                            {
+                                sm.Om[(c.D0 + a) * NLO + lane] = 0.0;
+                                sm.Om[lane * NLO + c.D0 + a] = 0.0;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
     PHASE_CLK(2);
     PHASE_CLK(4);
@@ -780,6 +929,21 @@ qp_condensed_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const doub
     PHASE_CLK(3);
 }
 
+// The builds of the kernel (one body): register budget and pipeline per batch size
+#define CD_KERNEL_ARGS                                                                                                     \
+    const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all, double* __restrict__ ws_all,      \
+        double* __restrict__ z_all, double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,       \
+        int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,     \
+        int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode
+#define CD_KERNEL_PASS cfgv, B, qd_all, ws_all, z_all, st, out_rows, status, n_factor, n_solve, n_pivot, ws_stride, want_z, fb_list, fb_count, fb_mode
+// large batches: eight CTAs per SM, 128 registers
+__global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel(CD_KERNEL_ARGS) { qp_condensed_body<false>(CD_KERNEL_PASS); }
+// (a 144-register build for the one wave of seven CTAs per SM at B = 1024 was tried: 207 us instead of 165 — the register file
+// is split over the four sub-partitions, 14 warps put four on two of them and four warps of 144 registers do not fit 16 384,
+// so the SM holds six CTAs and the launch takes two waves; 128 registers is the cap for anything above twelve warps per SM)
+// small batches, at most four CTAs per SM: decoupled pipeline, no register cap that matters (232 registers, no spills)
+__global__ void __launch_bounds__(CD_THREADS, 4) qp_condensed_kernel_pipe(CD_KERNEL_ARGS) { qp_condensed_body<true>(CD_KERNEL_PASS); }
+
 int condensed_phase_clocks(long long* host, int n)
 {
 #ifdef VSMPC_PHASE_CLOCKS
@@ -805,9 +969,24 @@ cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h
                                 int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
                                 cudaStream_t s)
 {
-    qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot,
-                                                 condensed_ws_doubles(h_cfg), want_z, fb_list, fb_count,
-                                                 fb_list && fb_count ? fb_mode : 0);
+    // small batches (at most four CTAs per SM): the decoupled pipeline, which shortens a single solve; otherwise lock step
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int pipe_ctas = -1;      // development: VSMPC_K2_PIPE_CTAS overrides the number of CTAs per SM up to which PIPE is used
+    if (pipe_ctas < 0)
+    {
+        const char* e = getenv("VSMPC_K2_PIPE_CTAS");
+        pipe_ctas = e ? atoi(e) : 4;
+    }
+    const size_t wsd = condensed_ws_doubles(h_cfg);
+    const int fbm = fb_list && fb_count ? fb_mode : 0;
+    if (B <= pipe_ctas * sms)
+        qp_condensed_kernel_pipe<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
+                                                          want_z, fb_list, fb_count, fbm);
+    else
+        qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
+                                                     want_z, fb_list, fb_count, fbm);
     return cudaGetLastError();
 }
 

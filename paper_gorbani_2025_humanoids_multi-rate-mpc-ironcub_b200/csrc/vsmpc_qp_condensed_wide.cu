@@ -497,7 +497,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                 const bool elim = ta == TK_STAGE && !(held && ka >= Nc - 1);
                 if (ta != TK_SCHUR)
                 {
-                    a_prop(c, ka, elim, y, qd_lane, hux, own);
+                    a_prop(c, ka, sl, elim, y, qd_lane, hux, own);
                     WSUB(wk0, tclk);
                 }
                 else
