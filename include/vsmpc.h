@@ -179,7 +179,9 @@ int vsmpc_debug_set_working_set(vsmpc_handle* h, const signed char* working_set_
  * still in flight when the call returns: pack_host must stay untouched until vsmpc_wait / vsmpc_wait_output / a blocking
  * getter of THIS tick has returned (pageable memory is staged by the driver before the call returns).  A handle is driven by
  * one host thread; vsmpc_set_stream between vsmpc_set_state and vsmpc_solve keeps the order (the new stream waits for the
- * old one). */
+ * old one).  The linearise kernel of this call runs on a stream of the handle's own, concurrently with the QP kernel of the
+ * tick before (vsmpc_solve_async of that tick may still be running): every later call of the handle that reads what it
+ * produced waits for it. */
 int vsmpc_set_state(vsmpc_handle* h, const double* pack_host);
 /* same, pack already resident on the handle's GPU */
 int vsmpc_set_state_device(vsmpc_handle* h, const double* pack_dev);

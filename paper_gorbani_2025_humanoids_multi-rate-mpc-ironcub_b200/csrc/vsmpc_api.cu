@@ -101,6 +101,20 @@ struct vsmpc_handle
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};
     cudaEvent_t ev_out[2] = {nullptr, nullptr};
     int pack_idx = 0, out_idx = 0;
+    // Overlapped linearisation (host-pack path): the linearise kernel of tick j+1 runs on its own stream WHILE the QP kernel of
+    // tick j runs on the compute stream — it only needs tick j+1's pack and the tick state the previous linearise kernel left
+    // (the QP kernels write one block of that state, the joint accumulator, which the linearise kernel does not use).  What the
+    // two kernels would share is double-buffered: the QP data block K1 -> K2 and the fallback list / count.
+    cudaStream_t k1_stream = nullptr;
+    cudaEvent_t ev_lin[2] = {nullptr, nullptr};      // linearise kernel that filled QP buffer q is done (on k1_stream)
+    cudaEvent_t ev_qp[2] = {nullptr, nullptr};       // QP + fallback kernels that read QP buffer q are done (on the compute stream)
+    cudaEvent_t ev_lin_main = nullptr;               // last linearise kernel launched on the compute stream
+    double* d_qd2[2] = {nullptr, nullptr};
+    int* d_fb_list2[2] = {nullptr, nullptr};
+    int* d_fb_count2[2] = {nullptr, nullptr};
+    int qd_idx = 0;                                  // buffer the last linearise kernel filled = the one the next solve reads
+    bool lin_on_k1 = false;                          // that kernel ran on k1_stream and the compute stream has not waited for it yet
+    bool capturing = false;                          // a rollout tick is being captured: no event records for other streams
     // asynchronous read-back: the rows are snapshotted on the compute stream into one of two staging buffers and copied to
     // the host from there, so that the next QP kernel (which rewrites d_out in place: held outputs) does not wait for PCIe
     double* d_out_stage[2] = {nullptr, nullptr};
@@ -411,7 +425,16 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     A(dalloc(&h->d_tvel, tv.size()));
     A(dalloc(&h->d_trpy, tr.size()));
     A(dalloc(&h->d_trpyd, td.size()));
-    A(dalloc(&h->d_qd, (size_t)g.qd_stride * B));
+    A(dalloc(&h->d_qd2[0], (size_t)g.qd_stride * B));
+    A(dalloc(&h->d_qd2[1], (size_t)g.qd_stride * B));
+    h->d_qd = h->d_qd2[0];
+    A(cudaStreamCreateWithFlags(&h->k1_stream, cudaStreamNonBlocking));
+    A(cudaEventCreateWithFlags(&h->ev_lin_main, cudaEventDisableTiming));
+    for (int q = 0; q < 2; ++q)
+    {
+        A(cudaEventCreateWithFlags(&h->ev_lin[q], cudaEventDisableTiming));
+        A(cudaEventCreateWithFlags(&h->ev_qp[q], cudaEventDisableTiming));
+    }
     {
         size_t wsd = (size_t)g.N * WS_STAGE;
         if (h->solver == 0 && condensed_ws_doubles(g) > wsd)
@@ -446,14 +469,20 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         h->fb_slots = (int)slots;
         std::vector<int> pos(fallback_pos_ints(g));
         fallback_positions(g, pos.data());
-        A(dalloc(&h->d_fb_list, (size_t)B));
-        A(dalloc(&h->d_fb_count, 1));
+        for (int q = 0; q < 2; ++q)
+        {
+            A(dalloc(&h->d_fb_list2[q], (size_t)B));
+            A(dalloc(&h->d_fb_count2[q], 1));
+        }
+        h->d_fb_list = h->d_fb_list2[0];
+        h->d_fb_count = h->d_fb_count2[0];
         A(dalloc(&h->d_fb_pos, pos.size()));
         A(dalloc(&h->d_fb_scratch, fallback_slot_doubles(g) * slots));
         if (ok)
         {
             A(cudaMemcpy(h->d_fb_pos, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
-            A(cudaMemset(h->d_fb_count, 0, sizeof(int)));
+            A(cudaMemset(h->d_fb_count2[0], 0, sizeof(int)));
+            A(cudaMemset(h->d_fb_count2[1], 0, sizeof(int)));
         }
         h->fb_mode = 1;
     }
@@ -492,8 +521,9 @@ int vsmpc_destroy(vsmpc_handle* h)
     if (h->B > 0)
         cudaSetDevice(h->device);
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
-                    h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_out,
-                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset, h->d_kin, h->d_ks[0], h->d_ks[1],
+                    h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd2[0], h->d_qd2[1], h->d_ws, h->d_scratch, h->d_z, h->d_out,
+                    h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list2[0], h->d_fb_list2[1], h->d_fb_count2[0],
+                    h->d_fb_count2[1], h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset, h->d_kin, h->d_ks[0], h->d_ks[1],
                     h->d_out_stage[0], h->d_out_stage[1], h->d_status_stage[0], h->d_status_stage[1], h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -501,6 +531,15 @@ int vsmpc_destroy(vsmpc_handle* h)
         if (h->ev_k1[q]) cudaEventDestroy(h->ev_k1[q]);
         if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]);
     }
+    for (int q = 0; q < 2; ++q)
+    {
+        if (h->ev_lin[q]) cudaEventDestroy(h->ev_lin[q]);
+        if (h->ev_qp[q]) cudaEventDestroy(h->ev_qp[q]);
+    }
+    if (h->ev_lin_main)
+        cudaEventDestroy(h->ev_lin_main);
+    if (h->k1_stream)
+        cudaStreamDestroy(h->k1_stream);
     if (h->copy_stream)
         cudaStreamDestroy(h->copy_stream);
     if (h->out_stream)
@@ -539,13 +578,56 @@ int vsmpc_n_var(const vsmpc_handle* h) { return h ? h->cfg.n_var : -1; }
 int vsmpc_n_constraints(const vsmpc_handle* h) { return h ? h->cfg.n_con : -1; }
 int vsmpc_n_instances(const vsmpc_handle* h) { return h ? h->B : -1; }
 
+// the compute stream catches up with a linearise kernel that ran on k1_stream (before anything on it reads the QP data)
+static int join_linearise(vsmpc_handle* h)
+{
+    if (h->lin_on_k1)
+    {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_lin[h->qd_idx], 0));
+        h->lin_on_k1 = false;
+    }
+    return VSMPC_OK;
+}
+
+// linearise kernel on the compute stream (device-resident packs, configure, rollouts): it fills the current QP buffer
 static int run_linearise(vsmpc_handle* h, int mode)
 {
+    int rc = join_linearise(h);
+    if (rc)
+        return rc;
     if (mode == 1 && h->d_wset)     // IMPCProblem::configure: no previous solve, the guess is the all-lower vertex
         CK(cudaMemsetAsync(h->d_wset, 0xFF, h->wset_bytes, h->stream));
     CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
                         h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd,
                         h->use_ip ? h->d_ip : nullptr, h->d_fb_count, h->use_jl_table ? h->d_jl : nullptr, h->stream));
+    if (!h->capturing)
+        CK(cudaEventRecord(h->ev_lin_main, h->stream));
+    return VSMPC_OK;
+}
+
+// linearise kernel of a HOST pack staged in d_pack_in[q], on k1_stream, into QP buffer q: overlaps the QP kernel of the tick
+// before on the compute stream.  Ordered behind: the copy of the pack (ev_h2d[q]), the QP / fallback kernels that read buffer
+// q two ticks ago (ev_qp[q]), the last linearise kernel that ran on the compute stream (tick state), and — k1_stream being
+// in order — the linearise kernel of the tick before.
+static int run_linearise_overlapped(vsmpc_handle* h, int q, const double* pack_dev)
+{
+    CK(cudaStreamWaitEvent(h->k1_stream, h->ev_h2d[q], 0));
+    CK(cudaStreamWaitEvent(h->k1_stream, h->ev_qp[q], 0));
+    CK(cudaStreamWaitEvent(h->k1_stream, h->ev_lin_main, 0));
+    h->qd_idx = q;
+    h->d_qd = h->d_qd2[q];
+    if (h->d_fb_list2[q])
+    {
+        h->d_fb_list = h->d_fb_list2[q];
+        h->d_fb_count = h->d_fb_count2[q];
+    }
+    drop_tick_graph(h);         // a captured rollout tick bakes the buffer pointers in
+    CK(launch_linearise(h->d_cfg, h->cfg, h->B, 0, pack_dev, h->d_jpos, nullptr, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
+                        h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd, h->use_ip ? h->d_ip : nullptr, h->d_fb_count,
+                        h->use_jl_table ? h->d_jl : nullptr, h->k1_stream));
+    CK(cudaEventRecord(h->ev_lin[q], h->k1_stream));
+    CK(cudaEventRecord(h->ev_k1[q], h->k1_stream));     // the pack staging buffer q is free again
+    h->lin_on_k1 = true;
     return VSMPC_OK;
 }
 
@@ -724,21 +806,20 @@ int vsmpc_set_state_kinematics(vsmpc_handle* h, const double* kin_state_host)
     CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1[q], 0));
     CK(cudaMemcpyAsync(h->d_ks[q], kin_state_host, (size_t)h->ks_rows * h->B * 8, cudaMemcpyHostToDevice, h->copy_stream));
     CK(cudaEventRecord(h->ev_h2d[q], h->copy_stream));
-    CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[q], 0));
-    CK(launch_kinematics(h->d_kin, h->ks_rows, h->B, h->d_ks[q], h->d_pack_in[q], nullptr, h->stream));
-    double* saved = h->d_pack;
-    h->d_pack = h->d_pack_in[q];
-    int rc = run_linearise(h, 0);
-    h->d_pack = saved;
+    // kinematics + linearise kernels on k1_stream: both overlap the QP kernel of the tick before (run_linearise_overlapped)
+    CK(cudaStreamWaitEvent(h->k1_stream, h->ev_h2d[q], 0));
+    CK(launch_kinematics(h->d_kin, h->ks_rows, h->B, h->d_ks[q], h->d_pack_in[q], nullptr, h->k1_stream));
+    int rc = run_linearise_overlapped(h, q, h->d_pack_in[q]);
     if (rc)
         return rc;
-    CK(cudaEventRecord(h->ev_k1[q], h->stream));
     h->has_state = true;
     return VSMPC_OK;
 }
 
 int vsmpc_get_kinematics_pack(vsmpc_handle* h, double* pack_host)
 {
+    if (h && h->B > 0 && join_linearise(h) != VSMPC_OK)
+        return VSMPC_ERR_CUDA;
     if (!h || h->B <= 0 || !pack_host)
         return VSMPC_ERR_ARG;
     if (!h->d_kin)
@@ -781,14 +862,9 @@ int vsmpc_set_state_strided(vsmpc_handle* h, const double* pack_host, size_t row
     CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1[q], 0));
     CK(copy_soa_h2d(h->d_pack_in[q], pack_host, VSMPC_PACK_DOUBLES, (size_t)h->B, row_stride, h->copy_stream));
     CK(cudaEventRecord(h->ev_h2d[q], h->copy_stream));
-    CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[q], 0));
-    double* saved = h->d_pack;
-    h->d_pack = h->d_pack_in[q];
-    int rc = run_linearise(h, 0);
-    h->d_pack = saved;
+    int rc = run_linearise_overlapped(h, q, h->d_pack_in[q]);
     if (rc)
         return rc;
-    CK(cudaEventRecord(h->ev_k1[q], h->stream));
     h->has_state = true;
     return VSMPC_OK;
 }
@@ -831,6 +907,11 @@ int vsmpc_wait(vsmpc_handle* h)
     if (!h || h->B <= 0)
         return VSMPC_ERR_ARG;
     CK(cudaSetDevice(h->device));
+    {
+        const int rc = join_linearise(h);      // a linearise kernel alone (vsmpc_linearise) runs on its own stream
+        if (rc)
+            return rc;
+    }
     CK(cudaStreamSynchronize(h->stream));
     return VSMPC_OK;
 }
@@ -935,6 +1016,8 @@ int vsmpc_get_full_solution(vsmpc_handle* h, double* z_host)
 
 int vsmpc_get_dynamics(vsmpc_handle* h, double* A, double* BJ, double* BT, double* c, double* dt)
 {
+    if (h && h->B > 0 && join_linearise(h) != VSMPC_OK)
+        return VSMPC_ERR_CUDA;
     if (!h || h->B <= 0 || !A || !BJ || !BT || !c)
         return VSMPC_ERR_ARG;
     if (!h->configured)
@@ -962,6 +1045,8 @@ int vsmpc_get_dynamics(vsmpc_handle* h, double* A, double* BJ, double* BT, doubl
 
 int vsmpc_get_qp_vectors(vsmpc_handle* h, double* q, double* l, double* u)
 {
+    if (h && h->B > 0 && join_linearise(h) != VSMPC_OK)
+        return VSMPC_ERR_CUDA;
     if (!h || h->B <= 0 || !q || !l || !u)
         return VSMPC_ERR_ARG;
     if (!h->configured)
@@ -1008,6 +1093,8 @@ int vsmpc_get_pivot_counts(vsmpc_handle* h, int* n_pivot)
 
 int vsmpc_get_references(vsmpc_handle* h, double* refs_host)
 {
+    if (h && h->B > 0 && join_linearise(h) != VSMPC_OK)
+        return VSMPC_ERR_CUDA;
     if (!h || h->B <= 0 || !refs_host)
         return VSMPC_ERR_ARG;
     if (!h->configured)
@@ -1048,6 +1135,8 @@ int vsmpc_get_hessian(vsmpc_handle* h, int instance, double* P_host)
 
 int vsmpc_get_constraint_matrix(vsmpc_handle* h, int instance, double* A_host)
 {
+    if (h && h->B > 0 && join_linearise(h) != VSMPC_OK)
+        return VSMPC_ERR_CUDA;
     if (!h || h->B <= 0 || !A_host || instance < 0 || instance >= h->B)
         return fail(h, VSMPC_ERR_ARG, "vsmpc_get_constraint_matrix: bad argument");
     if (!h->configured)
@@ -1110,6 +1199,11 @@ static_assert(sizeof(PlantModel) == sizeof(vsmpc_plant_model), "PlantModel must 
 
 static int solve_launch(vsmpc_handle* h)
 {
+    {
+        const int rc = join_linearise(h);      // the QP kernel waits for the linearise kernel wherever it ran
+        if (rc)
+            return rc;
+    }
     g_last_qp_solver.store(h->solver, std::memory_order_relaxed);
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
@@ -1129,6 +1223,8 @@ static int solve_launch(vsmpc_handle* h)
         CK(launch_qp_fallback(h->cfg, h->B, h->fb_slots, h->d_qd, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch,
                               h->d_z, h->d_st, h->d_out, h->d_status, h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0,
                               h->stream));
+    if (!h->capturing)
+        CK(cudaEventRecord(h->ev_qp[h->qd_idx], h->stream));     // QP buffer qd_idx may be refilled after this point
     return VSMPC_OK;
 }
 
@@ -1206,11 +1302,18 @@ int vsmpc_rollout_run(vsmpc_handle* h, int n_ticks, int record_every, double* re
     double* d_rec = nullptr;
     if (n_rec > 0)
         CK(dalloc(&d_rec, (size_t)n_rec * B * PLANT_REC));
+    {
+        const int rcj = join_linearise(h);      // outside any capture: a linearise kernel still running on k1_stream
+        if (rcj)
+            return rcj;
+    }
     if (use_graph && !h->tick_graph)
     {
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        h->capturing = true;
         int rc = e == cudaSuccess ? tick_launch(h, nullptr) : VSMPC_ERR_CUDA;
+        h->capturing = false;
         cudaError_t e2 = cudaStreamEndCapture(h->stream, &g);
         if (e != cudaSuccess || rc != VSMPC_OK || e2 != cudaSuccess)
         {
