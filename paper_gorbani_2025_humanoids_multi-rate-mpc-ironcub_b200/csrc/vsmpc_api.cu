@@ -33,7 +33,8 @@ size_t fallback_pos_ints(const DeviceConfig& cfg);
 void fallback_positions(const DeviceConfig& cfg, int* out);
 cudaError_t launch_qp_fallback(const DeviceConfig& h_cfg, int B, int n_slots, const double* qd, const int* fb_list,
                                const int* fb_count, const int* pos, double* scratch, double* z, double* st, double* out_rows,
-                               int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, cudaStream_t s);
+                               int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, double* out2, int* status2,
+                               cudaStream_t s);
 cudaError_t launch_expand_dynamics(const DeviceConfig* d_cfg, int B, const double* qd, double* A, double* BJ,
                                    double* BT, double* c, cudaStream_t s);
 cudaError_t launch_expand_qp_vectors(const DeviceConfig* d_cfg, int B, const double* qd, double* q, double* l,
@@ -57,14 +58,14 @@ size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
                                 int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
-                                cudaStream_t s);
+                                double* out2, int* status2, cudaStream_t s);
 bool condensed_wide_supported(const DeviceConfig& cfg);
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
-                                     int warm, cudaStream_t s);
+                                     int warm, double* out2, int* status2, cudaStream_t s);
 size_t condensed_wide_wset_bytes(const DeviceConfig& cfg);
 struct KinModelDev;
 const char* kin_prepare(const vsmpc_kin_model& m, KinModelDev& K);
@@ -119,6 +120,7 @@ struct vsmpc_handle
     // the host from there, so that the next QP kernel (which rewrites d_out in place: held outputs) does not wait for PCIe
     double* d_out_stage[2] = {nullptr, nullptr};
     int* d_status_stage[2] = {nullptr, nullptr};
+    int stage_written = -1;   // staging buffer the last QP kernel filled by itself (condensed kernels), -1: none
     // device buffers
     double* d_pack = nullptr;
     double* d_jpos = nullptr;
@@ -453,6 +455,11 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
     }
     A(dalloc(&h->d_z, (size_t)g.n_var * B));
     A(dalloc(&h->d_out, (size_t)VSMPC_OUT_DOUBLES * B));
+    for (int q = 0; q < 2; ++q)
+    {
+        A(dalloc(&h->d_out_stage[q], (size_t)VSMPC_OUT_DOUBLES * B));
+        A(dalloc(&h->d_status_stage[q], (size_t)B));
+    }
     A(dalloc(&h->d_status, (size_t)B));
     A(dalloc(&h->d_nf, (size_t)B));
     A(dalloc(&h->d_ns, (size_t)B));
@@ -944,24 +951,21 @@ int vsmpc_get_output_async(vsmpc_handle* h, double* out_rows_host, int* status_h
     if (!h || h->B <= 0 || !ticket)
         return VSMPC_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    // snapshot on the compute stream (device-to-device, a few microseconds), read-back of the snapshot on its own stream:
-    // neither the next linearise kernel nor the next QP kernel (which rewrites d_out in place) waits for the PCIe copy
+    // the rows are read back from a staging buffer on the read-back stream: neither the next linearise kernel nor the next QP
+    // kernel (which rewrites d_out in place) waits for the PCIe copy.  The condensed kernels fill the staging buffer themselves
+    // (solve_launch); after anything else (other solvers, rollouts, a second read-back of the same tick) a snapshot kernel does.
     const int q = h->out_idx ^= 1;
     const size_t nb_out = (size_t)VSMPC_OUT_DOUBLES * h->B * 8, nb_st = (size_t)h->B * 4;
-    for (int e = 0; e < 2; ++e)
-        if (!h->d_out_stage[e])
-        {
-            CK(dalloc(&h->d_out_stage[e], (size_t)VSMPC_OUT_DOUBLES * h->B));
-            CK(dalloc(&h->d_status_stage[e], (size_t)h->B));
-        }
-    CK(cudaStreamWaitEvent(h->stream, h->ev_out[q], 0));   // the read-back that used this staging buffer two calls ago
+    if (h->stage_written != q)
     {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out[q], 0));   // the read-back that used this staging buffer two calls ago
         const int threads = 256;
         const int blocks = (int)std::min<size_t>(592, (nb_out / 16 + threads - 1) / threads);
         snapshot_outputs_kernel<<<blocks, threads, 0, h->stream>>>(nb_out / 8, h->B, h->d_out, h->d_status, h->d_out_stage[q],
                                                                    h->d_status_stage[q]);
         CK(cudaGetLastError());
     }
+    h->stage_written = -1;
     CK(cudaEventRecord(h->ev_solved, h->stream));
     CK(cudaStreamWaitEvent(h->out_stream, h->ev_solved, 0));
     if (out_rows_host)
@@ -1205,14 +1209,28 @@ static int solve_launch(vsmpc_handle* h)
             return rc;
     }
     g_last_qp_solver.store(h->solver, std::memory_order_relaxed);
+    // the condensed kernels (and the fallback kernel behind them) also write every instance's row + status into the staging
+    // buffer the next vsmpc_get_output_async will read back: no snapshot kernel between this tick and the next.  The read-back
+    // that used this staging buffer two calls ago must be over.
+    double* out2 = nullptr;
+    int* status2 = nullptr;
+    h->stage_written = -1;
+    if (!h->capturing && (h->solver == 0 || h->solver == SOLVER_WIDE))
+    {
+        const int q = h->out_idx ^ 1;
+        CK(cudaStreamWaitEvent(h->stream, h->ev_out[q], 0));
+        out2 = h->d_out_stage[q];
+        status2 = h->d_status_stage[q];
+        h->stage_written = q;
+    }
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
                                h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count, h->fb_mode,
-                               h->stream));
+                               out2, status2, h->stream));
     else if (h->solver == SOLVER_WIDE)
         CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
                                     h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count,
-                                    h->fb_mode, h->d_wset, h->warm ? 1 : 0, h->stream));
+                                    h->fb_mode, h->d_wset, h->warm ? 1 : 0, out2, status2, h->stream));
     else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));
@@ -1222,7 +1240,7 @@ static int solve_launch(vsmpc_handle* h)
     if (h->fb_mode != 0 && (h->solver == 0 || h->solver == SOLVER_WIDE))
         CK(launch_qp_fallback(h->cfg, h->B, h->fb_slots, h->d_qd, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch,
                               h->d_z, h->d_st, h->d_out, h->d_status, h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0,
-                              h->stream));
+                              out2, status2, h->stream));
     if (!h->capturing)
         CK(cudaEventRecord(h->ev_qp[h->qd_idx], h->stream));     // QP buffer qd_idx may be refilled after this point
     return VSMPC_OK;

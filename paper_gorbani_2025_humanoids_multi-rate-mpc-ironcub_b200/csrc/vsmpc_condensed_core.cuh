@@ -522,4 +522,20 @@ __device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, cons
     return false;
 }
 
+// Copy of an instance's output row and status into the staging buffers of the asynchronous read-back (one warp; the row was
+// written — or is being held — by this warp).  vsmpc_get_output_async then reads the staging buffer back without a snapshot
+// kernel between the QP kernel and the next tick.
+__device__ __forceinline__ void cd_stage_outputs(const double* o, const int* status, int inst, int lane,
+                                                 double* __restrict__ out2, int* __restrict__ status2)
+{
+    if (!out2)
+        return;
+    __syncwarp();
+    double* o2 = out2 + (size_t)inst * VSMPC_OUT_DOUBLES;
+    for (int e = lane; e < VSMPC_OUT_DOUBLES; e += 32)
+        o2[e] = o[e];
+    if (lane == 0)
+        status2[inst] = status[inst];
+}
+
 } // namespace vsmpc

@@ -368,7 +368,8 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
                   double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
                   double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
                   int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,
-                  int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode)
+                  int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode, double* __restrict__ out2,
+                  int* __restrict__ status2)
 {
     using CdSmem = CdSmemT<PIPE ? CD_PIPE_SLOTS : 2>;
     using CdCtx = CdCtxT<CdSmem>;
@@ -915,7 +916,10 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
         n_pivot[inst] = sm.flags[2];
     }
     if (!solved)
+    {
+        cd_stage_outputs(o, status, inst, lane, out2, status2);     // the held row
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
+    }
     const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
     if (cd_forward(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl) && lane == 0)
     {
@@ -926,6 +930,7 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
         if (fb_mode != 0)
             fb_list[atomicAdd(fb_count, 1)] = inst;
     }
+    cd_stage_outputs(o, status, inst, lane, out2, status2);
     PHASE_CLK(3);
 }
 
@@ -934,8 +939,8 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
     const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all, double* __restrict__ ws_all,      \
         double* __restrict__ z_all, double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,       \
         int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,     \
-        int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode
-#define CD_KERNEL_PASS cfgv, B, qd_all, ws_all, z_all, st, out_rows, status, n_factor, n_solve, n_pivot, ws_stride, want_z, fb_list, fb_count, fb_mode
+        int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode, double* __restrict__ out2, int* __restrict__ status2
+#define CD_KERNEL_PASS cfgv, B, qd_all, ws_all, z_all, st, out_rows, status, n_factor, n_solve, n_pivot, ws_stride, want_z, fb_list, fb_count, fb_mode, out2, status2
 // large batches: eight CTAs per SM, 128 registers
 __global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel(CD_KERNEL_ARGS) { qp_condensed_body<false>(CD_KERNEL_PASS); }
 // (a 144-register build for the one wave of seven CTAs per SM at B = 1024 was tried: 207 us instead of 165 — the register file
@@ -967,7 +972,7 @@ size_t condensed_ws_doubles(const DeviceConfig& cfg)
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
                                 int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
-                                cudaStream_t s)
+                                double* out2, int* status2, cudaStream_t s)
 {
     // small batches (at most four CTAs per SM): the decoupled pipeline, which shortens a single solve; otherwise lock step
     int dev = 0, sms = 148;
@@ -983,10 +988,10 @@ cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h
     const int fbm = fb_list && fb_count ? fb_mode : 0;
     if (B <= pipe_ctas * sms)
         qp_condensed_kernel_pipe<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
-                                                          want_z, fb_list, fb_count, fbm);
+                                                          want_z, fb_list, fb_count, fbm, out2, status2);
     else
         qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
-                                                     want_z, fb_list, fb_count, fbm);
+                                                     want_z, fb_list, fb_count, fbm, out2, status2);
     return cudaGetLastError();
 }
 

@@ -416,7 +416,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
                          int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride,
                          int want_z, int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode,
-                         signed char* __restrict__ wset_all, int warm)
+                         signed char* __restrict__ wset_all, int warm, double* __restrict__ out2, int* __restrict__ status2)
 {
     extern __shared__ __align__(16) unsigned char cw_raw[];
     CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
@@ -926,7 +926,10 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         n_pivot[inst] = sm.flags[2];
     }
     if (stat != VSMPC_STATUS_SOLVED)
+    {
+        cd_stage_outputs(o, status, inst, lane, out2, status2);     // the held row
         return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
+    }
     const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
     if (cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st, sm.ostage, jl) && lane == 0)
     {
@@ -935,6 +938,7 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         if (fb_mode != 0)
             fb_list[atomicAdd(fb_count, 1)] = inst;
     }
+    cd_stage_outputs(o, status, inst, lane, out2, status2);
     WCLK(7);
 }
 
@@ -980,7 +984,7 @@ size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
-                                     int warm, cudaStream_t s)
+                                     int warm, double* out2, int* status2, cudaStream_t s)
 {
     static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
     const CwLayout L = cw_layout(h_cfg);
@@ -994,14 +998,14 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                       n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm);
+                                                                       n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2);
     }
     else if (L.G == 3)
     {
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                        n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm);
+                                                                        n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2);
     }
     else
     {
@@ -1010,7 +1014,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
         // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
         qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
-            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm);
+            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2);
     }
     return cudaGetLastError();
 }

@@ -131,7 +131,8 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
                    const int* __restrict__ fb_list, const int* __restrict__ fb_count, const int* __restrict__ pos,
                    double* __restrict__ scratch, size_t slot_doubles, double* __restrict__ z_all, double* __restrict__ st,
                    double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
-                   int* __restrict__ n_solve, int* __restrict__ n_pivot, int want_z, int use_window)
+                   int* __restrict__ n_solve, int* __restrict__ n_pivot, int want_z, int use_window, double* __restrict__ out2,
+                   int* __restrict__ status2)
 {
     const DeviceConfig& cfg = cfgv;
     __shared__ double A[NX * NX], BJ[NX * NJ], BT[NX * NT], cv[NX];
@@ -866,6 +867,13 @@ qp_fallback_kernel(const __grid_constant__ DeviceConfig cfgv, const FbLayout L, 
             }
         }
         __syncthreads();
+        if (out2)
+        { // staging buffers of the asynchronous read-back (cd_stage_outputs): the row as it stands now
+            if (tid < VSMPC_OUT_DOUBLES)
+                out2[(size_t)inst * VSMPC_OUT_DOUBLES + tid] = out_rows[(size_t)inst * VSMPC_OUT_DOUBLES + tid];
+            if (tid == 0)
+                status2[inst] = status[inst];
+        }
     }
 }
 
@@ -928,7 +936,8 @@ void fallback_positions(const DeviceConfig& cfg, int* out)
 
 cudaError_t launch_qp_fallback(const DeviceConfig& h_cfg, int B, int n_slots, const double* qd, const int* fb_list,
                                const int* fb_count, const int* pos, double* scratch, double* z, double* st, double* out_rows,
-                               int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, cudaStream_t s)
+                               int* status, int* n_factor, int* n_solve, int* n_pivot, int want_z, double* out2, int* status2,
+                               cudaStream_t s)
 {
     const FallbackPlan P = fb_plan(h_cfg);
     static bool attr_set[64] = {};
@@ -937,7 +946,7 @@ cudaError_t launch_qp_fallback(const DeviceConfig& h_cfg, int B, int n_slots, co
         return e;
     qp_fallback_kernel<<<n_slots, FB_THREADS, fb_dyn_bytes(P.L), s>>>(h_cfg, P.L, B, qd, fb_list, fb_count, pos, scratch, P.slot_doubles,
                                                                      z, st, out_rows, status, n_factor, n_solve, n_pivot, want_z,
-                                                                     fb_use_window(P.L) ? 1 : 0);
+                                                                     fb_use_window(P.L) ? 1 : 0, out2, status2);
     return cudaGetLastError();
 }
 
