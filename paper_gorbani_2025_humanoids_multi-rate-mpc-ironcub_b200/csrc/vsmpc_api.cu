@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -618,6 +619,24 @@ static int run_linearise(vsmpc_handle* h, int mode)
 // in order — the linearise kernel of the tick before.
 static int run_linearise_overlapped(vsmpc_handle* h, int q, const double* pack_dev)
 {
+    static int no_overlap = -1;     // development: VSMPC_NO_OVERLAP=1 keeps the linearise kernel on the compute stream
+    if (no_overlap < 0)
+    {
+        const char* e = getenv("VSMPC_NO_OVERLAP");
+        no_overlap = e ? atoi(e) : 0;
+    }
+    if (no_overlap)
+    {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[q], 0));
+        double* saved = h->d_pack;
+        h->d_pack = const_cast<double*>(pack_dev);
+        const int rc = run_linearise(h, 0);
+        h->d_pack = saved;
+        if (rc)
+            return rc;
+        CK(cudaEventRecord(h->ev_k1[q], h->stream));
+        return VSMPC_OK;
+    }
     CK(cudaStreamWaitEvent(h->k1_stream, h->ev_h2d[q], 0));
     CK(cudaStreamWaitEvent(h->k1_stream, h->ev_qp[q], 0));
     CK(cudaStreamWaitEvent(h->k1_stream, h->ev_lin_main, 0));
