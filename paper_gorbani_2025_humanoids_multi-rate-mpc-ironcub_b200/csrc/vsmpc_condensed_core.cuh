@@ -24,6 +24,36 @@ struct alignas(16) CdSlot
 
 enum : int { TK_NONE = 0, TK_STAGE = 1, TK_PROP = 2, TK_SCHUR = 3 };
 
+// mbarriers (shared memory) of the decoupled A -> B pipeline (small batches of the reference-horizon kernel; the long-horizon kernel, where FREE and B2A count every column warp): every lane of the posting
+// warp arrives (count 32), the waiting warp polls the phase parity with mbarrier.try_wait (default .acquire.cta / .release.cta
+// semantics order the published data).  FULL + s: slot s published (A posts, B waits); FREE + s: slot s consumed (B posts, A
+// waits); B2A: warp B's propagation of the held-block knot done (A waits before the Schur step); SCHUR: Schur step published.
+constexpr int CD_PIPE_SLOTS = 3;
+constexpr int MB_FULL = 0, MB_FREE = CD_PIPE_SLOTS, MB_B2A = 2 * CD_PIPE_SLOTS, MB_SCHUR = 2 * CD_PIPE_SLOTS + 1,
+              MB_COUNT = 2 * CD_PIPE_SLOTS + 2;
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_post(unsigned long long* b)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+    unsigned done;
+    do
+    {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+
+
 // y <- T_x^T y,  T_x = I + dt A_c   (structure: SURVEY App. A-3)
 __device__ __forceinline__ void applyTtx(double (&y)[NX], const double* __restrict__ cf, double dt)
 {

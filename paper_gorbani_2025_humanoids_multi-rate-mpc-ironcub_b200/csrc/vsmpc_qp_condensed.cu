@@ -38,34 +38,6 @@ constexpr int WSC_STAGE = NJ * NX + 2 * NJ * NL; // 720
 
 constexpr int CD_MAXN = 32;   // knots kept in shared memory (dt grid)
 
-// mbarriers (shared memory) of the decoupled A -> B pipeline (small batches, see qp_condensed_kernel): every lane of the posting
-// warp arrives (count 32), the waiting warp polls the phase parity with mbarrier.try_wait (default .acquire.cta / .release.cta
-// semantics order the published data).  FULL + s: slot s published (A posts, B waits); FREE + s: slot s consumed (B posts, A
-// waits); B2A: warp B's propagation of the held-block knot done (A waits before the Schur step); SCHUR: Schur step published.
-constexpr int CD_PIPE_SLOTS = 3;
-constexpr int MB_FULL = 0, MB_FREE = CD_PIPE_SLOTS, MB_B2A = 2 * CD_PIPE_SLOTS, MB_SCHUR = 2 * CD_PIPE_SLOTS + 1,
-              MB_COUNT = 2 * CD_PIPE_SLOTS + 2;
-__device__ __forceinline__ void mbar_init(unsigned long long* b, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_post(unsigned long long* b)
-{
-    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity)
-{
-    const unsigned a = (unsigned)__cvta_generic_to_shared(b);
-    unsigned done;
-    do
-    {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done)
-                     : "r"(a), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
-
 template <int NSLOT> struct alignas(16) CdSmemT
 {
     double cf[CCF];
