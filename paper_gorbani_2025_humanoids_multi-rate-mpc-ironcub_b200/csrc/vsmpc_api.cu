@@ -59,7 +59,8 @@ size_t condensed_ws_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
                                 int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
-                                double* out2, int* status2, cudaStream_t s);
+                                double* out2, int* status2, unsigned* jlset, cudaStream_t s);
+size_t condensed_jlset_words();
 bool condensed_wide_supported(const DeviceConfig& cfg);
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
@@ -160,6 +161,8 @@ struct vsmpc_handle
     int ks_rows = 0;
     signed char* d_wset = nullptr;   // long-horizon kernel: working set of the last solve per instance (warm start)
     size_t wset_bytes = 0;
+    unsigned* d_jlset = nullptr;     // reference-horizon kernel with joint-limit rows: working set of the joint boxes per instance
+    size_t jlset_bytes = 0;
     bool warm = true;
     double* d_jl = nullptr;   // per-instance joint limits [rad], SoA double[16][B]: 8 lower rows, 8 upper rows (optional)
     bool use_jl_table = false;
@@ -454,6 +457,13 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         if (ok)
             A(cudaMemset(h->d_wset, 0xFF, h->wset_bytes));     // all-lower vertex
     }
+    if (h->solver == 0 && g.use_jl)
+    {
+        h->jlset_bytes = condensed_jlset_words() * sizeof(unsigned) * B;
+        A(dalloc(&h->d_jlset, h->jlset_bytes / sizeof(unsigned)));
+        if (ok)
+            A(cudaMemset(h->d_jlset, 0, h->jlset_bytes));         // nothing clamped
+    }
     A(dalloc(&h->d_z, (size_t)g.n_var * B));
     A(dalloc(&h->d_out, (size_t)VSMPC_OUT_DOUBLES * B));
     for (int q = 0; q < 2; ++q)
@@ -531,7 +541,7 @@ int vsmpc_destroy(vsmpc_handle* h)
     void* ptrs[] = {h->d_cfg, h->d_pack, h->d_jpos, h->d_phase, h->d_st, h->d_si, h->d_alpha, h->d_tpos,
                     h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd2[0], h->d_qd2[1], h->d_ws, h->d_scratch, h->d_z, h->d_out,
                     h->d_status, h->d_nf, h->d_ns, h->d_np, h->d_fb_list2[0], h->d_fb_list2[1], h->d_fb_count2[0],
-                    h->d_fb_count2[1], h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset, h->d_kin, h->d_ks[0], h->d_ks[1],
+                    h->d_fb_count2[1], h->d_fb_pos, h->d_fb_scratch, h->d_pm, h->d_ps, h->d_pp, h->d_ip, h->d_jl, h->d_wset, h->d_jlset, h->d_kin, h->d_ks[0], h->d_ks[1],
                     h->d_out_stage[0], h->d_out_stage[1], h->d_status_stage[0], h->d_status_stage[1], h->d_pack_in[0], h->d_pack_in[1], h->d_nn, h->d_thr_sub};
     for (int q = 0; q < 2; ++q)
     {
@@ -605,6 +615,8 @@ static int run_linearise(vsmpc_handle* h, int mode)
         return rc;
     if (mode == 1 && h->d_wset)     // IMPCProblem::configure: no previous solve, the guess is the all-lower vertex
         CK(cudaMemsetAsync(h->d_wset, 0xFF, h->wset_bytes, h->stream));
+    if (mode == 1 && h->d_jlset)
+        CK(cudaMemsetAsync(h->d_jlset, 0, h->jlset_bytes, h->stream));
     CK(launch_linearise(h->d_cfg, h->cfg, h->B, mode, h->d_pack, h->d_jpos, mode == 1 ? h->d_phase : nullptr, h->d_st,
                         h->d_si, h->d_alpha, h->d_tpos, h->d_tvel, h->d_trpy, h->d_trpyd, h->d_qd,
                         h->use_ip ? h->d_ip : nullptr, h->d_fb_count, h->use_jl_table ? h->d_jl : nullptr, h->stream));
@@ -726,6 +738,8 @@ int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const doub
         return fail(h, VSMPC_ERR_STATE, "vsmpc_set_joint_limits: the handle was created without use_joint_limits");
     CK(cudaSetDevice(h->device));
     drop_tick_graph(h);
+    if (h->d_jlset)       // new boxes: the working set of the last solve is no guess for them
+        CK(cudaMemsetAsync(h->d_jlset, 0, h->jlset_bytes, h->stream));
     if (!q_min_host && !q_max_host)
     {
         h->use_jl_table = false;
@@ -1245,7 +1259,7 @@ static int solve_launch(vsmpc_handle* h)
     if (h->solver == 0)
         CK(launch_qp_condensed(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_z, h->d_st, h->d_out, h->d_status,
                                h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count, h->fb_mode,
-                               out2, status2, h->stream));
+                               out2, status2, h->warm ? h->d_jlset : nullptr, h->stream));
     else if (h->solver == SOLVER_WIDE)
         CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
                                     h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count,

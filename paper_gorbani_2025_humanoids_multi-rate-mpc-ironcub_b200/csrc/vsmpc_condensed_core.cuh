@@ -203,14 +203,57 @@ template <class SM> struct CdCtxT
     int kS;       // knot where the held joint block is eliminated (-1: none)
 };
 
+// ---- joint increments held on a bound of their box (optional joint-limit rows; JL builds only) -----------------------
+// Joint block k of an instance may have components CLAMPED: cm bit c = at the upper bound, bit 8 + c = at the lower one.
+// A clamped component is a constant b_c in the elimination of its block (tools/condensed_model.py, ClampedCondensedQP):
+//   * H_uu is inverted on the free components (clamped rows / columns replaced by the identity), so row c of
+//     K = H_uu^-1 H_ux and of F = H_uu^-1 H_utheta come out as the RAW rows H_ux[c, :] and H_utheta[c, :] — exactly what the
+//     multiplier of the bound needs in the forward pass — and P, Psi, Om skip them;
+//   * the free rows see the constants through  H_utheta[m, affine] += sum_c H_uu[m][c] b_c  (hb, published by warp A);
+//   * the constants enter the value function through  Psi[:, affine] += sum_c b_c H_ux[c, :]'  and
+//     Om[:, affine] += b_c H_utheta[c, :]' (+ transpose).
+struct CdClamp
+{
+    unsigned cm;              // 0: nothing clamped in this block (the only value outside the JL builds)
+    const double* jb;         // lower bounds [8], upper bounds [8] of the joint increments (shared memory)
+    double* hb;               // [8] out (warp A) / in (warp B): sum_c H_uu[m][c] b_c
+    double* uraw;             // [8][8] out: H_uu (with R) of the block, for the multipliers (workspace)
+};
+__device__ __forceinline__ unsigned cd_clamped(unsigned cm) { return (cm | (cm >> 8)) & 0xffu; }
+__device__ __forceinline__ double cd_bval(const double* __restrict__ jb, unsigned cm, int c)
+{
+    return ((cm >> c) & 1u) ? jb[NJ + c] : (((cm >> (8 + c)) & 1u) ? jb[c] : 0.0);
+}
+
 // ---- warp A --------------------------------------------------------------------------------------------------
 // steps i-k of a knot: invert H_uu (own = this lane's pair of it), K = H_uu^-1 H_ux, P <- P - H_ux' K
-template <class SM>
+template <class SM, bool JL = false>
 __device__ __forceinline__ bool a_eliminate(const CdCtxT<SM>& c, CdSlot& sl, double (&p)[NX], const double (&hux)[NJ],
-                                            double2 own, double* __restrict__ wsk)
+                                            double2 own, double* __restrict__ wsk, CdClamp cl = CdClamp{0u, nullptr, nullptr, nullptr})
 {
     SM& sm = c.sm;
     const int lane = c.lane;
+    unsigned cany = 0u;
+    if constexpr (JL)
+    {
+        if (cl.cm != 0u)
+        {
+            cany = cd_clamped(cl.cm);
+            const int r = lane & 7, q = lane >> 3;
+            cl.uraw[r * NJ + 2 * q] = own.x;
+            cl.uraw[r * NJ + 2 * q + 1] = own.y;
+            double part = own.x * cd_bval(cl.jb, cl.cm, 2 * q) + own.y * cd_bval(cl.jb, cl.cm, 2 * q + 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 8);
+            part += __shfl_xor_sync(0xffffffffu, part, 16);
+            if (lane < NJ)
+                cl.hb[lane] = part;
+            const bool rc = (cany >> r) & 1u;
+            if (rc || ((cany >> (2 * q)) & 1u))
+                own.x = (r == 2 * q) ? 1.0 : 0.0;
+            if (rc || ((cany >> (2 * q + 1)) & 1u))
+                own.y = (r == 2 * q + 1) ? 1.0 : 0.0;
+        }
+    }
     const bool ok = gj8(sl.Hinv, sm.Mt, own, lane);   // Mt: free between the transposition and the gain rows
     if (lane < NX)
     {
@@ -236,6 +279,11 @@ __device__ __forceinline__ bool a_eliminate(const CdCtxT<SM>& c, CdSlot& sl, dou
 #pragma unroll 2
         for (int m = 0; m < NJ; ++m)
         {
+            if constexpr (JL)
+            {
+                if ((cany >> m) & 1u)
+                    continue;        // clamped component: its K row holds the raw H_ux row, P does not see it
+            }
             const double h = sl.Hux[m * NX + lane];
             const double2* kr = reinterpret_cast<const double2*>(sm.Mt + m * NX);
 #pragma unroll
@@ -428,12 +476,19 @@ __device__ __forceinline__ void cd_schedule(int t, int N, int kS, int& ta, int& 
 // joint-limit rows on (jl != nullptr: QD_JLO / QD_JHI of this instance) a joint increment outside its box means that the
 // minimiser of the problem WITHOUT those rows is not the answer: nothing is committed, the function returns true and the
 // caller hands the instance to the fallback kernel, which carries the joint boxes in its active set.
-template <class SM>
-__device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, const double* __restrict__ ws, int stage,
-                                           const double* __restrict__ theta, const double* __restrict__ fth,
-                                           double* __restrict__ xs, int lane, int B, int inst, double* __restrict__ z,
-                                           double* __restrict__ o, double* __restrict__ st, double* __restrict__ ostage,
-                                           const double* __restrict__ jl)
+// JL builds (reference-horizon kernel with joint-limit rows): `clamp` holds the working set of the joint boxes per block (CdClamp);
+// a clamped increment is set to its bound and its multiplier is read off the raw rows the elimination left in its place
+// (H_ux[c, :] x in the gain row, H_utheta[c, :] theta in fth, H_uu[c, :] in uraw_all); the function writes the NEXT working set
+// (violated free components join at the bound they crossed, clamped ones with the wrong multiplier sign leave — a primal-dual
+// active-set step on all blocks at once) and returns 1 if it differs from the one this pass was factorised with, 0 at the
+// fixed point (outputs committed), 2 on a non-finite increment.  Without JL: 1 = a joint box is violated (fallback kernel).
+template <class SM, bool JL = false>
+__device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const double* __restrict__ ws, int stage,
+                                          const double* __restrict__ theta, const double* __restrict__ fth,
+                                          double* __restrict__ xs, int lane, int B, int inst, double* __restrict__ z,
+                                          double* __restrict__ o, double* __restrict__ st, double* __restrict__ ostage,
+                                          const double* __restrict__ jl, unsigned* __restrict__ clamp = nullptr,
+                                          const double* __restrict__ uraw_all = nullptr)
 {
     const int N = cfg.N, Nc = cfg.Nc, nv = 4 * cfg.nblk;
     CdFwdTab tab;
@@ -449,8 +504,9 @@ __device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, cons
     __syncwarp();
     const int ka = lane & 7, kq = lane >> 3;   // gain row / quarter of the state handled by this lane
     const int j0 = kq * 7, jn = kq == 3 ? 5 : 7;
-    const double jlo = jl ? jl[ka] - 1e-9 : -INFINITY, jhi = jl ? jl[NJ + ka] + 1e-9 : INFINITY;
-    bool viol = false;
+    const double blo = jl ? jl[ka] : -INFINITY, bhi = jl ? jl[NJ + ka] : INFINITY;
+    const double jlo = blo - 1e-9, jhi = bhi + 1e-9;
+    bool viol = false, bad = false;
     // gain rows are prefetched one knot ahead (their addresses do not depend on the state) into the register set the
     // other knot parity uses, so that no instruction of knot k waits for the loads of knot k+1
     double kA[7], kB[7];
@@ -486,8 +542,24 @@ __device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, cons
             part += part2;
             part += __shfl_xor_sync(0xffffffffu, part, 8);
             part += __shfl_xor_sync(0xffffffffu, part, 16);
-            const double u = -part - fth[k * NJ + ka];
-            viol = viol || !(u >= jlo && u <= jhi);
+            double u = -part - fth[k * NJ + ka];
+            unsigned cm = 0u;
+            double g0 = 0.0;
+            bool cup = false, clo = false;
+            if constexpr (JL)
+            {
+                cm = clamp[k];
+                cup = (cm >> ka) & 1u;
+                clo = (cm >> (8 + ka)) & 1u;
+                if (cup || clo)
+                {
+                    g0 = -u;                 // H_ux[c, :] x_k + H_utheta[c, :] theta (raw rows in place of K and F)
+                    u = cup ? bhi : blo;
+                }
+                bad = bad || !isfinite(u);
+            }
+            else
+                viol = viol || !(u >= jlo && u <= jhi);
             if (lane < NJ)
             {
                 dqs[lane] = u;
@@ -495,6 +567,26 @@ __device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, cons
                     ostage[VSMPC_OUT_DELTA_Q + lane] = u;
                 if (z)
                     z[NX * (N + 1) + k * NJ + lane] = u;
+            }
+            if constexpr (JL)
+            {
+                __syncwarp();
+                double grad = g0;
+                if (cm != 0u && (cup || clo) && lane < NJ)
+                {
+                    const double* __restrict__ ur = uraw_all + k * (NJ * NJ) + ka * NJ;
+#pragma unroll
+                    for (int m = 0; m < NJ; ++m)
+                        grad = fma(ur[m], dqs[m], grad);
+                }
+                // next working set of this block: the multiplier of an upper bound is -grad, of a lower bound +grad
+                const bool nup = (cup || clo) ? (cup && grad <= 0.0) : (u > jhi);
+                const bool nlo = (cup || clo) ? (clo && grad >= 0.0) : (u < jlo);
+                const unsigned nm = (__ballot_sync(0xffffffffu, nup && lane < NJ) & 0xffu) |
+                                    ((__ballot_sync(0xffffffffu, nlo && lane < NJ) & 0xffu) << 8);
+                viol = viol || (nm != cm);
+                if (lane == 0)
+                    clamp[k] = nm;
             }
         }
         __syncwarp();
@@ -527,8 +619,10 @@ __device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, cons
         if (k + 1 < N)
             knot(k + 1, kB, kA);
     }
+    if (__any_sync(0xffffffffu, bad))
+        return 2;
     if (__any_sync(0xffffffffu, viol))
-        return true;     // a joint increment left its box: nothing committed (z holds the unconstrained minimiser)
+        return 1;     // a joint increment left its box / the working set moved: nothing committed
     // remaining outputs (variableSamplingMPC.cpp:96-108,138-151), then the commit of the staged ones
     __syncwarp();
     for (int e = lane; e < VSMPC_OUT_JOINTS_REF; e += 32)
@@ -549,7 +643,7 @@ __device__ __forceinline__ bool cd_forward(const DeviceConfig& cfg, SM& sm, cons
         for (int e = lane; e < nv; e += 32)
             z[base + e] = theta[e];
     }
-    return false;
+    return 0;
 }
 
 // Copy of an instance's output row and status into the staging buffers of the asynchronous read-back (one warp; the row was

@@ -38,7 +38,20 @@ constexpr int WSC_STAGE = NJ * NX + 2 * NJ * NL; // 720
 
 constexpr int CD_MAXN = 32;   // knots kept in shared memory (dt grid)
 
-template <int NSLOT> struct alignas(16) CdSmemT
+// working set of the optional joint boxes (JL build only: the other builds keep their shared-memory footprint)
+template <bool JL> struct CdJlSmem
+{
+    unsigned clamp[CD_MAXN];    // per joint block: bit c = increment c held at its upper bound, bit 8 + c at its lower bound
+    double jb[2 * NJ];          // bounds of the increments: lower [8], upper [8]  (QD_JLO / QD_JHI)
+    double hb[2][NJ];           // warp A -> warp B, per mailbox slot: sum_c H_uu[m][c] b_c
+};
+template <> struct CdJlSmem<false>
+{
+};
+constexpr int CD_JL_PASSES = 8;   // factorisations per solve before the instance is handed to the fallback kernel
+constexpr int WSC_U = NJ * NJ;    // per joint block, behind the Nc stages of the workspace: raw H_uu [8][8]
+
+template <int NSLOT, bool JL = false> struct alignas(16) CdSmemT : CdJlSmem<JL>
 {
     double cf[CCF];
     alignas(16) double lam[6 * NJ];         // dt-free B_J rows: [q][a], q = 0..2 linear, 3..5 angular momentum
@@ -114,15 +127,18 @@ __device__ __forceinline__ bool rp_pivot(double (&t)[CD_MAXW], double* __restric
 // down-date of the parameter columns with the eliminated block: F = H_uu^-1 H_utheta, Psi -= H_ux' F.  The matching
 // down-date of Om (Om -= H_utheta' F) is NOT done knot by knot: H_utheta and F of every elimination knot are stacked
 // in the workspace and contracted once after the recursion on the FP64 tensor cores (cd_omega_downdate).
-template <class CdCtx>
+// cany (JL build): clamped components of the block — their F rows come out as the raw H_utheta rows (identity rows of the
+// masked inverse; the forward pass reads the multiplier off them), their H_utheta rows are stacked as zeros (no share in the
+// Om down-date) and Psi skips them.
+template <bool JL = false, class CdCtx>
 __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&s)[NX], const double (&hut)[NJ],
-                                           double* __restrict__ wsk, bool clear_col)
+                                           double* __restrict__ wsk, bool clear_col, unsigned cany = 0u)
 {
     const int lane = c.lane;
     double* Fs = sl.PD;   // the P'D columns of this knot were consumed by b_prop: reuse as F [l][LDH]
 #pragma unroll
     for (int m = 0; m < NJ; ++m)
-        wsk[WSC_H + m * NL + lane] = hut[m];
+        wsk[WSC_H + m * NL + lane] = (JL && ((cany >> m) & 1u)) ? 0.0 : hut[m];
     {
         const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
 #pragma unroll 1
@@ -146,6 +162,11 @@ __device__ __forceinline__ void b_downdate(const CdCtx& c, CdSlot& sl, double (&
 #pragma unroll 2
         for (int m = 0; m < NJ; ++m)
         {
+            if constexpr (JL)
+            {
+                if ((cany >> m) & 1u)
+                    continue;
+            }
             const double f = Fs[lane * LDH + m];
             const double2* hr = reinterpret_cast<const double2*>(sl.Hux + m * NX);
 #pragma unroll
@@ -334,16 +355,17 @@ __device__ __forceinline__ void b_prop(const CdCtx& c, int k, CdSlot& sl, bool t
 // spends a quarter of the recursion waiting at the common barrier (132 k cycles against 99 k busy); without contention that
 // wait is pure latency of a single solve.  At B = 1024 (seven CTAs per SM) the same pipeline gained nothing and its 30 KB of
 // shared memory cost the eighth CTA per SM (profiles/r02_k2_experiments.md), so the launcher uses it for small batches only.
-template <bool PIPE>
+template <bool PIPE, bool JL>
 __device__ __forceinline__ void
 qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd_all,
                   double* __restrict__ ws_all, double* __restrict__ z_all, double* __restrict__ st,
                   double* __restrict__ out_rows, int* __restrict__ status, int* __restrict__ n_factor,
                   int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,
                   int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode, double* __restrict__ out2,
-                  int* __restrict__ status2)
+                  int* __restrict__ status2, unsigned* __restrict__ jlset)
 {
-    using CdSmem = CdSmemT<PIPE ? CD_PIPE_SLOTS : 2>;
+    static_assert(!(PIPE && JL), "the joint-box working set is built into the lock-step loop only");
+    using CdSmem = CdSmemT<PIPE ? CD_PIPE_SLOTS : 2, JL>;
     using CdCtx = CdCtxT<CdSmem>;
     __shared__ CdSmem sm;
     const DeviceConfig& cfg = cfgv;   // kernel parameter space (constant bank)
@@ -358,14 +380,23 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
     PHASE_CLK(0);
     // ---- stage the QP data: coefficients, reference window; finiteness gate --------------------------------------
     bool fin = true;
-    for (int e = threadIdx.x; e < cfg.qd_stride; e += CD_THREADS)
+    // (three loads in flight per thread: the block is read once, a load per trip would cost an L2 round trip each)
+    for (int e0 = threadIdx.x; e0 < cfg.qd_stride; e0 += 3 * CD_THREADS)
     {
-        const double v = qd[e];
-        fin = fin && isfinite(v);
-        if (e < CCF)
-            sm.cf[e] = v;
-        else if (e >= QD_XREF && e < QD_XREF + 12 * NC)
-            sm.xref[e - QD_XREF] = v;
+        double v[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            v[u] = e0 + u * CD_THREADS < cfg.qd_stride ? qd[e0 + u * CD_THREADS] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+        {
+            const int e = e0 + u * CD_THREADS;
+            fin = fin && isfinite(v[u]);
+            if (e < CCF)
+                sm.cf[e] = v[u];
+            else if (e >= QD_XREF && e < QD_XREF + 12 * NC)
+                sm.xref[e - QD_XREF] = v[u];
+        }
     }
     for (int e = threadIdx.x; e < NLO * NLO; e += CD_THREADS)
         sm.Om[e] = 0.0;
@@ -379,8 +410,30 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
         sm.lam[e] = qd[(e < 3 * NJ ? QD_LLIN : QD_LANG - 3 * NJ) + e];
     if (PIPE && threadIdx.x < MB_COUNT)
         mbar_init(&sm.mbar[threadIdx.x], 32);
+    if constexpr (JL)
+    {
+        if (threadIdx.x < 2 * NJ)
+            sm.jb[threadIdx.x] = qd[QD_JLO + threadIdx.x];
+        // warm start: the working set the last solve of this instance ended with (zeros after configure)
+        if (threadIdx.x < CD_MAXN)
+            sm.clamp[threadIdx.x] = (jlset && threadIdx.x < Nc) ? jlset[(size_t)inst * CD_MAXN + threadIdx.x] : 0u;
+    }
     const bool all_fin = __syncthreads_and(fin);
+    // JL build: primal-dual active set on the joint boxes around the whole solve — pass p factorises with the working set pass
+    // p - 1 left in sm.clamp (empty at pass 0), the forward pass writes the next one; a solve without an active joint bound is
+    // one pass, like the other builds
+    for (int pass = 0;; ++pass)
+    {
     int stat = all_fin ? VSMPC_STATUS_SOLVED : VSMPC_STATUS_NUMERICAL;
+    if constexpr (JL)
+    {
+        if (pass > 0)
+        {
+            for (int e = threadIdx.x; e < NLO * NLO; e += CD_THREADS)
+                sm.Om[e] = 0.0;
+            __syncthreads();
+        }
+    }
 
     PHASE_CLK(1);
     // ---- factorisation: warp A = P recursion, warp B = parameter columns, one knot apart --------------------------
@@ -531,7 +584,12 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
                     }
                     __syncwarp();
                     if (elim || ta == TK_SCHUR)
-                        ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * WSC_STAGE) && ok;
+                    {
+                        CdClamp cl{0u, nullptr, nullptr, nullptr};
+                        if constexpr (JL)
+                            cl = CdClamp{sm.clamp[ka], sm.jb, sm.hb[ka & 1], c.ws + (size_t)Nc * WSC_STAGE + ka * WSC_U};
+                        ok = a_eliminate<CdSmem, JL>(c, sl, y, hux, own, c.ws + (size_t)ka * WSC_STAGE, cl) && ok;
+                    }
                     SUBCLK(clkA1, tclk);
                 }
             }
@@ -578,7 +636,44 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
                             hut[m] += sm.cf[QD_GQ + m];
                     }
                     const bool schur = tbk == TK_SCHUR;
-                    b_downdate(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD);
+                    unsigned cany = 0u;
+                    if constexpr (JL)
+                    {
+                        const unsigned cm = sm.clamp[kb];
+                        if (cm != 0u)
+                        {
+                            cany = cd_clamped(cm);
+                            // the constants of the clamped components in the value function and in the free rows (CdClamp)
+#pragma unroll
+                            for (int cc = 0; cc < NJ; ++cc)
+                            {
+                                if (!((cany >> cc) & 1u))
+                                    continue;
+                                const double bc = cd_bval(sm.jb, cm, cc);
+                                if (lane < NLO)
+                                {
+                                    const double v = bc * hut[cc];
+                                    sm.Om[lane * NLO + AFFL] += v;
+                                    sm.Om[AFFL * NLO + lane] += v;
+                                }
+                                if (lane == AFFL)
+                                {
+#pragma unroll
+                                    for (int j = 0; j < NX; ++j)
+                                        y[j] = fma(bc, sl.Hux[cc * NX + j], y[j]);
+                                }
+                            }
+                            if (lane == AFFL)
+                            {
+#pragma unroll
+                                for (int m = 0; m < NJ; ++m)
+                                    if (!((cany >> m) & 1u))
+                                        hut[m] += sm.hb[kb & 1][m];
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    b_downdate<JL>(c, sl, y, hut, c.ws + (size_t)kb * WSC_STAGE, schur && isD, cany);
                     SUBCLK(clkB1, tclk);
                     if (schur)
                     {
@@ -867,43 +962,71 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
     }
     __syncthreads();
     PHASE_CLK(6);
-    if (warp != 0)
-        return;
+    if constexpr (!JL)
+    {
+        if (warp != 0)
+            return;
+    }
 
     // ---- warp A: forward rollout ---------------------------------------------------------------------------------------
-    double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
-    double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
-    if (fb_mode == 2 && all_fin)
-        stat = VSMPC_STATUS_NUMERICAL;   // test hook: every instance goes through the fallback kernel
-    const bool solved = stat == VSMPC_STATUS_SOLVED;
-    if (lane == 0)
+    int again = 0;
+    if (warp == 0)
     {
-        // the recursion broke down on finite data (expanding open-loop dynamics, vsmpc_qp_fallback.cu): hand the instance to
-        // the pivoted-LU kernel that runs behind this one; until it succeeds the status stays and the outputs are held
-        if (!solved && all_fin && fb_mode != 0)
-            fb_list[atomicAdd(fb_count, 1)] = inst;
-        status[inst] = stat;
-        n_factor[inst] = 1;              // one backward recursion (no re-factorisation: the active set works on H_r)
-        n_solve[inst] = solved ? 1 : 0;  // one forward pass, skipped for a held instance
-        n_pivot[inst] = sm.flags[2];
+        double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
+        double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
+        if (fb_mode == 2 && all_fin)
+            stat = VSMPC_STATUS_NUMERICAL;   // test hook: every instance goes through the fallback kernel
+        const bool solved = stat == VSMPC_STATUS_SOLVED;
+        int fwd = 0;
+        if (solved)
+        {
+            const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
+            if constexpr (JL)
+            {
+                fwd = cd_forward<CdSmem, true>(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl,
+                                               sm.clamp, c.ws + (size_t)Nc * WSC_STAGE);
+                // the working set of the joint boxes moved: factorise again with it
+                again = (fwd == 1 && pass + 1 < CD_JL_PASSES) ? 1 : 0;
+            }
+            else
+                fwd = cd_forward(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl);
+        }
+        if (!again)
+        {
+            if (lane == 0)
+            {
+                // handed to the pivoted-LU kernel that runs behind this one (vsmpc_qp_fallback.cu): the recursion broke down on
+                // finite data (expanding open-loop dynamics), or a joint box is active at the minimiser and this build does not
+                // carry the joint boxes (or its working set did not settle); until the fallback succeeds the outputs and the
+                // joint accumulator are held (variableSamplingMPC.cpp:91)
+                if (((!solved && all_fin) || fwd != 0) && fb_mode != 0)
+                    fb_list[atomicAdd(fb_count, 1)] = inst;
+                status[inst] = (solved && fwd != 0) ? VSMPC_STATUS_NUMERICAL : stat;
+                n_factor[inst] = pass + 1;                       // backward recursions (one unless joint boxes became active)
+                n_solve[inst] = (solved && fwd == 0) ? 1 : 0;    // committed forward pass
+                n_pivot[inst] = sm.flags[2];
+            }
+            cd_stage_outputs(o, status, inst, lane, out2, status2);
+            if constexpr (JL)
+            {
+                // next tick's guess: the working set of a committed solve, nothing otherwise
+                if (jlset)
+                    jlset[(size_t)inst * CD_MAXN + lane] = (solved && fwd == 0) ? sm.clamp[lane] : 0u;
+            }
+            PHASE_CLK(3);
+        }
     }
-    if (!solved)
+    if constexpr (JL)
     {
-        cd_stage_outputs(o, status, inst, lane, out2, status2);     // the held row
-        return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
+        if (warp == 0 && lane == 0)
+            sm.flags[3] = again;
+        __syncthreads();
+        if (sm.flags[3] == 0)
+            return;
     }
-    const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
-    if (cd_forward(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl) && lane == 0)
-    {
-        // a joint box is active at the minimiser: the fallback kernel solves the problem with the joint boxes in its active
-        // set; until then the outputs are held
-        status[inst] = VSMPC_STATUS_NUMERICAL;
-        n_solve[inst] = 0;
-        if (fb_mode != 0)
-            fb_list[atomicAdd(fb_count, 1)] = inst;
-    }
-    cd_stage_outputs(o, status, inst, lane, out2, status2);
-    PHASE_CLK(3);
+    else
+        return;
+    }   // pass
 }
 
 // The builds of the kernel (one body): register budget and pipeline per batch size
@@ -911,15 +1034,19 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
     const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all, double* __restrict__ ws_all,      \
         double* __restrict__ z_all, double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,       \
         int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride, int want_z,     \
-        int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode, double* __restrict__ out2, int* __restrict__ status2
-#define CD_KERNEL_PASS cfgv, B, qd_all, ws_all, z_all, st, out_rows, status, n_factor, n_solve, n_pivot, ws_stride, want_z, fb_list, fb_count, fb_mode, out2, status2
+        int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode, double* __restrict__ out2, int* __restrict__ status2,    \
+        unsigned* __restrict__ jlset
+#define CD_KERNEL_PASS cfgv, B, qd_all, ws_all, z_all, st, out_rows, status, n_factor, n_solve, n_pivot, ws_stride, want_z, fb_list, fb_count, fb_mode, out2, status2, jlset
 // large batches: eight CTAs per SM, 128 registers
-__global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel(CD_KERNEL_ARGS) { qp_condensed_body<false>(CD_KERNEL_PASS); }
+__global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel(CD_KERNEL_ARGS) { qp_condensed_body<false, false>(CD_KERNEL_PASS); }
+// handles with joint-limit rows (vsmpc_config.use_joint_limits): the same lock-step body with the working set of the joint boxes
+// carried through the elimination (CdClamp) and a pass loop around the solve; any batch size
+__global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel_jl(CD_KERNEL_ARGS) { qp_condensed_body<false, true>(CD_KERNEL_PASS); }
 // (a 144-register build for the one wave of seven CTAs per SM at B = 1024 was tried: 207 us instead of 165 — the register file
 // is split over the four sub-partitions, 14 warps put four on two of them and four warps of 144 registers do not fit 16 384,
 // so the SM holds six CTAs and the launch takes two waves; 128 registers is the cap for anything above twelve warps per SM)
 // small batches, at most four CTAs per SM: decoupled pipeline, no register cap that matters (232 registers, no spills)
-__global__ void __launch_bounds__(CD_THREADS, 4) qp_condensed_kernel_pipe(CD_KERNEL_ARGS) { qp_condensed_body<true>(CD_KERNEL_PASS); }
+__global__ void __launch_bounds__(CD_THREADS, 4) qp_condensed_kernel_pipe(CD_KERNEL_ARGS) { qp_condensed_body<true, false>(CD_KERNEL_PASS); }
 
 int condensed_phase_clocks(long long* host, int n)
 {
@@ -936,15 +1063,20 @@ bool condensed_supported(const DeviceConfig& cfg)
     return cfg.nblk >= 1 && 4 * cfg.nblk <= CD_MAXW && cfg.NC <= CD_MAXNC && cfg.Nc <= 32 && cfg.N <= CD_MAXN;
 }
 
+size_t condensed_jlset_words()
+{
+    return CD_MAXN;   // one word per joint block
+}
+
 size_t condensed_ws_doubles(const DeviceConfig& cfg)
 {
-    return (size_t)cfg.Nc * WSC_STAGE;
+    return (size_t)cfg.Nc * (WSC_STAGE + WSC_U);   // the stages, then raw H_uu per joint block (written by the JL build only)
 }
 
 cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h_cfg, int B, const double* qd,
                                 double* ws, double* z, double* st, double* out_rows, int* status, int* n_factor,
                                 int* n_solve, int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode,
-                                double* out2, int* status2, cudaStream_t s)
+                                double* out2, int* status2, unsigned* jlset, cudaStream_t s)
 {
     // small batches (at most four CTAs per SM): the decoupled pipeline, which shortens a single solve; otherwise lock step
     int dev = 0, sms = 148;
@@ -958,12 +1090,15 @@ cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h
     }
     const size_t wsd = condensed_ws_doubles(h_cfg);
     const int fbm = fb_list && fb_count ? fb_mode : 0;
-    if (B <= pipe_ctas * sms)
+    if (h_cfg.use_jl)
+        qp_condensed_kernel_jl<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
+                                                        want_z, fb_list, fb_count, fbm, out2, status2, jlset);
+    else if (B <= pipe_ctas * sms)
         qp_condensed_kernel_pipe<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
-                                                          want_z, fb_list, fb_count, fbm, out2, status2);
+                                                          want_z, fb_list, fb_count, fbm, out2, status2, jlset);
     else
         qp_condensed_kernel<<<B, CD_THREADS, 0, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd,
-                                                     want_z, fb_list, fb_count, fbm, out2, status2);
+                                                     want_z, fb_list, fb_count, fbm, out2, status2, jlset);
     return cudaGetLastError();
 }
 

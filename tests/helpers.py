@@ -147,7 +147,7 @@ def split_hessian(H, n_iter, n_ctrl):
     return Pd, (-float(w[0]) if w.size else 0.0)
 
 
-def kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, n_iter=17, n_small=7, n_ctrl=12):
+def kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, n_iter=17, n_small=7, n_ctrl=12, dq_lo=None, dq_hi=None):
     """Solver-independent KKT certificate of a batch of returned primals, in NumPy, from what the library itself exposes
     (dense continuous-time blocks, dt grid, gradient, bounds, Hessian).  Lagrangian g + A'y = 0 with g = P z + q:
       * the multipliers of the dynamics rows follow from stationarity in x_N .. x_1 by a backward costate recursion
@@ -155,6 +155,9 @@ def kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, n_iter=17, n_small=7, n_
       * stationarity in every joint-increment block is then a genuine residual: g_dq_j + sum_{k: block j} dt_k B_J' y_k;
       * in every throttle block the same sum IS minus the multiplier of its box row: it must vanish strictly inside the box,
         be <= 0 on the lower bound and >= 0 on the upper bound (l <= v <= u; pinned rows are equalities: free sign).
+    With the optional joint-limit rows (dq_lo / dq_hi: (B, 8) bounds of every increment block) the joint-increment residual
+    is read the same way: zero strictly inside the box, <= 0 on the upper bound and >= 0 on the lower one (keys *_dq, box_dq,
+    n_dq_at_bound); stationarity_dq then covers the increments strictly inside.
     Returns relative residuals (each against the magnitude of the terms it is the difference of)."""
     B = z.shape[0]
     nblk = n_ctrl - n_small + 1
@@ -183,6 +186,17 @@ def kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, n_iter=17, n_small=7, n_
         sdq_mag[:, jb] += np.abs(tj)
         sv[:, tb] += tt
         sv_mag[:, tb] += np.abs(tt)
+    extra = {}
+    if dq_lo is not None:
+        dq = z[:, nx:nx + 8 * n_ctrl].reshape(B, n_ctrl, 8)
+        jl_, jh_ = dq_lo[:, None, :], dq_hi[:, None, :]
+        j_lo, j_up = dq <= jl_ + 1e-12, dq >= jh_ - 1e-12
+        j_in = ~(j_lo | j_up)
+        jscale = np.maximum(sdq_mag.max(axis=(1, 2), keepdims=True), 1e-300)
+        extra = dict(dual_sign_dq=((np.where(j_lo, np.maximum(-sdq, 0.0), 0.0) + np.where(j_up, np.maximum(sdq, 0.0), 0.0)) / jscale).max(axis=(1, 2)),
+                     box_dq=np.maximum(np.maximum(jl_ - dq, dq - jh_), 0.0).max(axis=(1, 2)),
+                     n_dq_at_bound=int((j_lo | j_up).sum()), instances_dq_at_bound=int((j_lo | j_up).any(axis=(1, 2)).sum()))
+        sdq = np.where(j_in, sdq, 0.0)
     stat_dq = np.abs(sdq).max(axis=(1, 2)) / np.maximum(sdq_mag.max(axis=(1, 2)), 1e-300)
     t0 = 26 * n_iter + 26
     lo, up = l[:, t0:t0 + 4 * nblk].reshape(B, nblk, 4), u[:, t0:t0 + 4 * nblk].reshape(B, nblk, 4)
@@ -196,6 +210,6 @@ def kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, n_iter=17, n_small=7, n_
     sign = (np.where(at_lo, np.maximum(nu, 0.0), 0.0) + np.where(at_up, np.maximum(-nu, 0.0), 0.0)) / scale
     box = np.maximum(np.maximum(lo - v, v - up), 0.0)
     return dict(stationarity_dq=stat_dq, complementarity=comp.max(axis=(1, 2)), dual_sign=sign.max(axis=(1, 2)),
-                box=box.max(axis=(1, 2)), n_at_bound=int((at_lo | at_up).sum()), n_inside=int(inside.sum()))
+                box=box.max(axis=(1, 2)), n_at_bound=int((at_lo | at_up).sum()), n_inside=int(inside.sum()), **extra)
 
 

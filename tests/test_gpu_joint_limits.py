@@ -4,8 +4,11 @@ The reference carries a JointPositionConstraint (constraintsVSMPC.cpp:388-468) t
 (variableSamplingMPC.cpp:77-84) and whose parameters jointPos_max / jointPos_min are absent from the XML.  Offered here as an
 extension: 8 * nIter rows after the throttle rows, block i < controlHorizon bounding dq_i by limits - q_cmd (:450-453) for
 every block (the m_firstIteriation slip of :440-449 is fixed, not ported).  The oracle registers the same class when the two
-parameters are given; the product solves instances whose unconstrained joint increments stay inside the box with the
-condensed kernels and hands the others to the KKT fallback kernel, whose active set then carries the joint boxes.
+parameters are given.  At the reference horizon the QP kernel carries the joint boxes itself: a primal-dual working set on
+the 8 x controlHorizon boxes, clamped increments held as constants inside the 8 x 8 eliminations, one more factorisation per
+change of the working set (2-4 in all when bounds are active, tools/condensed_model.py ClampedCondensedQP).  The long-horizon
+kernel solves instances whose unconstrained joint increments stay inside the box and hands the others to the KKT fallback
+kernel, whose active set then carries the joint boxes.
   * CPU: the oracle's rows, bounds and minimiser (KKT certificate of the exact solver, boxes respected, bounds active);
   * GPU: gradient / bounds / constraint matrix against the oracle's assembly, the minimiser and every output field per
     physical quantity (1e-6 relative) on a workload where well over 10 % of the instances have an active joint bound,
@@ -13,7 +16,7 @@ condensed kernels and hands the others to the KKT fallback kernel, whose active 
 import numpy as np
 import pytest
 
-from helpers import assert_output_rows_close, assert_solution_close, load_trajectories, pkg
+from helpers import assert_output_rows_close, assert_solution_close, kkt_certificate, load_trajectories, pkg, split_hessian
 from oracle_driver import OracleInstance, oracle_trajectories_to_product
 
 # degrees, around the synthetic commanded posture (shoulder pitch / roll / yaw, elbow; left then right)
@@ -58,6 +61,55 @@ def test_oracle_joint_limit_rows_cpu():
             assert np.count_nonzero(blk) == 0 and not m.lowerBound[-8 * 17:][8 * i:8 * i + 8].any()
 
 
+def test_clamped_recursion_specification_and_certificate_cpu():
+    """tools/condensed_model.ClampedCondensedQP — the NumPy specification of the QP kernel's working set on the joint boxes —
+    against the oracle's exact solver, and tests/helpers.kkt_certificate with the joint boxes on the oracle's minimisers."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from condensed_model import ClampedCondensedQP
+    import oracle.vsmpc_oracle as O
+    syn = pkg("synthetic")
+    traj = load_trajectories()
+    B = 4
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=5, perturbed=True, near_bound_fraction=0.3)
+    p = O.default_params()
+    zs, As, BJs, BTs, qs, ls, us, los, his = [], [], [], [], [], [], [], [], []
+    n_clamped = 0
+    for i in range(B):
+        o = OracleInstance(nom, i, params=LIMITS, trajectories=traj, phase0=(0 if i % 2 else 19))
+        o.update(per)
+        z = o.solve().copy()
+        cs, rt, tc, jl = o.mpc.vectorConstraints[0], o.mpc.vectorCosts[0], o.mpc.vectorConstraints[2], o.mpc.vectorConstraints[3]
+        jm = o.qp.getJetModel()
+        vbar = np.array([jm.compute_v(jm.standardizeThrottle_u2T(u)) for u in o.qp.getThrottleMPC()])
+        pinned = not np.array_equal(o.mpc.lowerBound[468:472], np.full(4, tc.vMin))
+        m = ClampedCondensedQP(cs.A, cs.BJ, cs.BT, cs.c, cs.dt, np.diag(rt.Q).copy(), rt.stateReference.T.copy(),
+                               np.array(p["weightDeltaJoint"]) + p["weightRegularizationJointPos"],
+                               o.mpc.vectorCosts[3].gradient[468:476].copy(), p["weightThrottle"], p["weightInitialThrottle"],
+                               vbar, pinned, tc.vMin, tc.vMax, o.mpc.vectorConstraints[1].initialState, 17, 7, 12)
+        lo, hi = jl.lowerBound[:8].copy(), jl.upperBound[:8].copy()
+        x, dq, v, passes, clamp = m.solve_boxes(lo, hi)
+        assert 1 <= passes <= 6 and m.status == 0
+        assert np.abs(m.pack_z(x, dq, v) - z).max() / max(1.0, np.abs(z).max()) < 1e-10
+        n_clamped += int((clamp != 0).sum())
+        A, BJ, BT, c, dt = o.dynamics()
+        zs.append(z); As.append(A.copy()); BJs.append(BJ.copy()); BTs.append(BT.copy()); los.append(lo); his.append(hi)
+        qs.append(o.mpc.gradient.copy()); ls.append(o.mpc.lowerBound.copy()); us.append(o.mpc.upperBound.copy())
+        H = o.mpc.hessian
+    assert n_clamped > 0
+    Pd, w_t = split_hessian(H, 17, 12)
+    arr = np.array
+    k = kkt_certificate(arr(zs), arr(As), arr(BJs), arr(BTs), dt, arr(qs), arr(ls), arr(us), Pd, w_t, dq_lo=arr(los), dq_hi=arr(his))
+    assert k["stationarity_dq"].max() < 1e-10 and k["dual_sign_dq"].max() < 1e-10 and k["box_dq"].max() < 1e-12
+    assert k["complementarity"].max() < 1e-10 and k["dual_sign"].max() < 1e-10 and k["n_dq_at_bound"] == n_clamped
+    # the same points against boxes that are a little wider: the increments on the old bounds are now strictly inside with a
+    # non-zero residual, which the certificate must report
+    kb = kkt_certificate(arr(zs), arr(As), arr(BJs), arr(BTs), dt, arr(qs), arr(ls), arr(us), Pd, w_t,
+                         dq_lo=arr(los) - 1e-3, dq_hi=arr(his) + 1e-3)
+    assert kb["stationarity_dq"].max() > 1e-6
+
+
 def _compare_tick(mpc, oracles, per, N, Nc, nblk, what):
     mpc.update(per)
     q, l, u = mpc.get_qp_vectors()
@@ -92,6 +144,8 @@ def test_joint_limit_rows_match_oracle(horizon):
     nom = syn.make_states(B, perturbed=False)
     mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), full_solution=True)
     mpc.configure(nom)
+    if horizon is None:
+        mpc.set_fallback(0)       # reference horizon: the QP kernel carries the joint boxes itself (working set + re-factorisation)
     oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
     p = oracles[0].params
     N, Nc, nblk = p["nIter"], p["controlHorizon"], p["controlHorizon"] - p["nIterSmall"] + 1
@@ -130,10 +184,12 @@ def test_per_instance_joint_limits_match_oracle():
     for i in range(B):
         pi = dict(jointPos_min=list(np.degrees(lo[i])), jointPos_max=list(np.degrees(hi[i])))
         oracles.append(OracleInstance(nom, i, params=pi, trajectories=traj))
+    mpc.set_fallback(0)            # no KKT fallback: the passes below are the QP kernel's own
     n_act = _compare_tick(mpc, oracles, per, 17, 12, 6, "per-instance")
     nf, _ = mpc.get_counts()
-    assert 2 <= n_act < B          # both routes in one batch: condensed kernel alone and the hand-over
-    assert (nf == 2).sum() >= n_act and (nf == 1).sum() >= 1
+    assert 2 <= n_act < B          # both kinds in one batch: no joint bound active (one factorisation) and a working set
+    assert (nf >= 2).sum() >= n_act and (nf == 1).sum() >= 1 and nf.max() <= 6
+    mpc.set_fallback(1)
     # back to the handle-wide limits
     mpc.set_joint_limits(None, None)
     oracles = [OracleInstance(nom, i, params=LIMITS, trajectories=traj) for i in range(B)]
@@ -154,3 +210,45 @@ def test_joint_limits_need_the_flag_and_the_default_solver():
     mpc.close()
     with pytest.raises(bat.VsmpcError):
         bat.BatchedVSMPC(2, dict(jointPos_min=JMAX, jointPos_max=JMIN), traj)
+
+
+@pytest.mark.gpu
+def test_joint_boxes_inside_the_qp_kernel_kkt_certificate_at_1024_instances():
+    """Reference horizon, B = 1024, joint-limit rows on, fallback kernel OFF: every instance is solved by the QP kernel's own
+    working set on the joint boxes.  Solver-independent KKT certificate (stationarity, complementarity and multiplier signs of
+    the throttle AND the joint boxes) for all instances + the oracle on a seeded sample."""
+    B = 1024
+    syn, bat, P = pkg("synthetic"), pkg("batched"), pkg("pack")
+    traj = load_trajectories()
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=4242, perturbed=True, near_bound_fraction=0.3)
+    mpc = bat.BatchedVSMPC(B, LIMITS, oracle_trajectories_to_product(traj), full_solution=True)
+    phase0 = (np.arange(B) % 20).astype(np.int32)
+    mpc.configure_pack(P.build_pack(nom), np.ascontiguousarray(nom["joint_pos"][:, P.DEFAULT_JOINT_SELECTOR].T), phase0)
+    mpc.set_fallback(0)
+    mpc.update(per)
+    A, BJ, BT, c, dt = mpc.get_dynamics()
+    q, l, u = mpc.get_qp_vectors()
+    H = mpc.getHessian(0)
+    mpc.solveMPC()
+    z = mpc.getSolution()
+    out, status = mpc.get_output()
+    nf, ns = mpc.get_counts()
+    mpc.close()
+    assert (status == 0).all(), np.unique(status, return_counts=True)
+    Pd, w_t = split_hessian(H, 17, 12)
+    lo = np.radians(JMIN)[None, :] - per["q_cmd"][:, SEL]
+    hi = np.radians(JMAX)[None, :] - per["q_cmd"][:, SEL]
+    k = kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, 17, 7, 12, dq_lo=lo, dq_hi=hi)
+    assert k["stationarity_dq"].max() < 1e-9, k["stationarity_dq"].max()
+    assert k["complementarity"].max() < 1e-9 and k["dual_sign"].max() < 1e-9
+    assert k["dual_sign_dq"].max() < 1e-9, k["dual_sign_dq"].max()
+    assert k["box"].max() < 1e-12 and k["box_dq"].max() <= 1e-9
+    assert k["instances_dq_at_bound"] > B // 10 and k["n_dq_at_bound"] > B       # the workload exercises the joint boxes
+    assert (nf[(ns == 1)] >= 1).all() and nf.max() <= 8 and (nf >= 2).sum() >= k["instances_dq_at_bound"]
+    for i in np.random.default_rng(7).choice(B, 6, replace=False):
+        o = OracleInstance(nom, int(i), params=LIMITS, trajectories=traj, phase0=int(phase0[i]))
+        o.update(per)
+        zo = o.solve()
+        assert_solution_close(z[i], zo, 1e-6, N=17, Nc=12, nblk=6, what=("z", int(i)))
+        assert_output_rows_close(out[i], o.output_row(), 1e-6, what=("row", int(i)))

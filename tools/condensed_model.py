@@ -280,3 +280,121 @@ class CondensedQP:
 
     def pack_z(self, x, dq, v):
         return np.concatenate([x.reshape(-1), dq.reshape(-1), v.reshape(-1)])
+
+
+class ClampedCondensedQP(CondensedQP):
+    """The optional joint-limit rows inside the condensed recursion (JL build of csrc/vsmpc_qp_condensed.cu).
+
+    Every joint-increment block k < Nc has the box lo <= dq_k <= hi (JointPositionConstraint semantics, constraintsVSMPC.cpp:450-453).
+    A primal-dual active set runs AROUND the solve: with a working set clamp[k][c] in {0, +1 (upper), -1 (lower)} a clamped
+    component is the constant b_c inside the elimination of its block,
+        H_uu restricted to the free components (identity on the clamped ones),
+        H_utheta[m, affine] += sum_c H_uu[m][c] b_c                      for the free rows m,
+        Psi[:, affine]      += sum_c b_c H_ux[c, :]',      Om[:, affine] += b_c H_utheta[c, :]'  (+ its transpose),
+    and P, Psi, Om skip the clamped rows.  The forward pass sets dq_c = b_c and reads the gradient of the cost-to-go in dq_c,
+        grad_c = H_ux[c, :] x_k + H_uu[c, :] dq_k + H_utheta[c, :] theta,
+    off the raw rows (upper bound: multiplier -grad_c, lower bound: +grad_c).  Next working set: free components outside their
+    box join at the bound they crossed, clamped ones with a negative multiplier leave; a fixed point is the minimiser (all KKT
+    conditions hold).  The iteration is not guaranteed to settle in general — the kernel hands an instance to the KKT fallback
+    after 8 passes — on the test workloads it takes 2-4."""
+
+    def factor_clamped(self, clamp, lo, hi):
+        N, Nc = self.N, self.Nc
+        P = np.zeros((NX, NX))
+        Psi = np.zeros((NX, NL))
+        Om = np.zeros((NL, NL))
+        self.K, self.F, self.raw = [None] * N, [None] * N, [None] * N
+        I = np.eye(NX)
+        for k in range(N - 1, -1, -1):
+            T = I + self.dt[k] * self.Ac
+            Bu = self.dt[k] * self.BJ
+            D = self._D(k)
+            Pp = P + np.diag(self.Qd)
+            Psp = Psi.copy()
+            Psp[:, AFF] -= self.Qd * self.xref[k]
+            Ps2 = Psp + Pp @ D
+            PT = T.T @ Pp @ T
+            PsT = T.T @ Ps2
+            OmT = Om + D.T @ Ps2 + Psp.T @ D
+            tail = self.held and k >= Nc - 1
+            if not tail:
+                Huu = np.diag(self.Rqd) + Bu.T @ Pp @ Bu
+                Hux = Bu.T @ Pp @ T
+                Hut = Bu.T @ Ps2
+            elif k == Nc - 1:
+                d = slice(self.D0, self.D0 + NJ)
+                Huu = OmT[d, d] + np.diag(self.Rqd)
+                Hux = PsT[:, d].T.copy()
+                Hut = OmT[d, :].copy()
+                Hut[:, d] = 0.0
+                PsT[:, d] = 0.0
+                OmT[d, :] = 0.0
+                OmT[:, d] = 0.0
+            else:
+                P, Psi, Om = PT, PsT, OmT
+                continue
+            Hut[:, AFF] += self.gq
+            cl = clamp[k]
+            C = cl != 0
+            b = np.where(cl > 0, hi, np.where(cl < 0, lo, 0.0))
+            self.raw[k] = (Hux.copy(), Huu.copy(), Hut.copy())
+            Hm = Huu.copy()
+            Hm[C, :] = 0.0
+            Hm[:, C] = 0.0
+            Hm[C, C] = 1.0
+            Hi = np.linalg.inv(Hm)
+            hut = Hut.copy()
+            hut[~C, AFF] += ((Huu - np.diag(self.Rqd)) @ b)[~C]       # off-diagonal coupling (the diagonal is never a free-clamped pair)
+            Kk = Hi @ Hux                                            # clamped rows: the raw H_ux rows
+            Fk = Hi @ hut                                            # clamped rows: the raw H_utheta rows
+            Kf, Ff, Huxf, hutf = Kk.copy(), Fk.copy(), Hux.copy(), hut.copy()
+            Kf[C], Ff[C], Huxf[C], hutf[C] = 0.0, 0.0, 0.0, 0.0
+            P = PT - Huxf.T @ Kf
+            Psi = PsT - Huxf.T @ Ff
+            Psi[:, AFF] += Hux[C].T @ b[C]
+            Om = OmT - hutf.T @ Ff
+            for c in np.nonzero(C)[0]:
+                Om[:, AFF] += b[c] * Hut[c]
+                Om[AFF, :] += b[c] * Hut[c]
+            self.K[k], self.F[k] = Kk, Fk
+        self.P0, self.Psi0, self.Om0 = P, Psi, Om
+
+    def forward_clamped(self, v, clamp, lo, hi):
+        N = self.N
+        theta = np.zeros(NL)
+        theta[:4 * self.nblk] = v.reshape(-1)
+        theta[AFF] = 1.0
+        x = np.zeros((N + 1, NX))
+        dq = np.zeros((self.Nc, NJ))
+        grad = np.zeros((self.Nc, NJ))
+        x[0] = self.x0
+        I = np.eye(NX)
+        for k in range(N):
+            if self.K[k] is not None:
+                raw = self.K[k] @ x[k] + self.F[k] @ theta          # free rows: -dq ; clamped rows: H_ux x + H_utheta theta
+                cl = clamp[k]
+                u = np.where(cl > 0, hi, np.where(cl < 0, lo, -raw))
+                dq[self.jb[k]] = u
+                grad[k] = raw + self.raw[k][1] @ u
+            u = dq[self.jb[k]]
+            x[k + 1] = (I + self.dt[k] * self.Ac) @ x[k] + self.dt[k] * (self.BJ @ u + self.BT @ v[self.tb[k]] + self.c)
+        return x, dq, v, grad
+
+    def solve_boxes(self, lo, hi, max_pass=8, tol=1e-9):
+        """-> x, dq, v, passes (-1: the working set did not settle), clamp"""
+        clamp = np.zeros((self.Nc, NJ), dtype=int)
+        for p in range(max_pass):
+            self.factor_clamped(clamp, lo, hi)
+            H, g, first = self.reduced_qp()
+            vv, self.active, self.status = box_qp_pivot(H, g, self.vmin, self.vmax)
+            v = (np.concatenate([self.vbar, vv]) if self.pinned else vv).reshape(self.nblk, 4)
+            x, dq, v, grad = self.forward_clamped(v, clamp, lo, hi)
+            new = clamp.copy()
+            new[(clamp == 0) & (dq > hi + tol)] = 1
+            new[(clamp == 0) & (dq < lo - tol)] = -1
+            new[(clamp > 0) & (grad > 0)] = 0
+            new[(clamp < 0) & (grad < 0)] = 0
+            if (new == clamp).all():
+                return x, dq, v, p + 1, clamp
+            clamp = new
+        return x, dq, v, -1, clamp
