@@ -252,3 +252,38 @@ def test_joint_boxes_inside_the_qp_kernel_kkt_certificate_at_1024_instances():
         zo = o.solve()
         assert_solution_close(z[i], zo, 1e-6, N=17, Nc=12, nblk=6, what=("z", int(i)))
         assert_output_rows_close(out[i], o.output_row(), 1e-6, what=("row", int(i)))
+
+
+@pytest.mark.gpu
+def test_joint_box_working_set_warm_start_same_minimiser_fewer_factorisations():
+    """The working set of the joint boxes a solve ended with is the next tick's first guess (vsmpc_set_warm_start): the same
+    minimiser as a cold start, and on a repeated state hardly any re-factorisation."""
+    B = 256
+    syn, bat = pkg("synthetic"), pkg("batched")
+    traj = oracle_trajectories_to_product(load_trajectories())
+    nom = syn.make_states(B, perturbed=False)
+    pers = [syn.make_states(B, seed=70 + j, perturbed=True, near_bound_fraction=0.3) for j in range(2)]
+    runs = {}
+    for warm in (0, 1):
+        mpc = bat.BatchedVSMPC(B, LIMITS, traj, full_solution=True)
+        mpc.configure(nom)
+        mpc.set_fallback(0)
+        mpc.set_warm_start(warm)
+        zs, nfs = [], []
+        for per in (pers[0], pers[0], pers[1], pers[1]):
+            mpc.update(per)
+            mpc.solveMPC()
+            _, status = mpc.get_output()
+            assert (status == 0).all()
+            zs.append(mpc.getSolution().copy())
+            nfs.append(mpc.get_counts()[0].copy())
+        runs[warm] = (zs, nfs)
+        mpc.close()
+    for t in range(4):
+        zc, zw = runs[0][0][t], runs[1][0][t]
+        assert np.abs(zc - zw).max() <= 1e-9 * max(1.0, np.abs(zc).max()), t
+    cold, warm = runs[0][1], runs[1][1]
+    assert cold[1].mean() > 2.0                       # the workload needs its working set
+    assert np.array_equal(cold[0], warm[0])           # first tick after configure: empty guess either way
+    # the same state again: the guess is the answer up to the 20-tick phase of the throttle rows
+    assert warm[1].mean() < 1.5 and warm[3].mean() < 1.5 and warm[1].mean() < 0.6 * cold[1].mean()
