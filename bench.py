@@ -263,12 +263,13 @@ def run_ours(args):
     if rank == 0 and args.rollout_ticks > 0:
         closed = closed_loop_leg(bat, B, local_rank, stream, args.rollout_ticks, args.solver)
     # ---------------- the other BASELINE configurations, every rank (skipped by --no-extras / --horizon) ------------
-    gather = long_h = monte = e2e_kin = None
+    gather = long_h = monte = sweep = e2e_kin = None
     if not args.no_extras and not params:
         e2e_kin = e2e_kinematics_leg(bat, L, B, world, rank, local_rank, stream, dev, K, Wm)
         gather = gather_leg(mpc, B, world, dev, stream, h_out, h_status)
         long_h = long_horizon_leg(bat, lib, d_packs, nom_pack, jp, phase0, B, local_rank, stream, flush, world, dev, args.solver)
         monte = monte_carlo_leg(bat, args.mc_instances, args.mc_ticks, rank, world, local_rank, stream, dev)
+        sweep = monte_carlo_leg(bat, args.sweep_instances, args.mc_ticks, rank, world, local_rank, stream, dev, joint_boxes=True)
     # ---------------- reduce over ranks: max time --------------------------------------------------------
     t = torch.tensor([total_ms, e2e_s * 1e3, k1_ms, k2_ms, e2e_blocking_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -338,7 +339,7 @@ def run_ours(args):
                                   "qp_fallback_kernel"] if args.solver == 0 else 2,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "single_solve_latency": latency, "closed_loop": closed,
-        "e2e_kinematics": e2e_kin, "monte_carlo": monte, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
+        "e2e_kinematics": e2e_kin, "monte_carlo": monte, "param_sweep": sweep, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
         "solved_fraction": solved_frac, "wall_ms_timed_loop": t_wall * 1e3,
     }
     print(json.dumps(line))
@@ -492,14 +493,17 @@ def finish_long_horizon(rows, peak_tflops):
             "what": "configs[3]: qp_condensed_wide_kernel, same synthetic packs as the main leg, L2 flushed between steps"}
 
 
-def monte_carlo_leg(bat, n_total, ticks, rank, world, device, stream, dev):
+def monte_carlo_leg(bat, n_total, ticks, rank, world, device, stream, dev, joint_boxes=False):
     """BASELINE configs[2] x configs[4]: a Monte Carlo closed-loop sweep of n_total instances IN TOTAL (contiguous
     ranges over the ranks: strong scaling) over initial states, constant thrust disturbances and per-instance model
     parameters (jet coefficients / normalisation, mass, inertia, throttle limits), `ticks` controller ticks each,
-    entirely on the device (surrogate plant); CUDA events, max over ranks."""
+    entirely on the device (surrogate plant); CUDA events, max over ranks.
+    joint_boxes (BASELINE configs[4] "per-instance constraint sets", SURVEY §8d Config 5): n_total instances PER RANK (weak
+    scaling: 16 384 on eight GPUs = 2048 each), the same parameter sweep with the optional joint-limit rows on and every instance
+    its own box around the commanded posture (two thirds 0.1-0.5 rad to either side, a third open)."""
     import torch
     ro, syn, cfg, sh = pkg("rollout"), pkg("synthetic"), pkg("config"), pkg("sharding")
-    lo, hi = sh.shard_range(n_total, rank, world)
+    lo, hi = (rank * n_total, (rank + 1) * n_total) if joint_boxes else sh.shard_range(n_total, rank, world)
     Bl = hi - lo
     rb = syn.SyntheticRobot()
     g = np.random.default_rng(20251002 + 7 * rank)
@@ -520,9 +524,17 @@ def monte_carlo_leg(bat, n_total, ticks, rank, world, device, stream, dev):
     norm[:, 1] *= g.uniform(0.9, 1.1, Bl)
     trj = dict(load_traj())
     trj["alphaGravity"] = np.ones_like(trj["alphaGravity"])      # in flight: the surrogate has no ground contact
-    mpc = bat.BatchedVSMPC(Bl, None, trj, device=device)
+    params = None
+    if joint_boxes:
+        pk = pkg("pack")
+        params = dict(jointPos_min=[-180.0] * 8, jointPos_max=[180.0] * 8)        # replaced per instance below
+    mpc = bat.BatchedVSMPC(Bl, params, trj, device=device)
     mpc.set_stream(stream.cuda_stream)
     mpc.set_instance_params(coeff, norm, g.uniform(0.0, 20.0, Bl), g.uniform(80.0, 100.0, Bl))
+    if joint_boxes:
+        qc = st["q_cmd"][:, pk.DEFAULT_JOINT_SELECTOR]
+        width = np.where(np.arange(Bl)[:, None] % 3 == 0, 3.0, g.uniform(0.1, 0.5, (Bl, 8)))
+        mpc.set_joint_limits(qc - width, qc + width * g.uniform(0.5, 1.5, (Bl, 8)))
     loop = ro.BatchedRollout(mpc, rb)
     loop.init(st, mass_scale=ms_, inertia_scale=isc, thrust_disturbance=g.normal(0, 10.0, (Bl, 4)),
               phase0=(np.arange(Bl) % 20).astype(np.int32))
@@ -535,24 +547,32 @@ def monte_carlo_leg(bat, n_total, ticks, rank, world, device, stream, dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     _, status = mpc.get_output()
+    nf, _ = mpc.get_counts()
     ps = loop.plant_state()
     fin = np.isfinite(ps).all(axis=0)
     drift = np.linalg.norm(ps[0:3].T - st["p_com"], axis=1)
     mpc.close()
     import torch.distributed as dist
-    cnt = torch.tensor([float((status == 0).sum()), float(fin.sum()), float(Bl)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float((status == 0).sum()), float(fin.sum()), float(Bl), float(nf.sum()), float((nf >= 2).sum())],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms_max = _max_over_ranks([ms], world, dev)[0]
-    solved, finite, total = [float(x) for x in cnt.tolist()]
-    return {"value": total * ticks / (ms_max * 1e-3), "unit": "closed-loop solves/s", "scaling": "strong",
-            "instances_total": int(total), "instances_per_rank": int(Bl), "ticks": int(ticks), "ms_total": ms_max,
-            "ms_per_tick": ms_max / ticks, "kernels_per_tick": 3, "cuda_graph": True,
-            "solved_fraction_last_tick": solved / total, "finite_plant_states": finite / total,
-            "rank0_median_com_drift_m": float(np.median(drift[fin])),
-            "what": "per-instance initial state, thrust disturbance N(0, 10 N), mass x U(0.9, 1.1), inertia x U(0.8, 1.2), jet "
-                    "c1, c2, mu_T, sigma_T x U(0.9, 1.1), throttleMin U(0, 20), throttleMax U(80, 100); surrogate plant "
-                    "(5 x 1 ms) + linearise + QP per tick, device-resident, staggered 20-tick phases"}
+    solved, finite, total, nf_sum, nf_multi = [float(x) for x in cnt.tolist()]
+    out = {"value": total * ticks / (ms_max * 1e-3), "unit": "closed-loop solves/s", "scaling": "weak" if joint_boxes else "strong",
+           "instances_total": int(total), "instances_per_rank": int(Bl), "ticks": int(ticks), "ms_total": ms_max,
+           "ms_per_tick": ms_max / ticks, "kernels_per_tick": 3, "cuda_graph": True,
+           "solved_fraction_last_tick": solved / total, "finite_plant_states": finite / total,
+           "rank0_median_com_drift_m": float(np.median(drift[fin])),
+           "what": "per-instance initial state, thrust disturbance N(0, 10 N), mass x U(0.9, 1.1), inertia x U(0.8, 1.2), jet "
+                   "c1, c2, mu_T, sigma_T x U(0.9, 1.1), throttleMin U(0, 20), throttleMax U(80, 100); surrogate plant "
+                   "(5 x 1 ms) + linearise + QP per tick, device-resident, staggered 20-tick phases"}
+    if joint_boxes:
+        out["what"] += ("; joint-limit rows on, per-instance boxes around the commanded posture (two thirds 0.1-0.5 rad to either side, a "
+                        "third open), carried by the QP kernel's own working set")
+        out["factorisations_per_solve_last_tick"] = nf_sum / total
+        out["instances_refactorised_last_tick"] = nf_multi / total
+    return out
 
 
 def closed_loop_leg(bat, B, device, stream, n_ticks, solver):
@@ -674,6 +694,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the gather / long-horizon / Monte Carlo legs")
     ap.add_argument("--mc-instances", type=int, default=65536, help="Monte Carlo sweep: instances in total over all ranks")
     ap.add_argument("--mc-ticks", type=int, default=200)
+    ap.add_argument("--sweep-instances", type=int, default=2048,
+                    help="parameter sweep with per-instance joint-limit rows (configs[4]): instances per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

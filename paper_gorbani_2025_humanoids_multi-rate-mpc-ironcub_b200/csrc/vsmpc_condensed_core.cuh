@@ -488,7 +488,8 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
                                           double* __restrict__ xs, int lane, int B, int inst, double* __restrict__ z,
                                           double* __restrict__ o, double* __restrict__ st, double* __restrict__ ostage,
                                           const double* __restrict__ jl, unsigned* __restrict__ clamp = nullptr,
-                                          const double* __restrict__ uraw_all = nullptr)
+                                          const double* __restrict__ uraw_all = nullptr, unsigned* __restrict__ cand = nullptr,
+                                          bool careful = false)
 {
     const int N = cfg.N, Nc = cfg.Nc, nv = 4 * cfg.nblk;
     CdFwdTab tab;
@@ -571,22 +572,29 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
             if constexpr (JL)
             {
                 __syncwarp();
-                double grad = g0;
+                double grad = g0, gmag = fabs(g0);
                 if (cm != 0u && (cup || clo) && lane < NJ)
                 {
                     const double* __restrict__ ur = uraw_all + k * (NJ * NJ) + ka * NJ;
 #pragma unroll
                     for (int m = 0; m < NJ; ++m)
-                        grad = fma(ur[m], dqs[m], grad);
+                    {
+                        const double t = ur[m] * dqs[m];
+                        grad += t;
+                        gmag += fabs(t);
+                    }
                 }
-                // next working set of this block: the multiplier of an upper bound is -grad, of a lower bound +grad
-                const bool nup = (cup || clo) ? (cup && grad <= 0.0) : (u > jhi);
-                const bool nlo = (cup || clo) ? (clo && grad >= 0.0) : (u < jlo);
-                const unsigned nm = (__ballot_sync(0xffffffffu, nup && lane < NJ) & 0xffu) |
-                                    ((__ballot_sync(0xffffffffu, nlo && lane < NJ) & 0xffu) << 8);
-                viol = viol || (nm != cm);
+                // candidates of this block: free increments outside their box (beyond 1e-9 rad) join at the bound they crossed;
+                // clamped ones leave when their multiplier (upper bound: -grad, lower bound: +grad) is negative beyond the
+                // rounding of its own terms — without that margin a degenerate increment (on its bound with a zero multiplier)
+                // is released on noise, comes back 1e-9 outside, and the working set never settles
+                const bool addu = !(cup || clo) && u > jhi, addl = !(cup || clo) && u < jlo;
+                const bool rel = (cup && grad > 1e-9 * gmag) || (clo && grad < -1e-9 * gmag);
+                const unsigned ad = (__ballot_sync(0xffffffffu, addu && lane < NJ) & 0xffu) |
+                                    ((__ballot_sync(0xffffffffu, addl && lane < NJ) & 0xffu) << 8);
+                const unsigned rl = __ballot_sync(0xffffffffu, rel && lane < NJ) & 0xffu;
                 if (lane == 0)
-                    clamp[k] = nm;
+                    cand[k] = ad | (rl << 16);
             }
         }
         __syncwarp();
@@ -621,6 +629,23 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
     }
     if (__any_sync(0xffffffffu, bad))
         return 2;
+    if constexpr (JL)
+    {
+        // next working set, all blocks at once (lane = block).  First passes: joins and leaves together (two to four passes on
+        // the test workloads).  careful (later passes): leaves only once no free increment is outside its box — the joint
+        // add / release of the plain iteration can cycle on general data
+        __syncwarp();
+        const unsigned old = lane < Nc ? clamp[lane] : 0u, cd = lane < Nc ? cand[lane] : 0u;
+        const unsigned ad = cd & 0xffffu, rl = (cd >> 16) & 0xffu;
+        const bool any_add = __any_sync(0xffffffffu, ad != 0u);
+        unsigned nm = old | ad;
+        if (!(careful && any_add))
+            nm &= ~(rl | (rl << 8));
+        viol = nm != old;
+        if (lane < Nc)
+            clamp[lane] = nm;
+        __syncwarp();
+    }
     if (__any_sync(0xffffffffu, viol))
         return 1;     // a joint increment left its box / the working set moved: nothing committed
     // remaining outputs (variableSamplingMPC.cpp:96-108,138-151), then the commit of the staged ones

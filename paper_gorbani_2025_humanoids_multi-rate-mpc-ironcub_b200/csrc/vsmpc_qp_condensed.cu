@@ -42,13 +42,15 @@ constexpr int CD_MAXN = 32;   // knots kept in shared memory (dt grid)
 template <bool JL> struct CdJlSmem
 {
     unsigned clamp[CD_MAXN];    // per joint block: bit c = increment c held at its upper bound, bit 8 + c at its lower bound
+    unsigned cand[CD_MAXN];     // forward pass: increments that would join (bits 0-15, like clamp) / leave (bits 16-23)
     double jb[2 * NJ];          // bounds of the increments: lower [8], upper [8]  (QD_JLO / QD_JHI)
     double hb[2][NJ];           // warp A -> warp B, per mailbox slot: sum_c H_uu[m][c] b_c
 };
 template <> struct CdJlSmem<false>
 {
 };
-constexpr int CD_JL_PASSES = 8;   // factorisations per solve before the instance is handed to the fallback kernel
+constexpr int CD_JL_PASSES = 14;  // factorisations per solve before the instance is handed to the fallback kernel
+constexpr int CD_JL_PLAIN = 5;    // of which with joins and leaves applied together; then leaves wait for primal feasibility
 constexpr int WSC_U = NJ * NJ;    // per joint block, behind the Nc stages of the workspace: raw H_uu [8][8]
 
 template <int NSLOT, bool JL = false> struct alignas(16) CdSmemT : CdJlSmem<JL>
@@ -984,7 +986,7 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
             if constexpr (JL)
             {
                 fwd = cd_forward<CdSmem, true>(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl,
-                                               sm.clamp, c.ws + (size_t)Nc * WSC_STAGE);
+                                               sm.clamp, c.ws + (size_t)Nc * WSC_STAGE, sm.cand, pass >= CD_JL_PLAIN);
                 // the working set of the joint boxes moved: factorise again with it
                 again = (fwd == 1 && pass + 1 < CD_JL_PASSES) ? 1 : 0;
             }
