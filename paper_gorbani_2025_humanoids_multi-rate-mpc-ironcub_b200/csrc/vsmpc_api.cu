@@ -67,7 +67,7 @@ size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
-                                     int warm, double* out2, int* status2, cudaStream_t s);
+                                     int warm, double* out2, int* status2, unsigned* jlset, cudaStream_t s);
 size_t condensed_wide_wset_bytes(const DeviceConfig& cfg);
 struct KinModelDev;
 const char* kin_prepare(const vsmpc_kin_model& m, KinModelDev& K);
@@ -457,7 +457,7 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         if (ok)
             A(cudaMemset(h->d_wset, 0xFF, h->wset_bytes));     // all-lower vertex
     }
-    if (h->solver == 0 && g.use_jl)
+    if ((h->solver == 0 || h->solver == SOLVER_WIDE) && g.use_jl)
     {
         h->jlset_bytes = condensed_jlset_words() * sizeof(unsigned) * B;
         A(dalloc(&h->d_jlset, h->jlset_bytes / sizeof(unsigned)));
@@ -1263,7 +1263,7 @@ static int solve_launch(vsmpc_handle* h)
     else if (h->solver == SOLVER_WIDE)
         CK(launch_qp_condensed_wide(h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out, h->d_status,
                                     h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0, h->d_fb_list, h->d_fb_count,
-                                    h->fb_mode, h->d_wset, h->warm ? 1 : 0, out2, status2, h->stream));
+                                    h->fb_mode, h->d_wset, h->warm ? 1 : 0, out2, status2, h->warm ? h->d_jlset : nullptr, h->stream));
     else if (h->solver == 1)
         CK(launch_qp_generic(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                              h->d_status, h->d_nf, h->d_ns, h->stream));

@@ -219,6 +219,7 @@ struct CdClamp
     double* hb;               // [8] out (warp A) / in (warp B): sum_c H_uu[m][c] b_c
     double* uraw;             // [8][8] out: H_uu (with R) of the block, for the multipliers (workspace)
 };
+constexpr int CD_JLSET_WORDS = 64;   // words per instance of the stored working set (one per joint block; both condensed kernels)
 __device__ __forceinline__ unsigned cd_clamped(unsigned cm) { return (cm | (cm >> 8)) & 0xffu; }
 __device__ __forceinline__ double cd_bval(const double* __restrict__ jb, unsigned cm, int c)
 {
@@ -635,15 +636,21 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
         // the test workloads).  careful (later passes): leaves only once no free increment is outside its box — the joint
         // add / release of the plain iteration can cycle on general data
         __syncwarp();
-        const unsigned old = lane < Nc ? clamp[lane] : 0u, cd = lane < Nc ? cand[lane] : 0u;
-        const unsigned ad = cd & 0xffffu, rl = (cd >> 16) & 0xffu;
-        const bool any_add = __any_sync(0xffffffffu, ad != 0u);
-        unsigned nm = old | ad;
-        if (!(careful && any_add))
-            nm &= ~(rl | (rl << 8));
-        viol = nm != old;
-        if (lane < Nc)
-            clamp[lane] = nm;
+        const int ncr = (Nc + 31) & ~31;
+        bool any_add = false;
+        for (int k0 = lane; k0 < ncr; k0 += 32)
+            any_add = __any_sync(0xffffffffu, k0 < Nc && (cand[k0 < Nc ? k0 : 0] & 0xffffu) != 0u) || any_add;
+        viol = false;
+        for (int k0 = lane; k0 < Nc; k0 += 32)
+        {
+            const unsigned old = clamp[k0], cd = cand[k0];
+            const unsigned ad = cd & 0xffffu, rl = (cd >> 16) & 0xffu;
+            unsigned nm = old | ad;
+            if (!(careful && any_add))
+                nm &= ~(rl | (rl << 8));
+            viol = viol || nm != old;
+            clamp[k0] = nm;
+        }
         __syncwarp();
     }
     if (__any_sync(0xffffffffu, viol))

@@ -418,7 +418,7 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
             sm.jb[threadIdx.x] = qd[QD_JLO + threadIdx.x];
         // warm start: the working set the last solve of this instance ended with (zeros after configure)
         if (threadIdx.x < CD_MAXN)
-            sm.clamp[threadIdx.x] = (jlset && threadIdx.x < Nc) ? jlset[(size_t)inst * CD_MAXN + threadIdx.x] : 0u;
+            sm.clamp[threadIdx.x] = (jlset && threadIdx.x < Nc) ? jlset[(size_t)inst * CD_JLSET_WORDS + threadIdx.x] : 0u;
     }
     const bool all_fin = __syncthreads_and(fin);
     // JL build: primal-dual active set on the joint boxes around the whole solve — pass p factorises with the working set pass
@@ -1013,7 +1013,7 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
             {
                 // next tick's guess: the working set of a committed solve, nothing otherwise
                 if (jlset)
-                    jlset[(size_t)inst * CD_MAXN + lane] = (solved && fwd == 0) ? sm.clamp[lane] : 0u;
+                    jlset[(size_t)inst * CD_JLSET_WORDS + lane] = (solved && fwd == 0) ? sm.clamp[lane] : 0u;
             }
             PHASE_CLK(3);
         }
@@ -1067,7 +1067,7 @@ bool condensed_supported(const DeviceConfig& cfg)
 
 size_t condensed_jlset_words()
 {
-    return CD_MAXN;   // one word per joint block
+    return CD_JLSET_WORDS;   // one word per joint block
 }
 
 size_t condensed_ws_doubles(const DeviceConfig& cfg)

@@ -31,7 +31,21 @@ constexpr int CW_MAXTHREADS = 256;                  // 1 + CW_MAXG warps, rounde
 constexpr int CW_SMEM_LIMIT = 227 * 1024;           // opt-in shared memory per CTA on sm_100
 constexpr int CW_MD = 8;                            // pivots deferred before one rank-8 update of the matrix
 
-struct alignas(16) CwSmem
+// working set of the optional joint boxes (JL builds; see CdClamp in vsmpc_condensed_core.cuh and the reference-horizon kernel)
+template <bool JL> struct CwJlSmem
+{
+    unsigned clamp[MAX_ITER];   // per joint block: bit c = increment c held at its upper bound, bit 8 + c at its lower bound
+    unsigned cand[MAX_ITER];    // forward pass: increments that would join / leave
+    double jb[2 * NJ];          // bounds of the increments: lower [8], upper [8]
+    double hb[2][NJ];           // warp 0 -> column warps, per mailbox slot: sum_c H_uu[m][c] b_c
+};
+template <> struct CwJlSmem<false>
+{
+};
+constexpr int CW_JL_PASSES = 14, CW_JL_PLAIN = 5;   // as in the reference-horizon kernel
+constexpr int CW_WSU = NJ * NJ;                       // per joint block, behind the Nc stages of the workspace: raw H_uu [8][8]
+
+template <bool JL> struct alignas(16) CwSmemT : CwJlSmem<JL>
 {
     double cf[CCF];
     alignas(16) double lam[6 * NJ];   // dt-free B_J rows: [q][a]
@@ -86,7 +100,7 @@ __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
     return L;
 }
 
-using CwCtx = CdCtxT<CwSmem>;
+using CwSmem = CwSmemT<false>;
 
 #ifdef VSMPC_PHASE_CLOCKS
 __device__ long long g_wide_clk[4096][16];
@@ -104,12 +118,13 @@ __device__ __forceinline__ void cw_bar_columns(int n_threads)
 
 // propagation of the parameter columns through knot k (Psi'' = Psi' + P'D, Om += D'Psi'' + Psi''D, Psi <- T'Psi'');
 // returns dt B_J' Psi''[:, gc] in bj2.  gc: column of this lane
+template <class CwCtx>
 __device__ __forceinline__ void w_prop(const CwCtx& c, const CwLayout& L, double* __restrict__ Om,
                                        const double* __restrict__ xref, int k, bool tail, int gc, double (&s)[NX],
                                        double (&bj2)[NJ])
 {
     const DeviceConfig& cfg = c.cfg;
-    CwSmem& sm = c.sm;
+    auto& sm = c.sm;
     const double* cf = sm.cf;
     const double dt = sm.dtk[k];
     CdSlot& sl = sm.slot[k & 1];
@@ -185,13 +200,16 @@ __device__ __forceinline__ void w_prop(const CwCtx& c, const CwLayout& L, double
 
 // down-date of the parameter columns with the eliminated block: F = H_uu^-1 H_utheta, Psi -= H_ux' F; H_utheta and F go
 // to the workspace stacks for the deferred down-date of Om
+// cany (JL builds): clamped components of the block — raw H_utheta rows come out in their F rows, zero rows go to the H stack,
+// Psi skips them (see b_downdate of the reference-horizon kernel)
+template <bool JL = false>
 __device__ __forceinline__ void w_downdate(const CdSlot& sl, const CwLayout& L, int gc, double (&s)[NX],
-                                           const double (&hut)[NJ], double* __restrict__ wsk, bool clear_col)
+                                           const double (&hut)[NJ], double* __restrict__ wsk, bool clear_col, unsigned cany = 0u)
 {
     double f[NJ];
 #pragma unroll
     for (int m = 0; m < NJ; ++m)
-        wsk[L.wsH + m * L.ldc + gc] = hut[m];
+        wsk[L.wsH + m * L.ldc + gc] = (JL && ((cany >> m) & 1u)) ? 0.0 : hut[m];
     const double2* hi = reinterpret_cast<const double2*>(sl.Hinv);
 #pragma unroll
     for (int a = 0; a < NJ; ++a)
@@ -212,6 +230,11 @@ __device__ __forceinline__ void w_downdate(const CdSlot& sl, const CwLayout& L, 
 #pragma unroll
         for (int m = 0; m < NJ; ++m)
         {
+            if constexpr (JL)
+            {
+                if ((cany >> m) & 1u)
+                    continue;
+            }
             const double2* hr = reinterpret_cast<const double2*>(sl.Hux + m * NX);
 #pragma unroll
             for (int j = 0; j < NX / 2; ++j)
@@ -409,18 +432,21 @@ __device__ __forceinline__ double cw_block_best(double v, double* __restrict__ r
 // THREADS / MINB: launch bounds per number of column warps, so that the register cap follows what shared memory allows
 // anyway (<96, 4>: two column warps, 168 registers; <128, 2> and <224, 1>: 255 registers) — the column warps keep a Psi
 // column plus three 8-vectors in registers, and spills there sit on the critical path of every knot
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool JL>
 __global__ void __launch_bounds__(THREADS, MINB)
 qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const double* __restrict__ qd_all,
                          double* __restrict__ ws_all, double* __restrict__ z_all,
                          double* __restrict__ st, double* __restrict__ out_rows, int* __restrict__ status,
                          int* __restrict__ n_factor, int* __restrict__ n_solve, int* __restrict__ n_pivot, size_t ws_stride,
                          int want_z, int* __restrict__ fb_list, int* __restrict__ fb_count, int fb_mode,
-                         signed char* __restrict__ wset_all, int warm, double* __restrict__ out2, int* __restrict__ status2)
+                         signed char* __restrict__ wset_all, int warm, double* __restrict__ out2, int* __restrict__ status2,
+                         unsigned* __restrict__ jlset)
 {
+    using CwSm = CwSmemT<JL>;
+    using CwCtx = CdCtxT<CwSm>;
     extern __shared__ __align__(16) unsigned char cw_raw[];
-    CwSmem& sm = *reinterpret_cast<CwSmem*>(cw_raw);
-    double* dyn = reinterpret_cast<double*>(cw_raw + sizeof(CwSmem));
+    CwSm& sm = *reinterpret_cast<CwSm*>(cw_raw);
+    double* dyn = reinterpret_cast<double*>(cw_raw + sizeof(CwSm));
     const DeviceConfig& cfg = cfgv;
     const CwLayout L = cw_layout(cfg);
     double* Om = dyn + L.om;
@@ -467,8 +493,30 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
         sm.dtk[e] = cfg.dt[e];
     for (int e = threadIdx.x; e < 6 * NJ; e += nthr)
         sm.lam[e] = qd[(e < 3 * NJ ? QD_LLIN : QD_LANG - 3 * NJ) + e];
+    if constexpr (JL)
+    {
+        if (threadIdx.x < 2 * NJ)
+            sm.jb[threadIdx.x] = qd[QD_JLO + threadIdx.x];
+        // warm start: the working set of the joint boxes the last solve of this instance ended with (zeros after configure)
+        for (int e = threadIdx.x; e < MAX_ITER; e += nthr)
+            sm.clamp[e] = (jlset && e < Nc && e < CD_JLSET_WORDS) ? jlset[(size_t)inst * CD_JLSET_WORDS + e] : 0u;
+    }
     const bool all_fin = __syncthreads_and(fin);
+    // JL builds: primal-dual active set on the joint boxes around the whole solve, as in the reference-horizon kernel
+    for (int pass = 0;; ++pass)
+    {
     int stat = all_fin ? VSMPC_STATUS_SOLVED : VSMPC_STATUS_NUMERICAL;
+    if constexpr (JL)
+    {
+        if (pass > 0)
+        {
+            for (int e = threadIdx.x; e < L.nlo * ldo; e += nthr)
+                Om[e] = 0.0;
+            for (int e = threadIdx.x; e < 2 * CW_MD * L.nvs; e += nthr)
+                P.As[e] = 0.0;
+            __syncthreads();
+        }
+    }
 
     WCLK(1);
     // ---- factorisation: warp 0 = P recursion, warps 1..G = parameter columns, one knot apart ----------------------
@@ -513,7 +561,12 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                 }
                 __syncwarp();
                 if (elim || ta == TK_SCHUR)
-                    ok = a_eliminate(c, sl, y, hux, own, c.ws + (size_t)ka * L.stage) && ok;
+                {
+                    CdClamp cl{0u, nullptr, nullptr, nullptr};
+                    if constexpr (JL)
+                        cl = CdClamp{sm.clamp[ka], sm.jb, sm.hb[ka & 1], c.ws + (size_t)Nc * L.stage + ka * CW_WSU};
+                    ok = a_eliminate<CwSm, JL>(c, sl, y, hux, own, c.ws + (size_t)ka * L.stage, cl) && ok;
+                }
                 WSUB(wk1, tclk);
             }
         }
@@ -556,7 +609,41 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
                         hut[m] += sm.cf[QD_GQ + m];
                 }
                 const bool schur = tbk == TK_SCHUR;
-                w_downdate(sl, L, gc, y, hut, c.ws + (size_t)kb * L.stage, schur && isD);
+                unsigned cany = 0u;
+                if constexpr (JL)
+                {
+                    const unsigned cm = sm.clamp[kb];
+                    if (cm != 0u)
+                    {
+                        cany = cd_clamped(cm);
+                        // the constants of the clamped components in the value function and in the free rows (CdClamp).  Only
+                        // column `aff` of Om is ever read (gradient of the reduced QP, H_utheta of the Schur step): its entry
+                        // in row gc belongs to this lane after the column barrier of w_prop
+#pragma unroll
+                        for (int cc = 0; cc < NJ; ++cc)
+                        {
+                            if (!((cany >> cc) & 1u))
+                                continue;
+                            const double bc = cd_bval(sm.jb, cm, cc);
+                            if (gc < L.nlo && !isD)
+                                Om[gc * ldo + L.aff] += bc * hut[cc];
+                            if (gc == L.aff)
+                            {
+#pragma unroll
+                                for (int j = 0; j < NX; ++j)
+                                    y[j] = fma(bc, sl.Hux[cc * NX + j], y[j]);
+                            }
+                        }
+                        if (gc == L.aff)
+                        {
+#pragma unroll
+                            for (int m = 0; m < NJ; ++m)
+                                if (!((cany >> m) & 1u))
+                                    hut[m] += sm.hb[kb & 1][m];
+                        }
+                    }
+                }
+                w_downdate<JL>(sl, L, gc, y, hut, c.ws + (size_t)kb * L.stage, schur && isD, cany);
                 WSUB(wk1, tclk);
                 if (schur && gc < L.nlo)
                 {
@@ -908,38 +995,69 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     }
     __syncthreads();
     WCLK(6);
-    if (warp != 0)
-        return;
+    if constexpr (!JL)
+    {
+        if (warp != 0)
+            return;
+    }
 
     // ---- warp 0: forward rollout and outputs ----------------------------------------------------------------------
-    double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
-    double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
-    if (fb_mode == 2 && all_fin)
-        stat = VSMPC_STATUS_NUMERICAL;   // test hook: every instance goes through the fallback kernel
-    if (lane == 0)
+    int again = 0;
+    if (warp == 0)
     {
-        if (stat != VSMPC_STATUS_SOLVED && all_fin && fb_mode != 0)   // see vsmpc_qp_fallback.cu
-            fb_list[atomicAdd(fb_count, 1)] = inst;
-        status[inst] = stat;
-        n_factor[inst] = 1;
-        n_solve[inst] = stat == VSMPC_STATUS_SOLVED ? 1 : 0;
-        n_pivot[inst] = sm.flags[2];
+        double* z = want_z ? z_all + (size_t)inst * cfg.n_var : nullptr;
+        double* o = out_rows + (size_t)inst * VSMPC_OUT_DOUBLES;
+        if (fb_mode == 2 && all_fin)
+            stat = VSMPC_STATUS_NUMERICAL;   // test hook: every instance goes through the fallback kernel
+        const bool solved = stat == VSMPC_STATUS_SOLVED;
+        int fwd = 0;
+        if (solved)
+        {
+            const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
+            if constexpr (JL)
+            {
+                fwd = cd_forward<CwSm, true>(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st, sm.ostage, jl,
+                                             sm.clamp, c.ws + (size_t)Nc * L.stage, sm.cand, pass >= CW_JL_PLAIN);
+                again = (fwd == 1 && pass + 1 < CW_JL_PASSES) ? 1 : 0;      // the working set of the joint boxes moved
+            }
+            else
+                fwd = cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st, sm.ostage, jl);
+        }
+        if (!again)
+        {
+            if (lane == 0)
+            {
+                // see vsmpc_qp_condensed.cu: recursion broken down on finite data, or a joint box active that this build does not
+                // carry (or whose working set did not settle) -> fallback kernel; outputs and the joint accumulator are held
+                // (variableSamplingMPC.cpp:91)
+                if (((!solved && all_fin) || fwd != 0) && fb_mode != 0)
+                    fb_list[atomicAdd(fb_count, 1)] = inst;
+                status[inst] = (solved && fwd != 0) ? VSMPC_STATUS_NUMERICAL : stat;
+                n_factor[inst] = pass + 1;
+                n_solve[inst] = (solved && fwd == 0) ? 1 : 0;
+                n_pivot[inst] = sm.flags[2];
+            }
+            cd_stage_outputs(o, status, inst, lane, out2, status2);
+            if constexpr (JL)
+            {
+                if (jlset)
+                    for (int e = lane; e < CD_JLSET_WORDS; e += 32)
+                        jlset[(size_t)inst * CD_JLSET_WORDS + e] = (solved && fwd == 0 && e < Nc) ? sm.clamp[e] : 0u;
+            }
+            WCLK(7);
+        }
     }
-    if (stat != VSMPC_STATUS_SOLVED)
+    if constexpr (JL)
     {
-        cd_stage_outputs(o, status, inst, lane, out2, status2);     // the held row
-        return; // outputs and the joint accumulator are held (variableSamplingMPC.cpp:91)
+        if (warp == 0 && lane == 0)
+            sm.flags[3] = again;
+        __syncthreads();
+        if (sm.flags[3] == 0)
+            return;
     }
-    const double* jl = qd[QD_JLIM] != 0.0 ? qd + QD_JLO : nullptr;     // optional joint-limit rows
-    if (cd_forward(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st, sm.ostage, jl) && lane == 0)
-    {
-        status[inst] = VSMPC_STATUS_NUMERICAL;       // see vsmpc_qp_condensed.cu: a joint box is active, fallback kernel
-        n_solve[inst] = 0;
-        if (fb_mode != 0)
-            fb_list[atomicAdd(fb_count, 1)] = inst;
-    }
-    cd_stage_outputs(o, status, inst, lane, out2, status2);
-    WCLK(7);
+    else
+        return;
+    }   // pass
 }
 
 int condensed_wide_phase_clocks(long long* host, int n)
@@ -952,9 +1070,17 @@ int condensed_wide_phase_clocks(long long* host, int n)
 #endif
 }
 
-static size_t cw_smem_bytes(const DeviceConfig& cfg)
+static size_t cw_smem_bytes(const DeviceConfig& cfg, bool jl = false)
 {
-    return sizeof(CwSmem) + (size_t)cw_layout(cfg).total * sizeof(double);
+    return (jl ? sizeof(CwSmemT<true>) : sizeof(CwSmem)) + (size_t)cw_layout(cfg).total * sizeof(double);
+}
+
+// the build that carries the joint boxes itself: up to three column warps (2x and 3x the reference knot count); beyond that the
+// shared memory of the CTA is spent on Om, the plain build checks the boxes and the fallback kernel carries them
+static bool cw_jl_build(const DeviceConfig& cfg)
+{
+    const CwLayout L = cw_layout(cfg);
+    return cfg.use_jl && L.G <= 3 && cfg.Nc <= CD_JLSET_WORDS && cw_smem_bytes(cfg, true) <= (size_t)CW_SMEM_LIMIT;
 }
 
 bool condensed_wide_supported(const DeviceConfig& cfg)
@@ -967,7 +1093,7 @@ bool condensed_wide_supported(const DeviceConfig& cfg)
 
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg)
 {
-    return (size_t)cfg.Nc * cw_layout(cfg).stage;
+    return (size_t)cfg.Nc * (cw_layout(cfg).stage + CW_WSU);   // the stages, then raw H_uu per joint block (JL builds)
 }
 
 size_t condensed_wide_wset_bytes(const DeviceConfig& cfg)
@@ -984,37 +1110,52 @@ size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg)
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
                                      double* z, double* st, double* out_rows, int* status, int* n_factor, int* n_solve,
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
-                                     int warm, double* out2, int* status2, cudaStream_t s)
+                                     int warm, double* out2, int* status2, unsigned* jlset, cudaStream_t s)
 {
-    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {};
+    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {}, attr_d[64] = {}, attr_e[64] = {};
     const CwLayout L = cw_layout(h_cfg);
-    const size_t smem = cw_smem_bytes(h_cfg);
+    const bool jlb = cw_jl_build(h_cfg);
+    const size_t smem = cw_smem_bytes(h_cfg, jlb);
     const size_t wsd = condensed_wide_ws_doubles(h_cfg);
     (void)scratch;     // no global scratch beyond the workspace stacks
     const int fbm = fb_list && fb_count ? fb_mode : 0;
     cudaError_t e;
-    if (L.G <= 2)
+    if (jlb && L.G <= 2)
     {
-        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4, true>, CW_SMEM_LIMIT, attr_d)) != cudaSuccess)
             return e;
-        qp_condensed_wide_kernel<96, 4><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                       n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2);
+        qp_condensed_wide_kernel<96, 4, true><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                             n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, jlset);
+    }
+    else if (jlb)
+    {
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2, true>, CW_SMEM_LIMIT, attr_e)) != cudaSuccess)
+            return e;
+        qp_condensed_wide_kernel<128, 2, true><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                              n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, jlset);
+    }
+    else if (L.G <= 2)
+    {
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<96, 4, false>, CW_SMEM_LIMIT, attr_a)) != cudaSuccess)
+            return e;
+        qp_condensed_wide_kernel<96, 4, false><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                              n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, nullptr);
     }
     else if (L.G == 3)
     {
-        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2, false>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
-        qp_condensed_wide_kernel<128, 2><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                        n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2);
+        qp_condensed_wide_kernel<128, 2, false><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                               n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, nullptr);
     }
     else
     {
-        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<CW_MAXTHREADS, 1>, CW_SMEM_LIMIT, attr_c)) != cudaSuccess)
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<CW_MAXTHREADS, 1, false>, CW_SMEM_LIMIT, attr_c)) != cudaSuccess)
             return e;
         // eight warps whatever G: the block-wide phases (tensor-core contractions, pivots, active set) are bound by the
         // per-sub-partition FP64 / shared-memory throughput, which 5-7 warps load unevenly
-        qp_condensed_wide_kernel<CW_MAXTHREADS, 1><<<B, CW_MAXTHREADS, smem, s>>>(
-            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2);
+        qp_condensed_wide_kernel<CW_MAXTHREADS, 1, false><<<B, CW_MAXTHREADS, smem, s>>>(
+            h_cfg, B, qd, ws, z, st, out_rows, status, n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, nullptr);
     }
     return cudaGetLastError();
 }
