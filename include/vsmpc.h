@@ -125,10 +125,11 @@ typedef struct vsmpc_config
      * jointPos_min [degrees, :421-423] are absent from the XML).  When enabled, 8 * nIter rows are appended after the throttle
      * rows (:391), block i < controlHorizon bounding dq_i — the displacement from the commanded posture acting on knot i — by
      * jointPos_min - q_cmd <= dq_i <= jointPos_max - q_cmd (:450-453), per block.  The reference's m_firstIteriation slip
-     * (:440-449, identity rows only for block 0) is fixed, not ported.  Default solver only.  At the reference horizon the QP
-     * kernel carries the joint boxes in its own working set (clamped increments inside its 8 x 8 eliminations, one more
-     * factorisation per change of the working set, vsmpc_get_counts reports them); long horizons hand an instance with an
-     * active joint bound to the fallback kernel (vsmpc_set_fallback). */
+     * (:440-449, identity rows only for block 0) is fixed, not ported.  Default solver only.  The QP kernels carry the joint boxes in
+     * their own working set (clamped increments inside the 8 x 8 eliminations, one more factorisation per change of the
+     * working set, vsmpc_get_counts reports them; reference horizon and up to twice its knot count); an instance whose working
+     * set does not settle goes to the fallback kernel (vsmpc_set_fallback), whose size limit — 4 x throttle blocks +
+     * 8 x controlHorizon <= 256 — is also the limit of the rows: vsmpc_create refuses them beyond. */
     int use_joint_limits;
     double joint_pos_min_deg[VSMPC_NJ];   /* jointPos_min of the controlled joints */
     double joint_pos_max_deg[VSMPC_NJ];   /* jointPos_max */
@@ -170,7 +171,7 @@ int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const doub
 
 /* Warm start — the counterpart of the reference running OSQP with setWarmStart(true) (IMPCProblem.cpp:140).  Long horizons
  * (more than 6 throttle blocks): the active set of the reduced throttle QP starts from the working set the instance ended its
- * previous solve with (device-resident; all-lower vertex after vsmpc_configure).  Reference horizon with joint-limit rows:
+ * previous solve with (device-resident; all-lower vertex after vsmpc_configure).  Joint-limit rows (any horizon that has them):
  * the working set of the joint boxes starts from the one the previous solve ended with (empty after vsmpc_configure and after
  * vsmpc_set_joint_limits).  Any guess gives the same minimiser; enable = 0 starts every solve cold (tests, A/B timing).
  * Default: on. */

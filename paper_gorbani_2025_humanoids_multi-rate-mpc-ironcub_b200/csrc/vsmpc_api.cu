@@ -62,6 +62,7 @@ cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h
                                 double* out2, int* status2, unsigned* jlset, cudaStream_t s);
 size_t condensed_jlset_words();
 bool condensed_wide_supported(const DeviceConfig& cfg);
+bool condensed_wide_jl_supported(const DeviceConfig& cfg);
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,
@@ -396,6 +397,9 @@ int vsmpc_create(const vsmpc_config* c, int n_instances, int device, vsmpc_handl
         return bail(VSMPC_ERR_UNSUPPORTED, "horizons with more than 48 throttle blocks are not supported");
     if (h->solver == 2 && (NT * g.nblk > 24 || g.N > 32))
         return bail(VSMPC_ERR_UNSUPPORTED, "the structured one-warp kernel covers horizons with <= 6 throttle blocks and <= 32 knots");
+    // joint-limit rows: the reference-horizon kernel and the long-horizon kernel with up to two column warps carry the joint
+    // boxes in their own working set; the fallback kernel is the net behind a working set that does not settle and the
+    // carrier where the QP kernel has none — so the rows go as far as the fallback kernel's size limit
     if (g.use_jl && !((h->solver == 0 || h->solver == SOLVER_WIDE) && fallback_supported(g)))
         return bail(VSMPC_ERR_UNSUPPORTED, "joint-limit rows need the default solver on a horizon the fallback kernel covers");
     const int B = n_instances;
@@ -1270,7 +1274,7 @@ static int solve_launch(vsmpc_handle* h)
     else
         CK(launch_qp_structured(h->d_cfg, h->cfg, h->B, h->d_qd, h->d_ws, h->d_scratch, h->d_z, h->d_st, h->d_out,
                                 h->d_status, h->d_nf, h->d_ns, h->want_full ? 1 : 0, h->stream));
-    if (h->fb_mode != 0 && (h->solver == 0 || h->solver == SOLVER_WIDE))
+    if (h->fb_mode != 0 && h->d_fb_list && (h->solver == 0 || h->solver == SOLVER_WIDE))
         CK(launch_qp_fallback(h->cfg, h->B, h->fb_slots, h->d_qd, h->d_fb_list, h->d_fb_count, h->d_fb_pos, h->d_fb_scratch,
                               h->d_z, h->d_st, h->d_out, h->d_status, h->d_nf, h->d_ns, h->d_np, h->want_full ? 1 : 0,
                               out2, status2, h->stream));

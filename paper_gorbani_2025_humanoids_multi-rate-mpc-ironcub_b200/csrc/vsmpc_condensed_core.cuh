@@ -490,7 +490,7 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
                                           double* __restrict__ o, double* __restrict__ st, double* __restrict__ ostage,
                                           const double* __restrict__ jl, unsigned* __restrict__ clamp = nullptr,
                                           const double* __restrict__ uraw_all = nullptr, unsigned* __restrict__ cand = nullptr,
-                                          bool careful = false)
+                                          int mode = 0)
 {
     const int N = cfg.N, Nc = cfg.Nc, nv = 4 * cfg.nblk;
     CdFwdTab tab;
@@ -632,9 +632,12 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
         return 2;
     if constexpr (JL)
     {
-        // next working set, all blocks at once (lane = block).  First passes: joins and leaves together (two to four passes on
-        // the test workloads).  careful (later passes): leaves only once no free increment is outside its box — the joint
-        // add / release of the plain iteration can cycle on general data
+        // next working set, all blocks at once (lane = block).  mode 0 (first passes): joins and leaves together (two to four
+        // passes on the test workloads).  mode 2 (last pass of the first group): the same, but a set that still moves is
+        // EMPTIED — a warm start from an unrelated working set can cycle where the cold start settles.  mode 1 (late passes):
+        // leaves only once no free increment is outside its box — the joint add / release of the plain iteration can cycle
+        // on general data
+        const bool careful = mode == 1;
         __syncwarp();
         const int ncr = (Nc + 31) & ~31;
         bool any_add = false;
@@ -650,6 +653,11 @@ __device__ __forceinline__ int cd_forward(const DeviceConfig& cfg, SM& sm, const
                 nm &= ~(rl | (rl << 8));
             viol = viol || nm != old;
             clamp[k0] = nm;
+        }
+        if (mode == 2 && __any_sync(0xffffffffu, viol))
+        {
+            for (int k0 = lane; k0 < Nc; k0 += 32)
+                clamp[k0] = 0u;
         }
         __syncwarp();
     }

@@ -49,8 +49,13 @@ template <bool JL> struct CdJlSmem
 template <> struct CdJlSmem<false>
 {
 };
-constexpr int CD_JL_PASSES = 14;  // factorisations per solve before the instance is handed to the fallback kernel
-constexpr int CD_JL_PLAIN = 5;    // of which with joins and leaves applied together; then leaves wait for primal feasibility
+constexpr int CD_JL_PASSES = 16;  // factorisations per solve before the instance is handed to the fallback kernel
+constexpr int CD_JL_PLAIN = 5;    // passes 0..4 from the stored working set and 5..9 from the empty one apply joins and leaves together;
+                                  // from pass 10 leaves wait for primal feasibility (cd_forward)
+__device__ __forceinline__ int cd_jl_mode(int pass, int plain)
+{
+    return pass == plain - 1 ? 2 : (pass < 2 * plain ? 0 : 1);
+}
 constexpr int WSC_U = NJ * NJ;    // per joint block, behind the Nc stages of the workspace: raw H_uu [8][8]
 
 template <int NSLOT, bool JL = false> struct alignas(16) CdSmemT : CdJlSmem<JL>
@@ -986,7 +991,7 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
             if constexpr (JL)
             {
                 fwd = cd_forward<CdSmem, true>(cfg, sm, c.ws, WSC_STAGE, sm.theta, fth, xs, lane, B, inst, z, o, st, sm.Mt + 304, jl,
-                                               sm.clamp, c.ws + (size_t)Nc * WSC_STAGE, sm.cand, pass >= CD_JL_PLAIN);
+                                               sm.clamp, c.ws + (size_t)Nc * WSC_STAGE, sm.cand, cd_jl_mode(pass, CD_JL_PLAIN));
                 // the working set of the joint boxes moved: factorise again with it
                 again = (fwd == 1 && pass + 1 < CD_JL_PASSES) ? 1 : 0;
             }

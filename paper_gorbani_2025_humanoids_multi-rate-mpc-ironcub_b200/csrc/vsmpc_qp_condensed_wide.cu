@@ -42,7 +42,7 @@ template <bool JL> struct CwJlSmem
 template <> struct CwJlSmem<false>
 {
 };
-constexpr int CW_JL_PASSES = 14, CW_JL_PLAIN = 5;   // as in the reference-horizon kernel
+constexpr int CW_JL_PASSES = 24, CW_JL_PLAIN = 6;   // more boxes than at the reference horizon: more passes before the hand-over
 constexpr int CW_WSU = NJ * NJ;                       // per joint block, behind the Nc stages of the workspace: raw H_uu [8][8]
 
 template <bool JL> struct alignas(16) CwSmemT : CwJlSmem<JL>
@@ -1017,7 +1017,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
             if constexpr (JL)
             {
                 fwd = cd_forward<CwSm, true>(cfg, sm, c.ws, L.stage, theta, fth, sm.xs, lane, B, inst, z, o, st, sm.ostage, jl,
-                                             sm.clamp, c.ws + (size_t)Nc * L.stage, sm.cand, pass >= CW_JL_PLAIN);
+                                             sm.clamp, c.ws + (size_t)Nc * L.stage, sm.cand,
+                                             pass == CW_JL_PLAIN - 1 ? 2 : (pass < 2 * CW_JL_PLAIN + 2 ? 0 : 1));
                 again = (fwd == 1 && pass + 1 < CW_JL_PASSES) ? 1 : 0;      // the working set of the joint boxes moved
             }
             else
@@ -1075,12 +1076,14 @@ static size_t cw_smem_bytes(const DeviceConfig& cfg, bool jl = false)
     return (jl ? sizeof(CwSmemT<true>) : sizeof(CwSmem)) + (size_t)cw_layout(cfg).total * sizeof(double);
 }
 
-// the build that carries the joint boxes itself: up to three column warps (2x and 3x the reference knot count); beyond that the
-// shared memory of the CTA is spent on Om, the plain build checks the boxes and the fallback kernel carries them
+// the build that carries the joint boxes itself: up to two column warps (2x the reference knot count), which is as far as the
+// fallback kernel — the net behind a working set that does not settle — covers joint-limit rows (vsmpc_create refuses them
+// beyond).  Tried at 3x (four column warps, 288 boxes, no net): on the tight-box test workload a tenth of the instances did not
+// settle within 24 passes, so the rows stay refused there.
 static bool cw_jl_build(const DeviceConfig& cfg)
 {
     const CwLayout L = cw_layout(cfg);
-    return cfg.use_jl && L.G <= 3 && cfg.Nc <= CD_JLSET_WORDS && cw_smem_bytes(cfg, true) <= (size_t)CW_SMEM_LIMIT;
+    return cfg.use_jl && L.G <= 2 && cfg.Nc <= CD_JLSET_WORDS && cw_smem_bytes(cfg, true) <= (size_t)CW_SMEM_LIMIT;
 }
 
 bool condensed_wide_supported(const DeviceConfig& cfg)
@@ -1089,6 +1092,13 @@ bool condensed_wide_supported(const DeviceConfig& cfg)
         return false;
     const CwLayout L = cw_layout(cfg);
     return L.G <= CW_MAXG && cw_smem_bytes(cfg) <= (size_t)CW_SMEM_LIMIT;
+}
+
+bool condensed_wide_jl_supported(const DeviceConfig& cfg)
+{
+    DeviceConfig c = cfg;
+    c.use_jl = 1;
+    return condensed_wide_supported(cfg) && cw_jl_build(c);
 }
 
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg)
@@ -1112,7 +1122,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
                                      int warm, double* out2, int* status2, unsigned* jlset, cudaStream_t s)
 {
-    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {}, attr_d[64] = {}, attr_e[64] = {};
+    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {}, attr_d[64] = {};
     const CwLayout L = cw_layout(h_cfg);
     const bool jlb = cw_jl_build(h_cfg);
     const size_t smem = cw_smem_bytes(h_cfg, jlb);
@@ -1126,13 +1136,6 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
             return e;
         qp_condensed_wide_kernel<96, 4, true><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
                                                                              n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, jlset);
-    }
-    else if (jlb)
-    {
-        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2, true>, CW_SMEM_LIMIT, attr_e)) != cudaSuccess)
-            return e;
-        qp_condensed_wide_kernel<128, 2, true><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
-                                                                              n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, jlset);
     }
     else if (L.G <= 2)
     {

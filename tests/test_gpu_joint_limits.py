@@ -6,9 +6,9 @@ extension: 8 * nIter rows after the throttle rows, block i < controlHorizon boun
 every block (the m_firstIteriation slip of :440-449 is fixed, not ported).  The oracle registers the same class when the two
 parameters are given.  At the reference horizon the QP kernel carries the joint boxes itself: a primal-dual working set on
 the 8 x controlHorizon boxes, clamped increments held as constants inside the 8 x 8 eliminations, one more factorisation per
-change of the working set (2-4 in all when bounds are active, tools/condensed_model.py ClampedCondensedQP).  The long-horizon
-kernel solves instances whose unconstrained joint increments stay inside the box and hands the others to the KKT fallback
-kernel, whose active set then carries the joint boxes.
+change of the working set (2-4 in all when bounds are active, tools/condensed_model.py ClampedCondensedQP); the long-horizon
+kernel does the same up to twice the reference knot count.  The KKT fallback kernel, whose active set can carry the joint boxes
+too, is the net behind a working set that does not settle.
   * CPU: the oracle's rows, bounds and minimiser (KKT certificate of the exact solver, boxes respected, bounds active);
   * GPU: gradient / bounds / constraint matrix against the oracle's assembly, the minimiser and every output field per
     physical quantity (1e-6 relative) on a workload where well over 10 % of the instances have an active joint bound,
@@ -144,8 +144,7 @@ def test_joint_limit_rows_match_oracle(horizon):
     nom = syn.make_states(B, perturbed=False)
     mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), full_solution=True)
     mpc.configure(nom)
-    if horizon is None:
-        mpc.set_fallback(0)       # reference horizon: the QP kernel carries the joint boxes itself (working set + re-factorisation)
+    mpc.set_fallback(0)           # both kernels carry the joint boxes themselves (working set + re-factorisation): no KKT fallback
     oracles = [OracleInstance(nom, i, params=params, trajectories=traj) for i in range(B)]
     p = oracles[0].params
     N, Nc, nblk = p["nIter"], p["controlHorizon"], p["controlHorizon"] - p["nIterSmall"] + 1
@@ -245,7 +244,7 @@ def test_joint_boxes_inside_the_qp_kernel_kkt_certificate_at_1024_instances():
     assert k["dual_sign_dq"].max() < 1e-9, k["dual_sign_dq"].max()
     assert k["box"].max() < 1e-12 and k["box_dq"].max() <= 1e-9
     assert k["instances_dq_at_bound"] > B // 10 and k["n_dq_at_bound"] > B       # the workload exercises the joint boxes
-    assert (nf[(ns == 1)] >= 1).all() and nf.max() <= 14 and (nf >= 2).sum() >= k["instances_dq_at_bound"]
+    assert (nf[(ns == 1)] >= 1).all() and nf.max() <= 16 and (nf >= 2).sum() >= k["instances_dq_at_bound"]
     for i in np.random.default_rng(7).choice(B, 6, replace=False):
         o = OracleInstance(nom, int(i), params=LIMITS, trajectories=traj, phase0=int(phase0[i]))
         o.update(per)
@@ -287,3 +286,43 @@ def test_joint_box_working_set_warm_start_same_minimiser_fewer_factorisations():
     assert np.array_equal(cold[0], warm[0])           # first tick after configure: empty guess either way
     # the same state again: the guess is the answer up to the 20-tick phase of the throttle rows
     assert warm[1].mean() < 1.5 and warm[3].mean() < 1.5 and warm[1].mean() < 0.6 * cold[1].mean()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hz", [(34, 14, 24), (28, 10, 20)])
+def test_joint_boxes_inside_the_long_horizon_kernel_kkt_certificate(hz):
+    """Twice the reference knot count and a horizon in between (the JL build of the long-horizon kernel, two column warps),
+    joint-limit rows on, fallback kernel OFF: KKT certificate including the joint boxes for every instance."""
+    N, Ns, Nc = hz
+    B = 128
+    syn, bat, P = pkg("synthetic"), pkg("batched"), pkg("pack")
+    traj = load_trajectories()
+    params = dict(LIMITS, nIter=N, nIterSmall=Ns, controlHorizon=Nc)
+    nom = syn.make_states(B, perturbed=False)
+    per = syn.make_states(B, seed=515 + N, perturbed=True, near_bound_fraction=0.3)
+    mpc = bat.BatchedVSMPC(B, params, oracle_trajectories_to_product(traj), full_solution=True)
+    phase0 = (np.arange(B) % 20).astype(np.int32)
+    mpc.configure_pack(P.build_pack(nom), np.ascontiguousarray(nom["joint_pos"][:, P.DEFAULT_JOINT_SELECTOR].T), phase0)
+    mpc.set_fallback(0)
+    for tick in range(2):                  # the second tick starts from the stored working sets (throttle and joint boxes)
+        mpc.update(per)
+        A, BJ, BT, c, dt = mpc.get_dynamics()
+        q, l, u = mpc.get_qp_vectors()
+        mpc.solveMPC()
+        z = mpc.getSolution()
+        _, status = mpc.get_output()
+        nf, ns = mpc.get_counts()
+        assert (status == 0).all(), (tick, np.unique(status, return_counts=True))
+        if tick == 0:
+            H = mpc.getHessian(0)
+            Pd, w_t = split_hessian(H, N, Nc)
+            nf0 = nf.copy()
+        # the commanded posture the rows are written against moves with the accumulated joint references: bounds from the library
+        nrow_thr = l.shape[1] - 26 * N - 26 - 8 * N
+        lo, hi = l[:, 26 * N + 26 + nrow_thr:][:, :8], u[:, 26 * N + 26 + nrow_thr:][:, :8]
+        k = kkt_certificate(z, A, BJ, BT, dt, q, l, u, Pd, w_t, N, Ns, Nc, dq_lo=lo, dq_hi=hi)
+        assert k["stationarity_dq"].max() < 1e-9 and k["dual_sign_dq"].max() < 1e-9 and k["box_dq"].max() <= 1e-9, (tick, k)
+        assert k["complementarity"].max() < 1e-9 and k["dual_sign"].max() < 1e-9 and k["box"].max() < 1e-12
+        assert k["instances_dq_at_bound"] > B // 10
+    assert nf0.max() <= 24 and (nf0 >= 2).sum() > B // 10 and nf.mean() < nf0.mean()
+    mpc.close()

@@ -383,12 +383,14 @@ class ClampedCondensedQP(CondensedQP):
         self.gmag = gmag
         return x, dq, v, grad
 
-    def solve_boxes(self, lo, hi, clamp0=None, max_pass=14, plain_passes=5, tol=1e-9):
+    def solve_boxes(self, lo, hi, clamp0=None, max_pass=16, plain_passes=5, tol=1e-9):
         """-> x, dq, v, passes (-1: the working set did not settle), clamp.  clamp0: first guess (warm start).
         Joins: free increments more than tol outside their box.  Leaves: clamped increments whose multiplier is negative beyond
         the rounding of its own terms (1e-9 relative: a degenerate increment — on its bound, zero multiplier — must not be
-        released on noise, it would come back 1e-9 outside and the iteration would never settle).  The first plain_passes apply
-        joins and leaves together; after that leaves wait until no free increment is outside its box."""
+        released on noise, it would come back 1e-9 outside and the iteration would never settle).  Passes 0 .. plain_passes - 1
+        (from the guess) and plain_passes .. 2 plain_passes - 1 (from the EMPTY set, if the first group did not settle: an
+        unrelated guess can cycle where the cold start settles) apply joins and leaves together; after that leaves wait until
+        no free increment is outside its box."""
         clamp = np.zeros((self.Nc, NJ), dtype=int) if clamp0 is None else np.array(clamp0, dtype=int)
         for p in range(max_pass):
             self.factor_clamped(clamp, lo, hi)
@@ -401,9 +403,9 @@ class ClampedCondensedQP(CondensedQP):
             new = clamp.copy()
             new[add_u] = 1
             new[add_l] = -1
-            if not (p >= plain_passes and (add_u.any() or add_l.any())):
+            if not (p >= 2 * plain_passes and (add_u.any() or add_l.any())):
                 new[rel] = 0
             if (new == clamp).all():
                 return x, dq, v, p + 1, clamp
-            clamp = new
+            clamp = np.zeros_like(new) if p == plain_passes - 1 else new
         return x, dq, v, -1, clamp
