@@ -62,7 +62,6 @@ cudaError_t launch_qp_condensed(const DeviceConfig* d_cfg, const DeviceConfig& h
                                 double* out2, int* status2, unsigned* jlset, cudaStream_t s);
 size_t condensed_jlset_words();
 bool condensed_wide_supported(const DeviceConfig& cfg);
-bool condensed_wide_jl_supported(const DeviceConfig& cfg);
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg);
 size_t condensed_wide_scratch_doubles(const DeviceConfig& cfg);
 cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const double* qd, double* ws, double* scratch,

@@ -1094,13 +1094,6 @@ bool condensed_wide_supported(const DeviceConfig& cfg)
     return L.G <= CW_MAXG && cw_smem_bytes(cfg) <= (size_t)CW_SMEM_LIMIT;
 }
 
-bool condensed_wide_jl_supported(const DeviceConfig& cfg)
-{
-    DeviceConfig c = cfg;
-    c.use_jl = 1;
-    return condensed_wide_supported(cfg) && cw_jl_build(c);
-}
-
 size_t condensed_wide_ws_doubles(const DeviceConfig& cfg)
 {
     return (size_t)cfg.Nc * (cw_layout(cfg).stage + CW_WSU);   // the stages, then raw H_uu per joint block (JL builds)
