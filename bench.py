@@ -52,28 +52,78 @@ def flops_per_solve(nx, nu, N, n_f, n_s):
     return F_l + n_f * F_f + n_s * F_s, dict(F_f=F_f, F_s=F_s, F_l=F_l)
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs.  The sampler is a child process writing to
-    a file that is parsed afterwards: a Python reader thread would take the GIL away from the host loop being timed."""
+_NVML_CHILD = r"""
+import os, sys, time
+import pynvml as N
+N.nvmlInit()
+ppid = os.getppid()
+ident, path = sys.argv[1], sys.argv[2]
+try:
+    h = N.nvmlDeviceGetHandleByUUID(ident if ident.startswith("GPU-") else "GPU-" + ident) if "-" in ident else N.nvmlDeviceGetHandleByIndex(int(ident))
+except Exception:
+    h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[3]))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+with open(path, "w") as f:
+    while True:
+        f.write("%.6f,%d,%d,%d\n" % (time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), mx, int(reasons(h))))
+        f.flush()
+        time.sleep(0.004)
+        if os.getppid() != ppid:      # the bench is gone: do not linger
+            break
+"""
 
-    def __init__(self, gpu_index: int):
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled WHILE the timed region runs (B200_PROFILING.md's clocks line).  The timed region of
+    this bench is tens of milliseconds, shorter than one `nvidia-smi -lms` period plus its start-up, so the sampler is a child
+    process reading NVML every 4 ms into a file (a Python thread in this process would take the GIL away from the host loop
+    being timed); the parent marks the timed windows with wall-clock times and summarises the samples that fall inside them.
+    Falls back to `nvidia-smi -lms 20` if NVML's Python module is missing."""
+    # NVML clocks event reasons (nvml.h): sw power cap 0x4, hw slowdown 0x8, sw thermal 0x20, hw thermal 0x40
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+
+    def __init__(self, gpu_index: int, uuid: str = ""):
         import tempfile
-        self.gpu = gpu_index
-        self.samples = []
-        self.proc = None
+        self.gpu, self.uuid = gpu_index, uuid
+        self.samples, self.windows = [], []
+        self.proc, self.mode = None, None
         self.path = tempfile.mktemp(prefix="vsmpc_clocks_", suffix=".csv")
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.out = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=self.out, stderr=subprocess.DEVNULL)
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_CHILD, self.uuid or str(self.gpu), self.path, str(self.gpu)],
+                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            self.mode = "nvml"
         except Exception:
             self.proc = None
+
+    def ready(self):
+        """True once the child has written its first sample (or has died: then the nvidia-smi fallback is started)."""
+        try:
+            if os.path.getsize(self.path) > 0:
+                return True
+        except OSError:
+            pass
+        if self.proc is not None and self.proc.poll() is not None and self.mode == "nvml":
+            q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown")
+            try:
+                self.out = open(self.path, "w")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.uuid and 'GPU-' + self.uuid or self.gpu}", f"--query-gpu={q}",
+                                              "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.out, stderr=subprocess.DEVNULL)
+                self.mode = "smi"
+            except Exception:
+                self.proc, self.mode = None, "none"
+                return True
+        return self.proc is None
+
+    def begin(self):
+        self.windows.append([time.time(), None])
+
+    def end(self):
+        if self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.time()
 
     def stop(self):
         if self.proc:
@@ -83,7 +133,6 @@ class ClockSampler:
             except Exception:
                 pass
         try:
-            self.out.close()
             with open(self.path) as f:
                 self.samples = [[x.strip() for x in line.split(",")] for line in f if line.strip()]
             os.remove(self.path)
@@ -91,21 +140,29 @@ class ClockSampler:
             pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm, mx, reasons, sm_all = [], [], set(), []
         for s in self.samples:
             try:
-                sm.append(float(s[0]))
-                mx.append(float(s[1]))
-                for n, v in zip(names, s[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                if self.mode == "nvml":
+                    t, c, m, r = float(s[0]), float(s[1]), float(s[2]), int(s[3])
+                    inside = any(a <= t <= (b if b is not None else t) for a, b in self.windows) or not self.windows
+                    rs = [n for n, bit in self.BITS if r & bit]
+                else:       # nvidia-smi lines carry no epoch time: every line counts (the loop started before the windows)
+                    c, m = float(s[1]), float(s[2])
+                    inside = True
+                    rs = [n for (n, _), v in zip(self.BITS, s[3:7]) if v.lower().startswith("active")]
+                sm_all.append(c)
+                if inside:
+                    sm.append(c)
+                    mx.append(m)
+                    reasons.update(rs)
             except Exception:
                 continue
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_min": float(min(sm)), "source": "NVML every 4 ms, samples inside the timed windows" if self.mode == "nvml"
+                else "nvidia-smi -lms 20", "samples_total": len(sm_all)}
 
 
 def load_traj():
@@ -193,11 +250,24 @@ def run_ours(args):
     del scratch
 
     # ---------------- device-resident leg -------------------------------------------------------------
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = ""
+    sampler = ClockSampler(local_rank, uuid)
+    sampler.start()
     for j in range(Wm):
         step_dev(j)
+    # the warm-up goes on (GPU under load, clocks up) until the clock sampler has delivered its first sample
+    t_ready = time.perf_counter()
+    j = Wm
+    while not sampler.ready() and time.perf_counter() - t_ready < 5.0:
+        step_dev(j)
+        j += 1
+        if j % 16 == 0:
+            torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     nf_sum = ns_sum = 0.0
@@ -211,6 +281,7 @@ def run_ours(args):
         mpc.solve_async()
         e2.record(stream)
     barrier()
+    sampler.end()
     t_wall = time.perf_counter() - t_wall0
     k1_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in ev)
     k2_ms = sum(e1.elapsed_time(e2) for _, e1, e2 in ev)
@@ -236,10 +307,12 @@ def run_ours(args):
 
     e2e_loop(Wm)
     barrier()
+    sampler.begin()
     t0 = time.perf_counter()
     e2e_loop(K)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    sampler.end()
     barrier()
     # the same sequence with a blocking read-back every step (no overlap), for reference
     for j in range(Wm):
