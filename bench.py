@@ -145,7 +145,8 @@ class ClockSampler:
             try:
                 if self.mode == "nvml":
                     t, c, m, r = float(s[0]), float(s[1]), float(s[2]), int(s[3])
-                    inside = any(a <= t <= (b if b is not None else t) for a, b in self.windows) or not self.windows
+                    # windows padded by 20 ms: the GPU is under the same load right before (warm-up) and after them
+                    inside = any(a - 0.02 <= t <= (b if b is not None else t) + 0.02 for a, b in self.windows) or not self.windows
                     rs = [n for n, bit in self.BITS if r & bit]
                 else:       # nvidia-smi lines carry no epoch time: every line counts (the loop started before the windows)
                     c, m = float(s[1]), float(s[2])
@@ -161,7 +162,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "sm_mhz_min": float(min(sm)), "source": "NVML every 4 ms, samples inside the timed windows" if self.mode == "nvml"
+                "sm_mhz_min": float(min(sm)), "source": "NVML every 4 ms, samples inside the timed windows (+- 20 ms)" if self.mode == "nvml"
                 else "nvidia-smi -lms 20", "samples_total": len(sm_all)}
 
 
