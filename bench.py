@@ -337,8 +337,10 @@ def run_ours(args):
     if rank == 0 and args.rollout_ticks > 0:
         closed = closed_loop_leg(bat, B, local_rank, stream, args.rollout_ticks, args.solver)
     # ---------------- the other BASELINE configurations, every rank (skipped by --no-extras / --horizon) ------------
-    gather = long_h = monte = sweep = e2e_kin = None
+    gather = long_h = monte = sweep = e2e_kin = cpp_host = None
     if not args.no_extras and not params:
+        if rank == 0:
+            cpp_host = cpp_host_leg(B, nom_pack, jp, packs, max(K, 50), Wm, local_rank)
         e2e_kin = e2e_kinematics_leg(bat, L, B, world, rank, local_rank, stream, dev, K, Wm)
         gather = gather_leg(mpc, B, world, dev, stream, h_out, h_status)
         long_h = long_horizon_leg(bat, lib, d_packs, nom_pack, jp, phase0, B, local_rank, stream, flush, world, dev, args.solver)
@@ -413,7 +415,7 @@ def run_ours(args):
                                   "qp_fallback_kernel"] if args.solver == 0 else 2,
         "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "single_solve_latency": latency, "closed_loop": closed,
-        "e2e_kinematics": e2e_kin, "monte_carlo": monte, "param_sweep": sweep, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
+        "e2e_kinematics": e2e_kin, "e2e_cpp_host": cpp_host, "monte_carlo": monte, "param_sweep": sweep, "long_horizon": finish_long_horizon(long_h, tf.value), "gather": gather,
         "solved_fraction": solved_frac, "wall_ms_timed_loop": t_wall * 1e3,
     }
     print(json.dumps(line))
@@ -565,6 +567,46 @@ def finish_long_horizon(rows, peak_tflops):
         r["roofline_frac"] = ach / peak_tflops if peak_tflops > 0 else None
     return {"scaling": "weak", "variants": rows,
             "what": "configs[3]: qp_condensed_wide_kernel, same synthetic packs as the main leg, L2 flushed between steps"}
+
+
+def cpp_host_leg(B, nom_state_pack, jp_rows, packs, K, Wm, device):
+    """north_star (a), the C++ host layer end to end: examples/cpp_host_bench.cpp packs the per-instance records of every tick
+    (array of structures) into the page-locked SoA buffer (vsmpc::PackBatch::setMany), uploads, solves and reads the rows back,
+    two ticks in flight — the same C-ABI calls as the e2e leg, with the AoS -> SoA pack INSIDE the timed region.  Runs the
+    compiled example as a child process on this rank's device; rank 0 only."""
+    import tempfile
+    exe = os.path.join(ROOT, "examples", "bin", "cpp_host_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "examples/bin/cpp_host_bench not built"}
+    d = np.load(os.path.join(ROOT, "tests", "golden", "trajectories.npz"))
+    pk = pkg("pack")
+    # joint positions of every instance (all joints): only the controlled ones matter, take them from the configure rows
+    nj = 23
+    jpos = np.zeros((B, nj))
+    jpos[:, list(pk.DEFAULT_JOINT_SELECTOR)] = jp_rows.T
+    blob = np.concatenate([
+        [d["alphaGravity"].size, d["positionCoM"].shape[1], len(packs), nj, B],
+        d["alphaGravity"].ravel(), d["positionCoM"].T.ravel(), d["velocityCoM"].T.ravel(), d["RPY"].T.ravel(),
+        d["RPYDot"].T.ravel(), np.array(list(pk.DEFAULT_JOINT_SELECTOR), dtype=np.float64), jpos.ravel(),
+        nom_state_pack.T.ravel()] + [p.T.ravel() for p in packs]).astype(np.float64)          # instance-major records
+    path = tempfile.mktemp(prefix="vsmpc_cpp_host_", suffix=".bin")
+    blob.tofile(path)
+    threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+    try:
+        res = subprocess.run([exe, path, str(K), str(max(Wm, 3)), str(threads), str(device)], capture_output=True, text=True, timeout=120)
+        if res.returncode != 0:
+            return {"unavailable": "cpp_host_bench rc %d: %s" % (res.returncode, res.stderr.strip()[-200:])}
+        out = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:      # noqa: BLE001 - a bench leg must not take the line down
+        return {"unavailable": "cpp_host_bench: %s" % e}
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    out["what"] = ("C++ host (include/vsmpc_adapter.hpp): per tick PackBatch::setMany of B per-instance records into page-locked SoA "
+                   "+ vsmpc_set_state + vsmpc_solve_async + vsmpc_get_output_async, two ticks in flight; pack inside the timed region")
+    return out
 
 
 def monte_carlo_leg(bat, n_total, ticks, rank, world, device, stream, dev, joint_boxes=False):

@@ -179,6 +179,12 @@ int vsmpc_set_warm_start(vsmpc_handle* h, int enable);
 /* tests: overwrite the stored working sets, signed char[B][4 * throttle blocks] (+1 upper bound, -1 lower bound, 0 free) */
 int vsmpc_debug_set_working_set(vsmpc_handle* h, const signed char* working_set_host);
 
+/* Page-locked host memory (cudaHostAlloc) for the SoA buffers a caller hands to vsmpc_set_state / vsmpc_get_output_async, so that
+ * a host program that does not link the CUDA runtime itself (include/vsmpc_adapter.hpp: vsmpc::PackBatch) gets copies that are
+ * asynchronous and run at the full PCIe rate.  Not tied to a handle; free with vsmpc_host_free. */
+int vsmpc_host_alloc(size_t bytes, void** out);
+int vsmpc_host_free(void* p);
+
 /* IMPCProblem::update (IMPCProblem.cpp:150-194): copy the pack H2D and run the linearise kernel.
  * Asynchronous: the call returns once the copy and the kernel are ENQUEUED (copy on the handle's own copy stream into one of
  * two staging buffers, so that it overlaps the QP kernel of the tick before).  From pinned host memory the copy itself is

@@ -63,11 +63,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def build_examples(force: bool = False) -> str:
     """C++ host examples over include/vsmpc_adapter.hpp (g++ only; link libvsmpc.so by relative rpath): the single-instance
-    controller loop and the one-process multi-GPU batch.  Returns the path of the first."""
+    controller loop, the one-process multi-GPU batch and the end-to-end bench of the C++ host layer (pack + upload + solve).  Returns the path of the first."""
     out_dir = os.path.join(ROOT, "examples", "bin")
     os.makedirs(out_dir, exist_ok=True)
     exes = []
-    for name in ("cpp_controller", "cpp_multi_gpu"):
+    for name in ("cpp_controller", "cpp_multi_gpu", "cpp_host_bench"):
         src = os.path.join(ROOT, "examples", name + ".cpp")
         exe = os.path.join(out_dir, name)
         exes.append(exe)
@@ -75,7 +75,7 @@ def build_examples(force: bool = False) -> str:
         if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
             continue
         cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), src,
-               "-L", HERE, "-lvsmpc", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE), "-o", exe]
+               "-L", HERE, "-lvsmpc", "-pthread", "-Wl,-rpath,$ORIGIN/../../" + os.path.basename(HERE), "-o", exe]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)

@@ -64,6 +64,7 @@ class VsmpcPlantModel(C.Structure):
 
 
 EXPORTS = [
+    "vsmpc_host_alloc", "vsmpc_host_free",
     "vsmpc_create", "vsmpc_destroy", "vsmpc_last_error", "vsmpc_set_stream", "vsmpc_n_var",
     "vsmpc_n_constraints", "vsmpc_n_instances", "vsmpc_configure", "vsmpc_set_state",
     "vsmpc_set_state_device", "vsmpc_solve", "vsmpc_solve_async", "vsmpc_wait", "vsmpc_get_output",

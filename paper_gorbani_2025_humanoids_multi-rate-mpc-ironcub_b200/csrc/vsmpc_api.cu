@@ -763,6 +763,19 @@ int vsmpc_set_joint_limits(vsmpc_handle* h, const double* q_min_host, const doub
     return VSMPC_OK;
 }
 
+int vsmpc_host_alloc(size_t bytes, void** out)
+{
+    if (!out || bytes == 0)
+        return VSMPC_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? VSMPC_OK : VSMPC_ERR_CUDA;
+}
+
+int vsmpc_host_free(void* p)
+{
+    return (!p || cudaFreeHost(p) == cudaSuccess) ? VSMPC_OK : VSMPC_ERR_CUDA;
+}
+
 int vsmpc_set_warm_start(vsmpc_handle* h, int enable)
 {
     if (!h || h->B <= 0)

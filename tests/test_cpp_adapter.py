@@ -154,3 +154,26 @@ def test_python_multi_handle_matches_single(tmp_path):
             assert np.array_equal(o1, o2) and np.array_equal(s1, s2) and (s1 == 0).all()
             assert np.array_equal(one.getSolution(), multi.getSolution())
         one.close(); multi.close()
+
+
+def test_pack_batch_blocked_scatter_equals_one_instance_at_a_time():
+    """vsmpc::PackBatch::setMany (eight instances per cache line, several host threads, ranges off the 64-byte boundary) writes
+    the same SoA as PackBatch::set — examples/cpp_host_bench --selftest, no GPU needed."""
+    pkg("_build").build_examples()
+    res = subprocess.run([os.path.join(ROOT, "examples", "bin", "cpp_host_bench"), "--selftest"], capture_output=True, text=True)
+    assert res.returncode == 0 and "selftest ok" in res.stdout, (res.returncode, res.stdout, res.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_host_bench_runs_and_solves(tmp_path):
+    """examples/cpp_host_bench.cpp: pack + upload + solve + read-back pipelined from C++ (page-locked PackBatch, two ticks in
+    flight); every instance solved, and the pack is timed inside the loop."""
+    import json
+    pkg("_build").build_examples()
+    exe = os.path.join(ROOT, "examples", "bin", "cpp_host_bench")
+    fin, nom, packs, sel = _batch_inputs(tmp_path, 300, 3)
+    res = subprocess.run([exe, fin, "12", "3", "2", "0"], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stderr)
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["instances"] == 300 and out["steps"] == 12 and out["pinned"] is True
+    assert out["solved_fraction_last_step"] == 1.0 and out["value"] > 0 and 0 < out["pack_ms_per_step"] < out["ms_per_step"]
