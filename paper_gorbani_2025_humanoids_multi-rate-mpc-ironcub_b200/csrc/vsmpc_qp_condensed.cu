@@ -18,6 +18,9 @@
 // * one forward pass with the stored gains K_k (8 x 26) and F_k (8 x 32) produces the outputs.
 // Compared with vsmpc_qp_structured.cu (one warp, 38-dim augmented state, one Riccati back-solve per active
 // bound) the serial depth drops from (1 + n_s) x 34 knot steps to 17 + 17.
+// * optional joint-limit rows (JointPositionConstraint, constraintsVSMPC.cpp:388-468; JL build): a working set on the boxes of
+//   the joint increments is carried through the eliminations (CdClamp in vsmpc_condensed_core.cuh) and a pass loop around
+//   the solve re-factorises until the forward pass confirms it (ClampedCondensedQP in tools/condensed_model.py).
 #include <cstdlib>
 
 #include "vsmpc_condensed_core.cuh"

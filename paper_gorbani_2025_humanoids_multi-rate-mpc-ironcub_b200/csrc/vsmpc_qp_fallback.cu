@@ -20,6 +20,9 @@
 // with one warp per right-hand side, then the SAME Goldfarb-Idnani dual active set as the condensed kernels on
 // T = (K^-1)_vv (= the fully exchanged principal pivot transform of the reduced throttle Hessian) and
 // z = z_unc - sum_a s_a lam_a K^-1 e_a.
+// With the optional joint-limit rows the boxes of the joint increments join the throttle boxes in that active set: this kernel is
+// the net behind the condensed kernels' own working set on the joint boxes when it does not settle (vsmpc_qp_condensed.cu, JL
+// builds), and the only carrier of the rows where the long-horizon kernel has no JL build.
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
