@@ -1049,9 +1049,14 @@ qp_condensed_body(const DeviceConfig& cfgv, int B, const double* __restrict__ qd
 #define CD_KERNEL_PASS cfgv, B, qd_all, ws_all, z_all, st, out_rows, status, n_factor, n_solve, n_pivot, ws_stride, want_z, fb_list, fb_count, fb_mode, out2, status2, jlset
 // large batches: eight CTAs per SM, 128 registers
 __global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel(CD_KERNEL_ARGS) { qp_condensed_body<false, false>(CD_KERNEL_PASS); }
+// (a 168-register build with six CTAs per SM for many-wave batches was tried for this body as well: 2.42 ms against 2.39 ms at
+// B = 16 384, ahead only where the wave count favours it — profiles/r02_k2_experiments.md; the JL build below, whose 128-register
+// form spills more, does gain from it)
 // handles with joint-limit rows (vsmpc_config.use_joint_limits): the same lock-step body with the working set of the joint boxes
-// carried through the elimination (CdClamp) and a pass loop around the solve; any batch size
-__global__ void __launch_bounds__(CD_THREADS, 8) qp_condensed_kernel_jl(CD_KERNEL_ARGS) { qp_condensed_body<false, true>(CD_KERNEL_PASS); }
+// carried through the elimination (CdClamp) and a pass loop around the solve; any batch size.  168 registers, six CTAs per SM:
+// 3.57 M against 3.21 M closed-loop solves/s in the parameter sweep at 2048 instances, 4.50 M against 3.75 M at 16 384, compared
+// with the 128-register build (profiles/r02bo_time_jl.txt)
+__global__ void __launch_bounds__(CD_THREADS, 6) qp_condensed_kernel_jl(CD_KERNEL_ARGS) { qp_condensed_body<false, true>(CD_KERNEL_PASS); }
 // (a 144-register build for the one wave of seven CTAs per SM at B = 1024 was tried: 207 us instead of 165 — the register file
 // is split over the four sub-partitions, 14 warps put four on two of them and four warps of 144 registers do not fit 16 384,
 // so the SM holds six CTAs and the launch takes two waves; 128 registers is the cap for anything above twelve warps per SM)
