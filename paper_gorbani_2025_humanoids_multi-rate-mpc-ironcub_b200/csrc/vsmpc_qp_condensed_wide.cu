@@ -59,6 +59,8 @@ template <bool JL> struct alignas(16) CwSmemT : CwJlSmem<JL>
     int flags[4];
 };
 
+constexpr int CW_ALIAS_DOUBLES = (2 * (int)sizeof(CdSlot) + NX * LDM * (int)sizeof(double)) / (int)sizeof(double);   // slot[2] + Mt
+
 struct CwLayout
 {
     int G, ldc;                 // column warps, columns carried (32 G)
@@ -92,7 +94,16 @@ __host__ __device__ inline CwLayout cw_layout(const DeviceConfig& cfg)
     L.theta = o;  o += L.ldc;
     L.vv = o;     o += L.nv;
     L.grad = o;   o += L.nv;
-    L.stk = o;    o += 2 * CW_MD * L.nvs;   // deferred pivots: A [8][nvs] then B [8][nvs]
+    // deferred pivots: A [8][nvs] then B [8][nvs].  They are used only after the recursion, when the mailbox slots and the
+    // transposition buffer of the static part are free: up to 29 throttle blocks the stacks live THERE (stk = -1) — at 3x the
+    // reference knot count that takes the CTA from 118 KB to 105 KB, i.e. from one CTA per SM to two
+    if (2 * CW_MD * L.nvs <= CW_ALIAS_DOUBLES)
+        L.stk = -1;
+    else
+    {
+        L.stk = o;
+        o += 2 * CW_MD * L.nvs;
+    }
     L.xref = o;   o += 12 * cfg.NC;
     L.rb = o;     o += 4 * 8;      // two block-reduction buffers: value [8], index [8] each
     L.actg = o;   o += (L.nvp + 1) / 2 + 2;   // working-set guess, int [nvp]; then two doubles broadcast by the dropping thread
@@ -454,7 +465,8 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
     double* theta = dyn + L.theta;
     double* vv = dyn + L.vv;
     double* grad = dyn + L.grad;
-    const CwPiv P{Om, dyn + L.stk, dyn + L.stk + CW_MD * L.nvs, L.ldo, L.nvs, 0, L.nv, L.nvp};
+    double* stkp = L.stk < 0 ? reinterpret_cast<double*>(&sm.slot[0]) : dyn + L.stk;
+    const CwPiv P{Om, stkp, stkp + CW_MD * L.nvs, L.ldo, L.nvs, 0, L.nv, L.nvp};
     double* xref = dyn + L.xref;
     double* rbA = dyn + L.rb;
     double* rbB = dyn + L.rb + 16;
@@ -669,6 +681,13 @@ qp_condensed_wide_kernel(const __grid_constant__ DeviceConfig cfgv, int B, const
 #endif
     if (warp == 0 && lane == 0)
         sm.flags[0] = ok ? 0 : 1;
+    if (L.stk < 0)
+    {
+        // the deferred-pivot stacks share the mailbox slots / transposition buffer (cw_layout): the recursion is over (the
+        // __syncthreads that closed its last knot), they start empty; the barrier after the Om down-date publishes the zeros
+        for (int e = threadIdx.x; e < 2 * CW_MD * L.nvs; e += nthr)
+            P.As[e] = 0.0;
+    }
     // Psi_0' x0 while the column warps still hold their columns
     double g_psi = 0.0;
     if (warp >= 1 && gc < nv)
@@ -1115,7 +1134,7 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
                                      int* n_pivot, int want_z, int* fb_list, int* fb_count, int fb_mode, signed char* wset,
                                      int warm, double* out2, int* status2, unsigned* jlset, cudaStream_t s)
 {
-    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {}, attr_d[64] = {};
+    static bool attr_a[64] = {}, attr_b[64] = {}, attr_c[64] = {}, attr_d[64] = {}, attr_g[64] = {};
     const CwLayout L = cw_layout(h_cfg);
     const bool jlb = cw_jl_build(h_cfg);
     const size_t smem = cw_smem_bytes(h_cfg, jlb);
@@ -1142,6 +1161,15 @@ cudaError_t launch_qp_condensed_wide(const DeviceConfig& h_cfg, int B, const dou
         if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<128, 2, false>, CW_SMEM_LIMIT, attr_b)) != cudaSuccess)
             return e;
         qp_condensed_wide_kernel<128, 2, false><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
+                                                                               n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, nullptr);
+    }
+    else if (L.G == 4 && 2 * (smem + 1024) <= (size_t)CW_SMEM_LIMIT + 1024)
+    {
+        // four column warps and a CTA small enough for two per SM (3x the reference knot count, with the deferred-pivot stacks
+        // in the static part): five warps per CTA, 168 registers (launch bounds of 192 threads: 65 536 / 384), no idle warps
+        if ((e = ensure_dynamic_smem(qp_condensed_wide_kernel<192, 2, false>, CW_SMEM_LIMIT, attr_g)) != cudaSuccess)
+            return e;
+        qp_condensed_wide_kernel<192, 2, false><<<B, 32 * (1 + L.G), smem, s>>>(h_cfg, B, qd, ws, z, st, out_rows, status,
                                                                                n_factor, n_solve, n_pivot, wsd, want_z, fb_list, fb_count, fbm, wset, warm, out2, status2, nullptr);
     }
     else
